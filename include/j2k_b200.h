@@ -1,0 +1,289 @@
+/*
+ * j2k_b200.h — C ABI of the B200-native JPEG 2000 sample-domain path.
+ *
+ * This is the drop-in boundary for go-dicom-codec's data-parallel hot path
+ * (DC level shift, RCT / ICT / Part-2 custom MCT, multi-level 5/3 and 9/7
+ * lifting DWT in both directions, scalar quantization / dequantization).
+ * T1 (EBCOT/MQ), T2, HTJ2K block coding and codestream parsing stay in Go.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers and sizes, and names
+ * the reference code it replaces as `path:line` relative to the reference
+ * repository root (github.com/cocosip/go-dicom-codecs).  The cgo binding a
+ * maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - return 0 on success, a negative j2k_status on failure; the message is
+ *     available through j2k_last_error() (per calling thread).  Nothing ever
+ *     falls back to a CPU implementation: without a usable CUDA device every
+ *     compute entry point fails with J2K_ERR_CUDA.
+ *   - all host buffers are caller-owned; no pointer is retained after return
+ *     (cgo rule).  Buffers from j2k_acquire_buffer() are library-owned pinned
+ *     memory and may be used for zero-staging transfers.
+ *   - every entry point selects its CUDA device itself (goroutines migrate
+ *     between OS threads across cgo calls); a context is thread-safe.
+ *
+ * Buffer layouts
+ *   pixels : DICOM native frame, component-interleaved samples, 1 byte when
+ *            bit_depth <= 8 else 2 bytes little-endian
+ *            (jpeg2000/encoder.go:357-380, jpeg2000/decoder.go:857-859,938-940).
+ *   coeffs : for each tile in raster order (jpeg2000/encoder.go:1966-1983), for
+ *            each component, one row-major int32[th][tw] plane in Mallat layout
+ *            (LL_L top-left; per resolution HL right, LH below, HH diagonal;
+ *            rectangles as jpeg2000/encoder.go:2352-2389, jpeg2000/t2/geometry.go:53-92),
+ *            row stride = tile width.  This is exactly the `tileData [][]int32`
+ *            that buildTilePacketEncoder consumes (jpeg2000/encoder.go:2391) and
+ *            the `comp.coefficients` that applyIDWT consumes
+ *            (jpeg2000/t2/tile_decoder.go:886).
+ */
+#ifndef J2K_B200_H
+#define J2K_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define J2K_B200_ABI_VERSION 1
+
+#define J2K_MAX_COMPONENTS 4   /* jpeg2000/encoder.go:298 (1..4 components) */
+#define J2K_MAX_LEVELS 10      /* API caps at 6 (encoder.go:306); the wavelet package and norm tables reach deeper (quantization.go:17-22) */
+#define J2K_MAX_BANDS (3 * J2K_MAX_LEVELS + 1)
+#define J2K_MAX_BINDINGS 4
+
+typedef enum j2k_status {
+    J2K_OK = 0,
+    J2K_ERR_INVALID_ARG = -1, /* parameter validation failed (encoder.go:291-339) */
+    J2K_ERR_SIZE = -2,        /* buffer too small ("insufficient pixel data", encoder.go:346-348) */
+    J2K_ERR_CUDA = -3,        /* CUDA runtime / driver failure, or no device */
+    J2K_ERR_NOMEM = -4,
+    J2K_ERR_UNSUPPORTED = -5,
+    J2K_ERR_TICKET = -6
+} j2k_status;
+
+/* Multi-component transform selector.
+ * encode: Encoder.Encode dispatch, jpeg2000/encoder.go:196-209
+ * decode: Decoder.applyInverseTransforms, jpeg2000/decoder.go:620-628 */
+typedef enum j2k_mct_mode {
+    J2K_MCT_NONE = 0,
+    J2K_MCT_RCT = 1,          /* colorspace/rct.go:6-21 (3 components, reversible) */
+    J2K_MCT_ICT = 2,          /* encode: float32 ICT encoder.go:277-288; decode: float64 ICT colorspace/ict.go:16-21 */
+    J2K_MCT_CUSTOM_INT = 3,   /* encode: integer matrix, int64 accumulate, encoder.go:489-505 */
+    J2K_MCT_CUSTOM_Q13 = 4,   /* encode: Q13 fixed point, encoder.go:506-523,662-665 */
+    J2K_MCT_CUSTOM_FLOAT = 5, /* decode: float64 matrix + math.Round, decoder.go:696-723 */
+    J2K_MCT_BINDINGS = 6      /* Part-2 binding list, encoder.go:527-660 / decoder.go:630-694 */
+} j2k_mct_mode;
+
+/* One Part-2 binding; mirrors MCTBindingParams (jpeg2000/encoder.go:111-121,
+ * built by MCTBindingBuilder jpeg2000/mct_builder.go:4-29) on encode and the
+ * decoder's mctBinding (jpeg2000/decoder.go:630-694) on decode. */
+typedef struct j2k_mct_binding {
+    int32_t n_components;                      /* len(ComponentIDs); 0 = all components in order (encoder.go:562-568) */
+    int32_t component_ids[J2K_MAX_COMPONENTS];
+    int32_t element_type;                      /* encode: 0 = integer matrix else Q13 (encoder.go:554-558); decode: 0 = integer (reversible) else float64 (decoder.go:636-641) */
+    int32_t has_matrix;                        /* 0 = identity (encoder.go:596-608); decode: 0 = skip the matrix */
+    double matrix[J2K_MAX_COMPONENTS * J2K_MAX_COMPONENTS]; /* row-major n x n */
+    int32_t has_offsets;                       /* encode subtracts before (encoder.go:582-594), decode adds after (decoder.go:683-694) */
+    int32_t offsets[J2K_MAX_COMPONENTS];
+} j2k_mct_binding;
+
+/* Forward (encode-side) parameters: each field mirrors something the Go path reads. */
+typedef struct j2k_fwd_params {
+    int32_t width, height;       /* EncodeParams.Width/Height        encoder.go:19-20 */
+    int32_t components;          /* EncodeParams.Components          encoder.go:21 */
+    int32_t bit_depth;           /* EncodeParams.BitDepth (1..16)    encoder.go:22 */
+    int32_t is_signed;           /* EncodeParams.IsSigned            encoder.go:23 */
+    int32_t tile_width;          /* 0 = whole image                  encoder.go:26,1990-1997 */
+    int32_t tile_height;
+    int32_t num_levels;          /* EncodeParams.NumLevels           encoder.go:30 (this ABI accepts up to J2K_MAX_LEVELS) */
+    int32_t reversible;          /* EncodeParams.Lossless: 1 = 5/3, 0 = 9/7  encoder.go:31 */
+    int32_t htj2k;               /* EncodeParams.HTJ2KMode: quant scale 1 instead of 64, no <<6  encoder.go:97,2312-2315,3294 */
+    int32_t mct_mode;            /* j2k_mct_mode */
+    double mct_matrix[J2K_MAX_COMPONENTS * J2K_MAX_COMPONENTS]; /* MCTMatrix, row-major C x C (custom modes) encoder.go:76 */
+    int32_t mct_has_offsets;     /* MCTOffsets present and len == components  encoder.go:481 */
+    int32_t mct_offsets[J2K_MAX_COMPONENTS];
+    int32_t n_bindings;          /* MCTBindings, already in application order (encoder.go:532-537) */
+    j2k_mct_binding bindings[J2K_MAX_BINDINGS];
+    int32_t n_steps;             /* 9/7 only: 3*num_levels+1 runtime steps in QCD order, or 0 = plain rounding (encoder.go:2266-2273) */
+    double steps[J2K_MAX_BANDS]; /* OpenJPEGRuntimeQuantizationSteps(...) values (quantization.go:140-154); <= 0 = plain rounding for that band (encoder.go:2320-2321) */
+    int32_t fuse_t1_shift;       /* 1 = also apply the classic-EBCOT `<<6` of encodeCodeBlock (encoder.go:3294-3300); only meaningful when reversible && !htj2k */
+    int32_t reserved[7];
+} j2k_fwd_params;
+
+/* Inverse (decode-side) parameters. */
+typedef struct j2k_inv_params {
+    /* SIZ geometry (jpeg2000/tile_assembler.go:33-56, jpeg2000/t2/tile_decoder.go:269-294) */
+    int32_t xsiz, ysiz, xosiz, yosiz, xtsiz, ytsiz, xtosiz, ytosiz;
+    int32_t components;          /* Csiz; XRsiz = YRsiz = 1 is the only supported sampling (tile_assembler.go:152-159) */
+    int32_t bit_depth;           /* component 0 precision  decoder.go:143-144 */
+    int32_t is_signed;
+    int32_t num_levels;          /* COD NumberOfDecompositionLevels  t2/tile_decoder.go:352 */
+    int32_t reversible;          /* COD Transformation: 1 = 5/3, 0 = 9/7  t2/tile_decoder.go:893-916 */
+    int32_t htj2k;               /* COD code-block style bit 0x40  decoder.go:588; dequant by step instead of 0.5*step  t2/tile_decoder.go:974-977 */
+    int32_t n_steps;             /* 9/7 only: number of decoded steps (<= 3L+1; bands beyond it are only converted, t2/tile_decoder.go:1022-1028); 0 = QCD style 0 (no dequantization, :909-911) */
+    double steps[J2K_MAX_BANDS]; /* decodeQuantizationSteps(...) values WITHOUT the 0.5 factor (t2/tile_decoder.go:995-1046); <= 0 = band left unscaled (:971-973) */
+    int32_t mct_mode;            /* NONE / RCT / ICT / CUSTOM_FLOAT / BINDINGS */
+    double mct_matrix[J2K_MAX_COMPONENTS * J2K_MAX_COMPONENTS]; /* mctInverse, row-major C x C  decoder.go:696-711 */
+    int32_t mct_has_offsets;
+    int32_t mct_offsets[J2K_MAX_COMPONENTS];   /* added after the matrix  decoder.go:712-722 */
+    int32_t n_bindings;
+    j2k_mct_binding bindings[J2K_MAX_BINDINGS];
+    int32_t fuse_t1_halve;       /* 1 = also apply the truncating `/2` of normalizeOpenJPEGReversibleT1Coefficients (t2/tile_decoder.go:989-993); only meaningful when reversible && !htj2k */
+    int32_t reserved[7];
+} j2k_inv_params;
+
+/* CUDA-event timing of the most recent synchronous call on this context (milliseconds). */
+typedef struct j2k_timing {
+    float h2d_ms;
+    float kernel_ms;
+    float d2h_ms;
+    float total_ms;
+    int32_t kernel_launches;     /* kernels launched by that call */
+    int32_t reserved;
+} j2k_timing;
+
+typedef struct j2k_ctx j2k_ctx;
+
+/* ---------------------------------------------------------------- lifetime */
+
+/* Create a context over `n_devices` CUDA devices (`devices == NULL` -> device 0..n-1,
+ * n_devices == 0 -> the device named by env J2K_B200_DEVICE, default 0).
+ * Replaces nothing in the reference (it has no device); called once from the
+ * shim's init(), next to RegisterJPEG2000LosslessCodec (jpeg2000/lossless/codec.go:306-322). */
+int j2k_init(j2k_ctx** ctx, const int* devices, int n_devices);
+void j2k_shutdown(j2k_ctx* ctx);
+/* Message of the last failure on the calling thread (never NULL). */
+const char* j2k_last_error(j2k_ctx* ctx);
+int j2k_abi_version(void);
+int j2k_device_count(const j2k_ctx* ctx);
+/* Total number of CUDA kernels this context has launched (bench.py's gpu_launches). */
+int64_t j2k_launch_count(const j2k_ctx* ctx);
+int j2k_last_timing(j2k_ctx* ctx, j2k_timing* out);
+
+/* Library-owned pinned host memory (Go wraps it with unsafe.Slice). */
+void* j2k_acquire_buffer(j2k_ctx* ctx, size_t nbytes);
+void j2k_release_buffer(j2k_ctx* ctx, void* p);
+
+/* ------------------------------------------------------------------- sizes */
+
+/* expectedBytes of convertPixelData (jpeg2000/encoder.go:344). */
+size_t j2k_fwd_pixel_bytes(const j2k_fwd_params* p);
+/* width*height*components int32 values (all tiles, all components). */
+size_t j2k_fwd_coeff_count(const j2k_fwd_params* p);
+size_t j2k_inv_pixel_bytes(const j2k_inv_params* p);
+size_t j2k_inv_coeff_count(const j2k_inv_params* p);
+/* Tile grid of the encoder (jpeg2000/encoder.go:1966-1997) / decoder (tile_assembler.go:33-101):
+ * writes x0,y0,x1,y1 (image-local, exclusive) of tile `idx`; returns the tile count. */
+int j2k_fwd_tile_bounds(const j2k_fwd_params* p, int idx, int32_t bounds[4]);
+int j2k_inv_tile_bounds(const j2k_inv_params* p, int idx, int32_t bounds[4]);
+
+/* ----------------------------------------------------------------- forward */
+
+/* Replaces, for one frame: Encoder.Encode's sample-domain head
+ * (convertPixelData, applyDCLevelShift, MCT dispatch: jpeg2000/encoder.go:187-209,341-383,3698-3711)
+ * plus, for every tile, Encoder.transformTile (jpeg2000/encoder.go:2213-2237) =
+ * applyWaveletTransform / applyIrreversibleWaveletTransform / applyQuantizationBySubbandFloat
+ * (:2187-2329).  `coeffs_out` receives what writeTile (:2099) hands to buildTilePacketEncoder. */
+int j2k_forward(j2k_ctx* ctx, const j2k_fwd_params* p, const void* pixels, size_t nbytes,
+                int32_t* coeffs_out, size_t ncoeffs);
+
+/* Planar twin for Encoder.EncodeComponents([][]int32) (jpeg2000/encoder.go:221-273): skips convertPixelData. */
+int j2k_forward_planar(j2k_ctx* ctx, const j2k_fwd_params* p, const int32_t* const* planes,
+                       int32_t* coeffs_out, size_t ncoeffs);
+
+/* Batched frames sharing one parameter set: the frame loops of the codec adapters
+ * (jpeg2000/lossless/codec.go:246-261, jpeg2000/lossy/codec.go:149-176).  Frames are
+ * contiguous: frame f at pixels + f*frame_stride_bytes, result at coeffs_out + f*coeff_count.
+ * Frames are sharded over the context's devices in contiguous blocks; no collective. */
+int j2k_forward_batch(j2k_ctx* ctx, const j2k_fwd_params* p, int nframes, const void* pixels,
+                      size_t frame_stride_bytes, int32_t* coeffs_out);
+
+/* Device-resident form: d_pixels / d_coeffs are device pointers on device index
+ * `dev` of the context, work is enqueued on `cuda_stream` (a cudaStream_t, NULL = the
+ * context's compute stream) and NOT synchronised. */
+int j2k_forward_device(j2k_ctx* ctx, int dev, const j2k_fwd_params* p, int nframes,
+                       const void* d_pixels, size_t frame_stride_bytes, int32_t* d_coeffs,
+                       void* cuda_stream);
+
+/* ----------------------------------------------------------------- inverse */
+
+/* Replaces, for one frame: TileDecoder.applyIDWT for every tile-component
+ * (jpeg2000/t2/tile_decoder.go:886-919 incl. applyDequantizationBySubbandFloat :925-987),
+ * TileAssembler.AssembleTile (jpeg2000/tile_assembler.go:138-178),
+ * Decoder.applyInverseTransforms + applyInverseDCLevelShift (jpeg2000/decoder.go:540-542,620-735,948-962)
+ * and Decoder.GetPixelData (jpeg2000/decoder.go:777-944).
+ * `planes_out` (optional, may be NULL) receives Decoder.GetImageData()
+ * (jpeg2000/decoder.go:738-740): `components` planes of int32[H*W], unclamped. */
+int j2k_inverse(j2k_ctx* ctx, const j2k_inv_params* p, const int32_t* coeffs_in, size_t ncoeffs,
+                void* pixels_out, size_t nbytes, int32_t* planes_out);
+
+int j2k_inverse_batch(j2k_ctx* ctx, const j2k_inv_params* p, int nframes, const int32_t* coeffs_in,
+                      void* pixels_out, size_t frame_stride_bytes, int32_t* planes_out);
+
+int j2k_inverse_device(j2k_ctx* ctx, int dev, const j2k_inv_params* p, int nframes,
+                       const int32_t* d_coeffs, void* d_pixels, size_t frame_stride_bytes,
+                       int32_t* d_planes, void* cuda_stream);
+
+/* ------------------------------------------------------------ asynchronous */
+
+/* Ticketed forms of the batch calls.  Buffers MUST come from j2k_acquire_buffer()
+ * and stay untouched until j2k_wait() returns.  This is what lets the Go frame
+ * loop run T1/T2 of frame i while the GPUs transform frames i+1... */
+int64_t j2k_submit_forward(j2k_ctx* ctx, const j2k_fwd_params* p, int nframes, const void* pixels,
+                           size_t frame_stride_bytes, int32_t* coeffs_out);
+int64_t j2k_submit_inverse(j2k_ctx* ctx, const j2k_inv_params* p, int nframes, const int32_t* coeffs_in,
+                           void* pixels_out, size_t frame_stride_bytes, int32_t* planes_out);
+int j2k_wait(j2k_ctx* ctx, int64_t ticket);
+
+/* -------------------------------------------- wavelet package API (in place) */
+
+/* wavelet.ForwardMultilevelWithParity / InverseMultilevelWithParity
+ * (jpeg2000/wavelet/dwt53.go:365-394,404-434): int32 plane, stride = width. */
+int j2k_dwt53_forward(j2k_ctx* ctx, int32_t* data, int width, int height, int levels, int x0, int y0);
+int j2k_dwt53_inverse(j2k_ctx* ctx, int32_t* data, int width, int height, int levels, int x0, int y0);
+/* wavelet.ForwardMultilevel97Float32WithParity / InverseMultilevel97OpenJPEGWithParity
+ * (jpeg2000/wavelet/dwt97.go:388-407,425-451): float32 plane, stride = width. */
+int j2k_dwt97_forward(j2k_ctx* ctx, float* data, int width, int height, int levels, int x0, int y0);
+int j2k_dwt97_inverse(j2k_ctx* ctx, float* data, int width, int height, int levels, int x0, int y0);
+/* wavelet.ConvertFloat32ToInt32OpenJPEG (dwt97.go:473-503): round half to even. */
+int j2k_convert_f32_to_i32(j2k_ctx* ctx, const float* in, int32_t* out, size_t n);
+
+/* ----------------------------------------- colorspace package API (planar) */
+
+/* colorspace.ApplyRCTToComponents / ApplyInverseRCTToComponents (colorspace/rct.go:26-49). */
+int j2k_rct_forward(j2k_ctx* ctx, size_t n, const int32_t* r, const int32_t* g, const int32_t* b,
+                    int32_t* y, int32_t* cb, int32_t* cr);
+int j2k_rct_inverse(j2k_ctx* ctx, size_t n, const int32_t* y, const int32_t* cb, const int32_t* cr,
+                    int32_t* r, int32_t* g, int32_t* b);
+/* colorspace.ApplyICTToComponents / ApplyInverseICTToComponents (colorspace/ict.go:24-45): float64 + math.Round. */
+int j2k_ict_forward(j2k_ctx* ctx, size_t n, const int32_t* r, const int32_t* g, const int32_t* b,
+                    int32_t* y, int32_t* cb, int32_t* cr);
+int j2k_ict_inverse(j2k_ctx* ctx, size_t n, const int32_t* y, const int32_t* cb, const int32_t* cr,
+                    int32_t* r, int32_t* g, int32_t* b);
+
+/* -------------------------------------------------- quantization.go API */
+
+/* QuantizeCoefficients / DequantizeCoefficients (jpeg2000/quantization.go:310-340):
+ * RoundToEven(float64(c)/step), RoundToEven(float64(c)*step); step <= 0 copies. */
+int j2k_quantize_coefficients(j2k_ctx* ctx, const int32_t* in, int32_t* out, size_t n, double step);
+int j2k_dequantize_coefficients(j2k_ctx* ctx, const int32_t* in, int32_t* out, size_t n, double step);
+
+/* Scalar step-table metadata (no device work).  These stay in Go in a real
+ * integration; they are exported so that non-Go hosts
+ * (bench.py, the Python mirror) can build the same tables.
+ *   j2k_quant_openjpeg_params  = CalculateOpenJPEGQuantizationParams (quantization.go:212-236)
+ *   j2k_quant_quality_params   = CalculateQuantizationParams         (quantization.go:180-208)
+ *   j2k_quant_runtime_steps    = OpenJPEGRuntimeQuantizationSteps    (quantization.go:140-154)
+ *   j2k_quant_decode_steps     = TileDecoder.decodeQuantizationSteps, style 2 (t2/tile_decoder.go:1018-1043)
+ * `encoded`/`steps` hold 3*num_levels+1 entries.  Return the entry count or a negative status. */
+int j2k_quant_openjpeg_params(int num_levels, int bit_depth, uint16_t* encoded, double* step_sizes);
+int j2k_quant_quality_params(int quality, int num_levels, int bit_depth, uint16_t* encoded, double* step_sizes);
+int j2k_quant_runtime_steps(const uint16_t* encoded, int n, int num_levels, int bit_depth, double* steps);
+int j2k_quant_decode_steps(const uint16_t* encoded, int n, int num_levels, int bit_depth, int reversible,
+                           double* steps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* J2K_B200_H */
