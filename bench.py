@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""bench.py — J2K DWT+MCT+quant throughput on B200 (metric of BASELINE.json).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # CPU arm: the oracle port on the host cores
+
+A "step" is one pass of the forward hot path (unpack -> DC shift -> [MCT] -> multi-level DWT ->
+quantization) over one batch of synthetic frames that is already resident in HBM.  The workload at
+every N is BASELINE.json configs[1]: 4096x4096 12-bit mono DX frames, 9/7 irreversible, 6 levels,
+OpenJPEG default steps; each rank owns `--frames` frames (weak scaling, frames never exchange data,
+no collective on the data path).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "go-dicom-codec_b200"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+W, H, BITS, LEVELS = 4096, 4096, 12, 6
+PIX = W * H
+WORKLOAD = "C2: 4096x4096 12-bit mono DX frame, 9/7 irreversible 6-level DWT + quantization (forward)"
+
+
+def alg_bytes_per_frame(levels=LEVELS, s_in=2):
+    """B_fwd = S*(s_in+4) + 8*S*sum_{k=1}^{L-1} 4^-k."""
+    return PIX * (s_in + 4) + 8 * PIX * sum(4.0 ** -k for k in range(1, levels))
+
+
+def synth_frames(n, seed):
+    """Seeded 'smooth + noise' 12-bit frames, as little-endian u16 bytes [n, H*W*2]."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    base = 2 ** (BITS - 1) + 2 ** (BITS - 2) * np.sin(xx / 17.0) * np.cos(yy / 23.0)
+    out = np.empty((n, H * W * 2), np.uint8)
+    for f in range(n):
+        v = np.clip(np.rint(base + rng.normal(0, 2 ** BITS / 256, (H, W)).astype(np.float32)), 0, 2 ** BITS - 1)
+        out[f] = v.astype("<u2").reshape(-1).view(np.uint8)
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_leg(threads, frames, steps, warmup):
+    """Oracle port of the reference loops on the host cores; returns (Mpixel/s, ms/step)."""
+    import oracle_lib
+    from j2kb200 import abi
+    orc = oracle_lib.Oracle()
+    enc, _ = orc.openjpeg_quant_params(LEVELS, BITS)
+    fp = abi.fwd_params(W, H, 1, BITS, False, num_levels=LEVELS, reversible=False, steps=orc.runtime_quant_steps(enc, LEVELS, BITS))
+    data = synth_frames(frames, 4242)
+    out = np.empty((frames, PIX), np.int32)
+    for _ in range(warmup):
+        orc.forward_batch(fp, frames, data, data.strides[0], out, threads)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        orc.forward_batch(fp, frames, data, data.strides[0], out, threads)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return frames * PIX / dt / 1e6, dt * 1e3
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    frames = max(1, min(cores, 16))  # one frame per host thread ("goroutine-per-frame" upper bound), bounded sample
+    steps = min(args.steps, 5)
+    warm = min(args.warmup, 1)
+    val, ms = cpu_leg(cores, frames, steps, warm)
+    line = {
+        "impl": "reference", "metric": "J2K DWT+MCT+quant Mpixel/s", "value": val, "unit": "Mpixel/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "frames_per_step": frames, "direction": "forward"},
+        "cpu_baseline": {"value": val, "unit": "Mpixel/s", "cores": min(cores, frames), "kind": "port",
+                         "sample": f"{frames} C2 frames per step, one frame per thread, oracle C port of the Go loops "
+                                   f"(gcc -O2 -ffp-contract=off); the Go reference itself cannot run here (no Go toolchain)"},
+        "e2e": {"value": val, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--frames", type=int, default=8, help="C2 frames per rank per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import j2kb200
+    from j2kb200 import abi
+
+    rank, local_rank, world = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    use_dist = world > 1
+    if use_dist:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    warm = max(args.warmup, 3)
+    ctx = j2kb200.Context(devices=[local_rank])
+    enc, _ = j2kb200.openjpeg_quant_params(LEVELS, BITS)
+    steps_enc = j2kb200.runtime_quant_steps(enc, LEVELS, BITS)
+    fp = abi.fwd_params(W, H, 1, BITS, False, num_levels=LEVELS, reversible=False, steps=steps_enc)
+    B = args.frames
+    frame_bytes = PIX * 2
+    host = synth_frames(min(B, 2), 2 + rank)  # two distinct seeded frames tiled over the batch
+    d_in = torch.empty((B, frame_bytes), dtype=torch.uint8, device="cuda")
+    for f in range(B):
+        d_in[f].copy_(torch.from_numpy(host[f % host.shape[0]]))
+    d_out = torch.empty((B, PIX), dtype=torch.int32, device="cuda")
+    stream = torch.cuda.current_stream()
+
+    def step():
+        ctx.forward_device(fp, B, d_in.data_ptr(), frame_bytes, d_out.data_ptr(), stream=stream.cuda_stream)
+
+    def barrier():
+        if use_dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing (value)
+    for _ in range(warm):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    launches = ctx.launch_count - l0
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    t = torch.tensor([ms_total], device="cuda")
+    if use_dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = world * B * PIX / (ms_step * 1e-3) / 1e6
+
+    # ---- dominant kernel, timed live with CUDA events on the launching stream (roofline)
+    ctx.set_profiling(True)
+    lvl1 = []
+    per_level = {}
+    for _ in range(5):
+        step()
+        for lv, ms in ctx.get_profile():
+            per_level.setdefault(lv, []).append(ms)
+            if lv == 1:
+                lvl1.append(ms)
+    ctx.set_profiling(False)
+    peak, peak_src = measured_peak()
+    k_ms = statistics.mean(lvl1) if lvl1 else float("nan")
+    k_bytes = B * PIX * (2 + 4)  # level-1 launch: reads the u16 frame, writes LL1 (f32) + HL1/LH1/HH1 (int32)
+    achieved = k_bytes / (k_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            tj = json.load(open(tpath))
+            traffic = tj.get("fwd_level1_dram_bytes_per_frame", None)
+            if traffic is not None:
+                traffic = traffic * B
+        except Exception:
+            traffic = None
+    step_alg = B * alg_bytes_per_frame()
+    roofline = {
+        "bound": "hbm", "kernel": "fwd_level_kernel<97,NP=4,NC=1,u16> (level 1: unpack+DC shift+vertical+horizontal 9/7+quantize)",
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+        "peak_source": peak_src, "algorithmic_bytes_per_launch": k_bytes, "kernel_ms": k_ms,
+        "step_algorithmic_GBps": step_alg / (ms_step * 1e-3) / 1e9, "step_frac": step_alg / (ms_step * 1e-3) / 1e9 / peak,
+        "per_level_ms": {str(k): statistics.mean(v) for k, v in sorted(per_level.items())},
+    }
+
+    # ---- end to end through the C ABI with host buffers (pinned), copies inside the timed region
+    h_in = ctx.pinned(B * frame_bytes).reshape(B, frame_bytes)
+    h_out = ctx.pinned(B * PIX * 4, np.int32).reshape(B, PIX)
+    for f in range(B):
+        h_in[f] = host[f % host.shape[0]]
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        ctx.forward_batch(fp, h_in, h_out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.forward_batch(fp, h_in, h_out)
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], device="cuda")
+    if use_dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = world * B * PIX / (float(t.item()) / e2e_steps) / 1e6
+    # the e2e result must be the same coefficients as the resident run
+    same = bool(torch.equal(torch.from_numpy(np.asarray(h_out[0])).cuda(), d_out[0]))
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        v, ms = cpu_leg(1, 2, 5, 1)  # 2 frames x (1 warm-up + 5 steps) ~ 11 s of single-thread CPU work
+        cpu = {"value": v, "unit": "Mpixel/s", "cores": 1, "kind": "port",
+               "sample": "2 C2 frames per step, 5 steps, single thread (the reference is single-goroutine per call); "
+                         "oracle C port of the Go loops, gcc -O2 -ffp-contract=off; host has %d cores" % (os.cpu_count() or 1)}
+
+    if rank == 0:
+        line = {
+            "metric": "J2K DWT+MCT+quant Mpixel/s", "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
+            "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": B, "direction": "forward", "levels": LEVELS,
+                       "cache": "inputs larger than L2 (%.0f MB in + %.0f MB out per step per GPU)" % (B * frame_bytes / 1e6, B * PIX * 4 / 1e6),
+                       "parallelism": "frame-sharded, %d rank(s), no collective" % world},
+            "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_val, "unit": "Mpixel/s", "h2d_bytes_per_step": B * frame_bytes, "d2h_bytes_per_step": B * PIX * 4,
+                    "steps": e2e_steps, "matches_resident": same},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if use_dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

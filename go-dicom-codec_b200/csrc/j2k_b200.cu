@@ -1,0 +1,1548 @@
+// j2k_b200.cu — host side of libj2kb200.so: contexts, plans, launch logic and the C ABI of
+// include/j2k_b200.h.  No torch, no CPU fallback: every compute entry point needs a CUDA device.
+//
+// Data layout in HBM (per device):
+//   pixels  : caller frames, interleaved samples (u8 / u16 LE)
+//   coeffs  : caller coefficient planes, per frame [tile][component][th][tw] int32 (Mallat layout)
+//   scratch : LL ping-pong buffers A (LL of odd levels, <= 1/4 plane) and B (even levels, <= 1/16):
+//             the shrinking LL band never lands on unread inputs of another CTA, HL/LH/HH go straight
+//             to the coefficient plane, only LL_L is written into the plane.
+//   temp    : planar int32/float32 image planes, only on the generic path (Part-2 MCT, planar API,
+//             tiles that perform no level).
+#include <cuda_runtime.h>
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/j2k_b200.h"
+#include "j2k_kernels.cuh"
+#include "j2k_pointwise.cuh"
+
+#ifndef J2K_LAUNCH
+#define J2K_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#endif
+
+using namespace j2k;
+
+namespace {
+
+thread_local std::string t_err = "";
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    t_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) return fail(J2K_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+// ------------------------------------------------------------------ geometry (parity.go, layout.go)
+
+inline int split_len(int n, bool even) { return even ? (n + 1) / 2 : n / 2; }   // wavelet/parity.go:3-8
+inline int next_coord(int v) { return (v + 1) >> 1; }                            // wavelet/parity.go:14-16
+inline int ceil_div(int a, int b) { return b <= 0 ? 0 : (a >= 0 ? (a + b - 1) / b : a / b); }  // tile_assembler.go:207-215
+
+struct LevelGeom { int w, h, px, py, lw, lh; };
+struct Rect { int x, y, w, h; };
+
+// Levels the reference actually performs (ForwardMultilevel*WithParity, dwt53.go:365-394, dwt97.go:388-407:
+// stop when the window is <= 1x1) and the residual LL window.
+void performed_levels(int w, int h, int x0, int y0, int L, std::vector<LevelGeom>& out, int& cw, int& ch) {
+    out.clear();
+    cw = w; ch = h;
+    int cx = x0, cy = y0;
+    for (int l = 0; l < L; l++) {
+        if (cw <= 1 && ch <= 1) break;
+        if (cw <= 0 || ch <= 0) break;  // empty window (odd origin, 1-sample dimension): every deeper level is a no-op
+        LevelGeom g;
+        g.w = cw; g.h = ch; g.px = cx & 1; g.py = cy & 1;
+        g.lw = split_len(cw, g.px == 0); g.lh = split_len(ch, g.py == 0);
+        out.push_back(g);
+        cw = g.lw; ch = g.lh; cx = next_coord(cx); cy = next_coord(cy);
+    }
+}
+
+// bandInfosForResolution over all resolutions, QCD order (encoder.go:2352-2389, t2/geometry.go:53-92)
+std::vector<Rect> go_band_rects(int width, int height, int x0, int y0, int L) {
+    auto dims = [&](int res, int& rw, int& rh) {
+        int level_no = L - res;
+        if (level_no < 0) level_no = 0;
+        rw = width; rh = height;
+        int rx = x0, ry = y0;
+        for (int i = 0; i < level_no; i++) {
+            rw = split_len(rw, (rx & 1) == 0); rh = split_len(rh, (ry & 1) == 0);
+            rx = next_coord(rx); ry = next_coord(ry);
+        }
+    };
+    std::vector<Rect> r;
+    int rw, rh;
+    dims(0, rw, rh);
+    r.push_back({0, 0, rw, rh});
+    for (int res = 1; res <= L; res++) {
+        int lw, lh;
+        dims(res, rw, rh);
+        dims(res - 1, lw, lh);
+        int hw = rw - lw, hh = rh - lh;
+        r.push_back({lw, 0, hw, lh});
+        r.push_back({0, lh, lw, hh});
+        r.push_back({lw, lh, hw, hh});
+    }
+    return r;
+}
+
+inline bool rect_empty(const Rect& r) { return r.w <= 0 || r.h <= 0; }
+inline bool rect_same(const Rect& a, const Rect& b) {
+    if (rect_empty(a) && rect_empty(b)) return true;
+    return a.x == b.x && a.y == b.y && a.w == b.w && a.h == b.h;
+}
+
+// True when the literal band rectangles coincide with the windows the DWT levels write, so the
+// quantizer can be fused into the level kernels (always, except odd origins with 1-sample windows).
+bool geometry_regular(const std::vector<LevelGeom>& lv, int cw, int ch, const std::vector<Rect>& rects, int L) {
+    std::vector<Rect> mine(3 * L + 1, Rect{0, 0, 0, 0});
+    mine[0] = {0, 0, cw, ch};
+    for (size_t k = 0; k < lv.size(); k++) {  // level k+1 <-> resolution L-k
+        const LevelGeom& g = lv[k];
+        int res = L - (int)k;
+        int idx = 3 * (res - 1) + 1;
+        mine[idx] = {g.lw, 0, g.w - g.lw, g.lh};
+        mine[idx + 1] = {0, g.lh, g.lw, g.h - g.lh};
+        mine[idx + 2] = {g.lw, g.lh, g.w - g.lw, g.h - g.lh};
+    }
+    for (int i = 0; i < 3 * L + 1; i++)
+        if (!rect_same(mine[i], rects[i])) return false;
+    return true;
+}
+
+// ------------------------------------------------------------------ device resources
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { p = nullptr; return fail(J2K_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e)); }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+enum BufId { B_NONE = 0, B_PIX, B_COEF, B_PLANES, B_TEMP, B_SA, B_SB, B_CTEMP, B_COUNT };
+
+struct LevelLaunch {
+    LevelArgs a;
+    int WT, NP, NC, KIND, MCT;  // KIND: InKind of the interleaved side
+    int x_buf, ll_buf, band_buf, planes_buf;
+    int x_elem_bytes;           // element size of x_base for alignment checks
+    int level;                  // 1 = finest
+};
+
+enum PwKind { PW_PREP, PW_FINALIZE, PW_QUANT_RECTS, PW_SHIFT, PW_COPY, PW_DEQUANT_RECTS };
+struct PwLaunch {
+    int kind;
+    int src_buf, dst_buf;
+    const long long *src_off, *dst_off;
+    int src_stride, dst_stride, n_items, w, h, cvt, all_round, shift;
+    RectTable rt;
+};
+
+struct Plan;
+
+struct DeviceCtx {
+    int dev = 0;
+    cudaStream_t s_main = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_t[4] = {nullptr, nullptr, nullptr, nullptr};      // timing
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    bool ev_k_used[2] = {false, false}, ev_out_used[2] = {false, false};
+    DevBuf in[2], out[2], planes[2], api[8];
+    std::map<std::string, std::unique_ptr<Plan>> plans;
+};
+
+struct Plan {
+    bool fwd = true;
+    int nframes = 0;
+    // shared
+    int C = 1, W = 0, H = 0, L = 0, bps = 1;
+    bool reversible = true;
+    bool generic = false;        // prep / finalize path
+    bool direct = false;         // wavelet package API: planar working-type in, raw bands out
+    RawFmt raw{};
+    MctProgram prog{};
+    int pix_kind = IN_U8;
+    long long frame_samples = 0; // caller frame stride in samples
+    long long coeffs_per_frame = 0;
+    bool want_planes = false;
+    DevBuf tables, temp, sa, sb, ctemp;
+    std::vector<LevelLaunch> levels;   // in execution order
+    std::vector<PwLaunch> pre, post;   // pointwise launches before / after the level launches
+    int launches_per_run = 0;
+    ~Plan() { tables.release(); temp.release(); sa.release(); sb.release(); ctemp.release(); }
+};
+
+}  // namespace
+
+struct j2k_ctx {
+    std::vector<DeviceCtx> devs;
+    std::mutex mu;
+    std::atomic<long long> launches{0};
+    j2k_timing last{};
+    std::vector<void*> pinned;
+    long long next_ticket = 1;
+    std::map<long long, std::vector<int>> tickets;
+    // per-launch profiling (j2k_set_profiling)
+    bool profiling = false;
+    int prof_dev = 0;
+    std::vector<cudaEvent_t> prof_ev;   // 2 per launch
+    std::vector<int> prof_level;
+    cudaStream_t prof_stream = nullptr;
+};
+
+namespace {
+
+// ------------------------------------------------------------------ level kernel dispatch
+
+#define J2K_GRID(a) (unsigned)((((long long)(a).n_items * (a).nchunks * (a).nstrips) + 3) / 4)
+
+#define FWD_CASE(wt, np, nc, in, mct)                                                                   \
+    if (l.WT == wt && l.NP == np && l.NC == nc && l.KIND == in && l.MCT == mct) {                       \
+        J2K_LAUNCH((fwd_level_kernel<wt, np, nc, in, mct>), J2K_GRID(a), 128, st, a);                   \
+        return cudaGetLastError();                                                                      \
+    }
+#define INV_CASE(wt, np, nc, out, mct)                                                                  \
+    if (l.WT == wt && l.NP == np && l.NC == nc && l.KIND == out && l.MCT == mct) {                      \
+        J2K_LAUNCH((inv_level_kernel<wt, np, nc, out, mct>), J2K_GRID(a), 128, st, a);                  \
+        return cudaGetLastError();                                                                      \
+    }
+
+cudaError_t launch_fwd_level(const LevelLaunch& l, const LevelArgs& a, cudaStream_t st) {
+    FWD_CASE(53, 4, 1, IN_U8, MCTK_NONE) FWD_CASE(53, 4, 1, IN_U16, MCTK_NONE)
+    FWD_CASE(53, 1, 1, IN_U8, MCTK_NONE) FWD_CASE(53, 1, 1, IN_U16, MCTK_NONE)
+    FWD_CASE(53, 1, 1, IN_I32, MCTK_NONE) FWD_CASE(53, 2, 1, IN_I32, MCTK_NONE)
+    FWD_CASE(53, 2, 3, IN_U8, MCTK_RCT) FWD_CASE(53, 2, 3, IN_U16, MCTK_RCT)
+    FWD_CASE(97, 4, 1, IN_U8, MCTK_NONE) FWD_CASE(97, 4, 1, IN_U16, MCTK_NONE)
+    FWD_CASE(97, 1, 1, IN_U8, MCTK_NONE) FWD_CASE(97, 1, 1, IN_U16, MCTK_NONE)
+    FWD_CASE(97, 1, 1, IN_I32, MCTK_NONE) FWD_CASE(97, 2, 1, IN_I32, MCTK_NONE)
+    FWD_CASE(97, 1, 1, IN_F32, MCTK_NONE) FWD_CASE(97, 2, 1, IN_F32, MCTK_NONE)
+    FWD_CASE(97, 2, 3, IN_U8, MCTK_ICT) FWD_CASE(97, 2, 3, IN_U16, MCTK_ICT)
+    return cudaErrorInvalidDeviceFunction;
+}
+
+cudaError_t launch_inv_level(const LevelLaunch& l, const LevelArgs& a, cudaStream_t st) {
+    INV_CASE(53, 4, 1, IN_U8, MCTK_NONE) INV_CASE(53, 4, 1, IN_U16, MCTK_NONE)
+    INV_CASE(53, 1, 1, IN_U8, MCTK_NONE) INV_CASE(53, 1, 1, IN_U16, MCTK_NONE)
+    INV_CASE(53, 1, 1, IN_I32, MCTK_NONE) INV_CASE(53, 2, 1, IN_I32, MCTK_NONE)
+    INV_CASE(53, 2, 3, IN_U8, MCTK_RCT) INV_CASE(53, 2, 3, IN_U16, MCTK_RCT)
+    INV_CASE(97, 4, 1, IN_U8, MCTK_NONE) INV_CASE(97, 4, 1, IN_U16, MCTK_NONE)
+    INV_CASE(97, 1, 1, IN_U8, MCTK_NONE) INV_CASE(97, 1, 1, IN_U16, MCTK_NONE)
+    INV_CASE(97, 1, 1, IN_F32, MCTK_NONE) INV_CASE(97, 2, 1, IN_F32, MCTK_NONE)
+    INV_CASE(97, 2, 3, IN_U8, MCTK_ICT) INV_CASE(97, 2, 3, IN_U16, MCTK_ICT)
+    return cudaErrorInvalidDeviceFunction;
+}
+
+// ------------------------------------------------------------------ plan building
+
+struct TileGeom { int x0, y0, tw, th, ox, oy; long long coeff_off; };
+
+struct Spec {  // superset of the public parameter blocks
+    bool fwd;
+    int W, H, C, bit_depth, is_signed, L, reversible, htj2k, mct_mode;
+    std::vector<TileGeom> tiles;
+    int n_steps; double steps[J2K_MAX_BANDS];
+    bool fuse_shift;        // fwd <<6 / inv /2
+    bool planar_in;         // j2k_forward_planar
+    bool direct;            // wavelet API
+    bool want_planes;
+    const double* mct_matrix; int mct_has_offsets; const int32_t* mct_offsets;
+    int n_bindings; const j2k_mct_binding* bindings;
+};
+
+RawFmt make_raw(const Spec& s) {
+    RawFmt r{};
+    r.pix_stride = s.C;
+    if (s.is_signed) {
+        if (s.bit_depth <= 8) { r.sign_thresh = 128; r.sign_sub = 256; }               // encoder.go:362-364
+        else { r.sign_thresh = 1 << (s.bit_depth - 1); r.sign_sub = 1 << s.bit_depth; } // encoder.go:374-376
+        r.dc = 0;
+        r.clamp_lo = -(1 << (s.bit_depth - 1)); r.clamp_hi = (1 << (s.bit_depth - 1)) - 1;
+        r.wrap_add = 1 << s.bit_depth;
+    } else {
+        r.sign_thresh = 0x7fffffff; r.sign_sub = 0;
+        r.dc = 1 << (s.bit_depth - 1);
+        r.clamp_lo = 0; r.clamp_hi = (1 << s.bit_depth) - 1;
+        r.wrap_add = 0;
+    }
+    return r;
+}
+
+void fill_op_from_binding(const j2k_mct_binding& b, int C, bool fwd, MctOp& op) {
+    memset(&op, 0, sizeof op);
+    int n = b.n_components;
+    if (n == 0 && fwd) { n = C; for (int i = 0; i < n; i++) op.ids[i] = i; }  // encoder.go:562-568
+    else for (int i = 0; i < n; i++) op.ids[i] = b.component_ids[i];
+    op.n = n;
+    op.kind = b.element_type == 0 ? 0 : 1;
+    op.has_matrix = fwd ? 1 : b.has_matrix;
+    for (int r = 0; r < n; r++)
+        for (int k = 0; k < n; k++) {
+            double m = b.has_matrix ? b.matrix[r * n + k] : (r == k ? 1.0 : 0.0);  // encoder.go:596-608
+            op.mf[r * n + k] = m;
+            if (fwd && op.kind == 1) op.mi[r * n + k] = (int)(m * (double)(1 << 13));
+            else op.mi[r * n + k] = (int)m;
+        }
+    op.has_off = b.has_offsets;
+    for (int i = 0; i < n; i++) op.off[i] = b.offsets[i];
+}
+
+int make_prog(const Spec& s, MctProgram& prog) {
+    memset(&prog, 0, sizeof prog);
+    switch (s.mct_mode) {
+    case J2K_MCT_NONE: prog.kind = 0; return 0;
+    case J2K_MCT_RCT:
+        if (s.C != 3 || !s.reversible) return fail(J2K_ERR_INVALID_ARG, "RCT needs 3 components and the reversible transform");
+        prog.kind = 1; return 0;
+    case J2K_MCT_ICT:
+        if (s.C != 3 || s.reversible) return fail(J2K_ERR_INVALID_ARG, "ICT needs 3 components and the irreversible transform");
+        prog.kind = 2; return 0;
+    case J2K_MCT_CUSTOM_INT: case J2K_MCT_CUSTOM_Q13: case J2K_MCT_CUSTOM_FLOAT: {
+        if ((s.mct_mode == J2K_MCT_CUSTOM_FLOAT) == s.fwd) return fail(J2K_ERR_INVALID_ARG, "custom MCT mode %d is not valid in this direction", s.mct_mode);
+        prog.kind = 3; prog.n_ops = 1;
+        MctOp& op = prog.ops[0];
+        op.n = s.C;
+        for (int i = 0; i < s.C; i++) op.ids[i] = i;
+        op.kind = s.mct_mode == J2K_MCT_CUSTOM_INT ? 0 : 1;
+        op.has_matrix = 1;
+        for (int i = 0; i < s.C * s.C; i++) {
+            op.mf[i] = s.mct_matrix[i];
+            op.mi[i] = s.mct_mode == J2K_MCT_CUSTOM_Q13 ? (int)(s.mct_matrix[i] * (double)(1 << 13)) : (int)s.mct_matrix[i];
+        }
+        op.has_off = s.mct_has_offsets;
+        for (int i = 0; i < s.C; i++) op.off[i] = s.mct_offsets[i];
+        return 0;
+    }
+    case J2K_MCT_BINDINGS:
+        if (s.n_bindings < 0 || s.n_bindings > J2K_MAX_BINDINGS) return fail(J2K_ERR_INVALID_ARG, "n_bindings out of range");
+        prog.kind = 3; prog.n_ops = 0;
+        for (int i = 0; i < s.n_bindings; i++) {
+            const j2k_mct_binding& b = s.bindings[i];
+            if (b.n_components < 0 || b.n_components > s.C) return fail(J2K_ERR_INVALID_ARG, "binding %d: bad component count", i);
+            for (int k = 0; k < b.n_components; k++)
+                if (b.component_ids[k] < 0 || b.component_ids[k] >= s.C) return fail(J2K_ERR_INVALID_ARG, "binding %d: bad component id", i);
+            if (!s.fwd && b.n_components == 0) continue;  // decoder.go:633-635
+            fill_op_from_binding(b, s.C, s.fwd, prog.ops[prog.n_ops++]);
+        }
+        return 0;
+    }
+    return fail(J2K_ERR_INVALID_ARG, "unknown mct_mode %d", s.mct_mode);
+}
+
+inline bool all_mult(const std::vector<long long>& v, size_t b, size_t e, int m) {
+    for (size_t i = b; i < e; i++) if (v[i] % m) return false;
+    return true;
+}
+
+struct TableBuilder {
+    std::vector<long long> host;
+    size_t add(const std::vector<long long>& v) { size_t o = host.size(); host.insert(host.end(), v.begin(), v.end()); return o; }
+};
+
+struct ClassTmp {
+    std::vector<int> tiles;
+    std::vector<LevelGeom> lv;
+    int cw, ch, tw, th, ox, oy;
+    bool regular;
+    std::vector<Rect> rects;
+};
+
+void choose_chunks(LevelArgs& a, int valid_pairs) {
+    a.nstrips = (a.Kx + valid_pairs - 1) / valid_pairs;
+    if (a.nstrips < 1) a.nstrips = 1;
+    long long base = (long long)a.n_items * a.nstrips;
+    const long long target = 148LL * 32;  // >= 2 waves of 16 warps per SM
+    long long want = (target + base - 1) / base;
+    int max_chunks = (a.Ky + 15) / 16;
+    if (max_chunks < 1) max_chunks = 1;
+    if (want > max_chunks) want = max_chunks;
+    if (want < 1) want = 1;
+    a.chunk_pairs = (int)((a.Ky + want - 1) / want);
+    if (a.chunk_pairs < 1) a.chunk_pairs = 1;
+    a.nchunks = (a.Ky + a.chunk_pairs - 1) / a.chunk_pairs;
+    if (a.nchunks < 1) a.nchunks = 1;
+}
+
+inline int valid_pairs_of(int wt, int np) {
+    int halo = wt == 97 ? 2 : 1;
+    int hln = (halo + np - 1) / np;
+    return (32 - 2 * hln) * np;
+}
+
+void set_geom(LevelArgs& a, const LevelGeom& g) {
+    a.w = g.w; a.h = g.h; a.px = g.px; a.py = g.py; a.lw = g.lw; a.lh = g.lh;
+    a.Kx = (g.w + g.px + 1) / 2; a.Ky = (g.h + g.py + 1) / 2;
+    a.hskip = g.w <= 1; a.vskip = g.h <= 1;
+}
+
+// Quantizer / dequantizer mode of band `idx` (QCD order).
+void band_mode_fwd(const Spec& s, int idx, BandIO& b) {
+    b.shift = 0; b.step = 1.f; b.rcp = 1.f; b.scale = 1.f;
+    if (s.direct) { b.mode = Q_RAW; return; }
+    if (s.reversible) {
+        if (s.fuse_shift && !s.htj2k) { b.mode = Q_SHIFT; b.shift = 6; } else b.mode = Q_RAW;
+        return;
+    }
+    if (s.n_steps == 0) { b.mode = Q_ROUND; return; }     // encoder.go:2266-2273
+    if (idx >= s.n_steps) { b.mode = Q_ZERO; return; }    // encoder.go:2283,2294
+    if (s.steps[idx] <= 0) { b.mode = Q_ROUND; return; }  // encoder.go:2320-2321
+    b.mode = Q_QUANT;
+    b.step = (float)s.steps[idx];                          // float32(stepSize), encoder.go:2323
+    b.rcp = 1.0f / b.step;                                 // correctly rounded reciprocal for div_by_step
+    b.scale = s.htj2k ? 1.f : 64.f;                        // encoder.go:2312-2315
+}
+void band_mode_inv(const Spec& s, int idx, BandIO& b) {
+    b.shift = 0; b.step = 1.f; b.rcp = 1.f; b.scale = 1.f;
+    if (s.direct) { b.mode = DQ_RAW; return; }
+    if (s.reversible) { b.mode = (s.fuse_shift && !s.htj2k) ? DQ_HALVE : DQ_RAW; return; }
+    if (s.n_steps == 0 || idx >= s.n_steps || s.steps[idx] <= 0) { b.mode = DQ_CVT; return; }
+    b.mode = DQ_SCALE;
+    b.scale = (float)(s.htj2k ? s.steps[idx] : 0.5 * s.steps[idx]);  // t2/tile_decoder.go:974-977,983
+}
+
+void fill_rect_table(const Spec& s, const std::vector<Rect>& rects, RectTable& rt) {
+    memset(&rt, 0, sizeof rt);
+    rt.n = (int)rects.size();
+    for (int i = 0; i < rt.n; i++) {
+        rt.x[i] = rects[i].x; rt.y[i] = rects[i].y; rt.w[i] = rects[i].w; rt.h[i] = rects[i].h;
+        BandIO b{};
+        if (s.fwd) band_mode_fwd(s, i, b); else band_mode_inv(s, i, b);
+        rt.mode[i] = b.mode; rt.step[i] = b.step; rt.rcp[i] = b.rcp; rt.scale[i] = b.scale;
+    }
+}
+
+// Builds the launch list of one direction.  Returns 0 or a negative status.
+int build_plan(const Spec& s, int nframes, long long frame_samples, Plan& P) {
+    P.fwd = s.fwd; P.nframes = nframes; P.C = s.C; P.W = s.W; P.H = s.H; P.L = s.L;
+    P.bps = s.bit_depth <= 8 ? 1 : 2;
+    P.reversible = s.reversible != 0;
+    P.direct = s.direct;
+    P.raw = make_raw(s);
+    P.pix_kind = s.bit_depth <= 8 ? IN_U8 : IN_U16;
+    P.frame_samples = frame_samples;
+    P.coeffs_per_frame = (long long)s.W * s.H * s.C;
+    P.want_planes = s.want_planes;
+    if (!s.direct) { int rc = make_prog(s, P.prog); if (rc) return rc; }
+    const int WT = s.reversible ? 53 : 97;
+    const long long HW = (long long)s.W * s.H;
+
+    // classes of tiles that share every level window
+    std::vector<ClassTmp> classes;
+    const int pm = (1 << (s.L > 0 ? (s.L > 20 ? 20 : s.L) : 0)) - 1;
+    for (size_t t = 0; t < s.tiles.size(); t++) {
+        const TileGeom& g = s.tiles[t];
+        if (g.tw <= 0 || g.th <= 0) continue;
+        size_t k = 0;
+        for (; k < classes.size(); k++)
+            if (classes[k].tw == g.tw && classes[k].th == g.th && (classes[k].ox & pm) == (g.ox & pm) && (classes[k].oy & pm) == (g.oy & pm)) break;
+        if (k == classes.size()) {
+            ClassTmp c;
+            c.tw = g.tw; c.th = g.th; c.ox = g.ox; c.oy = g.oy;
+            performed_levels(g.tw, g.th, g.ox, g.oy, s.L, c.lv, c.cw, c.ch);
+            c.rects = go_band_rects(g.tw, g.th, g.ox, g.oy, s.L);
+            c.regular = s.reversible || s.direct || geometry_regular(c.lv, c.cw, c.ch, c.rects, s.L);
+            classes.push_back(c);
+        }
+        classes[k].tiles.push_back((int)t);
+    }
+    bool any_nolevel = false;
+    for (auto& c : classes) if (c.lv.empty()) any_nolevel = true;
+    const bool std_mct = s.mct_mode == J2K_MCT_NONE || s.mct_mode == J2K_MCT_RCT || s.mct_mode == J2K_MCT_ICT;
+    P.generic = !s.direct && (!std_mct || s.planar_in || any_nolevel);
+    const bool nc3 = !P.generic && !s.direct && (s.mct_mode == J2K_MCT_RCT || s.mct_mode == J2K_MCT_ICT);
+    const bool temp_is_f32 = s.fwd && s.mct_mode == J2K_MCT_ICT;  // encoder.go:206
+
+    TableBuilder tb;
+    struct Fix { int which; size_t level; size_t off; };  // which: 0 x_off, 1 ll, 2 hl, 3 lh, 4 hh, 5 planes
+    std::vector<Fix> fixes;
+    struct PwFix { bool post; size_t i; size_t src, dst; };
+    std::vector<PwFix> pwfixes;
+    long long sa_total = 0, sb_total = 0;
+
+    auto pad4 = [](long long v) { return (v + 3) & ~3LL; };
+
+    for (auto& c : classes) {
+        const int nt = (int)c.tiles.size();
+        const int Lp = (int)c.lv.size();
+        const long long tn = (long long)c.tw * c.th;
+        const long long sa_item = Lp >= 1 ? pad4((long long)c.lv[0].lw * c.lv[0].lh) : 0;
+        const long long sb_item = Lp >= 2 ? pad4((long long)c.lv[1].lw * c.lv[1].lh) : 0;
+        const long long n_comp_items = (long long)nframes * nt * s.C;
+        const long long n_pix_items = (long long)nframes * nt;
+        // offset tables (elements)
+        std::vector<long long> plane_c(n_comp_items), sa_c(n_comp_items), sb_c(n_comp_items), x_c(n_comp_items), img_c(n_comp_items);
+        std::vector<long long> plane_p(n_pix_items), sa_p(n_pix_items), x_p(n_pix_items), img_p(n_pix_items);
+        for (int f = 0; f < nframes; f++)
+            for (int ti = 0; ti < nt; ti++) {
+                const TileGeom& g = s.tiles[c.tiles[ti]];
+                long long pi = (long long)f * nt + ti;
+                long long tile_pix = (long long)g.y0 * s.W + g.x0;
+                plane_p[pi] = (long long)f * P.coeffs_per_frame + g.coeff_off;
+                sa_p[pi] = sa_total + pi * s.C * sa_item;
+                x_p[pi] = (long long)f * frame_samples + tile_pix * s.C;          // interleaved pixels
+                img_p[pi] = (long long)f * s.C * HW + tile_pix;                    // planar image planes (temp / planes_out)
+                for (int comp = 0; comp < s.C; comp++) {
+                    long long ci = pi * s.C + comp;
+                    plane_c[ci] = plane_p[pi] + comp * tn;
+                    sa_c[ci] = sa_p[pi] + comp * sa_item;
+                    sb_c[ci] = sb_total + ci * sb_item;
+                    x_c[ci] = x_p[pi] + comp;
+                    img_c[ci] = img_p[pi] + comp * HW;
+                }
+            }
+        const size_t o_plane_c = tb.add(plane_c), o_sa_c = tb.add(sa_c), o_sb_c = tb.add(sb_c), o_x_c = tb.add(x_c), o_img_c = tb.add(img_c);
+        const size_t o_plane_p = tb.add(plane_p), o_sa_p = tb.add(sa_p), o_x_p = tb.add(x_p), o_img_p = tb.add(img_p);
+        sa_total += n_comp_items * sa_item;
+        sb_total += n_comp_items * sb_item;
+
+        RectTable rt;
+        fill_rect_table(s, c.rects, rt);
+        const bool irregular = !c.regular;
+        // which buffer holds the coefficient planes the level kernels touch
+        const int coef_buf = (!s.fwd && irregular) ? B_CTEMP : B_COEF;
+
+        if (Lp == 0) {
+            // no level is performed (num_levels == 0 or <= 1x1 tiles): copy windows + literal band passes
+            PwLaunch pw{};
+            pw.n_items = (int)n_comp_items; pw.w = c.tw; pw.h = c.th;
+            if (s.fwd) {
+                if (s.direct) continue;  // nothing to do: data is unchanged
+                pw.kind = PW_COPY; pw.src_buf = B_TEMP; pw.dst_buf = B_COEF; pw.src_stride = s.W; pw.dst_stride = c.tw;
+                pw.cvt = (s.reversible || temp_is_f32) ? 0 : 1;
+                pwfixes.push_back({true, P.post.size(), o_img_c, o_plane_c});
+                P.post.push_back(pw);
+                if (!s.reversible) {
+                    PwLaunch q{};
+                    q.kind = PW_QUANT_RECTS; q.dst_buf = B_COEF; q.n_items = (int)n_comp_items; q.w = c.tw; q.h = c.th; q.dst_stride = c.tw;
+                    q.all_round = (s.L == 0 || s.n_steps == 0); q.rt = rt;
+                    pwfixes.push_back({true, P.post.size(), o_plane_c, o_plane_c});
+                    P.post.push_back(q);
+                } else if (s.fuse_shift && !s.htj2k) {
+                    PwLaunch q{};
+                    q.kind = PW_SHIFT; q.dst_buf = B_COEF; q.n_items = (int)n_comp_items; q.w = c.tw; q.h = c.th; q.dst_stride = c.tw; q.shift = 6;
+                    pwfixes.push_back({true, P.post.size(), o_plane_c, o_plane_c});
+                    P.post.push_back(q);
+                }
+            } else {
+                if (s.direct) continue;
+                if (s.reversible || s.L == 0) {  // t2/tile_decoder.go:887-898
+                    pw.kind = PW_COPY; pw.src_buf = B_COEF; pw.dst_buf = B_TEMP; pw.src_stride = c.tw; pw.dst_stride = s.W;
+                    pw.cvt = (s.reversible && s.fuse_shift && !s.htj2k) ? 3 : 0;
+                    pwfixes.push_back({false, P.pre.size(), o_plane_c, o_img_c});
+                    P.pre.push_back(pw);
+                } else {                          // dequantize, (no-op inverse), round: t2/tile_decoder.go:899-913
+                    pw.kind = PW_DEQUANT_RECTS; pw.src_buf = B_COEF; pw.dst_buf = B_TEMP; pw.src_stride = c.tw; pw.dst_stride = s.W; pw.rt = rt;
+                    pwfixes.push_back({false, P.pre.size(), o_plane_c, o_img_c});
+                    P.pre.push_back(pw);
+                    PwLaunch r2{};
+                    r2.kind = PW_COPY; r2.src_buf = B_TEMP; r2.dst_buf = B_TEMP; r2.src_stride = s.W; r2.dst_stride = s.W;
+                    r2.n_items = (int)n_comp_items; r2.w = c.tw; r2.h = c.th; r2.cvt = 2;
+                    pwfixes.push_back({false, P.pre.size(), o_img_c, o_img_c});
+                    P.pre.push_back(r2);
+                }
+            }
+            continue;
+        }
+
+        if (!s.fwd && irregular) {  // literal dequantization into a float copy of the planes
+            PwLaunch pw{};
+            pw.kind = PW_DEQUANT_RECTS; pw.src_buf = B_COEF; pw.dst_buf = B_CTEMP; pw.src_stride = c.tw; pw.dst_stride = c.tw;
+            pw.n_items = (int)n_comp_items; pw.w = c.tw; pw.h = c.th; pw.rt = rt;
+            pwfixes.push_back({false, P.pre.size(), o_plane_c, o_plane_c});
+            P.pre.push_back(pw);
+        }
+
+        // level launches: forward k = 1..Lp, inverse k = Lp..1
+        for (int step_i = 0; step_i < Lp; step_i++) {
+            const int k = s.fwd ? step_i + 1 : Lp - step_i;  // 1-based level
+            const LevelGeom& g = c.lv[k - 1];
+            LevelLaunch l{};
+            LevelArgs& a = l.a;
+            memset(&a, 0, sizeof a);
+            set_geom(a, g);
+            l.WT = WT;
+            l.level = k;
+            a.raw = P.raw;
+            const bool first = (k == 1);       // touches the image side
+            const bool last = (k == Lp);       // touches the coarsest LL
+            const bool use_nc3 = nc3 && first;
+            l.NC = use_nc3 ? 3 : 1;
+            l.MCT = use_nc3 ? (s.mct_mode == J2K_MCT_RCT ? MCTK_RCT : MCTK_ICT) : MCTK_NONE;
+            a.n_items = (int)(use_nc3 ? n_pix_items : n_comp_items);
+            const int res = s.L - (k - 1);     // resolution whose bands this level holds
+            const int bidx = 3 * (res - 1) + 1;
+
+            // ---- interleaved side
+            size_t o_x;
+            if (first) {
+                if (s.direct) {
+                    l.KIND = s.reversible ? IN_I32 : IN_F32;
+                    l.x_buf = s.fwd ? B_PIX : B_PLANES; l.x_elem_bytes = 4;
+                    a.x_row_stride = s.W; a.x_comp_stride = HW; o_x = o_img_c;
+                    a.raw.dc = 0; a.x_mode = 0;
+                } else if (P.generic) {
+                    l.KIND = s.fwd ? (temp_is_f32 ? IN_F32 : IN_I32) : (s.reversible ? IN_I32 : IN_F32);
+                    l.x_buf = B_TEMP; l.x_elem_bytes = 4;
+                    a.x_row_stride = s.W; a.x_comp_stride = HW; o_x = o_img_c;
+                    a.raw.dc = 0;
+                    a.x_mode = 1;  // inverse: store rounded int32 samples (finalize_kernel does the rest)
+                } else {
+                    l.KIND = P.pix_kind;
+                    l.x_buf = B_PIX; l.x_elem_bytes = P.bps;
+                    a.x_row_stride = s.W * s.C; o_x = use_nc3 ? o_x_p : o_x_c;
+                    a.x_mode = 1;
+                    if (!s.fwd && s.want_planes) {
+                        l.planes_buf = B_PLANES;
+                        a.planes_comp_stride = HW; a.planes_row_stride = s.W;
+                        fixes.push_back({5, P.levels.size(), use_nc3 ? o_img_p : o_img_c});
+                    }
+                }
+            } else {
+                l.KIND = s.reversible ? IN_I32 : IN_F32;
+                // forward reads LL_{k-1}; inverse writes LL_{k-1}
+                l.x_buf = ((k - 1) & 1) ? B_SA : B_SB; l.x_elem_bytes = 4;
+                a.x_row_stride = c.lv[k - 2].lw; o_x = ((k - 1) & 1) ? o_sa_c : o_sb_c;
+                a.raw.dc = 0; a.x_mode = 0;
+            }
+            a.x_kind = l.KIND;
+            fixes.push_back({0, P.levels.size(), o_x});
+
+            // ---- band side
+            auto band = [&](BandIO& b, int xo, int yo, int idx) {
+                b.row_stride = c.tw; b.x_off = xo; b.y_off = yo; b.comp_stride = tn;
+                if (s.fwd) band_mode_fwd(s, idx, b); else band_mode_inv(s, idx, b);
+                if (s.fwd && irregular) b.mode = Q_RAW;         // literal quantization runs afterwards
+                if (!s.fwd && irregular) b.mode = DQ_RAW;       // already dequantized into B_CTEMP
+            };
+            band(a.hl, g.lw, 0, bidx);
+            band(a.lh_, 0, g.lh, bidx + 1);
+            band(a.hh, g.lw, g.lh, bidx + 2);
+            l.band_buf = coef_buf;
+            const size_t o_plane = use_nc3 ? o_plane_p : o_plane_c;
+            fixes.push_back({2, P.levels.size(), o_plane});
+            fixes.push_back({3, P.levels.size(), o_plane});
+            fixes.push_back({4, P.levels.size(), o_plane});
+            size_t o_ll;
+            if (last) {
+                band(a.ll, 0, 0, 0);
+                l.ll_buf = coef_buf;
+                o_ll = o_plane;
+            } else {
+                a.ll.row_stride = g.lw; a.ll.x_off = 0; a.ll.y_off = 0;
+                a.ll.mode = s.fwd ? (int)Q_RAW : (int)DQ_RAW; a.ll.step = a.ll.rcp = a.ll.scale = 1.f;
+                a.ll.comp_stride = (k & 1) ? sa_item : sb_item;
+                l.ll_buf = (k & 1) ? B_SA : B_SB;
+                o_ll = (k & 1) ? (use_nc3 ? o_sa_p : o_sa_c) : o_sb_c;
+            }
+            fixes.push_back({1, P.levels.size(), o_ll});
+
+            // ---- kernel shape
+            if (l.NC == 3) l.NP = 2;
+            else if (l.KIND == IN_U8 || l.KIND == IN_U16) l.NP = (a.Kx >= 64) ? 4 : 1;
+            else l.NP = (a.Kx > valid_pairs_of(WT, 1)) ? 2 : 1;
+            choose_chunks(a, valid_pairs_of(WT, l.NP));
+
+            // ---- 128-bit fast paths: every offset, stride and band origin a multiple of the vector width
+            const int NS = 2 * l.NP;
+            {
+                const std::vector<long long>& H = tb.host;
+                size_t n = (size_t)a.n_items;
+                bool okx = g.px == 0 && (a.x_row_stride % NS) == 0 && all_mult(H, o_x, o_x + n, NS);
+                if (l.NC == 3 && first && !P.generic) okx = g.px == 0 && (a.x_row_stride % 4) == 0 && all_mult(H, o_x, o_x + n, 4);
+                if (l.NC == 1 && first && !P.generic && !s.direct && s.C != 1) okx = false;  // strided components
+                a.vec_x = okx;
+                bool okb = g.px == 0 && (c.tw % l.NP) == 0 && (g.lw % l.NP) == 0 && (tn % l.NP) == 0 &&
+                           all_mult(H, o_plane, o_plane + n, l.NP) && (a.ll.row_stride % l.NP) == 0 &&
+                           (a.ll.comp_stride % l.NP) == 0 && all_mult(H, o_ll, o_ll + n, l.NP);
+                a.vec_b = okb;
+            }
+            P.levels.push_back(l);
+        }
+
+        if (s.fwd && irregular && !s.direct) {
+            PwLaunch q{};
+            q.kind = PW_QUANT_RECTS; q.dst_buf = B_COEF; q.n_items = (int)n_comp_items; q.w = c.tw; q.h = c.th; q.dst_stride = c.tw;
+            q.all_round = (s.n_steps == 0); q.rt = rt;
+            pwfixes.push_back({true, P.post.size(), o_plane_c, o_plane_c});
+            P.post.push_back(q);
+        }
+    }
+
+    // ---- device allocations and table upload
+    int rc;
+    if ((rc = P.tables.ensure(tb.host.size() * sizeof(long long) + 16))) return rc;
+    CK(cudaMemcpy(P.tables.p, tb.host.data(), tb.host.size() * sizeof(long long), cudaMemcpyHostToDevice));
+    if (sa_total && (rc = P.sa.ensure((size_t)sa_total * 4))) return rc;
+    if (sb_total && (rc = P.sb.ensure((size_t)sb_total * 4))) return rc;
+    if (P.generic && (rc = P.temp.ensure((size_t)nframes * s.C * HW * 4))) return rc;
+    bool need_ctemp = false;
+    for (auto& l : P.levels) if (l.band_buf == B_CTEMP) need_ctemp = true;
+    if (need_ctemp && (rc = P.ctemp.ensure((size_t)nframes * P.coeffs_per_frame * 4))) return rc;
+    const long long* T = (const long long*)P.tables.p;
+    for (auto& f : fixes) {
+        LevelArgs& a = P.levels[f.level].a;
+        switch (f.which) {
+        case 0: a.x_off = T + f.off; break;
+        case 1: a.ll.off = T + f.off; break;
+        case 2: a.hl.off = T + f.off; break;
+        case 3: a.lh_.off = T + f.off; break;
+        case 4: a.hh.off = T + f.off; break;
+        case 5: a.planes_off = T + f.off; break;
+        }
+    }
+    for (auto& f : pwfixes) {
+        PwLaunch& pw = f.post ? P.post[f.i] : P.pre[f.i];
+        pw.src_off = T + f.src; pw.dst_off = T + f.dst;
+    }
+    P.launches_per_run = (int)(P.levels.size() + P.pre.size() + P.post.size()) + (P.generic ? 1 : 0);
+    return 0;
+}
+
+// ------------------------------------------------------------------ running a plan
+
+inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+
+int run_pw(const PwLaunch& pw, void* const* bufs, cudaStream_t st) {
+    long long total = (long long)pw.w * pw.h * pw.n_items;
+    if (total <= 0) return 0;
+    unsigned grid = (unsigned)((total + 255) / 256);
+    switch (pw.kind) {
+    case PW_COPY:
+        J2K_LAUNCH(copy_window_kernel, grid, 256, st, (const int*)bufs[pw.src_buf], pw.src_off, pw.src_stride, (int*)bufs[pw.dst_buf],
+                   pw.dst_off, pw.dst_stride, pw.n_items, pw.w, pw.h, pw.cvt);
+        break;
+    case PW_QUANT_RECTS:
+        J2K_LAUNCH(quant_rects_kernel, grid, 256, st, (int*)bufs[pw.dst_buf], pw.dst_off, pw.n_items, pw.w, pw.h, pw.dst_stride, pw.rt,
+                   pw.all_round);
+        break;
+    case PW_SHIFT:
+        J2K_LAUNCH(shift_planes_kernel, grid, 256, st, (int*)bufs[pw.dst_buf], pw.dst_off, pw.n_items, pw.w, pw.h, pw.dst_stride, pw.shift);
+        break;
+    case PW_DEQUANT_RECTS:
+        J2K_LAUNCH(dequant_rects_kernel, grid, 256, st, (const int*)bufs[pw.src_buf], pw.src_off, pw.src_stride, (int*)bufs[pw.dst_buf],
+                   pw.dst_off, pw.dst_stride, pw.n_items, pw.w, pw.h, pw.rt);
+        break;
+    default: return fail(J2K_ERR_UNSUPPORTED, "internal: bad pointwise kind");
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// pixels / coeffs / planes are device pointers.  Forward: pixels -> coeffs.  Inverse: coeffs -> pixels (+planes).
+// For the planar forward entry `pixels` holds nframes x C x H x W int32.  For direct plans `pixels` is the
+// forward source plane and `planes` the inverse destination plane.
+struct ProfScope {
+    j2k_ctx* ctx; cudaStream_t st; bool on;
+    ProfScope(j2k_ctx* c, cudaStream_t s) : ctx(c), st(s), on(c->profiling) { if (on) { ctx->prof_level.clear(); ctx->prof_stream = s; } }
+    void begin(int level) {
+        if (!on) return;
+        size_t i = ctx->prof_level.size();
+        while (ctx->prof_ev.size() < 2 * (i + 1)) { cudaEvent_t e; cudaEventCreate(&e); ctx->prof_ev.push_back(e); }
+        ctx->prof_level.push_back(level);
+        cudaEventRecord(ctx->prof_ev[2 * i], st);
+    }
+    void end() { if (on) cudaEventRecord(ctx->prof_ev[2 * (ctx->prof_level.size() - 1) + 1], st); }
+};
+
+int run_plan(j2k_ctx* ctx, Plan& P, void* pixels, void* coeffs, void* planes, bool planar_in, cudaStream_t st) {
+    ProfScope prof(ctx, st);
+    void* bufs[B_COUNT] = {nullptr};
+    bufs[B_PIX] = pixels; bufs[B_COEF] = coeffs; bufs[B_PLANES] = planes;
+    bufs[B_TEMP] = P.temp.p; bufs[B_SA] = P.sa.p; bufs[B_SB] = P.sb.p; bufs[B_CTEMP] = P.ctemp.p;
+    const long long HW = (long long)P.W * P.H;
+    int nl = 0;
+    if (P.fwd && P.generic) {
+        long long total = HW * P.nframes;
+        unsigned grid = (unsigned)((total + 255) / 256);
+        prof.begin(0);
+        J2K_LAUNCH(prep_kernel, grid, 256, st, pixels, planar_in ? (int)IN_I32 : P.pix_kind,
+                   planar_in ? (long long)P.C * HW : P.frame_samples, HW, P.C, P.raw, P.prog, (int*)P.temp.p, (long long)P.C * HW, P.nframes);
+        prof.end();
+        CK(cudaGetLastError());
+        nl++;
+    }
+    for (auto& pw : P.pre) { prof.begin(0); int rc = run_pw(pw, bufs, st); prof.end(); if (rc) return rc; nl++; }
+    for (auto& l : P.levels) {
+        LevelArgs a = l.a;
+        a.x_base = bufs[l.x_buf];
+        a.ll.base = bufs[l.ll_buf];
+        a.hl.base = a.lh_.base = a.hh.base = bufs[l.band_buf];
+        a.planes_out = l.planes_buf ? (int32_t*)bufs[l.planes_buf] : nullptr;
+        if (!aligned16(a.x_base)) a.vec_x = 0;
+        if (!aligned16(a.ll.base) || !aligned16(a.hl.base)) a.vec_b = 0;
+        prof.begin(l.level);
+        cudaError_t e = P.fwd ? launch_fwd_level(l, a, st) : launch_inv_level(l, a, st);
+        prof.end();
+        if (e != cudaSuccess)
+            return fail(J2K_ERR_CUDA, "level kernel launch (WT=%d NP=%d NC=%d kind=%d mct=%d) failed: %s", l.WT, l.NP, l.NC, l.KIND, l.MCT,
+                        cudaGetErrorString(e));
+        nl++;
+    }
+    for (auto& pw : P.post) { prof.begin(0); int rc = run_pw(pw, bufs, st); prof.end(); if (rc) return rc; nl++; }
+    if (!P.fwd && P.generic) {
+        long long total = HW * P.nframes;
+        unsigned grid = (unsigned)((total + 255) / 256);
+        prof.begin(0);
+        J2K_LAUNCH(finalize_kernel, grid, 256, st, (const int*)P.temp.p, (long long)P.C * HW, HW, P.C, P.raw, P.prog, pixels, P.pix_kind,
+                   P.frame_samples, (int*)planes, (long long)P.C * HW, P.nframes);
+        prof.end();
+        CK(cudaGetLastError());
+        nl++;
+    }
+    ctx->launches += nl;
+    return nl;
+}
+
+// ------------------------------------------------------------------ parameter validation -> Spec
+
+int validate_common(int w, int h, int C, int B, int L) {
+    if (w <= 0 || h <= 0) return fail(J2K_ERR_INVALID_ARG, "invalid dimensions: %dx%d", w, h);                                  // encoder.go:294-296
+    if (C <= 0 || C > J2K_MAX_COMPONENTS) return fail(J2K_ERR_INVALID_ARG, "invalid number of components: %d (must be 1-4)", C); // encoder.go:298-300
+    if (B < 1 || B > 16) return fail(J2K_ERR_INVALID_ARG, "invalid bit depth: %d (must be 1-16)", B);                            // encoder.go:302-304
+    if (L < 0 || L > J2K_MAX_LEVELS) return fail(J2K_ERR_INVALID_ARG, "invalid decomposition levels: %d (must be 0-%d)", L, J2K_MAX_LEVELS);
+    if ((long long)w * h * C > (1LL << 31) - 1) return fail(J2K_ERR_INVALID_ARG, "frame too large");
+    return 0;
+}
+
+int fwd_tiles(const j2k_fwd_params* p, std::vector<TileGeom>* out) {  // encoder.go:1966-1997
+    int tw = p->tile_width ? p->tile_width : p->width, th = p->tile_height ? p->tile_height : p->height;
+    if (tw <= 0 || th <= 0) return 0;
+    int ntx = (p->width + tw - 1) / tw, nty = (p->height + th - 1) / th;
+    if (out) {
+        long long off = 0;
+        for (int t = 0; t < ntx * nty; t++) {
+            int tx = t % ntx, ty = t / ntx;
+            TileGeom g;
+            g.x0 = tx * tw; g.y0 = ty * th;
+            int x1 = g.x0 + tw > p->width ? p->width : g.x0 + tw, y1 = g.y0 + th > p->height ? p->height : g.y0 + th;
+            g.tw = x1 - g.x0; g.th = y1 - g.y0; g.ox = g.x0; g.oy = g.y0; g.coeff_off = off;
+            off += (long long)g.tw * g.th * p->components;
+            out->push_back(g);
+        }
+    }
+    return ntx * nty;
+}
+
+int inv_tiles(const j2k_inv_params* p, std::vector<TileGeom>* out) {  // tile_assembler.go:33-101, t2/tile_decoder.go:269-294
+    int ntx = ceil_div(p->xsiz - p->xtosiz, p->xtsiz), nty = ceil_div(p->ysiz - p->ytosiz, p->ytsiz);
+    if (out) {
+        long long off = 0;
+        for (int t = 0; t < ntx * nty; t++) {
+            int tx = t % ntx, ty = t / ntx;
+            int gx0 = tx * p->xtsiz + p->xtosiz, gy0 = ty * p->ytsiz + p->ytosiz, gx1 = gx0 + p->xtsiz, gy1 = gy0 + p->ytsiz;
+            if (gx0 < p->xosiz) gx0 = p->xosiz;
+            if (gy0 < p->yosiz) gy0 = p->yosiz;
+            if (gx1 > p->xsiz) gx1 = p->xsiz;
+            if (gy1 > p->ysiz) gy1 = p->ysiz;
+            TileGeom g;
+            g.x0 = gx0 - p->xosiz; g.y0 = gy0 - p->yosiz; g.tw = gx1 - gx0; g.th = gy1 - gy0;
+            if (g.tw < 0) g.tw = 0;
+            if (g.th < 0) g.th = 0;
+            g.ox = gx0; g.oy = gy0; g.coeff_off = off;
+            off += (long long)g.tw * g.th * p->components;
+            out->push_back(g);
+        }
+    }
+    return ntx * nty;
+}
+
+int spec_from_fwd(const j2k_fwd_params* p, bool planar, Spec& s) {
+    if (!p) return fail(J2K_ERR_INVALID_ARG, "params is NULL");
+    int rc = validate_common(p->width, p->height, p->components, p->bit_depth, p->num_levels);
+    if (rc) return rc;
+    if (p->tile_width < 0 || p->tile_height < 0) return fail(J2K_ERR_INVALID_ARG, "invalid tile size");
+    if (p->n_steps < 0 || p->n_steps > J2K_MAX_BANDS) return fail(J2K_ERR_INVALID_ARG, "n_steps out of range");
+    s = Spec{};
+    s.fwd = true; s.W = p->width; s.H = p->height; s.C = p->components; s.bit_depth = p->bit_depth; s.is_signed = p->is_signed != 0;
+    s.L = p->num_levels; s.reversible = p->reversible != 0; s.htj2k = p->htj2k != 0; s.mct_mode = p->mct_mode;
+    fwd_tiles(p, &s.tiles);
+    s.n_steps = p->n_steps; memcpy(s.steps, p->steps, sizeof s.steps);
+    s.fuse_shift = p->fuse_t1_shift != 0; s.planar_in = planar; s.direct = false; s.want_planes = false;
+    s.mct_matrix = p->mct_matrix; s.mct_has_offsets = p->mct_has_offsets; s.mct_offsets = p->mct_offsets;
+    s.n_bindings = p->n_bindings; s.bindings = p->bindings;
+    return 0;
+}
+
+int spec_from_inv(const j2k_inv_params* p, bool want_planes, Spec& s) {
+    if (!p) return fail(J2K_ERR_INVALID_ARG, "params is NULL");
+    if (p->xtsiz <= 0 || p->ytsiz <= 0) return fail(J2K_ERR_INVALID_ARG, "invalid tile size %dx%d", p->xtsiz, p->ytsiz);
+    if (p->xosiz < 0 || p->yosiz < 0 || p->xtosiz < 0 || p->ytosiz < 0 || p->xtosiz > p->xosiz || p->ytosiz > p->yosiz)
+        return fail(J2K_ERR_INVALID_ARG, "invalid image / tile offsets");
+    int rc = validate_common(p->xsiz - p->xosiz, p->ysiz - p->yosiz, p->components, p->bit_depth, p->num_levels);
+    if (rc) return rc;
+    if (p->n_steps < 0 || p->n_steps > J2K_MAX_BANDS) return fail(J2K_ERR_INVALID_ARG, "n_steps out of range");
+    s = Spec{};
+    s.fwd = false; s.W = p->xsiz - p->xosiz; s.H = p->ysiz - p->yosiz; s.C = p->components; s.bit_depth = p->bit_depth;
+    s.is_signed = p->is_signed != 0; s.L = p->num_levels; s.reversible = p->reversible != 0; s.htj2k = p->htj2k != 0; s.mct_mode = p->mct_mode;
+    inv_tiles(p, &s.tiles);
+    s.n_steps = p->n_steps; memcpy(s.steps, p->steps, sizeof s.steps);
+    s.fuse_shift = p->fuse_t1_halve != 0; s.planar_in = false; s.direct = false; s.want_planes = want_planes;
+    s.mct_matrix = p->mct_matrix; s.mct_has_offsets = p->mct_has_offsets; s.mct_offsets = p->mct_offsets;
+    s.n_bindings = p->n_bindings; s.bindings = p->bindings;
+    return 0;
+}
+
+int get_plan(DeviceCtx& d, const Spec& s, const void* pblob, size_t pbytes, int nframes, long long frame_samples, Plan** out) {
+    std::string key((const char*)pblob, pbytes);
+    char tail[96];
+    snprintf(tail, sizeof tail, "|%d|%d|%lld|%d|%d|%d", s.fwd ? 1 : 0, nframes, frame_samples, s.planar_in ? 1 : 0, s.want_planes ? 1 : 0, s.direct ? 1 : 0);
+    key += tail;
+    auto it = d.plans.find(key);
+    if (it != d.plans.end()) { *out = it->second.get(); return 0; }
+    if (d.plans.size() >= 24) d.plans.clear();
+    std::unique_ptr<Plan> P(new Plan());
+    int rc = build_plan(s, nframes, frame_samples, *P);
+    if (rc) return rc;
+    *out = P.get();
+    d.plans[key] = std::move(P);
+    return 0;
+}
+
+int set_dev(j2k_ctx* ctx, int di) {
+    if (!ctx) return fail(J2K_ERR_INVALID_ARG, "context is NULL");
+    if (di < 0 || di >= (int)ctx->devs.size()) return fail(J2K_ERR_INVALID_ARG, "device index %d out of range", di);
+    CK(cudaSetDevice(ctx->devs[di].dev));
+    return 0;
+}
+
+// Frames [f0, f1) of a host batch on device di: H2D, run, D2H, double-buffered in sub-batches.
+struct HostJob {
+    bool fwd; bool planar;
+    const Spec* spec; const void* pblob; size_t pbytes;
+    const unsigned char* h_pix_in; unsigned char* h_pix_out; size_t frame_stride_bytes;
+    const int32_t* h_coef_in; int32_t* h_coef_out;
+    int32_t* h_planes;
+    size_t pix_bytes_per_frame; long long coeffs_per_frame;
+};
+
+int enqueue_host_job(j2k_ctx* ctx, int di, const HostJob& J, int f0, int f1, bool timing) {
+    DeviceCtx& d = ctx->devs[di];
+    int rc = set_dev(ctx, di);
+    if (rc) return rc;
+    const int n = f1 - f0;
+    if (n <= 0) return 0;
+    const Spec& s = *J.spec;
+    const long long HW = (long long)s.W * s.H;
+    // sub-batches: enough frames per launch to fill the GPU, at least two to overlap copies with kernels
+    long long frame_samples_total = HW * s.C;
+    int sub = (int)((64LL << 20) / (frame_samples_total > 0 ? frame_samples_total : 1));
+    if (sub < 1) sub = 1;
+    if (sub > n) sub = n;
+    if (timing) CK(cudaEventRecord(d.ev_t[0], d.s_h2d));
+    int it = 0;
+    for (int b = f0; b < f1; b += sub, it++) {
+        const int nb = (b + sub <= f1) ? sub : f1 - b;
+        const int slot = it & 1;
+        const size_t in_bytes = J.fwd ? (J.planar ? (size_t)nb * s.C * HW * 4 : (size_t)nb * J.pix_bytes_per_frame) : (size_t)nb * J.coeffs_per_frame * 4;
+        const size_t out_bytes = J.fwd ? (size_t)nb * J.coeffs_per_frame * 4 : (size_t)nb * J.pix_bytes_per_frame;
+        if ((rc = d.in[slot].ensure(in_bytes))) return rc;
+        if ((rc = d.out[slot].ensure(out_bytes))) return rc;
+        if (J.h_planes && (rc = d.planes[slot].ensure((size_t)nb * s.C * HW * 4))) return rc;
+        // the slot's previous kernel must have consumed `in`, its previous D2H must have drained `out`
+        if (d.ev_k_used[slot]) CK(cudaStreamWaitEvent(d.s_h2d, d.ev_k[slot], 0));
+        if (J.fwd) {
+            if (J.planar || J.frame_stride_bytes == J.pix_bytes_per_frame) {
+                const unsigned char* src = J.planar ? J.h_pix_in : J.h_pix_in + (size_t)b * J.frame_stride_bytes;
+                CK(cudaMemcpyAsync(d.in[slot].p, src, in_bytes, cudaMemcpyHostToDevice, d.s_h2d));
+            } else {
+                CK(cudaMemcpy2DAsync(d.in[slot].p, J.pix_bytes_per_frame, J.h_pix_in + (size_t)b * J.frame_stride_bytes, J.frame_stride_bytes,
+                                     J.pix_bytes_per_frame, nb, cudaMemcpyHostToDevice, d.s_h2d));
+            }
+        } else {
+            CK(cudaMemcpyAsync(d.in[slot].p, J.h_coef_in + (size_t)b * J.coeffs_per_frame, in_bytes, cudaMemcpyHostToDevice, d.s_h2d));
+        }
+        CK(cudaEventRecord(d.ev_in[slot], d.s_h2d));
+        CK(cudaStreamWaitEvent(d.s_main, d.ev_in[slot], 0));
+        if (d.ev_out_used[slot]) CK(cudaStreamWaitEvent(d.s_main, d.ev_out[slot], 0));
+        Plan* P = nullptr;
+        long long fs = J.fwd ? (J.planar ? 0 : (long long)(J.pix_bytes_per_frame / (s.bit_depth <= 8 ? 1 : 2))) : (long long)(J.pix_bytes_per_frame / (s.bit_depth <= 8 ? 1 : 2));
+        if ((rc = get_plan(d, s, J.pblob, J.pbytes, nb, fs, &P))) return rc;
+        if (timing && it == 0) CK(cudaEventRecord(d.ev_t[1], d.s_main));
+        if (J.fwd) rc = run_plan(ctx, *P, d.in[slot].p, d.out[slot].p, nullptr, J.planar, d.s_main);
+        else rc = run_plan(ctx, *P, d.out[slot].p, d.in[slot].p, J.h_planes ? d.planes[slot].p : nullptr, false, d.s_main);
+        if (rc < 0) return rc;
+        CK(cudaEventRecord(d.ev_k[slot], d.s_main));
+        d.ev_k_used[slot] = true;
+        CK(cudaStreamWaitEvent(d.s_d2h, d.ev_k[slot], 0));
+        if (J.fwd) {
+            CK(cudaMemcpyAsync(J.h_coef_out + (size_t)b * J.coeffs_per_frame, d.out[slot].p, out_bytes, cudaMemcpyDeviceToHost, d.s_d2h));
+        } else {
+            if (J.frame_stride_bytes == J.pix_bytes_per_frame)
+                CK(cudaMemcpyAsync(J.h_pix_out + (size_t)b * J.frame_stride_bytes, d.out[slot].p, out_bytes, cudaMemcpyDeviceToHost, d.s_d2h));
+            else
+                CK(cudaMemcpy2DAsync(J.h_pix_out + (size_t)b * J.frame_stride_bytes, J.frame_stride_bytes, d.out[slot].p, J.pix_bytes_per_frame,
+                                     J.pix_bytes_per_frame, nb, cudaMemcpyDeviceToHost, d.s_d2h));
+            if (J.h_planes)
+                CK(cudaMemcpyAsync(J.h_planes + (size_t)b * s.C * HW, d.planes[slot].p, (size_t)nb * s.C * HW * 4, cudaMemcpyDeviceToHost, d.s_d2h));
+        }
+        CK(cudaEventRecord(d.ev_out[slot], d.s_d2h));
+        d.ev_out_used[slot] = true;
+    }
+    if (timing) {
+        CK(cudaEventRecord(d.ev_t[2], d.s_main));
+        CK(cudaEventRecord(d.ev_t[3], d.s_d2h));
+    }
+    return 0;
+}
+
+int sync_dev(j2k_ctx* ctx, int di) {
+    int rc = set_dev(ctx, di);
+    if (rc) return rc;
+    DeviceCtx& d = ctx->devs[di];
+    CK(cudaStreamSynchronize(d.s_h2d));
+    CK(cudaStreamSynchronize(d.s_main));
+    CK(cudaStreamSynchronize(d.s_d2h));
+    return 0;
+}
+
+// Shards nframes over the devices in contiguous blocks (no collective), optionally waits.
+int run_host_batch(j2k_ctx* ctx, const HostJob& J, int nframes, bool wait, std::vector<int>* used) {
+    const int nd = (int)ctx->devs.size();
+    const int per = (nframes + nd - 1) / nd;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    long long l0 = ctx->launches.load();
+    int rc = 0;
+    for (int di = 0; di < nd && rc == 0; di++) {
+        int f0 = di * per, f1 = f0 + per > nframes ? nframes : f0 + per;
+        if (f0 >= f1) break;
+        rc = enqueue_host_job(ctx, di, J, f0, f1, wait && di == 0);
+        if (used) used->push_back(di);
+    }
+    if (!wait) return rc;
+    for (int di = 0; di < nd; di++) {
+        int f0 = di * per;
+        if (f0 >= nframes) break;
+        int r2 = sync_dev(ctx, di);
+        if (rc == 0) rc = r2;
+    }
+    if (rc == 0) {
+        DeviceCtx& d = ctx->devs[0];
+        j2k_timing t{};
+        cudaEventElapsedTime(&t.h2d_ms, d.ev_t[0], d.ev_t[1]);
+        cudaEventElapsedTime(&t.kernel_ms, d.ev_t[1], d.ev_t[2]);
+        cudaEventElapsedTime(&t.d2h_ms, d.ev_t[2], d.ev_t[3]);
+        cudaEventElapsedTime(&t.total_ms, d.ev_t[0], d.ev_t[3]);
+        t.kernel_launches = (int32_t)(ctx->launches.load() - l0);
+        ctx->last = t;
+    }
+    return rc;
+}
+
+size_t pix_bytes(int w, int h, int C, int B) { return (size_t)w * h * C * ((B + 7) / 8); }
+
+// small synchronous helper for the package-API entry points: upload n buffers, run `body`, download
+struct ApiIo { const void* h_in; void* h_out; size_t bytes; };
+
+}  // namespace
+
+// =================================================================== C ABI
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+int j2k_abi_version(void) { return J2K_B200_ABI_VERSION; }
+
+const char* j2k_last_error(j2k_ctx*) { return t_err.c_str(); }
+
+int j2k_init(j2k_ctx** out, const int* devices, int n_devices) {
+    if (!out) return fail(J2K_ERR_INVALID_ARG, "ctx out pointer is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0)
+        return fail(J2K_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    std::vector<int> ids;
+    if (n_devices <= 0) {
+        const char* env = getenv("J2K_B200_DEVICE");
+        ids.push_back(env ? atoi(env) : 0);
+    } else {
+        for (int i = 0; i < n_devices; i++) ids.push_back(devices ? devices[i] : i);
+    }
+    for (int id : ids) if (id < 0 || id >= count) return fail(J2K_ERR_INVALID_ARG, "device %d out of range (0..%d)", id, count - 1);
+    std::unique_ptr<j2k_ctx> ctx(new j2k_ctx());
+    ctx->devs.resize(ids.size());
+    for (size_t i = 0; i < ids.size(); i++) {
+        DeviceCtx& d = ctx->devs[i];
+        d.dev = ids[i];
+        CK(cudaSetDevice(d.dev));
+        CK(cudaStreamCreateWithFlags(&d.s_main, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&d.s_h2d, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&d.s_d2h, cudaStreamNonBlocking));
+        for (auto& ev : d.ev_t) CK(cudaEventCreate(&ev));
+        for (int k = 0; k < 2; k++) {
+            CK(cudaEventCreateWithFlags(&d.ev_in[k], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&d.ev_k[k], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&d.ev_out[k], cudaEventDisableTiming));
+        }
+    }
+    *out = ctx.release();
+    return J2K_OK;
+}
+
+void j2k_shutdown(j2k_ctx* ctx) {
+    if (!ctx) return;
+    for (auto& d : ctx->devs) {
+        cudaSetDevice(d.dev);
+        cudaStreamSynchronize(d.s_main); cudaStreamSynchronize(d.s_h2d); cudaStreamSynchronize(d.s_d2h);
+        d.plans.clear();
+        for (auto& b : d.in) b.release();
+        for (auto& b : d.out) b.release();
+        for (auto& b : d.planes) b.release();
+        for (auto& b : d.api) b.release();
+        for (auto& ev : d.ev_t) if (ev) cudaEventDestroy(ev);
+        for (int k = 0; k < 2; k++) { cudaEventDestroy(d.ev_in[k]); cudaEventDestroy(d.ev_k[k]); cudaEventDestroy(d.ev_out[k]); }
+        cudaStreamDestroy(d.s_main); cudaStreamDestroy(d.s_h2d); cudaStreamDestroy(d.s_d2h);
+    }
+    for (void* p : ctx->pinned) cudaFreeHost(p);
+    for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
+    delete ctx;
+}
+
+int j2k_device_count(const j2k_ctx* ctx) { return ctx ? (int)ctx->devs.size() : 0; }
+int64_t j2k_launch_count(const j2k_ctx* ctx) { return ctx ? (int64_t)ctx->launches.load() : 0; }
+
+int j2k_last_timing(j2k_ctx* ctx, j2k_timing* out) {
+    if (!ctx || !out) return fail(J2K_ERR_INVALID_ARG, "NULL argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    *out = ctx->last;
+    return J2K_OK;
+}
+
+int j2k_set_profiling(j2k_ctx* ctx, int enabled) {
+    if (!ctx) return fail(J2K_ERR_INVALID_ARG, "context is NULL");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->profiling = enabled != 0;
+    return J2K_OK;
+}
+
+int j2k_get_profile(j2k_ctx* ctx, float* ms, int32_t* levels, int max) {
+    if (!ctx || !ms || max < 0) return fail(J2K_ERR_INVALID_ARG, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    int n = (int)ctx->prof_level.size();
+    if (n == 0) return 0;
+    CK(cudaStreamSynchronize(ctx->prof_stream));
+    for (int i = 0; i < n && i < max; i++) {
+        CK(cudaEventElapsedTime(&ms[i], ctx->prof_ev[2 * i], ctx->prof_ev[2 * i + 1]));
+        if (levels) levels[i] = ctx->prof_level[i];
+    }
+    return n;
+}
+
+void* j2k_acquire_buffer(j2k_ctx* ctx, size_t nbytes) {
+    if (!ctx || nbytes == 0) { fail(J2K_ERR_INVALID_ARG, "NULL context or zero size"); return nullptr; }
+    void* p = nullptr;
+    cudaSetDevice(ctx->devs[0].dev);
+    cudaError_t e = cudaHostAlloc(&p, nbytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) { fail(J2K_ERR_NOMEM, "cudaHostAlloc(%zu) failed: %s", nbytes, cudaGetErrorString(e)); return nullptr; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->pinned.push_back(p);
+    return p;
+}
+
+void j2k_release_buffer(j2k_ctx* ctx, void* p) {
+    if (!ctx || !p) return;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    for (size_t i = 0; i < ctx->pinned.size(); i++)
+        if (ctx->pinned[i] == p) { ctx->pinned.erase(ctx->pinned.begin() + (long)i); cudaFreeHost(p); return; }
+}
+
+// ---- sizes
+
+size_t j2k_fwd_pixel_bytes(const j2k_fwd_params* p) { return p ? pix_bytes(p->width, p->height, p->components, p->bit_depth) : 0; }
+size_t j2k_fwd_coeff_count(const j2k_fwd_params* p) { return p ? (size_t)p->width * p->height * p->components : 0; }
+size_t j2k_inv_pixel_bytes(const j2k_inv_params* p) { return p ? pix_bytes(p->xsiz - p->xosiz, p->ysiz - p->yosiz, p->components, p->bit_depth) : 0; }
+size_t j2k_inv_coeff_count(const j2k_inv_params* p) { return p ? (size_t)(p->xsiz - p->xosiz) * (p->ysiz - p->yosiz) * p->components : 0; }
+
+int j2k_fwd_tile_bounds(const j2k_fwd_params* p, int idx, int32_t b[4]) {
+    if (!p) return fail(J2K_ERR_INVALID_ARG, "params is NULL");
+    std::vector<TileGeom> t;
+    int n = fwd_tiles(p, &t);
+    if (b && idx >= 0 && idx < n) { b[0] = t[idx].x0; b[1] = t[idx].y0; b[2] = t[idx].x0 + t[idx].tw; b[3] = t[idx].y0 + t[idx].th; }
+    return n;
+}
+int j2k_inv_tile_bounds(const j2k_inv_params* p, int idx, int32_t b[4]) {
+    if (!p) return fail(J2K_ERR_INVALID_ARG, "params is NULL");
+    if (p->xtsiz <= 0 || p->ytsiz <= 0) return fail(J2K_ERR_INVALID_ARG, "invalid tile size");
+    std::vector<TileGeom> t;
+    int n = inv_tiles(p, &t);
+    if (b && idx >= 0 && idx < n) { b[0] = t[idx].x0; b[1] = t[idx].y0; b[2] = t[idx].x0 + t[idx].tw; b[3] = t[idx].y0 + t[idx].th; }
+    return n;
+}
+
+// ---- forward
+
+static int forward_host(j2k_ctx* ctx, const j2k_fwd_params* p, int nframes, const void* pixels, size_t stride, int32_t* coeffs_out,
+                        bool planar, bool wait, std::vector<int>* used) {
+    if (!ctx) return fail(J2K_ERR_INVALID_ARG, "context is NULL");
+    Spec s;
+    int rc = spec_from_fwd(p, planar, s);
+    if (rc) return rc;
+    if (!pixels || !coeffs_out) return fail(J2K_ERR_INVALID_ARG, "NULL buffer");
+    if (nframes <= 0) return fail(J2K_ERR_INVALID_ARG, "nframes must be positive");
+    HostJob J{};
+    J.fwd = true; J.planar = planar; J.spec = &s; J.pblob = p; J.pbytes = sizeof *p;
+    J.h_pix_in = (const unsigned char*)pixels; J.h_coef_out = coeffs_out;
+    J.pix_bytes_per_frame = j2k_fwd_pixel_bytes(p); J.coeffs_per_frame = (long long)j2k_fwd_coeff_count(p);
+    J.frame_stride_bytes = planar ? 0 : stride;
+    if (!planar && stride < J.pix_bytes_per_frame) return fail(J2K_ERR_SIZE, "frame stride %zu smaller than a frame (%zu bytes)", stride, J.pix_bytes_per_frame);
+    return run_host_batch(ctx, J, nframes, wait, used);
+}
+
+int j2k_forward(j2k_ctx* ctx, const j2k_fwd_params* p, const void* pixels, size_t nbytes, int32_t* coeffs_out, size_t ncoeffs) {
+    if (!p) return fail(J2K_ERR_INVALID_ARG, "params is NULL");
+    size_t need = j2k_fwd_pixel_bytes(p);
+    if (nbytes < need) return fail(J2K_ERR_SIZE, "insufficient pixel data: got %zu bytes, need %zu", nbytes, need);  // encoder.go:346-348
+    if (ncoeffs < j2k_fwd_coeff_count(p)) return fail(J2K_ERR_SIZE, "coefficient buffer too small: got %zu, need %zu", ncoeffs, j2k_fwd_coeff_count(p));
+    return forward_host(ctx, p, 1, pixels, need, coeffs_out, false, true, nullptr);
+}
+
+int j2k_forward_planar(j2k_ctx* ctx, const j2k_fwd_params* p, const int32_t* const* planes, int32_t* coeffs_out, size_t ncoeffs) {
+    if (!p || !planes) return fail(J2K_ERR_INVALID_ARG, "NULL argument");
+    int rc = validate_common(p->width, p->height, p->components, p->bit_depth, p->num_levels);
+    if (rc) return rc;
+    if (ncoeffs < j2k_fwd_coeff_count(p)) return fail(J2K_ERR_SIZE, "coefficient buffer too small");
+    size_t hw = (size_t)p->width * p->height;
+    std::vector<int32_t> packed(hw * p->components);  // gather the component slices (they are separate Go slices)
+    for (int c = 0; c < p->components; c++) {
+        if (!planes[c]) return fail(J2K_ERR_INVALID_ARG, "component %d is NULL", c);
+        memcpy(packed.data() + c * hw, planes[c], hw * 4);
+    }
+    return forward_host(ctx, p, 1, packed.data(), 0, coeffs_out, true, true, nullptr);
+}
+
+int j2k_forward_batch(j2k_ctx* ctx, const j2k_fwd_params* p, int nframes, const void* pixels, size_t frame_stride_bytes, int32_t* coeffs_out) {
+    return forward_host(ctx, p, nframes, pixels, frame_stride_bytes, coeffs_out, false, true, nullptr);
+}
+
+int j2k_forward_device(j2k_ctx* ctx, int dev, const j2k_fwd_params* p, int nframes, const void* d_pixels, size_t frame_stride_bytes,
+                       int32_t* d_coeffs, void* cuda_stream) {
+    int rc = set_dev(ctx, dev);
+    if (rc) return rc;
+    Spec s;
+    if ((rc = spec_from_fwd(p, false, s))) return rc;
+    if (!d_pixels || !d_coeffs || nframes <= 0) return fail(J2K_ERR_INVALID_ARG, "bad device buffers / nframes");
+    int bps = s.bit_depth <= 8 ? 1 : 2;
+    if (frame_stride_bytes < j2k_fwd_pixel_bytes(p) || frame_stride_bytes % bps) return fail(J2K_ERR_SIZE, "bad frame stride");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceCtx& d = ctx->devs[dev];
+    Plan* P = nullptr;
+    if ((rc = get_plan(d, s, p, sizeof *p, nframes, (long long)(frame_stride_bytes / bps), &P))) return rc;
+    rc = run_plan(ctx, *P, (void*)d_pixels, d_coeffs, nullptr, false, cuda_stream ? (cudaStream_t)cuda_stream : d.s_main);
+    return rc < 0 ? rc : J2K_OK;
+}
+
+// ---- inverse
+
+static int inverse_host(j2k_ctx* ctx, const j2k_inv_params* p, int nframes, const int32_t* coeffs_in, void* pixels_out, size_t stride,
+                        int32_t* planes_out, bool wait, std::vector<int>* used) {
+    if (!ctx) return fail(J2K_ERR_INVALID_ARG, "context is NULL");
+    Spec s;
+    int rc = spec_from_inv(p, planes_out != nullptr, s);
+    if (rc) return rc;
+    if (!coeffs_in || !pixels_out) return fail(J2K_ERR_INVALID_ARG, "NULL buffer");
+    if (nframes <= 0) return fail(J2K_ERR_INVALID_ARG, "nframes must be positive");
+    HostJob J{};
+    J.fwd = false; J.planar = false; J.spec = &s; J.pblob = p; J.pbytes = sizeof *p;
+    J.h_coef_in = coeffs_in; J.h_pix_out = (unsigned char*)pixels_out; J.h_planes = planes_out;
+    J.pix_bytes_per_frame = j2k_inv_pixel_bytes(p); J.coeffs_per_frame = (long long)j2k_inv_coeff_count(p);
+    J.frame_stride_bytes = stride;
+    if (stride < J.pix_bytes_per_frame) return fail(J2K_ERR_SIZE, "frame stride smaller than a frame");
+    return run_host_batch(ctx, J, nframes, wait, used);
+}
+
+int j2k_inverse(j2k_ctx* ctx, const j2k_inv_params* p, const int32_t* coeffs_in, size_t ncoeffs, void* pixels_out, size_t nbytes,
+                int32_t* planes_out) {
+    if (!p) return fail(J2K_ERR_INVALID_ARG, "params is NULL");
+    if (ncoeffs < j2k_inv_coeff_count(p)) return fail(J2K_ERR_SIZE, "coefficient buffer too small: got %zu, need %zu", ncoeffs, j2k_inv_coeff_count(p));
+    size_t need = j2k_inv_pixel_bytes(p);
+    if (nbytes < need) return fail(J2K_ERR_SIZE, "pixel buffer too small: got %zu bytes, need %zu", nbytes, need);
+    return inverse_host(ctx, p, 1, coeffs_in, pixels_out, need, planes_out, true, nullptr);
+}
+
+int j2k_inverse_batch(j2k_ctx* ctx, const j2k_inv_params* p, int nframes, const int32_t* coeffs_in, void* pixels_out,
+                      size_t frame_stride_bytes, int32_t* planes_out) {
+    return inverse_host(ctx, p, nframes, coeffs_in, pixels_out, frame_stride_bytes, planes_out, true, nullptr);
+}
+
+int j2k_inverse_device(j2k_ctx* ctx, int dev, const j2k_inv_params* p, int nframes, const int32_t* d_coeffs, void* d_pixels,
+                       size_t frame_stride_bytes, int32_t* d_planes, void* cuda_stream) {
+    int rc = set_dev(ctx, dev);
+    if (rc) return rc;
+    Spec s;
+    if ((rc = spec_from_inv(p, d_planes != nullptr, s))) return rc;
+    if (!d_pixels || !d_coeffs || nframes <= 0) return fail(J2K_ERR_INVALID_ARG, "bad device buffers / nframes");
+    int bps = s.bit_depth <= 8 ? 1 : 2;
+    if (frame_stride_bytes < j2k_inv_pixel_bytes(p) || frame_stride_bytes % bps) return fail(J2K_ERR_SIZE, "bad frame stride");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceCtx& d = ctx->devs[dev];
+    Plan* P = nullptr;
+    if ((rc = get_plan(d, s, p, sizeof *p, nframes, (long long)(frame_stride_bytes / bps), &P))) return rc;
+    rc = run_plan(ctx, *P, d_pixels, (void*)d_coeffs, d_planes, false, cuda_stream ? (cudaStream_t)cuda_stream : d.s_main);
+    return rc < 0 ? rc : J2K_OK;
+}
+
+// ---- asynchronous
+
+int64_t j2k_submit_forward(j2k_ctx* ctx, const j2k_fwd_params* p, int nframes, const void* pixels, size_t frame_stride_bytes,
+                           int32_t* coeffs_out) {
+    std::vector<int> used;
+    int rc = forward_host(ctx, p, nframes, pixels, frame_stride_bytes, coeffs_out, false, false, &used);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    long long t = ctx->next_ticket++;
+    ctx->tickets[t] = used;
+    return t;
+}
+
+int64_t j2k_submit_inverse(j2k_ctx* ctx, const j2k_inv_params* p, int nframes, const int32_t* coeffs_in, void* pixels_out,
+                           size_t frame_stride_bytes, int32_t* planes_out) {
+    std::vector<int> used;
+    int rc = inverse_host(ctx, p, nframes, coeffs_in, pixels_out, frame_stride_bytes, planes_out, false, &used);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    long long t = ctx->next_ticket++;
+    ctx->tickets[t] = used;
+    return t;
+}
+
+int j2k_wait(j2k_ctx* ctx, int64_t ticket) {
+    if (!ctx) return fail(J2K_ERR_INVALID_ARG, "context is NULL");
+    std::vector<int> used;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        auto it = ctx->tickets.find(ticket);
+        if (it == ctx->tickets.end()) return fail(J2K_ERR_TICKET, "unknown ticket %lld", (long long)ticket);
+        used = it->second;
+        ctx->tickets.erase(it);
+    }
+    int rc = 0;
+    for (int di : used) { int r2 = sync_dev(ctx, di); if (!rc) rc = r2; }
+    return rc;
+}
+
+// ---- wavelet package API: in place on a host plane, origin (x0, y0), stride = width
+
+static int dwt_api(j2k_ctx* ctx, void* data, int width, int height, int levels, int x0, int y0, bool reversible, bool fwd) {
+    if (!ctx || !data) return fail(J2K_ERR_INVALID_ARG, "NULL argument");
+    if (width <= 0 || height <= 0) return fail(J2K_ERR_INVALID_ARG, "invalid dimensions: %dx%d", width, height);
+    if (levels < 0) levels = 0;
+    if (levels > 30) levels = 30;  // windows are 1x1 long before that
+    if (x0 < 0 || y0 < 0) return fail(J2K_ERR_INVALID_ARG, "negative origin");
+    int rc = set_dev(ctx, 0);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceCtx& d = ctx->devs[0];
+    Spec s{};
+    s.fwd = fwd; s.W = width; s.H = height; s.C = 1; s.bit_depth = 16; s.is_signed = 1; s.L = levels; s.reversible = reversible;
+    s.mct_mode = J2K_MCT_NONE; s.direct = true;
+    TileGeom g{0, 0, width, height, x0, y0, 0};
+    s.tiles.push_back(g);
+    struct { int w, h, l, x, y, r, f; } blob = {width, height, levels, x0 & 0xfffff, y0 & 0xfffff, reversible, fwd};
+    Plan* P = nullptr;
+    if ((rc = get_plan(d, s, &blob, sizeof blob, 1, (long long)width * height, &P))) return rc;
+    size_t bytes = (size_t)width * height * 4;
+    if ((rc = d.api[0].ensure(bytes)) || (rc = d.api[1].ensure(bytes))) return rc;
+    CK(cudaMemcpyAsync(d.api[0].p, data, bytes, cudaMemcpyHostToDevice, d.s_main));
+    // the untouched part of the plane (nothing, when at least one level runs) keeps the input values
+    CK(cudaMemcpyAsync(d.api[1].p, d.api[0].p, bytes, cudaMemcpyDeviceToDevice, d.s_main));
+    if (fwd) rc = run_plan(ctx, *P, d.api[0].p, d.api[1].p, nullptr, false, d.s_main);
+    else rc = run_plan(ctx, *P, nullptr, d.api[0].p, d.api[1].p, false, d.s_main);
+    if (rc < 0) return rc;
+    CK(cudaMemcpyAsync(data, d.api[1].p, bytes, cudaMemcpyDeviceToHost, d.s_main));
+    CK(cudaStreamSynchronize(d.s_main));
+    return J2K_OK;
+}
+
+int j2k_dwt53_forward(j2k_ctx* ctx, int32_t* data, int w, int h, int levels, int x0, int y0) { return dwt_api(ctx, data, w, h, levels, x0, y0, true, true); }
+int j2k_dwt53_inverse(j2k_ctx* ctx, int32_t* data, int w, int h, int levels, int x0, int y0) { return dwt_api(ctx, data, w, h, levels, x0, y0, true, false); }
+int j2k_dwt97_forward(j2k_ctx* ctx, float* data, int w, int h, int levels, int x0, int y0) { return dwt_api(ctx, data, w, h, levels, x0, y0, false, true); }
+int j2k_dwt97_inverse(j2k_ctx* ctx, float* data, int w, int h, int levels, int x0, int y0) { return dwt_api(ctx, data, w, h, levels, x0, y0, false, false); }
+
+// ---- pointwise package APIs
+
+static int api3(j2k_ctx* ctx, int op, size_t n, const int32_t* a, const int32_t* b, const int32_t* c, int32_t* x, int32_t* y, int32_t* z) {
+    if (!ctx) return fail(J2K_ERR_INVALID_ARG, "context is NULL");
+    if (n == 0) return J2K_OK;
+    if (!a || !b || !c || !x || !y || !z) return fail(J2K_ERR_INVALID_ARG, "NULL buffer");
+    int rc = set_dev(ctx, 0);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceCtx& d = ctx->devs[0];
+    const int32_t* hin[3] = {a, b, c};
+    int32_t* hout[3] = {x, y, z};
+    for (int i = 0; i < 6; i++) if ((rc = d.api[i].ensure(n * 4))) return rc;
+    for (int i = 0; i < 3; i++) CK(cudaMemcpyAsync(d.api[i].p, hin[i], n * 4, cudaMemcpyHostToDevice, d.s_main));
+    J2K_LAUNCH(color_api_kernel, (unsigned)((n + 255) / 256), 256, d.s_main, op, (long long)n, (const int*)d.api[0].p, (const int*)d.api[1].p,
+               (const int*)d.api[2].p, (int*)d.api[3].p, (int*)d.api[4].p, (int*)d.api[5].p);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    for (int i = 0; i < 3; i++) CK(cudaMemcpyAsync(hout[i], d.api[3 + i].p, n * 4, cudaMemcpyDeviceToHost, d.s_main));
+    CK(cudaStreamSynchronize(d.s_main));
+    return J2K_OK;
+}
+
+int j2k_rct_forward(j2k_ctx* ctx, size_t n, const int32_t* r, const int32_t* g, const int32_t* b, int32_t* y, int32_t* cb, int32_t* cr) { return api3(ctx, 0, n, r, g, b, y, cb, cr); }
+int j2k_rct_inverse(j2k_ctx* ctx, size_t n, const int32_t* y, const int32_t* cb, const int32_t* cr, int32_t* r, int32_t* g, int32_t* b) { return api3(ctx, 1, n, y, cb, cr, r, g, b); }
+int j2k_ict_forward(j2k_ctx* ctx, size_t n, const int32_t* r, const int32_t* g, const int32_t* b, int32_t* y, int32_t* cb, int32_t* cr) { return api3(ctx, 2, n, r, g, b, y, cb, cr); }
+int j2k_ict_inverse(j2k_ctx* ctx, size_t n, const int32_t* y, const int32_t* cb, const int32_t* cr, int32_t* r, int32_t* g, int32_t* b) { return api3(ctx, 3, n, y, cb, cr, r, g, b); }
+
+static int api1(j2k_ctx* ctx, int op, const void* in, void* out, size_t n, double step) {
+    if (!ctx) return fail(J2K_ERR_INVALID_ARG, "context is NULL");
+    if (n == 0) return J2K_OK;
+    if (!in || !out) return fail(J2K_ERR_INVALID_ARG, "NULL buffer");
+    if (op < 2 && step <= 0) { memmove(out, in, n * 4); return J2K_OK; }  // quantization.go:311-314,327-330: returns the input
+    int rc = set_dev(ctx, 0);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceCtx& d = ctx->devs[0];
+    if ((rc = d.api[0].ensure(n * 4)) || (rc = d.api[1].ensure(n * 4))) return rc;
+    CK(cudaMemcpyAsync(d.api[0].p, in, n * 4, cudaMemcpyHostToDevice, d.s_main));
+    unsigned grid = (unsigned)((n + 255) / 256);
+    if (op < 2) J2K_LAUNCH(quant_api_kernel, grid, 256, d.s_main, op, (long long)n, (const int*)d.api[0].p, (int*)d.api[1].p, step);
+    else J2K_LAUNCH(f32_to_i32_kernel, grid, 256, d.s_main, (const float*)d.api[0].p, (int*)d.api[1].p, (long long)n);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    CK(cudaMemcpyAsync(out, d.api[1].p, n * 4, cudaMemcpyDeviceToHost, d.s_main));
+    CK(cudaStreamSynchronize(d.s_main));
+    return J2K_OK;
+}
+
+int j2k_quantize_coefficients(j2k_ctx* ctx, const int32_t* in, int32_t* out, size_t n, double step) { return api1(ctx, 0, in, out, n, step); }
+int j2k_dequantize_coefficients(j2k_ctx* ctx, const int32_t* in, int32_t* out, size_t n, double step) { return api1(ctx, 1, in, out, n, step); }
+int j2k_convert_f32_to_i32(j2k_ctx* ctx, const float* in, int32_t* out, size_t n) { return api1(ctx, 2, in, out, n, 1.0); }
+
+// ---- quantization.go scalar metadata (host only)
+
+static const double kNorms97[4][10] = {  // quantization.go:17-22
+    {1.000, 1.965, 4.177, 8.403, 16.90, 33.84, 67.69, 135.3, 270.6, 540.9},
+    {2.022, 3.989, 8.355, 17.04, 34.27, 68.63, 137.3, 274.6, 549.0, 0.0},
+    {2.022, 3.989, 8.355, 17.04, 34.27, 68.63, 137.3, 274.6, 549.0, 0.0},
+    {2.080, 3.865, 8.307, 17.18, 34.71, 69.59, 139.3, 278.6, 557.2, 0.0},
+};
+
+static double norm97(int level, int orient) {  // quantization.go:39-52
+    if (level < 0) level = 0;
+    if (orient == 0 && level >= 10) level = 9;
+    else if (orient > 0 && level >= 9) level = 8;
+    if (orient < 0 || orient > 3) return 1.0;
+    return kNorms97[orient][level];
+}
+
+static void band_params(int idx, int L, int* orient, int* level) {  // quantization.go:68-83
+    int resno = 0;
+    if (idx == 0) *orient = 0;
+    else { resno = (idx - 1) / 3 + 1; *orient = (idx - 1) % 3 + 1; }
+    *level = L - resno;
+    if (*level < 0) *level = 0;
+}
+
+static uint16_t encode_step(double step, int numbps) {  // quantization.go:102-128
+    if (step <= 0) return 0;
+    int32_t fixed = (int32_t)floor(step * 8192.0);
+    if (fixed <= 0) fixed = 1;
+    int lg = 0;
+    for (uint32_t v = (uint32_t)fixed; v > 1; v >>= 1) lg++;
+    int pw = lg - 13, n = 11 - lg;
+    int32_t mant = n < 0 ? (fixed >> -n) : (int32_t)((uint32_t)fixed << n);
+    mant &= 0x7ff;
+    int expn = numbps - pw;
+    if (expn < 0) expn = 0;
+    if (expn > 0x1f) expn = 0x1f;
+    return (uint16_t)((expn << 11) | mant);
+}
+
+int j2k_quant_openjpeg_params(int L, int bit_depth, uint16_t* encoded, double* step_sizes) {
+    if (!encoded || !step_sizes) return fail(J2K_ERR_INVALID_ARG, "NULL argument");
+    if (L < 0) L = 0;
+    if (L > J2K_MAX_LEVELS) return fail(J2K_ERR_INVALID_ARG, "too many levels");
+    int nb = 3 * L + 1;
+    for (int b = 0; b < nb; b++) {
+        int o, lv;
+        band_params(b, L, &o, &lv);
+        double norm = norm97(lv, o), st = 1.0;
+        if (norm > 0) st = 1.0 / norm;
+        step_sizes[b] = st;
+        encoded[b] = encode_step(st, bit_depth);
+    }
+    return nb;
+}
+
+int j2k_quant_quality_params(int quality, int L, int bit_depth, uint16_t* encoded, double* step_sizes) {
+    if (!encoded || !step_sizes) return fail(J2K_ERR_INVALID_ARG, "NULL argument");
+    if (L > J2K_MAX_LEVELS) return fail(J2K_ERR_INVALID_ARG, "too many levels");
+    if (quality < 1) quality = 1;
+    if (quality > 100) quality = 100;
+    double scale = pow(2.0, (100.0 - (double)quality) / 12.5);  // quantization.go:54-66
+    if (scale < 0.01) scale = 0.01;
+    scale *= 0.05;
+    int nb;
+    if (L <= 0) { nb = 1; step_sizes[0] = scale; }
+    else {
+        nb = 3 * L + 1;
+        for (int b = 0; b < nb; b++) {
+            int o, lv;
+            band_params(b, L, &o, &lv);
+            double norm = norm97(lv, o);
+            step_sizes[b] = norm <= 0 ? scale : scale / norm;
+        }
+    }
+    for (int b = 0; b < nb; b++) encoded[b] = encode_step(step_sizes[b], bit_depth);
+    return nb;
+}
+
+int j2k_quant_runtime_steps(const uint16_t* encoded, int n, int L, int bit_depth, double* steps) {
+    if (!encoded || !steps || n < 0) return fail(J2K_ERR_INVALID_ARG, "bad argument");
+    for (int i = 0; i < n; i++) {
+        int o, lv;
+        band_params(i, L, &o, &lv);
+        int gain = o == 3 ? 2 : (o == 1 || o == 2) ? 1 : 0;
+        int expn = (encoded[i] >> 11) & 0x1f;
+        double mant = (double)(encoded[i] & 0x7ff);
+        steps[i] = (double)(float)ldexp(1.0 + mant / 2048.0, bit_depth + gain - expn);  // quantization.go:130-135,151
+    }
+    return n;
+}
+
+int j2k_quant_decode_steps(const uint16_t* encoded, int n, int L, int bit_depth, int reversible, double* steps) {
+    (void)L;
+    if (!encoded || !steps || n < 0) return fail(J2K_ERR_INVALID_ARG, "bad argument");
+    for (int i = 0; i < n; i++) {
+        int expn = (encoded[i] >> 11) & 0x1f, mant = encoded[i] & 0x7ff;
+        int gain = 0;
+        if (reversible && i != 0) gain = ((i - 1) % 3 + 1) == 3 ? 2 : 1;  // t2/tile_decoder.go:1048-1060
+        steps[i] = ldexp(1.0 + (double)mant / 2048.0, bit_depth + gain - expn);  // t2/tile_decoder.go:1062-1065
+    }
+    return n;
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

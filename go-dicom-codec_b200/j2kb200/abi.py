@@ -167,7 +167,7 @@ LIB_PATH = os.path.join(os.path.dirname(_PKG_DIR), "csrc", "build", "libj2kb200.
 # every symbol include/j2k_b200.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = [
     "j2k_init", "j2k_shutdown", "j2k_last_error", "j2k_abi_version", "j2k_device_count", "j2k_launch_count",
-    "j2k_last_timing", "j2k_acquire_buffer", "j2k_release_buffer",
+    "j2k_last_timing", "j2k_set_profiling", "j2k_get_profile", "j2k_acquire_buffer", "j2k_release_buffer",
     "j2k_fwd_pixel_bytes", "j2k_fwd_coeff_count", "j2k_inv_pixel_bytes", "j2k_inv_coeff_count",
     "j2k_fwd_tile_bounds", "j2k_inv_tile_bounds",
     "j2k_forward", "j2k_forward_planar", "j2k_forward_batch", "j2k_forward_device",
@@ -179,19 +179,23 @@ EXPORTED_SYMBOLS = [
     "j2k_quant_openjpeg_params", "j2k_quant_quality_params", "j2k_quant_runtime_steps", "j2k_quant_decode_steps",
 ]
 
-_lib = None
+_libs = {}
 
 
-def load() -> C.CDLL:
-    """Load libj2kb200.so and declare the prototypes.  Raises if it is not built."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
+def load(path: str | None = None) -> C.CDLL:
+    """Load libj2kb200.so and declare the prototypes.  Raises if it is not built.
+
+    `path` exists for the test-suite's CPU emulator build of the same sources (tests/emu);
+    the product always loads LIB_PATH.
+    """
+    path = path or LIB_PATH
+    if path in _libs:
+        return _libs[path]
+    if not os.path.exists(path):
         raise RuntimeError(
-            f"{LIB_PATH} is missing: the CUDA extension is the product and has no fallback; "
+            f"{path} is missing: the CUDA extension is the product and has no fallback; "
             "build it with `python -c 'import __graft_entry__ as g; g.build()'`")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     vp, i32p, f32p, u16p, f64p = C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_float), C.POINTER(C.c_uint16), C.POINTER(C.c_double)
     sz, ci = C.c_size_t, C.c_int
     FP, IP = C.POINTER(FwdParams), C.POINTER(InvParams)
@@ -203,6 +207,8 @@ def load() -> C.CDLL:
         "j2k_device_count": (ci, [vp]),
         "j2k_launch_count": (C.c_int64, [vp]),
         "j2k_last_timing": (ci, [vp, C.POINTER(Timing)]),
+        "j2k_set_profiling": (ci, [vp, ci]),
+        "j2k_get_profile": (ci, [vp, f32p, i32p, ci]),
         "j2k_acquire_buffer": (vp, [vp, sz]),
         "j2k_release_buffer": (None, [vp, vp]),
         "j2k_fwd_pixel_bytes": (sz, [FP]),
@@ -241,5 +247,5 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError here == a declared symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    _lib = lib
+    _libs[path] = lib
     return lib

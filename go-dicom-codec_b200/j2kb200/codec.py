@@ -1,0 +1,238 @@
+"""Context: the ctypes face of libj2kb200.so (numpy in, numpy out; device pointers for resident data)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+
+
+class J2KError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"j2k_b200 error {code}: {msg}")
+        self.code = code
+
+
+def _vp(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+class Context:
+    """One library context (one or more CUDA devices).  Fails loudly without a device: no CPU fallback."""
+
+    def __init__(self, devices=None, lib_path: str | None = None):
+        self.lib = abi.load(lib_path)
+        h = C.c_void_p()
+        if devices is None:
+            rc = self.lib.j2k_init(C.byref(h), None, 0)
+        else:
+            arr = (C.c_int * len(devices))(*devices)
+            rc = self.lib.j2k_init(C.byref(h), arr, len(devices))
+        if rc != 0:
+            raise J2KError(rc, self.lib.j2k_last_error(None).decode())
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.j2k_shutdown(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        if rc < 0:
+            raise J2KError(rc, self.lib.j2k_last_error(self.h).decode())
+        return rc
+
+    # ---- bookkeeping
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.j2k_launch_count(self.h))
+
+    @property
+    def device_count(self) -> int:
+        return int(self.lib.j2k_device_count(self.h))
+
+    def last_timing(self) -> abi.Timing:
+        t = abi.Timing()
+        self._ck(self.lib.j2k_last_timing(self.h, C.byref(t)))
+        return t
+
+    def set_profiling(self, on: bool):
+        self._ck(self.lib.j2k_set_profiling(self.h, int(on)))
+
+    def get_profile(self, max_launches: int = 256):
+        """[(level, ms)] of the most recent profiled run (level 0 = pointwise kernel)."""
+        ms = (C.c_float * max_launches)()
+        lv = (C.c_int32 * max_launches)()
+        n = self._ck(self.lib.j2k_get_profile(self.h, ms, lv, max_launches))
+        return [(int(lv[i]), float(ms[i])) for i in range(min(n, max_launches))]
+
+    def pinned(self, nbytes: int, dtype=np.uint8) -> np.ndarray:
+        """A numpy view of library-owned pinned memory (j2k_acquire_buffer)."""
+        p = self.lib.j2k_acquire_buffer(self.h, nbytes)
+        if not p:
+            raise J2KError(abi.J2K_ERR_NOMEM, self.lib.j2k_last_error(self.h).decode())
+        buf = (C.c_uint8 * nbytes).from_address(p)
+        return np.frombuffer(buf, dtype=np.uint8).view(dtype)
+
+    def release(self, arr: np.ndarray):
+        self.lib.j2k_release_buffer(self.h, C.c_void_p(arr.ctypes.data))
+
+    # ---- forward
+    def forward(self, p: abi.FwdParams, pixels) -> np.ndarray:
+        px = np.ascontiguousarray(pixels).view(np.uint8).reshape(-1)
+        n = self.lib.j2k_fwd_coeff_count(C.byref(p))
+        out = np.empty(n, np.int32)
+        self._ck(self.lib.j2k_forward(self.h, C.byref(p), _vp(px), px.size, _vp(out), out.size))
+        return out
+
+    def forward_planar(self, p: abi.FwdParams, planes) -> np.ndarray:
+        pl = [np.ascontiguousarray(v, dtype=np.int32) for v in planes]
+        arr = (C.c_void_p * len(pl))(*[v.ctypes.data for v in pl])
+        out = np.empty(self.lib.j2k_fwd_coeff_count(C.byref(p)), np.int32)
+        self._ck(self.lib.j2k_forward_planar(self.h, C.byref(p), arr, _vp(out), out.size))
+        return out
+
+    def forward_batch(self, p: abi.FwdParams, frames: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        """frames: [nframes, frame_bytes] uint8 (row stride = frame stride)."""
+        assert frames.ndim == 2 and frames.dtype == np.uint8 and frames.strides[1] == 1
+        n = frames.shape[0]
+        nc = self.lib.j2k_fwd_coeff_count(C.byref(p))
+        if out is None:
+            out = np.empty((n, nc), np.int32)
+        self._ck(self.lib.j2k_forward_batch(self.h, C.byref(p), n, _vp(frames), frames.strides[0], _vp(out)))
+        return out
+
+    def submit_forward(self, p: abi.FwdParams, frames: np.ndarray, out: np.ndarray) -> int:
+        return self._ck(self.lib.j2k_submit_forward(self.h, C.byref(p), frames.shape[0], _vp(frames), frames.strides[0], _vp(out)))
+
+    def submit_inverse(self, p: abi.InvParams, coeffs: np.ndarray, out: np.ndarray) -> int:
+        return self._ck(self.lib.j2k_submit_inverse(self.h, C.byref(p), coeffs.shape[0], _vp(coeffs), _vp(out), out.strides[0], None))
+
+    def wait(self, ticket: int):
+        self._ck(self.lib.j2k_wait(self.h, ticket))
+
+    def forward_device(self, p: abi.FwdParams, nframes: int, d_pixels: int, frame_stride_bytes: int, d_coeffs: int,
+                       stream: int = 0, dev: int = 0):
+        self._ck(self.lib.j2k_forward_device(self.h, dev, C.byref(p), nframes, C.c_void_p(d_pixels), frame_stride_bytes,
+                                             C.c_void_p(d_coeffs), C.c_void_p(stream)))
+
+    # ---- inverse
+    def inverse(self, p: abi.InvParams, coeffs, want_planes: bool = False):
+        co = np.ascontiguousarray(coeffs, dtype=np.int32).reshape(-1)
+        nb = self.lib.j2k_inv_pixel_bytes(C.byref(p))
+        px = np.empty(nb, np.uint8)
+        w, h = p.xsiz - p.xosiz, p.ysiz - p.yosiz
+        planes = np.empty((p.components, h, w), np.int32) if want_planes else None
+        self._ck(self.lib.j2k_inverse(self.h, C.byref(p), _vp(co), co.size, _vp(px), px.size,
+                                      _vp(planes) if want_planes else None))
+        return (px, planes) if want_planes else px
+
+    def inverse_batch(self, p: abi.InvParams, coeffs: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        assert coeffs.ndim == 2 and coeffs.dtype == np.int32 and coeffs.flags.c_contiguous
+        n = coeffs.shape[0]
+        nb = self.lib.j2k_inv_pixel_bytes(C.byref(p))
+        if out is None:
+            out = np.empty((n, nb), np.uint8)
+        self._ck(self.lib.j2k_inverse_batch(self.h, C.byref(p), n, _vp(coeffs), _vp(out), out.strides[0], None))
+        return out
+
+    def inverse_device(self, p: abi.InvParams, nframes: int, d_coeffs: int, d_pixels: int, frame_stride_bytes: int,
+                       d_planes: int = 0, stream: int = 0, dev: int = 0):
+        self._ck(self.lib.j2k_inverse_device(self.h, dev, C.byref(p), nframes, C.c_void_p(d_coeffs), C.c_void_p(d_pixels),
+                                             frame_stride_bytes, C.c_void_p(d_planes) if d_planes else None, C.c_void_p(stream)))
+
+    # ---- wavelet package API
+    def _dwt(self, fn, data, levels, x0, y0, dtype):
+        a = np.ascontiguousarray(data, dtype=dtype).copy()
+        h, w = a.shape
+        self._ck(getattr(self.lib, fn)(self.h, _vp(a), w, h, levels, x0, y0))
+        return a
+
+    def dwt53_forward(self, data, levels, x0=0, y0=0):
+        return self._dwt("j2k_dwt53_forward", data, levels, x0, y0, np.int32)
+
+    def dwt53_inverse(self, data, levels, x0=0, y0=0):
+        return self._dwt("j2k_dwt53_inverse", data, levels, x0, y0, np.int32)
+
+    def dwt97_forward(self, data, levels, x0=0, y0=0):
+        return self._dwt("j2k_dwt97_forward", data, levels, x0, y0, np.float32)
+
+    def dwt97_inverse(self, data, levels, x0=0, y0=0):
+        return self._dwt("j2k_dwt97_inverse", data, levels, x0, y0, np.float32)
+
+    def convert_f32_to_i32(self, data):
+        a = np.ascontiguousarray(data, dtype=np.float32)
+        out = np.empty(a.shape, np.int32)
+        self._ck(self.lib.j2k_convert_f32_to_i32(self.h, _vp(a), _vp(out), a.size))
+        return out
+
+    # ---- colorspace / quantization package API
+    def _c3(self, fn, a, b, c):
+        a, b, c = (np.ascontiguousarray(v, dtype=np.int32) for v in (a, b, c))
+        o = [np.empty(a.shape, np.int32) for _ in range(3)]
+        self._ck(getattr(self.lib, fn)(self.h, a.size, _vp(a), _vp(b), _vp(c), _vp(o[0]), _vp(o[1]), _vp(o[2])))
+        return o
+
+    def rct_forward(self, r, g, b):
+        return self._c3("j2k_rct_forward", r, g, b)
+
+    def rct_inverse(self, y, cb, cr):
+        return self._c3("j2k_rct_inverse", y, cb, cr)
+
+    def ict_forward(self, r, g, b):
+        return self._c3("j2k_ict_forward", r, g, b)
+
+    def ict_inverse(self, y, cb, cr):
+        return self._c3("j2k_ict_inverse", y, cb, cr)
+
+    def quantize_coefficients(self, data, step):
+        a = np.ascontiguousarray(data, dtype=np.int32)
+        out = np.empty_like(a)
+        self._ck(self.lib.j2k_quantize_coefficients(self.h, _vp(a), _vp(out), a.size, float(step)))
+        return out
+
+    def dequantize_coefficients(self, data, step):
+        a = np.ascontiguousarray(data, dtype=np.int32)
+        out = np.empty_like(a)
+        self._ck(self.lib.j2k_dequantize_coefficients(self.h, _vp(a), _vp(out), a.size, float(step)))
+        return out
+
+
+# ---- scalar step tables (host only, no context needed)
+def openjpeg_quant_params(num_levels: int, bit_depth: int, lib_path: str | None = None):
+    lib = abi.load(lib_path)
+    n = 3 * max(num_levels, 0) + 1
+    enc, st = np.zeros(n, np.uint16), np.zeros(n, np.float64)
+    lib.j2k_quant_openjpeg_params(num_levels, bit_depth, enc.ctypes.data_as(C.POINTER(C.c_uint16)), st.ctypes.data_as(C.POINTER(C.c_double)))
+    return enc, st
+
+
+def quality_quant_params(quality: int, num_levels: int, bit_depth: int, lib_path: str | None = None):
+    lib = abi.load(lib_path)
+    n = 3 * max(num_levels, 0) + 1
+    enc, st = np.zeros(n, np.uint16), np.zeros(n, np.float64)
+    lib.j2k_quant_quality_params(quality, num_levels, bit_depth, enc.ctypes.data_as(C.POINTER(C.c_uint16)), st.ctypes.data_as(C.POINTER(C.c_double)))
+    return enc, st
+
+
+def runtime_quant_steps(encoded, num_levels: int, bit_depth: int, lib_path: str | None = None):
+    lib = abi.load(lib_path)
+    enc = np.ascontiguousarray(encoded, dtype=np.uint16)
+    st = np.zeros(enc.size, np.float64)
+    lib.j2k_quant_runtime_steps(enc.ctypes.data_as(C.POINTER(C.c_uint16)), enc.size, num_levels, bit_depth, st.ctypes.data_as(C.POINTER(C.c_double)))
+    return st
+
+
+def decode_quant_steps(encoded, num_levels: int, bit_depth: int, reversible: bool = False, lib_path: str | None = None):
+    lib = abi.load(lib_path)
+    enc = np.ascontiguousarray(encoded, dtype=np.uint16)
+    st = np.zeros(enc.size, np.float64)
+    lib.j2k_quant_decode_steps(enc.ctypes.data_as(C.POINTER(C.c_uint16)), enc.size, num_levels, bit_depth, int(reversible), st.ctypes.data_as(C.POINTER(C.c_double)))
+    return st

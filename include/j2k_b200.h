@@ -160,6 +160,12 @@ int j2k_device_count(const j2k_ctx* ctx);
 /* Total number of CUDA kernels this context has launched (bench.py's gpu_launches). */
 int64_t j2k_launch_count(const j2k_ctx* ctx);
 int j2k_last_timing(j2k_ctx* ctx, j2k_timing* out);
+/* Per-launch CUDA-event timing of plan runs (bench.py's roofline leg; off by default).  While
+ * enabled every kernel of a run is bracketed by events on the launching stream.
+ * j2k_get_profile synchronises and returns the launches of the most recent run: ms[i] is the
+ * duration, levels[i] the DWT level the kernel computed (1 = finest) or 0 for a pointwise kernel. */
+int j2k_set_profiling(j2k_ctx* ctx, int enabled);
+int j2k_get_profile(j2k_ctx* ctx, float* ms, int32_t* levels, int max);
 
 /* Library-owned pinned host memory (Go wraps it with unsafe.Slice). */
 void* j2k_acquire_buffer(j2k_ctx* ctx, size_t nbytes);

@@ -1,0 +1,54 @@
+"""Product sources (csrc/*.cu, *.cuh) compiled for the CPU emulator (tests/emu) vs the oracle.
+
+Covers the host logic (plans, tile classes, offset tables, kernel selection) and the kernels' index
+arithmetic and lifting order without a GPU.  Sizes are small: the emulator runs one lane at a time.
+The `-m gpu` suite repeats these through the real sm_100a build at full sizes."""
+import numpy as np
+import pytest
+
+import parity_cases as PC
+from j2kb200 import abi
+
+
+@pytest.fixture(scope="module")
+def ectx():
+    import emu_lib
+    import j2kb200
+    c = j2kb200.Context(lib_path=emu_lib.build())
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("w,h,levels,x0,y0", [
+    (16, 16, 1, 0, 0), (64, 64, 3, 0, 0), (17, 19, 3, 0, 0), (33, 17, 2, 1, 0), (20, 9, 4, 0, 1), (64, 48, 3, 1, 2),
+    (7, 1, 2, 0, 0), (1, 9, 3, 1, 1), (5, 5, 6, 3, 3), (2, 2, 3, 1, 1), (1, 1, 2, 1, 0), (13, 2, 5, 2, 7),
+    (130, 70, 5, 0, 0), (257, 3, 2, 0, 0), (3, 300, 3, 1, 0),
+])
+def test_wavelet_api(ectx, oracle, w, h, levels, x0, y0):
+    PC.check_wavelet_api(ectx, oracle, w, h, levels, x0, y0, seed=w * 1000 + h)
+
+
+@pytest.mark.parametrize("w,h,c,bits,signed,L,rev", [
+    (64, 64, 1, 8, False, 3, True), (64, 64, 1, 16, False, 5, True), (61, 47, 1, 16, True, 3, True),
+    (64, 64, 1, 12, False, 3, False), (67, 53, 1, 8, False, 2, False), (160, 40, 1, 16, False, 4, False),
+    (48, 40, 3, 8, False, 3, True), (48, 40, 3, 8, False, 3, False), (37, 29, 3, 16, False, 2, False),
+    (256, 8, 1, 16, False, 2, True), (256, 8, 1, 12, True, 2, False), (40, 40, 2, 8, False, 2, True),
+    (24, 24, 1, 8, False, 0, True), (24, 24, 1, 8, False, 0, False), (1, 1, 1, 8, False, 2, False),
+])
+def test_pipeline(ectx, oracle, w, h, c, bits, signed, L, rev):
+    PC.check_pipeline(ectx, oracle, w, h, c, bits, signed, L, rev)
+
+
+@pytest.mark.parametrize("w,h,c,tile,L,rev", [
+    (96, 64, 1, (32, 32), 2, True), (100, 70, 1, (48, 32), 3, False), (70, 50, 3, (32, 32), 2, False),
+    (65, 33, 3, (32, 32), 3, True), (50, 50, 1, (33, 17), 3, False), (33, 33, 1, (32, 32), 3, False),
+])
+def test_tiles(ectx, oracle, w, h, c, tile, L, rev):
+    PC.check_pipeline(ectx, oracle, w, h, c, 8, False, L, rev, tile=tile)
+
+
+def test_htj2k_and_fused_t1_shift(ectx, oracle):
+    PC.check_pipeline(ectx, oracle, 40, 36, 1, 16, False, 3, True, fuse=True)
+    PC.check_pipeline(ectx, oracle, 40, 36, 1, 16, False, 3, True, htj2k=True, fuse=True)
+    PC.check_pipeline(ectx, oracle, 40, 36, 1, 8, False, 3, False, htj2k=True)
+    PC.check_pipeline(ectx, oracle, 40, 36, 3, 8, False, 2, False, steps_kind="quality")

@@ -1,0 +1,115 @@
+"""GPU parity tests proper: libj2kb200.so (sm_100a) through the C ABI vs the oracle, same seeded inputs.
+
+Bit-exact everywhere (the 9/7 and ICT paths are built without FMA contraction, so they are exact too;
+the test would report the max-abs sub-band error otherwise)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import parity_cases as PC
+from j2kb200 import abi
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.mark.parametrize("w,h,levels,x0,y0", [
+    (16, 16, 1, 0, 0), (64, 64, 3, 0, 0), (17, 19, 3, 0, 0), (33, 17, 2, 1, 0), (20, 9, 4, 0, 1), (64, 48, 3, 1, 2),
+    (7, 1, 2, 0, 0), (1, 9, 3, 1, 1), (5, 5, 6, 3, 3), (2, 2, 3, 1, 1), (1, 1, 2, 1, 0), (13, 2, 5, 2, 7),
+    (256, 256, 6, 0, 0), (333, 211, 6, 0, 0), (888, 459, 5, 0, 0), (127, 129, 5, 1, 2), (1024, 768, 7, 0, 0), (100, 100, 1, 0, 0),
+])
+def test_wavelet_api(ctx, oracle, w, h, levels, x0, y0):
+    PC.check_wavelet_api(ctx, oracle, w, h, levels, x0, y0, seed=w * 1000 + h)
+
+
+@pytest.mark.parametrize("w,h,c,bits,signed,L,rev,kind", [
+    (512, 512, 1, 16, True, 5, True, "smooth"),      # C1
+    (512, 512, 1, 16, False, 5, True, "noise"),
+    (1024, 1024, 1, 12, False, 6, False, "smooth"),  # C2 shape at 1/16 area
+    (1024, 512, 1, 12, False, 6, False, "noise"),
+    (512, 384, 3, 8, False, 5, False, "smooth"),     # C3 (i)
+    (512, 384, 3, 8, False, 5, True, "smooth"),      # C3 (ii)
+    (333, 211, 1, 12, False, 6, False, "noise"), (127, 129, 3, 8, False, 5, True, "noise"),
+    (888, 459, 1, 16, False, 5, True, "smooth"), (640, 480, 3, 16, False, 4, False, "smooth"),
+    (300, 200, 2, 8, False, 3, True, "noise"), (300, 200, 4, 12, True, 3, False, "noise"),
+    (64, 64, 1, 8, False, 0, True, "noise"), (64, 64, 1, 8, False, 0, False, "noise"), (1, 1, 1, 8, False, 2, False, "noise"),
+    (2048, 64, 1, 16, False, 3, True, "smooth"), (64, 2048, 1, 12, False, 3, False, "smooth"),
+])
+def test_pipeline(ctx, oracle, w, h, c, bits, signed, L, rev, kind):
+    PC.check_pipeline(ctx, oracle, w, h, c, bits, signed, L, rev, kind=kind, seed=w + h)
+
+
+@pytest.mark.parametrize("w,h,c,tile,L,rev", [
+    (1024, 768, 1, (256, 256), 5, True), (1000, 700, 1, (256, 256), 5, False), (700, 500, 3, (256, 128), 4, False),
+    (513, 257, 3, (256, 256), 5, True), (500, 500, 1, (333, 177), 3, False), (2048, 2048, 3, (1024, 1024), 7, False),
+])
+def test_tiles(ctx, oracle, w, h, c, tile, L, rev):
+    PC.check_pipeline(ctx, oracle, w, h, c, 8, False, L, rev, tile=tile)
+
+
+def test_htj2k_and_fused_t1_shift(ctx, oracle):
+    PC.check_pipeline(ctx, oracle, 400, 360, 1, 16, False, 5, True, fuse=True)
+    PC.check_pipeline(ctx, oracle, 400, 360, 1, 16, False, 5, True, htj2k=True, fuse=True)
+    PC.check_pipeline(ctx, oracle, 400, 360, 1, 8, False, 5, False, htj2k=True)
+    PC.check_pipeline(ctx, oracle, 400, 360, 3, 8, False, 4, False, steps_kind="quality")
+
+
+def test_interop_raws(ctx, oracle):
+    man = json.load(open(os.path.join(HERE, "golden", "interop", "manifest.json")))
+    for fx in man["fixtures"]:
+        raw = np.fromfile(os.path.join(HERE, "golden", "interop", fx["name"] + ".raw"), np.uint8)
+        C = fx["components"]
+        mct = abi.MCT_RCT if C == 3 else abi.MCT_NONE
+        fp = abi.fwd_params(fx["width"], fx["height"], C, fx["bitsStored"], fx["signed"], num_levels=5, reversible=True, mct_mode=mct)
+        ip = abi.inv_params(fx["width"], fx["height"], C, fx["bitsStored"], fx["signed"], num_levels=5, reversible=True, mct_mode=mct)
+        co = ctx.forward(fp, raw)
+        assert np.array_equal(co, oracle.forward(fp, raw)), fx["name"]
+        assert np.array_equal(ctx.inverse(ip, co), raw), fx["name"]
+
+
+def test_batch_matches_single_and_roundtrip_at_full_size(ctx, oracle):
+    # C4-shaped batch: 64 frames 512x512 16-bit 5/3 L=5; frame 0 and 63 vs oracle, all frames by the identity property
+    rng = np.random.default_rng(1000)
+    n, w, h = 64, 512, 512
+    frames = rng.integers(0, 65536, (n, h * w), dtype=np.uint16).view(np.uint8).reshape(n, -1)
+    fp = abi.fwd_params(w, h, 1, 16, False, num_levels=5, reversible=True)
+    ip = abi.inv_params(w, h, 1, 16, False, num_levels=5, reversible=True)
+    co = ctx.forward_batch(fp, frames)
+    for f in (0, n - 1):
+        assert np.array_equal(co[f], oracle.forward(fp, frames[f]))
+    back = ctx.inverse_batch(ip, co)
+    assert np.array_equal(back, frames)
+    # C2 full size, 9/7 L=6: oracle on the full frame takes seconds
+    img = PC.synth(rng, 4096, 4096, 1, 12)
+    es, ds = PC.steps_for(oracle, 6, 12)
+    fp = abi.fwd_params(4096, 4096, 1, 12, False, num_levels=6, reversible=False, steps=es)
+    got = ctx.forward(fp, PC.raw_bytes(img))
+    want = oracle.forward(fp, PC.raw_bytes(img))
+    assert np.count_nonzero(got != want) == 0
+
+
+def test_async_tickets(ctx, oracle):
+    rng = np.random.default_rng(5)
+    n, w, h = 8, 256, 256
+    fp = abi.fwd_params(w, h, 1, 16, False, num_levels=5, reversible=True)
+    fin = ctx.pinned(n * w * h * 2).reshape(n, -1)
+    fout = ctx.pinned(n * w * h * 4, np.int32).reshape(n, -1)
+    fin[:] = rng.integers(0, 256, fin.shape, dtype=np.uint8)
+    t = ctx.submit_forward(fp, fin, fout)
+    ctx.wait(t)
+    assert np.array_equal(fout[3], oracle.forward(fp, fin[3]))
+    ctx.release(fin)
+    ctx.release(fout)
+
+
+def test_errors(ctx):
+    import j2kb200
+    fp = abi.fwd_params(64, 64, 1, 8, False, num_levels=3)
+    with pytest.raises(j2kb200.J2KError) as e:
+        ctx.forward(fp, np.zeros(100, np.uint8))
+    assert e.value.code == abi.J2K_ERR_SIZE and "insufficient pixel data" in str(e.value)
+    bad = abi.fwd_params(0, 64, 1, 8, False)
+    with pytest.raises(j2kb200.J2KError):
+        ctx.forward(bad, np.zeros(10, np.uint8))
