@@ -158,6 +158,8 @@ struct LevelLaunch {
     int x_buf, ll_buf, band_buf, planes_buf;
     int x_elem_bytes;           // element size of x_base for alignment checks
     int level;                  // 1 = finest
+    bool fast;                  // eligible for the fast-path kernel (FwdFast)
+    FastQ4 fq;
 };
 
 enum PwKind { PW_PREP, PW_FINALIZE, PW_QUANT_RECTS, PW_SHIFT, PW_COPY, PW_DEQUANT_RECTS };
@@ -247,6 +249,27 @@ cudaError_t launch_fwd_level(const LevelLaunch& l, const LevelArgs& a, cudaStrea
     FWD_CASE(97, 1, 1, IN_I32, MCTK_NONE) FWD_CASE(97, 2, 1, IN_I32, MCTK_NONE)
     FWD_CASE(97, 1, 1, IN_F32, MCTK_NONE) FWD_CASE(97, 2, 1, IN_F32, MCTK_NONE)
     FWD_CASE(97, 2, 3, IN_U8, MCTK_ICT) FWD_CASE(97, 2, 3, IN_U16, MCTK_ICT)
+    return cudaErrorInvalidDeviceFunction;
+}
+
+#define FAST_CASE(wt, np, nc, in, mct)                                                                  \
+    if (l.WT == wt && l.NP == np && l.NC == nc && l.KIND == in && l.MCT == mct) {                       \
+        J2K_LAUNCH((fwd_fast_kernel<wt, np, nc, in, mct>), J2K_GRID(a), 128, st, a, l.fq);              \
+        return cudaGetLastError();                                                                      \
+    }
+
+bool has_fwd_fast(const LevelLaunch& l) {
+    if (l.NC == 3) return l.NP == 2 && (l.KIND == IN_U8 || l.KIND == IN_U16);
+    if (l.KIND == IN_U8 || l.KIND == IN_U16) return l.NP == 4;
+    return l.NP == 2;
+}
+
+cudaError_t launch_fwd_fast(const LevelLaunch& l, const LevelArgs& a, cudaStream_t st) {
+    FAST_CASE(53, 4, 1, IN_U8, MCTK_NONE) FAST_CASE(53, 4, 1, IN_U16, MCTK_NONE) FAST_CASE(53, 2, 1, IN_I32, MCTK_NONE)
+    FAST_CASE(53, 2, 3, IN_U8, MCTK_RCT) FAST_CASE(53, 2, 3, IN_U16, MCTK_RCT)
+    FAST_CASE(97, 4, 1, IN_U8, MCTK_NONE) FAST_CASE(97, 4, 1, IN_U16, MCTK_NONE) FAST_CASE(97, 2, 1, IN_I32, MCTK_NONE)
+    FAST_CASE(97, 2, 1, IN_F32, MCTK_NONE)
+    FAST_CASE(97, 2, 3, IN_U8, MCTK_ICT) FAST_CASE(97, 2, 3, IN_U16, MCTK_ICT)
     return cudaErrorInvalidDeviceFunction;
 }
 
@@ -685,6 +708,20 @@ int build_plan(const Spec& s, int nframes, long long frame_samples, Plan& P) {
                            (a.ll.comp_stride % l.NP) == 0 && all_mult(H, o_ll, o_ll + n, l.NP);
                 a.vec_b = okb;
             }
+            l.fast = false;
+            if (s.fwd && a.vec_x && a.vec_b && g.px == 0 && !a.hskip && !a.vskip && has_fwd_fast(l)) {
+                const BandIO* bands[4] = {&a.ll, &a.hl, &a.lh_, &a.hh};
+                bool ok = true;
+                for (int bi = 0; bi < 4; bi++) {
+                    const BandIO& b = *bands[bi];
+                    FastQ& q = l.fq.q[bi];
+                    q.mode = b.mode; q.shift = 0; q.step = 1.f; q.rcp = 1.f;
+                    if (WT == 53) { if (b.mode == Q_SHIFT) q.shift = b.shift; else if (b.mode != Q_RAW) ok = false; }
+                    else if (b.mode == Q_QUANT) { q.step = b.step / b.scale; q.rcp = 1.0f / q.step; }  // scale is a power of two: exact
+                    else if (b.mode != Q_RAW) ok = false;
+                }
+                l.fast = ok;
+            }
             P.levels.push_back(l);
         }
 
@@ -799,8 +836,13 @@ int run_plan(j2k_ctx* ctx, Plan& P, void* pixels, void* coeffs, void* planes, bo
         a.planes_out = l.planes_buf ? (int32_t*)bufs[l.planes_buf] : nullptr;
         if (!aligned16(a.x_base)) a.vec_x = 0;
         if (!aligned16(a.ll.base) || !aligned16(a.hl.base)) a.vec_b = 0;
+        static const bool trace = getenv("J2K_B200_TRACE") != nullptr;
+        if (trace)
+            fprintf(stderr, "[j2k] %s level %d %dx%d WT=%d NP=%d NC=%d kind=%d mct=%d items=%d chunks=%d strips=%d vec_x=%d vec_b=%d fast=%d\n",
+                    P.fwd ? "fwd" : "inv", l.level, a.w, a.h, l.WT, l.NP, l.NC, l.KIND, l.MCT, a.n_items, a.nchunks, a.nstrips, a.vec_x, a.vec_b,
+                    (int)(l.fast && a.vec_x && a.vec_b));
         prof.begin(l.level);
-        cudaError_t e = P.fwd ? launch_fwd_level(l, a, st) : launch_inv_level(l, a, st);
+        cudaError_t e = P.fwd ? ((l.fast && a.vec_x && a.vec_b) ? launch_fwd_fast(l, a, st) : launch_fwd_level(l, a, st)) : launch_inv_level(l, a, st);
         prof.end();
         if (e != cudaSuccess)
             return fail(J2K_ERR_CUDA, "level kernel launch (WT=%d NP=%d NC=%d kind=%d mct=%d) failed: %s", l.WT, l.NP, l.NC, l.KIND, l.MCT,

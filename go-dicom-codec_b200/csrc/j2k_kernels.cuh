@@ -490,6 +490,259 @@ __global__ void __launch_bounds__(128) fwd_level_kernel(const __grid_constant__ 
     FwdLevel<WT, NP, NC, IN, MCT>::run(a);
 }
 
+// ------------------------------------------------------------------ forward level kernel, fast path
+//
+// Same algorithm and arithmetic as FwdLevel, specialised for the geometry every BASELINE config has on
+// its large levels: even column origin (px == 0), no 1-sample dimension, every row / plane / band
+// offset a multiple of the vector width.  What changes is only HOW the work is issued:
+//   * interior lanes move data with 128-bit (64-bit for u8) loads and stores through lane pointers
+//     that are computed once; only lanes that straddle the left / right image border fall back to the
+//     mirrored scalar path of FwdLevel;
+//   * the two rows of iteration t+1 are fetched into registers before iteration t is computed
+//     (software pipelining: two more independent 16-byte loads in flight per lane);
+//   * the quantizer is branch-free: q = rint(c / step') with step' = step / scale (a power of two, so
+//     (c / step) * scale == c / step' exactly) and the IEEE quotient from the correctly rounded
+//     reciprocal (Markstein), 3 flops + 1 convert per coefficient (tests/test_div_markstein.py).
+// Detail bands must be Q_QUANT / Q_RAW / Q_SHIFT; anything else stays on FwdLevel.
+
+struct FastQ {  // per band, precomputed on the host
+    float step, rcp;  // step' = step / scale, rcp = RN(1 / step')
+    int mode, shift;
+};
+
+template <int WT, int NP, int NC, int IN, int MCT>
+struct FwdFast {
+    typedef FwdLevel<WT, NP, NC, IN, MCT> Slow;
+    typedef typename Wt<WT>::T T;
+    static constexpr int LAG = Wt<WT>::LAG;
+    static constexpr int HLN = Slow::HLN, VP = Slow::VP, NS = Slow::NS;
+    static constexpr int ES = (IN == IN_U8) ? 1 : (IN == IN_U16 ? 2 : 4);
+    static constexpr int NW = NC * NS * ES / 4;  // 32-bit words per lane per row
+
+    static __device__ __forceinline__ void fetch(const unsigned char* p, unsigned (&w)[NW]) {
+        if constexpr (NW % 4 == 0) {
+#pragma unroll
+            for (int k = 0; k < NW / 4; k++) {
+                uint4 q = __ldg((const uint4*)p + k);
+                w[4 * k] = q.x; w[4 * k + 1] = q.y; w[4 * k + 2] = q.z; w[4 * k + 3] = q.w;
+            }
+        } else if constexpr (NW % 2 == 0) {
+#pragma unroll
+            for (int k = 0; k < NW / 2; k++) {
+                uint2 q = __ldg((const uint2*)p + k);
+                w[2 * k] = q.x; w[2 * k + 1] = q.y;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < NW; k++) w[k] = __ldg((const unsigned*)p + k);
+        }
+    }
+
+    // words -> level-shifted working values (+ forward MCT); `sgn` is warp-uniform
+    static __device__ __forceinline__ void unpack(const unsigned (&w)[NW], const RawFmt& r, T (&out)[NC][NS]) {
+        int v[NC][NS];
+#pragma unroll
+        for (int s = 0; s < NS; s++)
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                const int e = NC * s + c;  // element index inside the lane's span
+                if constexpr (IN == IN_U8) v[c][s] = (w[e >> 2] >> (8 * (e & 3))) & 0xFF;
+                else if constexpr (IN == IN_U16) v[c][s] = (e & 1) ? (w[e >> 1] >> 16) : (w[e >> 1] & 0xFFFF);
+                else v[c][s] = (int)w[e];
+            }
+        if constexpr (IN == IN_U8 || IN == IN_U16) {
+            if (r.sign_sub) {
+#pragma unroll
+                for (int c = 0; c < NC; c++)
+#pragma unroll
+                    for (int s = 0; s < NS; s++) v[c][s] = raw_to_int(v[c][s], r);
+            } else {
+#pragma unroll
+                for (int c = 0; c < NC; c++)
+#pragma unroll
+                    for (int s = 0; s < NS; s++) v[c][s] -= r.dc;
+            }
+        } else if constexpr (IN == IN_I32) {
+#pragma unroll
+            for (int c = 0; c < NC; c++)
+#pragma unroll
+                for (int s = 0; s < NS; s++) v[c][s] -= r.dc;
+        }
+#pragma unroll
+        for (int s = 0; s < NS; s++) {
+            if constexpr (IN == IN_F32) {
+#pragma unroll
+                for (int c = 0; c < NC; c++) out[c][s] = (T)__int_as_float(v[c][s]);
+            } else if constexpr (NC == 3 && MCT != MCTK_NONE) {
+                mct_forward<WT, MCT>(v[0][s], v[1][s], v[2][s], out[0][s], out[1][s], out[2][s]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < NC; c++) out[c][s] = (T)v[c][s];
+            }
+        }
+    }
+
+    static __device__ __forceinline__ void quant_vec(const T (&v)[NP], const FastQ& q, int (&o)[NP]) {
+        if constexpr (WT == 53) {
+#pragma unroll
+            for (int j = 0; j < NP; j++) o[j] = (int)((unsigned)(int)v[j] << q.shift);  // shift == 0 for Q_RAW
+        } else {
+            if (q.mode == Q_QUANT) {
+#pragma unroll
+                for (int j = 0; j < NP; j++) {
+                    float c = (float)v[j];
+                    float q0 = __fmul_rn(c, q.rcp);
+                    float e = __fmaf_rn(-q0, q.step, c);
+                    o[j] = __float2int_rn(__fmaf_rn(e, q.rcp, q0));
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < NP; j++) o[j] = __float_as_int((float)v[j]);
+            }
+        }
+    }
+
+    static __device__ __forceinline__ void store_vec(int* p, const int (&o)[NP]) {
+        if constexpr (NP == 4) *(int4*)p = make_int4(o[0], o[1], o[2], o[3]);
+        else if constexpr (NP == 2) *(int2*)p = make_int2(o[0], o[1]);
+        else *p = o[0];
+    }
+
+    static __device__ __forceinline__ void run(const LevelArgs& a, const FastQ (&fq)[4]) {
+        const int lane = threadIdx.x & 31;
+        const long long job = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        const long long njobs = (long long)a.n_items * a.nchunks * a.nstrips;
+        if (job >= njobs) return;
+        const int strip = (int)(job % a.nstrips);
+        const int chunk = (int)((job / a.nstrips) % a.nchunks);
+        const int item = (int)(job / ((long long)a.nstrips * a.nchunks));
+
+        const int kx0 = strip * VP - HLN * NP + lane * NP;
+        const int i0 = 2 * kx0;  // px == 0
+        const bool lane_out = lane >= HLN && lane < 32 - HLN;
+        const int hw = a.w - a.lw, hh = a.h - a.lh;
+        const bool ld_full = i0 >= 0 && i0 + NS <= a.w;
+        const bool st_full = kx0 >= 0 && kx0 + NP <= hw;  // hw <= lw when px == 0
+        const long long x_off = a.x_off[item];
+        const unsigned char* xlane = (const unsigned char*)a.x_base + (x_off + (long long)i0 * (IN == IN_U8 || IN == IN_U16 ? NC : 1)) * ES;
+        const long long xrow_bytes = (long long)a.x_row_stride * ES;
+        const long long ll_off = a.ll.off[item], hl_off = a.hl.off[item], lh_off = a.lh_.off[item], hh_off = a.hh.off[item];
+        int* p_ll = (int*)a.ll.base + ll_off + (long long)a.ll.y_off * a.ll.row_stride + a.ll.x_off + kx0;
+        int* p_hl = (int*)a.hl.base + hl_off + (long long)a.hl.y_off * a.hl.row_stride + a.hl.x_off + kx0;
+        int* p_lh = (int*)a.lh_.base + lh_off + (long long)a.lh_.y_off * a.lh_.row_stride + a.lh_.x_off + kx0;
+        int* p_hh = (int*)a.hh.base + hh_off + (long long)a.hh.y_off * a.hh.row_stride + a.hh.x_off + kx0;
+
+        const int ky0 = chunk * a.chunk_pairs;
+        const int ky1 = min(ky0 + a.chunk_pairs, a.Ky);
+
+        T pe[NC][NS], po[NC][NS], s1p[NC][NS], d1p[NC][NS], d2p[NC][NS];
+#pragma unroll
+        for (int c = 0; c < NC; c++)
+#pragma unroll
+            for (int s = 0; s < NS; s++) { pe[c][s] = 0; po[c][s] = 0; s1p[c][s] = 0; d1p[c][s] = 0; d2p[c][s] = 0; }
+
+        const int t_begin = ky0 - LAG, t_end = ky1 + LAG;
+        unsigned ne[NW], no[NW];
+        if (ld_full) {
+            fetch(xlane + (long long)mirror_idx(2 * t_begin - a.py, a.h) * xrow_bytes, ne);
+            fetch(xlane + (long long)mirror_idx(2 * t_begin + 1 - a.py, a.h) * xrow_bytes, no);
+        }
+        for (int t = t_begin; t < t_end; t++) {
+            T e[NC][NS], o[NC][NS];
+            if (ld_full) {
+                unsigned ce[NW], co[NW];
+#pragma unroll
+                for (int k = 0; k < NW; k++) { ce[k] = ne[k]; co[k] = no[k]; }
+                if (t + 1 < t_end) {
+                    fetch(xlane + (long long)mirror_idx(2 * t + 2 - a.py, a.h) * xrow_bytes, ne);
+                    fetch(xlane + (long long)mirror_idx(2 * t + 3 - a.py, a.h) * xrow_bytes, no);
+                }
+                unpack(ce, a.raw, e);
+                unpack(co, a.raw, o);
+            } else {
+                Slow::load_row(a, x_off, mirror_idx(2 * t - a.py, a.h), i0, false, e);
+                Slow::load_row(a, x_off, mirror_idx(2 * t + 1 - a.py, a.h), i0, false, o);
+            }
+            T lo[NC][NS], hi[NC][NS];
+            if constexpr (WT == 97) {
+#pragma unroll
+                for (int c = 0; c < NC; c++)
+#pragma unroll
+                    for (int s = 0; s < NS; s++) {
+                        float d1 = lift97((float)po[c][s], (float)pe[c][s], (float)e[c][s], J2K_ALPHA);
+                        float s1 = lift97((float)pe[c][s], (float)d1p[c][s], d1, J2K_BETA);
+                        float d2 = lift97((float)d1p[c][s], (float)s1p[c][s], s1, J2K_GAMMA);
+                        float s2 = lift97((float)s1p[c][s], (float)d2p[c][s], d2, J2K_DELTA);
+                        lo[c][s] = (T)__fmul_rn(s2, J2K_INVK);
+                        hi[c][s] = (T)__fmul_rn(d2, J2K_K);
+                        pe[c][s] = e[c][s]; po[c][s] = o[c][s]; d1p[c][s] = (T)d1; s1p[c][s] = (T)s1; d2p[c][s] = (T)d2;
+                    }
+            } else {
+#pragma unroll
+                for (int c = 0; c < NC; c++)
+#pragma unroll
+                    for (int s = 0; s < NS; s++) {
+                        int d = (int)po[c][s] - (((int)pe[c][s] + (int)e[c][s]) >> 1);
+                        int sv = (int)pe[c][s] + (((int)d1p[c][s] + d + 2) >> 2);
+                        lo[c][s] = (T)sv; hi[c][s] = (T)d;
+                        pe[c][s] = e[c][s]; po[c][s] = o[c][s]; d1p[c][s] = (T)d;
+                    }
+            }
+            const int ky = t - LAG;
+            if (ky < ky0) continue;
+            const int yl = ky - a.py, yh = ky;
+            const bool row_l = yl >= 0 && yl < a.lh, row_h = yh < hh;
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                Slow::hlift(lo[c], false);
+                Slow::hlift(hi[c], false);
+                if (!lane_out) continue;
+                T lowv[NP], highv[NP];
+                if (st_full) {
+                    int q[NP];
+                    if (row_l) {
+#pragma unroll
+                        for (int j = 0; j < NP; j++) { lowv[j] = lo[c][2 * j]; highv[j] = lo[c][2 * j + 1]; }
+                        quant_vec(lowv, fq[0], q);
+                        store_vec(p_ll + c * a.ll.comp_stride + (long long)yl * a.ll.row_stride, q);
+                        quant_vec(highv, fq[1], q);
+                        store_vec(p_hl + c * a.hl.comp_stride + (long long)yl * a.hl.row_stride, q);
+                    }
+                    if (row_h) {
+#pragma unroll
+                        for (int j = 0; j < NP; j++) { lowv[j] = hi[c][2 * j]; highv[j] = hi[c][2 * j + 1]; }
+                        quant_vec(lowv, fq[2], q);
+                        store_vec(p_lh + c * a.lh_.comp_stride + (long long)yh * a.lh_.row_stride, q);
+                        quant_vec(highv, fq[3], q);
+                        store_vec(p_hh + c * a.hh.comp_stride + (long long)yh * a.hh.row_stride, q);
+                    }
+                } else {
+                    if (row_l) {
+#pragma unroll
+                        for (int j = 0; j < NP; j++) { lowv[j] = lo[c][2 * j]; highv[j] = lo[c][2 * j + 1]; }
+                        Slow::store_band(a.ll, ll_off, c, yl, kx0, a.lw, lowv, false);
+                        Slow::store_band(a.hl, hl_off, c, yl, kx0, hw, highv, false);
+                    }
+                    if (row_h) {
+#pragma unroll
+                        for (int j = 0; j < NP; j++) { lowv[j] = hi[c][2 * j]; highv[j] = hi[c][2 * j + 1]; }
+                        Slow::store_band(a.lh_, lh_off, c, yh, kx0, a.lw, lowv, false);
+                        Slow::store_band(a.hh, hh_off, c, yh, kx0, hw, highv, false);
+                    }
+                }
+            }
+        }
+    }
+};
+
+struct FastQ4 { FastQ q[4]; };
+
+template <int WT, int NP, int NC, int IN, int MCT>
+__global__ void __launch_bounds__(128, (NP * NC >= 4 && WT == 97) ? 4 : 5)
+fwd_fast_kernel(const __grid_constant__ LevelArgs a, const __grid_constant__ FastQ4 fq) {
+    FwdFast<WT, NP, NC, IN, MCT>::run(a, fq.q);
+}
+
 // ------------------------------------------------------------------ inverse level kernel
 
 // OUT: IN_I32 / IN_F32 = raw store of the working type (int32 for 5/3, float32 for 9/7);
