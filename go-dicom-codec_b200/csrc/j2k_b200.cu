@@ -27,9 +27,11 @@
 #include "../../include/j2k_b200.h"
 #include "j2k_kernels.cuh"
 #include "j2k_pointwise.cuh"
+#include "j2k_ring.cuh"
 
 #ifndef J2K_LAUNCH
 #define J2K_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#define J2K_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #endif
 
 using namespace j2k;
@@ -160,6 +162,19 @@ struct LevelLaunch {
     int level;                  // 1 = finest
     bool fast;                  // eligible for the fast-path kernel (FwdFast)
     FastQ4 fq;
+    int cls;                    // tile class the launch belongs to
+    bool nc3_first;             // 3-component image-side launch (items are pixel items)
+    size_t o_x, o_ll, o_plane;  // offset-table positions (alignment checks of the ring path)
+};
+
+// Persistent single-launch form of a whole plan direction (j2k_ring.cuh); built when every level qualifies.
+struct RingPlan {
+    bool ok = false;
+    RingArgs args;
+    int WT = 0, NP1 = 0, NC1 = 0, IN1 = 0, MCT1 = 0, SG1 = 0;
+    int x_buf[J2K_RING_MAXSEG], ll_buf[J2K_RING_MAXSEG], band_buf[J2K_RING_MAXSEG];
+    int level[J2K_RING_MAXSEG];
+    unsigned grid = 0;
 };
 
 enum PwKind { PW_PREP, PW_FINALIZE, PW_QUANT_RECTS, PW_SHIFT, PW_COPY, PW_DEQUANT_RECTS };
@@ -197,11 +212,12 @@ struct Plan {
     long long frame_samples = 0; // caller frame stride in samples
     long long coeffs_per_frame = 0;
     bool want_planes = false;
-    DevBuf tables, temp, sa, sb, ctemp;
+    DevBuf tables, temp, sa, sb, ctemp, ctl;
+    RingPlan ring;
     std::vector<LevelLaunch> levels;   // in execution order
     std::vector<PwLaunch> pre, post;   // pointwise launches before / after the level launches
     int launches_per_run = 0;
-    ~Plan() { tables.release(); temp.release(); sa.release(); sb.release(); ctemp.release(); }
+    ~Plan() { tables.release(); temp.release(); sa.release(); sb.release(); ctemp.release(); ctl.release(); }
 };
 
 }  // namespace
@@ -463,6 +479,181 @@ void fill_rect_table(const Spec& s, const std::vector<Rect>& rects, RectTable& r
     }
 }
 
+
+// ------------------------------------------------------------------ persistent single-launch plan (j2k_ring.cuh)
+
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+// Job decomposition of one ring segment: even column strips, row chunks sized for ~2 jobs per resident warp.
+void ring_chunks(RingSeg& g, int NP, int n_cols_total_hint, int level) {
+    const int VP = 30 * NP;  // 32 lanes minus one halo lane per side (9/7 needs 2 pairs, 5/3 one: both fit NP >= 2)
+    g.nstrips = (g.Kx + VP - 1) / VP;
+    if (g.nstrips < 1) g.nstrips = 1;
+    int sp = (g.Kx + g.nstrips - 1) / g.nstrips;
+    g.strip_pairs = (sp + NP - 1) / NP * NP;
+    const int max_chunk = level <= 1 ? env_int("J2K_RING_CHUNK", 64) : env_int("J2K_RING_CHUNK_DEEP", env_int("J2K_RING_CHUNK", 64));
+    const long long target = env_int("J2K_RING_TARGET_JOBS", 148 * 16 * 2);
+    long long cols = (long long)n_cols_total_hint * g.nstrips;
+    long long want = (target + cols - 1) / cols;
+    if (want < 1) want = 1;
+    int cp = (int)((g.Ky + want - 1) / want);
+    const int min_chunk = env_int("J2K_RING_CHUNK_MIN", 8);
+    if (cp < min_chunk) cp = min_chunk;
+    if (cp > max_chunk) cp = max_chunk;
+    if (cp > g.Ky) cp = g.Ky;
+    if (cp < 1) cp = 1;
+    g.chunk_pairs = cp;
+    g.nchunks = (g.Ky + cp - 1) / cp;
+}
+
+bool ring_variant_supported(int WT, int NP, int NC, int IN, int MCT, int SG) {
+    if (NC == 3) return NP == 2 && SG == 0 && (IN == IN_U8 || IN == IN_U16) && MCT == (WT == 53 ? MCTK_RCT : MCTK_ICT);
+    if (NP != 4 || MCT != MCTK_NONE) return false;
+    if (IN == IN_U8 || IN == IN_U16) return true;
+    if (SG) return false;
+    return IN == IN_I32 || (IN == IN_F32 && WT == 97);
+}
+
+// Converts the per-level launch list into ONE persistent launch when every level qualifies; otherwise P.ring.ok stays false
+// and run_plan uses the per-level kernels.
+int build_ring_fwd(const Spec& s, Plan& P, const std::vector<long long>& tab) {
+    RingPlan& R = P.ring;
+    R.ok = false;
+    if (env_int("J2K_RING_DISABLE", 0)) return 0;
+    if (P.levels.empty() || P.levels.size() > J2K_RING_MAXSEG) return 0;
+    memset(&R.args, 0, sizeof R.args);
+    const int WT = s.reversible ? 53 : 97;
+    // order: level-major, then class (the launch list is class-major)
+    std::vector<int> order;
+    int maxlevel = 0;
+    for (auto& l : P.levels) maxlevel = l.level > maxlevel ? l.level : maxlevel;
+    for (int k = 1; k <= maxlevel; k++)
+        for (size_t i = 0; i < P.levels.size(); i++)
+            if (P.levels[i].level == k) order.push_back((int)i);
+    std::vector<int> seg_of(P.levels.size(), -1);
+    bool have_first = false;
+    int n_ctl = 2, jobs = 0;
+    for (size_t si = 0; si < order.size(); si++) {
+        const LevelLaunch& l = P.levels[order[si]];
+        const LevelArgs& a = l.a;
+        RingSeg& g = R.args.seg[si];
+        const bool first = l.level == 1;
+        const bool raw_in = l.KIND == IN_U8 || l.KIND == IN_U16;
+        const int NP = l.NC == 3 ? 2 : 4;
+        const int SG = (raw_in && P.raw.sign_sub != 0) ? 1 : 0;
+        const int ES = l.KIND == IN_U8 ? 1 : (l.KIND == IN_U16 ? 2 : 4);
+        const int PB = ES * (raw_in ? l.NC : 1);
+        if (a.px != 0 || a.hskip || a.vskip) return 0;
+        if (a.w % (2 * NP)) return 0;  // whole-vector stores only: low and high band widths are multiples of NP
+        if (first) {
+            if (!ring_variant_supported(WT, NP, l.NC, l.KIND, l.MCT, SG)) return 0;
+            if (l.NC == 1 && raw_in && s.C != 1) return 0;  // strided components
+            if (!have_first) { R.WT = WT; R.NP1 = NP; R.NC1 = l.NC; R.IN1 = l.KIND; R.MCT1 = l.MCT; R.SG1 = SG; have_first = true; }
+            else if (R.NP1 != NP || R.NC1 != l.NC || R.IN1 != l.KIND || R.MCT1 != l.MCT || R.SG1 != SG) return 0;
+        } else {
+            if (l.NC != 1 || l.KIND != (WT == 53 ? IN_I32 : IN_F32)) return 0;
+        }
+        // alignment of the staged side: row pitch, row length and every item origin are multiples of 16 bytes
+        const long long pitch = (long long)a.x_row_stride * ES;
+        const long long row_bytes = (long long)a.w * PB;
+        if (pitch % 16 || row_bytes % 16 || row_bytes > 0x7fffffffLL) return 0;
+        for (int i = 0; i < a.n_items; i++)
+            if ((tab[l.o_x + i] * ES) % 16) return 0;
+        // alignment of the band side for NP-wide vector stores
+        if ((a.hl.row_stride % NP) || (a.lw % NP) || (a.hl.comp_stride % NP) || (a.ll.row_stride % NP) || (a.ll.comp_stride % NP) ||
+            (a.hl.x_off % NP) || (a.hh.x_off % NP) || (a.ll.x_off % NP) || (a.lh_.x_off % NP))
+            return 0;
+        for (int i = 0; i < a.n_items; i++)
+            if ((tab[l.o_plane + i] % NP) || (tab[l.o_ll + i] % NP)) return 0;
+        const BandIO* bands[4] = {&a.ll, &a.hl, &a.lh_, &a.hh};
+        for (int bi = 0; bi < 4; bi++) {
+            const BandIO& b = *bands[bi];
+            FastQ& q = g.q[bi];
+            q.mode = b.mode; q.shift = 0; q.step = 1.f; q.rcp = 1.f;
+            if (WT == 53) { if (b.mode == Q_SHIFT) q.shift = b.shift; else if (b.mode != Q_RAW) return 0; }
+            else if (b.mode == Q_QUANT) { q.step = b.step / b.scale; q.rcp = 1.0f / q.step; }  // scale is a power of two: exact
+            else if (b.mode != Q_RAW) return 0;
+        }
+        g.w = a.w; g.h = a.h; g.py = a.py; g.lw = a.lw; g.lh = a.lh; g.Kx = a.Kx; g.Ky = a.Ky;
+        g.n_items = a.n_items;
+        g.first = first ? 1 : 0;
+        g.row_bytes = (int)row_bytes;
+        g.dc = first ? a.raw.dc : 0;
+        g.x_off = a.x_off;
+        g.x_row_bytes = pitch;
+        g.ll = a.ll; g.hl = a.hl; g.lh_ = a.lh_; g.hh = a.hh;
+        ring_chunks(g, NP, a.n_items, l.level);
+        g.dep_seg = -1; g.dep_div = 1; g.dep_target = 0;
+        if (!first) {
+            // producer: same class, previous level
+            for (size_t pj = 0; pj < si; pj++) {
+                const LevelLaunch& pl = P.levels[order[pj]];
+                if (pl.cls == l.cls && pl.level == l.level - 1) {
+                    g.dep_seg = (int)pj;
+                    g.dep_div = pl.nc3_first ? 3 : 1;
+                    g.dep_target = R.args.seg[pj].nchunks * R.args.seg[pj].nstrips;
+                }
+            }
+            if (g.dep_seg < 0) return 0;
+        }
+        g.job_begin = jobs;
+        long long nj = (long long)g.n_items * g.nchunks * g.nstrips;
+        if (nj + jobs > 0x3fffffffLL) return 0;
+        jobs += (int)nj;
+        g.job_end = jobs;
+        g.done_base = n_ctl;
+        n_ctl += g.n_items;
+        R.x_buf[si] = l.x_buf; R.ll_buf[si] = l.ll_buf; R.band_buf[si] = l.band_buf; R.level[si] = l.level;
+        seg_of[order[si]] = (int)si;
+    }
+    if (!have_first) return 0;
+    R.args.nseg = (int)order.size();
+    R.args.total_jobs = jobs;
+    R.args.n_ctl = n_ctl;
+    R.args.raw = P.raw;
+    R.args.one = 1.0f;
+    int rc = P.ctl.ensure((size_t)n_ctl * sizeof(unsigned));
+    if (rc) return rc;
+    CK(cudaMemset(P.ctl.p, 0, (size_t)n_ctl * sizeof(unsigned)));
+    R.args.ctl = (unsigned*)P.ctl.p;
+    R.ok = true;
+    return 0;
+}
+
+#define RING_CASE(wt, np, nc, in, mct, sg)                                                                                   \
+    if (R.WT == wt && R.NP1 == np && R.NC1 == nc && R.IN1 == in && R.MCT1 == mct && R.SG1 == sg) {                           \
+        if (query) return ring_blocks_per_sm((const void*)fwd_ring_kernel<wt, np, nc, in, mct, sg>);                        \
+        J2K_LAUNCH_SMEM((fwd_ring_kernel<wt, np, nc, in, mct, sg>), grid, J2K_RING_WARPS * 32, J2K_RING_CTA_SMEM, st, A);   \
+        return 0;                                                                                                           \
+    }
+
+int ring_blocks_per_sm(const void* fn) {
+#ifdef J2K_EMU
+    (void)fn;
+    return 1;
+#else
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, J2K_RING_WARPS * 32, J2K_RING_CTA_SMEM) != cudaSuccess) return -1;
+    return n;
+#endif
+}
+
+// query = true: resident CTAs per SM of the variant (or -1); query = false: launch (0 = launched, -1 = no such variant)
+int ring_dispatch_fwd(const RingPlan& R, const RingArgs& A, unsigned grid, cudaStream_t st, bool query) {
+    RING_CASE(97, 4, 1, IN_U8, MCTK_NONE, 0) RING_CASE(97, 4, 1, IN_U16, MCTK_NONE, 0)
+    RING_CASE(97, 4, 1, IN_U8, MCTK_NONE, 1) RING_CASE(97, 4, 1, IN_U16, MCTK_NONE, 1)
+    RING_CASE(97, 2, 3, IN_U8, MCTK_ICT, 0) RING_CASE(97, 2, 3, IN_U16, MCTK_ICT, 0)
+    RING_CASE(97, 4, 1, IN_F32, MCTK_NONE, 0) RING_CASE(97, 4, 1, IN_I32, MCTK_NONE, 0)
+    RING_CASE(53, 4, 1, IN_U8, MCTK_NONE, 0) RING_CASE(53, 4, 1, IN_U16, MCTK_NONE, 0)
+    RING_CASE(53, 4, 1, IN_U8, MCTK_NONE, 1) RING_CASE(53, 4, 1, IN_U16, MCTK_NONE, 1)
+    RING_CASE(53, 2, 3, IN_U8, MCTK_RCT, 0) RING_CASE(53, 2, 3, IN_U16, MCTK_RCT, 0)
+    RING_CASE(53, 4, 1, IN_I32, MCTK_NONE, 0)
+    return -1;
+}
+
 // Builds the launch list of one direction.  Returns 0 or a negative status.
 int build_plan(const Spec& s, int nframes, long long frame_samples, Plan& P) {
     P.fwd = s.fwd; P.nframes = nframes; P.C = s.C; P.W = s.W; P.H = s.H; P.L = s.L;
@@ -708,6 +899,9 @@ int build_plan(const Spec& s, int nframes, long long frame_samples, Plan& P) {
                            (a.ll.comp_stride % l.NP) == 0 && all_mult(H, o_ll, o_ll + n, l.NP);
                 a.vec_b = okb;
             }
+            l.cls = (int)(&c - &classes[0]);
+            l.nc3_first = use_nc3;
+            l.o_x = o_x; l.o_ll = o_ll; l.o_plane = o_plane;
             l.fast = false;
             if (s.fwd && a.vec_x && a.vec_b && g.px == 0 && !a.hskip && !a.vskip && has_fwd_fast(l)) {
                 const BandIO* bands[4] = {&a.ll, &a.hl, &a.lh_, &a.hh};
@@ -761,6 +955,10 @@ int build_plan(const Spec& s, int nframes, long long frame_samples, Plan& P) {
         pw.src_off = T + f.src; pw.dst_off = T + f.dst;
     }
     P.launches_per_run = (int)(P.levels.size() + P.pre.size() + P.post.size()) + (P.generic ? 1 : 0);
+    if (s.fwd) {
+        int rc2 = build_ring_fwd(s, P, tb.host);
+        if (rc2) return rc2;
+    }
     return 0;
 }
 
@@ -828,7 +1026,83 @@ int run_plan(j2k_ctx* ctx, Plan& P, void* pixels, void* coeffs, void* planes, bo
         nl++;
     }
     for (auto& pw : P.pre) { prof.begin(0); int rc = run_pw(pw, bufs, st); prof.end(); if (rc) return rc; nl++; }
+    bool use_ring = P.fwd && P.ring.ok;
+    if (use_ring) {
+        for (int i = 0; i < P.ring.args.nseg && use_ring; i++)
+            use_ring = aligned16(bufs[P.ring.x_buf[i]]) && aligned16(bufs[P.ring.ll_buf[i]]) && aligned16(bufs[P.ring.band_buf[i]]);
+    }
+    if (use_ring) {
+        RingPlan& R = P.ring;
+        if (R.grid == 0) {
+            int per_sm = ring_dispatch_fwd(R, R.args, 0, st, true);
+            if (per_sm <= 0) return fail(J2K_ERR_CUDA, "ring kernel variant (WT=%d NP=%d NC=%d kind=%d mct=%d sg=%d) cannot be resident", R.WT, R.NP1,
+                                         R.NC1, R.IN1, R.MCT1, R.SG1);
+            int sms = 1;
+#ifndef J2K_EMU
+            int devid = 0;
+            CK(cudaGetDevice(&devid));
+            CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, devid));
+#endif
+            long long want = (long long)sms * per_sm;
+            int cap = env_int("J2K_RING_GRID", 0);
+            if (cap > 0 && cap < want) want = cap;
+            R.grid = (unsigned)want;
+        }
+        RingArgs A = R.args;
+        for (int i = 0; i < A.nseg; i++) {
+            RingSeg& g = A.seg[i];
+            g.x_base = (const unsigned char*)bufs[R.x_buf[i]];
+            g.ll.base = bufs[R.ll_buf[i]];
+            g.hl.base = g.lh_.base = g.hh.base = bufs[R.band_buf[i]];
+        }
+        static const bool trace = getenv("J2K_B200_TRACE") != nullptr;
+        static const bool per_level = env_int("J2K_RING_PER_LEVEL", 0) != 0;
+        static const bool dry = env_int("J2K_RING_DRY", 0) != 0;  // diagnostic: launch overhead only (no job is claimed)
+        if (dry) A.total_jobs = 0;
+        if (trace)
+            fprintf(stderr, "[j2k] fwd ring WT=%d NP=%d NC=%d kind=%d mct=%d sg=%d segs=%d jobs=%d grid=%u\n", R.WT, R.NP1, R.NC1, R.IN1, R.MCT1,
+                    R.SG1, A.nseg, A.total_jobs, R.grid);
+        if (!per_level) {
+            unsigned grid = R.grid;
+            unsigned need = (unsigned)((A.total_jobs + J2K_RING_WARPS - 1) / J2K_RING_WARPS);
+            if (need < grid) grid = need;
+            if (grid < 1) grid = 1;
+            prof.begin(100);
+            int rc = ring_dispatch_fwd(R, A, grid, st, false);
+            prof.end();
+            if (rc) return fail(J2K_ERR_CUDA, "ring kernel variant missing");
+            CK(cudaGetLastError());
+            nl++;
+        } else {
+            // diagnostic mode: one launch per level (same kernel, dependencies satisfied by stream order)
+            int i = 0;
+            while (i < A.nseg) {
+                int j = i;
+                while (j < A.nseg && R.level[j] == R.level[i]) j++;
+                RingArgs B = A;
+                B.nseg = j - i;
+                int base = A.seg[i].job_begin;
+                for (int k = i; k < j; k++) {
+                    B.seg[k - i] = A.seg[k];
+                    B.seg[k - i].job_begin -= base; B.seg[k - i].job_end -= base;
+                    B.seg[k - i].dep_seg = -1;
+                }
+                B.total_jobs = A.seg[j - 1].job_end - base;
+                unsigned grid = R.grid;
+                unsigned need = (unsigned)((B.total_jobs + J2K_RING_WARPS - 1) / J2K_RING_WARPS);
+                if (need < grid) grid = need;
+                prof.begin(R.level[i]);
+                int rc = ring_dispatch_fwd(R, B, grid, st, false);
+                prof.end();
+                if (rc) return fail(J2K_ERR_CUDA, "ring kernel variant missing");
+                CK(cudaGetLastError());
+                nl++;
+                i = j;
+            }
+        }
+    }
     for (auto& l : P.levels) {
+        if (use_ring) break;
         LevelArgs a = l.a;
         a.x_base = bufs[l.x_buf];
         a.ll.base = bufs[l.ll_buf];

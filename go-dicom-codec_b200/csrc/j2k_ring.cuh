@@ -1,0 +1,688 @@
+// j2k_ring.cuh — persistent, TMA-staged DWT kernels for sm_100a (the production path on regular geometries).
+//
+// ONE launch runs every decomposition level of every frame / tile of a batch:
+//
+//   * the work is a flat, ordered list of jobs (level-major, then item, row chunk, column strip); the
+//     warps of a grid sized to the machine (148 SMs x resident CTAs) claim jobs with an atomic counter,
+//     so there is no wave quantisation and no per-level launch gap;
+//   * a job of level k+1 waits (acquire on a per-item counter) until the jobs of level k that produce
+//     its LL input have published their stores (release); jobs are claimed in order, so a waiting warp
+//     only ever waits on warps that are already running — no co-residency requirement, no grid sync,
+//     and the small deep levels overlap the tail of the big ones;
+//   * inside a job a warp owns a strip of the level window: 32 lanes x NP sample pairs wide, `chunk_pairs`
+//     row pairs tall (+ halo).  Rows are staged HBM -> shared memory by the TMA engine
+//     (cp.async.bulk + mbarrier complete_tx; SASS: UBLKCP / SYNCS) into a warp-private ring of D
+//     row-pair stages, D-1 stages always in flight, so the bytes in flight per SM are set by the ring
+//     (~7 KB per warp) and not by registers.  Whole-sample symmetric extension at the image borders is
+//     an index computation on the staged row (or on the row number for the vertical direction): every
+//     global read is a plain, aligned, in-bounds segment;
+//   * the arithmetic is the register sliding-window vertical lifting + warp-shuffle horizontal lifting
+//     of j2k_kernels.cuh (same operation order, no FMA contraction), fused with unpack / DC shift / MCT
+//     in front and the quantizer behind; results are bit-identical to the per-level kernels.
+//
+// The emulator build (tests/emu, J2K_EMU) runs the same code with the async copy executed synchronously.
+#pragma once
+#include "j2k_kernels.cuh"
+
+namespace j2k {
+
+#define J2K_RING_MAXSEG 14   // (tile class, level) segments one launch can chain
+#define J2K_RING_WARPS 4     // warps per CTA
+#ifndef J2K_RING_BYTES
+#define J2K_RING_BYTES 8704  // staging bytes per warp (8 stages of two 512 B + 32 B rows)
+#endif
+#define J2K_RING_MAXD 8
+#define J2K_RING_WARP_SMEM (J2K_RING_BYTES + J2K_RING_MAXD * 8)
+#define J2K_RING_CTA_SMEM (J2K_RING_WARPS * J2K_RING_WARP_SMEM)
+
+struct RingSeg {
+    // level window (px == 0 always on this path)
+    int w, h, py, lw, lh, Kx, Ky;
+    int n_items, nchunks, nstrips, chunk_pairs, strip_pairs;
+    int first;                         // 1 = image-side variant (raw words / planar api input), 0 = planar working type
+    int dep_seg, dep_div, dep_target;  // wait until ctl[done_base(dep_seg) + item / dep_div] == dep_target (dep_seg < 0: none)
+    int job_begin, job_end;            // this segment's slice of the job list
+    int done_base;                     // index in ctl[] of this segment's per-item completion counters
+    int row_bytes;                     // w * bytes per pixel position (multiple of 16)
+    int dc;                            // DC level shift applied on load (image-side variant)
+    int pad_;
+    const unsigned char* x_base;       // interleaved side (forward: source, inverse: destination)
+    const long long* x_off;            // per item, elements
+    long long x_row_bytes;             // row pitch in bytes (multiple of 16)
+    BandIO ll, hl, lh_, hh;
+    FastQ q[4];
+};
+
+struct RingArgs {
+    int nseg, total_jobs;
+    unsigned* ctl;  // [0] job counter, [1] retired-warp counter, [2..] per-(segment,item) completion counters
+    int n_ctl;      // entries of ctl (for the self-reset at kernel end)
+    float one;      // 1.0f, opaque to the compiler (see addp2 in j2k_ring.cuh)
+    RawFmt raw;
+    RingSeg seg[J2K_RING_MAXSEG];
+};
+
+// ------------------------------------------------------------------ async-copy / barrier primitives
+
+#ifdef J2K_EMU
+#define J2K_SMEM_DECL(name) unsigned char* name = emu::smem()
+typedef unsigned char* smem_t;  // "shared address": a host pointer in the emulator
+__device__ __forceinline__ smem_t smem_handle(void* p) { return (unsigned char*)p; }
+__device__ __forceinline__ unsigned char* smem_ptr(smem_t h) { return h; }
+__device__ __forceinline__ void mbar_init(smem_t, int) {}
+__device__ __forceinline__ void mbar_fence_init() {}
+__device__ __forceinline__ void mbar_expect_tx(smem_t, unsigned) {}
+__device__ __forceinline__ void mbar_wait(smem_t, unsigned) {}
+__device__ __forceinline__ void bulk_g2s(smem_t dst, const void* src, unsigned bytes, smem_t) { memcpy(dst, src, bytes); }
+__device__ __forceinline__ void fence_proxy_async() {}
+__device__ __forceinline__ unsigned ld_relaxed(const unsigned* p) { return *p; }
+__device__ __forceinline__ void fence_acquire() {}
+__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) { *p += v; }
+__device__ __forceinline__ void backoff() {}
+__device__ __forceinline__ uint4 lds128(smem_t a) { uint4 v; memcpy(&v, a, 16); return v; }
+__device__ __forceinline__ uint2 lds64(smem_t a) { uint2 v; memcpy(&v, a, 8); return v; }
+__device__ __forceinline__ unsigned lds32(smem_t a) { unsigned v; memcpy(&v, a, 4); return v; }
+#else
+#define J2K_SMEM_DECL(name) extern __shared__ __align__(128) unsigned char name[]
+typedef unsigned smem_t;  // 32-bit shared-window address
+__device__ __forceinline__ smem_t smem_handle(void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned char* smem_ptr(smem_t h) { return (unsigned char*)__cvta_shared_to_generic((size_t)h); }
+__device__ __forceinline__ void mbar_init(smem_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(smem_t bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(smem_t bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+// TMA bulk copy global -> shared, completion signalled on `bar` (complete_tx::bytes).  SASS: UBLKCP.
+__device__ __forceinline__ void bulk_g2s(smem_t dst, const void* src, unsigned bytes, smem_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ unsigned ld_relaxed(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_acquire() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void backoff() { __nanosleep(400); }
+__device__ __forceinline__ uint4 lds128(smem_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint2 lds64(smem_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ unsigned lds32(smem_t a) {
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+#endif
+
+struct RingWarp {
+    smem_t ring;     // J2K_RING_BYTES of staging, 16-byte aligned
+    smem_t bars;     // J2K_RING_MAXD mbarriers (8 bytes each)
+    unsigned phase;  // bit s = parity the next wait on barrier s uses
+    float one;       // 1.0f the compiler cannot see (see lift97x2)
+};
+
+// single reflection is enough next to the window; anything else (tiny windows) takes the general form
+__device__ __noinline__ int mirror_slow(int i, int n) { return mirror_idx(i, n); }
+__device__ __forceinline__ int mirror_fast(int i, int n) {
+    if ((unsigned)i < (unsigned)n) return i;
+    int r = i < 0 ? -i : 2 * (n - 1) - i;
+    if ((unsigned)r < (unsigned)n) return r;
+    return mirror_slow(i, n);
+}
+
+// ------------------------------------------------------------------ packed fp32x2 arithmetic
+//
+// sm_100a has two-wide fp32 instructions (PTX add/mul/fma.rn.f32x2, SASS FADD2 / FMUL2 / FFMA2): each half is
+// rounded exactly like the scalar instruction, so the lifting stays bit-identical to the reference while the
+// issue slots spent on arithmetic are halved.  Vertical lifting pairs two adjacent columns; horizontal lifting
+// pairs the two rows (vertical low / high) that one iteration finishes.
+
+#ifdef J2K_EMU
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return make_float2(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return make_float2(__fmaf_rn(a.x, b.x, c.x), __fmaf_rn(a.y, b.y, c.y)); }
+#else
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+#endif
+__device__ __forceinline__ float2 splat2(float c) { return make_float2(c, c); }
+// a + b where a is a product: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (single rounding) even
+// under -fmad=false, which would break bit-exactness.  fma(a, one, b) with a 1.0f it cannot see (a kernel
+// parameter) rounds once, a * 1 + b = a + b, and cannot absorb the multiply that produced a.
+__device__ __forceinline__ float2 addp2(float2 a, float2 b, float one) { return fma2(a, make_float2(one, one), b); }
+// x + (l + r) * c, three roundings per half (dwt97.go:104-116)
+__device__ __forceinline__ float2 lift97x2(float2 x, float2 l, float2 r, float2 c, float one) {
+    return addp2(mul2(add2(l, r), c), x, one);
+}
+__device__ __forceinline__ float2 shfl_down2(float2 v) {
+    return make_float2(__shfl_down_sync(0xffffffffu, v.x, 1), __shfl_down_sync(0xffffffffu, v.y, 1));
+}
+__device__ __forceinline__ float2 shfl_up2(float2 v) {
+    return make_float2(__shfl_up_sync(0xffffffffu, v.x, 1), __shfl_up_sync(0xffffffffu, v.y, 1));
+}
+
+// ------------------------------------------------------------------ forward job
+
+template <int WT, int NP, int NC, int IN, int MCT, int SG>
+struct FwdRing {
+    typedef FwdLevel<WT, NP, NC, IN, MCT> Slow;
+    typedef typename Wt<WT>::T T;
+    static constexpr int LAG = Wt<WT>::LAG;
+    static constexpr int HLN = Slow::HLN, NS = Slow::NS;
+    static constexpr bool RAWIN = (IN == IN_U8 || IN == IN_U16);
+    static constexpr int ES = (IN == IN_U8) ? 1 : (IN == IN_U16 ? 2 : 4);
+    static constexpr int PB = ES * (RAWIN ? NC : 1);  // bytes per pixel position of one staged row
+    static constexpr int LB = NS * PB;                // bytes per lane per row
+    static constexpr int NW = LB / 4;                 // 32-bit words per lane per row
+    static constexpr int ROWB = 32 * LB + 32;         // staged row slot (16 B slack for the alignment phase, 16 B rounding)
+    static constexpr int STAGEB = 2 * ROWB;
+    static constexpr int D = (J2K_RING_BYTES / STAGEB) > J2K_RING_MAXD ? J2K_RING_MAXD : (J2K_RING_BYTES / STAGEB);
+    static constexpr int LDALIGN = (LB % 16 == 0) ? 16 : (LB % 8 == 0 ? 8 : 4);
+    static constexpr bool MAGIC = (WT == 97 && RAWIN && SG == 0);  // u8/u16 -> float32 without I2F
+    static_assert(D >= 2, "ring too small for this row size");
+    static_assert(LB % 4 == 0, "lane span must be whole words");
+    static_assert(NC == 1 || RAWIN, "3-component jobs read interleaved raw words");
+
+    static __device__ __forceinline__ void fetch(smem_t p, unsigned (&w)[NW]) {
+        if constexpr (LDALIGN == 16) {
+#pragma unroll
+            for (int k = 0; k < NW / 4; k++) {
+                uint4 q = lds128(p + 16 * k);
+                w[4 * k] = q.x; w[4 * k + 1] = q.y; w[4 * k + 2] = q.z; w[4 * k + 3] = q.w;
+            }
+        } else if constexpr (LDALIGN == 8) {
+#pragma unroll
+            for (int k = 0; k < NW / 2; k++) {
+                uint2 q = lds64(p + 8 * k);
+                w[2 * k] = q.x; w[2 * k + 1] = q.y;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < NW; k++) w[k] = lds32(p + 4 * k);
+        }
+    }
+
+    // raw words of one lane -> integers (no sign fix, no DC shift yet)
+    static __device__ __forceinline__ void words_to_ints(const unsigned (&w)[NW], int (&v)[NC][NS]) {
+#pragma unroll
+        for (int s = 0; s < NS; s++)
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                const int e = NC * s + c;
+                if constexpr (IN == IN_U8) v[c][s] = (w[e >> 2] >> (8 * (e & 3))) & 0xFF;
+                else if constexpr (IN == IN_U16) v[c][s] = (e & 1) ? (w[e >> 1] >> 16) : (w[e >> 1] & 0xFFFF);
+                else v[c][s] = (int)w[e];
+            }
+    }
+
+    // integer tail: sign fix, DC shift, MCT, conversion to the working type (encoder.go:341-383,3698-3711,196-209)
+    static __device__ __forceinline__ void finish_ints(int (&v)[NC][NS], const RawFmt& r, int dc, T (&out)[NC][NS]) {
+        if constexpr (IN == IN_F32) {
+#pragma unroll
+            for (int c = 0; c < NC; c++)
+#pragma unroll
+                for (int s = 0; s < NS; s++) out[c][s] = (T)__int_as_float(v[c][s]);
+            return;
+        }
+#pragma unroll
+        for (int c = 0; c < NC; c++)
+#pragma unroll
+            for (int s = 0; s < NS; s++) {
+                if constexpr (RAWIN && SG == 1) { if (v[c][s] >= r.sign_thresh) v[c][s] -= r.sign_sub; }
+                v[c][s] -= dc;
+            }
+#pragma unroll
+        for (int s = 0; s < NS; s++) {
+            if constexpr (NC == 3 && MCT != MCTK_NONE) {
+                mct_forward<WT, MCT>(v[0][s], v[1][s], v[2][s], out[0][s], out[1][s], out[2][s]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < NC; c++) out[c][s] = (T)v[c][s];
+            }
+        }
+    }
+
+    // Border strips: the lane span just outside the window (pixels [-NS, 0) and [w, w + NS)) is filled, inside the staged
+    // row, with whole-sample-mirrored copies (dwt53.go / dwt97.go border cases == symmetric extension,
+    // tests/test_oracle_mirror.py); lanes 0..NS-1 write the left span, lanes NS..2NS-1 the right one.  The TMA copy
+    // of a border strip never covers those bytes, so the plain stores cannot race with a refill.
+    static __device__ __forceinline__ void fix_halo(smem_t row_e, smem_t row_o, int lane, bool fix_l, bool fix_r, int w, int vb) {
+        if (lane < 2 * NS) {
+            const bool left = lane < NS;
+            const int k = left ? lane : lane - NS;
+            if (left ? fix_l : fix_r) {
+                const int pi = left ? -(k + 1) : w + k;
+                const int so = mirror_fast(pi, w) * PB - vb, d_o = pi * PB - vb;
+                unsigned char* re = smem_ptr(row_e);
+                unsigned char* ro = smem_ptr(row_o);
+#pragma unroll
+                for (int c = 0; c < PB / ES; c++) {
+                    if constexpr (ES == 1) { re[d_o + c] = re[so + c]; ro[d_o + c] = ro[so + c]; }
+                    else if constexpr (ES == 2) {
+                        *(unsigned short*)(re + d_o + 2 * c) = *(const unsigned short*)(re + so + 2 * c);
+                        *(unsigned short*)(ro + d_o + 2 * c) = *(const unsigned short*)(ro + so + 2 * c);
+                    } else {
+                        *(unsigned*)(re + d_o + 4 * c) = *(const unsigned*)(re + so + 4 * c);
+                        *(unsigned*)(ro + d_o + 4 * c) = *(const unsigned*)(ro + so + 4 * c);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+
+    // one staged row of this lane as working values in scalar form (5/3, signed raw words, border lanes)
+    static __device__ __forceinline__ void load_scalar(smem_t row, int lane_off, bool active, const RawFmt& raw, int dc,
+                                                       T (&out)[NC][NS]) {
+        if (active) {
+            unsigned wv[NW];
+            fetch(row + lane_off, wv);
+            int v[NC][NS];
+            words_to_ints(wv, v);
+            finish_ints(v, raw, dc, out);
+        } else {
+#pragma unroll
+            for (int c = 0; c < NC; c++)
+#pragma unroll
+                for (int s = 0; s < NS; s++) out[c][s] = 0;
+        }
+    }
+
+    // the same row as column pairs of float32 (9/7): pair j = samples 2j, 2j+1
+    static __device__ __forceinline__ void load_pairs(smem_t row, int lane_off, bool active, const RawFmt& raw, int dc, float fmagic,
+                                                      float one, float2 (&out)[NC][NP]) {
+        if (active) {
+            unsigned wv[NW];
+            fetch(row + lane_off, wv);
+            if constexpr (IN == IN_F32) {
+#pragma unroll
+                for (int j = 0; j < NP; j++) out[0][j] = make_float2(__uint_as_float(wv[2 * j]), __uint_as_float(wv[2 * j + 1]));
+            } else if constexpr (MAGIC) {
+                // 0x4B000000 | v is the float 2^23 + v: one exact packed add removes 2^23 + dc
+                float2 f[NC][NP];
+                const float2 nm = splat2(-fmagic);
+#pragma unroll
+                for (int j = 0; j < NP; j++)
+#pragma unroll
+                    for (int c = 0; c < NC; c++) {
+                        unsigned p[2];
+#pragma unroll
+                        for (int k = 0; k < 2; k++) {
+                            const int e = NC * (2 * j + k) + c;
+                            if constexpr (IN == IN_U8) p[k] = __byte_perm(wv[e >> 2], 0x4B000000u, 0x7440u | (e & 3));
+                            else p[k] = __byte_perm(wv[e >> 1], 0x4B000000u, (e & 1) ? 0x7432u : 0x7410u);
+                        }
+                        f[c][j] = add2(make_float2(__uint_as_float(p[0]), __uint_as_float(p[1])), nm);
+                    }
+#pragma unroll
+                for (int j = 0; j < NP; j++) {
+                    if constexpr (NC == 3 && MCT == MCTK_ICT) {  // encoder.go:277-288 on exact float32(int) inputs
+                        const float2 fr = f[0][j], fg = f[1][j], fb = f[2][j];
+                        out[0][j] = addp2(mul2(fb, splat2(0.114f)), addp2(mul2(fr, splat2(0.299f)), mul2(fg, splat2(0.587f)), one), one);
+                        out[1][j] = addp2(mul2(fb, splat2(0.5f)), addp2(mul2(fr, splat2(-0.16875f)), mul2(fg, splat2(-0.331260f)), one), one);
+                        out[2][j] = addp2(mul2(fb, splat2(-0.08131f)), addp2(mul2(fr, splat2(0.5f)), mul2(fg, splat2(-0.41869f)), one), one);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < NC; c++) out[c][j] = f[c][j];
+                    }
+                }
+            } else {
+                int v[NC][NS];
+                float t[NC][NS];
+                words_to_ints(wv, v);
+                finish_ints(v, raw, dc, t);
+#pragma unroll
+                for (int c = 0; c < NC; c++)
+#pragma unroll
+                    for (int j = 0; j < NP; j++) out[c][j] = make_float2(t[c][2 * j], t[c][2 * j + 1]);
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < NC; c++)
+#pragma unroll
+                for (int j = 0; j < NP; j++) out[c][j] = make_float2(0.f, 0.f);
+        }
+    }
+
+    static __device__ __forceinline__ void store_vec(int* p, const int (&o)[NP]) {
+        if constexpr (NP == 4) *(int4*)p = make_int4(o[0], o[1], o[2], o[3]);
+        else if constexpr (NP == 2) *(int2*)p = make_int2(o[0], o[1]);
+        else *p = o[0];
+    }
+
+    static __device__ __forceinline__ void run(const RingSeg& S, const RawFmt& raw, int item, int chunk, int strip, RingWarp& rw,
+                                               int lane) {
+        const int w = S.w, h = S.h, py = S.py;
+        const int hw = w - S.lw, hh = h - S.lh, lh = S.lh;
+        const int kxs = strip * S.strip_pairs;
+        const int kxe = min(kxs + S.strip_pairs, S.Kx);
+        const int nl = (kxe - kxs + NP - 1) / NP + 2 * HLN;  // lanes that carry data
+        const int kx0 = kxs - HLN * NP + lane * NP;
+        const int i0w = 2 * (kxs - HLN * NP);
+        const int m = (i0w * PB) & 15;
+        const int vb = i0w * PB - m;  // virtual (16 B aligned) byte position of the slot start inside the row
+        const int c0 = max(vb, 0);
+        const int c1 = min(vb + ((m + nl * LB + 15) & ~15), S.row_bytes);
+        const unsigned copy_bytes = (unsigned)(c1 - c0);
+        const int dst_off = c0 - vb;
+        const int lane_off = m + lane * LB;
+        const bool active = lane < nl;                              // lanes beyond the right halo lane carry nothing
+        const bool fix_l = kxs == 0, fix_r = kxe == S.Kx;           // warp-uniform: this strip touches a window border
+        const bool fix = fix_l || fix_r;
+        // the window width is a multiple of 2 NP on this path: a lane stores whole vectors or nothing
+        const bool st = lane >= HLN && kx0 < kxe && kx0 + NP <= hw;
+
+        const int dc = S.dc;
+        const float fmagic = 8388608.0f + (float)dc;
+        const float one = rw.one;
+        const unsigned char* src = S.x_base + S.x_off[item] * ES + c0;
+        const long long pitch = S.x_row_bytes;
+
+        const int ky0 = chunk * S.chunk_pairs;
+        const int ky1 = min(ky0 + S.chunk_pairs, S.Ky);
+        const int r_begin = 2 * (ky0 - LAG) - py;  // low-type row of iteration 0
+        const int n_it = ky1 - ky0 + 2 * LAG;
+        // iterations j_lo <= j < j_hi stage two in-range, adjacent rows; the others mirror the row number
+        const int j_lo = r_begin < 0 ? (1 - r_begin) >> 1 : 0;
+        const int j_hi = (h - r_begin) >> 1;
+
+        int* p_ll = (int*)S.ll.base + S.ll.off[item] + (long long)S.ll.y_off * S.ll.row_stride + S.ll.x_off + kx0;
+        int* p_hl = (int*)S.hl.base + S.hl.off[item] + (long long)S.hl.y_off * S.hl.row_stride + S.hl.x_off + kx0;
+        int* p_lh = (int*)S.lh_.base + S.lh_.off[item] + (long long)S.lh_.y_off * S.lh_.row_stride + S.lh_.x_off + kx0;
+        int* p_hh = (int*)S.hh.base + S.hh.off[item] + (long long)S.hh.y_off * S.hh.row_stride + S.hh.x_off + kx0;
+        const int rs_ll = S.ll.row_stride, rs_b = S.hl.row_stride;
+        const long long cs_ll = S.ll.comp_stride, cs_b = S.hl.comp_stride;
+
+        // producer cursor (warp-uniform): next iteration to stage, its slot and the source pointer of its low-type row
+        int pj = 0, pslot = 0;
+        const unsigned char* psrc = src + (long long)r_begin * pitch;
+        const smem_t dst_s = rw.ring + dst_off;
+        // lane 0 stages both rows of iteration pj (TMA bulk copies, completion on the stage barrier)
+        auto issue = [&]() {
+            if (lane == 0) {
+                const unsigned char* se = psrc;
+                const unsigned char* so = psrc + pitch;
+                if (pj < j_lo || pj >= j_hi) {
+                    const int r0 = r_begin + 2 * pj;
+                    se = src + (long long)mirror_fast(r0, h) * pitch;
+                    so = src + (long long)mirror_fast(r0 + 1, h) * pitch;
+                }
+                const smem_t bar = rw.bars + 8 * pslot;
+                const smem_t dst = dst_s + pslot * STAGEB;
+                mbar_expect_tx(bar, 2 * copy_bytes);
+                bulk_g2s(dst, se, copy_bytes, bar);
+                bulk_g2s(dst + ROWB, so, copy_bytes, bar);
+            }
+            pj++;
+            psrc += 2 * pitch;
+            pslot = (pslot + 1 == D) ? 0 : pslot + 1;
+        };
+        __syncwarp();
+#pragma unroll 1
+        for (int j = 0; j < D - 1 && j < n_it; j++) issue();
+
+        int cslot = 0;
+        const smem_t lane_s = rw.ring + lane_off;
+        if constexpr (WT == 97) {
+            const float2 A2 = splat2(J2K_ALPHA), B2 = splat2(J2K_BETA), G2 = splat2(J2K_GAMMA), D2 = splat2(J2K_DELTA);
+            // quantizer constants per row pair: E positions hold (LL, LH), O positions hold (HL, HH)
+            const float2 rcpE = make_float2(S.q[0].rcp, S.q[2].rcp), nstE = make_float2(-S.q[0].step, -S.q[2].step);
+            const float2 rcpO = make_float2(S.q[1].rcp, S.q[3].rcp), nstO = make_float2(-S.q[1].step, -S.q[3].step);
+            const bool raw_ll = S.q[0].mode != Q_QUANT, raw_hl = S.q[1].mode != Q_QUANT, raw_lh = S.q[2].mode != Q_QUANT,
+                       raw_hh = S.q[3].mode != Q_QUANT;
+            float2 pe[NC][NP], po[NC][NP], s1p[NC][NP], d1p[NC][NP], d2p[NC][NP];
+#pragma unroll
+            for (int c = 0; c < NC; c++)
+#pragma unroll
+                for (int j = 0; j < NP; j++) { pe[c][j] = po[c][j] = s1p[c][j] = d1p[c][j] = d2p[c][j] = make_float2(0.f, 0.f); }
+#pragma unroll 1
+            for (int it = 0; it < n_it; it++) {
+                // the slot of iteration it-1 (slot D-1 when it == 0) is free once every lane is past its arithmetic: refill it
+                __syncwarp();
+                if (pj < n_it) issue();
+                mbar_wait(rw.bars + 8 * cslot, (rw.phase >> cslot) & 1u);
+                rw.phase ^= 1u << cslot;
+                const smem_t row_e = rw.ring + cslot * STAGEB;
+                const smem_t row_o = row_e + ROWB;
+                cslot = (cslot + 1 == D) ? 0 : cslot + 1;
+
+                float2 e[NC][NP], o[NC][NP];
+                if (fix) fix_halo(row_e, row_o, lane, fix_l, fix_r, w, vb);
+                load_pairs(row_e, lane_off, active, raw, dc, fmagic, one, e);
+                load_pairs(row_o, lane_off, active, raw, dc, fmagic, one, o);
+                // vertical lifting on column pairs; the finished (low, high) row values of column s land in Q[c][s]
+                float2 Q[NC][NS];
+#pragma unroll
+                for (int c = 0; c < NC; c++)
+#pragma unroll
+                    for (int j = 0; j < NP; j++) {
+                        const float2 d1 = lift97x2(po[c][j], pe[c][j], e[c][j], A2, one);
+                        const float2 s1 = lift97x2(pe[c][j], d1p[c][j], d1, B2, one);
+                        const float2 d2 = lift97x2(d1p[c][j], s1p[c][j], s1, G2, one);
+                        const float2 s2 = lift97x2(s1p[c][j], d2p[c][j], d2, D2, one);
+                        Q[c][2 * j] = make_float2(__fmul_rn(s2.x, J2K_INVK), __fmul_rn(d2.x, J2K_K));
+                        Q[c][2 * j + 1] = make_float2(__fmul_rn(s2.y, J2K_INVK), __fmul_rn(d2.y, J2K_K));
+                        pe[c][j] = e[c][j]; po[c][j] = o[c][j]; d1p[c][j] = d1; s1p[c][j] = s1; d2p[c][j] = d2;
+                    }
+                if (it < 2 * LAG) continue;  // warm-up of the vertical window (warp-uniform)
+                const int ky = ky0 + it - 2 * LAG;
+                const int yl = ky - py, yh = ky;
+                const bool row_l = st && yl >= 0 && yl < lh, row_h = st && yh < hh;
+#pragma unroll
+                for (int c = 0; c < NC; c++) {
+                    // horizontal lifting of both rows at once: E_j = Q[2j], O_j = Q[2j+1]
+                    float2 E[NP + 1], O[NP + 1];  // O[0] = previous lane's last, E[NP] = next lane's first
+#pragma unroll
+                    for (int j = 0; j < NP; j++) { E[j] = Q[c][2 * j]; O[j + 1] = Q[c][2 * j + 1]; }
+                    E[NP] = shfl_down2(E[0]);
+#pragma unroll
+                    for (int j = 0; j < NP; j++) O[j + 1] = lift97x2(O[j + 1], E[j], E[j + 1], A2, one);
+                    O[0] = shfl_up2(O[NP]);
+#pragma unroll
+                    for (int j = 0; j < NP; j++) E[j] = lift97x2(E[j], O[j], O[j + 1], B2, one);
+                    E[NP] = shfl_down2(E[0]);
+#pragma unroll
+                    for (int j = 0; j < NP; j++) O[j + 1] = lift97x2(O[j + 1], E[j], E[j + 1], G2, one);
+                    O[0] = shfl_up2(O[NP]);
+#pragma unroll
+                    for (int j = 0; j < NP; j++) E[j] = lift97x2(E[j], O[j], O[j + 1], D2, one);
+                    int q_ll[NP], q_hl[NP], q_lh[NP], q_hh[NP];
+#pragma unroll
+                    for (int j = 0; j < NP; j++) {
+                        const float2 ve = mul2(E[j], splat2(J2K_INVK)), vo = mul2(O[j + 1], splat2(J2K_K));
+                        // q = rint(c / step') from the correctly rounded reciprocal (Markstein), both rows at once
+                        const float2 e0 = mul2(ve, rcpE), o0 = mul2(vo, rcpO);
+                        const float2 re = fma2(fma2(e0, nstE, ve), rcpE, e0), ro = fma2(fma2(o0, nstO, vo), rcpO, o0);
+                        q_ll[j] = raw_ll ? __float_as_int(ve.x) : __float2int_rn(re.x);
+                        q_lh[j] = raw_lh ? __float_as_int(ve.y) : __float2int_rn(re.y);
+                        q_hl[j] = raw_hl ? __float_as_int(vo.x) : __float2int_rn(ro.x);
+                        q_hh[j] = raw_hh ? __float_as_int(vo.y) : __float2int_rn(ro.y);
+                    }
+                    if (row_l) {
+                        store_vec(p_ll + c * cs_ll + (long long)yl * rs_ll, q_ll);
+                        store_vec(p_hl + c * cs_b + (long long)yl * rs_b, q_hl);
+                    }
+                    if (row_h) {
+                        store_vec(p_lh + c * cs_b + (long long)yh * rs_b, q_lh);
+                        store_vec(p_hh + c * cs_b + (long long)yh * rs_b, q_hh);
+                    }
+                }
+            }
+        } else {
+            const int sh_ll = S.q[0].shift, sh_hl = S.q[1].shift, sh_lh = S.q[2].shift, sh_hh = S.q[3].shift;
+            int pe[NC][NS], po[NC][NS], d1p[NC][NS];
+#pragma unroll
+            for (int c = 0; c < NC; c++)
+#pragma unroll
+                for (int s = 0; s < NS; s++) { pe[c][s] = 0; po[c][s] = 0; d1p[c][s] = 0; }
+#pragma unroll 1
+            for (int it = 0; it < n_it; it++) {
+                __syncwarp();
+                if (pj < n_it) issue();
+                mbar_wait(rw.bars + 8 * cslot, (rw.phase >> cslot) & 1u);
+                rw.phase ^= 1u << cslot;
+                const smem_t row_e = rw.ring + cslot * STAGEB;
+                const smem_t row_o = row_e + ROWB;
+                cslot = (cslot + 1 == D) ? 0 : cslot + 1;
+
+                int e[NC][NS], o[NC][NS], lo[NC][NS], hi[NC][NS];
+                if (fix) fix_halo(row_e, row_o, lane, fix_l, fix_r, w, vb);
+                load_scalar(row_e, lane_off, active, raw, dc, e);
+                load_scalar(row_o, lane_off, active, raw, dc, o);
+#pragma unroll
+                for (int c = 0; c < NC; c++)
+#pragma unroll
+                    for (int s = 0; s < NS; s++) {
+                        const int d = po[c][s] - ((pe[c][s] + e[c][s]) >> 1);
+                        const int sv = pe[c][s] + ((d1p[c][s] + d + 2) >> 2);
+                        lo[c][s] = sv; hi[c][s] = d;
+                        pe[c][s] = e[c][s]; po[c][s] = o[c][s]; d1p[c][s] = d;
+                    }
+                if (it < 2 * LAG) continue;
+                const int ky = ky0 + it - 2 * LAG;
+                const int yl = ky - py, yh = ky;
+                const bool row_l = st && yl >= 0 && yl < lh, row_h = st && yh < hh;
+#pragma unroll
+                for (int c = 0; c < NC; c++) {
+                    Slow::hlift(lo[c], false);
+                    Slow::hlift(hi[c], false);
+                    int q_a[NP], q_b[NP];
+                    if (row_l) {
+#pragma unroll
+                        for (int j = 0; j < NP; j++) { q_a[j] = (int)((unsigned)lo[c][2 * j] << sh_ll); q_b[j] = (int)((unsigned)lo[c][2 * j + 1] << sh_hl); }
+                        store_vec(p_ll + c * cs_ll + (long long)yl * rs_ll, q_a);
+                        store_vec(p_hl + c * cs_b + (long long)yl * rs_b, q_b);
+                    }
+                    if (row_h) {
+#pragma unroll
+                        for (int j = 0; j < NP; j++) { q_a[j] = (int)((unsigned)hi[c][2 * j] << sh_lh); q_b[j] = (int)((unsigned)hi[c][2 * j + 1] << sh_hh); }
+                        store_vec(p_lh + c * cs_b + (long long)yh * rs_b, q_a);
+                        store_vec(p_hh + c * cs_b + (long long)yh * rs_b, q_b);
+                    }
+                }
+            }
+        }
+        (void)lane_s;
+    }
+};
+
+// ------------------------------------------------------------------ job loop shared by both directions
+
+struct RingJob { int seg, item, chunk, strip; };
+
+// Claims the next job (warp-uniform result); returns false when the list is exhausted.
+__device__ __forceinline__ bool ring_claim(const RingArgs& A, int lane, RingJob& J) {
+    int job = 0;
+    if (lane == 0) job = (int)atomicAdd(A.ctl, 1u);
+    job = __shfl_sync(0xffffffffu, job, 0);
+    if (job >= A.total_jobs) return false;
+    int k = 0;
+    while (k + 1 < A.nseg && job >= A.seg[k].job_end) k++;
+    const int local = job - A.seg[k].job_begin;
+    const int ns = A.seg[k].nstrips, nc = A.seg[k].nchunks;
+    J.seg = k;
+    J.strip = local % ns;
+    J.chunk = (local / ns) % nc;
+    J.item = local / (ns * nc);
+    return true;
+}
+
+// Acquire: the producers of this job's input have published their stores.
+__device__ __forceinline__ void ring_wait_dep(const RingArgs& A, const RingSeg& S, int item, int lane) {
+    if (S.dep_seg < 0) return;
+    if (lane == 0) {
+        const unsigned* d = A.ctl + A.seg[S.dep_seg].done_base + item / S.dep_div;
+        while (ld_relaxed(d) < (unsigned)S.dep_target) backoff();  // relaxed polling: no L1 invalidation per probe
+        fence_acquire();
+        fence_proxy_async();  // the staged reads that follow go through the async proxy
+    }
+    __syncwarp();
+}
+
+// Release: every lane's stores of this job happen-before the counter increment.
+__device__ __forceinline__ void ring_signal(const RingArgs& A, const RingSeg& S, int item, int lane) {
+    __syncwarp();
+    if (lane == 0) red_release_add(A.ctl + S.done_base + item, 1u);
+}
+
+// The last warp to retire puts the control block back to zero for the next launch.
+__device__ __forceinline__ void ring_retire(const RingArgs& A, int lane) {
+    const unsigned total_warps = gridDim.x * (blockDim.x >> 5);
+    unsigned last = 0;
+    if (lane == 0) {
+        __threadfence();
+        last = atomicAdd(A.ctl + 1, 1u) == total_warps - 1 ? 1u : 0u;
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last) {
+        for (int i = lane; i < A.n_ctl; i += 32) A.ctl[i] = 0;
+        __threadfence();
+    }
+}
+
+__device__ __forceinline__ void ring_warp_init(unsigned char* smem, RingWarp& rw, int lane) {
+    const int wib = threadIdx.x >> 5;
+    rw.ring = smem_handle(smem + wib * J2K_RING_WARP_SMEM);
+    rw.bars = rw.ring + J2K_RING_BYTES;
+    rw.phase = 0;
+    if (lane == 0) {
+        for (int s = 0; s < J2K_RING_MAXD; s++) mbar_init(rw.bars + 8 * s, 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+}
+
+// WT: 53 / 97.  IN1 / NC1 / MCT1 / SG1: the image-side variant of segments with first == 1
+// (raw interleaved words, or planar int32 / float32 for the wavelet-package API); deeper levels always
+// read planar working-type LL planes.
+template <int WT, int NP1, int NC1, int IN1, int MCT1, int SG1>
+__global__ void __launch_bounds__(J2K_RING_WARPS * 32, 4) fwd_ring_kernel(const __grid_constant__ RingArgs A) {
+    J2K_SMEM_DECL(smem);
+    const int lane = threadIdx.x & 31;
+    RingWarp rw;
+    ring_warp_init(smem, rw, lane);
+    rw.one = A.one;
+    RingJob J;
+    while (ring_claim(A, lane, J)) {
+        const RingSeg& S = A.seg[J.seg];
+        ring_wait_dep(A, S, J.item, lane);
+        if (S.first) FwdRing<WT, NP1, NC1, IN1, MCT1, SG1>::run(S, A.raw, J.item, J.chunk, J.strip, rw, lane);
+        else FwdRing<WT, 4, 1, (WT == 53 ? IN_I32 : IN_F32), MCTK_NONE, 0>::run(S, A.raw, J.item, J.chunk, J.strip, rw, lane);
+        ring_signal(A, S, J.item, lane);
+    }
+    ring_retire(A, lane);
+}
+
+}  // namespace j2k

@@ -188,7 +188,7 @@ def load(path: str | None = None) -> C.CDLL:
     `path` exists for the test-suite's CPU emulator build of the same sources (tests/emu);
     the product always loads LIB_PATH.
     """
-    path = path or LIB_PATH
+    path = path or os.environ.get("J2K_B200_LIB") or LIB_PATH  # the env override is for kernel experiments (profiles/)
     if path in _libs:
         return _libs[path]
     if not os.path.exists(path):

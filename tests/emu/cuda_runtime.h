@@ -16,10 +16,12 @@
 #include <algorithm>
 #include <functional>
 
+#define J2K_EMU 1
 #define __global__
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __grid_constant__
 #define __launch_bounds__(...)
 #define __restrict__
@@ -31,6 +33,8 @@ struct int2 { int x, y; };
 struct int4 { int x, y, z, w; };
 struct uint2 { unsigned x, y; };
 struct uint4 { unsigned x, y, z, w; };
+struct float2 { float x, y; };
+static inline float2 make_float2(float x, float y) { return {x, y}; }
 static inline int2 make_int2(int x, int y) { return {x, y}; }
 static inline int4 make_int4(int x, int y, int z, int w) { return {x, y, z, w}; }
 static inline uint2 make_uint2(unsigned x, unsigned y) { return {x, y}; }
@@ -49,6 +53,7 @@ static inline double __dmul_rn(double a, double b) { volatile double r = a * b; 
 static inline double __ddiv_rn(double a, double b) { volatile double r = a / b; return r; }
 static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
 static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
+static inline float __uint_as_float(unsigned i) { float f; memcpy(&f, &i, 4); return f; }
 static inline int __float2int_rn(float f) {
     if (f != f) return 0;
     if (f >= 2147483648.0f) return 2147483647;
@@ -60,7 +65,29 @@ namespace emu {
 uint32_t shfl_exchange(uint32_t v, int src_lane);  // yields the calling fiber
 int lane_id();
 void launch(unsigned grid, unsigned block, const std::function<void()>& body);
+unsigned char* smem();  // per-CTA dynamic shared memory (warps of a CTA run one after the other)
 }  // namespace emu
+
+static inline void __syncwarp(unsigned = 0xffffffffu) { emu::shfl_exchange(0, emu::lane_id()); }
+template <typename T> static inline T __shfl_sync(unsigned, T v, int src) {
+    static_assert(sizeof(T) == 4, "emu shuffles move 32-bit values");
+    uint32_t b; memcpy(&b, &v, 4);
+    b = emu::shfl_exchange(b, src & 31);
+    T r; memcpy(&r, &b, 4); return r;
+}
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
+static inline void __threadfence() {}
+static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
+    unsigned long long src = ((unsigned long long)y << 32) | x;
+    unsigned r = 0;
+    for (int i = 0; i < 4; i++) {
+        unsigned sel = (s >> (4 * i)) & 0xF;
+        unsigned b = (unsigned)(src >> (8 * (sel & 7))) & 0xFF;
+        if (sel & 8) b = (b & 0x80) ? 0xFF : 0x00;
+        r |= b << (8 * i);
+    }
+    return r;
+}
 
 template <typename T> static inline T __shfl_down_sync(unsigned, T v, int d) {
     static_assert(sizeof(T) == 4, "emu shuffles move 32-bit values");
@@ -109,4 +136,7 @@ static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return cuda
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
 
+static inline cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
+
 #define J2K_LAUNCH(kernel, grid, block, stream, ...) emu::launch((grid), (block), [&]() { kernel(__VA_ARGS__); })
+#define J2K_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...) emu::launch((grid), (block), [&]() { kernel(__VA_ARGS__); })

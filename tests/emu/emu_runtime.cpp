@@ -27,6 +27,11 @@ void trampoline() {
 
 int lane_id() { return g_cur; }
 
+unsigned char* smem() {
+    alignas(128) static unsigned char buf[256 * 1024];
+    return buf;
+}
+
 uint32_t shfl_exchange(uint32_t v, int src) {
     int me = g_cur;
     unsigned r = g_round[me]++;
