@@ -577,6 +577,8 @@ int build_ring_fwd(const Spec& s, Plan& P, const std::vector<long long>& tab) {
             else if (b.mode == Q_QUANT) { q.step = b.step / b.scale; q.rcp = 1.0f / q.step; }  // scale is a power of two: exact
             else if (b.mode != Q_RAW) return 0;
         }
+        g.rcpE = make_float2(g.q[0].rcp, g.q[2].rcp); g.nstE = make_float2(-g.q[0].step, -g.q[2].step);
+        g.rcpO = make_float2(g.q[1].rcp, g.q[3].rcp); g.nstO = make_float2(-g.q[1].step, -g.q[3].step);
         g.w = a.w; g.h = a.h; g.py = a.py; g.lw = a.lw; g.lh = a.lh; g.Kx = a.Kx; g.Ky = a.Ky;
         g.n_items = a.n_items;
         g.first = first ? 1 : 0;
@@ -636,6 +638,8 @@ int ring_blocks_per_sm(const void* fn) {
     return 1;
 #else
     int n = 0;
+    if (J2K_RING_CTA_SMEM > 48 * 1024 &&
+        cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, J2K_RING_CTA_SMEM) != cudaSuccess) return -1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, J2K_RING_WARPS * 32, J2K_RING_CTA_SMEM) != cudaSuccess) return -1;
     return n;
 #endif

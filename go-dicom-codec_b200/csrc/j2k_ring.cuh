@@ -32,6 +32,9 @@ namespace j2k {
 #define J2K_RING_BYTES 8704  // staging bytes per warp (8 stages of two 512 B + 32 B rows)
 #endif
 #define J2K_RING_MAXD 8
+#ifndef J2K_RING_MINB
+#define J2K_RING_MINB 3      // resident CTAs per SM the register allocation targets (168 registers: no spills in the 9/7 loop)
+#endif
 #define J2K_RING_WARP_SMEM (J2K_RING_BYTES + J2K_RING_MAXD * 8)
 #define J2K_RING_CTA_SMEM (J2K_RING_WARPS * J2K_RING_WARP_SMEM)
 
@@ -51,6 +54,7 @@ struct RingSeg {
     long long x_row_bytes;             // row pitch in bytes (multiple of 16)
     BandIO ll, hl, lh_, hh;
     FastQ q[4];
+    float2 rcpE, nstE, rcpO, nstO;     // quantizer pairs (LL, LH) and (HL, HH): reciprocal and negated step' (9/7)
 };
 
 struct RingArgs {
@@ -458,17 +462,19 @@ struct FwdRing {
         if constexpr (WT == 97) {
             const float2 A2 = splat2(J2K_ALPHA), B2 = splat2(J2K_BETA), G2 = splat2(J2K_GAMMA), D2 = splat2(J2K_DELTA);
             // quantizer constants per row pair: E positions hold (LL, LH), O positions hold (HL, HH)
-            const float2 rcpE = make_float2(S.q[0].rcp, S.q[2].rcp), nstE = make_float2(-S.q[0].step, -S.q[2].step);
-            const float2 rcpO = make_float2(S.q[1].rcp, S.q[3].rcp), nstO = make_float2(-S.q[1].step, -S.q[3].step);
+            const float2 rcpE = S.rcpE, nstE = S.nstE, rcpO = S.rcpO, nstO = S.nstO;
             const bool raw_ll = S.q[0].mode != Q_QUANT, raw_hl = S.q[1].mode != Q_QUANT, raw_lh = S.q[2].mode != Q_QUANT,
                        raw_hh = S.q[3].mode != Q_QUANT;
-            float2 pe[NC][NP], po[NC][NP], s1p[NC][NP], d1p[NC][NP], d2p[NC][NP];
+            // the shape of every level but the last: LL stays float32 (next level's input), the details are quantized
+            const bool std_modes = raw_ll && !raw_hl && !raw_lh && !raw_hh;
+            struct VState { float2 pe[NC][NP], po[NC][NP], s1p[NC][NP], d1p[NC][NP], d2p[NC][NP]; };
+            VState sa, sb;
 #pragma unroll
             for (int c = 0; c < NC; c++)
 #pragma unroll
-                for (int j = 0; j < NP; j++) { pe[c][j] = po[c][j] = s1p[c][j] = d1p[c][j] = d2p[c][j] = make_float2(0.f, 0.f); }
-#pragma unroll 1
-            for (int it = 0; it < n_it; it++) {
+                for (int j = 0; j < NP; j++) { sa.pe[c][j] = sa.po[c][j] = sa.s1p[c][j] = sa.d1p[c][j] = sa.d2p[c][j] = make_float2(0.f, 0.f); }
+            // one iteration: consumes the vertical window state `in`, leaves the advanced state in `out`
+            auto body = [&](int it, const VState& in, VState& out) {
                 // the slot of iteration it-1 (slot D-1 when it == 0) is free once every lane is past its arithmetic: refill it
                 __syncwarp();
                 if (pj < n_it) issue();
@@ -478,25 +484,24 @@ struct FwdRing {
                 const smem_t row_o = row_e + ROWB;
                 cslot = (cslot + 1 == D) ? 0 : cslot + 1;
 
-                float2 e[NC][NP], o[NC][NP];
                 if (fix) fix_halo(row_e, row_o, lane, fix_l, fix_r, w, vb);
-                load_pairs(row_e, lane_off, active, raw, dc, fmagic, one, e);
-                load_pairs(row_o, lane_off, active, raw, dc, fmagic, one, o);
+                load_pairs(row_e, lane_off, active, raw, dc, fmagic, one, out.pe);
+                load_pairs(row_o, lane_off, active, raw, dc, fmagic, one, out.po);
                 // vertical lifting on column pairs; the finished (low, high) row values of column s land in Q[c][s]
                 float2 Q[NC][NS];
 #pragma unroll
                 for (int c = 0; c < NC; c++)
 #pragma unroll
                     for (int j = 0; j < NP; j++) {
-                        const float2 d1 = lift97x2(po[c][j], pe[c][j], e[c][j], A2, one);
-                        const float2 s1 = lift97x2(pe[c][j], d1p[c][j], d1, B2, one);
-                        const float2 d2 = lift97x2(d1p[c][j], s1p[c][j], s1, G2, one);
-                        const float2 s2 = lift97x2(s1p[c][j], d2p[c][j], d2, D2, one);
+                        const float2 d1 = lift97x2(in.po[c][j], in.pe[c][j], out.pe[c][j], A2, one);
+                        const float2 s1 = lift97x2(in.pe[c][j], in.d1p[c][j], d1, B2, one);
+                        const float2 d2 = lift97x2(in.d1p[c][j], in.s1p[c][j], s1, G2, one);
+                        const float2 s2 = lift97x2(in.s1p[c][j], in.d2p[c][j], d2, D2, one);
                         Q[c][2 * j] = make_float2(__fmul_rn(s2.x, J2K_INVK), __fmul_rn(d2.x, J2K_K));
                         Q[c][2 * j + 1] = make_float2(__fmul_rn(s2.y, J2K_INVK), __fmul_rn(d2.y, J2K_K));
-                        pe[c][j] = e[c][j]; po[c][j] = o[c][j]; d1p[c][j] = d1; s1p[c][j] = s1; d2p[c][j] = d2;
+                        out.d1p[c][j] = d1; out.s1p[c][j] = s1; out.d2p[c][j] = d2;
                     }
-                if (it < 2 * LAG) continue;  // warm-up of the vertical window (warp-uniform)
+                if (it < 2 * LAG) return;  // warm-up of the vertical window (warp-uniform)
                 const int ky = ky0 + it - 2 * LAG;
                 const int yl = ky - py, yh = ky;
                 const bool row_l = st && yl >= 0 && yl < lh, row_h = st && yh < hh;
@@ -506,29 +511,61 @@ struct FwdRing {
                     float2 E[NP + 1], O[NP + 1];  // O[0] = previous lane's last, E[NP] = next lane's first
 #pragma unroll
                     for (int j = 0; j < NP; j++) { E[j] = Q[c][2 * j]; O[j + 1] = Q[c][2 * j + 1]; }
+                    // each step as three passes over the NP independent pairs (sum, scale, accumulate) so that the
+                    // dependent triples of different pairs interleave in the instruction stream
+                    float2 T[NP];
                     E[NP] = shfl_down2(E[0]);
 #pragma unroll
-                    for (int j = 0; j < NP; j++) O[j + 1] = lift97x2(O[j + 1], E[j], E[j + 1], A2, one);
+                    for (int j = 0; j < NP; j++) T[j] = add2(E[j], E[j + 1]);
+#pragma unroll
+                    for (int j = 0; j < NP; j++) T[j] = mul2(T[j], A2);
+#pragma unroll
+                    for (int j = 0; j < NP; j++) O[j + 1] = addp2(T[j], O[j + 1], one);
                     O[0] = shfl_up2(O[NP]);
 #pragma unroll
-                    for (int j = 0; j < NP; j++) E[j] = lift97x2(E[j], O[j], O[j + 1], B2, one);
+                    for (int j = 0; j < NP; j++) T[j] = add2(O[j], O[j + 1]);
+#pragma unroll
+                    for (int j = 0; j < NP; j++) T[j] = mul2(T[j], B2);
+#pragma unroll
+                    for (int j = 0; j < NP; j++) E[j] = addp2(T[j], E[j], one);
                     E[NP] = shfl_down2(E[0]);
 #pragma unroll
-                    for (int j = 0; j < NP; j++) O[j + 1] = lift97x2(O[j + 1], E[j], E[j + 1], G2, one);
+                    for (int j = 0; j < NP; j++) T[j] = add2(E[j], E[j + 1]);
+#pragma unroll
+                    for (int j = 0; j < NP; j++) T[j] = mul2(T[j], G2);
+#pragma unroll
+                    for (int j = 0; j < NP; j++) O[j + 1] = addp2(T[j], O[j + 1], one);
                     O[0] = shfl_up2(O[NP]);
 #pragma unroll
-                    for (int j = 0; j < NP; j++) E[j] = lift97x2(E[j], O[j], O[j + 1], D2, one);
+                    for (int j = 0; j < NP; j++) T[j] = add2(O[j], O[j + 1]);
+#pragma unroll
+                    for (int j = 0; j < NP; j++) T[j] = mul2(T[j], D2);
+#pragma unroll
+                    for (int j = 0; j < NP; j++) E[j] = addp2(T[j], E[j], one);
                     int q_ll[NP], q_hl[NP], q_lh[NP], q_hh[NP];
+                    // q = rint(c / step') from the correctly rounded reciprocal (Markstein), both rows at once
+                    if (std_modes) {
 #pragma unroll
-                    for (int j = 0; j < NP; j++) {
-                        const float2 ve = mul2(E[j], splat2(J2K_INVK)), vo = mul2(O[j + 1], splat2(J2K_K));
-                        // q = rint(c / step') from the correctly rounded reciprocal (Markstein), both rows at once
-                        const float2 e0 = mul2(ve, rcpE), o0 = mul2(vo, rcpO);
-                        const float2 re = fma2(fma2(e0, nstE, ve), rcpE, e0), ro = fma2(fma2(o0, nstO, vo), rcpO, o0);
-                        q_ll[j] = raw_ll ? __float_as_int(ve.x) : __float2int_rn(re.x);
-                        q_lh[j] = raw_lh ? __float_as_int(ve.y) : __float2int_rn(re.y);
-                        q_hl[j] = raw_hl ? __float_as_int(vo.x) : __float2int_rn(ro.x);
-                        q_hh[j] = raw_hh ? __float_as_int(vo.y) : __float2int_rn(ro.y);
+                        for (int j = 0; j < NP; j++) {
+                            const float2 ve = mul2(E[j], splat2(J2K_INVK)), vo = mul2(O[j + 1], splat2(J2K_K));
+                            const float2 e0 = mul2(ve, rcpE), o0 = mul2(vo, rcpO);
+                            const float2 re = fma2(fma2(e0, nstE, ve), rcpE, e0), ro = fma2(fma2(o0, nstO, vo), rcpO, o0);
+                            q_ll[j] = __float_as_int(ve.x);
+                            q_lh[j] = __float2int_rn(re.y);
+                            q_hl[j] = __float2int_rn(ro.x);
+                            q_hh[j] = __float2int_rn(ro.y);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < NP; j++) {
+                            const float2 ve = mul2(E[j], splat2(J2K_INVK)), vo = mul2(O[j + 1], splat2(J2K_K));
+                            const float2 e0 = mul2(ve, rcpE), o0 = mul2(vo, rcpO);
+                            const float2 re = fma2(fma2(e0, nstE, ve), rcpE, e0), ro = fma2(fma2(o0, nstO, vo), rcpO, o0);
+                            q_ll[j] = raw_ll ? __float_as_int(ve.x) : __float2int_rn(re.x);
+                            q_lh[j] = raw_lh ? __float_as_int(ve.y) : __float2int_rn(re.y);
+                            q_hl[j] = raw_hl ? __float_as_int(vo.x) : __float2int_rn(ro.x);
+                            q_hh[j] = raw_hh ? __float_as_int(vo.y) : __float2int_rn(ro.y);
+                        }
                     }
                     if (row_l) {
                         store_vec(p_ll + c * cs_ll + (long long)yl * rs_ll, q_ll);
@@ -539,6 +576,13 @@ struct FwdRing {
                         store_vec(p_hh + c * cs_b + (long long)yh * rs_b, q_hh);
                     }
                 }
+            };
+            // two iterations per trip with the window state ping-ponging between sa and sb: no register shuffling
+#pragma unroll 1
+            for (int it = 0; it < n_it; it += 2) {
+                body(it, sa, sb);
+                if (it + 1 >= n_it) break;
+                body(it + 1, sb, sa);
             }
         } else {
             const int sh_ll = S.q[0].shift, sh_hl = S.q[1].shift, sh_lh = S.q[2].shift, sh_hh = S.q[3].shift;
@@ -668,7 +712,7 @@ __device__ __forceinline__ void ring_warp_init(unsigned char* smem, RingWarp& rw
 // (raw interleaved words, or planar int32 / float32 for the wavelet-package API); deeper levels always
 // read planar working-type LL planes.
 template <int WT, int NP1, int NC1, int IN1, int MCT1, int SG1>
-__global__ void __launch_bounds__(J2K_RING_WARPS * 32, 4) fwd_ring_kernel(const __grid_constant__ RingArgs A) {
+__global__ void __launch_bounds__(J2K_RING_WARPS * 32, J2K_RING_MINB) fwd_ring_kernel(const __grid_constant__ RingArgs A) {
     J2K_SMEM_DECL(smem);
     const int lane = threadIdx.x & 31;
     RingWarp rw;
