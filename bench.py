@@ -144,7 +144,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--frames", type=int, default=8, help="C2 frames per rank per step")
+    ap.add_argument("--frames", type=int, default=16, help="C2 frames per rank per step")
+    ap.add_argument("--streams", type=int, default=2, help="streams the resident steps alternate over (1 = serial)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
@@ -176,12 +177,19 @@ def main():
     d_in = torch.empty((B, frame_bytes), dtype=torch.uint8, device="cuda")
     for f in range(B):
         d_in[f].copy_(torch.from_numpy(host[f % host.shape[0]]))
-    d_out = torch.empty((B, PIX), dtype=torch.int32, device="cuda")
-    stream = torch.cuda.Stream()  # a real (non-NULL) stream handle: kernels and the timing events share it
+    # Steps are independent batches: consecutive steps alternate between two streams (each with its own output buffer
+    # and, inside the library, its own scratch) so that the short dependent tail of one launch (the deep levels of the
+    # last frame) runs under the head of the next launch.  --streams 1 serialises the steps.
+    NS = max(1, args.streams)
+    d_outs = [torch.empty((B, PIX), dtype=torch.int32, device="cuda") for _ in range(NS)]
+    d_out = d_outs[0]
+    streams = [torch.cuda.Stream() for _ in range(NS)]  # real (non-NULL) stream handles: kernels and timing events share them
+    stream = streams[0]
     torch.cuda.synchronize()
 
-    def step():
-        ctx.forward_device(fp, B, d_in.data_ptr(), frame_bytes, d_out.data_ptr(), stream=stream.cuda_stream)
+    def step(i=0):
+        k = i % NS
+        ctx.forward_device(fp, B, d_in.data_ptr(), frame_bytes, d_outs[k].data_ptr(), stream=streams[k].cuda_stream)
 
     def barrier():
         if use_dist:
@@ -189,17 +197,23 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident timing (value)
-    for _ in range(warm):
-        step()
+    for i in range(warm * NS):
+        step(i)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     l0 = ctx.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        step()
-    e1.record(stream)
+    e0.record(streams[0])
+    for st in streams[1:]:
+        st.wait_event(e0)
+    for i in range(args.steps):
+        step(i)
+    for st in streams[1:]:
+        ev = torch.cuda.Event()
+        ev.record(st)
+        streams[0].wait_event(ev)
+    e1.record(streams[0])
     barrier()
     launches = ctx.launch_count - l0
     ms_total = e0.elapsed_time(e1)
@@ -287,7 +301,8 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": B, "direction": "forward", "levels": LEVELS,
                        "cache": "inputs larger than L2 (%.0f MB in + %.0f MB out per step per GPU)" % (B * frame_bytes / 1e6, B * PIX * 4 / 1e6),
-                       "parallelism": "frame-sharded, %d rank(s), no collective" % world},
+                       "parallelism": "frame-sharded, %d rank(s), no collective" % world,
+                       "streams": NS},
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": "Mpixel/s", "h2d_bytes_per_step": B * frame_bytes, "d2h_bytes_per_step": B * PIX * 4,
                     "steps": e2e_steps, "matches_resident": same},

@@ -1231,10 +1231,14 @@ int spec_from_inv(const j2k_inv_params* p, bool want_planes, Spec& s) {
     return 0;
 }
 
-int get_plan(DeviceCtx& d, const Spec& s, const void* pblob, size_t pbytes, int nframes, long long frame_samples, Plan** out) {
+// A plan owns its scratch (LL ping-pong planes, job-control block): plans are cached per stream so that launches the
+// caller enqueues on different streams may overlap (the tail of one batch under the head of the next).
+int get_plan(DeviceCtx& d, const Spec& s, const void* pblob, size_t pbytes, int nframes, long long frame_samples, Plan** out,
+             const void* stream_tag = nullptr) {
     std::string key((const char*)pblob, pbytes);
-    char tail[96];
-    snprintf(tail, sizeof tail, "|%d|%d|%lld|%d|%d|%d", s.fwd ? 1 : 0, nframes, frame_samples, s.planar_in ? 1 : 0, s.want_planes ? 1 : 0, s.direct ? 1 : 0);
+    char tail[128];
+    snprintf(tail, sizeof tail, "|%d|%d|%lld|%d|%d|%d|%p", s.fwd ? 1 : 0, nframes, frame_samples, s.planar_in ? 1 : 0, s.want_planes ? 1 : 0,
+             s.direct ? 1 : 0, stream_tag);
     key += tail;
     auto it = d.plans.find(key);
     if (it != d.plans.end()) { *out = it->second.get(); return 0; }
@@ -1575,7 +1579,7 @@ int j2k_forward_device(j2k_ctx* ctx, int dev, const j2k_fwd_params* p, int nfram
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceCtx& d = ctx->devs[dev];
     Plan* P = nullptr;
-    if ((rc = get_plan(d, s, p, sizeof *p, nframes, (long long)(frame_stride_bytes / bps), &P))) return rc;
+    if ((rc = get_plan(d, s, p, sizeof *p, nframes, (long long)(frame_stride_bytes / bps), &P, cuda_stream))) return rc;
     rc = run_plan(ctx, *P, (void*)d_pixels, d_coeffs, nullptr, false, cuda_stream ? (cudaStream_t)cuda_stream : d.s_main);
     return rc < 0 ? rc : J2K_OK;
 }
@@ -1625,7 +1629,7 @@ int j2k_inverse_device(j2k_ctx* ctx, int dev, const j2k_inv_params* p, int nfram
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceCtx& d = ctx->devs[dev];
     Plan* P = nullptr;
-    if ((rc = get_plan(d, s, p, sizeof *p, nframes, (long long)(frame_stride_bytes / bps), &P))) return rc;
+    if ((rc = get_plan(d, s, p, sizeof *p, nframes, (long long)(frame_stride_bytes / bps), &P, cuda_stream))) return rc;
     rc = run_plan(ctx, *P, d_pixels, (void*)d_coeffs, d_planes, false, cuda_stream ? (cudaStream_t)cuda_stream : d.s_main);
     return rc < 0 ? rc : J2K_OK;
 }

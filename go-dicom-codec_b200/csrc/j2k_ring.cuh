@@ -27,7 +27,9 @@
 namespace j2k {
 
 #define J2K_RING_MAXSEG 14   // (tile class, level) segments one launch can chain
+#ifndef J2K_RING_WARPS
 #define J2K_RING_WARPS 4     // warps per CTA
+#endif
 #ifndef J2K_RING_BYTES
 #define J2K_RING_BYTES 8704  // staging bytes per warp (8 stages of two 512 B + 32 B rows)
 #endif
@@ -711,8 +713,13 @@ __device__ __forceinline__ void ring_warp_init(unsigned char* smem, RingWarp& rw
 // WT: 53 / 97.  IN1 / NC1 / MCT1 / SG1: the image-side variant of segments with first == 1
 // (raw interleaved words, or planar int32 / float32 for the wavelet-package API); deeper levels always
 // read planar working-type LL planes.
+#ifdef J2K_RING_MAXNREG
+#define J2K_RING_BOUNDS __maxnreg__(J2K_RING_MAXNREG)
+#else
+#define J2K_RING_BOUNDS __launch_bounds__(J2K_RING_WARPS * 32, J2K_RING_MINB)
+#endif
 template <int WT, int NP1, int NC1, int IN1, int MCT1, int SG1>
-__global__ void __launch_bounds__(J2K_RING_WARPS * 32, J2K_RING_MINB) fwd_ring_kernel(const __grid_constant__ RingArgs A) {
+__global__ void J2K_RING_BOUNDS fwd_ring_kernel(const __grid_constant__ RingArgs A) {
     J2K_SMEM_DECL(smem);
     const int lane = threadIdx.x & 31;
     RingWarp rw;

@@ -1,6 +1,6 @@
 run() { # label, env...
   label=$1; shift
-  env "$@" timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/b.json 2> gpurun_out/b.err
+  env "$@" > gpurun_out/b.json 2> gpurun_out/b.err
   python - "$label" <<'PY'
 import json,sys
 try:
@@ -9,10 +9,8 @@ except Exception as e:
     print(sys.argv[1], "FAILED", open("gpurun_out/b.err").read()[-300:])
 PY
 }
-B=go-dicom-codec_b200/csrc/build
-run mb3_17k J2K_B200_LIB=$B/libj2kb200_mb3_17k.so
-run mb3_17k_pl J2K_B200_LIB=$B/libj2kb200_mb3_17k.so J2K_RING_PER_LEVEL=1
-run mb2_17k J2K_B200_LIB=$B/libj2kb200_mb2_17k.so
-run mb2_17k_pl J2K_B200_LIB=$B/libj2kb200_mb2_17k.so J2K_RING_PER_LEVEL=1
-run mb3_17k_c128 J2K_B200_LIB=$B/libj2kb200_mb3_17k.so J2K_RING_CHUNK=128
-run mb3_c128 J2K_RING_CHUNK=128
+timeout 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+run s1 timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-e2e --streams 1
+run s2 timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-e2e --streams 2
+run s3 timeout 300 python bench.py --steps 21 --warmup 3 --no-cpu-baseline --no-e2e --streams 3
+run s2f16 timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-e2e --streams 2 --frames 16
