@@ -148,6 +148,7 @@ def main():
     ap.add_argument("--streams", type=int, default=2, help="streams the resident steps alternate over (1 = serial)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-inverse", action="store_true", help="skip the supplementary inverse-direction leg")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -265,6 +266,40 @@ def main():
         "per_level_ms": {str(k): statistics.mean(v) for k, v in sorted(per_level.items())},
     }
 
+    # ---- inverse direction, device-resident (supplementary: the headline metric is the forward step above)
+    inverse = None
+    if not args.no_inverse:
+        dec = j2kb200.decode_quant_steps(enc, LEVELS, BITS, False)
+        ip = abi.inv_params(W, H, 1, BITS, False, num_levels=LEVELS, reversible=False, steps=dec)
+        d_pix = [torch.empty((B, frame_bytes), dtype=torch.uint8, device="cuda") for _ in range(NS)]
+
+        def istep(i=0):
+            k = i % NS
+            ctx.inverse_device(ip, B, d_outs[0].data_ptr(), d_pix[k].data_ptr(), frame_bytes, stream=streams[k].cuda_stream)
+
+        for i in range(warm * NS):
+            istep(i)
+        barrier()
+        i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        i0.record(streams[0])
+        for st in streams[1:]:
+            st.wait_event(i0)
+        for i in range(args.steps):
+            istep(i)
+        for st in streams[1:]:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            streams[0].wait_event(ev)
+        i1.record(streams[0])
+        barrier()
+        t = torch.tensor([i0.elapsed_time(i1)], device="cuda")
+        if use_dist:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ims = float(t.item()) / args.steps
+        inverse = {"value": world * B * PIX / (ims * 1e-3) / 1e6, "unit": "Mpixel/s", "ms_per_step": ims,
+                   "step_frac_of_hbm_peak": step_alg / (ims * 1e-3) / 1e9 / peak,
+                   "what": "coefficients -> dequantize -> 6-level inverse 9/7 -> round -> +DC -> clamp -> pack u16 (D4-D13), resident"}
+
     # ---- end to end through the C ABI with host buffers (pinned), copies inside the timed region
     e2e_val, same, e2e_steps = None, None, 0
     if not args.no_e2e:
@@ -303,7 +338,7 @@ def main():
                        "cache": "inputs larger than L2 (%.0f MB in + %.0f MB out per step per GPU)" % (B * frame_bytes / 1e6, B * PIX * 4 / 1e6),
                        "parallelism": "frame-sharded, %d rank(s), no collective" % world,
                        "streams": NS},
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "inverse": inverse, "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": "Mpixel/s", "h2d_bytes_per_step": B * frame_bytes, "d2h_bytes_per_step": B * PIX * 4,
                     "steps": e2e_steps, "matches_resident": same},
             "gpu_launches": int(launches), "clocks": clocks,

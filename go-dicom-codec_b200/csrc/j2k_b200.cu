@@ -172,7 +172,7 @@ struct RingPlan {
     bool ok = false;
     RingArgs args;
     int WT = 0, NP1 = 0, NC1 = 0, IN1 = 0, MCT1 = 0, SG1 = 0;
-    int x_buf[J2K_RING_MAXSEG], ll_buf[J2K_RING_MAXSEG], band_buf[J2K_RING_MAXSEG];
+    int x_buf[J2K_RING_MAXSEG], ll_buf[J2K_RING_MAXSEG], band_buf[J2K_RING_MAXSEG], planes_buf[J2K_RING_MAXSEG];
     int level[J2K_RING_MAXSEG];
     unsigned grid = 0;
 };
@@ -625,25 +625,25 @@ int build_ring_fwd(const Spec& s, Plan& P, const std::vector<long long>& tab) {
     return 0;
 }
 
+int ring_blocks_per_sm(const void* fn, int smem_bytes) {
+#ifdef J2K_EMU
+    (void)fn; (void)smem_bytes;
+    return 1;
+#else
+    int n = 0;
+    if (smem_bytes > 48 * 1024 && cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes) != cudaSuccess) return -1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, J2K_RING_WARPS * 32, smem_bytes) != cudaSuccess) return -1;
+    return n;
+#endif
+}
+
 #define RING_CASE(wt, np, nc, in, mct, sg)                                                                                   \
     if (R.WT == wt && R.NP1 == np && R.NC1 == nc && R.IN1 == in && R.MCT1 == mct && R.SG1 == sg) {                           \
-        if (query) return ring_blocks_per_sm((const void*)fwd_ring_kernel<wt, np, nc, in, mct, sg>);                        \
+        if (query) return ring_blocks_per_sm((const void*)fwd_ring_kernel<wt, np, nc, in, mct, sg>, J2K_RING_CTA_SMEM);                      \
         J2K_LAUNCH_SMEM((fwd_ring_kernel<wt, np, nc, in, mct, sg>), grid, J2K_RING_WARPS * 32, J2K_RING_CTA_SMEM, st, A);   \
         return 0;                                                                                                           \
     }
 
-int ring_blocks_per_sm(const void* fn) {
-#ifdef J2K_EMU
-    (void)fn;
-    return 1;
-#else
-    int n = 0;
-    if (J2K_RING_CTA_SMEM > 48 * 1024 &&
-        cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, J2K_RING_CTA_SMEM) != cudaSuccess) return -1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, J2K_RING_WARPS * 32, J2K_RING_CTA_SMEM) != cudaSuccess) return -1;
-    return n;
-#endif
-}
 
 // query = true: resident CTAs per SM of the variant (or -1); query = false: launch (0 = launched, -1 = no such variant)
 int ring_dispatch_fwd(const RingPlan& R, const RingArgs& A, unsigned grid, cudaStream_t st, bool query) {
@@ -655,6 +655,140 @@ int ring_dispatch_fwd(const RingPlan& R, const RingArgs& A, unsigned grid, cudaS
     RING_CASE(53, 4, 1, IN_U8, MCTK_NONE, 1) RING_CASE(53, 4, 1, IN_U16, MCTK_NONE, 1)
     RING_CASE(53, 2, 3, IN_U8, MCTK_RCT, 0) RING_CASE(53, 2, 3, IN_U16, MCTK_RCT, 0)
     RING_CASE(53, 4, 1, IN_I32, MCTK_NONE, 0)
+    return -1;
+}
+
+
+bool ring_inv_variant_supported(int WT, int NP, int NC, int OUT, int MCT) {
+    if (NC == 3) return NP == 2 && (OUT == IN_U8 || OUT == IN_U16) && MCT == (WT == 53 ? MCTK_RCT : MCTK_ICT);
+    if (NP != 4 || MCT != MCTK_NONE) return false;
+    if (OUT == IN_U8 || OUT == IN_U16) return true;
+    return OUT == (WT == 53 ? IN_I32 : IN_F32);
+}
+
+// Inverse counterpart of build_ring_fwd: coarsest level first, every level waits for the level above it.
+int build_ring_inv(const Spec& s, Plan& P, const std::vector<long long>& tab) {
+    RingPlan& R = P.ring;
+    R.ok = false;
+    if (env_int("J2K_RING_DISABLE", 0) || env_int("J2K_RING_INV_DISABLE", 0)) return 0;
+    if (P.levels.empty() || P.levels.size() > J2K_RING_MAXSEG) return 0;
+    memset(&R.args, 0, sizeof R.args);
+    const int WT = s.reversible ? 53 : 97;
+    std::vector<int> order;
+    int maxlevel = 0;
+    for (auto& l : P.levels) maxlevel = l.level > maxlevel ? l.level : maxlevel;
+    for (int k = maxlevel; k >= 1; k--)
+        for (size_t i = 0; i < P.levels.size(); i++)
+            if (P.levels[i].level == k) order.push_back((int)i);
+    bool have_first = false;
+    int n_ctl = 2, jobs = 0;
+    for (size_t si = 0; si < order.size(); si++) {
+        const LevelLaunch& l = P.levels[order[si]];
+        const LevelArgs& a = l.a;
+        RingSeg& g = R.args.seg[si];
+        const bool first = l.level == 1;
+        const bool raw_out = l.KIND == IN_U8 || l.KIND == IN_U16;
+        const int NP = l.NC == 3 ? 2 : 4;
+        const int ES = l.KIND == IN_U8 ? 1 : (l.KIND == IN_U16 ? 2 : 4);
+        const int PB = ES * (raw_out ? l.NC : 1);
+        if (a.px != 0 || a.hskip || a.vskip) return 0;
+        if (a.w % 8) return 0;  // band rows are staged in 16-byte units: low and high band widths are multiples of 4
+        if (first) {
+            if (!ring_inv_variant_supported(WT, NP, l.NC, l.KIND, l.MCT)) return 0;
+            if (l.NC == 1 && raw_out && s.C != 1) return 0;  // strided components
+            if (!have_first) { R.WT = WT; R.NP1 = NP; R.NC1 = l.NC; R.IN1 = l.KIND; R.MCT1 = l.MCT; R.SG1 = 0; have_first = true; }
+            else if (R.NP1 != NP || R.NC1 != l.NC || R.IN1 != l.KIND || R.MCT1 != l.MCT) return 0;
+        } else {
+            if (l.NC != 1 || l.KIND != (WT == 53 ? IN_I32 : IN_F32)) return 0;
+        }
+        // destination rows: vector stores
+        const long long pitch = (long long)a.x_row_stride * ES;
+        if (pitch % 16 || ((long long)a.w * PB) % 16) return 0;
+        for (int i = 0; i < a.n_items; i++)
+            if ((tab[l.o_x + i] * ES) % 16) return 0;
+        // band rows: 16-byte aligned TMA segments
+        if ((a.hl.row_stride % 4) || (a.lw % 4) || (a.hl.comp_stride % 4) || (a.ll.row_stride % 4) || (a.ll.comp_stride % 4) ||
+            (a.hl.x_off % 4) || (a.hh.x_off % 4) || (a.ll.x_off % 4) || (a.lh_.x_off % 4))
+            return 0;
+        for (int i = 0; i < a.n_items; i++)
+            if ((tab[l.o_plane + i] % 4) || (tab[l.o_ll + i] % 4)) return 0;
+        const BandIO* bands[4] = {&a.ll, &a.hl, &a.lh_, &a.hh};
+        float scl[4];
+        for (int bi = 0; bi < 4; bi++) {
+            const BandIO& b = *bands[bi];
+            scl[bi] = 1.f;
+            if (WT == 53) { if (b.mode != DQ_RAW && b.mode != DQ_HALVE) return 0; }
+            else if (b.mode == DQ_SCALE) scl[bi] = b.scale;
+            else if (b.mode != DQ_RAW && b.mode != DQ_CVT) return 0;
+        }
+        g.rcpE = make_float2(scl[0], scl[2]); g.rcpO = make_float2(scl[1], scl[3]);
+        g.nstE = g.nstO = make_float2(0.f, 0.f);
+        g.w = a.w; g.h = a.h; g.py = a.py; g.lw = a.lw; g.lh = a.lh; g.Kx = a.Kx; g.Ky = a.Ky;
+        g.n_items = a.n_items;
+        g.first = first ? 1 : 0;
+        g.row_bytes = (int)((long long)a.w * PB);
+        g.dc = 0;
+        g.x_off = a.x_off;
+        g.x_row_bytes = pitch;
+        g.x_mode = a.x_mode;
+        g.ll = a.ll; g.hl = a.hl; g.lh_ = a.lh_; g.hh = a.hh;
+        g.planes_out = nullptr; g.planes_off = a.planes_off; g.planes_comp_stride = a.planes_comp_stride; g.planes_row_stride = a.planes_row_stride;
+        if (l.planes_buf) {
+            if ((a.planes_row_stride % 4) || (a.planes_comp_stride % 4)) return 0;
+            for (int i = 0; i < a.n_items; i++)
+                if (a.planes_off && (tab[(size_t)(a.planes_off - (const long long*)P.tables.p) + i] % 4)) return 0;
+        }
+        ring_chunks(g, NP, a.n_items, l.level);
+        g.dep_seg = -1; g.dep_div = 1; g.dep_target = 0; g.dep_mul = 1;
+        {
+            // producer: same class, next coarser level (absent for the coarsest level of the class)
+            for (size_t pj = 0; pj < si; pj++) {
+                const LevelLaunch& pl = P.levels[order[pj]];
+                if (pl.cls == l.cls && pl.level == l.level + 1) {
+                    g.dep_seg = (int)pj;
+                    g.dep_mul = l.nc3_first ? 3 : 1;  // a pixel item consumes the LL planes of its three components
+                    g.dep_target = R.args.seg[pj].nchunks * R.args.seg[pj].nstrips;
+                }
+            }
+        }
+        g.job_begin = jobs;
+        long long nj = (long long)g.n_items * g.nchunks * g.nstrips;
+        if (nj + jobs > 0x3fffffffLL) return 0;
+        jobs += (int)nj;
+        g.job_end = jobs;
+        g.done_base = n_ctl;
+        n_ctl += g.n_items;
+        R.x_buf[si] = l.x_buf; R.ll_buf[si] = l.ll_buf; R.band_buf[si] = l.band_buf; R.level[si] = l.level;
+        R.planes_buf[si] = l.planes_buf;
+    }
+    if (!have_first) return 0;
+    R.args.nseg = (int)order.size();
+    R.args.total_jobs = jobs;
+    R.args.n_ctl = n_ctl;
+    R.args.raw = P.raw;
+    R.args.one = 1.0f;
+    int rc = P.ctl.ensure((size_t)n_ctl * sizeof(unsigned));
+    if (rc) return rc;
+    CK(cudaMemset(P.ctl.p, 0, (size_t)n_ctl * sizeof(unsigned)));
+    R.args.ctl = (unsigned*)P.ctl.p;
+    R.ok = true;
+    return 0;
+}
+
+#define RING_INV_CASE(wt, np, nc, out, mct)                                                                                  \
+    if (R.WT == wt && R.NP1 == np && R.NC1 == nc && R.IN1 == out && R.MCT1 == mct) {                                         \
+        if (query) return ring_blocks_per_sm((const void*)inv_ring_kernel<wt, np, nc, out, mct>, J2K_INV_CTA_SMEM);         \
+        J2K_LAUNCH_SMEM((inv_ring_kernel<wt, np, nc, out, mct>), grid, J2K_RING_WARPS * 32, J2K_INV_CTA_SMEM, st, A);       \
+        return 0;                                                                                                           \
+    }
+
+int ring_dispatch_inv(const RingPlan& R, const RingArgs& A, unsigned grid, cudaStream_t st, bool query) {
+    RING_INV_CASE(97, 4, 1, IN_U8, MCTK_NONE) RING_INV_CASE(97, 4, 1, IN_U16, MCTK_NONE)
+    RING_INV_CASE(97, 2, 3, IN_U8, MCTK_ICT) RING_INV_CASE(97, 2, 3, IN_U16, MCTK_ICT)
+    RING_INV_CASE(97, 4, 1, IN_F32, MCTK_NONE)
+    RING_INV_CASE(53, 4, 1, IN_U8, MCTK_NONE) RING_INV_CASE(53, 4, 1, IN_U16, MCTK_NONE)
+    RING_INV_CASE(53, 2, 3, IN_U8, MCTK_RCT) RING_INV_CASE(53, 2, 3, IN_U16, MCTK_RCT)
+    RING_INV_CASE(53, 4, 1, IN_I32, MCTK_NONE)
     return -1;
 }
 
@@ -959,8 +1093,8 @@ int build_plan(const Spec& s, int nframes, long long frame_samples, Plan& P) {
         pw.src_off = T + f.src; pw.dst_off = T + f.dst;
     }
     P.launches_per_run = (int)(P.levels.size() + P.pre.size() + P.post.size()) + (P.generic ? 1 : 0);
-    if (s.fwd) {
-        int rc2 = build_ring_fwd(s, P, tb.host);
+    {
+        int rc2 = s.fwd ? build_ring_fwd(s, P, tb.host) : build_ring_inv(s, P, tb.host);
         if (rc2) return rc2;
     }
     return 0;
@@ -1030,15 +1164,16 @@ int run_plan(j2k_ctx* ctx, Plan& P, void* pixels, void* coeffs, void* planes, bo
         nl++;
     }
     for (auto& pw : P.pre) { prof.begin(0); int rc = run_pw(pw, bufs, st); prof.end(); if (rc) return rc; nl++; }
-    bool use_ring = P.fwd && P.ring.ok;
+    bool use_ring = P.ring.ok;
     if (use_ring) {
         for (int i = 0; i < P.ring.args.nseg && use_ring; i++)
-            use_ring = aligned16(bufs[P.ring.x_buf[i]]) && aligned16(bufs[P.ring.ll_buf[i]]) && aligned16(bufs[P.ring.band_buf[i]]);
+            use_ring = aligned16(bufs[P.ring.x_buf[i]]) && aligned16(bufs[P.ring.ll_buf[i]]) && aligned16(bufs[P.ring.band_buf[i]]) &&
+                       (P.fwd || !P.ring.planes_buf[i] || aligned16(bufs[P.ring.planes_buf[i]]));
     }
     if (use_ring) {
         RingPlan& R = P.ring;
         if (R.grid == 0) {
-            int per_sm = ring_dispatch_fwd(R, R.args, 0, st, true);
+            int per_sm = P.fwd ? ring_dispatch_fwd(R, R.args, 0, st, true) : ring_dispatch_inv(R, R.args, 0, st, true);
             if (per_sm <= 0) return fail(J2K_ERR_CUDA, "ring kernel variant (WT=%d NP=%d NC=%d kind=%d mct=%d sg=%d) cannot be resident", R.WT, R.NP1,
                                          R.NC1, R.IN1, R.MCT1, R.SG1);
             int sms = 1;
@@ -1058,21 +1193,22 @@ int run_plan(j2k_ctx* ctx, Plan& P, void* pixels, void* coeffs, void* planes, bo
             g.x_base = (const unsigned char*)bufs[R.x_buf[i]];
             g.ll.base = bufs[R.ll_buf[i]];
             g.hl.base = g.lh_.base = g.hh.base = bufs[R.band_buf[i]];
+            g.planes_out = (!P.fwd && R.planes_buf[i]) ? (int32_t*)bufs[R.planes_buf[i]] : nullptr;
         }
         static const bool trace = getenv("J2K_B200_TRACE") != nullptr;
         static const bool per_level = env_int("J2K_RING_PER_LEVEL", 0) != 0;
         static const bool dry = env_int("J2K_RING_DRY", 0) != 0;  // diagnostic: launch overhead only (no job is claimed)
         if (dry) A.total_jobs = 0;
         if (trace)
-            fprintf(stderr, "[j2k] fwd ring WT=%d NP=%d NC=%d kind=%d mct=%d sg=%d segs=%d jobs=%d grid=%u\n", R.WT, R.NP1, R.NC1, R.IN1, R.MCT1,
-                    R.SG1, A.nseg, A.total_jobs, R.grid);
+            fprintf(stderr, "[j2k] %s ring WT=%d NP=%d NC=%d kind=%d mct=%d sg=%d segs=%d jobs=%d grid=%u\n", P.fwd ? "fwd" : "inv", R.WT, R.NP1, R.NC1,
+                    R.IN1, R.MCT1, R.SG1, A.nseg, A.total_jobs, R.grid);
         if (!per_level) {
             unsigned grid = R.grid;
             unsigned need = (unsigned)((A.total_jobs + J2K_RING_WARPS - 1) / J2K_RING_WARPS);
             if (need < grid) grid = need;
             if (grid < 1) grid = 1;
             prof.begin(100);
-            int rc = ring_dispatch_fwd(R, A, grid, st, false);
+            int rc = P.fwd ? ring_dispatch_fwd(R, A, grid, st, false) : ring_dispatch_inv(R, A, grid, st, false);
             prof.end();
             if (rc) return fail(J2K_ERR_CUDA, "ring kernel variant missing");
             CK(cudaGetLastError());
@@ -1096,7 +1232,7 @@ int run_plan(j2k_ctx* ctx, Plan& P, void* pixels, void* coeffs, void* planes, bo
                 unsigned need = (unsigned)((B.total_jobs + J2K_RING_WARPS - 1) / J2K_RING_WARPS);
                 if (need < grid) grid = need;
                 prof.begin(R.level[i]);
-                int rc = ring_dispatch_fwd(R, B, grid, st, false);
+                int rc = P.fwd ? ring_dispatch_fwd(R, B, grid, st, false) : ring_dispatch_inv(R, B, grid, st, false);
                 prof.end();
                 if (rc) return fail(J2K_ERR_CUDA, "ring kernel variant missing");
                 CK(cudaGetLastError());

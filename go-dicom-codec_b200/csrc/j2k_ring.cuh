@@ -39,6 +39,11 @@ namespace j2k {
 #endif
 #define J2K_RING_WARP_SMEM (J2K_RING_BYTES + J2K_RING_MAXD * 8)
 #define J2K_RING_CTA_SMEM (J2K_RING_WARPS * J2K_RING_WARP_SMEM)
+#ifndef J2K_INV_RING_BYTES
+#define J2K_INV_RING_BYTES 17408  // inverse: a stage holds four band rows per component (8 stages of four 512 B + 32 B rows)
+#endif
+#define J2K_INV_WARP_SMEM (J2K_INV_RING_BYTES + J2K_RING_MAXD * 8)
+#define J2K_INV_CTA_SMEM (J2K_RING_WARPS * J2K_INV_WARP_SMEM)
 
 struct RingSeg {
     // level window (px == 0 always on this path)
@@ -56,7 +61,15 @@ struct RingSeg {
     long long x_row_bytes;             // row pitch in bytes (multiple of 16)
     BandIO ll, hl, lh_, hh;
     FastQ q[4];
-    float2 rcpE, nstE, rcpO, nstO;     // quantizer pairs (LL, LH) and (HL, HH): reciprocal and negated step' (9/7)
+    float2 rcpE, nstE, rcpO, nstO;     // forward: quantizer pairs (LL, LH) and (HL, HH): reciprocal and negated step' (9/7)
+                                       // inverse: rcpE / rcpO hold the dequantizer scale pairs (LL, LH) / (HL, HH)
+    int dep_mul;                       // inverse: the job waits on dep_mul consecutive counters starting at item * dep_mul
+    int x_mode;                        // inverse, planar destination: 1 = store the 9/7 samples rounded half-even to int32
+    int32_t* planes_out;               // inverse final: optional GetImageData planes (decoder.go:738-740)
+    const long long* planes_off;
+    long long planes_comp_stride;
+    int planes_row_stride;
+    int pad2_;
 };
 
 struct RingArgs {
@@ -669,8 +682,10 @@ __device__ __forceinline__ bool ring_claim(const RingArgs& A, int lane, RingJob&
 __device__ __forceinline__ void ring_wait_dep(const RingArgs& A, const RingSeg& S, int item, int lane) {
     if (S.dep_seg < 0) return;
     if (lane == 0) {
-        const unsigned* d = A.ctl + A.seg[S.dep_seg].done_base + item / S.dep_div;
-        while (ld_relaxed(d) < (unsigned)S.dep_target) backoff();  // relaxed polling: no L1 invalidation per probe
+        const int mul = S.dep_mul > 1 ? S.dep_mul : 1;
+        const unsigned* d = A.ctl + A.seg[S.dep_seg].done_base + (item / S.dep_div) * mul;
+        for (int k = 0; k < mul; k++)
+            while (ld_relaxed(d + k) < (unsigned)S.dep_target) backoff();  // relaxed polling: no L1 invalidation per probe
         fence_acquire();
         fence_proxy_async();  // the staged reads that follow go through the async proxy
     }
@@ -698,10 +713,10 @@ __device__ __forceinline__ void ring_retire(const RingArgs& A, int lane) {
     }
 }
 
-__device__ __forceinline__ void ring_warp_init(unsigned char* smem, RingWarp& rw, int lane) {
+__device__ __forceinline__ void ring_warp_init(unsigned char* smem, RingWarp& rw, int lane, int ring_bytes) {
     const int wib = threadIdx.x >> 5;
-    rw.ring = smem_handle(smem + wib * J2K_RING_WARP_SMEM);
-    rw.bars = rw.ring + J2K_RING_BYTES;
+    rw.ring = smem_handle(smem + wib * (ring_bytes + J2K_RING_MAXD * 8));
+    rw.bars = rw.ring + ring_bytes;
     rw.phase = 0;
     if (lane == 0) {
         for (int s = 0; s < J2K_RING_MAXD; s++) mbar_init(rw.bars + 8 * s, 1);
@@ -723,7 +738,7 @@ __global__ void J2K_RING_BOUNDS fwd_ring_kernel(const __grid_constant__ RingArgs
     J2K_SMEM_DECL(smem);
     const int lane = threadIdx.x & 31;
     RingWarp rw;
-    ring_warp_init(smem, rw, lane);
+    ring_warp_init(smem, rw, lane, J2K_RING_BYTES);
     rw.one = A.one;
     RingJob J;
     while (ring_claim(A, lane, J)) {
@@ -731,6 +746,442 @@ __global__ void J2K_RING_BOUNDS fwd_ring_kernel(const __grid_constant__ RingArgs
         ring_wait_dep(A, S, J.item, lane);
         if (S.first) FwdRing<WT, NP1, NC1, IN1, MCT1, SG1>::run(S, A.raw, J.item, J.chunk, J.strip, rw, lane);
         else FwdRing<WT, 4, 1, (WT == 53 ? IN_I32 : IN_F32), MCTK_NONE, 0>::run(S, A.raw, J.item, J.chunk, J.strip, rw, lane);
+        ring_signal(A, S, J.item, lane);
+    }
+    ring_retire(A, lane);
+}
+
+}  // namespace j2k
+
+namespace j2k {
+
+// ------------------------------------------------------------------ inverse job
+//
+// Mirror image of FwdRing.  One iteration stages, per component, the four band rows that one pair of
+// interleaved rows needs (LL/HL row yl, LH/HH row yh), dequantizes, runs the horizontal synthesis of both rows
+// at once (packed f32x2 for 9/7: the pair is (low-type row, high-type row)), then the vertical synthesis as a
+// register sliding window over column pairs, and stores the two finished rows of pair t - LAG: planar working
+// type for an intermediate level, or rounded / inverse-MCT / DC-shifted / clamped / packed pixels for level 1.
+// Reference order per level: rows, then columns (dwt53.go:318-354, dwt97.go:360-384).
+
+template <int WT, int NP, int NC, int OUT, int MCT>
+struct InvRing {
+    typedef typename Wt<WT>::T T;
+    static constexpr int LAG = Wt<WT>::LAG;
+    static constexpr int HLN = (Wt<WT>::HALO + NP - 1) / NP;
+    static constexpr int NS = 2 * NP;
+    static constexpr bool FINAL = (OUT == IN_U8 || OUT == IN_U16);
+    static constexpr int LB = NP * 4;          // bytes per lane per band row
+    static constexpr int ROWB = 32 * LB + 32;  // staged band row slot
+    static constexpr int NROWS = 4 * NC;       // LL, HL, LH, HH per component
+    static constexpr int STAGEB = NROWS * ROWB;
+    static constexpr int D = (J2K_INV_RING_BYTES / STAGEB) > J2K_RING_MAXD ? J2K_RING_MAXD : (J2K_INV_RING_BYTES / STAGEB);
+    static_assert(D >= 2, "ring too small for this stage size");
+    static_assert(NC == 1 || FINAL, "3-component jobs write interleaved pixels");
+
+    static __device__ __forceinline__ void fetch(smem_t p, int (&q)[NP]) {
+        if constexpr (NP == 4) { uint4 v = lds128(p); q[0] = (int)v.x; q[1] = (int)v.y; q[2] = (int)v.z; q[3] = (int)v.w; }
+        else if constexpr (NP == 2) { uint2 v = lds64(p); q[0] = (int)v.x; q[1] = (int)v.y; }
+        else q[0] = (int)lds32(p);
+    }
+
+    // Border strips: band samples just outside the window, mirrored in the interleaved domain (low stays low, high
+    // stays high): lanes 0..NP-1 write the left span, lanes NP..2NP-1 the right one, in every staged band row.
+    static __device__ __forceinline__ void fix_halo(smem_t stage, int lane, bool fix_l, bool fix_r, int w, int bw, int vb) {
+        if (lane < 2 * NP) {
+            const bool left = lane < NP;
+            const int k = left ? lane : lane - NP;
+            if (left ? fix_l : fix_r) {
+                const int kx = left ? -(k + 1) : bw + k;  // band index outside [0, bw)
+                const int src_lo = mirror_fast(2 * kx, w) >> 1, src_hi = (mirror_fast(2 * kx + 1, w) - 1) >> 1;
+                unsigned char* st = smem_ptr(stage);
+#pragma unroll
+                for (int r = 0; r < NROWS; r++) {
+                    const int src = (r & 1) ? src_hi : src_lo;  // rows 1, 3 (HL, HH) are horizontally high-pass
+                    unsigned char* row = st + r * ROWB;
+                    *(unsigned*)(row + kx * 4 - vb) = *(const unsigned*)(row + src * 4 - vb);
+                }
+            }
+        }
+        __syncwarp();
+    }
+
+    // final stage of level 1: inverse MCT -> (+DC, optional planes) -> clamp -> pack -> one vector store per row
+    static __device__ __forceinline__ void store_final(const RingSeg& S, const RawFmt& raw, unsigned char* xrow, int* prow, int (&iv)[NC][NS]) {
+        if constexpr (NC == 3 && MCT != MCTK_NONE) {
+#pragma unroll
+            for (int s = 0; s < NS; s++) {
+                int r, g, b;
+                mct_inverse<MCT>(iv[0][s], iv[1][s], iv[2][s], r, g, b);
+                iv[0][s] = r; iv[1][s] = g; iv[2][s] = b;
+            }
+        }
+        if (prow) {
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                int* p = prow + c * S.planes_comp_stride;
+                if constexpr (NS == 8) {
+                    *(int4*)p = make_int4(iv[c][0] + raw.dc, iv[c][1] + raw.dc, iv[c][2] + raw.dc, iv[c][3] + raw.dc);
+                    *(int4*)(p + 4) = make_int4(iv[c][NS - 4] + raw.dc, iv[c][NS - 3] + raw.dc, iv[c][NS - 2] + raw.dc, iv[c][NS - 1] + raw.dc);
+                } else {
+                    *(int4*)p = make_int4(iv[c][0] + raw.dc, iv[c][1] + raw.dc, iv[c][2 % NS] + raw.dc, iv[c][3 % NS] + raw.dc);
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < NC; c++)
+#pragma unroll
+            for (int s = 0; s < NS; s++) iv[c][s] = int_to_raw(iv[c][s], raw);
+        constexpr int ES = (OUT == IN_U8) ? 1 : 2;
+        constexpr int NWO = NS * NC * ES / 4;  // 32-bit words per lane per row
+        unsigned wv[NWO];
+#pragma unroll
+        for (int k = 0; k < NWO; k++) wv[k] = 0;
+#pragma unroll
+        for (int s = 0; s < NS; s++)
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                const int e = NC * s + c;
+                if constexpr (OUT == IN_U8) wv[e >> 2] |= (unsigned)iv[c][s] << (8 * (e & 3));
+                else wv[e >> 1] |= (unsigned)iv[c][s] << (16 * (e & 1));
+            }
+        if constexpr (NWO % 4 == 0) {
+#pragma unroll
+            for (int k = 0; k < NWO / 4; k++) *((uint4*)xrow + k) = make_uint4(wv[4 * k], wv[4 * k + 1], wv[(4 * k + 2) % NWO], wv[(4 * k + 3) % NWO]);
+        } else if constexpr (NWO % 2 == 0) {
+#pragma unroll
+            for (int k = 0; k < NWO / 2; k++) *((uint2*)xrow + k) = make_uint2(wv[2 * k], wv[(2 * k + 1) % NWO]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < NWO; k++) *((unsigned*)xrow + k) = wv[k];
+        }
+    }
+
+    // planar destination (intermediate LL, wavelet-package API, generic path): working-type bits, or rounded samples
+    static __device__ __forceinline__ void store_planar(int* p, const int (&q)[NS]) {
+        if constexpr (NS == 8) {
+            *(int4*)p = make_int4(q[0], q[1], q[2], q[3]);
+            *(int4*)(p + 4) = make_int4(q[NS - 4], q[NS - 3], q[NS - 2], q[NS - 1]);
+        } else if constexpr (NS == 4) {
+            *(int4*)p = make_int4(q[0], q[1], q[2 % NS], q[3 % NS]);
+        } else {
+            *(int2*)p = make_int2(q[0], q[1 % NS]);
+        }
+    }
+
+    static __device__ __forceinline__ void run(const RingSeg& S, const RawFmt& raw, int item, int chunk, int strip, RingWarp& rw,
+                                               int lane) {
+        const int w = S.w, h = S.h, py = S.py;
+        const int bw = S.lw;  // == w - lw on this path (w is a multiple of 2 NP)
+        const int kxs = strip * S.strip_pairs;
+        const int kxe = min(kxs + S.strip_pairs, S.Kx);
+        const int nl = (kxe - kxs + NP - 1) / NP + 2 * HLN;
+        const int kx0 = kxs - HLN * NP + lane * NP;
+        const int k0w = kxs - HLN * NP;           // band index of lane 0's first element
+        const int m = (k0w * 4) & 15;
+        const int vb = k0w * 4 - m;               // virtual (16 B aligned) byte position of the slot start inside a band row
+        const int c0 = max(vb, 0);
+        const int c1 = min(vb + ((m + nl * LB + 15) & ~15), bw * 4);
+        const unsigned copy_bytes = (unsigned)(c1 - c0);
+        const int dst_off = c0 - vb;
+        const int lane_off = m + lane * LB;
+        const bool active = lane < nl;
+        const bool fix_l = kxs == 0, fix_r = kxe == S.Kx;
+        const bool fix = fix_l || fix_r;
+        const bool st = lane >= HLN && kx0 < kxe && kx0 + NP <= bw;
+        const float one = rw.one;
+
+        const int ky0 = chunk * S.chunk_pairs;
+        const int ky1 = min(ky0 + S.chunk_pairs, S.Ky);
+        const int t_begin = ky0 - LAG;
+        const int n_it = ky1 - ky0 + 2 * LAG;
+
+        // band row 0 of this item, at the copy start (bytes)
+        const unsigned char* b_ll = (const unsigned char*)((const int*)S.ll.base + S.ll.off[item] + (long long)S.ll.y_off * S.ll.row_stride + S.ll.x_off) + c0;
+        const unsigned char* b_hl = (const unsigned char*)((const int*)S.hl.base + S.hl.off[item] + (long long)S.hl.y_off * S.hl.row_stride + S.hl.x_off) + c0;
+        const unsigned char* b_lh = (const unsigned char*)((const int*)S.lh_.base + S.lh_.off[item] + (long long)S.lh_.y_off * S.lh_.row_stride + S.lh_.x_off) + c0;
+        const unsigned char* b_hh = (const unsigned char*)((const int*)S.hh.base + S.hh.off[item] + (long long)S.hh.y_off * S.hh.row_stride + S.hh.x_off) + c0;
+        const long long rp_ll = (long long)S.ll.row_stride * 4, rp_b = (long long)S.hl.row_stride * 4;
+        const long long cp_ll = S.ll.comp_stride * 4, cp_b = S.hl.comp_stride * 4;
+
+        int pj = 0, pslot = 0;
+        const smem_t dst_s = rw.ring + dst_off;
+        auto issue = [&]() {
+            if (lane == 0) {
+                // band rows of the pair: low-type interleaved row 2t - py -> yl, high-type row 2t + 1 - py -> yh (mirrored)
+                const int t = t_begin + pj;
+                const int pl = mirror_fast(2 * t - py, h), ph = mirror_fast(2 * t + 1 - py, h);
+                const int yl = (pl - py) >> 1, yh = (ph - (1 - py)) >> 1;
+                const smem_t bar = rw.bars + 8 * pslot;
+                const smem_t dst = dst_s + pslot * STAGEB;
+                mbar_expect_tx(bar, NROWS * copy_bytes);
+#pragma unroll
+                for (int c = 0; c < NC; c++) {
+                    bulk_g2s(dst + (4 * c + 0) * ROWB, b_ll + c * cp_ll + yl * rp_ll, copy_bytes, bar);
+                    bulk_g2s(dst + (4 * c + 1) * ROWB, b_hl + c * cp_b + yl * rp_b, copy_bytes, bar);
+                    bulk_g2s(dst + (4 * c + 2) * ROWB, b_lh + c * cp_b + yh * rp_b, copy_bytes, bar);
+                    bulk_g2s(dst + (4 * c + 3) * ROWB, b_hh + c * cp_b + yh * rp_b, copy_bytes, bar);
+                }
+            }
+            pj++;
+            pslot = (pslot + 1 == D) ? 0 : pslot + 1;
+        };
+        __syncwarp();
+#pragma unroll 1
+        for (int j = 0; j < D - 1 && j < n_it; j++) issue();
+
+        // destination rows
+        constexpr int XES = FINAL ? ((OUT == IN_U8) ? 1 : 2) : 4;
+        constexpr int XPB = XES * (FINAL ? NC : 1);
+        unsigned char* xlane = (unsigned char*)S.x_base + S.x_off[item] * XES + (long long)(2 * kx0) * XPB;
+        const long long xpitch = S.x_row_bytes;
+        int* planes = (FINAL && S.planes_out) ? S.planes_out + S.planes_off[item] + 2 * kx0 : nullptr;
+        const int planes_rs = S.planes_row_stride;
+        const int x_mode = S.x_mode;
+
+        int cslot = 0;
+        if constexpr (WT == 97) {
+            const float2 sclE = S.rcpE, sclO = S.rcpO;
+            const bool raw_ll = S.ll.mode == DQ_RAW, raw_hl = S.hl.mode == DQ_RAW, raw_lh = S.lh_.mode == DQ_RAW, raw_hh = S.hh.mode == DQ_RAW;
+            const float2 nD = splat2(-J2K_DELTA), nG = splat2(-J2K_GAMMA), nB = splat2(-J2K_BETA), nA = splat2(-J2K_ALPHA);
+            struct VState { float2 dp[NC][NP], s1p[NC][NP], d1p[NC][NP], s2p[NC][NP]; };
+            VState sa, sb;
+#pragma unroll
+            for (int c = 0; c < NC; c++)
+#pragma unroll
+                for (int j = 0; j < NP; j++) { sa.dp[c][j] = sa.s1p[c][j] = sa.d1p[c][j] = sa.s2p[c][j] = make_float2(0.f, 0.f); }
+            auto body = [&](int it, const VState& in, VState& out) {
+                __syncwarp();
+                if (pj < n_it) issue();
+                mbar_wait(rw.bars + 8 * cslot, (rw.phase >> cslot) & 1u);
+                rw.phase ^= 1u << cslot;
+                const smem_t stage = rw.ring + cslot * STAGEB;
+                cslot = (cslot + 1 == D) ? 0 : cslot + 1;
+                if (fix) fix_halo(stage, lane, fix_l, fix_r, w, bw, vb);
+
+                float2 xe[NC][NP], xo[NC][NP];  // finished rows of pair t - LAG as column pairs
+#pragma unroll
+                for (int c = 0; c < NC; c++) {
+                    // dequantize: S[j] = (LL, LH)[j], Dd[j] = (HL, HH)[j] as (low-type row, high-type row) pairs
+                    float2 Sx[NP + 1], Dx[NP + 1];  // Dx[0] = previous lane's last high, Sx[NP] = next lane's first low
+                    int q0[NP], q1[NP], q2[NP], q3[NP];
+                    if (active) {
+                        fetch(stage + (4 * c + 0) * ROWB + lane_off, q0);
+                        fetch(stage + (4 * c + 1) * ROWB + lane_off, q1);
+                        fetch(stage + (4 * c + 2) * ROWB + lane_off, q2);
+                        fetch(stage + (4 * c + 3) * ROWB + lane_off, q3);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < NP; j++) { q0[j] = q1[j] = q2[j] = q3[j] = 0; }
+                    }
+#pragma unroll
+                    for (int j = 0; j < NP; j++) {
+                        // float32(q) * float32(scale) (t2/tile_decoder.go:970-987); DQ_CVT is scale == 1 (exact)
+                        const float2 fs = make_float2((float)q0[j], (float)q2[j]), fd = make_float2((float)q1[j], (float)q3[j]);
+                        float2 vs = mul2(fs, sclE), vd = mul2(fd, sclO);
+                        if (raw_ll) vs.x = __int_as_float(q0[j]);
+                        if (raw_lh) vs.y = __int_as_float(q2[j]);
+                        if (raw_hl) vd.x = __int_as_float(q1[j]);
+                        if (raw_hh) vd.y = __int_as_float(q3[j]);
+                        // horizontal synthesis scaling: low * K, high * two_invK (dwt97.go:207-212)
+                        Sx[j] = mul2(vs, splat2(J2K_K));
+                        Dx[j + 1] = mul2(vd, splat2(J2K_TWOINVK));
+                    }
+                    float2 Tq[NP];
+                    Dx[0] = shfl_up2(Dx[NP]);
+#pragma unroll
+                    for (int j = 0; j < NP; j++) Tq[j] = add2(Dx[j], Dx[j + 1]);
+#pragma unroll
+                    for (int j = 0; j < NP; j++) Tq[j] = mul2(Tq[j], nD);
+#pragma unroll
+                    for (int j = 0; j < NP; j++) Sx[j] = addp2(Tq[j], Sx[j], one);
+                    Sx[NP] = shfl_down2(Sx[0]);
+#pragma unroll
+                    for (int j = 0; j < NP; j++) Tq[j] = add2(Sx[j], Sx[j + 1]);
+#pragma unroll
+                    for (int j = 0; j < NP; j++) Tq[j] = mul2(Tq[j], nG);
+#pragma unroll
+                    for (int j = 0; j < NP; j++) Dx[j + 1] = addp2(Tq[j], Dx[j + 1], one);
+                    Dx[0] = shfl_up2(Dx[NP]);
+#pragma unroll
+                    for (int j = 0; j < NP; j++) Tq[j] = add2(Dx[j], Dx[j + 1]);
+#pragma unroll
+                    for (int j = 0; j < NP; j++) Tq[j] = mul2(Tq[j], nB);
+#pragma unroll
+                    for (int j = 0; j < NP; j++) Sx[j] = addp2(Tq[j], Sx[j], one);
+                    Sx[NP] = shfl_down2(Sx[0]);
+#pragma unroll
+                    for (int j = 0; j < NP; j++) Tq[j] = add2(Sx[j], Sx[j + 1]);
+#pragma unroll
+                    for (int j = 0; j < NP; j++) Tq[j] = mul2(Tq[j], nA);
+#pragma unroll
+                    for (int j = 0; j < NP; j++) Dx[j + 1] = addp2(Tq[j], Dx[j + 1], one);
+                    // vertical synthesis on column pairs (2j, 2j+1) = (Sx[j], Dx[j+1]); .x = low-type row e, .y = high-type row o
+#pragma unroll
+                    for (int j = 0; j < NP; j++) {
+                        const float2 sv = make_float2(__fmul_rn(Sx[j].x, J2K_K), __fmul_rn(Dx[j + 1].x, J2K_K));
+                        const float2 dv = make_float2(__fmul_rn(Sx[j].y, J2K_TWOINVK), __fmul_rn(Dx[j + 1].y, J2K_TWOINVK));
+                        const float2 s1 = lift97x2(sv, in.dp[c][j], dv, nD, one);               // s'[t]
+                        const float2 d1 = lift97x2(in.dp[c][j], in.s1p[c][j], s1, nG, one);     // d'[t-1]
+                        const float2 s2 = lift97x2(in.s1p[c][j], in.d1p[c][j], d1, nB, one);    // s''[t-1]
+                        const float2 d2 = lift97x2(in.d1p[c][j], in.s2p[c][j], s2, nA, one);    // d''[t-2]
+                        xe[c][j] = in.s2p[c][j];                                                 // s''[t-2]
+                        xo[c][j] = d2;
+                        out.dp[c][j] = dv; out.s1p[c][j] = s1; out.d1p[c][j] = d1; out.s2p[c][j] = s2;
+                    }
+                }
+                if (it < 2 * LAG || !st) return;
+                const int ky = ky0 + it - 2 * LAG;
+                const int re = 2 * ky - py, ro = re + 1;
+                if constexpr (FINAL) {
+                    int iv[NC][NS];
+                    if (re >= 0 && re < h) {
+#pragma unroll
+                        for (int c = 0; c < NC; c++)
+#pragma unroll
+                            for (int j = 0; j < NP; j++) { iv[c][2 * j] = __float2int_rn(xe[c][j].x); iv[c][2 * j + 1] = __float2int_rn(xe[c][j].y); }
+                        store_final(S, raw, xlane + re * xpitch, planes ? planes + (long long)re * planes_rs : nullptr, iv);
+                    }
+                    if (ro < h) {
+#pragma unroll
+                        for (int c = 0; c < NC; c++)
+#pragma unroll
+                            for (int j = 0; j < NP; j++) { iv[c][2 * j] = __float2int_rn(xo[c][j].x); iv[c][2 * j + 1] = __float2int_rn(xo[c][j].y); }
+                        store_final(S, raw, xlane + ro * xpitch, planes ? planes + (long long)ro * planes_rs : nullptr, iv);
+                    }
+                } else {
+                    int q[NS];
+                    if (re >= 0 && re < h) {
+#pragma unroll
+                        for (int j = 0; j < NP; j++) {
+                            q[2 * j] = x_mode == 1 ? __float2int_rn(xe[0][j].x) : __float_as_int(xe[0][j].x);
+                            q[2 * j + 1] = x_mode == 1 ? __float2int_rn(xe[0][j].y) : __float_as_int(xe[0][j].y);
+                        }
+                        store_planar((int*)(xlane + re * xpitch), q);
+                    }
+                    if (ro < h) {
+#pragma unroll
+                        for (int j = 0; j < NP; j++) {
+                            q[2 * j] = x_mode == 1 ? __float2int_rn(xo[0][j].x) : __float_as_int(xo[0][j].x);
+                            q[2 * j + 1] = x_mode == 1 ? __float2int_rn(xo[0][j].y) : __float_as_int(xo[0][j].y);
+                        }
+                        store_planar((int*)(xlane + ro * xpitch), q);
+                    }
+                }
+            };
+#pragma unroll 1
+            for (int it = 0; it < n_it; it += 2) {
+                body(it, sa, sb);
+                if (it + 1 >= n_it) break;
+                body(it + 1, sb, sa);
+            }
+        } else {
+            const bool halve_ll = S.ll.mode == DQ_HALVE, halve_hl = S.hl.mode == DQ_HALVE, halve_lh = S.lh_.mode == DQ_HALVE,
+                       halve_hh = S.hh.mode == DQ_HALVE;
+            int dp[NC][NS], s1p[NC][NS];
+#pragma unroll
+            for (int c = 0; c < NC; c++)
+#pragma unroll
+                for (int s = 0; s < NS; s++) { dp[c][s] = 0; s1p[c][s] = 0; }
+#pragma unroll 1
+            for (int it = 0; it < n_it; it++) {
+                __syncwarp();
+                if (pj < n_it) issue();
+                mbar_wait(rw.bars + 8 * cslot, (rw.phase >> cslot) & 1u);
+                rw.phase ^= 1u << cslot;
+                const smem_t stage = rw.ring + cslot * STAGEB;
+                cslot = (cslot + 1 == D) ? 0 : cslot + 1;
+                if (fix) fix_halo(stage, lane, fix_l, fix_r, w, bw, vb);
+
+                int xe[NC][NS], xo[NC][NS];
+#pragma unroll
+                for (int c = 0; c < NC; c++) {
+                    int q0[NP], q1[NP], q2[NP], q3[NP];
+                    if (active) {
+                        fetch(stage + (4 * c + 0) * ROWB + lane_off, q0);
+                        fetch(stage + (4 * c + 1) * ROWB + lane_off, q1);
+                        fetch(stage + (4 * c + 2) * ROWB + lane_off, q2);
+                        fetch(stage + (4 * c + 3) * ROWB + lane_off, q3);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < NP; j++) { q0[j] = q1[j] = q2[j] = q3[j] = 0; }
+                    }
+                    // t2/tile_decoder.go:989-993: truncating /2 of the classic T1 output
+#pragma unroll
+                    for (int j = 0; j < NP; j++) {
+                        if (halve_ll) q0[j] /= 2;
+                        if (halve_hl) q1[j] /= 2;
+                        if (halve_lh) q2[j] /= 2;
+                        if (halve_hh) q3[j] /= 2;
+                    }
+                    // horizontal synthesis of the low-type row (q0 | q1) and the high-type row (q2 | q3) (dwt53.go:123-234)
+                    int e[NS], o[NS];
+                    {
+                        int s[NP + 1], d[NP + 1];
+#pragma unroll
+                        for (int j = 0; j < NP; j++) { s[j] = q0[j]; d[j + 1] = q1[j]; }
+                        d[0] = __shfl_up_sync(0xffffffffu, d[NP], 1);
+#pragma unroll
+                        for (int j = 0; j < NP; j++) s[j] = s[j] - ((d[j] + d[j + 1] + 2) >> 2);
+                        s[NP] = __shfl_down_sync(0xffffffffu, s[0], 1);
+#pragma unroll
+                        for (int j = 0; j < NP; j++) d[j + 1] = d[j + 1] + ((s[j] + s[j + 1]) >> 1);
+#pragma unroll
+                        for (int j = 0; j < NP; j++) { e[2 * j] = s[j]; e[2 * j + 1] = d[j + 1]; }
+                    }
+                    {
+                        int s[NP + 1], d[NP + 1];
+#pragma unroll
+                        for (int j = 0; j < NP; j++) { s[j] = q2[j]; d[j + 1] = q3[j]; }
+                        d[0] = __shfl_up_sync(0xffffffffu, d[NP], 1);
+#pragma unroll
+                        for (int j = 0; j < NP; j++) s[j] = s[j] - ((d[j] + d[j + 1] + 2) >> 2);
+                        s[NP] = __shfl_down_sync(0xffffffffu, s[0], 1);
+#pragma unroll
+                        for (int j = 0; j < NP; j++) d[j + 1] = d[j + 1] + ((s[j] + s[j + 1]) >> 1);
+#pragma unroll
+                        for (int j = 0; j < NP; j++) { o[2 * j] = s[j]; o[2 * j + 1] = d[j + 1]; }
+                    }
+                    // vertical synthesis (dwt53.go:318-354 columns after rows)
+#pragma unroll
+                    for (int s = 0; s < NS; s++) {
+                        const int sv = e[s] - ((dp[c][s] + o[s] + 2) >> 2);   // s[t]
+                        const int xodd = dp[c][s] + ((s1p[c][s] + sv) >> 1);  // x[2(t-1)+1]
+                        xe[c][s] = s1p[c][s];
+                        xo[c][s] = xodd;
+                        dp[c][s] = o[s]; s1p[c][s] = sv;
+                    }
+                }
+                if (it < 2 * LAG || !st) continue;
+                const int ky = ky0 + it - 2 * LAG;
+                const int re = 2 * ky - py, ro = re + 1;
+                if constexpr (FINAL) {
+                    if (re >= 0 && re < h) store_final(S, raw, xlane + re * xpitch, planes ? planes + (long long)re * planes_rs : nullptr, xe);
+                    if (ro < h) store_final(S, raw, xlane + ro * xpitch, planes ? planes + (long long)ro * planes_rs : nullptr, xo);
+                } else {
+                    if (re >= 0 && re < h) store_planar((int*)(xlane + re * xpitch), xe[0]);
+                    if (ro < h) store_planar((int*)(xlane + ro * xpitch), xo[0]);
+                }
+            }
+        }
+    }
+};
+
+// WT: 53 / 97.  OUT1 / NC1 / MCT1: the variant of segments with first == 1 (level 1: packed pixels, or planar for the
+// wavelet-package API / generic path); coarser levels always write planar working-type LL planes.
+template <int WT, int NP1, int NC1, int OUT1, int MCT1>
+__global__ void __launch_bounds__(J2K_RING_WARPS * 32, J2K_RING_MINB) inv_ring_kernel(const __grid_constant__ RingArgs A) {
+    J2K_SMEM_DECL(smem);
+    const int lane = threadIdx.x & 31;
+    RingWarp rw;
+    ring_warp_init(smem, rw, lane, J2K_INV_RING_BYTES);
+    rw.one = A.one;
+    RingJob J;
+    while (ring_claim(A, lane, J)) {
+        const RingSeg& S = A.seg[J.seg];
+        ring_wait_dep(A, S, J.item, lane);
+        if (S.first) InvRing<WT, NP1, NC1, OUT1, MCT1>::run(S, A.raw, J.item, J.chunk, J.strip, rw, lane);
+        else InvRing<WT, 4, 1, (WT == 53 ? IN_I32 : IN_F32), MCTK_NONE>::run(S, A.raw, J.item, J.chunk, J.strip, rw, lane);
         ring_signal(A, S, J.item, lane);
     }
     ring_retire(A, lane);
