@@ -122,7 +122,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    frames = max(1, min(cores, 16))  # one frame per host thread ("goroutine-per-frame" upper bound), bounded sample
+    frames = max(1, min(cores, 32))  # one frame per host thread ("goroutine-per-frame" upper bound), bounded sample
     steps = min(args.steps, 5)
     warm = min(args.warmup, 1)
     val, ms = cpu_leg(cores, frames, steps, warm)

@@ -731,7 +731,10 @@ __device__ __forceinline__ void ring_warp_init(unsigned char* smem, RingWarp& rw
 #ifdef J2K_RING_MAXNREG
 #define J2K_RING_BOUNDS __maxnreg__(J2K_RING_MAXNREG)
 #else
-#define J2K_RING_BOUNDS __launch_bounds__(J2K_RING_WARPS * 32, J2K_RING_MINB)
+#ifndef J2K_RING_MINB_RGB97
+#define J2K_RING_MINB_RGB97 2  // the 3-component 9/7 level-1 variant carries 3x the window state: 2 CTAs/SM, no spills
+#endif
+#define J2K_RING_BOUNDS __launch_bounds__(J2K_RING_WARPS * 32, (WT == 97 && NC1 == 3) ? J2K_RING_MINB_RGB97 : J2K_RING_MINB)
 #endif
 template <int WT, int NP1, int NC1, int IN1, int MCT1, int SG1>
 __global__ void J2K_RING_BOUNDS fwd_ring_kernel(const __grid_constant__ RingArgs A) {

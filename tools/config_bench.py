@@ -21,7 +21,7 @@ def alg_bytes(S, s_io, L):
     return S * (s_io + 4) + 8 * S * sum(4.0 ** -k for k in range(1, L))
 
 
-def run(ctx, name, w, h, c, bits, signed, L, rev, frames, tile=(0, 0), steps=10, peak=6547.2):
+def run_config(ctx, name, w, h, c, bits, signed, L, rev, frames, tile=(0, 0), steps=10, peak=6547.2):
     mct = (abi.MCT_RCT if rev else abi.MCT_ICT) if c == 3 else abi.MCT_NONE
     es = ds = None
     if not rev:
@@ -69,12 +69,16 @@ def run(ctx, name, w, h, c, bits, signed, L, rev, frames, tile=(0, 0), steps=10,
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--only", default="", help="substring of the config name to run")
     a = ap.parse_args()
     peak = 6547.2
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk):
         peak = float(json.load(open(pk))["hbm_gbs"])
     with j2kb200.Context(devices=[0]) as ctx:
+        def run(ctx, name, *aa, **kw):
+            if a.only in name:
+                run_config(ctx, name, *aa, **kw)
         run(ctx, "C1x256: 512x512 16-bit signed mono, 5/3 L5", 512, 512, 1, 16, True, 5, True, 256, steps=a.steps, peak=peak)
         run(ctx, "C2x16: 4096x4096 12-bit mono, 9/7 L6", 4096, 4096, 1, 12, False, 6, False, 16, steps=a.steps, peak=peak)
         run(ctx, "C3i x8: 2048x2048 RGB 8-bit, ICT + 9/7 L5", 2048, 2048, 3, 8, False, 5, False, 8, steps=a.steps, peak=peak)
