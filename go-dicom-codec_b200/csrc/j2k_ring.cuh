@@ -31,7 +31,7 @@ namespace j2k {
 #define J2K_RING_WARPS 4     // warps per CTA
 #endif
 #ifndef J2K_RING_BYTES
-#define J2K_RING_BYTES 8704  // staging bytes per warp (8 stages of two 512 B + 32 B rows)
+#define J2K_RING_BYTES 12800  // staging bytes per warp: 5 stages of four 544 B rows (u16), 3 stages of four 1056 B rows (float32)
 #endif
 #define J2K_RING_MAXD 8
 #ifndef J2K_RING_MINB
@@ -226,7 +226,8 @@ struct FwdRing {
     static constexpr int LB = NS * PB;                // bytes per lane per row
     static constexpr int NW = LB / 4;                 // 32-bit words per lane per row
     static constexpr int ROWB = 32 * LB + 32;         // staged row slot (16 B slack for the alignment phase, 16 B rounding)
-    static constexpr int STAGEB = 2 * ROWB;
+    static constexpr int RPS = 2;                     // row pairs (= loop iterations) per stage: one barrier, one issue per two
+    static constexpr int STAGEB = 2 * RPS * ROWB;
     static constexpr int D = (J2K_RING_BYTES / STAGEB) > J2K_RING_MAXD ? J2K_RING_MAXD : (J2K_RING_BYTES / STAGEB);
     static constexpr int LDALIGN = (LB % 16 == 0) ? 16 : (LB % 8 == 0 ? 8 : 4);
     static constexpr bool MAGIC = (WT == 97 && RAWIN && SG == 0);  // u8/u16 -> float32 without I2F
@@ -433,9 +434,10 @@ struct FwdRing {
         const int ky1 = min(ky0 + S.chunk_pairs, S.Ky);
         const int r_begin = 2 * (ky0 - LAG) - py;  // low-type row of iteration 0
         const int n_it = ky1 - ky0 + 2 * LAG;
-        // iterations j_lo <= j < j_hi stage two in-range, adjacent rows; the others mirror the row number
-        const int j_lo = r_begin < 0 ? (1 - r_begin) >> 1 : 0;
-        const int j_hi = (h - r_begin) >> 1;
+        const int n_st = (n_it + RPS - 1) / RPS;
+        // stages s_lo <= s < s_hi stage 2 RPS in-range, adjacent rows; the others mirror the row numbers
+        const int s_lo = r_begin < 0 ? (2 * RPS - 1 - r_begin) / (2 * RPS) : 0;
+        const int s_hi = (h - r_begin) / (2 * RPS);
 
         int* p_ll = (int*)S.ll.base + S.ll.off[item] + (long long)S.ll.y_off * S.ll.row_stride + S.ll.x_off + kx0;
         int* p_hl = (int*)S.hl.base + S.hl.off[item] + (long long)S.hl.y_off * S.hl.row_stride + S.hl.x_off + kx0;
@@ -444,35 +446,44 @@ struct FwdRing {
         const int rs_ll = S.ll.row_stride, rs_b = S.hl.row_stride;
         const long long cs_ll = S.ll.comp_stride, cs_b = S.hl.comp_stride;
 
-        // producer cursor (warp-uniform): next iteration to stage, its slot and the source pointer of its low-type row
+        // producer cursor (warp-uniform): next stage to fill, its slot and the source pointer of its first row
         int pj = 0, pslot = 0;
         const unsigned char* psrc = src + (long long)r_begin * pitch;
         const smem_t dst_s = rw.ring + dst_off;
-        // lane 0 stages both rows of iteration pj (TMA bulk copies, completion on the stage barrier)
+        // lane 0 stages the 2 RPS rows of stage pj (TMA bulk copies, completion on the stage barrier)
         auto issue = [&]() {
             if (lane == 0) {
-                const unsigned char* se = psrc;
-                const unsigned char* so = psrc + pitch;
-                if (pj < j_lo || pj >= j_hi) {
-                    const int r0 = r_begin + 2 * pj;
-                    se = src + (long long)mirror_fast(r0, h) * pitch;
-                    so = src + (long long)mirror_fast(r0 + 1, h) * pitch;
-                }
                 const smem_t bar = rw.bars + 8 * pslot;
                 const smem_t dst = dst_s + pslot * STAGEB;
-                mbar_expect_tx(bar, 2 * copy_bytes);
-                bulk_g2s(dst, se, copy_bytes, bar);
-                bulk_g2s(dst + ROWB, so, copy_bytes, bar);
+                mbar_expect_tx(bar, 2 * RPS * copy_bytes);
+                if (pj >= s_lo && pj < s_hi) {
+#pragma unroll
+                    for (int k = 0; k < 2 * RPS; k++) bulk_g2s(dst + k * ROWB, psrc + k * pitch, copy_bytes, bar);
+                } else {
+                    const int r0 = r_begin + 2 * RPS * pj;
+#pragma unroll
+                    for (int k = 0; k < 2 * RPS; k++) bulk_g2s(dst + k * ROWB, src + (long long)mirror_fast(r0 + k, h) * pitch, copy_bytes, bar);
+                }
             }
             pj++;
-            psrc += 2 * pitch;
+            psrc += 2 * RPS * pitch;
             pslot = (pslot + 1 == D) ? 0 : pslot + 1;
         };
         __syncwarp();
 #pragma unroll 1
-        for (int j = 0; j < D - 1 && j < n_it; j++) issue();
+        for (int j = 0; j < D - 1 && j < n_st; j++) issue();
 
         int cslot = 0;
+        smem_t stage = rw.ring;
+        // start of a stage: the previous stage's slot is free once every lane is past its arithmetic -> refill, then wait
+        auto next_stage = [&]() {
+            __syncwarp();
+            if (pj < n_st) issue();
+            mbar_wait(rw.bars + 8 * cslot, (rw.phase >> cslot) & 1u);
+            rw.phase ^= 1u << cslot;
+            stage = rw.ring + cslot * STAGEB;
+            cslot = (cslot + 1 == D) ? 0 : cslot + 1;
+        };
         const smem_t lane_s = rw.ring + lane_off;
         if constexpr (WT == 97) {
             const float2 A2 = splat2(J2K_ALPHA), B2 = splat2(J2K_BETA), G2 = splat2(J2K_GAMMA), D2 = splat2(J2K_DELTA);
@@ -489,15 +500,10 @@ struct FwdRing {
 #pragma unroll
                 for (int j = 0; j < NP; j++) { sa.pe[c][j] = sa.po[c][j] = sa.s1p[c][j] = sa.d1p[c][j] = sa.d2p[c][j] = make_float2(0.f, 0.f); }
             // one iteration: consumes the vertical window state `in`, leaves the advanced state in `out`
-            auto body = [&](int it, const VState& in, VState& out) {
-                // the slot of iteration it-1 (slot D-1 when it == 0) is free once every lane is past its arithmetic: refill it
-                __syncwarp();
-                if (pj < n_it) issue();
-                mbar_wait(rw.bars + 8 * cslot, (rw.phase >> cslot) & 1u);
-                rw.phase ^= 1u << cslot;
-                const smem_t row_e = rw.ring + cslot * STAGEB;
+            auto body = [&](int it, const int half, const VState& in, VState& out) {
+                if (half == 0) next_stage();
+                const smem_t row_e = stage + half * 2 * ROWB;
                 const smem_t row_o = row_e + ROWB;
-                cslot = (cslot + 1 == D) ? 0 : cslot + 1;
 
                 if (fix) fix_halo(row_e, row_o, lane, fix_l, fix_r, w, vb);
                 load_pairs(row_e, lane_off, active, raw, dc, fmagic, one, out.pe);
@@ -595,9 +601,9 @@ struct FwdRing {
             // two iterations per trip with the window state ping-ponging between sa and sb: no register shuffling
 #pragma unroll 1
             for (int it = 0; it < n_it; it += 2) {
-                body(it, sa, sb);
+                body(it, 0, sa, sb);
                 if (it + 1 >= n_it) break;
-                body(it + 1, sb, sa);
+                body(it + 1, 1, sb, sa);
             }
         } else {
             const int sh_ll = S.q[0].shift, sh_hl = S.q[1].shift, sh_lh = S.q[2].shift, sh_hh = S.q[3].shift;
@@ -608,13 +614,10 @@ struct FwdRing {
                 for (int s = 0; s < NS; s++) { pe[c][s] = 0; po[c][s] = 0; d1p[c][s] = 0; }
 #pragma unroll 1
             for (int it = 0; it < n_it; it++) {
-                __syncwarp();
-                if (pj < n_it) issue();
-                mbar_wait(rw.bars + 8 * cslot, (rw.phase >> cslot) & 1u);
-                rw.phase ^= 1u << cslot;
-                const smem_t row_e = rw.ring + cslot * STAGEB;
+                const int half = it & (RPS - 1);
+                if (half == 0) next_stage();
+                const smem_t row_e = stage + half * 2 * ROWB;
                 const smem_t row_o = row_e + ROWB;
-                cslot = (cslot + 1 == D) ? 0 : cslot + 1;
 
                 int e[NC][NS], o[NC][NS], lo[NC][NS], hi[NC][NS];
                 if (fix) fix_halo(row_e, row_o, lane, fix_l, fix_r, w, vb);
