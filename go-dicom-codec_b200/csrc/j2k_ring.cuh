@@ -780,7 +780,9 @@ struct InvRing {
     static constexpr int LB = NP * 4;          // bytes per lane per band row
     static constexpr int ROWB = 32 * LB + 32;  // staged band row slot
     static constexpr int NROWS = 4 * NC;       // LL, HL, LH, HH per component
-    static constexpr int STAGEB = NROWS * ROWB;
+    static constexpr int RPS = (NC == 1) ? 2 : 1;  // row pairs (= loop iterations) per stage
+    static constexpr int PAIRB = NROWS * ROWB;     // staged bytes of one row pair
+    static constexpr int STAGEB = RPS * PAIRB;
     static constexpr int D = (J2K_INV_RING_BYTES / STAGEB) > J2K_RING_MAXD ? J2K_RING_MAXD : (J2K_INV_RING_BYTES / STAGEB);
     static_assert(D >= 2, "ring too small for this stage size");
     static_assert(NC == 1 || FINAL, "3-component jobs write interleaved pixels");
@@ -910,23 +912,28 @@ struct InvRing {
         const long long rp_ll = (long long)S.ll.row_stride * 4, rp_b = (long long)S.hl.row_stride * 4;
         const long long cp_ll = S.ll.comp_stride * 4, cp_b = S.hl.comp_stride * 4;
 
+        const int n_st = (n_it + RPS - 1) / RPS;
         int pj = 0, pslot = 0;
         const smem_t dst_s = rw.ring + dst_off;
+        // lane 0 stages the band rows of the RPS row pairs of stage pj
         auto issue = [&]() {
             if (lane == 0) {
-                // band rows of the pair: low-type interleaved row 2t - py -> yl, high-type row 2t + 1 - py -> yh (mirrored)
-                const int t = t_begin + pj;
-                const int pl = mirror_fast(2 * t - py, h), ph = mirror_fast(2 * t + 1 - py, h);
-                const int yl = (pl - py) >> 1, yh = (ph - (1 - py)) >> 1;
                 const smem_t bar = rw.bars + 8 * pslot;
                 const smem_t dst = dst_s + pslot * STAGEB;
-                mbar_expect_tx(bar, NROWS * copy_bytes);
+                mbar_expect_tx(bar, RPS * NROWS * copy_bytes);
 #pragma unroll
-                for (int c = 0; c < NC; c++) {
-                    bulk_g2s(dst + (4 * c + 0) * ROWB, b_ll + c * cp_ll + yl * rp_ll, copy_bytes, bar);
-                    bulk_g2s(dst + (4 * c + 1) * ROWB, b_hl + c * cp_b + yl * rp_b, copy_bytes, bar);
-                    bulk_g2s(dst + (4 * c + 2) * ROWB, b_lh + c * cp_b + yh * rp_b, copy_bytes, bar);
-                    bulk_g2s(dst + (4 * c + 3) * ROWB, b_hh + c * cp_b + yh * rp_b, copy_bytes, bar);
+                for (int k = 0; k < RPS; k++) {
+                    // band rows of the pair: low-type interleaved row 2t - py -> yl, high-type row 2t + 1 - py -> yh (mirrored)
+                    const int t = t_begin + RPS * pj + k;
+                    const int pl = mirror_fast(2 * t - py, h), ph = mirror_fast(2 * t + 1 - py, h);
+                    const int yl = (pl - py) >> 1, yh = (ph - (1 - py)) >> 1;
+#pragma unroll
+                    for (int c = 0; c < NC; c++) {
+                        bulk_g2s(dst + k * PAIRB + (4 * c + 0) * ROWB, b_ll + c * cp_ll + yl * rp_ll, copy_bytes, bar);
+                        bulk_g2s(dst + k * PAIRB + (4 * c + 1) * ROWB, b_hl + c * cp_b + yl * rp_b, copy_bytes, bar);
+                        bulk_g2s(dst + k * PAIRB + (4 * c + 2) * ROWB, b_lh + c * cp_b + yh * rp_b, copy_bytes, bar);
+                        bulk_g2s(dst + k * PAIRB + (4 * c + 3) * ROWB, b_hh + c * cp_b + yh * rp_b, copy_bytes, bar);
+                    }
                 }
             }
             pj++;
@@ -934,7 +941,7 @@ struct InvRing {
         };
         __syncwarp();
 #pragma unroll 1
-        for (int j = 0; j < D - 1 && j < n_it; j++) issue();
+        for (int j = 0; j < D - 1 && j < n_st; j++) issue();
 
         // destination rows
         constexpr int XES = FINAL ? ((OUT == IN_U8) ? 1 : 2) : 4;
@@ -946,6 +953,15 @@ struct InvRing {
         const int x_mode = S.x_mode;
 
         int cslot = 0;
+        smem_t stage_base = rw.ring;
+        auto next_stage = [&]() {
+            __syncwarp();
+            if (pj < n_st) issue();
+            mbar_wait(rw.bars + 8 * cslot, (rw.phase >> cslot) & 1u);
+            rw.phase ^= 1u << cslot;
+            stage_base = rw.ring + cslot * STAGEB;
+            cslot = (cslot + 1 == D) ? 0 : cslot + 1;
+        };
         if constexpr (WT == 97) {
             const float2 sclE = S.rcpE, sclO = S.rcpO;
             const bool raw_ll = S.ll.mode == DQ_RAW, raw_hl = S.hl.mode == DQ_RAW, raw_lh = S.lh_.mode == DQ_RAW, raw_hh = S.hh.mode == DQ_RAW;
@@ -956,13 +972,9 @@ struct InvRing {
             for (int c = 0; c < NC; c++)
 #pragma unroll
                 for (int j = 0; j < NP; j++) { sa.dp[c][j] = sa.s1p[c][j] = sa.d1p[c][j] = sa.s2p[c][j] = make_float2(0.f, 0.f); }
-            auto body = [&](int it, const VState& in, VState& out) {
-                __syncwarp();
-                if (pj < n_it) issue();
-                mbar_wait(rw.bars + 8 * cslot, (rw.phase >> cslot) & 1u);
-                rw.phase ^= 1u << cslot;
-                const smem_t stage = rw.ring + cslot * STAGEB;
-                cslot = (cslot + 1 == D) ? 0 : cslot + 1;
+            auto body = [&](int it, const int half, const VState& in, VState& out) {
+                if (RPS == 1 || half == 0) next_stage();
+                const smem_t stage = stage_base + (RPS == 1 ? 0 : half) * PAIRB;
                 if (fix) fix_halo(stage, lane, fix_l, fix_r, w, bw, vb);
 
                 float2 xe[NC][NP], xo[NC][NP];  // finished rows of pair t - LAG as column pairs
@@ -1077,9 +1089,9 @@ struct InvRing {
             };
 #pragma unroll 1
             for (int it = 0; it < n_it; it += 2) {
-                body(it, sa, sb);
+                body(it, 0, sa, sb);
                 if (it + 1 >= n_it) break;
-                body(it + 1, sb, sa);
+                body(it + 1, 1, sb, sa);
             }
         } else {
             const bool halve_ll = S.ll.mode == DQ_HALVE, halve_hl = S.hl.mode == DQ_HALVE, halve_lh = S.lh_.mode == DQ_HALVE,
@@ -1091,12 +1103,9 @@ struct InvRing {
                 for (int s = 0; s < NS; s++) { dp[c][s] = 0; s1p[c][s] = 0; }
 #pragma unroll 1
             for (int it = 0; it < n_it; it++) {
-                __syncwarp();
-                if (pj < n_it) issue();
-                mbar_wait(rw.bars + 8 * cslot, (rw.phase >> cslot) & 1u);
-                rw.phase ^= 1u << cslot;
-                const smem_t stage = rw.ring + cslot * STAGEB;
-                cslot = (cslot + 1 == D) ? 0 : cslot + 1;
+                const int half = it & (RPS - 1);
+                if (half == 0) next_stage();
+                const smem_t stage = stage_base + half * PAIRB;
                 if (fix) fix_halo(stage, lane, fix_l, fix_r, w, bw, vb);
 
                 int xe[NC][NS], xo[NC][NS];
