@@ -49,20 +49,57 @@ def synth_frames(n, seed):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md): NVML polled from a thread
+    every ~4 ms (a timed region here lasts tens of ms), nvidia-smi -lms as the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.rows = []
         self.proc = None
+        self.sm, self.reasons, self.sm_max = [], set(), None
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.source = None
+
+    def _nvml_loop(self, nv, h):
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                for name, bit in self.BITS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.004)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            import pynvml as nv
+            nv.nvmlInit()
+            idx = self.gpu
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.gpu])
+                except Exception:
+                    idx = self.gpu
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.thread.start()
+            self.source = "nvml"
+            return
+        except Exception:
+            self.thread = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            self.source = "nvidia-smi"
         except Exception:
             self.proc = None
 
@@ -71,6 +108,13 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.thread:
+            self.stop_flag.set()
+            self.thread.join(timeout=1.0)
+            if not self.sm:
+                return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": [], "samples": 0, "source": self.source}
+            return {"sm_mhz": statistics.median(self.sm), "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+                    "samples": len(self.sm), "source": self.source}
         if self.proc:
             time.sleep(0.15)
             self.proc.terminate()
@@ -84,8 +128,9 @@ class ClockSampler:
             except Exception:
                 pass
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": self.source}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "source": self.source}
 
 
 def dist_env():
@@ -117,6 +162,27 @@ def cpu_leg(threads, frames, steps, warmup):
     return frames * PIX / dt / 1e6, dt * 1e3
 
 
+_JSON_FD = None
+
+
+def protect_stdout():
+    """The contract is ONE JSON line on stdout: anything a library prints there (NCCL's version banner, for one) is sent
+    to stderr instead, and the JSON line is written to the original stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def run_reference(args):
     rank, _, world = dist_env()
     if rank != 0:
@@ -136,13 +202,13 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--frames", type=int, default=16, help="C2 frames per rank per step")
     ap.add_argument("--streams", type=int, default=2, help="streams the resident steps alternate over (1 = serial)")
@@ -151,6 +217,7 @@ def main():
     ap.add_argument("--no-inverse", action="store_true", help="skip the supplementary inverse-direction leg")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
     args = ap.parse_args()
+    protect_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -343,7 +410,7 @@ def main():
                     "steps": e2e_steps, "matches_resident": same},
             "gpu_launches": int(launches), "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
     if use_dist:
         dist.destroy_process_group()

@@ -250,7 +250,16 @@ __global__ void __launch_bounds__(256) quant_api_kernel(int op, long long n, con
 // ---- wavelet.ConvertFloat32ToInt32OpenJPEG (dwt97.go:473-503)
 __global__ void __launch_bounds__(256) f32_to_i32_kernel(const float* in, int* out, long long n) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = __float2int_rn(in[i]);
+    if (i >= n) return;
+    const float v = in[i];
+    int r = __float2int_rn(v);
+    if (!(fabsf(v) < 2147483648.0f)) {
+        // outside int32 the reference truncates its int64 result (integers all: |v| >= 2^31), and beyond int64 the
+        // amd64 "integer indefinite" 0x8000000000000000 flows through the remaining arithmetic of dwt97.go:483-503
+        if (fabsf(v) < 9223372036854775808.0f) r = (int)(unsigned)(unsigned long long)__float2ll_rz(v);
+        else r = (v != v) ? 0 : (v > 0.f ? 1 : -1);
+    }
+    out[i] = r;
 }
 
 }  // namespace j2k

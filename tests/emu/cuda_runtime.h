@@ -60,6 +60,12 @@ static inline int __float2int_rn(float f) {
     if (f <= -2147483648.0f) return (-2147483647 - 1);
     return (int)lrintf(f);
 }
+static inline long long __float2ll_rz(float f) {  // saturating, NaN -> 0 (the device intrinsic's behaviour)
+    if (f != f) return 0;
+    if (f >= 9223372036854775808.0f) return 9223372036854775807LL;
+    if (f <= -9223372036854775808.0f) return (-9223372036854775807LL - 1);
+    return (long long)f;
+}
 
 namespace emu {
 uint32_t shfl_exchange(uint32_t v, int src_lane);  // yields the calling fiber

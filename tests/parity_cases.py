@@ -94,3 +94,84 @@ def check_pipeline(ctx, oracle, w, h, c, bits, signed, L, reversible, tile=(0, 0
     if reversible:
         assert np.array_equal(px, raw), "lossless identity"
     return got, px
+
+
+# ---- Part-2 custom MCT / binding lists (encoder.go:465-665, decoder.go:630-735), planar entry, package APIs
+
+CUSTOM_CASES = {
+    # name: (components, fwd mode, fwd kwargs, inv mode, inv kwargs)
+    "int_matrix": (3, abi.MCT_CUSTOM_INT, dict(mct_matrix=[[1, 1, 0], [0, 1, -1], [2, 0, 1]], mct_offsets=[3, -7, 0]),
+                   abi.MCT_CUSTOM_FLOAT, dict(mct_matrix=[[0.5, -0.25, 0.125], [0.0, 1.0, 0.5], [-1.0, 0.5, 0.75]], mct_offsets=[3, -7, 0])),
+    "q13_matrix": (3, abi.MCT_CUSTOM_Q13, dict(mct_matrix=[[0.299, 0.587, 0.114], [-0.16875, -0.33126, 0.5], [0.5, -0.41869, -0.08131]]),
+                   abi.MCT_CUSTOM_FLOAT, dict(mct_matrix=[[1.0, 0.0, 1.402], [1.0, -0.34413, -0.71414], [1.0, 1.772, 0.0]])),
+    "q13_4comp": (4, abi.MCT_CUSTOM_Q13, dict(mct_matrix=[[0.25, 0.25, 0.25, 0.25], [1, -1, 0, 0], [0, 1, -1, 0], [0.5, 0, 0, -0.5]],
+                                              mct_offsets=[1, 2, 3, 4]),
+                  abi.MCT_CUSTOM_FLOAT, dict(mct_matrix=[[1, 0.75, 0.5, 0.5], [1, -0.25, 0.5, 0.5], [1, -0.25, -0.5, 0.5], [1, 0.75, 0.5, -1.5]],
+                                             mct_offsets=[1, 2, 3, 4])),
+}
+
+
+def binding_cases():
+    fb = [abi.make_binding((0, 1, 2), [[1, 0, 1], [0, 1, 0], [-1, 0, 2]], [5, 0, -5], element_type=0),
+          abi.make_binding((2, 0), [[0.5, 0.5], [1.0, -1.0]], None, element_type=1),
+          abi.make_binding((), None, [1, 1, 1], element_type=0)]
+    ib = [abi.make_binding((2, 0), [[1.0, 0.5], [1.0, -0.5]], None, element_type=1),
+          abi.make_binding((0, 1, 2), [[2, 0, -1], [0, 1, 0], [1, 0, 1]], [5, 0, -5], element_type=0),
+          abi.make_binding((1,), None, [9], element_type=0)]
+    return fb, ib
+
+
+def check_custom_mct(ctx, oracle, w, h, bits, L, reversible, case, tile=(0, 0), seed=3):
+    """Forward and inverse pipelines with Part-2 transforms; the inverse is checked on the forward output (not an
+    identity: the reference's custom inverse is float64 + math.Round, decoder.go:696-723)."""
+    rng = np.random.default_rng(seed)
+    es = ds = None
+    if not reversible:
+        es, ds = steps_for(oracle, L, bits)
+    if case == "bindings":
+        C = 3
+        fb, ib = binding_cases()
+        fp = abi.fwd_params(w, h, C, bits, False, tile[0], tile[1], L, reversible, False, abi.MCT_BINDINGS, es, bindings=fb)
+        ip = abi.inv_params(w, h, C, bits, False, tile[0], tile[1], L, reversible, False, abi.MCT_BINDINGS, ds, bindings=ib)
+    else:
+        C, fm, fkw, im, ikw = CUSTOM_CASES[case]
+        fp = abi.fwd_params(w, h, C, bits, False, tile[0], tile[1], L, reversible, False, fm, es, **fkw)
+        ip = abi.inv_params(w, h, C, bits, False, tile[0], tile[1], L, reversible, False, im, ds, **ikw)
+    raw = raw_bytes(synth(rng, h, w, C, bits, False, "noise"))
+    got, want = ctx.forward(fp, raw), oracle.forward(fp, raw)
+    assert np.array_equal(got, want), f"custom MCT forward ({case})"
+    back_in = want if reversible else M.t1_emulate(want, False)
+    px, planes = ctx.inverse(ip, back_in, want_planes=True)
+    opx, oplanes = oracle.inverse(ip, back_in, want_planes=True)
+    assert np.array_equal(planes, oplanes), f"custom MCT inverse planes ({case})"
+    assert np.array_equal(px, opx), f"custom MCT inverse pixels ({case})"
+
+
+def check_planar(ctx, oracle, w, h, c, bits, signed, L, reversible, seed=4):
+    """EncodeComponents entry (encoder.go:221-273): planar int32 input, no byte conversion."""
+    rng = np.random.default_rng(seed)
+    lo, hi = (-(2 ** (bits - 1)), 2 ** (bits - 1)) if signed else (0, 2 ** bits)
+    planes = [rng.integers(lo, hi, (h, w)).astype(np.int32) for _ in range(c)]
+    fp, _ = fwd_inv_params(w, h, c, bits, signed, L, reversible, oracle)
+    assert np.array_equal(ctx.forward_planar(fp, planes), oracle.forward_planar(fp, planes)), "planar forward"
+
+
+def check_package_api(ctx, oracle, n=100_003, seed=6):
+    """colorspace / quantization package functions (rct.go, ict.go, quantization.go:310-340, dwt97.go:473-503)."""
+    rng = np.random.default_rng(seed)
+    r, g, b = (rng.integers(-40000, 70000, n).astype(np.int32) for _ in range(3))
+    for name in ("rct_forward", "rct_inverse", "ict_forward", "ict_inverse"):
+        got, want = getattr(ctx, name)(r, g, b), getattr(oracle, name)(r, g, b)
+        for k in range(3):
+            assert np.array_equal(got[k], want[k]), f"{name} component {k}"
+    y, cb, cr = oracle.rct_forward(r, g, b)
+    back = ctx.rct_inverse(y, cb, cr)
+    assert all(np.array_equal(u, v) for u, v in zip(back, (r, g, b))), "RCT identity"
+    co = rng.integers(-2 ** 20, 2 ** 20, n).astype(np.int32)
+    co[:8] = [0, 1, -1, 3, -3, 5, 7, -7]  # ties at step 2
+    for step in (1.0, 2.0, 0.5, 3.7, 0.0078125, 1234.5):
+        assert np.array_equal(ctx.quantize_coefficients(co, step), oracle.quantize_coefficients(co, step)), f"quantize step {step}"
+        assert np.array_equal(ctx.dequantize_coefficients(co >> 6, step), oracle.dequantize_coefficients(co >> 6, step)), f"dequantize step {step}"
+    f = (rng.standard_normal(n) * 1000).astype(np.float32)
+    f[:10] = [0.5, 1.5, 2.5, -0.5, -1.5, -2.5, 0.49999997, 2147483648.0, -2147483904.0, np.float32("nan")]
+    assert np.array_equal(ctx.convert_f32_to_i32(f), oracle.convert_f32_to_i32(f)), "float32 -> int32 rounding"

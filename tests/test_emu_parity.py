@@ -65,3 +65,24 @@ def test_fast_path_shapes(ectx, oracle, w, h, c, bits, signed, L, rev, capfd):
     import os
     os.environ["J2K_B200_TRACE"] = "1"
     PC.check_pipeline(ectx, oracle, w, h, c, bits, signed, L, rev, seed=w)
+
+
+@pytest.mark.parametrize("case", ["int_matrix", "q13_matrix", "q13_4comp", "bindings"])
+@pytest.mark.parametrize("rev", [True, False])
+def test_custom_mct(ectx, oracle, case, rev):
+    PC.check_custom_mct(ectx, oracle, 40, 24, 8, 2, rev, case)
+
+
+def test_custom_mct_tiled(ectx, oracle):
+    PC.check_custom_mct(ectx, oracle, 50, 40, 12, 2, True, "bindings", tile=(32, 32))
+
+
+@pytest.mark.parametrize("w,h,c,bits,signed,L,rev", [
+    (40, 24, 1, 12, True, 2, True), (40, 24, 3, 8, False, 2, False), (136, 12, 1, 16, False, 2, False), (33, 17, 3, 10, True, 3, True),
+])
+def test_planar_entry(ectx, oracle, w, h, c, bits, signed, L, rev):
+    PC.check_planar(ectx, oracle, w, h, c, bits, signed, L, rev)
+
+
+def test_package_api(ectx, oracle):
+    PC.check_package_api(ectx, oracle, n=5003)

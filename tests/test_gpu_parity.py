@@ -56,6 +56,27 @@ def test_htj2k_and_fused_t1_shift(ctx, oracle):
     PC.check_pipeline(ctx, oracle, 400, 360, 3, 8, False, 4, False, steps_kind="quality")
 
 
+@pytest.mark.parametrize("case", ["int_matrix", "q13_matrix", "q13_4comp", "bindings"])
+@pytest.mark.parametrize("rev", [True, False])
+def test_custom_mct(ctx, oracle, case, rev):
+    PC.check_custom_mct(ctx, oracle, 640, 360, 8 if rev else 12, 4, rev, case)
+
+
+def test_custom_mct_tiled(ctx, oracle):
+    PC.check_custom_mct(ctx, oracle, 700, 500, 12, 3, True, "bindings", tile=(256, 256))
+
+
+@pytest.mark.parametrize("w,h,c,bits,signed,L,rev", [
+    (512, 512, 1, 16, True, 5, True), (640, 480, 3, 8, False, 4, False), (1024, 256, 1, 12, False, 5, False), (333, 217, 3, 10, True, 3, True),
+])
+def test_planar_entry(ctx, oracle, w, h, c, bits, signed, L, rev):
+    PC.check_planar(ctx, oracle, w, h, c, bits, signed, L, rev)
+
+
+def test_package_api(ctx, oracle):
+    PC.check_package_api(ctx, oracle, n=1_000_003)
+
+
 def test_interop_raws(ctx, oracle):
     man = json.load(open(os.path.join(HERE, "golden", "interop", "manifest.json")))
     for fx in man["fixtures"]:
