@@ -367,27 +367,43 @@ def main():
                    "step_frac_of_hbm_peak": step_alg / (ims * 1e-3) / 1e9 / peak,
                    "what": "coefficients -> dequantize -> 6-level inverse 9/7 -> round -> +DC -> clamp -> pack u16 (D4-D13), resident"}
 
-    # ---- end to end through the C ABI with host buffers (pinned), copies inside the timed region
-    e2e_val, same, e2e_steps = None, None, 0
+    # ---- end to end through the C ABI with host buffers (pinned), copies inside the timed region.
+    # Headline form: the ticketed calls the codec adapter's frame loop uses -- step i+1 is submitted
+    # before step i is waited for, so its upload runs under step i's download; every step still moves its own input
+    # H2D and its own result D2H inside the timed region.  `sync_value` is the same through the blocking call.
+    e2e_val, e2e_sync, same, e2e_steps = None, None, None, 0
     if not args.no_e2e:
         h_in = ctx.pinned(B * frame_bytes).reshape(B, frame_bytes)
-        h_out = ctx.pinned(B * PIX * 4, np.int32).reshape(B, PIX)
+        h_outs = [ctx.pinned(B * PIX * 4, np.int32).reshape(B, PIX) for _ in range(2)]
         for f in range(B):
             h_in[f] = host[f % host.shape[0]]
         e2e_steps = max(3, min(args.steps, 10))
         for _ in range(2):
-            ctx.forward_batch(fp, h_in, h_out)
+            ctx.forward_batch(fp, h_in, h_outs[0])
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            ctx.forward_batch(fp, h_in, h_out)
+            ctx.forward_batch(fp, h_in, h_outs[0])
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], device="cuda")
+        if use_dist:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_sync = world * B * PIX / (float(t.item()) / e2e_steps) / 1e6
+        barrier()
+        t0 = time.perf_counter()
+        prev = ctx.submit_forward(fp, h_in, h_outs[0])
+        for i in range(1, e2e_steps):
+            cur = ctx.submit_forward(fp, h_in, h_outs[i & 1])
+            ctx.wait(prev)
+            prev = cur
+        ctx.wait(prev)
         dt = time.perf_counter() - t0
         t = torch.tensor([dt], device="cuda")
         if use_dist:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_val = world * B * PIX / (float(t.item()) / e2e_steps) / 1e6
-        # the e2e result must be the same coefficients as the resident run
-        same = bool(torch.equal(torch.from_numpy(np.asarray(h_out[0])).cuda(), d_out[0]))
+        # the e2e results must be the same coefficients as the resident run
+        same = all(bool(torch.equal(torch.from_numpy(np.asarray(h[B - 1])).cuda(), d_out[B - 1])) for h in h_outs)
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -407,7 +423,8 @@ def main():
                        "streams": NS},
             "roofline": roofline, "inverse": inverse, "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": "Mpixel/s", "h2d_bytes_per_step": B * frame_bytes, "d2h_bytes_per_step": B * PIX * 4,
-                    "steps": e2e_steps, "matches_resident": same},
+                    "steps": e2e_steps, "matches_resident": same, "sync_value": e2e_sync,
+                    "api": "j2k_submit_forward / j2k_wait, two steps in flight (sync_value: blocking j2k_forward_batch)"},
             "gpu_launches": int(launches), "clocks": clocks,
         }
         emit(line)

@@ -229,7 +229,8 @@ struct j2k_ctx {
     j2k_timing last{};
     std::vector<void*> pinned;
     long long next_ticket = 1;
-    std::map<long long, std::vector<int>> tickets;
+    struct TicketEv { int di; cudaEvent_t ev; };
+    std::map<long long, std::vector<TicketEv>> tickets;  // per device: an event behind the job's last D2H copy
     // per-launch profiling (j2k_set_profiling)
     bool profiling = false;
     int prof_dev = 0;
@@ -1414,7 +1415,9 @@ int enqueue_host_job(j2k_ctx* ctx, int di, const HostJob& J, int f0, int f1, boo
     const long long HW = (long long)s.W * s.H;
     // sub-batches: enough frames per launch to fill the GPU, at least two to overlap copies with kernels
     long long frame_samples_total = HW * s.C;
-    int sub = (int)((64LL << 20) / (frame_samples_total > 0 ? frame_samples_total : 1));
+    // ~16 Msamples per sub-batch: the first upload (the only copy nothing hides) stays short, a launch still fills the GPU
+    static const long long sub_samples = (long long)env_int("J2K_SUBBATCH_MSAMPLES", 16) << 20;
+    int sub = (int)(sub_samples / (frame_samples_total > 0 ? frame_samples_total : 1));
     if (sub < 1) sub = 1;
     if (sub > n) sub = n;
     if (timing) CK(cudaEventRecord(d.ev_t[0], d.s_h2d));
@@ -1582,6 +1585,7 @@ void j2k_shutdown(j2k_ctx* ctx) {
         for (int k = 0; k < 2; k++) { cudaEventDestroy(d.ev_in[k]); cudaEventDestroy(d.ev_k[k]); cudaEventDestroy(d.ev_out[k]); }
         cudaStreamDestroy(d.s_main); cudaStreamDestroy(d.s_h2d); cudaStreamDestroy(d.s_d2h);
     }
+    for (auto& kv : ctx->tickets) for (auto& t : kv.second) cudaEventDestroy(t.ev);
     for (void* p : ctx->pinned) cudaFreeHost(p);
     for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
     delete ctx;
@@ -1772,15 +1776,34 @@ int j2k_inverse_device(j2k_ctx* ctx, int dev, const j2k_inv_params* p, int nfram
 
 // ---- asynchronous
 
+// A ticket completes when the job's last device-to-host copy has landed: one event per device the job used, recorded
+// behind that copy, so waiting for ticket i does not wait for the jobs submitted after it (frame i+1 can be in
+// flight while the caller entropy-codes frame i).
+static int64_t make_ticket(j2k_ctx* ctx, const std::vector<int>& used) {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    std::vector<j2k_ctx::TicketEv> evs;
+    for (int di : used) {
+        DeviceCtx& d = ctx->devs[di];
+        cudaEvent_t ev = nullptr;
+        if (cudaSetDevice(d.dev) != cudaSuccess || cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventRecord(ev, d.s_d2h) != cudaSuccess) {
+            for (auto& t : evs) cudaEventDestroy(t.ev);
+            if (ev) cudaEventDestroy(ev);
+            return fail(J2K_ERR_CUDA, "ticket event: %s", cudaGetErrorString(cudaGetLastError()));
+        }
+        evs.push_back({di, ev});
+    }
+    long long t = ctx->next_ticket++;
+    ctx->tickets[t] = evs;
+    return t;
+}
+
 int64_t j2k_submit_forward(j2k_ctx* ctx, const j2k_fwd_params* p, int nframes, const void* pixels, size_t frame_stride_bytes,
                            int32_t* coeffs_out) {
     std::vector<int> used;
     int rc = forward_host(ctx, p, nframes, pixels, frame_stride_bytes, coeffs_out, false, false, &used);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    long long t = ctx->next_ticket++;
-    ctx->tickets[t] = used;
-    return t;
+    return make_ticket(ctx, used);
 }
 
 int64_t j2k_submit_inverse(j2k_ctx* ctx, const j2k_inv_params* p, int nframes, const int32_t* coeffs_in, void* pixels_out,
@@ -1788,24 +1811,26 @@ int64_t j2k_submit_inverse(j2k_ctx* ctx, const j2k_inv_params* p, int nframes, c
     std::vector<int> used;
     int rc = inverse_host(ctx, p, nframes, coeffs_in, pixels_out, frame_stride_bytes, planes_out, false, &used);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    long long t = ctx->next_ticket++;
-    ctx->tickets[t] = used;
-    return t;
+    return make_ticket(ctx, used);
 }
 
 int j2k_wait(j2k_ctx* ctx, int64_t ticket) {
     if (!ctx) return fail(J2K_ERR_INVALID_ARG, "context is NULL");
-    std::vector<int> used;
+    std::vector<j2k_ctx::TicketEv> evs;
     {
         std::lock_guard<std::mutex> lk(ctx->mu);
         auto it = ctx->tickets.find(ticket);
         if (it == ctx->tickets.end()) return fail(J2K_ERR_TICKET, "unknown ticket %lld", (long long)ticket);
-        used = it->second;
+        evs = it->second;
         ctx->tickets.erase(it);
     }
     int rc = 0;
-    for (int di : used) { int r2 = sync_dev(ctx, di); if (!rc) rc = r2; }
+    for (auto& t : evs) {
+        cudaError_t e = cudaSetDevice(ctx->devs[t.di].dev);
+        if (e == cudaSuccess) e = cudaEventSynchronize(t.ev);
+        cudaEventDestroy(t.ev);
+        if (e != cudaSuccess && !rc) rc = fail(J2K_ERR_CUDA, "j2k_wait: %s", cudaGetErrorString(e));
+    }
     return rc;
 }
 

@@ -98,6 +98,7 @@ __device__ __forceinline__ unsigned ld_relaxed(const unsigned* p) { return *p; }
 __device__ __forceinline__ void fence_acquire() {}
 __device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) { *p += v; }
 __device__ __forceinline__ void backoff() {}
+__device__ __forceinline__ bool elect_one() { return emu::lane_id() == 0; }
 __device__ __forceinline__ uint4 lds128(smem_t a) { uint4 v; memcpy(&v, a, 16); return v; }
 __device__ __forceinline__ uint2 lds64(smem_t a) { uint2 v; memcpy(&v, a, 8); return v; }
 __device__ __forceinline__ unsigned lds32(smem_t a) { unsigned v; memcpy(&v, a, 4); return v; }
@@ -147,6 +148,13 @@ __device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void backoff() { __nanosleep(400); }
+// One lane of the (converged) warp: the form ptxas recognises as warp-uniform single-thread code, so the bulk copies
+// it guards take their operands from uniform registers without a per-copy broadcast loop.
+__device__ __forceinline__ bool elect_one() {
+    unsigned p;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(p));
+    return p != 0;
+}
 __device__ __forceinline__ uint4 lds128(smem_t a) {
     uint4 v;
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
@@ -452,7 +460,7 @@ struct FwdRing {
         const smem_t dst_s = rw.ring + dst_off;
         // lane 0 stages the 2 RPS rows of stage pj (TMA bulk copies, completion on the stage barrier)
         auto issue = [&]() {
-            if (lane == 0) {
+            if (elect_one()) {
                 const smem_t bar = rw.bars + 8 * pslot;
                 const smem_t dst = dst_s + pslot * STAGEB;
                 mbar_expect_tx(bar, 2 * RPS * copy_bytes);
@@ -717,7 +725,7 @@ __device__ __forceinline__ void ring_retire(const RingArgs& A, int lane) {
 }
 
 __device__ __forceinline__ void ring_warp_init(unsigned char* smem, RingWarp& rw, int lane, int ring_bytes) {
-    const int wib = threadIdx.x >> 5;
+    const int wib = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler too: the staging addresses stay in uniform registers
     rw.ring = smem_handle(smem + wib * (ring_bytes + J2K_RING_MAXD * 8));
     rw.bars = rw.ring + ring_bytes;
     rw.phase = 0;
@@ -917,7 +925,7 @@ struct InvRing {
         const smem_t dst_s = rw.ring + dst_off;
         // lane 0 stages the band rows of the RPS row pairs of stage pj
         auto issue = [&]() {
-            if (lane == 0) {
+            if (elect_one()) {
                 const smem_t bar = rw.bars + 8 * pslot;
                 const smem_t dst = dst_s + pslot * STAGEB;
                 mbar_expect_tx(bar, RPS * NROWS * copy_bytes);
