@@ -614,6 +614,9 @@ int build_ring_fwd(const Spec& s, Plan& P, const std::vector<long long>& tab) {
     }
     if (!have_first) return 0;
     R.args.nseg = (int)order.size();
+    for (int k = 0; k < R.args.nseg; k++) R.args.seg[k].has_waiters = 0;
+    for (int k = 0; k < R.args.nseg; k++)
+        if (R.args.seg[k].dep_seg >= 0) R.args.seg[R.args.seg[k].dep_seg].has_waiters = 1;
     R.args.total_jobs = jobs;
     R.args.n_ctl = n_ctl;
     R.args.raw = P.raw;
@@ -764,6 +767,9 @@ int build_ring_inv(const Spec& s, Plan& P, const std::vector<long long>& tab) {
     }
     if (!have_first) return 0;
     R.args.nseg = (int)order.size();
+    for (int k = 0; k < R.args.nseg; k++) R.args.seg[k].has_waiters = 0;
+    for (int k = 0; k < R.args.nseg; k++)
+        if (R.args.seg[k].dep_seg >= 0) R.args.seg[R.args.seg[k].dep_seg].has_waiters = 1;
     R.args.total_jobs = jobs;
     R.args.n_ctl = n_ctl;
     R.args.raw = P.raw;
@@ -1227,6 +1233,7 @@ int run_plan(j2k_ctx* ctx, Plan& P, void* pixels, void* coeffs, void* planes, bo
                     B.seg[k - i] = A.seg[k];
                     B.seg[k - i].job_begin -= base; B.seg[k - i].job_end -= base;
                     B.seg[k - i].dep_seg = -1;
+                    B.seg[k - i].has_waiters = 0;
                 }
                 B.total_jobs = A.seg[j - 1].job_end - base;
                 unsigned grid = R.grid;

@@ -55,7 +55,7 @@ struct RingSeg {
     int done_base;                     // index in ctl[] of this segment's per-item completion counters
     int row_bytes;                     // w * bytes per pixel position (multiple of 16)
     int dc;                            // DC level shift applied on load (image-side variant)
-    int pad_;
+    int has_waiters;                   // 1 = some segment's jobs wait on this segment's completion counters
     const unsigned char* x_base;       // interleaved side (forward: source, inverse: destination)
     const long long* x_off;            // per item, elements
     long long x_row_bytes;             // row pitch in bytes (multiple of 16)
@@ -332,26 +332,20 @@ struct FwdRing {
     }
 
     // one staged row of this lane as working values in scalar form (5/3, signed raw words, border lanes)
-    static __device__ __forceinline__ void load_scalar(smem_t row, int lane_off, bool active, const RawFmt& raw, int dc,
-                                                       T (&out)[NC][NS]) {
-        if (active) {
-            unsigned wv[NW];
-            fetch(row + lane_off, wv);
-            int v[NC][NS];
-            words_to_ints(wv, v);
-            finish_ints(v, raw, dc, out);
-        } else {
-#pragma unroll
-            for (int c = 0; c < NC; c++)
-#pragma unroll
-                for (int s = 0; s < NS; s++) out[c][s] = 0;
-        }
+    // (every lane reads its span, also the lanes past the strip's right halo: the slot is theirs, the junk they compute is
+    // never stored and never reaches a storing lane -- no branch in front of the loads, so they hoist freely)
+    static __device__ __forceinline__ void load_scalar(smem_t row, int lane_off, const RawFmt& raw, int dc, T (&out)[NC][NS]) {
+        unsigned wv[NW];
+        fetch(row + lane_off, wv);
+        int v[NC][NS];
+        words_to_ints(wv, v);
+        finish_ints(v, raw, dc, out);
     }
 
     // the same row as column pairs of float32 (9/7): pair j = samples 2j, 2j+1
-    static __device__ __forceinline__ void load_pairs(smem_t row, int lane_off, bool active, const RawFmt& raw, int dc, float fmagic,
+    static __device__ __forceinline__ void load_pairs(smem_t row, int lane_off, const RawFmt& raw, int dc, float fmagic,
                                                       float one, float2 (&out)[NC][NP]) {
-        if (active) {
+        {
             unsigned wv[NW];
             fetch(row + lane_off, wv);
             if constexpr (IN == IN_F32) {
@@ -396,11 +390,6 @@ struct FwdRing {
 #pragma unroll
                     for (int j = 0; j < NP; j++) out[c][j] = make_float2(t[c][2 * j], t[c][2 * j + 1]);
             }
-        } else {
-#pragma unroll
-            for (int c = 0; c < NC; c++)
-#pragma unroll
-                for (int j = 0; j < NP; j++) out[c][j] = make_float2(0.f, 0.f);
         }
     }
 
@@ -426,7 +415,6 @@ struct FwdRing {
         const unsigned copy_bytes = (unsigned)(c1 - c0);
         const int dst_off = c0 - vb;
         const int lane_off = m + lane * LB;
-        const bool active = lane < nl;                              // lanes beyond the right halo lane carry nothing
         const bool fix_l = kxs == 0, fix_r = kxe == S.Kx;           // warp-uniform: this strip touches a window border
         const bool fix = fix_l || fix_r;
         // the window width is a multiple of 2 NP on this path: a lane stores whole vectors or nothing
@@ -453,6 +441,9 @@ struct FwdRing {
         int* p_hh = (int*)S.hh.base + S.hh.off[item] + (long long)S.hh.y_off * S.hh.row_stride + S.hh.x_off + kx0;
         const int rs_ll = S.ll.row_stride, rs_b = S.hl.row_stride;
         const long long cs_ll = S.ll.comp_stride, cs_b = S.hl.comp_stride;
+        // rows of the first storing iteration (low-type row ky0 - py, high-type row ky0); they advance one row per iteration
+        p_ll += (long long)(ky0 - py) * rs_ll; p_hl += (long long)(ky0 - py) * rs_b;
+        p_lh += (long long)ky0 * rs_b; p_hh += (long long)ky0 * rs_b;
 
         // producer cursor (warp-uniform): next stage to fill, its slot and the source pointer of its first row
         int pj = 0, pslot = 0;
@@ -514,8 +505,8 @@ struct FwdRing {
                 const smem_t row_o = row_e + ROWB;
 
                 if (fix) fix_halo(row_e, row_o, lane, fix_l, fix_r, w, vb);
-                load_pairs(row_e, lane_off, active, raw, dc, fmagic, one, out.pe);
-                load_pairs(row_o, lane_off, active, raw, dc, fmagic, one, out.po);
+                load_pairs(row_e, lane_off, raw, dc, fmagic, one, out.pe);
+                load_pairs(row_o, lane_off, raw, dc, fmagic, one, out.po);
                 // vertical lifting on column pairs; the finished (low, high) row values of column s land in Q[c][s]
                 float2 Q[NC][NS];
 #pragma unroll
@@ -597,14 +588,15 @@ struct FwdRing {
                         }
                     }
                     if (row_l) {
-                        store_vec(p_ll + c * cs_ll + (long long)yl * rs_ll, q_ll);
-                        store_vec(p_hl + c * cs_b + (long long)yl * rs_b, q_hl);
+                        store_vec(p_ll + c * cs_ll, q_ll);
+                        store_vec(p_hl + c * cs_b, q_hl);
                     }
                     if (row_h) {
-                        store_vec(p_lh + c * cs_b + (long long)yh * rs_b, q_lh);
-                        store_vec(p_hh + c * cs_b + (long long)yh * rs_b, q_hh);
+                        store_vec(p_lh + c * cs_b, q_lh);
+                        store_vec(p_hh + c * cs_b, q_hh);
                     }
                 }
+                p_ll += rs_ll; p_hl += rs_b; p_lh += rs_b; p_hh += rs_b;
             };
             // two iterations per trip with the window state ping-ponging between sa and sb: no register shuffling
 #pragma unroll 1
@@ -629,8 +621,8 @@ struct FwdRing {
 
                 int e[NC][NS], o[NC][NS], lo[NC][NS], hi[NC][NS];
                 if (fix) fix_halo(row_e, row_o, lane, fix_l, fix_r, w, vb);
-                load_scalar(row_e, lane_off, active, raw, dc, e);
-                load_scalar(row_o, lane_off, active, raw, dc, o);
+                load_scalar(row_e, lane_off, raw, dc, e);
+                load_scalar(row_o, lane_off, raw, dc, o);
 #pragma unroll
                 for (int c = 0; c < NC; c++)
 #pragma unroll
@@ -652,16 +644,17 @@ struct FwdRing {
                     if (row_l) {
 #pragma unroll
                         for (int j = 0; j < NP; j++) { q_a[j] = (int)((unsigned)lo[c][2 * j] << sh_ll); q_b[j] = (int)((unsigned)lo[c][2 * j + 1] << sh_hl); }
-                        store_vec(p_ll + c * cs_ll + (long long)yl * rs_ll, q_a);
-                        store_vec(p_hl + c * cs_b + (long long)yl * rs_b, q_b);
+                        store_vec(p_ll + c * cs_ll, q_a);
+                        store_vec(p_hl + c * cs_b, q_b);
                     }
                     if (row_h) {
 #pragma unroll
                         for (int j = 0; j < NP; j++) { q_a[j] = (int)((unsigned)hi[c][2 * j] << sh_lh); q_b[j] = (int)((unsigned)hi[c][2 * j + 1] << sh_hh); }
-                        store_vec(p_lh + c * cs_b + (long long)yh * rs_b, q_a);
-                        store_vec(p_hh + c * cs_b + (long long)yh * rs_b, q_b);
+                        store_vec(p_lh + c * cs_b, q_a);
+                        store_vec(p_hh + c * cs_b, q_b);
                     }
                 }
+                p_ll += rs_ll; p_hl += rs_b; p_lh += rs_b; p_hh += rs_b;
             }
         }
         (void)lane_s;
@@ -703,8 +696,10 @@ __device__ __forceinline__ void ring_wait_dep(const RingArgs& A, const RingSeg& 
     __syncwarp();
 }
 
-// Release: every lane's stores of this job happen-before the counter increment.
+// Release: every lane's stores of this job happen-before the counter increment.  Segments nobody waits on
+// (has_waiters == 0: the last forward level, the final inverse level) publish nothing.
 __device__ __forceinline__ void ring_signal(const RingArgs& A, const RingSeg& S, int item, int lane) {
+    if (!S.has_waiters) return;
     __syncwarp();
     if (lane == 0) red_release_add(A.ctl + S.done_base + item, 1u);
 }
@@ -901,7 +896,6 @@ struct InvRing {
         const unsigned copy_bytes = (unsigned)(c1 - c0);
         const int dst_off = c0 - vb;
         const int lane_off = m + lane * LB;
-        const bool active = lane < nl;
         const bool fix_l = kxs == 0, fix_r = kxe == S.Kx;
         const bool fix = fix_l || fix_r;
         const bool st = lane >= HLN && kx0 < kxe && kx0 + NP <= bw;
@@ -958,6 +952,9 @@ struct InvRing {
         const long long xpitch = S.x_row_bytes;
         int* planes = (FINAL && S.planes_out) ? S.planes_out + S.planes_off[item] + 2 * kx0 : nullptr;
         const int planes_rs = S.planes_row_stride;
+        // row 2 ky0 - py of the first storing iteration; both advance two rows per iteration
+        xlane += (long long)(2 * ky0 - py) * xpitch;
+        if (planes) planes += (long long)(2 * ky0 - py) * planes_rs;
         const int x_mode = S.x_mode;
 
         int cslot = 0;
@@ -973,6 +970,7 @@ struct InvRing {
         if constexpr (WT == 97) {
             const float2 sclE = S.rcpE, sclO = S.rcpO;
             const bool raw_ll = S.ll.mode == DQ_RAW, raw_hl = S.hl.mode == DQ_RAW, raw_lh = S.lh_.mode == DQ_RAW, raw_hh = S.hh.mode == DQ_RAW;
+            const bool std_modes = raw_ll && !raw_hl && !raw_lh && !raw_hh;
             const float2 nD = splat2(-J2K_DELTA), nG = splat2(-J2K_GAMMA), nB = splat2(-J2K_BETA), nA = splat2(-J2K_ALPHA);
             struct VState { float2 dp[NC][NP], s1p[NC][NP], d1p[NC][NP], s2p[NC][NP]; };
             VState sa, sb;
@@ -991,27 +989,34 @@ struct InvRing {
                     // dequantize: S[j] = (LL, LH)[j], Dd[j] = (HL, HH)[j] as (low-type row, high-type row) pairs
                     float2 Sx[NP + 1], Dx[NP + 1];  // Dx[0] = previous lane's last high, Sx[NP] = next lane's first low
                     int q0[NP], q1[NP], q2[NP], q3[NP];
-                    if (active) {
-                        fetch(stage + (4 * c + 0) * ROWB + lane_off, q0);
-                        fetch(stage + (4 * c + 1) * ROWB + lane_off, q1);
-                        fetch(stage + (4 * c + 2) * ROWB + lane_off, q2);
-                        fetch(stage + (4 * c + 3) * ROWB + lane_off, q3);
+                    fetch(stage + (4 * c + 0) * ROWB + lane_off, q0);  // every lane, also past the strip (see FwdRing::load_scalar)
+                    fetch(stage + (4 * c + 1) * ROWB + lane_off, q1);
+                    fetch(stage + (4 * c + 2) * ROWB + lane_off, q2);
+                    fetch(stage + (4 * c + 3) * ROWB + lane_off, q3);
+                    // float32(q) * float32(scale) (t2/tile_decoder.go:970-987); DQ_CVT is scale == 1 (exact); then the
+                    // horizontal synthesis scaling: low * K, high * two_invK (dwt97.go:207-212)
+                    if (std_modes) {  // every level but the coarsest: LL is the float32 plane of the level below
+#pragma unroll
+                        for (int j = 0; j < NP; j++) {
+                            const float2 fs = make_float2(0.f, (float)q2[j]), fd = make_float2((float)q1[j], (float)q3[j]);
+                            float2 vs = mul2(fs, sclE);
+                            const float2 vd = mul2(fd, sclO);
+                            vs.x = __int_as_float(q0[j]);
+                            Sx[j] = mul2(vs, splat2(J2K_K));
+                            Dx[j + 1] = mul2(vd, splat2(J2K_TWOINVK));
+                        }
                     } else {
 #pragma unroll
-                        for (int j = 0; j < NP; j++) { q0[j] = q1[j] = q2[j] = q3[j] = 0; }
-                    }
-#pragma unroll
-                    for (int j = 0; j < NP; j++) {
-                        // float32(q) * float32(scale) (t2/tile_decoder.go:970-987); DQ_CVT is scale == 1 (exact)
-                        const float2 fs = make_float2((float)q0[j], (float)q2[j]), fd = make_float2((float)q1[j], (float)q3[j]);
-                        float2 vs = mul2(fs, sclE), vd = mul2(fd, sclO);
-                        if (raw_ll) vs.x = __int_as_float(q0[j]);
-                        if (raw_lh) vs.y = __int_as_float(q2[j]);
-                        if (raw_hl) vd.x = __int_as_float(q1[j]);
-                        if (raw_hh) vd.y = __int_as_float(q3[j]);
-                        // horizontal synthesis scaling: low * K, high * two_invK (dwt97.go:207-212)
-                        Sx[j] = mul2(vs, splat2(J2K_K));
-                        Dx[j + 1] = mul2(vd, splat2(J2K_TWOINVK));
+                        for (int j = 0; j < NP; j++) {
+                            const float2 fs = make_float2((float)q0[j], (float)q2[j]), fd = make_float2((float)q1[j], (float)q3[j]);
+                            float2 vs = mul2(fs, sclE), vd = mul2(fd, sclO);
+                            if (raw_ll) vs.x = __int_as_float(q0[j]);
+                            if (raw_lh) vs.y = __int_as_float(q2[j]);
+                            if (raw_hl) vd.x = __int_as_float(q1[j]);
+                            if (raw_hh) vd.y = __int_as_float(q3[j]);
+                            Sx[j] = mul2(vs, splat2(J2K_K));
+                            Dx[j + 1] = mul2(vd, splat2(J2K_TWOINVK));
+                        }
                     }
                     float2 Tq[NP];
                     Dx[0] = shfl_up2(Dx[NP]);
@@ -1056,9 +1061,14 @@ struct InvRing {
                         out.dp[c][j] = dv; out.s1p[c][j] = s1; out.d1p[c][j] = d1; out.s2p[c][j] = s2;
                     }
                 }
-                if (it < 2 * LAG || !st) return;
+                if (it < 2 * LAG) return;
                 const int ky = ky0 + it - 2 * LAG;
                 const int re = 2 * ky - py, ro = re + 1;
+                unsigned char* const xrow = xlane;
+                int* const prow = planes;
+                xlane += 2 * xpitch;
+                if (planes) planes += 2 * planes_rs;
+                if (!st) return;
                 if constexpr (FINAL) {
                     int iv[NC][NS];
                     if (re >= 0 && re < h) {
@@ -1066,14 +1076,14 @@ struct InvRing {
                         for (int c = 0; c < NC; c++)
 #pragma unroll
                             for (int j = 0; j < NP; j++) { iv[c][2 * j] = __float2int_rn(xe[c][j].x); iv[c][2 * j + 1] = __float2int_rn(xe[c][j].y); }
-                        store_final(S, raw, xlane + re * xpitch, planes ? planes + (long long)re * planes_rs : nullptr, iv);
+                        store_final(S, raw, xrow, prow, iv);
                     }
                     if (ro < h) {
 #pragma unroll
                         for (int c = 0; c < NC; c++)
 #pragma unroll
                             for (int j = 0; j < NP; j++) { iv[c][2 * j] = __float2int_rn(xo[c][j].x); iv[c][2 * j + 1] = __float2int_rn(xo[c][j].y); }
-                        store_final(S, raw, xlane + ro * xpitch, planes ? planes + (long long)ro * planes_rs : nullptr, iv);
+                        store_final(S, raw, xrow + xpitch, prow ? prow + planes_rs : nullptr, iv);
                     }
                 } else {
                     int q[NS];
@@ -1083,7 +1093,7 @@ struct InvRing {
                             q[2 * j] = x_mode == 1 ? __float2int_rn(xe[0][j].x) : __float_as_int(xe[0][j].x);
                             q[2 * j + 1] = x_mode == 1 ? __float2int_rn(xe[0][j].y) : __float_as_int(xe[0][j].y);
                         }
-                        store_planar((int*)(xlane + re * xpitch), q);
+                        store_planar((int*)xrow, q);
                     }
                     if (ro < h) {
 #pragma unroll
@@ -1091,7 +1101,7 @@ struct InvRing {
                             q[2 * j] = x_mode == 1 ? __float2int_rn(xo[0][j].x) : __float_as_int(xo[0][j].x);
                             q[2 * j + 1] = x_mode == 1 ? __float2int_rn(xo[0][j].y) : __float_as_int(xo[0][j].y);
                         }
-                        store_planar((int*)(xlane + ro * xpitch), q);
+                        store_planar((int*)(xrow + xpitch), q);
                     }
                 }
             };
@@ -1120,15 +1130,10 @@ struct InvRing {
 #pragma unroll
                 for (int c = 0; c < NC; c++) {
                     int q0[NP], q1[NP], q2[NP], q3[NP];
-                    if (active) {
-                        fetch(stage + (4 * c + 0) * ROWB + lane_off, q0);
-                        fetch(stage + (4 * c + 1) * ROWB + lane_off, q1);
-                        fetch(stage + (4 * c + 2) * ROWB + lane_off, q2);
-                        fetch(stage + (4 * c + 3) * ROWB + lane_off, q3);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < NP; j++) { q0[j] = q1[j] = q2[j] = q3[j] = 0; }
-                    }
+                    fetch(stage + (4 * c + 0) * ROWB + lane_off, q0);  // every lane, also past the strip (see FwdRing::load_scalar)
+                    fetch(stage + (4 * c + 1) * ROWB + lane_off, q1);
+                    fetch(stage + (4 * c + 2) * ROWB + lane_off, q2);
+                    fetch(stage + (4 * c + 3) * ROWB + lane_off, q3);
                     // t2/tile_decoder.go:989-993: truncating /2 of the classic T1 output
 #pragma unroll
                     for (int j = 0; j < NP; j++) {
@@ -1175,15 +1180,20 @@ struct InvRing {
                         dp[c][s] = o[s]; s1p[c][s] = sv;
                     }
                 }
-                if (it < 2 * LAG || !st) continue;
+                if (it < 2 * LAG) continue;
                 const int ky = ky0 + it - 2 * LAG;
                 const int re = 2 * ky - py, ro = re + 1;
+                unsigned char* const xrow = xlane;
+                int* const prow = planes;
+                xlane += 2 * xpitch;
+                if (planes) planes += 2 * planes_rs;
+                if (!st) continue;
                 if constexpr (FINAL) {
-                    if (re >= 0 && re < h) store_final(S, raw, xlane + re * xpitch, planes ? planes + (long long)re * planes_rs : nullptr, xe);
-                    if (ro < h) store_final(S, raw, xlane + ro * xpitch, planes ? planes + (long long)ro * planes_rs : nullptr, xo);
+                    if (re >= 0 && re < h) store_final(S, raw, xrow, prow, xe);
+                    if (ro < h) store_final(S, raw, xrow + xpitch, prow ? prow + planes_rs : nullptr, xo);
                 } else {
-                    if (re >= 0 && re < h) store_planar((int*)(xlane + re * xpitch), xe[0]);
-                    if (ro < h) store_planar((int*)(xlane + ro * xpitch), xo[0]);
+                    if (re >= 0 && re < h) store_planar((int*)xrow, xe[0]);
+                    if (ro < h) store_planar((int*)(xrow + xpitch), xo[0]);
                 }
             }
         }
