@@ -95,7 +95,8 @@ __device__ __forceinline__ void mbar_wait(smem_t, unsigned) {}
 __device__ __forceinline__ void bulk_g2s(smem_t dst, const void* src, unsigned bytes, smem_t) { memcpy(dst, src, bytes); }
 __device__ __forceinline__ void fence_proxy_async() {}
 __device__ __forceinline__ unsigned ld_relaxed(const unsigned* p) { return *p; }
-__device__ __forceinline__ void fence_acquire() {}
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) { return *p; }
+__device__ __forceinline__ void fence_proxy_async_global() {}
 __device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) { *p += v; }
 __device__ __forceinline__ void backoff() {}
 __device__ __forceinline__ bool elect_one() { return emu::lane_id() == 0; }
@@ -143,7 +144,14 @@ __device__ __forceinline__ unsigned ld_relaxed(const unsigned* p) {
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void fence_acquire() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// generic-proxy accesses before, async-proxy (bulk copy) accesses of global memory after.  SASS: FENCE.VIEW.ASYNC.G alone;
+// the state-space-less form adds a MEMBAR.ALL.GPU.
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -688,10 +696,13 @@ __device__ __forceinline__ void ring_wait_dep(const RingArgs& A, const RingSeg& 
     if (lane == 0) {
         const int mul = S.dep_mul > 1 ? S.dep_mul : 1;
         const unsigned* d = A.ctl + A.seg[S.dep_seg].done_base + (item / S.dep_div) * mul;
-        for (int k = 0; k < mul; k++)
-            while (ld_relaxed(d + k) < (unsigned)S.dep_target) backoff();  // relaxed polling: no L1 invalidation per probe
-        fence_acquire();
-        fence_proxy_async();  // the staged reads that follow go through the async proxy
+        // relaxed polling (no L1 invalidation per probe), then one acquire load per counter: it synchronizes with the
+        // producers' release increments without the two MEMBAR.ALL.GPU + ERRBAR a fence.acq_rel.gpu + fence.proxy.async cost
+        for (int k = 0; k < mul; k++) {
+            while (ld_relaxed(d + k) < (unsigned)S.dep_target) backoff();
+            (void)ld_acquire(d + k);
+        }
+        fence_proxy_async_global();  // the staged reads that follow go through the async proxy
     }
     __syncwarp();
 }
