@@ -228,6 +228,41 @@ __device__ __forceinline__ float2 shfl_up2(float2 v) {
     return make_float2(__shfl_up_sync(0xffffffffu, v.x, 1), __shfl_up_sync(0xffffffffu, v.y, 1));
 }
 
+// ------------------------------------------------------------------ packed 16-bit clamp / pack (inverse, final level)
+//
+// +DC, clamp, two's-complement wrap and packing of GetPixelData (decoder.go:777-944) on two samples per instruction:
+// saturate both to int16 (the clamp range lies inside it), clamp to [lo - dc, hi - dc], add dc modulo 2^16, keep the
+// low B bits (the un-sign-extended word of a negative signed sample).  SASS: I2IP.S16.S32.SAT, VIMNMX.S16x2, VIADD.16x2.
+struct RawPack { unsigned lo2, hi2, dc2, mask2; };
+__device__ __forceinline__ RawPack make_raw_pack(const RawFmt& r) {
+    RawPack p;
+    p.lo2 = ((unsigned)(r.clamp_lo - r.dc) & 0xFFFFu) * 0x10001u;
+    p.hi2 = ((unsigned)(r.clamp_hi - r.dc) & 0xFFFFu) * 0x10001u;
+    p.dc2 = ((unsigned)r.dc & 0xFFFFu) * 0x10001u;
+    p.mask2 = ((unsigned)(r.clamp_hi - r.clamp_lo) & 0xFFFFu) * 0x10001u;  // 2^B - 1 in both halves
+    return p;
+}
+#ifdef J2K_EMU
+__device__ __forceinline__ unsigned pack_clamp2(int a, int b, const RawPack& p) {
+    auto one = [&](int v, int sh) {
+        v = v < -32768 ? -32768 : (v > 32767 ? 32767 : v);
+        const int lo = (short)(p.lo2 >> sh), hi = (short)(p.hi2 >> sh);
+        v = v < lo ? lo : (v > hi ? hi : v);
+        return (((unsigned)v + (p.dc2 >> sh)) & (p.mask2 >> sh)) & 0xFFFFu;
+    };
+    return one(a, 0) | (one(b, 16) << 16);
+}
+#else
+__device__ __forceinline__ unsigned pack_clamp2(int a, int b, const RawPack& p) {  // a -> low half, b -> high half
+    unsigned w;
+    asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(w) : "r"(b), "r"(a));
+    w = __vmaxs2(w, p.lo2);
+    w = __vmins2(w, p.hi2);
+    w = __vadd2(w, p.dc2);
+    return w & p.mask2;
+}
+#endif
+
 // ------------------------------------------------------------------ forward job
 
 template <int WT, int NP, int NC, int IN, int MCT, int SG>
@@ -829,7 +864,8 @@ struct InvRing {
     }
 
     // final stage of level 1: inverse MCT -> (+DC, optional planes) -> clamp -> pack -> one vector store per row
-    static __device__ __forceinline__ void store_final(const RingSeg& S, const RawFmt& raw, unsigned char* xrow, int* prow, int (&iv)[NC][NS]) {
+    static __device__ __forceinline__ void store_final(const RingSeg& S, const RawFmt& raw, const RawPack& rp, unsigned char* xrow, int* prow,
+                                                       int (&iv)[NC][NS]) {
         if constexpr (NC == 3 && MCT != MCTK_NONE) {
 #pragma unroll
             for (int s = 0; s < NS; s++) {
@@ -850,23 +886,20 @@ struct InvRing {
                 }
             }
         }
-#pragma unroll
-        for (int c = 0; c < NC; c++)
-#pragma unroll
-            for (int s = 0; s < NS; s++) iv[c][s] = int_to_raw(iv[c][s], raw);
         constexpr int ES = (OUT == IN_U8) ? 1 : 2;
         constexpr int NWO = NS * NC * ES / 4;  // 32-bit words per lane per row
         unsigned wv[NWO];
+        // element e of the lane's interleaved span is component e % NC of sample e / NC
 #pragma unroll
-        for (int k = 0; k < NWO; k++) wv[k] = 0;
-#pragma unroll
-        for (int s = 0; s < NS; s++)
-#pragma unroll
-            for (int c = 0; c < NC; c++) {
-                const int e = NC * s + c;
-                if constexpr (OUT == IN_U8) wv[e >> 2] |= (unsigned)iv[c][s] << (8 * (e & 3));
-                else wv[e >> 1] |= (unsigned)iv[c][s] << (16 * (e & 1));
+        for (int k = 0; k < NWO; k++) {
+            if constexpr (OUT == IN_U8) {
+                const unsigned t0 = pack_clamp2(iv[(4 * k) % NC][(4 * k) / NC], iv[(4 * k + 1) % NC][(4 * k + 1) / NC], rp);
+                const unsigned t1 = pack_clamp2(iv[(4 * k + 2) % NC][(4 * k + 2) / NC], iv[(4 * k + 3) % NC][(4 * k + 3) / NC], rp);
+                wv[k] = __byte_perm(t0, t1, 0x6420);
+            } else {
+                wv[k] = pack_clamp2(iv[(2 * k) % NC][(2 * k) / NC], iv[(2 * k + 1) % NC][(2 * k + 1) / NC], rp);
             }
+        }
         if constexpr (NWO % 4 == 0) {
 #pragma unroll
             for (int k = 0; k < NWO / 4; k++) *((uint4*)xrow + k) = make_uint4(wv[4 * k], wv[4 * k + 1], wv[(4 * k + 2) % NWO], wv[(4 * k + 3) % NWO]);
@@ -928,28 +961,50 @@ struct InvRing {
         const int n_st = (n_it + RPS - 1) / RPS;
         int pj = 0, pslot = 0;
         const smem_t dst_s = rw.ring + dst_off;
-        // lane 0 stages the band rows of the RPS row pairs of stage pj
+        // stages s_lo <= s < s_hi hold only in-range row pairs t (0 <= 2t - py, 2t + 1 - py < h): their band rows are
+        // yl = t - py, yh = t, reached with running pointers; the others mirror the interleaved row numbers
+        const int t_min = (py + 1) >> 1, t_max = (h - 2 + py) >> 1;  // first / last pair with both rows inside the window
+        const int s_lo = t_begin < t_min ? (t_min - t_begin + RPS - 1) / RPS : 0;
+        const int s_hi = t_max >= t_begin ? (t_max - t_begin + 1) / RPS : 0;
+        const unsigned char* q_ll = b_ll + (long long)(t_begin - py) * rp_ll;  // band rows of pair t_begin
+        const unsigned char* q_hl = b_hl + (long long)(t_begin - py) * rp_b;
+        const unsigned char* q_lh = b_lh + (long long)t_begin * rp_b;
+        const unsigned char* q_hh = b_hh + (long long)t_begin * rp_b;
+        // one elected lane stages the band rows of the RPS row pairs of stage pj
         auto issue = [&]() {
             if (elect_one()) {
                 const smem_t bar = rw.bars + 8 * pslot;
                 const smem_t dst = dst_s + pslot * STAGEB;
                 mbar_expect_tx(bar, RPS * NROWS * copy_bytes);
+                if (pj >= s_lo && pj < s_hi) {
 #pragma unroll
-                for (int k = 0; k < RPS; k++) {
-                    // band rows of the pair: low-type interleaved row 2t - py -> yl, high-type row 2t + 1 - py -> yh (mirrored)
-                    const int t = t_begin + RPS * pj + k;
-                    const int pl = mirror_fast(2 * t - py, h), ph = mirror_fast(2 * t + 1 - py, h);
-                    const int yl = (pl - py) >> 1, yh = (ph - (1 - py)) >> 1;
+                    for (int k = 0; k < RPS; k++)
 #pragma unroll
-                    for (int c = 0; c < NC; c++) {
-                        bulk_g2s(dst + k * PAIRB + (4 * c + 0) * ROWB, b_ll + c * cp_ll + yl * rp_ll, copy_bytes, bar);
-                        bulk_g2s(dst + k * PAIRB + (4 * c + 1) * ROWB, b_hl + c * cp_b + yl * rp_b, copy_bytes, bar);
-                        bulk_g2s(dst + k * PAIRB + (4 * c + 2) * ROWB, b_lh + c * cp_b + yh * rp_b, copy_bytes, bar);
-                        bulk_g2s(dst + k * PAIRB + (4 * c + 3) * ROWB, b_hh + c * cp_b + yh * rp_b, copy_bytes, bar);
+                        for (int c = 0; c < NC; c++) {
+                            bulk_g2s(dst + k * PAIRB + (4 * c + 0) * ROWB, q_ll + c * cp_ll + k * rp_ll, copy_bytes, bar);
+                            bulk_g2s(dst + k * PAIRB + (4 * c + 1) * ROWB, q_hl + c * cp_b + k * rp_b, copy_bytes, bar);
+                            bulk_g2s(dst + k * PAIRB + (4 * c + 2) * ROWB, q_lh + c * cp_b + k * rp_b, copy_bytes, bar);
+                            bulk_g2s(dst + k * PAIRB + (4 * c + 3) * ROWB, q_hh + c * cp_b + k * rp_b, copy_bytes, bar);
+                        }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < RPS; k++) {
+                        // band rows of the pair: low-type interleaved row 2t - py -> yl, high-type row 2t + 1 - py -> yh (mirrored)
+                        const int t = t_begin + RPS * pj + k;
+                        const int pl = mirror_fast(2 * t - py, h), ph = mirror_fast(2 * t + 1 - py, h);
+                        const int yl = (pl - py) >> 1, yh = (ph - (1 - py)) >> 1;
+#pragma unroll
+                        for (int c = 0; c < NC; c++) {
+                            bulk_g2s(dst + k * PAIRB + (4 * c + 0) * ROWB, b_ll + c * cp_ll + yl * rp_ll, copy_bytes, bar);
+                            bulk_g2s(dst + k * PAIRB + (4 * c + 1) * ROWB, b_hl + c * cp_b + yl * rp_b, copy_bytes, bar);
+                            bulk_g2s(dst + k * PAIRB + (4 * c + 2) * ROWB, b_lh + c * cp_b + yh * rp_b, copy_bytes, bar);
+                            bulk_g2s(dst + k * PAIRB + (4 * c + 3) * ROWB, b_hh + c * cp_b + yh * rp_b, copy_bytes, bar);
+                        }
                     }
                 }
             }
             pj++;
+            q_ll += RPS * rp_ll; q_hl += RPS * rp_b; q_lh += RPS * rp_b; q_hh += RPS * rp_b;
             pslot = (pslot + 1 == D) ? 0 : pslot + 1;
         };
         __syncwarp();
@@ -963,6 +1018,7 @@ struct InvRing {
         const long long xpitch = S.x_row_bytes;
         int* planes = (FINAL && S.planes_out) ? S.planes_out + S.planes_off[item] + 2 * kx0 : nullptr;
         const int planes_rs = S.planes_row_stride;
+        const RawPack rp = make_raw_pack(raw);
         // row 2 ky0 - py of the first storing iteration; both advance two rows per iteration
         xlane += (long long)(2 * ky0 - py) * xpitch;
         if (planes) planes += (long long)(2 * ky0 - py) * planes_rs;
@@ -1087,14 +1143,14 @@ struct InvRing {
                         for (int c = 0; c < NC; c++)
 #pragma unroll
                             for (int j = 0; j < NP; j++) { iv[c][2 * j] = __float2int_rn(xe[c][j].x); iv[c][2 * j + 1] = __float2int_rn(xe[c][j].y); }
-                        store_final(S, raw, xrow, prow, iv);
+                        store_final(S, raw, rp, xrow, prow, iv);
                     }
                     if (ro < h) {
 #pragma unroll
                         for (int c = 0; c < NC; c++)
 #pragma unroll
                             for (int j = 0; j < NP; j++) { iv[c][2 * j] = __float2int_rn(xo[c][j].x); iv[c][2 * j + 1] = __float2int_rn(xo[c][j].y); }
-                        store_final(S, raw, xrow + xpitch, prow ? prow + planes_rs : nullptr, iv);
+                        store_final(S, raw, rp, xrow + xpitch, prow ? prow + planes_rs : nullptr, iv);
                     }
                 } else {
                     int q[NS];
@@ -1200,8 +1256,8 @@ struct InvRing {
                 if (planes) planes += 2 * planes_rs;
                 if (!st) continue;
                 if constexpr (FINAL) {
-                    if (re >= 0 && re < h) store_final(S, raw, xrow, prow, xe);
-                    if (ro < h) store_final(S, raw, xrow + xpitch, prow ? prow + planes_rs : nullptr, xo);
+                    if (re >= 0 && re < h) store_final(S, raw, rp, xrow, prow, xe);
+                    if (ro < h) store_final(S, raw, rp, xrow + xpitch, prow ? prow + planes_rs : nullptr, xo);
                 } else {
                     if (re >= 0 && re < h) store_planar((int*)xrow, xe[0]);
                     if (ro < h) store_planar((int*)(xrow + xpitch), xo[0]);
