@@ -133,6 +133,28 @@ class ClockSampler:
                 "source": self.source}
 
 
+def bind_to_gpu_numa(gpu_index):
+    """Pin this rank to the CPUs NVML reports as local to its GPU before any pinned host memory is allocated (first-touch
+    puts the staging buffers on that NUMA node): the end-to-end leg is a PCIe / host-memory stream."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        idx = gpu_index
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            idx = int(vis.split(",")[gpu_index])
+        h = nv.nvmlDeviceGetHandleByIndex(idx)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = nv.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None
+
+
 def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
@@ -234,6 +256,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    bind_to_gpu_numa(local_rank)
     warm = max(args.warmup, 3)
     ctx = j2kb200.Context(devices=[local_rank])
     enc, _ = j2kb200.openjpeg_quant_params(LEVELS, BITS)
