@@ -11,6 +11,7 @@ OpenJPEG default steps; each rank owns `--frames` frames (weak scaling, frames n
 no collective on the data path).  Prints ONE JSON line on rank 0.
 """
 import argparse
+import ctypes as C
 import json
 import os
 import statistics
@@ -390,6 +391,42 @@ def main():
                    "step_frac_of_hbm_peak": step_alg / (ims * 1e-3) / 1e9 / peak,
                    "what": "coefficients -> dequantize -> 6-level inverse 9/7 -> round -> +DC -> clamp -> pack u16 (D4-D13), resident"}
 
+    # ---- code-block interface, device-resident: plane -> block-major + numbps, and back
+    blocks_leg = None
+    if not args.no_inverse:
+        cbw = cbh = 64
+        nblk = ctx.lib.j2k_fwd_block_count(C.byref(fp), cbw, cbh)
+        d_blk = torch.empty((B, PIX), dtype=torch.int32, device="cuda")
+        d_nb = torch.empty((B, nblk), dtype=torch.int32, device="cuda")
+        ipb = abi.inv_params(W, H, 1, BITS, False, num_levels=LEVELS, reversible=False, steps=j2kb200.decode_quant_steps(enc, LEVELS, BITS, False))
+
+        def timed(fn):
+            for _ in range(warm):
+                fn()
+            barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(streams[0])
+            for _ in range(args.steps):
+                fn()
+            a1.record(streams[0])
+            barrier()
+            t = torch.tensor([a0.elapsed_time(a1)], device="cuda")
+            if use_dist:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item()) / args.steps
+
+        g_ms = timed(lambda: ctx.gather_blocks_device(fp, B, d_outs[0].data_ptr(), d_blk.data_ptr(), d_nb.data_ptr(), cbw, cbh,
+                                                      stream=streams[0].cuda_stream))
+        s_ms = timed(lambda: ctx.scatter_blocks_device(ipb, B, d_blk.data_ptr(), d_outs[1 % NS].data_ptr(), cbw, cbh,
+                                                       stream=streams[0].cuda_stream))
+        ok = bool(torch.equal(d_outs[0], d_outs[1 % NS])) if NS > 1 else None
+        blocks_leg = {"code_block": [cbw, cbh], "blocks_per_frame": int(nblk),
+                      "gather_ms": g_ms, "gather_frac_of_hbm_peak": B * PIX * 8 / (g_ms * 1e-3) / 1e9 / peak,
+                      "scatter_ms": s_ms, "scatter_frac_of_hbm_peak": B * PIX * 8 / (s_ms * 1e-3) / 1e9 / peak,
+                      "scatter_of_gather_is_identity": ok,
+                      "what": "gather: sub-band extraction + code-block partition + numbps (encoder.go:3059-3285,3349-3362); "
+                              "scatter: assembleSubbands (t2/tile_decoder.go:840-883); 8 B/sample each, resident"}
+
     # ---- end to end through the C ABI with host buffers (pinned), copies inside the timed region.
     # Headline form: the ticketed calls the codec adapter's frame loop uses -- step i+1 is submitted
     # before step i is waited for, so its upload runs under step i's download; every step still moves its own input
@@ -444,7 +481,7 @@ def main():
                        "cache": "inputs larger than L2 (%.0f MB in + %.0f MB out per step per GPU)" % (B * frame_bytes / 1e6, B * PIX * 4 / 1e6),
                        "parallelism": "frame-sharded, %d rank(s), no collective" % world,
                        "streams": NS},
-            "roofline": roofline, "inverse": inverse, "cpu_baseline": cpu,
+            "roofline": roofline, "inverse": inverse, "code_blocks": blocks_leg, "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": "Mpixel/s", "h2d_bytes_per_step": B * frame_bytes, "d2h_bytes_per_step": B * PIX * 4,
                     "steps": e2e_steps, "matches_resident": same, "sync_value": e2e_sync,
                     "api": "j2k_submit_forward / j2k_wait, two steps in flight (sync_value: blocking j2k_forward_batch)"},

@@ -195,7 +195,9 @@ struct DeviceCtx {
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     bool ev_k_used[2] = {false, false}, ev_out_used[2] = {false, false};
     DevBuf in[2], out[2], planes[2], api[8];
+    DevBuf blk[2], nbp[2];  // code-block interface: block-major planes and per-block numbps of a sub-batch
     std::map<std::string, std::unique_ptr<Plan>> plans;
+    std::map<std::string, std::unique_ptr<struct BlockTable>> block_tables;
 };
 
 struct Plan {
@@ -1375,6 +1377,122 @@ int spec_from_inv(const j2k_inv_params* p, bool want_planes, Spec& s) {
     return 0;
 }
 
+// ------------------------------------------------------------------ code-block interface
+
+// Blocks of one tile-component plane in the order buildTilePacketEncoder walks them (encoder.go:2424-2431):
+// resolutions 0..L, sub-bands of getSubbandsForResolution (:3059-3197, origin-0 ceiling divisions), blocks of
+// partitionIntoCodeBlocks (:3215-3285) row-major over (cby, cbx).
+void codeblock_layout(int width, int height, int L, int cbw, int cbh, std::vector<j2k_cblk>& out) {
+    auto cdp2 = [](int a, int b) { return (a + (1 << b) - 1) >> b; };
+    long long off = 0;
+    auto band = [&](int bx0, int by0, int bw, int bh, int bandno, int res) {
+        if (bw <= 0 || bh <= 0) return;
+        const int ncbx = (bw + cbw - 1) / cbw, ncby = (bh + cbh - 1) / cbh;
+        for (int cby = 0; cby < ncby; cby++)
+            for (int cbx = 0; cbx < ncbx; cbx++) {
+                const int x0 = cbx * cbw, y0 = cby * cbh;
+                const int aw = (x0 + cbw > bw ? bw : x0 + cbw) - x0, ah = (y0 + cbh > bh ? bh : y0 + cbh) - y0;
+                out.push_back(j2k_cblk{bx0 + x0, by0 + y0, aw, ah, cbx, cby, bandno, res, off});
+                off += (long long)aw * ah;
+            }
+    };
+    const int div = 1 << L;
+    band(0, 0, (width + div - 1) / div, (height + div - 1) / div, 0, 0);
+    for (int res = 1; res <= L; res++) {
+        const int level = L - res;
+        const int llw = cdp2(width, level + 1), llh = cdp2(height, level + 1);
+        band(llw, 0, cdp2(width - (1 << level), level + 1), cdp2(height, level + 1), 1, res);
+        band(0, llh, cdp2(width, level + 1), cdp2(height - (1 << level), level + 1), 2, res);
+        band(llw, llh, cdp2(width - (1 << level), level + 1), cdp2(height - (1 << level), level + 1), 3, res);
+    }
+}
+
+int validate_cb(int cbw, int cbh) {  // EncodeParams.Validate, encoder.go:310-316
+    auto pow2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
+    if (cbw < 4 || cbw > 1024 || !pow2(cbw)) return fail(J2K_ERR_INVALID_ARG, "invalid code-block width: %d (must be power of 2, 4-1024)", cbw);
+    if (cbh < 4 || cbh > 1024 || !pow2(cbh)) return fail(J2K_ERR_INVALID_ARG, "invalid code-block height: %d (must be power of 2, 4-1024)", cbh);
+    return 0;
+}
+
+struct BlockTable {
+    DevBuf tab;
+    int nblocks = 0;                 // per frame
+    long long coeffs_per_frame = 0;
+    ~BlockTable() { tab.release(); }
+};
+
+size_t frame_block_count(const std::vector<TileGeom>& tiles, int C, int L, int cbw, int cbh) {
+    size_t n = 0;
+    std::vector<j2k_cblk> t;
+    for (const TileGeom& g : tiles) {
+        t.clear();
+        codeblock_layout(g.tw, g.th, L, cbw, cbh, t);
+        n += t.size() * (size_t)C;
+    }
+    return n;
+}
+
+// Flat per-frame table: every block of every tile-component, with its position in the coefficient planes.
+int get_block_table(DeviceCtx& d, const Spec& s, int cbw, int cbh, long long coeffs_per_frame, BlockTable** out) {
+    std::string key;
+    char buf[96];
+    snprintf(buf, sizeof buf, "%d|%d|%d|%d|%lld|", s.C, s.L, cbw, cbh, coeffs_per_frame);
+    key = buf;
+    for (const TileGeom& g : s.tiles) { snprintf(buf, sizeof buf, "%d,%d,%lld;", g.tw, g.th, g.coeff_off); key += buf; }
+    auto it = d.block_tables.find(key);
+    if (it != d.block_tables.end()) { *out = it->second.get(); return 0; }
+    if (d.block_tables.size() >= 16) d.block_tables.clear();
+    std::vector<BlockEntry> host;
+    std::vector<j2k_cblk> t;
+    for (const TileGeom& g : s.tiles) {
+        t.clear();
+        codeblock_layout(g.tw, g.th, s.L, cbw, cbh, t);
+        for (int c = 0; c < s.C; c++) {
+            const long long plane = g.coeff_off + (long long)c * g.tw * g.th;
+            for (const j2k_cblk& b : t) {
+                BlockEntry e;
+                e.plane_off = plane + (long long)b.y0 * g.tw + b.x0;
+                e.block_off = plane + b.offset;
+                e.stride = g.tw; e.w = b.width; e.h = b.height;
+                e.vec = (b.width % 4 == 0 && g.tw % 4 == 0 && e.plane_off % 4 == 0 && e.block_off % 4 == 0 && coeffs_per_frame % 4 == 0) ? 1 : 0;
+                host.push_back(e);
+            }
+        }
+    }
+    std::unique_ptr<BlockTable> T(new BlockTable());
+    T->nblocks = (int)host.size();
+    T->coeffs_per_frame = coeffs_per_frame;
+    int rc = T->tab.ensure(host.size() * sizeof(BlockEntry) + 16);
+    if (rc) return rc;
+    if (!host.empty()) CK(cudaMemcpy(T->tab.p, host.data(), host.size() * sizeof(BlockEntry), cudaMemcpyHostToDevice));
+    *out = T.get();
+    d.block_tables[key] = std::move(T);
+    return 0;
+}
+
+int launch_gather(j2k_ctx* ctx, BlockTable& T, int nframes, const int32_t* d_coeffs, int32_t* d_blocks, int32_t* d_numbps, bool sub6,
+                  cudaStream_t st) {
+    const long long total = (long long)T.nblocks * nframes;
+    if (total <= 0) return 0;
+    const unsigned grid = (unsigned)((total + 3) / 4);
+    J2K_LAUNCH(gather_blocks_kernel, grid, 128, st, (const int*)d_coeffs, T.coeffs_per_frame, (const BlockEntry*)T.tab.p, T.nblocks, total,
+               (int*)d_blocks, (int*)d_numbps, sub6 ? 1 : 0);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+}
+
+int launch_scatter(j2k_ctx* ctx, BlockTable& T, int nframes, const int32_t* d_blocks, int32_t* d_coeffs, cudaStream_t st) {
+    const long long total = (long long)T.nblocks * nframes;
+    if (total <= 0) return 0;
+    const unsigned grid = (unsigned)((total + 3) / 4);
+    J2K_LAUNCH(scatter_blocks_kernel, grid, 128, st, (const int*)d_blocks, T.coeffs_per_frame, (const BlockEntry*)T.tab.p, T.nblocks, total,
+               (int*)d_coeffs);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+}
+
 // A plan owns its scratch (LL ping-pong planes, job-control block): plans are cached per stream so that launches the
 // caller enqueues on different streams may overlap (the tail of one batch under the head of the next).
 int get_plan(DeviceCtx& d, const Spec& s, const void* pblob, size_t pbytes, int nframes, long long frame_samples, Plan** out,
@@ -1410,6 +1528,8 @@ struct HostJob {
     const int32_t* h_coef_in; int32_t* h_coef_out;
     int32_t* h_planes;
     size_t pix_bytes_per_frame; long long coeffs_per_frame;
+    int cb_w = 0, cb_h = 0;      // > 0: coefficients cross the boundary block-major (code-block interface)
+    int32_t* h_numbps = nullptr; // forward, block mode: cblkNumbps per block
 };
 
 int enqueue_host_job(j2k_ctx* ctx, int di, const HostJob& J, int f0, int f1, bool timing) {
@@ -1437,6 +1557,12 @@ int enqueue_host_job(j2k_ctx* ctx, int di, const HostJob& J, int f0, int f1, boo
         if ((rc = d.in[slot].ensure(in_bytes))) return rc;
         if ((rc = d.out[slot].ensure(out_bytes))) return rc;
         if (J.h_planes && (rc = d.planes[slot].ensure((size_t)nb * s.C * HW * 4))) return rc;
+        BlockTable* BT = nullptr;
+        if (J.cb_w > 0) {
+            if ((rc = get_block_table(d, s, J.cb_w, J.cb_h, J.coeffs_per_frame, &BT))) return rc;
+            if ((rc = d.blk[slot].ensure((size_t)nb * J.coeffs_per_frame * 4))) return rc;
+            if (J.fwd && (rc = d.nbp[slot].ensure((size_t)nb * BT->nblocks * 4 + 16))) return rc;
+        }
         // the slot's previous kernel must have consumed `in`, its previous D2H must have drained `out`
         if (d.ev_k_used[slot]) CK(cudaStreamWaitEvent(d.s_h2d, d.ev_k[slot], 0));
         if (J.fwd) {
@@ -1448,7 +1574,7 @@ int enqueue_host_job(j2k_ctx* ctx, int di, const HostJob& J, int f0, int f1, boo
                                      J.pix_bytes_per_frame, nb, cudaMemcpyHostToDevice, d.s_h2d));
             }
         } else {
-            CK(cudaMemcpyAsync(d.in[slot].p, J.h_coef_in + (size_t)b * J.coeffs_per_frame, in_bytes, cudaMemcpyHostToDevice, d.s_h2d));
+            CK(cudaMemcpyAsync(BT ? d.blk[slot].p : d.in[slot].p, J.h_coef_in + (size_t)b * J.coeffs_per_frame, in_bytes, cudaMemcpyHostToDevice, d.s_h2d));
         }
         CK(cudaEventRecord(d.ev_in[slot], d.s_h2d));
         CK(cudaStreamWaitEvent(d.s_main, d.ev_in[slot], 0));
@@ -1457,14 +1583,19 @@ int enqueue_host_job(j2k_ctx* ctx, int di, const HostJob& J, int f0, int f1, boo
         long long fs = J.fwd ? (J.planar ? 0 : (long long)(J.pix_bytes_per_frame / (s.bit_depth <= 8 ? 1 : 2))) : (long long)(J.pix_bytes_per_frame / (s.bit_depth <= 8 ? 1 : 2));
         if ((rc = get_plan(d, s, J.pblob, J.pbytes, nb, fs, &P))) return rc;
         if (timing && it == 0) CK(cudaEventRecord(d.ev_t[1], d.s_main));
+        if (!J.fwd && BT && (rc = launch_scatter(ctx, *BT, nb, (const int32_t*)d.blk[slot].p, (int32_t*)d.in[slot].p, d.s_main))) return rc;
         if (J.fwd) rc = run_plan(ctx, *P, d.in[slot].p, d.out[slot].p, nullptr, J.planar, d.s_main);
         else rc = run_plan(ctx, *P, d.out[slot].p, d.in[slot].p, J.h_planes ? d.planes[slot].p : nullptr, false, d.s_main);
         if (rc < 0) return rc;
+        if (J.fwd && BT && (rc = launch_gather(ctx, *BT, nb, (const int32_t*)d.out[slot].p, (int32_t*)d.blk[slot].p, (int32_t*)d.nbp[slot].p,
+                                               !s.htj2k, d.s_main))) return rc;
         CK(cudaEventRecord(d.ev_k[slot], d.s_main));
         d.ev_k_used[slot] = true;
         CK(cudaStreamWaitEvent(d.s_d2h, d.ev_k[slot], 0));
         if (J.fwd) {
-            CK(cudaMemcpyAsync(J.h_coef_out + (size_t)b * J.coeffs_per_frame, d.out[slot].p, out_bytes, cudaMemcpyDeviceToHost, d.s_d2h));
+            CK(cudaMemcpyAsync(J.h_coef_out + (size_t)b * J.coeffs_per_frame, BT ? d.blk[slot].p : d.out[slot].p, out_bytes, cudaMemcpyDeviceToHost, d.s_d2h));
+            if (BT && J.h_numbps)
+                CK(cudaMemcpyAsync(J.h_numbps + (size_t)b * BT->nblocks, d.nbp[slot].p, (size_t)nb * BT->nblocks * 4, cudaMemcpyDeviceToHost, d.s_d2h));
         } else {
             if (J.frame_stride_bytes == J.pix_bytes_per_frame)
                 CK(cudaMemcpyAsync(J.h_pix_out + (size_t)b * J.frame_stride_bytes, d.out[slot].p, out_bytes, cudaMemcpyDeviceToHost, d.s_d2h));
@@ -1587,6 +1718,9 @@ void j2k_shutdown(j2k_ctx* ctx) {
         for (auto& b : d.in) b.release();
         for (auto& b : d.out) b.release();
         for (auto& b : d.planes) b.release();
+        for (auto& b : d.blk) b.release();
+        for (auto& b : d.nbp) b.release();
+        d.block_tables.clear();
         for (auto& b : d.api) b.release();
         for (auto& ev : d.ev_t) if (ev) cudaEventDestroy(ev);
         for (int k = 0; k < 2; k++) { cudaEventDestroy(d.ev_in[k]); cudaEventDestroy(d.ev_k[k]); cudaEventDestroy(d.ev_out[k]); }
@@ -1779,6 +1913,112 @@ int j2k_inverse_device(j2k_ctx* ctx, int dev, const j2k_inv_params* p, int nfram
     if ((rc = get_plan(d, s, p, sizeof *p, nframes, (long long)(frame_stride_bytes / bps), &P, cuda_stream))) return rc;
     rc = run_plan(ctx, *P, d_pixels, (void*)d_coeffs, d_planes, false, cuda_stream ? (cudaStream_t)cuda_stream : d.s_main);
     return rc < 0 ? rc : J2K_OK;
+}
+
+// ---- code-block interface
+
+int j2k_codeblock_layout(int width, int height, int num_levels, int cb_width, int cb_height, j2k_cblk* out, int max_blocks) {
+    if (width <= 0 || height <= 0 || num_levels < 0 || num_levels > J2K_MAX_LEVELS) return fail(J2K_ERR_INVALID_ARG, "invalid plane geometry");
+    int rc = validate_cb(cb_width, cb_height);
+    if (rc) return rc;
+    std::vector<j2k_cblk> t;
+    codeblock_layout(width, height, num_levels, cb_width, cb_height, t);
+    if (out)
+        for (size_t i = 0; i < t.size() && (int)i < max_blocks; i++) out[i] = t[i];
+    return (int)t.size();
+}
+
+size_t j2k_fwd_block_count(const j2k_fwd_params* p, int cb_width, int cb_height) {
+    if (!p || validate_cb(cb_width, cb_height)) return 0;
+    std::vector<TileGeom> tiles;
+    fwd_tiles(p, &tiles);
+    return frame_block_count(tiles, p->components, p->num_levels, cb_width, cb_height);
+}
+
+size_t j2k_inv_block_count(const j2k_inv_params* p, int cb_width, int cb_height) {
+    if (!p || validate_cb(cb_width, cb_height)) return 0;
+    std::vector<TileGeom> tiles;
+    inv_tiles(p, &tiles);
+    return frame_block_count(tiles, p->components, p->num_levels, cb_width, cb_height);
+}
+
+// In block mode the coefficients leave exactly as encodeCodeBlock hands them to T1 (encoder.go:3294-3300): the << 6 of
+// the classic lossless path is applied once, inside the forward kernel (the quantizer stage does it for free).
+static j2k_fwd_params block_mode_params(const j2k_fwd_params* p) {
+    j2k_fwd_params q = *p;
+    q.fuse_t1_shift = (q.reversible && !q.htj2k) ? 1 : 0;
+    return q;
+}
+
+int j2k_forward_blocks(j2k_ctx* ctx, const j2k_fwd_params* p, int cb_width, int cb_height, int nframes, const void* pixels,
+                       size_t frame_stride_bytes, int32_t* blocks_out, int32_t* numbps_out) {
+    if (!ctx) return fail(J2K_ERR_INVALID_ARG, "context is NULL");
+    if (!p) return fail(J2K_ERR_INVALID_ARG, "params is NULL");
+    int rc = validate_cb(cb_width, cb_height);
+    if (rc) return rc;
+    const j2k_fwd_params q = block_mode_params(p);
+    Spec s;
+    if ((rc = spec_from_fwd(&q, false, s))) return rc;
+    if (!pixels || !blocks_out) return fail(J2K_ERR_INVALID_ARG, "NULL buffer");
+    if (nframes <= 0) return fail(J2K_ERR_INVALID_ARG, "nframes must be positive");
+    HostJob J{};
+    J.fwd = true; J.planar = false; J.spec = &s; J.pblob = &q; J.pbytes = sizeof q;
+    J.h_pix_in = (const unsigned char*)pixels; J.h_coef_out = blocks_out; J.h_numbps = numbps_out;
+    J.pix_bytes_per_frame = j2k_fwd_pixel_bytes(&q); J.coeffs_per_frame = (long long)j2k_fwd_coeff_count(&q);
+    J.frame_stride_bytes = frame_stride_bytes; J.cb_w = cb_width; J.cb_h = cb_height;
+    if (frame_stride_bytes < J.pix_bytes_per_frame) return fail(J2K_ERR_SIZE, "frame stride %zu smaller than a frame (%zu bytes)", frame_stride_bytes, J.pix_bytes_per_frame);
+    return run_host_batch(ctx, J, nframes, true, nullptr);
+}
+
+int j2k_inverse_blocks(j2k_ctx* ctx, const j2k_inv_params* p, int cb_width, int cb_height, int nframes, const int32_t* blocks_in,
+                       void* pixels_out, size_t frame_stride_bytes, int32_t* planes_out) {
+    if (!ctx) return fail(J2K_ERR_INVALID_ARG, "context is NULL");
+    if (!p) return fail(J2K_ERR_INVALID_ARG, "params is NULL");
+    int rc = validate_cb(cb_width, cb_height);
+    if (rc) return rc;
+    Spec s;
+    if ((rc = spec_from_inv(p, planes_out != nullptr, s))) return rc;
+    if (!blocks_in || !pixels_out) return fail(J2K_ERR_INVALID_ARG, "NULL buffer");
+    if (nframes <= 0) return fail(J2K_ERR_INVALID_ARG, "nframes must be positive");
+    HostJob J{};
+    J.fwd = false; J.planar = false; J.spec = &s; J.pblob = p; J.pbytes = sizeof *p;
+    J.h_coef_in = blocks_in; J.h_pix_out = (unsigned char*)pixels_out; J.h_planes = planes_out;
+    J.pix_bytes_per_frame = j2k_inv_pixel_bytes(p); J.coeffs_per_frame = (long long)j2k_inv_coeff_count(p);
+    J.frame_stride_bytes = frame_stride_bytes; J.cb_w = cb_width; J.cb_h = cb_height;
+    if (frame_stride_bytes < J.pix_bytes_per_frame) return fail(J2K_ERR_SIZE, "frame stride smaller than a frame");
+    return run_host_batch(ctx, J, nframes, true, nullptr);
+}
+
+int j2k_gather_blocks_device(j2k_ctx* ctx, int dev, const j2k_fwd_params* p, int cb_width, int cb_height, int nframes,
+                             const int32_t* d_coeffs, int32_t* d_blocks, int32_t* d_numbps, void* cuda_stream) {
+    int rc = set_dev(ctx, dev);
+    if (rc) return rc;
+    if (!p) return fail(J2K_ERR_INVALID_ARG, "params is NULL");
+    if ((rc = validate_cb(cb_width, cb_height))) return rc;
+    Spec s;
+    if ((rc = spec_from_fwd(p, false, s))) return rc;
+    if (!d_coeffs || !d_blocks || nframes <= 0) return fail(J2K_ERR_INVALID_ARG, "bad device buffers / nframes");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceCtx& d = ctx->devs[dev];
+    BlockTable* BT = nullptr;
+    if ((rc = get_block_table(d, s, cb_width, cb_height, (long long)j2k_fwd_coeff_count(p), &BT))) return rc;
+    return launch_gather(ctx, *BT, nframes, d_coeffs, d_blocks, d_numbps, !s.htj2k, cuda_stream ? (cudaStream_t)cuda_stream : d.s_main);
+}
+
+int j2k_scatter_blocks_device(j2k_ctx* ctx, int dev, const j2k_inv_params* p, int cb_width, int cb_height, int nframes,
+                              const int32_t* d_blocks, int32_t* d_coeffs, void* cuda_stream) {
+    int rc = set_dev(ctx, dev);
+    if (rc) return rc;
+    if (!p) return fail(J2K_ERR_INVALID_ARG, "params is NULL");
+    if ((rc = validate_cb(cb_width, cb_height))) return rc;
+    Spec s;
+    if ((rc = spec_from_inv(p, false, s))) return rc;
+    if (!d_coeffs || !d_blocks || nframes <= 0) return fail(J2K_ERR_INVALID_ARG, "bad device buffers / nframes");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceCtx& d = ctx->devs[dev];
+    BlockTable* BT = nullptr;
+    if ((rc = get_block_table(d, s, cb_width, cb_height, (long long)j2k_inv_coeff_count(p), &BT))) return rc;
+    return launch_scatter(ctx, *BT, nframes, d_blocks, d_coeffs, cuda_stream ? (cudaStream_t)cuda_stream : d.s_main);
 }
 
 // ---- asynchronous

@@ -262,4 +262,93 @@ __global__ void __launch_bounds__(256) f32_to_i32_kernel(const float* in, int* o
     out[i] = r;
 }
 
+// ---- code-block interface: plane (Mallat layout) <-> block-major plane
+//
+// gather = getSubbandsForResolution + partitionIntoCodeBlocks + codeBlockNumBps (jpeg2000/encoder.go:3059-3285,
+// 3349-3362, 3643-3667) in one pass: ONE WARP per code-block copies its rows (128-bit vectors when the block is
+// 4-aligned) into the contiguous block and reduces max |v| with shuffles; lane 0 writes cblkNumbps.  scatter =
+// TileDecoder.assembleSubbands (jpeg2000/t2/tile_decoder.go:840-883).  Both move 8 B per sample: HBM-bound.
+struct BlockEntry {
+    long long plane_off;   // first sample of the block inside the frame's coefficient planes (samples)
+    long long block_off;   // first sample of the block inside the frame's block-major planes
+    int stride, w, h, vec; // plane row stride (= tile width); vec: w % 4 == 0 and both sides 16-byte aligned in every frame
+};
+
+__device__ __forceinline__ int go_abs_max(int m, int v) {  // calculateMaxBitplane: abs wraps for INT_MIN, compare is signed
+    const int a = v < 0 ? (int)(0u - (unsigned)v) : v;
+    return a > m ? a : m;
+}
+
+__global__ void __launch_bounds__(128) gather_blocks_kernel(const int* __restrict__ coeffs, long long coeffs_per_frame,
+                                                            const BlockEntry* __restrict__ tab, int nblocks, long long total,
+                                                            int* __restrict__ blocks, int* __restrict__ numbps, int sub6) {
+    const int lane = threadIdx.x & 31;
+    const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (wid >= total) return;
+    const long long frame = wid / nblocks;
+    const int b = (int)(wid - frame * nblocks);
+    const BlockEntry e = tab[b];
+    const int* src = coeffs + frame * coeffs_per_frame + e.plane_off;
+    int* dst = blocks + frame * coeffs_per_frame + e.block_off;
+    int m = 0;
+    if (e.vec) {
+        const int w4 = e.w >> 2, n4 = w4 * e.h;
+#pragma unroll 4
+        for (int i = lane; i < n4; i += 32) {
+            const int y = i / w4, x = i - y * w4;
+            const int4 v = *(const int4*)(src + (long long)y * e.stride + 4 * x);
+            m = go_abs_max(go_abs_max(go_abs_max(go_abs_max(m, v.x), v.y), v.z), v.w);
+            *(int4*)(dst + 4 * i) = v;
+        }
+    } else {
+        const int n = e.w * e.h;
+        for (int i = lane; i < n; i += 32) {
+            const int y = i / e.w, x = i - y * e.w;
+            const int v = src[(long long)y * e.stride + x];
+            m = go_abs_max(m, v);
+            dst[i] = v;
+        }
+    }
+    if (numbps) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const int o = __shfl_xor_sync(0xffffffffu, m, d);
+            m = o > m ? o : m;
+        }
+        if (lane == 0) {
+            int bits = 0;  // rawMaxBitplane + 1
+            for (unsigned t = (unsigned)m; t; t >>= 1) bits++;
+            int v = m == 0 ? 0 : bits - (sub6 ? 6 : 0);  // codeBlockNumBps: minus t1NMSEDecFracBits unless HTJ2K
+            numbps[frame * nblocks + b] = v < 0 ? 0 : v;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) scatter_blocks_kernel(const int* __restrict__ blocks, long long coeffs_per_frame,
+                                                             const BlockEntry* __restrict__ tab, int nblocks, long long total,
+                                                             int* __restrict__ coeffs) {
+    const int lane = threadIdx.x & 31;
+    const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (wid >= total) return;
+    const long long frame = wid / nblocks;
+    const int b = (int)(wid - frame * nblocks);
+    const BlockEntry e = tab[b];
+    const int* src = blocks + frame * coeffs_per_frame + e.block_off;
+    int* dst = coeffs + frame * coeffs_per_frame + e.plane_off;
+    if (e.vec) {
+        const int w4 = e.w >> 2, n4 = w4 * e.h;
+#pragma unroll 4
+        for (int i = lane; i < n4; i += 32) {
+            const int y = i / w4, x = i - y * w4;
+            *(int4*)(dst + (long long)y * e.stride + 4 * x) = *(const int4*)(src + 4 * i);
+        }
+    } else {
+        const int n = e.w * e.h;
+        for (int i = lane; i < n; i += 32) {
+            const int y = i / e.w, x = i - y * e.w;
+            dst[(long long)y * e.stride + x] = src[i];
+        }
+    }
+}
+
 }  // namespace j2k

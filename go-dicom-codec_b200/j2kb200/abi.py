@@ -75,6 +75,15 @@ class InvParams(C.Structure):
     ]
 
 
+class Cblk(C.Structure):
+    """j2k_cblk: one code-block of a tile-component plane (codeBlockInfo, jpeg2000/encoder.go:3199-3212)."""
+    _fields_ = [
+        ("x0", C.c_int32), ("y0", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
+        ("cbx", C.c_int32), ("cby", C.c_int32), ("band", C.c_int32), ("res", C.c_int32),
+        ("offset", C.c_int64),
+    ]
+
+
 class Timing(C.Structure):
     _fields_ = [
         ("h2d_ms", C.c_float), ("kernel_ms", C.c_float), ("d2h_ms", C.c_float), ("total_ms", C.c_float),
@@ -173,6 +182,8 @@ EXPORTED_SYMBOLS = [
     "j2k_forward", "j2k_forward_planar", "j2k_forward_batch", "j2k_forward_device",
     "j2k_inverse", "j2k_inverse_batch", "j2k_inverse_device",
     "j2k_submit_forward", "j2k_submit_inverse", "j2k_wait",
+    "j2k_codeblock_layout", "j2k_fwd_block_count", "j2k_inv_block_count", "j2k_forward_blocks", "j2k_inverse_blocks",
+    "j2k_gather_blocks_device", "j2k_scatter_blocks_device",
     "j2k_dwt53_forward", "j2k_dwt53_inverse", "j2k_dwt97_forward", "j2k_dwt97_inverse", "j2k_convert_f32_to_i32",
     "j2k_rct_forward", "j2k_rct_inverse", "j2k_ict_forward", "j2k_ict_inverse",
     "j2k_quantize_coefficients", "j2k_dequantize_coefficients",
@@ -227,6 +238,13 @@ def load(path: str | None = None) -> C.CDLL:
         "j2k_submit_forward": (C.c_int64, [vp, FP, ci, vp, sz, vp]),
         "j2k_submit_inverse": (C.c_int64, [vp, IP, ci, vp, vp, sz, vp]),
         "j2k_wait": (ci, [vp, C.c_int64]),
+        "j2k_codeblock_layout": (ci, [ci, ci, ci, ci, ci, C.POINTER(Cblk), ci]),
+        "j2k_fwd_block_count": (sz, [FP, ci, ci]),
+        "j2k_inv_block_count": (sz, [IP, ci, ci]),
+        "j2k_forward_blocks": (ci, [vp, FP, ci, ci, ci, vp, sz, vp, vp]),
+        "j2k_inverse_blocks": (ci, [vp, IP, ci, ci, ci, vp, vp, sz, vp]),
+        "j2k_gather_blocks_device": (ci, [vp, ci, FP, ci, ci, ci, vp, vp, vp, vp]),
+        "j2k_scatter_blocks_device": (ci, [vp, ci, IP, ci, ci, ci, vp, vp, vp]),
         "j2k_dwt53_forward": (ci, [vp, vp, ci, ci, ci, ci, ci]),
         "j2k_dwt53_inverse": (ci, [vp, vp, ci, ci, ci, ci, ci]),
         "j2k_dwt97_forward": (ci, [vp, vp, ci, ci, ci, ci, ci]),

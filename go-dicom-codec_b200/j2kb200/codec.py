@@ -149,6 +149,44 @@ class Context:
                                              frame_stride_bytes, C.c_void_p(d_planes) if d_planes else None, C.c_void_p(stream)))
 
     # ---- wavelet package API
+    # ---- code-block interface
+    def codeblock_layout(self, width, height, num_levels, cb_width=64, cb_height=64):
+        """Blocks of one tile-component plane in the reference's order (encoder.go:2424-2431,3059-3285)."""
+        n = self._ck(self.lib.j2k_codeblock_layout(width, height, num_levels, cb_width, cb_height, None, 0))
+        arr = (abi.Cblk * max(n, 1))()
+        self._ck(self.lib.j2k_codeblock_layout(width, height, num_levels, cb_width, cb_height, arr, n))
+        return [arr[i] for i in range(n)]
+
+    def forward_blocks(self, p: abi.FwdParams, frames: np.ndarray, cb_width=64, cb_height=64):
+        """frames: [nframes, frame_bytes] uint8 -> (block-major coefficients [nframes, coeff_count], numbps [nframes, nblocks])."""
+        assert frames.ndim == 2 and frames.dtype == np.uint8 and frames.strides[1] == 1
+        n = frames.shape[0]
+        out = np.empty((n, self.lib.j2k_fwd_coeff_count(C.byref(p))), np.int32)
+        nb = np.empty((n, self.lib.j2k_fwd_block_count(C.byref(p), cb_width, cb_height)), np.int32)
+        self._ck(self.lib.j2k_forward_blocks(self.h, C.byref(p), cb_width, cb_height, n, _vp(frames), frames.strides[0], _vp(out), _vp(nb)))
+        return out, nb
+
+    def inverse_blocks(self, p: abi.InvParams, blocks: np.ndarray, cb_width=64, cb_height=64, want_planes: bool = False):
+        assert blocks.ndim == 2 and blocks.dtype == np.int32 and blocks.flags.c_contiguous
+        n = blocks.shape[0]
+        nbytes = self.lib.j2k_inv_pixel_bytes(C.byref(p))
+        out = np.empty((n, nbytes), np.uint8)
+        w, h = p.xsiz - p.xosiz, p.ysiz - p.yosiz
+        planes = np.empty((n, p.components, h, w), np.int32) if want_planes else None
+        self._ck(self.lib.j2k_inverse_blocks(self.h, C.byref(p), cb_width, cb_height, n, _vp(blocks), _vp(out), nbytes,
+                                             _vp(planes) if want_planes else None))
+        return (out, planes) if want_planes else out
+
+    def gather_blocks_device(self, p: abi.FwdParams, nframes, d_coeffs: int, d_blocks: int, d_numbps: int, cb_width=64, cb_height=64,
+                             stream: int = 0, dev: int = 0):
+        self._ck(self.lib.j2k_gather_blocks_device(self.h, dev, C.byref(p), cb_width, cb_height, nframes, C.c_void_p(d_coeffs),
+                                                   C.c_void_p(d_blocks), C.c_void_p(d_numbps), C.c_void_p(stream)))
+
+    def scatter_blocks_device(self, p: abi.InvParams, nframes, d_blocks: int, d_coeffs: int, cb_width=64, cb_height=64,
+                              stream: int = 0, dev: int = 0):
+        self._ck(self.lib.j2k_scatter_blocks_device(self.h, dev, C.byref(p), cb_width, cb_height, nframes, C.c_void_p(d_blocks),
+                                                    C.c_void_p(d_coeffs), C.c_void_p(stream)))
+
     def _dwt(self, fn, data, levels, x0, y0, dtype):
         a = np.ascontiguousarray(data, dtype=dtype).copy()
         h, w = a.shape

@@ -242,6 +242,52 @@ int64_t j2k_submit_inverse(j2k_ctx* ctx, const j2k_inv_params* p, int nframes, c
                            void* pixels_out, size_t frame_stride_bytes, int32_t* planes_out);
 int j2k_wait(j2k_ctx* ctx, int64_t ticket);
 
+/* ------------------------------------------- code-block interface */
+
+/* One code-block of a tile-component plane, as Encoder.partitionIntoCodeBlocks
+ * (jpeg2000/encoder.go:3215-3285) produces it from the sub-bands of
+ * getSubbandsForResolution (:3059-3197), in the reference's order: resolution 0 (LL),
+ * then per resolution HL, LH, HH; inside a sub-band row-major over (cby, cbx). */
+typedef struct j2k_cblk {
+    int32_t x0, y0;          /* codeBlockInfo.globalX0/globalY0: position in the tile-component plane */
+    int32_t width, height;   /* actual size (clipped at the sub-band edge)                        */
+    int32_t cbx, cby;        /* index inside the sub-band                                          */
+    int32_t band, res;       /* 0 = LL, 1 = HL, 2 = LH, 3 = HH; resolution level                   */
+    int64_t offset;          /* first sample of the block in the block-major plane (samples)       */
+} j2k_cblk;
+
+/* Block table of one tile-component plane of width x height samples; returns the number of
+ * blocks (also with out == NULL).  The block-major plane has width*height samples, like the
+ * Mallat plane it permutes.  Pure host arithmetic. */
+int j2k_codeblock_layout(int width, int height, int num_levels, int cb_width, int cb_height,
+                         j2k_cblk* out, int max_blocks);
+/* Blocks per frame: all tiles (raster order), all components. */
+size_t j2k_fwd_block_count(const j2k_fwd_params* p, int cb_width, int cb_height);
+size_t j2k_inv_block_count(const j2k_inv_params* p, int cb_width, int cb_height);
+
+/* j2k_forward_batch followed, on the device, by what buildTilePacketEncoder does before T1
+ * (jpeg2000/encoder.go:2424-2431): sub-band extraction + partitionIntoCodeBlocks, the T1
+ * scaling of encodeCodeBlock (:3294-3300: << 6 for classic lossless) and codeBlockNumBps
+ * (:3349-3362 with calculateMaxBitplane :3643-3667).  `blocks_out`: per frame, per tile, per
+ * component the block-major plane (each block contiguous, row-major); `numbps_out`: one
+ * int32 per block in the same order (cblkNumbps).  ROI scaling stays in Go behind this call. */
+int j2k_forward_blocks(j2k_ctx* ctx, const j2k_fwd_params* p, int cb_width, int cb_height, int nframes,
+                       const void* pixels, size_t frame_stride_bytes, int32_t* blocks_out, int32_t* numbps_out);
+
+/* Decode mirror: `blocks_in` holds the T1 output of every code-block (after the Go side's
+ * inverse ROI scaling), block-major as above; the device performs TileDecoder.assembleSubbands
+ * (jpeg2000/t2/tile_decoder.go:840-883) and then everything j2k_inverse_batch does.  The
+ * classic 5/3 "/2" (tile_decoder.go:989-993) is applied when p->fuse_t1_halve is set. */
+int j2k_inverse_blocks(j2k_ctx* ctx, const j2k_inv_params* p, int cb_width, int cb_height, int nframes,
+                       const int32_t* blocks_in, void* pixels_out, size_t frame_stride_bytes, int32_t* planes_out);
+
+/* Device-resident halves of the two calls above (plane <-> block-major), for pipelines that
+ * keep coefficients on the device; enqueued on `cuda_stream`, not synchronised. */
+int j2k_gather_blocks_device(j2k_ctx* ctx, int dev, const j2k_fwd_params* p, int cb_width, int cb_height, int nframes,
+                             const int32_t* d_coeffs, int32_t* d_blocks, int32_t* d_numbps, void* cuda_stream);
+int j2k_scatter_blocks_device(j2k_ctx* ctx, int dev, const j2k_inv_params* p, int cb_width, int cb_height, int nframes,
+                              const int32_t* d_blocks, int32_t* d_coeffs, void* cuda_stream);
+
 /* -------------------------------------------- wavelet package API (in place) */
 
 /* wavelet.ForwardMultilevelWithParity / InverseMultilevelWithParity

@@ -1270,6 +1270,136 @@ ORC_API int orc_inverse_batch(const j2k_inv_params* p, int nframes, const int32_
     return run_batch(&j, threads);
 }
 
+/* ------------------------------------------------------------------ code-block interface
+ * jpeg2000/encoder.go:3059-3197 (getSubbandsForResolution), :3215-3285 (partitionIntoCodeBlocks),
+ * :3294-3300 (T1 scaling), :3349-3362 + :3643-3667 (codeBlockNumBps / calculateMaxBitplane),
+ * consumed in buildTilePacketEncoder :2424-2431 (res 0..L, sub-bands in order, blocks in order). */
+
+typedef struct { int32_t* data; int x0, y0, width, height, band, res; } orc_subband;
+
+static int orc_ceildivpow2(int a, int b) { return (a + (1 << b) - 1) >> b; }
+
+/* getSubbandsForResolution: returns the number of sub-bands (1 or 3), each with a freshly extracted copy */
+static int get_subbands_for_resolution(const int32_t* data, size_t len, int width, int height, int num_levels, int resolution,
+                                       orc_subband sb[3]) {
+    if (resolution == 0) {
+        int divisor = 1 << num_levels;
+        int llw = (width + divisor - 1) / divisor, llh = (height + divisor - 1) / divisor;
+        int32_t* d = (int32_t*)calloc((size_t)llw * llh + 1, sizeof(int32_t));
+        for (int y = 0; y < llh; y++)
+            for (int x = 0; x < llw; x++) {
+                size_t src = (size_t)y * width + x;
+                if (src < len && y < height && x < width) d[(size_t)y * llw + x] = data[src];
+            }
+        sb[0] = (orc_subband){d, 0, 0, llw, llh, 0, 0};
+        return 1;
+    }
+    int level = num_levels - resolution;
+    if (level < 0) level = 0;
+    int llw = orc_ceildivpow2(width - (0 << level), level + 1), llh = orc_ceildivpow2(height - (0 << level), level + 1);
+    for (int b = 1; b <= 3; b++) {
+        int x0b = b & 1, y0b = b >> 1;
+        int bw = orc_ceildivpow2(width - (x0b << level), level + 1), bh = orc_ceildivpow2(height - (y0b << level), level + 1);
+        int ox = x0b ? llw : 0, oy = y0b ? llh : 0;
+        int32_t* d = (int32_t*)calloc((size_t)(bw > 0 ? bw : 0) * (bh > 0 ? bh : 0) + 1, sizeof(int32_t));
+        for (int y = 0; y < bh; y++)
+            for (int x = 0; x < bw; x++) {
+                size_t src = (size_t)(oy + y) * width + (ox + x);
+                if (src < len && oy + y < height && ox + x < width) d[(size_t)y * bw + x] = data[src];
+            }
+        sb[b - 1] = (orc_subband){d, ox, oy, bw, bh, b, resolution};
+    }
+    return 3;
+}
+
+/* calculateMaxBitplane :3643-3667 */
+static int calculate_max_bitplane(const int32_t* data, size_t n) {
+    int32_t max_abs = 0;
+    for (size_t i = 0; i < n; i++) {
+        int32_t a = data[i];
+        if (a < 0) a = (int32_t)(0u - (uint32_t)a);
+        if (a > max_abs) max_abs = a;
+    }
+    if (max_abs == 0) return -1;
+    int bitplane = 0;
+    while (max_abs > 0) { max_abs >>= 1; bitplane++; }
+    return bitplane - 1;
+}
+
+/* Walks one tile-component plane the way buildTilePacketEncoder does.  table / blocks / numbps may be NULL.
+ * Returns the number of code-blocks. */
+static int walk_code_blocks(const int32_t* plane, int width, int height, int num_levels, int cbw, int cbh, int shift6, int htj2k,
+                            j2k_cblk* table, int max_blocks, int32_t* blocks, int32_t* numbps) {
+    int n = 0;
+    int64_t off = 0;
+    size_t len = (size_t)width * height;
+    for (int res = 0; res <= num_levels; res++) {
+        orc_subband sb[3];
+        int nsb;
+        if (plane) nsb = get_subbands_for_resolution(plane, len, width, height, num_levels, res, sb);
+        else { /* geometry only: same formulas, no data */
+            int32_t* zero = (int32_t*)calloc(len + 1, sizeof(int32_t));
+            nsb = get_subbands_for_resolution(zero, len, width, height, num_levels, res, sb);
+            free(zero);
+        }
+        for (int s = 0; s < nsb; s++) {
+            const orc_subband* b = &sb[s];
+            int ncbx = b->width > 0 ? (b->width + cbw - 1) / cbw : 0, ncby = b->height > 0 ? (b->height + cbh - 1) / cbh : 0;
+            for (int cby = 0; cby < ncby; cby++)
+                for (int cbx = 0; cbx < ncbx; cbx++) { /* partitionIntoCodeBlocks :3226-3283 */
+                    int x0 = cbx * cbw, y0 = cby * cbh, x1 = x0 + cbw, y1 = y0 + cbh;
+                    if (x1 > b->width) x1 = b->width;
+                    if (y1 > b->height) y1 = b->height;
+                    int aw = x1 - x0, ah = y1 - y0;
+                    if (table && n < max_blocks)
+                        table[n] = (j2k_cblk){b->x0 + x0, b->y0 + y0, aw, ah, cbx, cby, b->band, b->res, off};
+                    if (blocks) {
+                        int32_t* cb = blocks + off;
+                        for (int y = 0; y < ah; y++)
+                            for (int x = 0; x < aw; x++) cb[(size_t)y * aw + x] = b->data[(size_t)(y0 + y) * b->width + (x0 + x)];
+                        if (shift6) /* encodeCodeBlock :3294-3300 */
+                            for (int i = 0; i < aw * ah; i++) cb[i] = (int32_t)((uint32_t)cb[i] << 6);
+                        if (numbps) { /* codeBlockNumBps :3349-3362 */
+                            int raw = calculate_max_bitplane(cb, (size_t)aw * ah);
+                            int v = raw < 0 ? 0 : raw + 1 - (htj2k ? 0 : 6);
+                            numbps[n] = v < 0 ? 0 : v;
+                        }
+                    }
+                    off += (int64_t)aw * ah;
+                    n++;
+                }
+            free(b->data);
+        }
+    }
+    return n;
+}
+
+ORC_API int orc_codeblock_layout(int width, int height, int num_levels, int cbw, int cbh, j2k_cblk* out, int max_blocks) {
+    return walk_code_blocks(NULL, width, height, num_levels, cbw, cbh, 0, 0, out, max_blocks, NULL, NULL);
+}
+
+/* plane (Mallat layout, stride = width) -> block-major plane + numbps, one tile-component */
+ORC_API int orc_gather_blocks(const int32_t* plane, int width, int height, int num_levels, int cbw, int cbh, int shift6, int htj2k,
+                              int32_t* blocks, int32_t* numbps) {
+    return walk_code_blocks(plane, width, height, num_levels, cbw, cbh, shift6, htj2k, NULL, 0, blocks, numbps);
+}
+
+/* TileDecoder.assembleSubbands (jpeg2000/t2/tile_decoder.go:840-883): block-major plane -> plane */
+ORC_API int orc_scatter_blocks(const int32_t* blocks, int width, int height, int num_levels, int cbw, int cbh, int32_t* plane) {
+    int n = orc_codeblock_layout(width, height, num_levels, cbw, cbh, NULL, 0);
+    j2k_cblk* t = (j2k_cblk*)calloc((size_t)n + 1, sizeof(j2k_cblk));
+    orc_codeblock_layout(width, height, num_levels, cbw, cbh, t, n);
+    memset(plane, 0, (size_t)width * height * sizeof(int32_t));
+    for (int i = 0; i < n; i++)
+        for (int y = 0; y < t[i].height; y++)
+            for (int x = 0; x < t[i].width; x++) {
+                size_t dst = (size_t)(t[i].y0 + y) * width + (t[i].x0 + x);
+                if (dst < (size_t)width * height) plane[dst] = blocks[t[i].offset + (int64_t)y * t[i].width + x];
+            }
+    free(t);
+    return n;
+}
+
 ORC_API int orc_abi_sizes(int* fwd, int* inv, int* binding) {
     *fwd = (int)sizeof(j2k_fwd_params); *inv = (int)sizeof(j2k_inv_params); *binding = (int)sizeof(j2k_mct_binding);
     return J2K_B200_ABI_VERSION;

@@ -109,6 +109,12 @@ template <typename T> static inline T __shfl_up_sync(unsigned, T v, int d) {
     b = emu::shfl_exchange(b, src);
     T r; memcpy(&r, &b, 4); return r;
 }
+template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int d) {
+    static_assert(sizeof(T) == 4, "emu shuffles move 32-bit values");
+    uint32_t b; memcpy(&b, &v, 4);
+    b = emu::shfl_exchange(b, (emu::lane_id() ^ d) & 31);
+    T r; memcpy(&r, &b, 4); return r;
+}
 
 // ---- runtime API subset (everything is synchronous host memory)
 typedef int cudaError_t;

@@ -205,6 +205,29 @@ class Oracle:
         n = self.lib.orc_band_rects(C.c_int(w), C.c_int(h), C.c_int(x0), C.c_int(y0), C.c_int(levels), _p(r))
         return r[:n]
 
+    # ---- code-block interface
+    def codeblock_layout(self, width, height, num_levels, cbw=64, cbh=64):
+        n = self.lib.orc_codeblock_layout(C.c_int(width), C.c_int(height), C.c_int(num_levels), C.c_int(cbw), C.c_int(cbh), None, C.c_int(0))
+        arr = (self.abi.Cblk * max(n, 1))()
+        self.lib.orc_codeblock_layout(C.c_int(width), C.c_int(height), C.c_int(num_levels), C.c_int(cbw), C.c_int(cbh), arr, C.c_int(n))
+        return [arr[i] for i in range(n)]
+
+    def gather_blocks(self, plane, num_levels, cbw=64, cbh=64, shift6=False, htj2k=False):
+        a = np.ascontiguousarray(plane, dtype=np.int32)
+        h, w = a.shape
+        n = self.lib.orc_codeblock_layout(C.c_int(w), C.c_int(h), C.c_int(num_levels), C.c_int(cbw), C.c_int(cbh), None, C.c_int(0))
+        blocks = np.zeros(a.size, np.int32)
+        nb = np.zeros(max(n, 1), np.int32)
+        self.lib.orc_gather_blocks(_p(a), C.c_int(w), C.c_int(h), C.c_int(num_levels), C.c_int(cbw), C.c_int(cbh), C.c_int(int(shift6)),
+                                   C.c_int(int(htj2k)), _p(blocks), _p(nb))
+        return blocks, nb[:n]
+
+    def scatter_blocks(self, blocks, width, height, num_levels, cbw=64, cbh=64):
+        b = np.ascontiguousarray(blocks, dtype=np.int32)
+        plane = np.empty((height, width), np.int32)
+        self.lib.orc_scatter_blocks(_p(b), C.c_int(width), C.c_int(height), C.c_int(num_levels), C.c_int(cbw), C.c_int(cbh), _p(plane))
+        return plane
+
     # ---- pipelines
     def fwd_tile_bounds(self, p, idx):
         b = (C.c_int32 * 4)()

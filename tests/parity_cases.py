@@ -175,3 +175,56 @@ def check_package_api(ctx, oracle, n=100_003, seed=6):
     f = (rng.standard_normal(n) * 1000).astype(np.float32)
     f[:10] = [0.5, 1.5, 2.5, -0.5, -1.5, -2.5, 0.49999997, 2147483648.0, -2147483904.0, np.float32("nan")]
     assert np.array_equal(ctx.convert_f32_to_i32(f), oracle.convert_f32_to_i32(f)), "float32 -> int32 rounding"
+
+
+# ---- code-block interface: block-major coefficients + numbps, and the decode-side scatter
+
+def tile_list(oracle, fp):
+    n, _ = oracle.fwd_tile_bounds(fp, 0)
+    return [oracle.fwd_tile_bounds(fp, i)[1] for i in range(n)]
+
+
+def check_blocks(ctx, oracle, w, h, c, bits, L, reversible, tile=(0, 0), cb=(64, 64), htj2k=False, seed=11, nframes=2):
+    """forward_blocks == oracle planes pushed through the restated getSubbandsForResolution / partitionIntoCodeBlocks /
+    T1 shift / codeBlockNumBps; inverse_blocks == oracle inverse of the scattered planes; layout tables identical."""
+    rng = np.random.default_rng(seed)
+    fp, ip = fwd_inv_params(w, h, c, bits, False, L, reversible, oracle, tile, htj2k)
+    frames = np.stack([raw_bytes(synth(rng, h, w, c, bits, False, "smooth" if f else "noise")) for f in range(nframes)])
+    got_blocks, got_nb = ctx.forward_blocks(fp, frames, cb[0], cb[1])
+    shift6 = reversible and not htj2k
+    for f in range(nframes):
+        planes = oracle.forward(fp, frames[f])
+        want_blocks, want_nb, off = [], [], 0
+        for (x0, y0, x1, y1) in tile_list(oracle, fp):
+            tw, th = x1 - x0, y1 - y0
+            lay_o = oracle.codeblock_layout(tw, th, L, cb[0], cb[1])
+            lay_p = ctx.codeblock_layout(tw, th, L, cb[0], cb[1])
+            assert len(lay_o) == len(lay_p)
+            for a, b in zip(lay_o, lay_p):
+                assert all(getattr(a, k) == getattr(b, k) for k, _ in abi.Cblk._fields_), "code-block table"
+            for comp in range(c):
+                plane = planes[off:off + tw * th].reshape(th, tw)
+                bl, nb = oracle.gather_blocks(plane, L, cb[0], cb[1], shift6, htj2k)
+                want_blocks.append(bl); want_nb.append(nb)
+                off += tw * th
+        want_blocks, want_nb = np.concatenate(want_blocks), np.concatenate(want_nb)
+        assert np.array_equal(got_blocks[f], want_blocks), f"block-major coefficients, frame {f}"
+        assert np.array_equal(got_nb[f], want_nb), f"numbps, frame {f}"
+    # decode side: what T1 hands back per block (classic 5/3: one half bit, halved inside when fuse_t1_halve is set)
+    if reversible:
+        back = (got_blocks >> 6) * 2 if shift6 else got_blocks
+        ip.fuse_t1_halve = 1 if shift6 else 0
+    else:
+        back = np.stack([M.t1_emulate(got_blocks[f], htj2k) for f in range(nframes)])
+    px = ctx.inverse_blocks(ip, np.ascontiguousarray(back, dtype=np.int32), cb[0], cb[1])
+    for f in range(nframes):
+        planes, off = [], 0
+        for (x0, y0, x1, y1) in tile_list(oracle, fp):
+            tw, th = x1 - x0, y1 - y0
+            for comp in range(c):
+                planes.append(oracle.scatter_blocks(back[f][off:off + tw * th], tw, th, L, cb[0], cb[1]).reshape(-1))
+                off += tw * th
+        want_px = oracle.inverse(ip, np.concatenate(planes))
+        assert np.array_equal(px[f], want_px), f"inverse from blocks, frame {f}"
+        if reversible:
+            assert np.array_equal(px[f], frames[f]), "lossless identity through the block interface"

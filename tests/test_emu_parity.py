@@ -86,3 +86,16 @@ def test_planar_entry(ectx, oracle, w, h, c, bits, signed, L, rev):
 
 def test_package_api(ectx, oracle):
     PC.check_package_api(ectx, oracle, n=5003)
+
+
+@pytest.mark.parametrize("w,h,c,bits,L,rev,tile,cb", [
+    (64, 48, 1, 8, 2, True, (0, 0), (16, 16)), (70, 50, 1, 12, 3, False, (0, 0), (16, 8)), (48, 40, 3, 8, 2, True, (32, 32), (8, 8)),
+    (33, 17, 1, 16, 3, True, (0, 0), (4, 4)), (40, 24, 3, 8, 2, False, (0, 0), (64, 64)), (24, 24, 1, 8, 0, True, (0, 0), (8, 8)),
+])
+def test_code_block_interface(ectx, oracle, w, h, c, bits, L, rev, tile, cb):
+    PC.check_blocks(ectx, oracle, w, h, c, bits, L, rev, tile=tile, cb=cb)
+
+
+def test_code_block_interface_htj2k(ectx, oracle):
+    PC.check_blocks(ectx, oracle, 40, 36, 1, 12, 2, True, cb=(16, 16), htj2k=True)
+    PC.check_blocks(ectx, oracle, 40, 36, 1, 12, 2, False, cb=(16, 16), htj2k=True)

@@ -77,6 +77,26 @@ def test_package_api(ctx, oracle):
     PC.check_package_api(ctx, oracle, n=1_000_003)
 
 
+@pytest.mark.parametrize("w,h,c,bits,L,rev,tile,cb", [
+    (512, 512, 1, 16, 5, True, (0, 0), (64, 64)),      # C1 with the default 64x64 code-blocks
+    (1024, 768, 1, 12, 6, False, (0, 0), (64, 64)),    # C2-shaped
+    (640, 480, 3, 8, 5, False, (0, 0), (32, 32)), (513, 257, 3, 8, 5, True, (256, 256), (64, 64)),
+    (333, 211, 1, 12, 4, False, (0, 0), (16, 64)), (127, 129, 1, 16, 5, True, (0, 0), (4, 4)), (100, 100, 1, 8, 0, True, (0, 0), (32, 32)),
+])
+def test_code_block_interface(ctx, oracle, w, h, c, bits, L, rev, tile, cb):
+    PC.check_blocks(ctx, oracle, w, h, c, bits, L, rev, tile=tile, cb=cb, nframes=3)
+
+
+def test_code_block_interface_htj2k_and_errors(ctx, oracle):
+    import j2kb200
+    PC.check_blocks(ctx, oracle, 400, 360, 1, 12, 4, True, cb=(64, 64), htj2k=True)
+    PC.check_blocks(ctx, oracle, 400, 360, 1, 12, 4, False, cb=(64, 64), htj2k=True)
+    fp = abi.fwd_params(64, 64, 1, 8, False, num_levels=2)
+    with pytest.raises(j2kb200.J2KError) as e:
+        ctx.forward_blocks(fp, np.zeros((1, 64 * 64), np.uint8), 48, 64)
+    assert "invalid code-block width" in str(e.value)
+
+
 def test_interop_raws(ctx, oracle):
     man = json.load(open(os.path.join(HERE, "golden", "interop", "manifest.json")))
     for fx in man["fixtures"]:
