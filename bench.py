@@ -233,7 +233,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--frames", type=int, default=16, help="C2 frames per rank per step")
+    ap.add_argument("--frames", type=int, default=32, help="C2 frames per rank per step")
     ap.add_argument("--streams", type=int, default=2, help="streams the resident steps alternate over (1 = serial)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -131,6 +131,56 @@ def test_batch_matches_single_and_roundtrip_at_full_size(ctx, oracle):
     assert np.count_nonzero(got != want) == 0
 
 
+def test_full_size_series_and_tile_block_properties(ctx, oracle):
+    """BASELINE sizes the oracle cannot cover in seconds, through size-independent properties."""
+    # C4: the whole 2000-frame 512x512 16-bit series, 5/3 lossless: encode -> decode is the identity, frame by frame
+    rng = np.random.default_rng(4000)
+    n, w, h = 2000, 512, 512
+    frames = rng.integers(0, 65536, (n, h * w), dtype=np.uint16).view(np.uint8).reshape(n, -1)
+    fp = abi.fwd_params(w, h, 1, 16, False, num_levels=5, reversible=True)
+    ip = abi.inv_params(w, h, 1, 16, False, num_levels=5, reversible=True)
+    co = ctx.forward_batch(fp, frames)
+    assert np.array_equal(ctx.inverse_batch(ip, co), frames)
+    for f in (0, 999, 1999):  # and three frames against the oracle
+        assert np.array_equal(co[f], oracle.forward(fp, frames[f]))
+    del co
+    # C5: one GPU's block of the slide, 128 tiles of 1024x1024 RGB (8192 x 16384), 7 levels.
+    W5, H5 = 8192, 16384
+    pool = [PC.synth(np.random.default_rng(5000 + k), 1024, 1024, 3, 8) for k in range(4)]
+    img = np.empty((H5, W5, 3), np.uint8)
+    for t in range(128):  # every tile differs: a pool tile, shifted and offset by the tile number
+        tyy, txx = t // 8, t % 8
+        img[tyy * 1024:(tyy + 1) * 1024, txx * 1024:(txx + 1) * 1024] = np.roll(pool[t % 4], t, axis=1) // 2 + (t % 100)
+    raw = img.reshape(-1)
+    # (i) RCT + 5/3: identity
+    fp = abi.fwd_params(W5, H5, 3, 8, False, 1024, 1024, 7, True, False, abi.MCT_RCT)
+    ip = abi.inv_params(W5, H5, 3, 8, False, 1024, 1024, 7, True, False, abi.MCT_RCT)
+    co = ctx.forward(fp, raw)
+    assert np.array_equal(ctx.inverse(ip, co), raw)
+    # every tile is transformed independently: tile 77 alone gives the same coefficients as inside the image
+    tx, ty = 77 % 8, 77 // 8
+    tile = np.ascontiguousarray(img[ty * 1024:(ty + 1) * 1024, tx * 1024:(tx + 1) * 1024]).reshape(-1)
+    fpt = abi.fwd_params(1024, 1024, 3, 8, False, 0, 0, 7, True, False, abi.MCT_RCT)
+    t_co = ctx.forward(fpt, tile)
+    assert np.array_equal(co[77 * 3 * 1024 * 1024:78 * 3 * 1024 * 1024], t_co)
+    assert np.array_equal(t_co, oracle.forward(fpt, tile))
+    # (ii) ICT + 9/7 with the OpenJPEG default steps: one tile against the oracle, the whole block by the lossy bound
+    es, ds = PC.steps_for(oracle, 7, 8)
+    fp = abi.fwd_params(W5, H5, 3, 8, False, 1024, 1024, 7, False, False, abi.MCT_ICT, es)
+    ip = abi.inv_params(W5, H5, 3, 8, False, 1024, 1024, 7, False, False, abi.MCT_ICT, ds)
+    co = ctx.forward(fp, raw)
+    fpt = abi.fwd_params(1024, 1024, 3, 8, False, 0, 0, 7, False, False, abi.MCT_ICT, es)
+    assert np.array_equal(co[77 * 3 * 1024 * 1024:78 * 3 * 1024 * 1024], oracle.forward(fpt, tile))
+    t1 = np.empty_like(co)
+    for k in range(0, co.size, 1 << 24):  # chunked: the stand-in for T1 works in int64
+        t1[k:k + (1 << 24)] = PC.M.t1_emulate(co[k:k + (1 << 24)], False)
+    back = ctx.inverse(ip, t1)
+    worst = 0
+    for k in range(0, raw.size, 1 << 26):
+        worst = max(worst, int(np.abs(back[k:k + (1 << 26)].astype(np.int16) - raw[k:k + (1 << 26)].astype(np.int16)).max()))
+    assert worst <= 12, worst  # the reference's own lossy end-to-end bound (SURVEY 4: <= 12 at default steps)
+
+
 def test_async_tickets(ctx, oracle):
     rng = np.random.default_rng(5)
     n, w, h = 8, 256, 256
