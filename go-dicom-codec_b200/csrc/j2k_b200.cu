@@ -513,6 +513,7 @@ void ring_chunks(RingSeg& g, int NP, int n_cols_total_hint, int level) {
 }
 
 bool ring_variant_supported(int WT, int NP, int NC, int IN, int MCT, int SG) {
+    if (NC == 3 && NP == 4) return WT == 97 && SG == 0 && (IN == IN_U8 || IN == IN_U16) && MCT == MCTK_ICT;  // component-split first level
     if (NC == 3) return NP == 2 && SG == 0 && (IN == IN_U8 || IN == IN_U16) && MCT == (WT == 53 ? MCTK_RCT : MCTK_ICT);
     if (NP != 4 || MCT != MCTK_NONE) return false;
     if (IN == IN_U8 || IN == IN_U16) return true;
@@ -522,7 +523,19 @@ bool ring_variant_supported(int WT, int NP, int NC, int IN, int MCT, int SG) {
 
 // Converts the per-level launch list into ONE persistent launch when every level qualifies; otherwise P.ring.ok stays false
 // and run_plan uses the per-level kernels.
+int build_ring_fwd_impl(const Spec& s, Plan& P, const std::vector<long long>& tab, bool split3);
+
+// 3-component 9/7 frames first try the component-split first level (NP = 4, one component per job); geometries it does not
+// take (widths that are not a multiple of 8, ...) fall back to the three-components-per-job variant (NP = 2).
 int build_ring_fwd(const Spec& s, Plan& P, const std::vector<long long>& tab) {
+    if (!s.reversible && env_int("J2K_RING_SPLIT3", 1)) {
+        int rc = build_ring_fwd_impl(s, P, tab, true);
+        if (rc || P.ring.ok) return rc;
+    }
+    return build_ring_fwd_impl(s, P, tab, false);
+}
+
+int build_ring_fwd_impl(const Spec& s, Plan& P, const std::vector<long long>& tab, bool split3) {
     RingPlan& R = P.ring;
     R.ok = false;
     if (env_int("J2K_RING_DISABLE", 0)) return 0;
@@ -545,7 +558,8 @@ int build_ring_fwd(const Spec& s, Plan& P, const std::vector<long long>& tab) {
         RingSeg& g = R.args.seg[si];
         const bool first = l.level == 1;
         const bool raw_in = l.KIND == IN_U8 || l.KIND == IN_U16;
-        const int NP = l.NC == 3 ? 2 : 4;
+        const bool split = split3 && first && l.NC == 3 && raw_in && l.MCT == MCTK_ICT;  // one component per job
+        const int NP = (l.NC == 3 && !split) ? 2 : 4;
         const int SG = (raw_in && P.raw.sign_sub != 0) ? 1 : 0;
         const int ES = l.KIND == IN_U8 ? 1 : (l.KIND == IN_U16 ? 2 : 4);
         const int PB = ES * (raw_in ? l.NC : 1);
@@ -583,14 +597,14 @@ int build_ring_fwd(const Spec& s, Plan& P, const std::vector<long long>& tab) {
         g.rcpE = make_float2(g.q[0].rcp, g.q[2].rcp); g.nstE = make_float2(-g.q[0].step, -g.q[2].step);
         g.rcpO = make_float2(g.q[1].rcp, g.q[3].rcp); g.nstO = make_float2(-g.q[1].step, -g.q[3].step);
         g.w = a.w; g.h = a.h; g.py = a.py; g.lw = a.lw; g.lh = a.lh; g.Kx = a.Kx; g.Ky = a.Ky;
-        g.n_items = a.n_items;
+        g.n_items = split ? 3 * a.n_items : a.n_items;
         g.first = first ? 1 : 0;
         g.row_bytes = (int)row_bytes;
         g.dc = first ? a.raw.dc : 0;
         g.x_off = a.x_off;
         g.x_row_bytes = pitch;
         g.ll = a.ll; g.hl = a.hl; g.lh_ = a.lh_; g.hh = a.hh;
-        ring_chunks(g, NP, a.n_items, l.level);
+        ring_chunks(g, NP, g.n_items, l.level);
         g.dep_seg = -1; g.dep_div = 1; g.dep_target = 0;
         if (!first) {
             // producer: same class, previous level
@@ -598,7 +612,7 @@ int build_ring_fwd(const Spec& s, Plan& P, const std::vector<long long>& tab) {
                 const LevelLaunch& pl = P.levels[order[pj]];
                 if (pl.cls == l.cls && pl.level == l.level - 1) {
                     g.dep_seg = (int)pj;
-                    g.dep_div = pl.nc3_first ? 3 : 1;
+                    g.dep_div = (pl.nc3_first && R.NP1 == 2) ? 3 : 1;  // component-split producers count per component
                     g.dep_target = R.args.seg[pj].nchunks * R.args.seg[pj].nstrips;
                 }
             }
@@ -656,6 +670,7 @@ int ring_dispatch_fwd(const RingPlan& R, const RingArgs& A, unsigned grid, cudaS
     RING_CASE(97, 4, 1, IN_U8, MCTK_NONE, 0) RING_CASE(97, 4, 1, IN_U16, MCTK_NONE, 0)
     RING_CASE(97, 4, 1, IN_U8, MCTK_NONE, 1) RING_CASE(97, 4, 1, IN_U16, MCTK_NONE, 1)
     RING_CASE(97, 2, 3, IN_U8, MCTK_ICT, 0) RING_CASE(97, 2, 3, IN_U16, MCTK_ICT, 0)
+    RING_CASE(97, 4, 3, IN_U8, MCTK_ICT, 0) RING_CASE(97, 4, 3, IN_U16, MCTK_ICT, 0)
     RING_CASE(97, 4, 1, IN_F32, MCTK_NONE, 0) RING_CASE(97, 4, 1, IN_I32, MCTK_NONE, 0)
     RING_CASE(53, 4, 1, IN_U8, MCTK_NONE, 0) RING_CASE(53, 4, 1, IN_U16, MCTK_NONE, 0)
     RING_CASE(53, 4, 1, IN_U8, MCTK_NONE, 1) RING_CASE(53, 4, 1, IN_U16, MCTK_NONE, 1)
@@ -744,7 +759,7 @@ int build_ring_inv(const Spec& s, Plan& P, const std::vector<long long>& tab) {
             for (int i = 0; i < a.n_items; i++)
                 if (a.planes_off && (tab[(size_t)(a.planes_off - (const long long*)P.tables.p) + i] % 4)) return 0;
         }
-        ring_chunks(g, NP, a.n_items, l.level);
+        ring_chunks(g, NP, g.n_items, l.level);
         g.dep_seg = -1; g.dep_div = 1; g.dep_target = 0; g.dep_mul = 1;
         {
             // producer: same class, next coarser level (absent for the coarsest level of the class)

@@ -265,7 +265,11 @@ __device__ __forceinline__ unsigned pack_clamp2(int a, int b, const RawPack& p) 
 
 // ------------------------------------------------------------------ forward job
 
-template <int WT, int NP, int NC, int IN, int MCT, int SG>
+// XC = 3: component-split first level of a 3-component frame.  The staged rows hold interleaved RGB pixels, but the job
+// produces ONE component (item = 3 * pixel item + component): it converts all three samples of a pixel and evaluates
+// only its own row of the ICT, so the warp runs the single-component pipeline (NP = 4, full occupancy) at the price of
+// converting the raw bytes three times (they arrive through L2 / shared memory, not HBM).
+template <int WT, int NP, int NC, int IN, int MCT, int SG, int XC = 1>
 struct FwdRing {
     typedef FwdLevel<WT, NP, NC, IN, MCT> Slow;
     typedef typename Wt<WT>::T T;
@@ -273,7 +277,7 @@ struct FwdRing {
     static constexpr int HLN = Slow::HLN, NS = Slow::NS;
     static constexpr bool RAWIN = (IN == IN_U8 || IN == IN_U16);
     static constexpr int ES = (IN == IN_U8) ? 1 : (IN == IN_U16 ? 2 : 4);
-    static constexpr int PB = ES * (RAWIN ? NC : 1);  // bytes per pixel position of one staged row
+    static constexpr int PB = ES * (RAWIN ? NC * XC : 1);  // bytes per pixel position of one staged row
     static constexpr int LB = NS * PB;                // bytes per lane per row
     static constexpr int NW = LB / 4;                 // 32-bit words per lane per row
     static constexpr int ROWB = 32 * LB + 32;         // staged row slot (16 B slack for the alignment phase, 16 B rounding)
@@ -285,6 +289,7 @@ struct FwdRing {
     static_assert(D >= 2, "ring too small for this row size");
     static_assert(LB % 4 == 0, "lane span must be whole words");
     static_assert(NC == 1 || RAWIN, "3-component jobs read interleaved raw words");
+    static_assert(XC == 1 || (XC == 3 && NC == 1 && MAGIC && MCT == MCTK_ICT), "component split: unsigned raw RGB, float32 ICT");
 
     static __device__ __forceinline__ void fetch(smem_t p, unsigned (&w)[NW]) {
         if constexpr (LDALIGN == 16) {
@@ -387,11 +392,30 @@ struct FwdRing {
 
     // the same row as column pairs of float32 (9/7): pair j = samples 2j, 2j+1
     static __device__ __forceinline__ void load_pairs(smem_t row, int lane_off, const RawFmt& raw, int dc, float fmagic,
-                                                      float one, float2 (&out)[NC][NP]) {
+                                                      float one, float2 (&out)[NC][NP], float k0 = 0.f, float k1 = 0.f, float k2 = 0.f) {
         {
             unsigned wv[NW];
             fetch(row + lane_off, wv);
-            if constexpr (IN == IN_F32) {
+            if constexpr (XC == 3) {
+                // one row of the float32 ICT (encoder.go:277-288): (r * k0 + g * k1) + b * k2 on exact float32(int) inputs
+                const float2 nm = splat2(-fmagic);
+#pragma unroll
+                for (int j = 0; j < NP; j++) {
+                    float2 f[3];
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        unsigned p[2];
+#pragma unroll
+                        for (int k = 0; k < 2; k++) {
+                            const int e = 3 * (2 * j + k) + c;
+                            if constexpr (IN == IN_U8) p[k] = __byte_perm(wv[e >> 2], 0x4B000000u, 0x7440u | (e & 3));
+                            else p[k] = __byte_perm(wv[e >> 1], 0x4B000000u, (e & 1) ? 0x7432u : 0x7410u);
+                        }
+                        f[c] = add2(make_float2(__uint_as_float(p[0]), __uint_as_float(p[1])), nm);
+                    }
+                    out[0][j] = addp2(mul2(f[2], splat2(k2)), addp2(mul2(f[0], splat2(k0)), mul2(f[1], splat2(k1)), one), one);
+                }
+            } else if constexpr (IN == IN_F32) {
 #pragma unroll
                 for (int j = 0; j < NP; j++) out[0][j] = make_float2(__uint_as_float(wv[2 * j]), __uint_as_float(wv[2 * j + 1]));
             } else if constexpr (MAGIC) {
@@ -466,6 +490,12 @@ struct FwdRing {
         const int dc = S.dc;
         const float fmagic = 8388608.0f + (float)dc;
         const float one = rw.one;
+        const int comp = XC == 3 ? item % 3 : 0;   // component-split first level: item = 3 * pixel item + component
+        if constexpr (XC == 3) item /= 3;
+        // this component's row of the ICT matrix (encoder.go:277-288); warp-uniform
+        const float k0 = comp == 0 ? 0.299f : (comp == 1 ? -0.16875f : 0.5f);
+        const float k1 = comp == 0 ? 0.587f : (comp == 1 ? -0.331260f : -0.41869f);
+        const float k2 = comp == 0 ? 0.114f : (comp == 1 ? 0.5f : -0.08131f);
         const unsigned char* src = S.x_base + S.x_off[item] * ES + c0;
         const long long pitch = S.x_row_bytes;
 
@@ -484,6 +514,7 @@ struct FwdRing {
         int* p_hh = (int*)S.hh.base + S.hh.off[item] + (long long)S.hh.y_off * S.hh.row_stride + S.hh.x_off + kx0;
         const int rs_ll = S.ll.row_stride, rs_b = S.hl.row_stride;
         const long long cs_ll = S.ll.comp_stride, cs_b = S.hl.comp_stride;
+        if constexpr (XC == 3) { p_ll += comp * cs_ll; p_hl += comp * cs_b; p_lh += comp * cs_b; p_hh += comp * cs_b; }
         // rows of the first storing iteration (low-type row ky0 - py, high-type row ky0); they advance one row per iteration
         p_ll += (long long)(ky0 - py) * rs_ll; p_hl += (long long)(ky0 - py) * rs_b;
         p_lh += (long long)ky0 * rs_b; p_hh += (long long)ky0 * rs_b;
@@ -548,8 +579,8 @@ struct FwdRing {
                 const smem_t row_o = row_e + ROWB;
 
                 if (fix) fix_halo(row_e, row_o, lane, fix_l, fix_r, w, vb);
-                load_pairs(row_e, lane_off, raw, dc, fmagic, one, out.pe);
-                load_pairs(row_o, lane_off, raw, dc, fmagic, one, out.po);
+                load_pairs(row_e, lane_off, raw, dc, fmagic, one, out.pe, k0, k1, k2);
+                load_pairs(row_o, lane_off, raw, dc, fmagic, one, out.po, k0, k1, k2);
                 // vertical lifting on column pairs; the finished (low, high) row values of column s land in Q[c][s]
                 float2 Q[NC][NS];
 #pragma unroll
@@ -786,7 +817,7 @@ __device__ __forceinline__ void ring_warp_init(unsigned char* smem, RingWarp& rw
 #ifndef J2K_RING_MINB_RGB97
 #define J2K_RING_MINB_RGB97 2  // the 3-component 9/7 level-1 variant carries 3x the window state: 2 CTAs/SM, no spills
 #endif
-#define J2K_RING_BOUNDS __launch_bounds__(J2K_RING_WARPS * 32, (WT == 97 && NC1 == 3) ? J2K_RING_MINB_RGB97 : J2K_RING_MINB)
+#define J2K_RING_BOUNDS __launch_bounds__(J2K_RING_WARPS * 32, (WT == 97 && NC1 == 3 && NP1 == 2) ? J2K_RING_MINB_RGB97 : J2K_RING_MINB)
 #endif
 template <int WT, int NP1, int NC1, int IN1, int MCT1, int SG1>
 __global__ void J2K_RING_BOUNDS fwd_ring_kernel(const __grid_constant__ RingArgs A) {
@@ -799,8 +830,11 @@ __global__ void J2K_RING_BOUNDS fwd_ring_kernel(const __grid_constant__ RingArgs
     while (ring_claim(A, lane, J)) {
         const RingSeg& S = A.seg[J.seg];
         ring_wait_dep(A, S, J.item, lane);
-        if (S.first) FwdRing<WT, NP1, NC1, IN1, MCT1, SG1>::run(S, A.raw, J.item, J.chunk, J.strip, rw, lane);
-        else FwdRing<WT, 4, 1, (WT == 53 ? IN_I32 : IN_F32), MCTK_NONE, 0>::run(S, A.raw, J.item, J.chunk, J.strip, rw, lane);
+        if (S.first) {
+            // NC1 == 3 with NP1 == 4 names the component-split variant (one component per job)
+            if constexpr (NC1 == 3 && NP1 == 4) FwdRing<WT, 4, 1, IN1, MCT1, SG1, 3>::run(S, A.raw, J.item, J.chunk, J.strip, rw, lane);
+            else FwdRing<WT, NP1, NC1, IN1, MCT1, SG1>::run(S, A.raw, J.item, J.chunk, J.strip, rw, lane);
+        } else FwdRing<WT, 4, 1, (WT == 53 ? IN_I32 : IN_F32), MCTK_NONE, 0>::run(S, A.raw, J.item, J.chunk, J.strip, rw, lane);
         ring_signal(A, S, J.item, lane);
     }
     ring_retire(A, lane);
