@@ -354,24 +354,22 @@ struct FwdRing {
     // row, with whole-sample-mirrored copies (dwt53.go / dwt97.go border cases == symmetric extension,
     // tests/test_oracle_mirror.py); lanes 0..NS-1 write the left span, lanes NS..2NS-1 the right one.  The TMA copy
     // of a border strip never covers those bytes, so the plain stores cannot race with a refill.
-    static __device__ __forceinline__ void fix_halo(smem_t row_e, smem_t row_o, int lane, bool fix_l, bool fix_r, int w, int vb) {
+    static __device__ __forceinline__ void fix_halo(smem_t stage, int lane, bool fix_l, bool fix_r, int w, int vb) {
         if (lane < 2 * NS) {
             const bool left = lane < NS;
             const int k = left ? lane : lane - NS;
             if (left ? fix_l : fix_r) {
                 const int pi = left ? -(k + 1) : w + k;
                 const int so = mirror_fast(pi, w) * PB - vb, d_o = pi * PB - vb;
-                unsigned char* re = smem_ptr(row_e);
-                unsigned char* ro = smem_ptr(row_o);
+                unsigned char* st = smem_ptr(stage);
 #pragma unroll
-                for (int c = 0; c < PB / ES; c++) {
-                    if constexpr (ES == 1) { re[d_o + c] = re[so + c]; ro[d_o + c] = ro[so + c]; }
-                    else if constexpr (ES == 2) {
-                        *(unsigned short*)(re + d_o + 2 * c) = *(const unsigned short*)(re + so + 2 * c);
-                        *(unsigned short*)(ro + d_o + 2 * c) = *(const unsigned short*)(ro + so + 2 * c);
-                    } else {
-                        *(unsigned*)(re + d_o + 4 * c) = *(const unsigned*)(re + so + 4 * c);
-                        *(unsigned*)(ro + d_o + 4 * c) = *(const unsigned*)(ro + so + 4 * c);
+                for (int r = 0; r < 2 * RPS; r++) {  // every row of the stage: one pass, one warp barrier per four rows
+                    unsigned char* row = st + r * ROWB;
+#pragma unroll
+                    for (int c = 0; c < PB / ES; c++) {
+                        if constexpr (ES == 1) row[d_o + c] = row[so + c];
+                        else if constexpr (ES == 2) *(unsigned short*)(row + d_o + 2 * c) = *(const unsigned short*)(row + so + 2 * c);
+                        else *(unsigned*)(row + d_o + 4 * c) = *(const unsigned*)(row + so + 4 * c);
                     }
                 }
             }
@@ -556,6 +554,7 @@ struct FwdRing {
             rw.phase ^= 1u << cslot;
             stage = rw.ring + cslot * STAGEB;
             cslot = (cslot + 1 == D) ? 0 : cslot + 1;
+            if (fix) fix_halo(stage, lane, fix_l, fix_r, w, vb);
         };
         const smem_t lane_s = rw.ring + lane_off;
         if constexpr (WT == 97) {
@@ -578,7 +577,6 @@ struct FwdRing {
                 const smem_t row_e = stage + half * 2 * ROWB;
                 const smem_t row_o = row_e + ROWB;
 
-                if (fix) fix_halo(row_e, row_o, lane, fix_l, fix_r, w, vb);
                 load_pairs(row_e, lane_off, raw, dc, fmagic, one, out.pe, k0, k1, k2);
                 load_pairs(row_o, lane_off, raw, dc, fmagic, one, out.po, k0, k1, k2);
                 // vertical lifting on column pairs; the finished (low, high) row values of column s land in Q[c][s]
@@ -694,7 +692,6 @@ struct FwdRing {
                 const smem_t row_o = row_e + ROWB;
 
                 int e[NC][NS], o[NC][NS], lo[NC][NS], hi[NC][NS];
-                if (fix) fix_halo(row_e, row_o, lane, fix_l, fix_r, w, vb);
                 load_scalar(row_e, lane_off, raw, dc, e);
                 load_scalar(row_o, lane_off, raw, dc, o);
 #pragma unroll
@@ -887,7 +884,7 @@ struct InvRing {
                 const int src_lo = mirror_fast(2 * kx, w) >> 1, src_hi = (mirror_fast(2 * kx + 1, w) - 1) >> 1;
                 unsigned char* st = smem_ptr(stage);
 #pragma unroll
-                for (int r = 0; r < NROWS; r++) {
+                for (int r = 0; r < RPS * NROWS; r++) {  // every band row of the stage (PAIRB == NROWS * ROWB)
                     const int src = (r & 1) ? src_hi : src_lo;  // rows 1, 3 (HL, HH) are horizontally high-pass
                     unsigned char* row = st + r * ROWB;
                     *(unsigned*)(row + kx * 4 - vb) = *(const unsigned*)(row + src * 4 - vb);
@@ -1067,6 +1064,7 @@ struct InvRing {
             rw.phase ^= 1u << cslot;
             stage_base = rw.ring + cslot * STAGEB;
             cslot = (cslot + 1 == D) ? 0 : cslot + 1;
+            if (fix) fix_halo(stage_base, lane, fix_l, fix_r, w, bw, vb);
         };
         if constexpr (WT == 97) {
             const float2 sclE = S.rcpE, sclO = S.rcpO;
@@ -1082,7 +1080,6 @@ struct InvRing {
             auto body = [&](int it, const int half, const VState& in, VState& out) {
                 if (RPS == 1 || half == 0) next_stage();
                 const smem_t stage = stage_base + (RPS == 1 ? 0 : half) * PAIRB;
-                if (fix) fix_halo(stage, lane, fix_l, fix_r, w, bw, vb);
 
                 float2 xe[NC][NP], xo[NC][NP];  // finished rows of pair t - LAG as column pairs
 #pragma unroll
@@ -1225,7 +1222,6 @@ struct InvRing {
                 const int half = it & (RPS - 1);
                 if (half == 0) next_stage();
                 const smem_t stage = stage_base + half * PAIRB;
-                if (fix) fix_halo(stage, lane, fix_l, fix_r, w, bw, vb);
 
                 int xe[NC][NS], xo[NC][NS];
 #pragma unroll
