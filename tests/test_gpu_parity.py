@@ -204,3 +204,30 @@ def test_errors(ctx):
     bad = abi.fwd_params(0, 64, 1, 8, False)
     with pytest.raises(j2kb200.J2KError):
         ctx.forward(bad, np.zeros(10, np.uint8))
+
+
+def test_in_process_multi_device_sharding(oracle):
+    """j2k_init with every visible device: a host batch is cut into contiguous frame blocks, one per GPU, no collective
+    (SURVEY 8e).  Runs on any box; with one GPU it degenerates to the single-device path."""
+    import torch
+
+    import j2kb200
+    nd = torch.cuda.device_count()
+    rng = np.random.default_rng(77)
+    n, w, h = 4 * max(nd, 1) + 1, 256, 192  # uneven split on purpose
+    frames = rng.integers(0, 4096, (n, h * w), dtype=np.uint16).view(np.uint8).reshape(n, -1)
+    es, ds = PC.steps_for(oracle, 4, 12)
+    fp = abi.fwd_params(w, h, 1, 12, False, num_levels=4, reversible=False, steps=es)
+    fl = abi.fwd_params(w, h, 1, 12, False, num_levels=4, reversible=True)
+    il = abi.inv_params(w, h, 1, 12, False, num_levels=4, reversible=True)
+    with j2kb200.Context(devices=list(range(nd))) as mctx:
+        assert mctx.device_count == nd
+        co = mctx.forward_batch(fp, frames)
+        for f in range(n):
+            assert np.array_equal(co[f], oracle.forward(fp, frames[f])), f"frame {f}"
+        assert np.array_equal(mctx.inverse_batch(il, mctx.forward_batch(fl, frames)), frames)
+        blocks, nb = mctx.forward_blocks(fl, frames, 32, 32)
+        one = j2kb200.Context(devices=[0])
+        b1, n1 = one.forward_blocks(fl, frames, 32, 32)
+        one.close()
+        assert np.array_equal(blocks, b1) and np.array_equal(nb, n1)
