@@ -231,3 +231,22 @@ def test_in_process_multi_device_sharding(oracle):
         b1, n1 = one.forward_blocks(fl, frames, 32, 32)
         one.close()
         assert np.array_equal(blocks, b1) and np.array_equal(nb, n1)
+
+
+def test_c1_ct1_j2ki_image(ctx, oracle):
+    """BASELINE config C1 on its own image: the reference's test-data/CT1_J2KI frame (512x512 signed 16-bit, fixture decoded
+    by OpenJPEG 2.5.4, tests/golden/make_golden.py), 5/3 lossless 5 levels round trip, and the 9/7 path."""
+    ob = np.load(os.path.join(HERE, "golden", "ct1_j2ki.npz"))["offset_binary"]
+    raw = (ob.astype(np.int32) - 32768).astype("<i2").view(np.uint8).reshape(-1)
+    fp = abi.fwd_params(512, 512, 1, 16, True, num_levels=5, reversible=True)
+    ip = abi.inv_params(512, 512, 1, 16, True, num_levels=5, reversible=True)
+    co = ctx.forward(fp, raw)
+    assert np.array_equal(co, oracle.forward(fp, raw))
+    assert np.array_equal(ctx.inverse(ip, co), raw)
+    es, ds = PC.steps_for(oracle, 5, 16)
+    fp = abi.fwd_params(512, 512, 1, 16, True, num_levels=5, reversible=False, steps=es)
+    ip = abi.inv_params(512, 512, 1, 16, True, num_levels=5, reversible=False, steps=ds)
+    co = ctx.forward(fp, raw)
+    assert np.array_equal(co, oracle.forward(fp, raw))
+    t1 = PC.M.t1_emulate(co)
+    assert np.array_equal(ctx.inverse(ip, t1), oracle.inverse(ip, t1))
