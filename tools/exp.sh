@@ -10,14 +10,8 @@ except Exception as e:
 PY
 }
 run base A=1
-run perlevel J2K_RING_PER_LEVEL=1
-run target2368 J2K_RING_TARGET_JOBS=2368
-run target1776 J2K_RING_TARGET_JOBS=1776
-run target1184 J2K_RING_TARGET_JOBS=1184
-run target592 J2K_RING_TARGET_JOBS=592
-run t1776min16 J2K_RING_TARGET_JOBS=1776 J2K_RING_CHUNK_MIN=16
-run t1184min16 J2K_RING_TARGET_JOBS=1184 J2K_RING_CHUNK_MIN=16
-run t1184min32 J2K_RING_TARGET_JOBS=1184 J2K_RING_CHUNK_MIN=32
 run chunk128 J2K_RING_CHUNK=128
-run chunk128t1184 J2K_RING_CHUNK=128 J2K_RING_TARGET_JOBS=1184 J2K_RING_CHUNK_MIN=16
-run frames32 BENCH_FRAMES=32
+run chunk96 J2K_RING_CHUNK=96
+run chunk128deep64 J2K_RING_CHUNK=128 J2K_RING_CHUNK_DEEP=64
+run chunk48 J2K_RING_CHUNK=48
+run perlevel J2K_RING_PER_LEVEL=1
