@@ -679,31 +679,31 @@ struct FwdRing {
             }
         } else {
             const int sh_ll = S.q[0].shift, sh_hl = S.q[1].shift, sh_lh = S.q[2].shift, sh_hh = S.q[3].shift;
-            int pe[NC][NS], po[NC][NS], d1p[NC][NS];
+            struct VState { int pe[NC][NS], po[NC][NS], d1p[NC][NS]; };
+            VState sa, sb;
 #pragma unroll
             for (int c = 0; c < NC; c++)
 #pragma unroll
-                for (int s = 0; s < NS; s++) { pe[c][s] = 0; po[c][s] = 0; d1p[c][s] = 0; }
-#pragma unroll 1
-            for (int it = 0; it < n_it; it++) {
-                const int half = it & (RPS - 1);
+                for (int s = 0; s < NS; s++) { sa.pe[c][s] = 0; sa.po[c][s] = 0; sa.d1p[c][s] = 0; }
+            // two iterations per trip with the window state ping-ponging between sa and sb (as in the 9/7 loop)
+            auto body = [&](int it, const int half, const VState& in, VState& out) {
                 if (half == 0) next_stage();
                 const smem_t row_e = stage + half * 2 * ROWB;
                 const smem_t row_o = row_e + ROWB;
 
-                int e[NC][NS], o[NC][NS], lo[NC][NS], hi[NC][NS];
-                load_scalar(row_e, lane_off, raw, dc, e);
-                load_scalar(row_o, lane_off, raw, dc, o);
+                int lo[NC][NS], hi[NC][NS];
+                load_scalar(row_e, lane_off, raw, dc, out.pe);
+                load_scalar(row_o, lane_off, raw, dc, out.po);
 #pragma unroll
                 for (int c = 0; c < NC; c++)
 #pragma unroll
                     for (int s = 0; s < NS; s++) {
-                        const int d = po[c][s] - ((pe[c][s] + e[c][s]) >> 1);
-                        const int sv = pe[c][s] + ((d1p[c][s] + d + 2) >> 2);
+                        const int d = in.po[c][s] - ((in.pe[c][s] + out.pe[c][s]) >> 1);
+                        const int sv = in.pe[c][s] + ((in.d1p[c][s] + d + 2) >> 2);
                         lo[c][s] = sv; hi[c][s] = d;
-                        pe[c][s] = e[c][s]; po[c][s] = o[c][s]; d1p[c][s] = d;
+                        out.d1p[c][s] = d;
                     }
-                if (it < 2 * LAG) continue;
+                if (it < 2 * LAG) return;
                 const int ky = ky0 + it - 2 * LAG;
                 const int yl = ky - py, yh = ky;
                 const bool row_l = st && yl >= 0 && yl < lh, row_h = st && yh < hh;
@@ -726,6 +726,12 @@ struct FwdRing {
                     }
                 }
                 p_ll += rs_ll; p_hl += rs_b; p_lh += rs_b; p_hh += rs_b;
+            };
+#pragma unroll 1
+            for (int it = 0; it < n_it; it += 2) {
+                body(it, 0, sa, sb);
+                if (it + 1 >= n_it) break;
+                body(it + 1, 1, sb, sa);
             }
         }
         (void)lane_s;
@@ -1212,16 +1218,18 @@ struct InvRing {
         } else {
             const bool halve_ll = S.ll.mode == DQ_HALVE, halve_hl = S.hl.mode == DQ_HALVE, halve_lh = S.lh_.mode == DQ_HALVE,
                        halve_hh = S.hh.mode == DQ_HALVE;
-            int dp[NC][NS], s1p[NC][NS];
+            const bool any_halve = halve_ll || halve_hl || halve_lh || halve_hh;
+            struct VState { int dp[NC][NS], s1p[NC][NS]; };
+            VState sa, sb;
 #pragma unroll
             for (int c = 0; c < NC; c++)
 #pragma unroll
-                for (int s = 0; s < NS; s++) { dp[c][s] = 0; s1p[c][s] = 0; }
-#pragma unroll 1
-            for (int it = 0; it < n_it; it++) {
-                const int half = it & (RPS - 1);
-                if (half == 0) next_stage();
-                const smem_t stage = stage_base + half * PAIRB;
+                for (int s = 0; s < NS; s++) { sa.dp[c][s] = 0; sa.s1p[c][s] = 0; }
+            // one iteration: consumes the vertical window state `in`, leaves the advanced state in `out` (two per trip,
+            // ping-ponging, so the window never moves between registers)
+            auto body = [&](int it, const int half, const VState& in, VState& out) {
+                if (RPS == 1 || half == 0) next_stage();
+                const smem_t stage = stage_base + (RPS == 1 ? 0 : half) * PAIRB;
 
                 int xe[NC][NS], xo[NC][NS];
 #pragma unroll
@@ -1231,13 +1239,15 @@ struct InvRing {
                     fetch(stage + (4 * c + 1) * ROWB + lane_off, q1);
                     fetch(stage + (4 * c + 2) * ROWB + lane_off, q2);
                     fetch(stage + (4 * c + 3) * ROWB + lane_off, q3);
-                    // t2/tile_decoder.go:989-993: truncating /2 of the classic T1 output
+                    // t2/tile_decoder.go:989-993: truncating /2 of the classic T1 output (fuse_t1_halve only: warp-uniform)
+                    if (any_halve) {
 #pragma unroll
-                    for (int j = 0; j < NP; j++) {
-                        if (halve_ll) q0[j] /= 2;
-                        if (halve_hl) q1[j] /= 2;
-                        if (halve_lh) q2[j] /= 2;
-                        if (halve_hh) q3[j] /= 2;
+                        for (int j = 0; j < NP; j++) {
+                            if (halve_ll) q0[j] /= 2;
+                            if (halve_hl) q1[j] /= 2;
+                            if (halve_lh) q2[j] /= 2;
+                            if (halve_hh) q3[j] /= 2;
+                        }
                     }
                     // horizontal synthesis of the low-type row (q0 | q1) and the high-type row (q2 | q3) (dwt53.go:123-234)
                     int e[NS], o[NS];
@@ -1270,21 +1280,21 @@ struct InvRing {
                     // vertical synthesis (dwt53.go:318-354 columns after rows)
 #pragma unroll
                     for (int s = 0; s < NS; s++) {
-                        const int sv = e[s] - ((dp[c][s] + o[s] + 2) >> 2);   // s[t]
-                        const int xodd = dp[c][s] + ((s1p[c][s] + sv) >> 1);  // x[2(t-1)+1]
-                        xe[c][s] = s1p[c][s];
+                        const int sv = e[s] - ((in.dp[c][s] + o[s] + 2) >> 2);        // s[t]
+                        const int xodd = in.dp[c][s] + ((in.s1p[c][s] + sv) >> 1);    // x[2(t-1)+1]
+                        xe[c][s] = in.s1p[c][s];
                         xo[c][s] = xodd;
-                        dp[c][s] = o[s]; s1p[c][s] = sv;
+                        out.dp[c][s] = o[s]; out.s1p[c][s] = sv;
                     }
                 }
-                if (it < 2 * LAG) continue;
+                if (it < 2 * LAG) return;
                 const int ky = ky0 + it - 2 * LAG;
                 const int re = 2 * ky - py, ro = re + 1;
                 unsigned char* const xrow = xlane;
                 int* const prow = planes;
                 xlane += 2 * xpitch;
                 if (planes) planes += 2 * planes_rs;
-                if (!st) continue;
+                if (!st) return;
                 if constexpr (FINAL) {
                     if (re >= 0 && re < h) store_final(S, raw, rp, xrow, prow, xe);
                     if (ro < h) store_final(S, raw, rp, xrow + xpitch, prow ? prow + planes_rs : nullptr, xo);
@@ -1292,6 +1302,12 @@ struct InvRing {
                     if (re >= 0 && re < h) store_planar((int*)xrow, xe[0]);
                     if (ro < h) store_planar((int*)(xrow + xpitch), xo[0]);
                 }
+            };
+#pragma unroll 1
+            for (int it = 0; it < n_it; it += 2) {
+                body(it, 0, sa, sb);
+                if (it + 1 >= n_it) break;
+                body(it + 1, 1, sb, sa);
             }
         }
     }
