@@ -1310,7 +1310,7 @@ int validate_common(int w, int h, int C, int B, int L) {
     if (C <= 0 || C > J2K_MAX_COMPONENTS) return fail(J2K_ERR_INVALID_ARG, "invalid number of components: %d (must be 1-4)", C); // encoder.go:298-300
     if (B < 1 || B > 16) return fail(J2K_ERR_INVALID_ARG, "invalid bit depth: %d (must be 1-16)", B);                            // encoder.go:302-304
     if (L < 0 || L > J2K_MAX_LEVELS) return fail(J2K_ERR_INVALID_ARG, "invalid decomposition levels: %d (must be 0-%d)", L, J2K_MAX_LEVELS);
-    if ((long long)w * h * C > (1LL << 31) - 1) return fail(J2K_ERR_INVALID_ARG, "frame too large");
+    if ((long long)w * h * C > (1LL << 34)) return fail(J2K_ERR_INVALID_ARG, "frame too large");  // frame-level offsets are 64-bit; a tile stays below 2^31 samples (checked per tile)
     return 0;
 }
 
@@ -1366,6 +1366,8 @@ int spec_from_fwd(const j2k_fwd_params* p, bool planar, Spec& s) {
     s.fwd = true; s.W = p->width; s.H = p->height; s.C = p->components; s.bit_depth = p->bit_depth; s.is_signed = p->is_signed != 0;
     s.L = p->num_levels; s.reversible = p->reversible != 0; s.htj2k = p->htj2k != 0; s.mct_mode = p->mct_mode;
     fwd_tiles(p, &s.tiles);
+    for (const TileGeom& g : s.tiles)
+        if ((long long)g.tw * g.th * s.C > (1LL << 31) - 1) return fail(J2K_ERR_INVALID_ARG, "tile too large: %dx%d", g.tw, g.th);
     s.n_steps = p->n_steps; memcpy(s.steps, p->steps, sizeof s.steps);
     s.fuse_shift = p->fuse_t1_shift != 0; s.planar_in = planar; s.direct = false; s.want_planes = false;
     s.mct_matrix = p->mct_matrix; s.mct_has_offsets = p->mct_has_offsets; s.mct_offsets = p->mct_offsets;
@@ -1385,6 +1387,8 @@ int spec_from_inv(const j2k_inv_params* p, bool want_planes, Spec& s) {
     s.fwd = false; s.W = p->xsiz - p->xosiz; s.H = p->ysiz - p->yosiz; s.C = p->components; s.bit_depth = p->bit_depth;
     s.is_signed = p->is_signed != 0; s.L = p->num_levels; s.reversible = p->reversible != 0; s.htj2k = p->htj2k != 0; s.mct_mode = p->mct_mode;
     inv_tiles(p, &s.tiles);
+    for (const TileGeom& g : s.tiles)
+        if ((long long)g.tw * g.th * s.C > (1LL << 31) - 1) return fail(J2K_ERR_INVALID_ARG, "tile too large: %dx%d", g.tw, g.th);
     s.n_steps = p->n_steps; memcpy(s.steps, p->steps, sizeof s.steps);
     s.fuse_shift = p->fuse_t1_halve != 0; s.planar_in = false; s.direct = false; s.want_planes = want_planes;
     s.mct_matrix = p->mct_matrix; s.mct_has_offsets = p->mct_has_offsets; s.mct_offsets = p->mct_offsets;

@@ -250,3 +250,34 @@ def test_c1_ct1_j2ki_image(ctx, oracle):
     assert np.array_equal(co, oracle.forward(fp, raw))
     t1 = PC.M.t1_emulate(co)
     assert np.array_equal(ctx.inverse(ip, t1), oracle.inverse(ip, t1))
+
+
+def test_c5_full_slide_single_call(ctx, oracle):
+    """BASELINE config C5 at its full size in ONE call: 32768x32768 RGB 8-bit as 1024 tiles of 1024x1024, 7 levels
+    (3.2 Gsamples: every offset beyond 2^31).  RCT + 5/3: the round trip is the identity; one tile against the oracle."""
+    rng = np.random.default_rng(5005)
+    cell = PC.synth(rng, 2048, 2048, 3, 8)                       # 2x2 tiles of distinct content ...
+    img = np.tile(cell, (16, 16, 1))                             # ... repeated over the slide
+    img[5 * 1024:6 * 1024, 9 * 1024:10 * 1024] = PC.synth(rng, 1024, 1024, 3, 8, kind="noise")  # and one odd tile
+    raw = img.reshape(-1)
+    W5 = H5 = 32768
+    fp = abi.fwd_params(W5, H5, 3, 8, False, 1024, 1024, 7, True, False, abi.MCT_RCT)
+    ip = abi.inv_params(W5, H5, 3, 8, False, 1024, 1024, 7, True, False, abi.MCT_RCT)
+    co = ctx.forward(fp, raw)
+    t = 5 * 32 + 9
+    tile = np.ascontiguousarray(img[5 * 1024:6 * 1024, 9 * 1024:10 * 1024]).reshape(-1)
+    fpt = abi.fwd_params(1024, 1024, 3, 8, False, 0, 0, 7, True, False, abi.MCT_RCT)
+    assert np.array_equal(co[t * 3 * 1024 * 1024:(t + 1) * 3 * 1024 * 1024], oracle.forward(fpt, tile))
+    back = ctx.inverse(ip, co)
+    del co
+    for k in range(0, raw.size, 1 << 28):
+        assert np.array_equal(back[k:k + (1 << 28)], raw[k:k + (1 << 28)])
+    del back
+    # ICT + 9/7 at the same size: the odd tile and the last tile against the oracle
+    es, _ = PC.steps_for(oracle, 7, 8)
+    fp = abi.fwd_params(W5, H5, 3, 8, False, 1024, 1024, 7, False, False, abi.MCT_ICT, es)
+    fpt = abi.fwd_params(1024, 1024, 3, 8, False, 0, 0, 7, False, False, abi.MCT_ICT, es)
+    co = ctx.forward(fp, raw)
+    assert np.array_equal(co[t * 3 * 1024 * 1024:(t + 1) * 3 * 1024 * 1024], oracle.forward(fpt, tile))
+    last = np.ascontiguousarray(img[31 * 1024:, 31 * 1024:]).reshape(-1)
+    assert np.array_equal(co[1023 * 3 * 1024 * 1024:], oracle.forward(fpt, last))
