@@ -492,11 +492,21 @@ int env_int(const char* name, int dflt) {
 
 // Job decomposition of one ring segment: even column strips, row chunks sized for ~2 jobs per resident warp.
 void ring_chunks(RingSeg& g, int NP, int n_cols_total_hint, int level) {
-    const int VP = 30 * NP;  // 32 lanes minus one halo lane per side (9/7 needs 2 pairs, 5/3 one: both fit NP >= 2)
+    int VP = 30 * NP;  // 32 lanes minus one halo lane per side (9/7 needs 2 pairs, 5/3 one: both fit NP >= 2)
+    // strips are a multiple of 8 pairs wide: every band-row piece a warp stores (and every pixel-row piece of the inverse)
+    // then covers whole 32-byte sectors, no partial-sector writes at the strip seams (+3 % on C2)
+    int align = 8 > NP ? 8 : NP;
+    {   // experiment knobs: strip width limit and alignment in pairs
+        int m = env_int("J2K_RING_STRIP_MAX", 0), al = env_int("J2K_RING_STRIP_ALIGN", 0);
+        if (m > 0 && m < VP) VP = m / NP * NP;
+        if (al >= NP) align = al / NP * NP;
+    }
     g.nstrips = (g.Kx + VP - 1) / VP;
     if (g.nstrips < 1) g.nstrips = 1;
     int sp = (g.Kx + g.nstrips - 1) / g.nstrips;
-    g.strip_pairs = (sp + NP - 1) / NP * NP;
+    g.strip_pairs = (sp + align - 1) / align * align;
+    if (g.strip_pairs > VP) g.strip_pairs = VP;
+    g.nstrips = (g.Kx + g.strip_pairs - 1) / g.strip_pairs;
     const int max_chunk = level <= 1 ? env_int("J2K_RING_CHUNK", 64) : env_int("J2K_RING_CHUNK_DEEP", env_int("J2K_RING_CHUNK", 64));
     const long long target = env_int("J2K_RING_TARGET_JOBS", 148 * 16 * 2);
     long long cols = (long long)n_cols_total_hint * g.nstrips;

@@ -743,10 +743,25 @@ struct FwdRing {
 struct RingJob { int seg, item, chunk, strip; };
 
 // Claims the next job (warp-uniform result); returns false when the list is exhausted.
+// A CTA claims J2K_RING_WARPS consecutive jobs at a time: its warps then walk ADJACENT strips of the same rows together,
+// so the band rows (and the staged source rows) are touched in runs of 4 x 480 B instead of isolated 480 B pieces.  The
+// store side of this kernel is what bounds it (with the loads removed it runs at the same speed), and
+// the longer runs are worth +4 % on C2.  Per-warp claiming (0) is kept for the emulator, whose warps run one by one.
+#ifndef J2K_RING_CTA_CLAIM
+#define J2K_RING_CTA_CLAIM 1
+#endif
 __device__ __forceinline__ bool ring_claim(const RingArgs& A, int lane, RingJob& J) {
     int job = 0;
+#if J2K_RING_CTA_CLAIM && !defined(J2K_EMU)
+    __shared__ int s_job;
+    __syncthreads();  // every warp has read the previous group's base
+    if (threadIdx.x == 0) s_job = (int)atomicAdd(A.ctl, (unsigned)(blockDim.x >> 5));
+    __syncthreads();
+    job = __shfl_sync(0xffffffffu, s_job + (int)(threadIdx.x >> 5), 0);  // (the shuffle keeps it warp-uniform for the compiler)
+#else
     if (lane == 0) job = (int)atomicAdd(A.ctl, 1u);
     job = __shfl_sync(0xffffffffu, job, 0);
+#endif
     if (job >= A.total_jobs) return false;
     int k = 0;
     while (k + 1 < A.nseg && job >= A.seg[k].job_end) k++;

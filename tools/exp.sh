@@ -10,8 +10,8 @@ except Exception as e:
 PY
 }
 run base A=1
-run chunk128 J2K_RING_CHUNK=128
-run chunk96 J2K_RING_CHUNK=96
-run chunk128deep64 J2K_RING_CHUNK=128 J2K_RING_CHUNK_DEEP=64
-run chunk48 J2K_RING_CHUNK=48
-run perlevel J2K_RING_PER_LEVEL=1
+run max96al32 J2K_RING_STRIP_MAX=96 J2K_RING_STRIP_ALIGN=32
+run max112al16 J2K_RING_STRIP_MAX=112 J2K_RING_STRIP_ALIGN=16
+run max120al8 J2K_RING_STRIP_MAX=120 J2K_RING_STRIP_ALIGN=8
+run max64al32 J2K_RING_STRIP_MAX=64 J2K_RING_STRIP_ALIGN=32
+run max96al32_pl J2K_RING_STRIP_MAX=96 J2K_RING_STRIP_ALIGN=32 J2K_RING_PER_LEVEL=1
