@@ -165,6 +165,7 @@ struct LevelLaunch {
     int cls;                    // tile class the launch belongs to
     bool nc3_first;             // 3-component image-side launch (items are pixel items)
     size_t o_x, o_ll, o_plane;  // offset-table positions (alignment checks of the ring path)
+    bool in_ring = false;       // handled by the persistent launch (levels 1..RingPlan::cut)
 };
 
 // Persistent single-launch form of a whole plan direction (j2k_ring.cuh); built when every level qualifies.
@@ -174,6 +175,7 @@ struct RingPlan {
     int WT = 0, NP1 = 0, NC1 = 0, IN1 = 0, MCT1 = 0, SG1 = 0;
     int x_buf[J2K_RING_MAXSEG], ll_buf[J2K_RING_MAXSEG], band_buf[J2K_RING_MAXSEG], planes_buf[J2K_RING_MAXSEG];
     int level[J2K_RING_MAXSEG];
+    int cut = 0;  // levels 1..cut run in the persistent launch, deeper ones (geometry it does not take) on the per-level kernels
     unsigned grid = 0;
 };
 
@@ -533,32 +535,41 @@ bool ring_variant_supported(int WT, int NP, int NC, int IN, int MCT, int SG) {
 
 // Converts the per-level launch list into ONE persistent launch when every level qualifies; otherwise P.ring.ok stays false
 // and run_plan uses the per-level kernels.
-int build_ring_fwd_impl(const Spec& s, Plan& P, const std::vector<long long>& tab, bool split3);
+int build_ring_fwd_impl(const Spec& s, Plan& P, const std::vector<long long>& tab, bool split3, int cut);
 
-// 3-component 9/7 frames first try the component-split first level (NP = 4, one component per job); geometries it does not
-// take (widths that are not a multiple of 8, ...) fall back to the three-components-per-job variant (NP = 2).
+// The persistent launch takes levels 1..cut, the largest cut whose levels all have the geometry it needs (window widths
+// that are multiples of 8, 16-byte aligned rows); deeper levels, which hold 1/4^cut of the samples, stay on the per-level
+// kernels behind it in stream order.  3-component 9/7 frames first try the component-split first level (NP = 4, one
+// component per job) and fall back to the three-components-per-job variant (NP = 2).
 int build_ring_fwd(const Spec& s, Plan& P, const std::vector<long long>& tab) {
-    if (!s.reversible && env_int("J2K_RING_SPLIT3", 1)) {
-        int rc = build_ring_fwd_impl(s, P, tab, true);
-        if (rc || P.ring.ok) return rc;
-    }
-    return build_ring_fwd_impl(s, P, tab, false);
+    int maxlevel = 0;
+    for (auto& l : P.levels) maxlevel = l.level > maxlevel ? l.level : maxlevel;
+    for (int split = (!s.reversible && env_int("J2K_RING_SPLIT3", 1)) ? 1 : 0; split >= 0; split--)
+        for (int cut = maxlevel; cut >= 1; cut--) {
+            int rc = build_ring_fwd_impl(s, P, tab, split != 0, cut);
+            if (rc) return rc;
+            if (P.ring.ok) {
+                P.ring.cut = cut;
+                for (auto& l : P.levels) l.in_ring = l.level <= cut;
+                return 0;
+            }
+        }
+    return 0;
 }
 
-int build_ring_fwd_impl(const Spec& s, Plan& P, const std::vector<long long>& tab, bool split3) {
+int build_ring_fwd_impl(const Spec& s, Plan& P, const std::vector<long long>& tab, bool split3, int cut) {
     RingPlan& R = P.ring;
     R.ok = false;
     if (env_int("J2K_RING_DISABLE", 0)) return 0;
-    if (P.levels.empty() || P.levels.size() > J2K_RING_MAXSEG) return 0;
+    if (P.levels.empty()) return 0;
     memset(&R.args, 0, sizeof R.args);
     const int WT = s.reversible ? 53 : 97;
     // order: level-major, then class (the launch list is class-major)
     std::vector<int> order;
-    int maxlevel = 0;
-    for (auto& l : P.levels) maxlevel = l.level > maxlevel ? l.level : maxlevel;
-    for (int k = 1; k <= maxlevel; k++)
+    for (int k = 1; k <= cut; k++)
         for (size_t i = 0; i < P.levels.size(); i++)
             if (P.levels[i].level == k) order.push_back((int)i);
+    if (order.empty() || order.size() > J2K_RING_MAXSEG) return 0;
     std::vector<int> seg_of(P.levels.size(), -1);
     bool have_first = false;
     int n_ctl = 2, jobs = 0;
@@ -698,19 +709,36 @@ bool ring_inv_variant_supported(int WT, int NP, int NC, int OUT, int MCT) {
 }
 
 // Inverse counterpart of build_ring_fwd: coarsest level first, every level waits for the level above it.
+int build_ring_inv_impl(const Spec& s, Plan& P, const std::vector<long long>& tab, int cut);
+
+// Levels cut..1 in the persistent launch (see build_ring_fwd); the coarser levels run first on the per-level kernels.
 int build_ring_inv(const Spec& s, Plan& P, const std::vector<long long>& tab) {
+    int maxlevel = 0;
+    for (auto& l : P.levels) maxlevel = l.level > maxlevel ? l.level : maxlevel;
+    for (int cut = maxlevel; cut >= 1; cut--) {
+        int rc = build_ring_inv_impl(s, P, tab, cut);
+        if (rc) return rc;
+        if (P.ring.ok) {
+            P.ring.cut = cut;
+            for (auto& l : P.levels) l.in_ring = l.level <= cut;
+            return 0;
+        }
+    }
+    return 0;
+}
+
+int build_ring_inv_impl(const Spec& s, Plan& P, const std::vector<long long>& tab, int cut) {
     RingPlan& R = P.ring;
     R.ok = false;
     if (env_int("J2K_RING_DISABLE", 0) || env_int("J2K_RING_INV_DISABLE", 0)) return 0;
-    if (P.levels.empty() || P.levels.size() > J2K_RING_MAXSEG) return 0;
+    if (P.levels.empty()) return 0;
     memset(&R.args, 0, sizeof R.args);
     const int WT = s.reversible ? 53 : 97;
     std::vector<int> order;
-    int maxlevel = 0;
-    for (auto& l : P.levels) maxlevel = l.level > maxlevel ? l.level : maxlevel;
-    for (int k = maxlevel; k >= 1; k--)
+    for (int k = cut; k >= 1; k--)
         for (size_t i = 0; i < P.levels.size(); i++)
             if (P.levels[i].level == k) order.push_back((int)i);
+    if (order.empty() || order.size() > J2K_RING_MAXSEG) return 0;
     bool have_first = false;
     int n_ctl = 2, jobs = 0;
     for (size_t si = 0; si < order.size(); si++) {
@@ -1199,10 +1227,40 @@ int run_plan(j2k_ctx* ctx, Plan& P, void* pixels, void* coeffs, void* planes, bo
     }
     for (auto& pw : P.pre) { prof.begin(0); int rc = run_pw(pw, bufs, st); prof.end(); if (rc) return rc; nl++; }
     bool use_ring = P.ring.ok;
+    // per-level kernels: every level when the persistent launch is off, else the levels beyond its cut
+    auto run_levels = [&]() -> int {
+        for (auto& l : P.levels) {
+            if (use_ring && l.in_ring) continue;
+            LevelArgs a = l.a;
+            a.x_base = bufs[l.x_buf];
+            a.ll.base = bufs[l.ll_buf];
+            a.hl.base = a.lh_.base = a.hh.base = bufs[l.band_buf];
+            a.planes_out = l.planes_buf ? (int32_t*)bufs[l.planes_buf] : nullptr;
+            if (!aligned16(a.x_base)) a.vec_x = 0;
+            if (!aligned16(a.ll.base) || !aligned16(a.hl.base)) a.vec_b = 0;
+            static const bool trace = getenv("J2K_B200_TRACE") != nullptr;
+            if (trace)
+                fprintf(stderr, "[j2k] %s level %d %dx%d WT=%d NP=%d NC=%d kind=%d mct=%d items=%d chunks=%d strips=%d vec_x=%d vec_b=%d fast=%d\n",
+                        P.fwd ? "fwd" : "inv", l.level, a.w, a.h, l.WT, l.NP, l.NC, l.KIND, l.MCT, a.n_items, a.nchunks, a.nstrips, a.vec_x, a.vec_b,
+                        (int)(l.fast && a.vec_x && a.vec_b));
+            prof.begin(l.level);
+            cudaError_t e = P.fwd ? ((l.fast && a.vec_x && a.vec_b) ? launch_fwd_fast(l, a, st) : launch_fwd_level(l, a, st)) : launch_inv_level(l, a, st);
+            prof.end();
+            if (e != cudaSuccess)
+                return fail(J2K_ERR_CUDA, "level kernel launch (WT=%d NP=%d NC=%d kind=%d mct=%d) failed: %s", l.WT, l.NP, l.NC, l.KIND, l.MCT,
+                            cudaGetErrorString(e));
+            nl++;
+        }
+        return 0;
+    };
     if (use_ring) {
         for (int i = 0; i < P.ring.args.nseg && use_ring; i++)
             use_ring = aligned16(bufs[P.ring.x_buf[i]]) && aligned16(bufs[P.ring.ll_buf[i]]) && aligned16(bufs[P.ring.band_buf[i]]) &&
                        (P.fwd || !P.ring.planes_buf[i] || aligned16(bufs[P.ring.planes_buf[i]]));
+    }
+    if (!P.fwd || !use_ring) {  // inverse: the coarse levels beyond the cut come first; no persistent launch: every level
+        int rc = run_levels();
+        if (rc) return rc;
     }
     if (use_ring) {
         RingPlan& R = P.ring;
@@ -1276,27 +1334,9 @@ int run_plan(j2k_ctx* ctx, Plan& P, void* pixels, void* coeffs, void* planes, bo
             }
         }
     }
-    for (auto& l : P.levels) {
-        if (use_ring) break;
-        LevelArgs a = l.a;
-        a.x_base = bufs[l.x_buf];
-        a.ll.base = bufs[l.ll_buf];
-        a.hl.base = a.lh_.base = a.hh.base = bufs[l.band_buf];
-        a.planes_out = l.planes_buf ? (int32_t*)bufs[l.planes_buf] : nullptr;
-        if (!aligned16(a.x_base)) a.vec_x = 0;
-        if (!aligned16(a.ll.base) || !aligned16(a.hl.base)) a.vec_b = 0;
-        static const bool trace = getenv("J2K_B200_TRACE") != nullptr;
-        if (trace)
-            fprintf(stderr, "[j2k] %s level %d %dx%d WT=%d NP=%d NC=%d kind=%d mct=%d items=%d chunks=%d strips=%d vec_x=%d vec_b=%d fast=%d\n",
-                    P.fwd ? "fwd" : "inv", l.level, a.w, a.h, l.WT, l.NP, l.NC, l.KIND, l.MCT, a.n_items, a.nchunks, a.nstrips, a.vec_x, a.vec_b,
-                    (int)(l.fast && a.vec_x && a.vec_b));
-        prof.begin(l.level);
-        cudaError_t e = P.fwd ? ((l.fast && a.vec_x && a.vec_b) ? launch_fwd_fast(l, a, st) : launch_fwd_level(l, a, st)) : launch_inv_level(l, a, st);
-        prof.end();
-        if (e != cudaSuccess)
-            return fail(J2K_ERR_CUDA, "level kernel launch (WT=%d NP=%d NC=%d kind=%d mct=%d) failed: %s", l.WT, l.NP, l.NC, l.KIND, l.MCT,
-                        cudaGetErrorString(e));
-        nl++;
+    if (P.fwd && use_ring) {  // forward: the levels beyond the cut follow the persistent launch in stream order
+        int rc = run_levels();
+        if (rc) return rc;
     }
     for (auto& pw : P.post) { prof.begin(0); int rc = run_pw(pw, bufs, st); prof.end(); if (rc) return rc; nl++; }
     if (!P.fwd && P.generic) {

@@ -99,3 +99,18 @@ def test_code_block_interface(ectx, oracle, w, h, c, bits, L, rev, tile, cb):
 def test_code_block_interface_htj2k(ectx, oracle):
     PC.check_blocks(ectx, oracle, 40, 36, 1, 12, 2, True, cb=(16, 16), htj2k=True)
     PC.check_blocks(ectx, oracle, 40, 36, 1, 12, 2, False, cb=(16, 16), htj2k=True)
+
+
+@pytest.mark.parametrize("w,h,c,bits,signed,L,rev", [
+    (520, 24, 1, 16, False, 4, False), (520, 24, 1, 12, False, 4, True), (144, 20, 3, 8, False, 3, False), (144, 20, 3, 8, False, 3, True),
+    (272, 18, 1, 8, False, 5, False),
+])
+def test_hybrid_plans(ectx, oracle, w, h, c, bits, signed, L, rev, capfd):
+    """Widths that are a multiple of 8 only for the first levels: the persistent launch takes those, the per-level kernels
+    the rest (forward: behind it, inverse: in front of it)."""
+    import os
+    os.environ["J2K_B200_TRACE"] = "1"
+    PC.check_pipeline(ectx, oracle, w, h, c, bits, signed, L, rev, seed=w + L)
+    err = capfd.readouterr().err
+    if "[j2k]" in err:  # the trace is latched at first use; when it is on, both kinds of launch must appear
+        assert " ring " in err and " level " in err

@@ -97,6 +97,14 @@ def test_code_block_interface_htj2k_and_errors(ctx, oracle):
     assert "invalid code-block width" in str(e.value)
 
 
+@pytest.mark.parametrize("w,h,c,bits,L,rev", [
+    (4160, 512, 1, 12, 6, False), (1000, 600, 1, 16, 5, True), (1048, 520, 3, 8, 5, False), (1048, 520, 3, 8, 5, True), (2056, 264, 1, 8, 6, False),
+])
+def test_hybrid_plans(ctx, oracle, w, h, c, bits, L, rev):
+    """Widths that stay a multiple of 8 only for the first levels: persistent launch for those, per-level kernels beyond."""
+    PC.check_pipeline(ctx, oracle, w, h, c, bits, False, L, rev, seed=w)
+
+
 def test_interop_raws(ctx, oracle):
     man = json.load(open(os.path.join(HERE, "golden", "interop", "manifest.json")))
     for fx in man["fixtures"]:
