@@ -320,9 +320,12 @@ def main():
     ctx.set_profiling(True)
     lvl1 = []
     per_level = {}
-    for _ in range(5):
+    for k in range(12):
         step()
-        for lv, ms in ctx.get_profile():
+        prof = ctx.get_profile()
+        if k < 2:
+            continue  # the first launches after the event machinery is switched on are not representative
+        for lv, ms in prof:
             per_level.setdefault(lv, []).append(ms)
             if lv == 1:
                 lvl1.append(ms)
@@ -331,11 +334,11 @@ def main():
     step_alg = B * alg_bytes_per_frame()
     fused = 100 in per_level  # the persistent ring kernel: ONE launch runs all levels of all frames
     if fused:
-        k_ms = statistics.mean(per_level[100])
+        k_ms = statistics.median(per_level[100])
         k_bytes = step_alg   # SURVEY 8(d) per-level-pass model: B_fwd per frame x frames per launch
         k_name = "fwd_ring_kernel<97,NP=4,NC=1,u16> (one persistent launch: unpack+DC shift+6-level 9/7 lifting+quantize, TMA-staged rows)"
     else:
-        k_ms = statistics.mean(lvl1) if lvl1 else float("nan")
+        k_ms = statistics.median(lvl1) if lvl1 else float("nan")
         k_bytes = B * PIX * (2 + 4)  # level-1 launch: reads the u16 frame, writes LL1 (f32) + HL1/LH1/HH1 (int32)
         k_name = "level-1 kernel (unpack+DC shift+vertical+horizontal 9/7+quantize)"
     achieved = k_bytes / (k_ms * 1e-3) / 1e9
@@ -354,7 +357,8 @@ def main():
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
         "peak_source": peak_src, "algorithmic_bytes_per_launch": k_bytes, "kernel_ms": k_ms,
         "step_algorithmic_GBps": step_alg / (ms_step * 1e-3) / 1e9, "step_frac": step_alg / (ms_step * 1e-3) / 1e9 / peak,
-        "per_level_ms": {str(k): statistics.mean(v) for k, v in sorted(per_level.items())},
+        "per_level_ms": {str(k): statistics.median(v) for k, v in sorted(per_level.items())},
+        "kernel_ms_samples": [round(x, 4) for x in per_level.get(100, lvl1)],
     }
 
     # ---- inverse direction, device-resident (supplementary: the headline metric is the forward step above)
