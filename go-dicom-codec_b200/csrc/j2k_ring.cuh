@@ -750,18 +750,22 @@ struct RingJob { int seg, item, chunk, strip; };
 #ifndef J2K_RING_CTA_CLAIM
 #define J2K_RING_CTA_CLAIM 1
 #endif
+template <bool CTA>
 __device__ __forceinline__ bool ring_claim(const RingArgs& A, int lane, RingJob& J) {
     int job = 0;
 #if J2K_RING_CTA_CLAIM && !defined(J2K_EMU)
+    if constexpr (CTA) {
     __shared__ int s_job;
     __syncthreads();  // every warp has read the previous group's base
     if (threadIdx.x == 0) s_job = (int)atomicAdd(A.ctl, (unsigned)(blockDim.x >> 5));
     __syncthreads();
     job = __shfl_sync(0xffffffffu, s_job + (int)(threadIdx.x >> 5), 0);  // (the shuffle keeps it warp-uniform for the compiler)
-#else
-    if (lane == 0) job = (int)atomicAdd(A.ctl, 1u);
-    job = __shfl_sync(0xffffffffu, job, 0);
+    } else
 #endif
+    {
+        if (lane == 0) job = (int)atomicAdd(A.ctl, 1u);
+        job = __shfl_sync(0xffffffffu, job, 0);
+    }
     if (job >= A.total_jobs) return false;
     int k = 0;
     while (k + 1 < A.nseg && job >= A.seg[k].job_end) k++;
@@ -845,7 +849,7 @@ __global__ void J2K_RING_BOUNDS fwd_ring_kernel(const __grid_constant__ RingArgs
     ring_warp_init(smem, rw, lane, J2K_RING_BYTES);
     rw.one = A.one;
     RingJob J;
-    while (ring_claim(A, lane, J)) {
+    while (ring_claim<true>(A, lane, J)) {
         const RingSeg& S = A.seg[J.seg];
         ring_wait_dep(A, S, J.item, lane);
         if (S.first) {
@@ -1338,7 +1342,7 @@ __global__ void __launch_bounds__(J2K_RING_WARPS * 32, J2K_RING_MINB) inv_ring_k
     ring_warp_init(smem, rw, lane, J2K_INV_RING_BYTES);
     rw.one = A.one;
     RingJob J;
-    while (ring_claim(A, lane, J)) {
+    while (ring_claim<false>(A, lane, J)) {  // per-warp: this direction is bound by its arithmetic, not by the store pattern
         const RingSeg& S = A.seg[J.seg];
         ring_wait_dep(A, S, J.item, lane);
         if (S.first) InvRing<WT, NP1, NC1, OUT1, MCT1>::run(S, A.raw, J.item, J.chunk, J.strip, rw, lane);
