@@ -2152,7 +2152,7 @@ int j2k_wait(j2k_ctx* ctx, int64_t ticket) {
 
 // ---- wavelet package API: in place on a host plane, origin (x0, y0), stride = width
 
-static int dwt_api(j2k_ctx* ctx, void* data, int width, int height, int levels, int x0, int y0, bool reversible, bool fwd) {
+static int dwt_api(j2k_ctx* ctx, void* data, int width, int height, int levels, int x0, int y0, bool reversible, bool fwd, bool f64 = false) {
     if (!ctx || !data) return fail(J2K_ERR_INVALID_ARG, "NULL argument");
     if (width <= 0 || height <= 0) return fail(J2K_ERR_INVALID_ARG, "invalid dimensions: %dx%d", width, height);
     if (levels < 0) levels = 0;
@@ -2172,15 +2172,107 @@ static int dwt_api(j2k_ctx* ctx, void* data, int width, int height, int levels, 
     if ((rc = get_plan(d, s, &blob, sizeof blob, 1, (long long)width * height, &P))) return rc;
     size_t bytes = (size_t)width * height * 4;
     if ((rc = d.api[0].ensure(bytes)) || (rc = d.api[1].ensure(bytes))) return rc;
+    const long long npx = (long long)width * height;
+    if (f64) {  // the float64 wrappers (dwt97.go:345-351,415-421): ConvertFloat64ToFloat32, the float32 transform, and back
+        if ((rc = d.api[2].ensure(bytes * 2))) return rc;
+        CK(cudaMemcpyAsync(d.api[2].p, data, bytes * 2, cudaMemcpyHostToDevice, d.s_main));
+        J2K_LAUNCH(f64_to_f32_kernel, (unsigned)((npx + 255) / 256), 256, d.s_main, (const double*)d.api[2].p, (float*)d.api[0].p, npx);
+        CK(cudaGetLastError());
+        ctx->launches++;
+    } else
     CK(cudaMemcpyAsync(d.api[0].p, data, bytes, cudaMemcpyHostToDevice, d.s_main));
     // the untouched part of the plane (nothing, when at least one level runs) keeps the input values
     CK(cudaMemcpyAsync(d.api[1].p, d.api[0].p, bytes, cudaMemcpyDeviceToDevice, d.s_main));
     if (fwd) rc = run_plan(ctx, *P, d.api[0].p, d.api[1].p, nullptr, false, d.s_main);
     else rc = run_plan(ctx, *P, nullptr, d.api[0].p, d.api[1].p, false, d.s_main);
     if (rc < 0) return rc;
+    if (f64) {
+        J2K_LAUNCH(f32_to_f64_kernel, (unsigned)((npx + 255) / 256), 256, d.s_main, (const float*)d.api[1].p, (double*)d.api[2].p, npx);
+        CK(cudaGetLastError());
+        ctx->launches++;
+        CK(cudaMemcpyAsync(data, d.api[2].p, bytes * 2, cudaMemcpyDeviceToHost, d.s_main));
+    } else
     CK(cudaMemcpyAsync(data, d.api[1].p, bytes, cudaMemcpyDeviceToHost, d.s_main));
     CK(cudaStreamSynchronize(d.s_main));
     return J2K_OK;
+}
+
+int j2k_dwt97_forward_f64(j2k_ctx* ctx, double* data, int w, int h, int levels, int x0, int y0) { return dwt_api(ctx, data, w, h, levels, x0, y0, false, true, true); }
+int j2k_dwt97_inverse_f64(j2k_ctx* ctx, double* data, int w, int h, int levels, int x0, int y0) { return dwt_api(ctx, data, w, h, levels, x0, y0, false, false, true); }
+
+// wavelet.LLDimensionsWithParity (layout.go:11-33); pure host arithmetic
+int j2k_ll_dimensions(int width, int height, int levels, int x0, int y0, int* ll_width, int* ll_height) {
+    if (!ll_width || !ll_height) return fail(J2K_ERR_INVALID_ARG, "NULL argument");
+    if (width <= 0 || height <= 0) { *ll_width = 0; *ll_height = 0; return J2K_OK; }
+    int cw = width, ch = height, cx = x0, cy = y0;
+    for (int l = 0; l < levels; l++) {
+        if (cw <= 1 && ch <= 1) break;
+        cw = split_len(cw, (cx & 1) == 0); ch = split_len(ch, (cy & 1) == 0);   // nextLowpassWindow, layout.go:35-44
+        cx = next_coord(cx); cy = next_coord(cy);
+    }
+    *ll_width = cw; *ll_height = ch;
+    return J2K_OK;
+}
+
+int j2k_convert_f64_to_i32(j2k_ctx* ctx, const double* in, int32_t* out, size_t n) {
+    if (!ctx) return fail(J2K_ERR_INVALID_ARG, "context is NULL");
+    if (n == 0) return J2K_OK;
+    if (!in || !out) return fail(J2K_ERR_INVALID_ARG, "NULL buffer");
+    int rc = set_dev(ctx, 0);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceCtx& d = ctx->devs[0];
+    if ((rc = d.api[0].ensure(n * 8)) || (rc = d.api[1].ensure(n * 4))) return rc;
+    CK(cudaMemcpyAsync(d.api[0].p, in, n * 8, cudaMemcpyHostToDevice, d.s_main));
+    J2K_LAUNCH(f64_to_i32_kernel, (unsigned)((n + 255) / 256), 256, d.s_main, (const double*)d.api[0].p, (int*)d.api[1].p, (long long)n);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    CK(cudaMemcpyAsync(out, d.api[1].p, n * 4, cudaMemcpyDeviceToHost, d.s_main));
+    CK(cudaStreamSynchronize(d.s_main));
+    return J2K_OK;
+}
+
+// colorspace.InterleaveComponents / DeinterleaveComponents (rgb.go:54-98)
+static int interleave_api(j2k_ctx* ctx, const int32_t* const* planes_in, int32_t* const* planes_out, int32_t* inter_out, const int32_t* inter_in,
+                          size_t n, int C) {
+    if (!ctx) return fail(J2K_ERR_INVALID_ARG, "context is NULL");
+    if (C <= 0 || C > 16) return fail(J2K_ERR_INVALID_ARG, "invalid number of components: %d", C);
+    if (n == 0) return J2K_OK;
+    int rc = set_dev(ctx, 0);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceCtx& d = ctx->devs[0];
+    const size_t bytes = n * (size_t)C * 4;
+    if ((rc = d.api[0].ensure(bytes)) || (rc = d.api[1].ensure(bytes))) return rc;
+    const bool to_inter = planes_in != nullptr;
+    if (to_inter) {
+        for (int c = 0; c < C; c++) {
+            if (!planes_in[c]) return fail(J2K_ERR_INVALID_ARG, "component %d is NULL", c);
+            CK(cudaMemcpyAsync((char*)d.api[0].p + (size_t)c * n * 4, planes_in[c], n * 4, cudaMemcpyHostToDevice, d.s_main));
+        }
+    } else {
+        CK(cudaMemcpyAsync(d.api[0].p, inter_in, bytes, cudaMemcpyHostToDevice, d.s_main));
+    }
+    J2K_LAUNCH(interleave_kernel, (unsigned)((n * C + 255) / 256), 256, d.s_main, (const int*)d.api[0].p, (int*)d.api[1].p, (long long)n, C, to_inter ? 1 : 0);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    if (to_inter) CK(cudaMemcpyAsync(inter_out, d.api[1].p, bytes, cudaMemcpyDeviceToHost, d.s_main));
+    else
+        for (int c = 0; c < C; c++) CK(cudaMemcpyAsync(planes_out[c], (char*)d.api[1].p + (size_t)c * n * 4, n * 4, cudaMemcpyDeviceToHost, d.s_main));
+    CK(cudaStreamSynchronize(d.s_main));
+    return J2K_OK;
+}
+
+int j2k_interleave_components(j2k_ctx* ctx, const int32_t* const* components, int n_components, size_t n_pixels, int32_t* out) {
+    if (!components || !out) return fail(J2K_ERR_INVALID_ARG, "NULL buffer");
+    return interleave_api(ctx, components, nullptr, out, nullptr, n_pixels, n_components);
+}
+
+int j2k_deinterleave_components(j2k_ctx* ctx, const int32_t* data, size_t n_pixels, int n_components, int32_t* const* components_out) {
+    if (!data || !components_out) return fail(J2K_ERR_INVALID_ARG, "NULL buffer");
+    for (int c = 0; c < n_components; c++)
+        if (!components_out[c]) return fail(J2K_ERR_INVALID_ARG, "component %d is NULL", c);
+    return interleave_api(ctx, nullptr, components_out, nullptr, data, n_pixels, n_components);
 }
 
 int j2k_dwt53_forward(j2k_ctx* ctx, int32_t* data, int w, int h, int levels, int x0, int y0) { return dwt_api(ctx, data, w, h, levels, x0, y0, true, true); }
@@ -2215,6 +2307,54 @@ int j2k_rct_forward(j2k_ctx* ctx, size_t n, const int32_t* r, const int32_t* g, 
 int j2k_rct_inverse(j2k_ctx* ctx, size_t n, const int32_t* y, const int32_t* cb, const int32_t* cr, int32_t* r, int32_t* g, int32_t* b) { return api3(ctx, 1, n, y, cb, cr, r, g, b); }
 int j2k_ict_forward(j2k_ctx* ctx, size_t n, const int32_t* r, const int32_t* g, const int32_t* b, int32_t* y, int32_t* cb, int32_t* cr) { return api3(ctx, 2, n, r, g, b, y, cb, cr); }
 int j2k_ict_inverse(j2k_ctx* ctx, size_t n, const int32_t* y, const int32_t* cb, const int32_t* cr, int32_t* r, int32_t* g, int32_t* b) { return api3(ctx, 3, n, y, cb, cr, r, g, b); }
+
+// colorspace.ConvertRGBToYCbCr / ConvertYCbCrToRGB (rgb.go:17-52): the ICT on an interleaved RGB image
+int j2k_rgb_to_ycbcr(j2k_ctx* ctx, const int32_t* rgb, int width, int height, int32_t* y, int32_t* cb, int32_t* cr) {
+    if (!ctx) return fail(J2K_ERR_INVALID_ARG, "context is NULL");
+    if (width <= 0 || height <= 0) return J2K_OK;
+    if (!rgb || !y || !cb || !cr) return fail(J2K_ERR_INVALID_ARG, "NULL buffer");
+    const size_t n = (size_t)width * height;
+    int rc = set_dev(ctx, 0);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceCtx& d = ctx->devs[0];
+    if ((rc = d.api[0].ensure(n * 12)) || (rc = d.api[1].ensure(n * 12)) || (rc = d.api[2].ensure(n * 12))) return rc;
+    CK(cudaMemcpyAsync(d.api[0].p, rgb, n * 12, cudaMemcpyHostToDevice, d.s_main));
+    J2K_LAUNCH(interleave_kernel, (unsigned)((n * 3 + 255) / 256), 256, d.s_main, (const int*)d.api[0].p, (int*)d.api[1].p, (long long)n, 3, 0);
+    const int* pl = (const int*)d.api[1].p;
+    int* o = (int*)d.api[2].p;
+    J2K_LAUNCH(color_api_kernel, (unsigned)((n + 255) / 256), 256, d.s_main, 2, (long long)n, pl, pl + n, pl + 2 * n, o, o + n, o + 2 * n);
+    CK(cudaGetLastError());
+    ctx->launches += 2;
+    int32_t* hout[3] = {y, cb, cr};
+    for (int i = 0; i < 3; i++) CK(cudaMemcpyAsync(hout[i], o + (size_t)i * n, n * 4, cudaMemcpyDeviceToHost, d.s_main));
+    CK(cudaStreamSynchronize(d.s_main));
+    return J2K_OK;
+}
+
+int j2k_ycbcr_to_rgb(j2k_ctx* ctx, const int32_t* y, const int32_t* cb, const int32_t* cr, int width, int height, int32_t* rgb) {
+    if (!ctx) return fail(J2K_ERR_INVALID_ARG, "context is NULL");
+    if (width <= 0 || height <= 0) return J2K_OK;
+    if (!rgb || !y || !cb || !cr) return fail(J2K_ERR_INVALID_ARG, "NULL buffer");
+    const size_t n = (size_t)width * height;
+    int rc = set_dev(ctx, 0);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceCtx& d = ctx->devs[0];
+    if ((rc = d.api[0].ensure(n * 12)) || (rc = d.api[1].ensure(n * 12)) || (rc = d.api[2].ensure(n * 12))) return rc;
+    const int32_t* hin[3] = {y, cb, cr};
+    int* pl = (int*)d.api[0].p;
+    for (int i = 0; i < 3; i++) CK(cudaMemcpyAsync(pl + (size_t)i * n, hin[i], n * 4, cudaMemcpyHostToDevice, d.s_main));
+    int* o = (int*)d.api[1].p;
+    J2K_LAUNCH(color_api_kernel, (unsigned)((n + 255) / 256), 256, d.s_main, 3, (long long)n, (const int*)pl, (const int*)(pl + n), (const int*)(pl + 2 * n),
+               o, o + n, o + 2 * n);
+    J2K_LAUNCH(interleave_kernel, (unsigned)((n * 3 + 255) / 256), 256, d.s_main, (const int*)o, (int*)d.api[2].p, (long long)n, 3, 1);
+    CK(cudaGetLastError());
+    ctx->launches += 2;
+    CK(cudaMemcpyAsync(rgb, d.api[2].p, n * 12, cudaMemcpyDeviceToHost, d.s_main));
+    CK(cudaStreamSynchronize(d.s_main));
+    return J2K_OK;
+}
 
 static int api1(j2k_ctx* ctx, int op, const void* in, void* out, size_t n, double step) {
     if (!ctx) return fail(J2K_ERR_INVALID_ARG, "context is NULL");

@@ -262,6 +262,36 @@ __global__ void __launch_bounds__(256) f32_to_i32_kernel(const float* in, int* o
     out[i] = r;
 }
 
+// ---- float64 wrappers of the wavelet package (dwt97.go:30-44,181-187,249-261,325-351,410-421): they convert to float32,
+// run the float32 transform and convert back; ConvertFloat64ToInt32 (dwt97.go:515-526) rounds half away from zero by
+// truncating v +- 0.5.
+__global__ void __launch_bounds__(256) f64_to_f32_kernel(const double* in, float* out, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)in[i];
+}
+__global__ void __launch_bounds__(256) f32_to_f64_kernel(const float* in, double* out, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (double)in[i];
+}
+__global__ void __launch_bounds__(256) f64_to_i32_kernel(const double* in, int* out, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double v = in[i];
+    const double t = v >= 0 ? __dadd_rn(v, 0.5) : __dadd_rn(v, -0.5);
+    // Go's float64 -> int32 conversion of an out-of-range value (or NaN) on amd64 is the "integer indefinite" 0x80000000
+    out[i] = (t > -2147483649.0 && t < 2147483648.0) ? (int)t : (int)0x80000000;
+}
+
+// ---- colorspace.InterleaveComponents / DeinterleaveComponents (rgb.go:54-98): planes [C][n] <-> interleaved [n][C]
+__global__ void __launch_bounds__(256) interleave_kernel(const int* planes, int* out, long long n, int C, int to_interleaved) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // index into the interleaved array
+    if (i >= n * C) return;
+    const long long p = i / C;
+    const int c = (int)(i - p * C);
+    if (to_interleaved) out[i] = planes[(long long)c * n + p];
+    else out[(long long)c * n + p] = planes[i];
+}
+
 // ---- code-block interface: plane (Mallat layout) <-> block-major plane
 //
 // gather = getSubbandsForResolution + partitionIntoCodeBlocks + codeBlockNumBps (jpeg2000/encoder.go:3059-3285,

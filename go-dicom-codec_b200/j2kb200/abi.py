@@ -186,6 +186,8 @@ EXPORTED_SYMBOLS = [
     "j2k_gather_blocks_device", "j2k_scatter_blocks_device",
     "j2k_dwt53_forward", "j2k_dwt53_inverse", "j2k_dwt97_forward", "j2k_dwt97_inverse", "j2k_convert_f32_to_i32",
     "j2k_rct_forward", "j2k_rct_inverse", "j2k_ict_forward", "j2k_ict_inverse",
+    "j2k_dwt97_forward_f64", "j2k_dwt97_inverse_f64", "j2k_convert_f64_to_i32", "j2k_ll_dimensions",
+    "j2k_rgb_to_ycbcr", "j2k_ycbcr_to_rgb", "j2k_interleave_components", "j2k_deinterleave_components",
     "j2k_quantize_coefficients", "j2k_dequantize_coefficients",
     "j2k_quant_openjpeg_params", "j2k_quant_quality_params", "j2k_quant_runtime_steps", "j2k_quant_decode_steps",
 ]
@@ -250,6 +252,14 @@ def load(path: str | None = None) -> C.CDLL:
         "j2k_dwt97_forward": (ci, [vp, vp, ci, ci, ci, ci, ci]),
         "j2k_dwt97_inverse": (ci, [vp, vp, ci, ci, ci, ci, ci]),
         "j2k_convert_f32_to_i32": (ci, [vp, vp, vp, sz]),
+        "j2k_dwt97_forward_f64": (ci, [vp, vp, ci, ci, ci, ci, ci]),
+        "j2k_dwt97_inverse_f64": (ci, [vp, vp, ci, ci, ci, ci, ci]),
+        "j2k_convert_f64_to_i32": (ci, [vp, vp, vp, sz]),
+        "j2k_ll_dimensions": (ci, [ci, ci, ci, ci, ci, C.POINTER(ci), C.POINTER(ci)]),
+        "j2k_rgb_to_ycbcr": (ci, [vp, vp, ci, ci, vp, vp, vp]),
+        "j2k_ycbcr_to_rgb": (ci, [vp, vp, vp, vp, ci, ci, vp]),
+        "j2k_interleave_components": (ci, [vp, C.POINTER(vp), ci, sz, vp]),
+        "j2k_deinterleave_components": (ci, [vp, vp, sz, ci, C.POINTER(vp)]),
         "j2k_rct_forward": (ci, [vp, sz, vp, vp, vp, vp, vp, vp]),
         "j2k_rct_inverse": (ci, [vp, sz, vp, vp, vp, vp, vp, vp]),
         "j2k_ict_forward": (ci, [vp, sz, vp, vp, vp, vp, vp, vp]),

@@ -205,6 +205,56 @@ class Context:
     def dwt97_inverse(self, data, levels, x0=0, y0=0):
         return self._dwt("j2k_dwt97_inverse", data, levels, x0, y0, np.float32)
 
+    # float64 wrappers of the wavelet package (dwt97.go:340-351,410-421,515-526) and layout.go
+    def dwt97_forward_f64(self, data, levels, x0=0, y0=0):
+        return self._dwt("j2k_dwt97_forward_f64", data, levels, x0, y0, np.float64)
+
+    def dwt97_inverse_f64(self, data, levels, x0=0, y0=0):
+        return self._dwt("j2k_dwt97_inverse_f64", data, levels, x0, y0, np.float64)
+
+    def convert_f64_to_i32(self, data):
+        a = np.ascontiguousarray(data, dtype=np.float64)
+        out = np.empty(a.shape, np.int32)
+        self._ck(self.lib.j2k_convert_f64_to_i32(self.h, _vp(a), _vp(out), a.size))
+        return out
+
+    def ll_dimensions(self, width, height, levels, x0=0, y0=0):
+        a, b = C.c_int(), C.c_int()
+        self._ck(self.lib.j2k_ll_dimensions(width, height, levels, x0, y0, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    # colorspace/rgb.go
+    def convert_rgb_to_ycbcr(self, rgb, width, height):
+        a = np.ascontiguousarray(rgb, dtype=np.int32).reshape(-1)
+        o = [np.empty(width * height, np.int32) for _ in range(3)]
+        self._ck(self.lib.j2k_rgb_to_ycbcr(self.h, _vp(a), width, height, _vp(o[0]), _vp(o[1]), _vp(o[2])))
+        return o
+
+    def convert_ycbcr_to_rgb(self, y, cb, cr, width, height):
+        y, cb, cr = (np.ascontiguousarray(v, dtype=np.int32) for v in (y, cb, cr))
+        out = np.empty(width * height * 3, np.int32)
+        self._ck(self.lib.j2k_ycbcr_to_rgb(self.h, _vp(y), _vp(cb), _vp(cr), width, height, _vp(out)))
+        return out
+
+    def interleave_components(self, components):
+        if len(components) == 0:
+            return None  # rgb.go:55-57
+        pl = [np.ascontiguousarray(v, dtype=np.int32).reshape(-1) for v in components]
+        arr = (C.c_void_p * len(pl))(*[v.ctypes.data for v in pl])
+        out = np.empty(pl[0].size * len(pl), np.int32)
+        self._ck(self.lib.j2k_interleave_components(self.h, arr, len(pl), pl[0].size, _vp(out)))
+        return out
+
+    def deinterleave_components(self, data, num_components):
+        a = np.ascontiguousarray(data, dtype=np.int32).reshape(-1)
+        if a.size == 0 or num_components == 0:
+            return None  # rgb.go:77-79
+        n = a.size // num_components
+        out = [np.empty(n, np.int32) for _ in range(num_components)]
+        arr = (C.c_void_p * num_components)(*[v.ctypes.data for v in out])
+        self._ck(self.lib.j2k_deinterleave_components(self.h, _vp(a), n, num_components, arr))
+        return out
+
     def convert_f32_to_i32(self, data):
         a = np.ascontiguousarray(data, dtype=np.float32)
         out = np.empty(a.shape, np.int32)

@@ -300,6 +300,14 @@ int j2k_dwt97_forward(j2k_ctx* ctx, float* data, int width, int height, int leve
 int j2k_dwt97_inverse(j2k_ctx* ctx, float* data, int width, int height, int levels, int x0, int y0);
 /* wavelet.ConvertFloat32ToInt32OpenJPEG (dwt97.go:473-503): round half to even. */
 int j2k_convert_f32_to_i32(j2k_ctx* ctx, const float* in, int32_t* out, size_t n);
+/* The float64 wrappers wavelet.ForwardMultilevel97WithParity / InverseMultilevel97WithParity
+ * (dwt97.go:340-351,410-421): convert to float32, transform, convert back. */
+int j2k_dwt97_forward_f64(j2k_ctx* ctx, double* data, int width, int height, int levels, int x0, int y0);
+int j2k_dwt97_inverse_f64(j2k_ctx* ctx, double* data, int width, int height, int levels, int x0, int y0);
+/* wavelet.ConvertFloat64ToInt32 (dwt97.go:515-526): truncate v +- 0.5 (half away from zero). */
+int j2k_convert_f64_to_i32(j2k_ctx* ctx, const double* in, int32_t* out, size_t n);
+/* wavelet.LLDimensionsWithParity (layout.go:11-33); LLDimensions is x0 = y0 = 0.  Host arithmetic. */
+int j2k_ll_dimensions(int width, int height, int levels, int x0, int y0, int* ll_width, int* ll_height);
 
 /* ----------------------------------------- colorspace package API (planar) */
 
@@ -313,6 +321,13 @@ int j2k_ict_forward(j2k_ctx* ctx, size_t n, const int32_t* r, const int32_t* g, 
                     int32_t* y, int32_t* cb, int32_t* cr);
 int j2k_ict_inverse(j2k_ctx* ctx, size_t n, const int32_t* y, const int32_t* cb, const int32_t* cr,
                     int32_t* r, int32_t* g, int32_t* b);
+/* colorspace.ConvertRGBToYCbCr / ConvertYCbCrToRGB (colorspace/rgb.go:17-52): the same ICT on an interleaved
+ * [R0,G0,B0,R1,...] image.  (ConvertComponentsRGBToYCbCr / ...YCbCrToRGB, rgb.go:100-123, are j2k_ict_forward / inverse.) */
+int j2k_rgb_to_ycbcr(j2k_ctx* ctx, const int32_t* rgb, int width, int height, int32_t* y, int32_t* cb, int32_t* cr);
+int j2k_ycbcr_to_rgb(j2k_ctx* ctx, const int32_t* y, const int32_t* cb, const int32_t* cr, int width, int height, int32_t* rgb);
+/* colorspace.InterleaveComponents / DeinterleaveComponents (colorspace/rgb.go:54-98): planes [C][n] <-> [n][C]. */
+int j2k_interleave_components(j2k_ctx* ctx, const int32_t* const* components, int n_components, size_t n_pixels, int32_t* out);
+int j2k_deinterleave_components(j2k_ctx* ctx, const int32_t* data, size_t n_pixels, int n_components, int32_t* const* components_out);
 
 /* -------------------------------------------------- quantization.go API */
 

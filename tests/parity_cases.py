@@ -228,3 +228,34 @@ def check_blocks(ctx, oracle, w, h, c, bits, L, reversible, tile=(0, 0), cb=(64,
         assert np.array_equal(px[f], want_px), f"inverse from blocks, frame {f}"
         if reversible:
             assert np.array_equal(px[f], frames[f]), "lossless identity through the block interface"
+
+
+def check_package_api_x1(ctx, oracle, seed=8):
+    """The rest of the exported API surface with test-only callers: float64 9/7 wrappers
+    (dwt97.go:340-351,410-421), ConvertFloat64ToInt32 (:515-526), LLDimensions (layout.go:5-33), rgb.go wrappers."""
+    rng = np.random.default_rng(seed)
+    for (w, h, L, x0, y0) in ((64, 48, 3, 0, 0), (33, 17, 2, 1, 0), (7, 1, 2, 0, 0), (130, 70, 5, 0, 0)):
+        b = rng.standard_normal((h, w)) * 3000
+        assert np.array_equal(ctx.dwt97_forward_f64(b, L, x0, y0).view(np.uint64), oracle.fwd97_f64(b, L, x0, y0).view(np.uint64)), "9/7 f64 forward"
+        assert np.array_equal(ctx.dwt97_inverse_f64(b, L, x0, y0).view(np.uint64), oracle.inv97_f64(b, L, x0, y0).view(np.uint64)), "9/7 f64 inverse"
+        assert ctx.ll_dimensions(w, h, L, x0, y0) == oracle.ll_dimensions(w, h, L, x0, y0)
+    for args in ((0, 5, 3), (5, 5, 0), (1, 1, 4), (1000, 3, 12)):
+        assert ctx.ll_dimensions(*args) == oracle.ll_dimensions(*args)
+    f = rng.standard_normal(5001) * 1000
+    f[:12] = [0.5, 1.5, 2.5, -0.5, -1.5, -2.5, 0.49999999999999994, -0.49999999999999994, 2147483647.4, 2147483647.5, -2147483648.4, np.nan]
+    assert np.array_equal(ctx.convert_f64_to_i32(f), oracle.convert_f64_to_i32(f)), "float64 -> int32 (half away from zero)"
+    n_w, n_h = 37, 21
+    rgb = rng.integers(-300, 300, n_w * n_h * 3).astype(np.int32)
+    r, g, b = rgb[0::3], rgb[1::3], rgb[2::3]
+    y, cb, cr = ctx.convert_rgb_to_ycbcr(rgb, n_w, n_h)
+    oy, ocb, ocr = oracle.ict_forward(r, g, b)
+    assert np.array_equal(y, oy) and np.array_equal(cb, ocb) and np.array_equal(cr, ocr), "ConvertRGBToYCbCr"
+    back = ctx.convert_ycbcr_to_rgb(y, cb, cr, n_w, n_h)
+    orr, og, ob = oracle.ict_inverse(oy, ocb, ocr)
+    assert np.array_equal(back[0::3], orr) and np.array_equal(back[1::3], og) and np.array_equal(back[2::3], ob), "ConvertYCbCrToRGB"
+    comps = [rng.integers(-9, 9, 1000).astype(np.int32) for _ in range(4)]
+    inter = ctx.interleave_components(comps)
+    assert np.array_equal(inter, np.stack(comps, axis=1).reshape(-1)), "InterleaveComponents"   # rgb_test.go:259-322
+    de = ctx.deinterleave_components(inter, 4)
+    assert all(np.array_equal(a, b) for a, b in zip(de, comps)), "DeinterleaveComponents"
+    assert ctx.interleave_components([]) is None and ctx.deinterleave_components(np.zeros(0, np.int32), 3) is None

@@ -114,3 +114,7 @@ def test_hybrid_plans(ectx, oracle, w, h, c, bits, signed, L, rev, capfd):
     err = capfd.readouterr().err
     if "[j2k]" in err:  # the trace is latched at first use; when it is on, both kinds of launch must appear
         assert " ring " in err and " level " in err
+
+
+def test_package_api_x1(ectx, oracle):
+    PC.check_package_api_x1(ectx, oracle)

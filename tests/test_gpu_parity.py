@@ -289,3 +289,7 @@ def test_c5_full_slide_single_call(ctx, oracle):
     assert np.array_equal(co[t * 3 * 1024 * 1024:(t + 1) * 3 * 1024 * 1024], oracle.forward(fpt, tile))
     last = np.ascontiguousarray(img[31 * 1024:, 31 * 1024:]).reshape(-1)
     assert np.array_equal(co[1023 * 3 * 1024 * 1024:], oracle.forward(fpt, last))
+
+
+def test_package_api_x1(ctx, oracle):
+    PC.check_package_api_x1(ctx, oracle)
