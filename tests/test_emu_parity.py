@@ -118,3 +118,8 @@ def test_hybrid_plans(ectx, oracle, w, h, c, bits, signed, L, rev, capfd):
 
 def test_package_api_x1(ectx, oracle):
     PC.check_package_api_x1(ectx, oracle)
+
+
+@pytest.mark.parametrize("k,case", list(enumerate(PC.random_geometry_cases(48, 20261018, 160, 40))))
+def test_random_geometry_sweep(ectx, oracle, k, case):
+    PC.check_random_case(ectx, oracle, case, 9000 + k)

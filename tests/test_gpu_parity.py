@@ -293,3 +293,12 @@ def test_c5_full_slide_single_call(ctx, oracle):
 
 def test_package_api_x1(ctx, oracle):
     PC.check_package_api_x1(ctx, oracle)
+
+
+def test_random_geometry_sweep(ctx, oracle):
+    """160 seeded random configurations (size, components, depth, sign, levels, wavelet, tiles, HTJ2K, fused shift)."""
+    for k, case in enumerate(PC.random_geometry_cases(160, 20261019, 1100, 300)):
+        try:
+            PC.check_random_case(ctx, oracle, case, 7000 + k)
+        except AssertionError as e:
+            raise AssertionError(f"case {k} {case}: {e}") from e
