@@ -295,3 +295,22 @@ def check_random_case(ctx, oracle, case, seed):
     # raw word), so the reference itself is not an identity there: parity with the oracle is checked, the identity is not
     ident = not (signed and bits not in (8, 16))
     check_pipeline(ctx, oracle, w, h, c, bits, signed, L, rev, tile=tile, htj2k=htj2k, fuse=fuse, kind="noise", seed=seed, identity=ident)
+
+
+def check_inverse_with_offsets(ctx, oracle, w, h, c, bits, L, reversible, xosiz, yosiz, tile=(0, 0), xtosiz=0, ytosiz=0, seed=21):
+    """Decoder-side SIZ geometry with a shifted image / tile grid (tile_assembler.go:33-101, t2/tile_decoder.go:269-294):
+    tile windows start at odd coordinates, so the inverse DWT runs with odd origin parity.  Random coefficient planes in,
+    pixels and planes compared with the oracle."""
+    rng = np.random.default_rng(seed)
+    mct = (abi.MCT_RCT if reversible else abi.MCT_ICT) if c == 3 else abi.MCT_NONE
+    ds = None
+    if not reversible:
+        _, ds = steps_for(oracle, L, bits)
+    ip = abi.inv_params(w, h, c, bits, False, tile[0], tile[1], L, reversible, False, mct, ds,
+                        xosiz=xosiz, yosiz=yosiz, xtosiz=xtosiz, ytosiz=ytosiz)
+    n = w * h * c
+    co = rng.integers(-(1 << (bits + 2)), 1 << (bits + 2), n).astype(np.int32)
+    px, planes = ctx.inverse(ip, co, want_planes=True)
+    opx, oplanes = oracle.inverse(ip, co, want_planes=True)
+    assert np.array_equal(planes, oplanes), "inverse planes with image / tile offsets"
+    assert np.array_equal(px, opx), "inverse pixels with image / tile offsets"

@@ -123,3 +123,11 @@ def test_package_api_x1(ectx, oracle):
 @pytest.mark.parametrize("k,case", list(enumerate(PC.random_geometry_cases(48, 20261018, 160, 40))))
 def test_random_geometry_sweep(ectx, oracle, k, case):
     PC.check_random_case(ectx, oracle, case, 9000 + k)
+
+
+@pytest.mark.parametrize("w,h,c,bits,L,rev,xo,yo,tile,xto,yto", [
+    (64, 48, 1, 8, 3, True, 1, 0, (0, 0), 0, 0), (64, 48, 1, 12, 3, False, 0, 1, (0, 0), 0, 0), (70, 50, 3, 8, 2, True, 1, 2, (32, 32), 1, 1),
+    (70, 50, 3, 8, 2, False, 3, 5, (32, 32), 2, 3), (33, 17, 1, 16, 4, True, 7, 7, (16, 16), 0, 0), (40, 40, 2, 8, 2, False, 5, 2, (0, 0), 0, 0),
+])
+def test_inverse_with_image_and_tile_offsets(ectx, oracle, w, h, c, bits, L, rev, xo, yo, tile, xto, yto):
+    PC.check_inverse_with_offsets(ectx, oracle, w, h, c, bits, L, rev, xo, yo, tile, xto, yto)

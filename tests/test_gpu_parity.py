@@ -296,9 +296,17 @@ def test_package_api_x1(ctx, oracle):
 
 
 def test_random_geometry_sweep(ctx, oracle):
-    """160 seeded random configurations (size, components, depth, sign, levels, wavelet, tiles, HTJ2K, fused shift)."""
-    for k, case in enumerate(PC.random_geometry_cases(160, 20261019, 1100, 300)):
+    """400 seeded random configurations (size, components, depth, sign, levels, wavelet, tiles, HTJ2K, fused shift)."""
+    for k, case in enumerate(PC.random_geometry_cases(400, 20261019, 1100, 300)):
         try:
             PC.check_random_case(ctx, oracle, case, 7000 + k)
         except AssertionError as e:
             raise AssertionError(f"case {k} {case}: {e}") from e
+
+
+@pytest.mark.parametrize("w,h,c,bits,L,rev,xo,yo,tile,xto,yto", [
+    (64, 48, 1, 8, 3, True, 1, 0, (0, 0), 0, 0), (64, 48, 1, 12, 3, False, 0, 1, (0, 0), 0, 0), (70, 50, 3, 8, 2, True, 1, 2, (32, 32), 1, 1),
+    (70, 50, 3, 8, 2, False, 3, 5, (32, 32), 2, 3), (33, 17, 1, 16, 4, True, 7, 7, (16, 16), 0, 0), (40, 40, 2, 8, 2, False, 5, 2, (0, 0), 0, 0),    (640, 480, 1, 12, 5, False, 1, 1, (0, 0), 0, 0), (513, 257, 3, 8, 5, True, 3, 2, (256, 256), 1, 2), (1000, 700, 1, 16, 5, True, 11, 6, (256, 256), 5, 3),
+])
+def test_inverse_with_image_and_tile_offsets(ctx, oracle, w, h, c, bits, L, rev, xo, yo, tile, xto, yto):
+    PC.check_inverse_with_offsets(ctx, oracle, w, h, c, bits, L, rev, xo, yo, tile, xto, yto)
