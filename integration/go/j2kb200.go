@@ -1,0 +1,357 @@
+// Package gpu binds libj2kb200.so (include/j2k_b200.h) into go-dicom-codec.
+//
+// Drop this file at jpeg2000/gpu/j2kb200.go of github.com/cocosip/go-dicom-codec and apply the three call-site changes of
+// INTEGRATION.md section 2.  It was written against the C header; Go is not installed in the image this repository is
+// built in, so it has not been compiled there.  Every C entry point it calls is exercised by tests/ through the Python
+// mirror (go-dicom-codec_b200/j2kb200) and by the plain C caller tests/c/abi_smoke.c.
+package gpu
+
+/*
+#cgo CFLAGS:  -I${SRCDIR}/../../third_party/j2k_b200/include
+#cgo LDFLAGS: -L${SRCDIR}/../../third_party/j2k_b200/lib -lj2kb200 -lcudart
+#include <stdlib.h>
+#include "j2k_b200.h"
+*/
+import "C"
+
+import (
+	"fmt"
+	"sync"
+	"unsafe"
+)
+
+var (
+	once sync.Once
+	ctx  *C.j2k_ctx
+	ierr error
+)
+
+// Init creates the process-wide context over every visible device (frames and tiles are sharded over the GPUs in
+// contiguous blocks; there is no collective).  Safe to call from any goroutine, any number of times.
+func Init() error {
+	once.Do(func() {
+		if rc := C.j2k_init(&ctx, nil, 0); rc != 0 {
+			ierr = fmt.Errorf("j2k_b200: init failed (%d): %s", int(rc), C.GoString(C.j2k_last_error(nil)))
+		}
+	})
+	return ierr
+}
+
+// Shutdown releases the context (streams, device scratch, pinned staging).
+func Shutdown() {
+	if ctx != nil {
+		C.j2k_shutdown(ctx)
+		ctx = nil
+	}
+}
+
+func lastErr(rc C.int) error {
+	return fmt.Errorf("j2k_b200 error %d: %s", int(rc), C.GoString(C.j2k_last_error(ctx)))
+}
+
+// MCT modes (j2k_mct_mode).
+const (
+	MCTNone        = int(C.J2K_MCT_NONE)
+	MCTRCT         = int(C.J2K_MCT_RCT)
+	MCTICT         = int(C.J2K_MCT_ICT)
+	MCTCustomInt   = int(C.J2K_MCT_CUSTOM_INT)
+	MCTCustomQ13   = int(C.J2K_MCT_CUSTOM_Q13)
+	MCTCustomFloat = int(C.J2K_MCT_CUSTOM_FLOAT)
+	MCTBindings    = int(C.J2K_MCT_BINDINGS)
+)
+
+// Binding mirrors jpeg2000.MCTBindingParams (encoder.go:111-121) / the decoder's mctBinding (decoder.go:630-694).
+type Binding struct {
+	ComponentIDs []int
+	ElementType  int       // encode: 0 = integer matrix, else Q13; decode: 0 = integer, else float64
+	Matrix       []float64 // row-major n x n, nil = identity (encode) / skipped (decode)
+	Offsets      []int32
+}
+
+func (b *Binding) c() C.j2k_mct_binding {
+	var c C.j2k_mct_binding
+	c.n_components = C.int32_t(len(b.ComponentIDs))
+	for i, id := range b.ComponentIDs {
+		c.component_ids[i] = C.int32_t(id)
+	}
+	c.element_type = C.int32_t(b.ElementType)
+	if b.Matrix != nil {
+		c.has_matrix = 1
+		for i, v := range b.Matrix {
+			c.matrix[i] = C.double(v)
+		}
+	}
+	if b.Offsets != nil {
+		c.has_offsets = 1
+		for i, v := range b.Offsets {
+			c.offsets[i] = C.int32_t(v)
+		}
+	}
+	return c
+}
+
+// FwdParams mirrors the fields of jpeg2000.EncodeParams the sample path reads (encoder.go:17-98).
+type FwdParams struct {
+	Width, Height, Components, BitDepth int
+	IsSigned                            bool
+	TileWidth, TileHeight, NumLevels    int
+	Lossless, HTJ2K                     bool
+	MCTMode                             int
+	MCTMatrix                           []float64 // custom modes: row-major C x C (EncodeParams.MCTMatrix)
+	MCTOffsets                          []int32
+	Bindings                            []Binding
+	Steps                               []float64 // OpenJPEGRuntimeQuantizationSteps(...), nil when Lossless
+	FuseT1Shift                         bool      // classic EBCOT lossless without ROI only
+}
+
+func (p *FwdParams) c() C.j2k_fwd_params {
+	var c C.j2k_fwd_params
+	c.width, c.height, c.components = C.int32_t(p.Width), C.int32_t(p.Height), C.int32_t(p.Components)
+	c.bit_depth = C.int32_t(p.BitDepth)
+	if p.IsSigned {
+		c.is_signed = 1
+	}
+	c.tile_width, c.tile_height, c.num_levels = C.int32_t(p.TileWidth), C.int32_t(p.TileHeight), C.int32_t(p.NumLevels)
+	if p.Lossless {
+		c.reversible = 1
+	}
+	if p.HTJ2K {
+		c.htj2k = 1
+	}
+	c.mct_mode = C.int32_t(p.MCTMode)
+	for i, v := range p.MCTMatrix {
+		c.mct_matrix[i] = C.double(v)
+	}
+	if len(p.MCTOffsets) == p.Components && p.Components > 0 {
+		c.mct_has_offsets = 1
+		for i, v := range p.MCTOffsets {
+			c.mct_offsets[i] = C.int32_t(v)
+		}
+	}
+	c.n_bindings = C.int32_t(len(p.Bindings))
+	for i := range p.Bindings {
+		c.bindings[i] = p.Bindings[i].c()
+	}
+	c.n_steps = C.int32_t(len(p.Steps))
+	for i, s := range p.Steps {
+		c.steps[i] = C.double(s)
+	}
+	if p.FuseT1Shift {
+		c.fuse_t1_shift = 1
+	}
+	return c
+}
+
+// InvParams carries what TileDecoder / Decoder read from SIZ, COD and QCD (t2/tile_decoder.go:269-294,886-987,
+// decoder.go:143-144,588,620-735).
+type InvParams struct {
+	Xsiz, Ysiz, XOsiz, YOsiz, XTsiz, YTsiz, XTOsiz, YTOsiz int
+	Components, BitDepth                                  int
+	IsSigned                                              bool
+	NumLevels                                             int
+	Reversible, HTJ2K                                     bool      // COD transformation == 1; code-block style bit 0x40
+	Steps                                                 []float64 // decodeQuantizationSteps(...) incl. the 0.5 / 1.0 factor
+	MCTMode                                               int
+	MCTMatrix                                             []float64
+	MCTOffsets                                            []int32
+	Bindings                                              []Binding
+	FuseT1Halve                                           bool
+}
+
+func (p *InvParams) c() C.j2k_inv_params {
+	var c C.j2k_inv_params
+	c.xsiz, c.ysiz, c.xosiz, c.yosiz = C.int32_t(p.Xsiz), C.int32_t(p.Ysiz), C.int32_t(p.XOsiz), C.int32_t(p.YOsiz)
+	c.xtsiz, c.ytsiz, c.xtosiz, c.ytosiz = C.int32_t(p.XTsiz), C.int32_t(p.YTsiz), C.int32_t(p.XTOsiz), C.int32_t(p.YTOsiz)
+	c.components, c.bit_depth, c.num_levels = C.int32_t(p.Components), C.int32_t(p.BitDepth), C.int32_t(p.NumLevels)
+	if p.IsSigned {
+		c.is_signed = 1
+	}
+	if p.Reversible {
+		c.reversible = 1
+	}
+	if p.HTJ2K {
+		c.htj2k = 1
+	}
+	c.n_steps = C.int32_t(len(p.Steps))
+	for i, s := range p.Steps {
+		c.steps[i] = C.double(s)
+	}
+	c.mct_mode = C.int32_t(p.MCTMode)
+	for i, v := range p.MCTMatrix {
+		c.mct_matrix[i] = C.double(v)
+	}
+	if len(p.MCTOffsets) == p.Components && p.Components > 0 {
+		c.mct_has_offsets = 1
+		for i, v := range p.MCTOffsets {
+			c.mct_offsets[i] = C.int32_t(v)
+		}
+	}
+	c.n_bindings = C.int32_t(len(p.Bindings))
+	for i := range p.Bindings {
+		c.bindings[i] = p.Bindings[i].c()
+	}
+	if p.FuseT1Halve {
+		c.fuse_t1_halve = 1
+	}
+	return c
+}
+
+// CoeffCount / PixelBytes size the caller's buffers.
+func (p *FwdParams) CoeffCount() int { cp := p.c(); return int(C.j2k_fwd_coeff_count(&cp)) }
+func (p *FwdParams) PixelBytes() int { cp := p.c(); return int(C.j2k_fwd_pixel_bytes(&cp)) }
+func (p *InvParams) CoeffCount() int { cp := p.c(); return int(C.j2k_inv_coeff_count(&cp)) }
+func (p *InvParams) PixelBytes() int { cp := p.c(); return int(C.j2k_inv_pixel_bytes(&cp)) }
+
+// Forward: one frame, interleaved pixel bytes in, all tiles' coefficient planes out (tile-major, component-major,
+// row-major, stride = tile width) - what transformTile returns for every tile.  The C side copies out of / into the Go
+// slices before it returns: no Go pointer is retained (cgo rule).
+func Forward(p *FwdParams, pixels []byte, coeffs []int32) error {
+	cp := p.c()
+	rc := C.j2k_forward(ctx, &cp, unsafe.Pointer(&pixels[0]), C.size_t(len(pixels)),
+		(*C.int32_t)(unsafe.Pointer(&coeffs[0])), C.size_t(len(coeffs)))
+	if rc != 0 {
+		return lastErr(rc)
+	}
+	return nil
+}
+
+// ForwardBatch: nframes contiguous frames sharing one parameter set (the adapters' frame loops).
+func ForwardBatch(p *FwdParams, nframes int, pixels []byte, frameStride int, coeffs []int32) error {
+	cp := p.c()
+	rc := C.j2k_forward_batch(ctx, &cp, C.int(nframes), unsafe.Pointer(&pixels[0]), C.size_t(frameStride),
+		(*C.int32_t)(unsafe.Pointer(&coeffs[0])))
+	if rc != 0 {
+		return lastErr(rc)
+	}
+	return nil
+}
+
+// Inverse: every tile-component's coefficient plane in (after assembleSubbands), packed pixel bytes out; planes, when
+// non-nil, receives Decoder.GetImageData() (Components planes of Width*Height int32).
+func Inverse(p *InvParams, coeffs []int32, pixels []byte, planes []int32) error {
+	cp := p.c()
+	var pl *C.int32_t
+	if planes != nil {
+		pl = (*C.int32_t)(unsafe.Pointer(&planes[0]))
+	}
+	rc := C.j2k_inverse(ctx, &cp, (*C.int32_t)(unsafe.Pointer(&coeffs[0])), C.size_t(len(coeffs)),
+		unsafe.Pointer(&pixels[0]), C.size_t(len(pixels)), pl)
+	if rc != 0 {
+		return lastErr(rc)
+	}
+	return nil
+}
+
+// InverseBatch: nframes frames, coefficient planes and pixel frames contiguous.
+func InverseBatch(p *InvParams, nframes int, coeffs []int32, pixels []byte, frameStride int) error {
+	cp := p.c()
+	rc := C.j2k_inverse_batch(ctx, &cp, C.int(nframes), (*C.int32_t)(unsafe.Pointer(&coeffs[0])),
+		unsafe.Pointer(&pixels[0]), C.size_t(frameStride), nil)
+	if rc != 0 {
+		return lastErr(rc)
+	}
+	return nil
+}
+
+// ---- asynchronous: pinned buffers owned by the library, tickets (INTEGRATION.md 2.3)
+
+// PinnedBytes / PinnedInt32 wrap a page-locked buffer from j2k_acquire_buffer; Release gives it back.
+func PinnedBytes(n int) ([]byte, error) {
+	p := C.j2k_acquire_buffer(ctx, C.size_t(n))
+	if p == nil {
+		return nil, lastErr(C.int(C.J2K_ERR_NOMEM))
+	}
+	return unsafe.Slice((*byte)(p), n), nil
+}
+
+func PinnedInt32(n int) ([]int32, error) {
+	p := C.j2k_acquire_buffer(ctx, C.size_t(n)*4)
+	if p == nil {
+		return nil, lastErr(C.int(C.J2K_ERR_NOMEM))
+	}
+	return unsafe.Slice((*int32)(p), n), nil
+}
+
+func ReleaseBytes(b []byte)   { C.j2k_release_buffer(ctx, unsafe.Pointer(&b[0])) }
+func ReleaseInt32(b []int32)  { C.j2k_release_buffer(ctx, unsafe.Pointer(&b[0])) }
+
+// Ticket identifies a submitted batch; it completes when that batch's last device-to-host copy has landed.
+type Ticket int64
+
+// SubmitForward enqueues nframes frames and returns at once.  pixels and coeffs MUST be pinned buffers from this
+// package and stay untouched until Wait returns.
+func SubmitForward(p *FwdParams, nframes int, pixels []byte, frameStride int, coeffs []int32) (Ticket, error) {
+	cp := p.c()
+	t := C.j2k_submit_forward(ctx, &cp, C.int(nframes), unsafe.Pointer(&pixels[0]), C.size_t(frameStride),
+		(*C.int32_t)(unsafe.Pointer(&coeffs[0])))
+	if t < 0 {
+		return 0, lastErr(C.int(t))
+	}
+	return Ticket(t), nil
+}
+
+func SubmitInverse(p *InvParams, nframes int, coeffs []int32, pixels []byte, frameStride int) (Ticket, error) {
+	cp := p.c()
+	t := C.j2k_submit_inverse(ctx, &cp, C.int(nframes), (*C.int32_t)(unsafe.Pointer(&coeffs[0])),
+		unsafe.Pointer(&pixels[0]), C.size_t(frameStride), nil)
+	if t < 0 {
+		return 0, lastErr(C.int(t))
+	}
+	return Ticket(t), nil
+}
+
+func Wait(t Ticket) error {
+	if rc := C.j2k_wait(ctx, C.int64_t(t)); rc != 0 {
+		return lastErr(rc)
+	}
+	return nil
+}
+
+// ---- code-block interface (INTEGRATION.md 2.4)
+
+// CodeBlock mirrors codeBlockInfo's geometry (encoder.go:3199-3212) plus the block's offset in the block-major plane.
+type CodeBlock struct {
+	X0, Y0, Width, Height, CBX, CBY, Band, Res int
+	Offset                                     int64
+}
+
+// CodeBlockLayout returns the blocks of one tile-component plane in the order buildTilePacketEncoder walks them.
+func CodeBlockLayout(width, height, numLevels, cbWidth, cbHeight int) ([]CodeBlock, error) {
+	n := C.j2k_codeblock_layout(C.int(width), C.int(height), C.int(numLevels), C.int(cbWidth), C.int(cbHeight), nil, 0)
+	if n < 0 {
+		return nil, lastErr(n)
+	}
+	if n == 0 {
+		return nil, nil
+	}
+	raw := make([]C.j2k_cblk, int(n))
+	C.j2k_codeblock_layout(C.int(width), C.int(height), C.int(numLevels), C.int(cbWidth), C.int(cbHeight), &raw[0], n)
+	out := make([]CodeBlock, int(n))
+	for i, b := range raw {
+		out[i] = CodeBlock{int(b.x0), int(b.y0), int(b.width), int(b.height), int(b.cbx), int(b.cby), int(b.band), int(b.res), int64(b.offset)}
+	}
+	return out, nil
+}
+
+// ForwardBlocks: like ForwardBatch, but the coefficients arrive partitioned into code-blocks (each contiguous, the T1
+// shift applied) together with cblkNumbps per block.
+func ForwardBlocks(p *FwdParams, cbWidth, cbHeight, nframes int, pixels []byte, frameStride int, blocks []int32, numbps []int32) error {
+	cp := p.c()
+	rc := C.j2k_forward_blocks(ctx, &cp, C.int(cbWidth), C.int(cbHeight), C.int(nframes), unsafe.Pointer(&pixels[0]),
+		C.size_t(frameStride), (*C.int32_t)(unsafe.Pointer(&blocks[0])), (*C.int32_t)(unsafe.Pointer(&numbps[0])))
+	if rc != 0 {
+		return lastErr(rc)
+	}
+	return nil
+}
+
+// InverseBlocks: the decode mirror; blocks holds every code-block's T1 output at CodeBlock.Offset.
+func InverseBlocks(p *InvParams, cbWidth, cbHeight, nframes int, blocks []int32, pixels []byte, frameStride int) error {
+	cp := p.c()
+	rc := C.j2k_inverse_blocks(ctx, &cp, C.int(cbWidth), C.int(cbHeight), C.int(nframes), (*C.int32_t)(unsafe.Pointer(&blocks[0])),
+		unsafe.Pointer(&pixels[0]), C.size_t(frameStride), nil)
+	if rc != 0 {
+		return lastErr(rc)
+	}
+	return nil
+}

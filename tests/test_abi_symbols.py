@@ -53,3 +53,17 @@ def test_product_sources_never_load_the_oracle():
                 text = open(os.path.join(d, f), errors="ignore").read()
                 hits = [b for b in banned if b in text]
                 assert not hits, f"{f} references the oracle: {hits}"
+
+
+def test_header_compiles_as_c_and_a_c_program_round_trips(tmp_path):
+    """tests/c/abi_smoke.c: a plain C caller (gcc -std=c99) linked against the CPU-emulator flavour of the library."""
+    import subprocess
+    import emu_lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = emu_lib.build()
+    exe = str(tmp_path / "abi_smoke")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), "-o", exe,
+                           os.path.join(root, "tests", "c", "abi_smoke.c"), lib, "-Wl,-rpath," + os.path.dirname(lib)])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert "c abi ok" in out.stdout
