@@ -34,6 +34,9 @@ namespace j2k {
 #define J2K_RING_BYTES 12800  // staging bytes per warp: 5 stages of four 544 B rows (u16), 3 stages of four 1056 B rows (float32)
 #endif
 #define J2K_RING_MAXD 8
+#ifndef J2K_RGB_SINGLE_BODY
+#define J2K_RGB_SINGLE_BODY 1
+#endif
 #ifndef J2K_RING_MINB
 #define J2K_RING_MINB 3      // resident CTAs per SM the register allocation targets (168 registers: no spills in the 9/7 loop)
 #endif
@@ -671,6 +674,15 @@ struct FwdRing {
                 p_ll += rs_ll; p_hl += rs_b; p_lh += rs_b; p_hh += rs_b;
             };
             // two iterations per trip with the window state ping-ponging between sa and sb: no register shuffling
+            if constexpr (NC == 3 && WT == 97 && J2K_RGB_SINGLE_BODY) {
+                // three 9/7 components: ONE copy of the body and a state move per iteration -- the two-copy form of these
+                // variants is ~60 KB of code and misses the instruction cache (stall_no_inst 11 % -> +15 % on C3 / C5)
+#pragma unroll 1
+                for (int it = 0; it < n_it; it++) {
+                    body(it, RPS == 1 ? 0 : (it & 1), sa, sb);
+                    sa = sb;
+                }
+            } else
 #pragma unroll 1
             for (int it = 0; it < n_it; it += 2) {
                 body(it, 0, sa, sb);
@@ -727,6 +739,15 @@ struct FwdRing {
                 }
                 p_ll += rs_ll; p_hl += rs_b; p_lh += rs_b; p_hh += rs_b;
             };
+            if constexpr (NC == 3 && WT == 97 && J2K_RGB_SINGLE_BODY) {
+                // three 9/7 components: ONE copy of the body and a state move per iteration -- the two-copy form of these
+                // variants is ~60 KB of code and misses the instruction cache (stall_no_inst 11 % -> +15 % on C3 / C5)
+#pragma unroll 1
+                for (int it = 0; it < n_it; it++) {
+                    body(it, RPS == 1 ? 0 : (it & 1), sa, sb);
+                    sa = sb;
+                }
+            } else
 #pragma unroll 1
             for (int it = 0; it < n_it; it += 2) {
                 body(it, 0, sa, sb);
@@ -1228,6 +1249,15 @@ struct InvRing {
                     }
                 }
             };
+            if constexpr (NC == 3 && WT == 97 && J2K_RGB_SINGLE_BODY) {
+                // three 9/7 components: ONE copy of the body and a state move per iteration -- the two-copy form of these
+                // variants is ~60 KB of code and misses the instruction cache (stall_no_inst 11 % -> +15 % on C3 / C5)
+#pragma unroll 1
+                for (int it = 0; it < n_it; it++) {
+                    body(it, RPS == 1 ? 0 : (it & 1), sa, sb);
+                    sa = sb;
+                }
+            } else
 #pragma unroll 1
             for (int it = 0; it < n_it; it += 2) {
                 body(it, 0, sa, sb);
@@ -1322,6 +1352,15 @@ struct InvRing {
                     if (ro < h) store_planar((int*)(xrow + xpitch), xo[0]);
                 }
             };
+            if constexpr (NC == 3 && WT == 97 && J2K_RGB_SINGLE_BODY) {
+                // three 9/7 components: ONE copy of the body and a state move per iteration -- the two-copy form of these
+                // variants is ~60 KB of code and misses the instruction cache (stall_no_inst 11 % -> +15 % on C3 / C5)
+#pragma unroll 1
+                for (int it = 0; it < n_it; it++) {
+                    body(it, RPS == 1 ? 0 : (it & 1), sa, sb);
+                    sa = sb;
+                }
+            } else
 #pragma unroll 1
             for (int it = 0; it < n_it; it += 2) {
                 body(it, 0, sa, sb);
@@ -1342,7 +1381,10 @@ __global__ void __launch_bounds__(J2K_RING_WARPS * 32, J2K_RING_MINB) inv_ring_k
     ring_warp_init(smem, rw, lane, J2K_INV_RING_BYTES);
     rw.one = A.one;
     RingJob J;
-    while (ring_claim<false>(A, lane, J)) {  // per-warp: this direction is bound by its arithmetic, not by the store pattern
+    #ifndef J2K_INV_CTA_CLAIM
+#define J2K_INV_CTA_CLAIM 0
+#endif
+    while (ring_claim<(J2K_INV_CTA_CLAIM != 0)>(A, lane, J)) {
         const RingSeg& S = A.seg[J.seg];
         ring_wait_dep(A, S, J.item, lane);
         if (S.first) InvRing<WT, NP1, NC1, OUT1, MCT1>::run(S, A.raw, J.item, J.chunk, J.strip, rw, lane);
