@@ -533,9 +533,90 @@ bool ring_variant_supported(int WT, int NP, int NC, int IN, int MCT, int SG) {
     return IN == IN_I32 || (IN == IN_F32 && WT == 97);
 }
 
+// Job order of the persistent launch.  The plain list is level-major: every item finishes level k before any job of
+// level k+1 is claimed, so an intermediate LL plane has long left the 126 MB L2 when its consumer reads it.  When the
+// segments form one dependency chain (one tile class) the list is cut into slices instead: items are taken in groups of
+// ~J2K_RING_GROUP_KS Ki samples, and the slice (level k, group g) is placed at tick g + k * lag, i.e. `lag` groups of
+// level-1 work behind the slice that produces its input — far enough that the producers have retired when it is
+// claimed (no warp parks on a dependency), close enough that the LL plane is still resident in L2.  A slice's producer
+// always precedes it in the list, so the in-order claiming argument (no co-residency requirement) is unchanged.
+// Allocates and zeroes the control block; the slice table lives behind the counters.
+int ring_schedule(RingPlan& R, Plan& P, int n_ctl) {
+    RingArgs& A = R.args;
+    std::vector<int> begin, info;
+    const int lag = env_int("J2K_RING_LAG", J2K_RING_DEFAULT_LAG);
+    bool chain = A.nseg >= 2 && lag > 0;
+    int base = 0x7fffffff;
+    for (int k = 0; k < A.nseg; k++) base = A.seg[k].n_items < base ? A.seg[k].n_items : base;
+    for (int k = 0; k < A.nseg && chain; k++)
+        if (base < 1 || A.seg[k].n_items % base || A.seg[k].dep_seg != k - 1) chain = false;
+    if (chain) {
+        long long big = 1;  // samples one base item (a frame / tile with all its components) holds at the largest level
+        for (int k = 0; k < A.nseg; k++) {
+            long long sz = (long long)A.seg[k].w * A.seg[k].h * (A.seg[k].n_items / base) * (A.seg[k].first && R.NC1 == 3 && R.NP1 == 2 ? 3 : 1);
+            big = sz > big ? sz : big;
+        }
+        const long long target = (long long)env_int("J2K_RING_GROUP_KS", J2K_RING_DEFAULT_GROUP_KS) * 1024;
+        long long G = target / big;
+        if (G < 1) G = 1;
+        const long long max_groups = J2K_RING_MAXSLICE / A.nseg;
+        if ((base + G - 1) / G > max_groups) G = (base + max_groups - 1) / max_groups;
+        const int NG = (int)((base + G - 1) / G);
+        if (NG > lag) {  // fewer groups than the lag: nothing to pipeline
+            long long jobs = 0;
+            for (int t = 0; t < NG + (A.nseg - 1) * lag; t++)
+                for (int k = A.nseg - 1; k >= 0; k--) {
+                    const int g = t - k * lag;
+                    if (g < 0 || g >= NG) continue;
+                    const long long ratio = A.seg[k].n_items / base;
+                    const long long i0 = g * G * ratio, i1 = ((g + 1) * G < base ? (g + 1) * G : base) * ratio;
+                    begin.push_back((int)jobs);
+                    info.push_back(k); info.push_back((int)i0);
+                    jobs += (i1 - i0) * A.seg[k].nchunks * A.seg[k].nstrips;
+                }
+            if (jobs != A.total_jobs) return fail(J2K_ERR_INVALID_ARG, "ring schedule: %lld jobs in slices, %d in segments", jobs, A.total_jobs);
+        }
+    }
+    // L2 policies: whatever is read once or written for the host leaves L2 first; the intermediate LL planes stay
+    {
+        static const unsigned long long pol[3] = {J2K_L2_EVICT_NORMAL, J2K_L2_EVICT_FIRST, J2K_L2_EVICT_LAST};
+        const int on = !begin.empty();
+        const int p_in = env_int("J2K_RING_POL_IN", on ? 1 : 0) % 3, p_llr = env_int("J2K_RING_POL_LLR", 0) % 3;
+        const int p_llw = env_int("J2K_RING_POL_LLW", on ? 2 : 0) % 3, p_band = env_int("J2K_RING_POL_BAND", on ? 1 : 0) % 3;
+        for (int k = 0; k < A.nseg; k++) {
+            RingSeg& g = A.seg[k];
+            if (P.fwd) {
+                g.pol_load = pol[g.first ? p_in : p_llr];
+                g.pol_ll = pol[g.has_waiters ? p_llw : p_band];
+                g.pol_band = pol[p_band];
+            } else {
+                g.pol_load = pol[p_in];
+                g.pol_ll = pol[p_llr];
+                g.pol_band = pol[g.has_waiters ? p_llw : p_band];
+            }
+        }
+    }
+    const size_t ctl_ints = ((size_t)n_ctl + 3) / 4 * 4, nb = (begin.size() + 1) / 2 * 2;
+    int rc = P.ctl.ensure((ctl_ints + nb + info.size()) * sizeof(unsigned));
+    if (rc) return rc;
+    CK(cudaMemset(P.ctl.p, 0, (size_t)n_ctl * sizeof(unsigned)));
+    A.ctl = (unsigned*)P.ctl.p;
+    A.nslice = (int)begin.size();
+    A.slice_begin = nullptr; A.slice_info = nullptr;
+    if (A.nslice) {
+        int* tb = (int*)P.ctl.p + ctl_ints;
+        CK(cudaMemcpy(tb, begin.data(), begin.size() * sizeof(int), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(tb + nb, info.data(), info.size() * sizeof(int), cudaMemcpyHostToDevice));
+        A.slice_begin = tb;
+        A.slice_info = (const int2*)(tb + nb);
+    }
+    return 0;
+}
+
 // Converts the per-level launch list into ONE persistent launch when every level qualifies; otherwise P.ring.ok stays false
 // and run_plan uses the per-level kernels.
 int build_ring_fwd_impl(const Spec& s, Plan& P, const std::vector<long long>& tab, bool split3, int cut);
+int ring_schedule(RingPlan& R, Plan& P, int n_ctl);
 
 // The persistent launch takes levels 1..cut, the largest cut whose levels all have the geometry it needs (window widths
 // that are multiples of 8, 16-byte aligned rows); deeper levels, which hold 1/4^cut of the samples, stay on the per-level
@@ -658,10 +739,8 @@ int build_ring_fwd_impl(const Spec& s, Plan& P, const std::vector<long long>& ta
     R.args.n_ctl = n_ctl;
     R.args.raw = P.raw;
     R.args.one = 1.0f;
-    int rc = P.ctl.ensure((size_t)n_ctl * sizeof(unsigned));
+    int rc = ring_schedule(R, P, n_ctl);
     if (rc) return rc;
-    CK(cudaMemset(P.ctl.p, 0, (size_t)n_ctl * sizeof(unsigned)));
-    R.args.ctl = (unsigned*)P.ctl.p;
     R.ok = true;
     return 0;
 }
@@ -829,10 +908,8 @@ int build_ring_inv_impl(const Spec& s, Plan& P, const std::vector<long long>& ta
     R.args.n_ctl = n_ctl;
     R.args.raw = P.raw;
     R.args.one = 1.0f;
-    int rc = P.ctl.ensure((size_t)n_ctl * sizeof(unsigned));
+    int rc = ring_schedule(R, P, n_ctl);
     if (rc) return rc;
-    CK(cudaMemset(P.ctl.p, 0, (size_t)n_ctl * sizeof(unsigned)));
-    R.args.ctl = (unsigned*)P.ctl.p;
     R.ok = true;
     return 0;
 }
@@ -1292,8 +1369,8 @@ int run_plan(j2k_ctx* ctx, Plan& P, void* pixels, void* coeffs, void* planes, bo
         static const bool dry = env_int("J2K_RING_DRY", 0) != 0;  // diagnostic: launch overhead only (no job is claimed)
         if (dry) A.total_jobs = 0;
         if (trace)
-            fprintf(stderr, "[j2k] %s ring WT=%d NP=%d NC=%d kind=%d mct=%d sg=%d segs=%d jobs=%d grid=%u\n", P.fwd ? "fwd" : "inv", R.WT, R.NP1, R.NC1,
-                    R.IN1, R.MCT1, R.SG1, A.nseg, A.total_jobs, R.grid);
+            fprintf(stderr, "[j2k] %s ring WT=%d NP=%d NC=%d kind=%d mct=%d sg=%d segs=%d jobs=%d slices=%d grid=%u\n", P.fwd ? "fwd" : "inv", R.WT, R.NP1, R.NC1,
+                    R.IN1, R.MCT1, R.SG1, A.nseg, A.total_jobs, A.nslice, R.grid);
         if (!per_level) {
             unsigned grid = R.grid;
             unsigned need = (unsigned)((A.total_jobs + J2K_RING_WARPS - 1) / J2K_RING_WARPS);
@@ -1313,6 +1390,7 @@ int run_plan(j2k_ctx* ctx, Plan& P, void* pixels, void* coeffs, void* planes, bo
                 while (j < A.nseg && R.level[j] == R.level[i]) j++;
                 RingArgs B = A;
                 B.nseg = j - i;
+                B.nslice = 0;
                 int base = A.seg[i].job_begin;
                 for (int k = i; k < j; k++) {
                     B.seg[k - i] = A.seg[k];

@@ -34,6 +34,14 @@ namespace j2k {
 #define J2K_RING_BYTES 12800  // staging bytes per warp: 5 stages of four 544 B rows (u16), 3 stages of four 1056 B rows (float32)
 #endif
 #define J2K_RING_MAXD 8
+#ifndef J2K_RING_L2_HINTS
+#define J2K_RING_L2_HINTS 0  // 1: L2 eviction-priority policies on the staged loads and the band stores of the forward kernel
+#endif
+#if J2K_RING_L2_HINTS
+#define J2K_POL_ARG(p) , p
+#else
+#define J2K_POL_ARG(p)
+#endif
 #ifndef J2K_RGB_SINGLE_BODY
 #define J2K_RGB_SINGLE_BODY 1
 #endif
@@ -73,16 +81,33 @@ struct RingSeg {
     long long planes_comp_stride;
     int planes_row_stride;
     int pad2_;
+    // L2 eviction-priority policies (createpolicy encodings): staged loads, LL stores, detail-band / pixel stores
+    unsigned long long pol_load, pol_ll, pol_band;
 };
+#define J2K_L2_EVICT_NORMAL 0x1000000000000000ull
+#define J2K_L2_EVICT_FIRST 0x12F0000000000000ull
+#define J2K_L2_EVICT_LAST 0x14F0000000000000ull
 
 struct RingArgs {
     int nseg, total_jobs;
     unsigned* ctl;  // [0] job counter, [1] retired-warp counter, [2..] per-(segment,item) completion counters
     int n_ctl;      // entries of ctl (for the self-reset at kernel end)
     float one;      // 1.0f, opaque to the compiler (see addp2 in j2k_ring.cuh)
+    // Group-pipelined job order (0 slices: the plain level-major list).  Slice s covers jobs [slice_begin[s],
+    // slice_begin[s+1]) = the jobs of segment slice_info[s].x for the items starting at slice_info[s].y.
+    int nslice;
+    const int* slice_begin;
+    const int2* slice_info;
     RawFmt raw;
     RingSeg seg[J2K_RING_MAXSEG];
 };
+#define J2K_RING_MAXSLICE 256
+#ifndef J2K_RING_DEFAULT_LAG
+#define J2K_RING_DEFAULT_LAG 0          // groups of level-1 work between a slice and its consumer (0: level-major list)
+#endif
+#ifndef J2K_RING_DEFAULT_GROUP_KS
+#define J2K_RING_DEFAULT_GROUP_KS 16384  // group size in Ki samples of the largest level (one 4096 x 4096 frame)
+#endif
 
 // ------------------------------------------------------------------ async-copy / barrier primitives
 
@@ -95,7 +120,8 @@ __device__ __forceinline__ void mbar_init(smem_t, int) {}
 __device__ __forceinline__ void mbar_fence_init() {}
 __device__ __forceinline__ void mbar_expect_tx(smem_t, unsigned) {}
 __device__ __forceinline__ void mbar_wait(smem_t, unsigned) {}
-__device__ __forceinline__ void bulk_g2s(smem_t dst, const void* src, unsigned bytes, smem_t) { memcpy(dst, src, bytes); }
+__device__ __forceinline__ void bulk_g2s(smem_t dst, const void* src, unsigned bytes, smem_t, unsigned long long = 0) { memcpy(dst, src, bytes); }
+__device__ __forceinline__ void stg128_hint(int* p, int a, int b, int c, int d, unsigned long long) { p[0] = a; p[1] = b; p[2] = c; p[3] = d; }
 __device__ __forceinline__ void fence_proxy_async() {}
 __device__ __forceinline__ unsigned ld_relaxed(const unsigned* p) { return *p; }
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) { return *p; }
@@ -140,6 +166,15 @@ __device__ __forceinline__ void bulk_g2s(smem_t dst, const void* src, unsigned b
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
                  "r"(bytes), "r"(bar)
                  : "memory");
+}
+// the same with an L2 eviction-priority policy
+__device__ __forceinline__ void bulk_g2s(smem_t dst, const void* src, unsigned bytes, smem_t bar, unsigned long long pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void stg128_hint(int* p, int a, int b, int c, int d, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ unsigned ld_relaxed(const unsigned* p) {
@@ -461,7 +496,11 @@ struct FwdRing {
         }
     }
 
-    static __device__ __forceinline__ void store_vec(int* p, const int (&o)[NP]) {
+    static __device__ __forceinline__ void store_vec(int* p, const int (&o)[NP], unsigned long long pol) {
+#if J2K_RING_L2_HINTS
+        if constexpr (NP == 4) { stg128_hint(p, o[0], o[1], o[2], o[3], pol); return; }
+#endif
+        (void)pol;
         if constexpr (NP == 4) *(int4*)p = make_int4(o[0], o[1], o[2], o[3]);
         else if constexpr (NP == 2) *(int2*)p = make_int2(o[0], o[1]);
         else *p = o[0];
@@ -488,6 +527,8 @@ struct FwdRing {
         // the window width is a multiple of 2 NP on this path: a lane stores whole vectors or nothing
         const bool st = lane >= HLN && kx0 < kxe && kx0 + NP <= hw;
 
+        const unsigned long long pol_load = S.pol_load, pol_ll = S.pol_ll, pol_band = S.pol_band;
+        (void)pol_load; (void)pol_ll; (void)pol_band;
         const int dc = S.dc;
         const float fmagic = 8388608.0f + (float)dc;
         const float one = rw.one;
@@ -532,11 +573,11 @@ struct FwdRing {
                 mbar_expect_tx(bar, 2 * RPS * copy_bytes);
                 if (pj >= s_lo && pj < s_hi) {
 #pragma unroll
-                    for (int k = 0; k < 2 * RPS; k++) bulk_g2s(dst + k * ROWB, psrc + k * pitch, copy_bytes, bar);
+                    for (int k = 0; k < 2 * RPS; k++) bulk_g2s(dst + k * ROWB, psrc + k * pitch, copy_bytes, bar J2K_POL_ARG(pol_load));
                 } else {
                     const int r0 = r_begin + 2 * RPS * pj;
 #pragma unroll
-                    for (int k = 0; k < 2 * RPS; k++) bulk_g2s(dst + k * ROWB, src + (long long)mirror_fast(r0 + k, h) * pitch, copy_bytes, bar);
+                    for (int k = 0; k < 2 * RPS; k++) bulk_g2s(dst + k * ROWB, src + (long long)mirror_fast(r0 + k, h) * pitch, copy_bytes, bar J2K_POL_ARG(pol_load));
                 }
             }
             pj++;
@@ -663,12 +704,12 @@ struct FwdRing {
                         }
                     }
                     if (row_l) {
-                        store_vec(p_ll + c * cs_ll, q_ll);
-                        store_vec(p_hl + c * cs_b, q_hl);
+                        store_vec(p_ll + c * cs_ll, q_ll, pol_ll);
+                        store_vec(p_hl + c * cs_b, q_hl, pol_band);
                     }
                     if (row_h) {
-                        store_vec(p_lh + c * cs_b, q_lh);
-                        store_vec(p_hh + c * cs_b, q_hh);
+                        store_vec(p_lh + c * cs_b, q_lh, pol_band);
+                        store_vec(p_hh + c * cs_b, q_hh, pol_band);
                     }
                 }
                 p_ll += rs_ll; p_hl += rs_b; p_lh += rs_b; p_hh += rs_b;
@@ -727,14 +768,14 @@ struct FwdRing {
                     if (row_l) {
 #pragma unroll
                         for (int j = 0; j < NP; j++) { q_a[j] = (int)((unsigned)lo[c][2 * j] << sh_ll); q_b[j] = (int)((unsigned)lo[c][2 * j + 1] << sh_hl); }
-                        store_vec(p_ll + c * cs_ll, q_a);
-                        store_vec(p_hl + c * cs_b, q_b);
+                        store_vec(p_ll + c * cs_ll, q_a, pol_ll);
+                        store_vec(p_hl + c * cs_b, q_b, pol_band);
                     }
                     if (row_h) {
 #pragma unroll
                         for (int j = 0; j < NP; j++) { q_a[j] = (int)((unsigned)hi[c][2 * j] << sh_lh); q_b[j] = (int)((unsigned)hi[c][2 * j + 1] << sh_hh); }
-                        store_vec(p_lh + c * cs_b, q_a);
-                        store_vec(p_hh + c * cs_b, q_b);
+                        store_vec(p_lh + c * cs_b, q_a, pol_band);
+                        store_vec(p_hh + c * cs_b, q_b, pol_band);
                     }
                 }
                 p_ll += rs_ll; p_hl += rs_b; p_lh += rs_b; p_hh += rs_b;
@@ -771,8 +812,18 @@ struct RingJob { int seg, item, chunk, strip; };
 #ifndef J2K_RING_CTA_CLAIM
 #define J2K_RING_CTA_CLAIM 1
 #endif
+// Slice starts of the group-pipelined order, staged in shared memory once per CTA (the emulator reads them in place).
+#ifdef J2K_EMU
+#define J2K_RING_SCHED_DECL(A, name) const int* name = (A).slice_begin
+#else
+#define J2K_RING_SCHED_DECL(A, name)                                                              \
+    __shared__ int name##_s[J2K_RING_MAXSLICE];                                                   \
+    for (int i_ = (int)threadIdx.x; i_ < (A).nslice; i_ += (int)blockDim.x) name##_s[i_] = (A).slice_begin[i_]; \
+    __syncthreads();                                                                              \
+    const int* name = name##_s
+#endif
 template <bool CTA>
-__device__ __forceinline__ bool ring_claim(const RingArgs& A, int lane, RingJob& J) {
+__device__ __forceinline__ bool ring_claim(const RingArgs& A, const int* sb, int lane, RingJob& J) {
     int job = 0;
 #if J2K_RING_CTA_CLAIM && !defined(J2K_EMU)
     if constexpr (CTA) {
@@ -788,14 +839,25 @@ __device__ __forceinline__ bool ring_claim(const RingArgs& A, int lane, RingJob&
         job = __shfl_sync(0xffffffffu, job, 0);
     }
     if (job >= A.total_jobs) return false;
-    int k = 0;
-    while (k + 1 < A.nseg && job >= A.seg[k].job_end) k++;
-    const int local = job - A.seg[k].job_begin;
+    int k = 0, local, item0 = 0;
+    if (A.nslice > 0) {
+        int lo = 0, hi = A.nslice - 1;  // last slice that starts at or before this job
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (sb[mid] <= job) lo = mid; else hi = mid - 1;
+        }
+        const int2 info = A.slice_info[lo];
+        k = info.x; item0 = info.y;
+        local = job - sb[lo];
+    } else {
+        while (k + 1 < A.nseg && job >= A.seg[k].job_end) k++;
+        local = job - A.seg[k].job_begin;
+    }
     const int ns = A.seg[k].nstrips, nc = A.seg[k].nchunks;
     J.seg = k;
     J.strip = local % ns;
     J.chunk = (local / ns) % nc;
-    J.item = local / (ns * nc);
+    J.item = item0 + local / (ns * nc);
     return true;
 }
 
@@ -870,7 +932,8 @@ __global__ void J2K_RING_BOUNDS fwd_ring_kernel(const __grid_constant__ RingArgs
     ring_warp_init(smem, rw, lane, J2K_RING_BYTES);
     rw.one = A.one;
     RingJob J;
-    while (ring_claim<true>(A, lane, J)) {
+    J2K_RING_SCHED_DECL(A, sched);
+    while (ring_claim<true>(A, sched, lane, J)) {
         const RingSeg& S = A.seg[J.seg];
         ring_wait_dep(A, S, J.item, lane);
         if (S.first) {
@@ -1384,7 +1447,8 @@ __global__ void __launch_bounds__(J2K_RING_WARPS * 32, J2K_RING_MINB) inv_ring_k
     #ifndef J2K_INV_CTA_CLAIM
 #define J2K_INV_CTA_CLAIM 0
 #endif
-    while (ring_claim<(J2K_INV_CTA_CLAIM != 0)>(A, lane, J)) {
+    J2K_RING_SCHED_DECL(A, sched);
+    while (ring_claim<(J2K_INV_CTA_CLAIM != 0)>(A, sched, lane, J)) {
         const RingSeg& S = A.seg[J.seg];
         ring_wait_dep(A, S, J.item, lane);
         if (S.first) InvRing<WT, NP1, NC1, OUT1, MCT1>::run(S, A.raw, J.item, J.chunk, J.strip, rw, lane);
