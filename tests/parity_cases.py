@@ -314,3 +314,36 @@ def check_inverse_with_offsets(ctx, oracle, w, h, c, bits, L, reversible, xosiz,
     opx, oplanes = oracle.inverse(ip, co, want_planes=True)
     assert np.array_equal(planes, oplanes), "inverse planes with image / tile offsets"
     assert np.array_equal(px, opx), "inverse pixels with image / tile offsets"
+
+
+def check_pipelined_order(ctx, oracle, w, h, c, bits, L, reversible, nframes, group_ks, lag, capfd=None):
+    """A batch through the persistent launch with the group-pipelined job order forced on (ring_schedule in j2k_b200.cu:
+    J2K_RING_GROUP_KS / J2K_RING_LAG are read when the plan is built, so the geometry must be new to the context)."""
+    import os
+    import re
+    old = {k: os.environ.get(k) for k in ("J2K_RING_GROUP_KS", "J2K_RING_LAG", "J2K_B200_TRACE")}
+    os.environ.update(J2K_RING_GROUP_KS=str(group_ks), J2K_RING_LAG=str(lag), J2K_B200_TRACE="1")
+    try:
+        rng = np.random.default_rng(w + nframes)
+        frames = np.stack([raw_bytes(synth(rng, h, w, c, bits, False, "noise")) for _ in range(nframes)])
+        fp, ip = fwd_inv_params(w, h, c, bits, False, L, reversible, oracle)
+        co = ctx.forward_batch(fp, frames)
+        for f in range(nframes):
+            assert np.array_equal(co[f], oracle.forward(fp, frames[f])), f"forward, frame {f}"
+        back = co if reversible else np.stack([M.t1_emulate(co[f], False) for f in range(nframes)])
+        px = ctx.inverse_batch(ip, back)
+        for f in range(nframes):
+            assert np.array_equal(px[f], oracle.inverse(ip, back[f])), f"inverse, frame {f}"
+        if reversible:
+            assert np.array_equal(px, frames), "lossless identity"
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    if capfd is not None:
+        err = capfd.readouterr().err
+        if "[j2k]" in err:  # the trace is latched at first use
+            n = [int(m) for m in re.findall(r" ring .* slices=(\d+)", err)]
+            assert n and (all(v > 0 for v in n) if nframes > lag else all(v == 0 for v in n)), err

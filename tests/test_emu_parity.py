@@ -140,28 +140,4 @@ def test_inverse_with_image_and_tile_offsets(ectx, oracle, w, h, c, bits, L, rev
 def test_group_pipelined_job_order(ectx, oracle, w, h, c, bits, L, rev, nframes, group_ks, lag, capfd):
     """Batches long enough for the group-pipelined job order of the persistent launch (ring_schedule): slices of
     (level, item group) interleaved `lag` groups apart; a batch no longer than the lag keeps the level-major list."""
-    import os
-    old = {k: os.environ.get(k) for k in ("J2K_RING_GROUP_KS", "J2K_RING_LAG", "J2K_B200_TRACE")}
-    os.environ.update(J2K_RING_GROUP_KS=str(group_ks), J2K_RING_LAG=str(lag), J2K_B200_TRACE="1")
-    try:
-        rng = np.random.default_rng(w + nframes)
-        frames = np.stack([PC.raw_bytes(PC.synth(rng, h, w, c, bits, False, "noise")) for _ in range(nframes)])
-        fp, ip = PC.fwd_inv_params(w, h, c, bits, False, L, rev, oracle)
-        co = ectx.forward_batch(fp, frames)
-        for f in range(nframes):
-            assert np.array_equal(co[f], oracle.forward(fp, frames[f])), f"forward, frame {f}"
-        back = co if rev else np.stack([PC.M.t1_emulate(co[f], False) for f in range(nframes)])
-        px = ectx.inverse_batch(ip, back)
-        for f in range(nframes):
-            assert np.array_equal(px[f], oracle.inverse(ip, back[f])), f"inverse, frame {f}"
-    finally:
-        for k, v in old.items():
-            if v is None:
-                os.environ.pop(k, None)
-            else:
-                os.environ[k] = v
-    err = capfd.readouterr().err
-    if "[j2k]" in err:  # the trace is latched at first use
-        import re
-        n = [int(m) for m in re.findall(r" ring .* slices=(\d+)", err)]
-        assert n and (all(v > 0 for v in n) if nframes > lag else all(v == 0 for v in n)), err
+    PC.check_pipelined_order(ectx, oracle, w, h, c, bits, L, rev, nframes, group_ks, lag, capfd)

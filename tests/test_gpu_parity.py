@@ -310,3 +310,14 @@ def test_random_geometry_sweep(ctx, oracle):
 ])
 def test_inverse_with_image_and_tile_offsets(ctx, oracle, w, h, c, bits, L, rev, xo, yo, tile, xto, yto):
     PC.check_inverse_with_offsets(ctx, oracle, w, h, c, bits, L, rev, xo, yo, tile, xto, yto)
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("w,h,c,bits,L,rev,nframes,group_ks,lag", [
+    (520, 264, 1, 16, 4, True, 24, 128, 1), (520, 264, 1, 12, 4, False, 40, 256, 2), (264, 136, 3, 8, 3, False, 30, 128, 3),
+    (264, 136, 3, 8, 3, True, 18, 64, 1),
+])
+def test_group_pipelined_job_order(ctx, oracle, w, h, c, bits, L, rev, nframes, group_ks, lag, capfd):
+    """The optional group-pipelined job order of the persistent launch (ring_schedule) under real concurrency: consumers
+    are claimed `lag` item groups behind their producers (lag 1: warps do park on unfinished producers), results unchanged."""
+    PC.check_pipelined_order(ctx, oracle, w, h, c, bits, L, rev, nframes, group_ks, lag, capfd)
