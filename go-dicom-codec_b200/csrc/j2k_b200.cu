@@ -1602,6 +1602,7 @@ int get_block_table(DeviceCtx& d, const Spec& s, int cbw, int cbh, long long coe
                 e.block_off = plane + b.offset;
                 e.stride = g.tw; e.w = b.width; e.h = b.height;
                 e.vec = (b.width % 4 == 0 && g.tw % 4 == 0 && e.plane_off % 4 == 0 && e.block_off % 4 == 0 && coeffs_per_frame % 4 == 0) ? 1 : 0;
+                e.comp = c; e.pad_ = 0;
                 host.push_back(e);
             }
         }
@@ -1629,12 +1630,26 @@ int launch_gather(j2k_ctx* ctx, BlockTable& T, int nframes, const int32_t* d_coe
     return 0;
 }
 
-int launch_scatter(j2k_ctx* ctx, BlockTable& T, int nframes, const int32_t* d_blocks, int32_t* d_coeffs, cudaStream_t st) {
+// Per-component MaxShift values of the caller (NULL: no ROI) -> kernel argument.
+int make_roi(const int32_t* roi_maxshift, int C, RoiShifts& r) {
+    memset(&r, 0, sizeof r);
+    if (!roi_maxshift) return 0;
+    if (C > J2K_ROI_MAXC) return fail(J2K_ERR_UNSUPPORTED, "ROI shifts for %d components (at most %d)", C, J2K_ROI_MAXC);
+    for (int c = 0; c < C; c++) {
+        if (roi_maxshift[c] < 0 || roi_maxshift[c] > 255) return fail(J2K_ERR_INVALID_ARG, "invalid ROI shift: %d (must be <=255)", roi_maxshift[c]);
+        r.shift[c] = roi_maxshift[c];
+        if (roi_maxshift[c]) r.any = 1;
+    }
+    return 0;
+}
+
+int launch_scatter(j2k_ctx* ctx, BlockTable& T, int nframes, const int32_t* d_blocks, int32_t* d_coeffs, cudaStream_t st,
+                   const RoiShifts& roi) {
     const long long total = (long long)T.nblocks * nframes;
     if (total <= 0) return 0;
     const unsigned grid = (unsigned)((total + 3) / 4);
     J2K_LAUNCH(scatter_blocks_kernel, grid, 128, st, (const int*)d_blocks, T.coeffs_per_frame, (const BlockEntry*)T.tab.p, T.nblocks, total,
-               (int*)d_coeffs);
+               (int*)d_coeffs, roi);
     CK(cudaGetLastError());
     ctx->launches++;
     return 0;
@@ -1677,6 +1692,7 @@ struct HostJob {
     size_t pix_bytes_per_frame; long long coeffs_per_frame;
     int cb_w = 0, cb_h = 0;      // > 0: coefficients cross the boundary block-major (code-block interface)
     int32_t* h_numbps = nullptr; // forward, block mode: cblkNumbps per block
+    RoiShifts roi{};             // inverse, block mode: per-component MaxShift applied while scattering
 };
 
 int enqueue_host_job(j2k_ctx* ctx, int di, const HostJob& J, int f0, int f1, bool timing) {
@@ -1730,7 +1746,7 @@ int enqueue_host_job(j2k_ctx* ctx, int di, const HostJob& J, int f0, int f1, boo
         long long fs = J.fwd ? (J.planar ? 0 : (long long)(J.pix_bytes_per_frame / (s.bit_depth <= 8 ? 1 : 2))) : (long long)(J.pix_bytes_per_frame / (s.bit_depth <= 8 ? 1 : 2));
         if ((rc = get_plan(d, s, J.pblob, J.pbytes, nb, fs, &P))) return rc;
         if (timing && it == 0) CK(cudaEventRecord(d.ev_t[1], d.s_main));
-        if (!J.fwd && BT && (rc = launch_scatter(ctx, *BT, nb, (const int32_t*)d.blk[slot].p, (int32_t*)d.in[slot].p, d.s_main))) return rc;
+        if (!J.fwd && BT && (rc = launch_scatter(ctx, *BT, nb, (const int32_t*)d.blk[slot].p, (int32_t*)d.in[slot].p, d.s_main, J.roi))) return rc;
         if (J.fwd) rc = run_plan(ctx, *P, d.in[slot].p, d.out[slot].p, nullptr, J.planar, d.s_main);
         else rc = run_plan(ctx, *P, d.out[slot].p, d.in[slot].p, J.h_planes ? d.planes[slot].p : nullptr, false, d.s_main);
         if (rc < 0) return rc;
@@ -2119,6 +2135,11 @@ int j2k_forward_blocks(j2k_ctx* ctx, const j2k_fwd_params* p, int cb_width, int 
 
 int j2k_inverse_blocks(j2k_ctx* ctx, const j2k_inv_params* p, int cb_width, int cb_height, int nframes, const int32_t* blocks_in,
                        void* pixels_out, size_t frame_stride_bytes, int32_t* planes_out) {
+    return j2k_inverse_blocks_roi(ctx, p, cb_width, cb_height, nframes, blocks_in, nullptr, pixels_out, frame_stride_bytes, planes_out);
+}
+
+int j2k_inverse_blocks_roi(j2k_ctx* ctx, const j2k_inv_params* p, int cb_width, int cb_height, int nframes, const int32_t* blocks_in,
+                           const int32_t* roi_maxshift, void* pixels_out, size_t frame_stride_bytes, int32_t* planes_out) {
     if (!ctx) return fail(J2K_ERR_INVALID_ARG, "context is NULL");
     if (!p) return fail(J2K_ERR_INVALID_ARG, "params is NULL");
     int rc = validate_cb(cb_width, cb_height);
@@ -2132,6 +2153,7 @@ int j2k_inverse_blocks(j2k_ctx* ctx, const j2k_inv_params* p, int cb_width, int 
     J.h_coef_in = blocks_in; J.h_pix_out = (unsigned char*)pixels_out; J.h_planes = planes_out;
     J.pix_bytes_per_frame = j2k_inv_pixel_bytes(p); J.coeffs_per_frame = (long long)j2k_inv_coeff_count(p);
     J.frame_stride_bytes = frame_stride_bytes; J.cb_w = cb_width; J.cb_h = cb_height;
+    if ((rc = make_roi(roi_maxshift, p->components, J.roi))) return rc;
     if (frame_stride_bytes < J.pix_bytes_per_frame) return fail(J2K_ERR_SIZE, "frame stride smaller than a frame");
     return run_host_batch(ctx, J, nframes, true, nullptr);
 }
@@ -2154,6 +2176,11 @@ int j2k_gather_blocks_device(j2k_ctx* ctx, int dev, const j2k_fwd_params* p, int
 
 int j2k_scatter_blocks_device(j2k_ctx* ctx, int dev, const j2k_inv_params* p, int cb_width, int cb_height, int nframes,
                               const int32_t* d_blocks, int32_t* d_coeffs, void* cuda_stream) {
+    return j2k_scatter_blocks_roi_device(ctx, dev, p, cb_width, cb_height, nframes, d_blocks, nullptr, d_coeffs, cuda_stream);
+}
+
+int j2k_scatter_blocks_roi_device(j2k_ctx* ctx, int dev, const j2k_inv_params* p, int cb_width, int cb_height, int nframes,
+                                  const int32_t* d_blocks, const int32_t* roi_maxshift, int32_t* d_coeffs, void* cuda_stream) {
     int rc = set_dev(ctx, dev);
     if (rc) return rc;
     if (!p) return fail(J2K_ERR_INVALID_ARG, "params is NULL");
@@ -2165,7 +2192,9 @@ int j2k_scatter_blocks_device(j2k_ctx* ctx, int dev, const j2k_inv_params* p, in
     DeviceCtx& d = ctx->devs[dev];
     BlockTable* BT = nullptr;
     if ((rc = get_block_table(d, s, cb_width, cb_height, (long long)j2k_inv_coeff_count(p), &BT))) return rc;
-    return launch_scatter(ctx, *BT, nframes, d_blocks, d_coeffs, cuda_stream ? (cudaStream_t)cuda_stream : d.s_main);
+    RoiShifts roi;
+    if ((rc = make_roi(roi_maxshift, p->components, roi))) return rc;
+    return launch_scatter(ctx, *BT, nframes, d_blocks, d_coeffs, cuda_stream ? (cudaStream_t)cuda_stream : d.s_main, roi);
 }
 
 // ---- asynchronous

@@ -302,7 +302,25 @@ struct BlockEntry {
     long long plane_off;   // first sample of the block inside the frame's coefficient planes (samples)
     long long block_off;   // first sample of the block inside the frame's block-major planes
     int stride, w, h, vec; // plane row stride (= tile width); vec: w % 4 == 0 and both sides 16-byte aligned in every frame
+    int comp, pad_;        // component of the block (per-component ROI shift)
 };
+
+// Srgn = 0 (MaxShift) ROI shifts per component, 0 = none (t2/tile_decoder.go:726-730)
+#define J2K_ROI_MAXC 16
+struct RoiShifts { int any; int shift[J2K_ROI_MAXC]; };
+
+// applyInverseMaxShift (t2/tile_decoder.go:1113-1138): magnitudes at or above 2^shift belong to the ROI and come down by
+// `shift`; shift >= 31 zeroes the block.  -mag wraps for INT_MIN as in Go (then mag < thresh: untouched).
+__device__ __forceinline__ int inverse_max_shift(int v, int shift) {
+    if (shift <= 0) return v;
+    if (shift >= 31) return 0;
+    int mag = v < 0 ? (int)(0u - (unsigned)v) : v;
+    if (mag >= (1 << shift)) {
+        mag >>= shift;
+        return v < 0 ? -mag : mag;
+    }
+    return v;
+}
 
 __device__ __forceinline__ int go_abs_max(int m, int v) {  // calculateMaxBitplane: abs wraps for INT_MIN, compare is signed
     const int a = v < 0 ? (int)(0u - (unsigned)v) : v;
@@ -356,7 +374,7 @@ __global__ void __launch_bounds__(128) gather_blocks_kernel(const int* __restric
 
 __global__ void __launch_bounds__(128) scatter_blocks_kernel(const int* __restrict__ blocks, long long coeffs_per_frame,
                                                              const BlockEntry* __restrict__ tab, int nblocks, long long total,
-                                                             int* __restrict__ coeffs) {
+                                                             int* __restrict__ coeffs, const RoiShifts roi) {
     const int lane = threadIdx.x & 31;
     const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (wid >= total) return;
@@ -365,18 +383,21 @@ __global__ void __launch_bounds__(128) scatter_blocks_kernel(const int* __restri
     const BlockEntry e = tab[b];
     const int* src = blocks + frame * coeffs_per_frame + e.block_off;
     int* dst = coeffs + frame * coeffs_per_frame + e.plane_off;
+    const int sh = roi.any ? roi.shift[e.comp] : 0;  // warp-uniform
     if (e.vec) {
         const int w4 = e.w >> 2, n4 = w4 * e.h;
 #pragma unroll 4
         for (int i = lane; i < n4; i += 32) {
             const int y = i / w4, x = i - y * w4;
-            *(int4*)(dst + (long long)y * e.stride + 4 * x) = *(const int4*)(src + 4 * i);
+            int4 v = *(const int4*)(src + 4 * i);
+            if (sh) { v.x = inverse_max_shift(v.x, sh); v.y = inverse_max_shift(v.y, sh); v.z = inverse_max_shift(v.z, sh); v.w = inverse_max_shift(v.w, sh); }
+            *(int4*)(dst + (long long)y * e.stride + 4 * x) = v;
         }
     } else {
         const int n = e.w * e.h;
         for (int i = lane; i < n; i += 32) {
             const int y = i / e.w, x = i - y * e.w;
-            dst[(long long)y * e.stride + x] = src[i];
+            dst[(long long)y * e.stride + x] = inverse_max_shift(src[i], sh);
         }
     }
 }

@@ -183,7 +183,7 @@ EXPORTED_SYMBOLS = [
     "j2k_inverse", "j2k_inverse_batch", "j2k_inverse_device",
     "j2k_submit_forward", "j2k_submit_inverse", "j2k_wait",
     "j2k_codeblock_layout", "j2k_fwd_block_count", "j2k_inv_block_count", "j2k_forward_blocks", "j2k_inverse_blocks",
-    "j2k_gather_blocks_device", "j2k_scatter_blocks_device",
+    "j2k_gather_blocks_device", "j2k_scatter_blocks_device", "j2k_inverse_blocks_roi", "j2k_scatter_blocks_roi_device",
     "j2k_dwt53_forward", "j2k_dwt53_inverse", "j2k_dwt97_forward", "j2k_dwt97_inverse", "j2k_convert_f32_to_i32",
     "j2k_rct_forward", "j2k_rct_inverse", "j2k_ict_forward", "j2k_ict_inverse",
     "j2k_dwt97_forward_f64", "j2k_dwt97_inverse_f64", "j2k_convert_f64_to_i32", "j2k_ll_dimensions",
@@ -247,6 +247,8 @@ def load(path: str | None = None) -> C.CDLL:
         "j2k_inverse_blocks": (ci, [vp, IP, ci, ci, ci, vp, vp, sz, vp]),
         "j2k_gather_blocks_device": (ci, [vp, ci, FP, ci, ci, ci, vp, vp, vp, vp]),
         "j2k_scatter_blocks_device": (ci, [vp, ci, IP, ci, ci, ci, vp, vp, vp]),
+        "j2k_inverse_blocks_roi": (ci, [vp, IP, ci, ci, ci, vp, vp, vp, sz, vp]),
+        "j2k_scatter_blocks_roi_device": (ci, [vp, ci, IP, ci, ci, ci, vp, vp, vp, vp]),
         "j2k_dwt53_forward": (ci, [vp, vp, ci, ci, ci, ci, ci]),
         "j2k_dwt53_inverse": (ci, [vp, vp, ci, ci, ci, ci, ci]),
         "j2k_dwt97_forward": (ci, [vp, vp, ci, ci, ci, ci, ci]),

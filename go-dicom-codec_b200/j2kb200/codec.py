@@ -166,15 +166,24 @@ class Context:
         self._ck(self.lib.j2k_forward_blocks(self.h, C.byref(p), cb_width, cb_height, n, _vp(frames), frames.strides[0], _vp(out), _vp(nb)))
         return out, nb
 
-    def inverse_blocks(self, p: abi.InvParams, blocks: np.ndarray, cb_width=64, cb_height=64, want_planes: bool = False):
+    def inverse_blocks(self, p: abi.InvParams, blocks: np.ndarray, cb_width=64, cb_height=64, want_planes: bool = False,
+                       roi_maxshift=None):
+        """roi_maxshift: per-component MaxShift (RGN Srgn = 0) undone on the device while the blocks are scattered
+        (decodeCodeBlock, t2/tile_decoder.go:726-730); None = the blocks carry no ROI scaling."""
         assert blocks.ndim == 2 and blocks.dtype == np.int32 and blocks.flags.c_contiguous
         n = blocks.shape[0]
         nbytes = self.lib.j2k_inv_pixel_bytes(C.byref(p))
         out = np.empty((n, nbytes), np.uint8)
         w, h = p.xsiz - p.xosiz, p.ysiz - p.yosiz
         planes = np.empty((n, p.components, h, w), np.int32) if want_planes else None
-        self._ck(self.lib.j2k_inverse_blocks(self.h, C.byref(p), cb_width, cb_height, n, _vp(blocks), _vp(out), nbytes,
-                                             _vp(planes) if want_planes else None))
+        if roi_maxshift is None:
+            self._ck(self.lib.j2k_inverse_blocks(self.h, C.byref(p), cb_width, cb_height, n, _vp(blocks), _vp(out), nbytes,
+                                                 _vp(planes) if want_planes else None))
+        else:
+            roi = np.ascontiguousarray(roi_maxshift, dtype=np.int32)
+            assert roi.size == p.components
+            self._ck(self.lib.j2k_inverse_blocks_roi(self.h, C.byref(p), cb_width, cb_height, n, _vp(blocks), _vp(roi), _vp(out), nbytes,
+                                                     _vp(planes) if want_planes else None))
         return (out, planes) if want_planes else out
 
     def gather_blocks_device(self, p: abi.FwdParams, nframes, d_coeffs: int, d_blocks: int, d_numbps: int, cb_width=64, cb_height=64,
@@ -183,9 +192,15 @@ class Context:
                                                    C.c_void_p(d_blocks), C.c_void_p(d_numbps), C.c_void_p(stream)))
 
     def scatter_blocks_device(self, p: abi.InvParams, nframes, d_blocks: int, d_coeffs: int, cb_width=64, cb_height=64,
-                              stream: int = 0, dev: int = 0):
-        self._ck(self.lib.j2k_scatter_blocks_device(self.h, dev, C.byref(p), cb_width, cb_height, nframes, C.c_void_p(d_blocks),
-                                                    C.c_void_p(d_coeffs), C.c_void_p(stream)))
+                              stream: int = 0, dev: int = 0, roi_maxshift=None):
+        if roi_maxshift is None:
+            self._ck(self.lib.j2k_scatter_blocks_device(self.h, dev, C.byref(p), cb_width, cb_height, nframes, C.c_void_p(d_blocks),
+                                                        C.c_void_p(d_coeffs), C.c_void_p(stream)))
+        else:
+            roi = np.ascontiguousarray(roi_maxshift, dtype=np.int32)
+            assert roi.size == p.components
+            self._ck(self.lib.j2k_scatter_blocks_roi_device(self.h, dev, C.byref(p), cb_width, cb_height, nframes, C.c_void_p(d_blocks),
+                                                            _vp(roi), C.c_void_p(d_coeffs), C.c_void_p(stream)))
 
     def _dwt(self, fn, data, levels, x0, y0, dtype):
         a = np.ascontiguousarray(data, dtype=dtype).copy()

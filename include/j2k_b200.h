@@ -281,12 +281,23 @@ int j2k_forward_blocks(j2k_ctx* ctx, const j2k_fwd_params* p, int cb_width, int 
 int j2k_inverse_blocks(j2k_ctx* ctx, const j2k_inv_params* p, int cb_width, int cb_height, int nframes,
                        const int32_t* blocks_in, void* pixels_out, size_t frame_stride_bytes, int32_t* planes_out);
 
+/* The same with the decode-side MaxShift ROI of decodeCodeBlock (jpeg2000/t2/tile_decoder.go:726-730): the blocks arrive
+ * as T1 leaves them and applyInverseMaxShift (:1113-1138) runs on the device while the blocks are scattered, before the
+ * classic 5/3 "/2".  `roi_maxshift`: one shift per component (RGN marker, Srgn = 0), 0 = none; NULL = no ROI.  General
+ * scaling (Srgn = 1, :735-741) depends on the ROI geometry per block and stays in Go. */
+int j2k_inverse_blocks_roi(j2k_ctx* ctx, const j2k_inv_params* p, int cb_width, int cb_height, int nframes,
+                           const int32_t* blocks_in, const int32_t* roi_maxshift, void* pixels_out, size_t frame_stride_bytes,
+                           int32_t* planes_out);
+
 /* Device-resident halves of the two calls above (plane <-> block-major), for pipelines that
  * keep coefficients on the device; enqueued on `cuda_stream`, not synchronised. */
 int j2k_gather_blocks_device(j2k_ctx* ctx, int dev, const j2k_fwd_params* p, int cb_width, int cb_height, int nframes,
                              const int32_t* d_coeffs, int32_t* d_blocks, int32_t* d_numbps, void* cuda_stream);
 int j2k_scatter_blocks_device(j2k_ctx* ctx, int dev, const j2k_inv_params* p, int cb_width, int cb_height, int nframes,
                               const int32_t* d_blocks, int32_t* d_coeffs, void* cuda_stream);
+/* `roi_maxshift` is a HOST array (one shift per component, NULL = none), as in j2k_inverse_blocks_roi. */
+int j2k_scatter_blocks_roi_device(j2k_ctx* ctx, int dev, const j2k_inv_params* p, int cb_width, int cb_height, int nframes,
+                                  const int32_t* d_blocks, const int32_t* roi_maxshift, int32_t* d_coeffs, void* cuda_stream);
 
 /* -------------------------------------------- wavelet package API (in place) */
 

@@ -345,6 +345,23 @@ func ForwardBlocks(p *FwdParams, cbWidth, cbHeight, nframes int, pixels []byte, 
 	return nil
 }
 
+// InverseBlocksROI: InverseBlocks for codestreams with an RGN marker of style 0 (MaxShift): blocks holds the T1 output
+// untouched and roiMaxShift[c] the shift of component c (0 = none); applyInverseMaxShift (t2/tile_decoder.go:1113-1138)
+// runs on the device while the blocks are scattered.  General scaling (Srgn = 1) stays in decodeCodeBlock.
+func InverseBlocksROI(p *InvParams, cbWidth, cbHeight, nframes int, blocks []int32, roiMaxShift []int32, pixels []byte, frameStride int) error {
+	cp := p.c()
+	var roi *C.int32_t
+	if len(roiMaxShift) > 0 {
+		roi = (*C.int32_t)(unsafe.Pointer(&roiMaxShift[0]))
+	}
+	rc := C.j2k_inverse_blocks_roi(ctx, &cp, C.int(cbWidth), C.int(cbHeight), C.int(nframes), (*C.int32_t)(unsafe.Pointer(&blocks[0])),
+		roi, unsafe.Pointer(&pixels[0]), C.size_t(frameStride), nil)
+	if rc != 0 {
+		return lastErr(rc)
+	}
+	return nil
+}
+
 // InverseBlocks: the decode mirror; blocks holds every code-block's T1 output at CodeBlock.Offset.
 func InverseBlocks(p *InvParams, cbWidth, cbHeight, nframes int, blocks []int32, pixels []byte, frameStride int) error {
 	cp := p.c()

@@ -1400,6 +1400,24 @@ ORC_API int orc_scatter_blocks(const int32_t* blocks, int width, int height, int
     return n;
 }
 
+/* applyInverseMaxShift (jpeg2000/t2/tile_decoder.go:1113-1138), the Srgn = 0 branch of decodeCodeBlock (:726-730):
+ * shift <= 0 leaves the block alone, shift >= 31 zeroes it, otherwise magnitudes >= 2^shift come down by shift
+ * (Go's -val wraps for INT_MIN: the magnitude stays negative, fails the threshold test and the value is kept). */
+ORC_API void orc_inverse_max_shift(int32_t* data, size_t n, int shift) {
+    if (shift <= 0) return;
+    if (shift >= 31) { for (size_t i = 0; i < n; i++) data[i] = 0; return; }
+    const int32_t thresh = (int32_t)1 << shift;
+    for (size_t i = 0; i < n; i++) {
+        const int32_t val = data[i];
+        int32_t mag = val;
+        if (mag < 0) mag = (int32_t)(0u - (uint32_t)mag);
+        if (mag >= thresh) {
+            mag >>= shift;
+            data[i] = val < 0 ? -mag : mag;
+        }
+    }
+}
+
 ORC_API int orc_abi_sizes(int* fwd, int* inv, int* binding) {
     *fwd = (int)sizeof(j2k_fwd_params); *inv = (int)sizeof(j2k_inv_params); *binding = (int)sizeof(j2k_mct_binding);
     return J2K_B200_ABI_VERSION;

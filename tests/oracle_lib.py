@@ -228,6 +228,11 @@ class Oracle:
         self.lib.orc_scatter_blocks(_p(b), C.c_int(width), C.c_int(height), C.c_int(num_levels), C.c_int(cbw), C.c_int(cbh), _p(plane))
         return plane
 
+    def inverse_max_shift(self, data, shift):
+        a = np.array(data, dtype=np.int32, copy=True).reshape(-1)
+        self.lib.orc_inverse_max_shift(_p(a), C.c_size_t(a.size), C.c_int(shift))
+        return a.reshape(np.shape(data))
+
     # ---- pipelines
     def fwd_tile_bounds(self, p, idx):
         b = (C.c_int32 * 4)()

@@ -347,3 +347,60 @@ def check_pipelined_order(ctx, oracle, w, h, c, bits, L, reversible, nframes, gr
         if "[j2k]" in err:  # the trace is latched at first use
             n = [int(m) for m in re.findall(r" ring .* slices=(\d+)", err)]
             assert n and (all(v > 0 for v in n) if nframes > lag else all(v == 0 for v in n)), err
+
+
+def check_blocks_roi(ctx, oracle, w, h, c, bits, L, reversible, shifts, tile=(0, 0), cb=(32, 32), seed=31, nframes=2):
+    """Decode-side MaxShift ROI (decodeCodeBlock, t2/tile_decoder.go:726-730 + applyInverseMaxShift :1113-1138) fused into
+    the block scatter: the blocks arrive as T1 leaves them, i.e. with the ROI samples of component k still shifted up by
+    shifts[k]; the device undoes it while scattering, before the classic 5/3 "/2".  Checked against the oracle's restated
+    rule followed by its scatter + inverse, and (lossless, 0 < shift < 31) against the original frames."""
+    rng = np.random.default_rng(seed)
+    fp, ip = fwd_inv_params(w, h, c, bits, False, L, reversible, oracle, tile)
+    frames = np.stack([raw_bytes(synth(rng, h, w, c, bits, False, "smooth" if f else "noise")) for f in range(nframes)])
+    blocks, _ = ctx.forward_blocks(fp, frames, cb[0], cb[1])
+    shift6 = bool(reversible)
+    if reversible:
+        back = ((blocks >> 6) * 2).astype(np.int32)
+        ip.fuse_t1_halve = 1
+    else:
+        back = np.stack([M.t1_emulate(blocks[f], False) for f in range(nframes)]).astype(np.int32)
+    # what an encoder with a MaxShift ROI leaves in the code-blocks: samples inside the region carry mag << shift, every
+    # background magnitude stays below 2^shift (that is the MaxShift condition, so small shifts are exercised with a
+    # region that holds every sample whose magnitude reaches the threshold)
+    sent = back.copy()
+    lossless_ok = True
+    for f in range(nframes):
+        off = 0
+        for (x0, y0, x1, y1) in tile_list(oracle, fp):
+            n = (x1 - x0) * (y1 - y0)
+            for comp in range(c):
+                sh = int(shifts[comp])
+                seg = sent[f][off:off + n]
+                if 0 < sh < 31:
+                    mag = np.abs(seg.astype(np.int64))
+                    region = (rng.random(n) < 0.3) | (mag >= (1 << sh))
+                    up = mag << sh
+                    ok = up < (1 << 31)
+                    region &= ok & (mag > 0)
+                    if np.any((mag >= (1 << sh)) & ~region):
+                        lossless_ok = False
+                    seg[region] = (np.sign(seg[region]) * up[region]).astype(np.int32)
+                elif sh >= 31:
+                    lossless_ok = False
+                off += n
+    px = ctx.inverse_blocks(ip, np.ascontiguousarray(sent), cb[0], cb[1], roi_maxshift=shifts)
+    for f in range(nframes):
+        planes, off = [], 0
+        for (x0, y0, x1, y1) in tile_list(oracle, fp):
+            tw, th = x1 - x0, y1 - y0
+            for comp in range(c):
+                blk = oracle.inverse_max_shift(sent[f][off:off + tw * th], int(shifts[comp]))
+                planes.append(oracle.scatter_blocks(blk, tw, th, L, cb[0], cb[1]).reshape(-1))
+                off += tw * th
+        want_px = oracle.inverse(ip, np.concatenate(planes))
+        assert np.array_equal(px[f], want_px), f"inverse from ROI-scaled blocks, frame {f}"
+        if reversible and lossless_ok:
+            assert np.array_equal(px[f], frames[f]), "lossless identity through MaxShift ROI blocks"
+    # no shifts at all == the plain call
+    assert np.array_equal(ctx.inverse_blocks(ip, np.ascontiguousarray(back), cb[0], cb[1], roi_maxshift=[0] * c),
+                          ctx.inverse_blocks(ip, np.ascontiguousarray(back), cb[0], cb[1]))

@@ -141,3 +141,11 @@ def test_group_pipelined_job_order(ectx, oracle, w, h, c, bits, L, rev, nframes,
     """Batches long enough for the group-pipelined job order of the persistent launch (ring_schedule): slices of
     (level, item group) interleaved `lag` groups apart; a batch no longer than the lag keeps the level-major list."""
     PC.check_pipelined_order(ectx, oracle, w, h, c, bits, L, rev, nframes, group_ks, lag, capfd)
+
+
+@pytest.mark.parametrize("w,h,c,bits,L,rev,shifts,tile,cb", [
+    (64, 48, 1, 8, 2, True, [5], (0, 0), (16, 16)), (70, 50, 1, 12, 3, False, [9], (0, 0), (16, 8)), (48, 40, 3, 8, 2, True, [4, 0, 7], (32, 32), (8, 8)),
+    (40, 24, 3, 8, 2, False, [0, 6, 31], (0, 0), (64, 64)), (33, 17, 1, 16, 3, True, [1], (0, 0), (4, 4)),
+])
+def test_code_block_interface_roi(ectx, oracle, w, h, c, bits, L, rev, shifts, tile, cb):
+    PC.check_blocks_roi(ectx, oracle, w, h, c, bits, L, rev, shifts, tile=tile, cb=cb)

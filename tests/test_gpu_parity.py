@@ -321,3 +321,13 @@ def test_group_pipelined_job_order(ctx, oracle, w, h, c, bits, L, rev, nframes, 
     """The optional group-pipelined job order of the persistent launch (ring_schedule) under real concurrency: consumers
     are claimed `lag` item groups behind their producers (lag 1: warps do park on unfinished producers), results unchanged."""
     PC.check_pipelined_order(ctx, oracle, w, h, c, bits, L, rev, nframes, group_ks, lag, capfd)
+
+
+@pytest.mark.parametrize("w,h,c,bits,L,rev,shifts,tile,cb", [
+    (512, 384, 1, 16, 5, True, [7], (0, 0), (64, 64)), (1000, 700, 1, 12, 5, False, [10], (256, 256), (32, 32)),
+    (513, 257, 3, 8, 4, True, [3, 0, 9], (256, 256), (64, 64)), (640, 480, 3, 8, 4, False, [0, 5, 31], (0, 0), (32, 64)),
+    (127, 129, 1, 8, 3, True, [1], (0, 0), (4, 4)),
+])
+def test_code_block_interface_roi(ctx, oracle, w, h, c, bits, L, rev, shifts, tile, cb):
+    """Decode-side MaxShift ROI fused into the block scatter."""
+    PC.check_blocks_roi(ctx, oracle, w, h, c, bits, L, rev, shifts, tile=tile, cb=cb, nframes=3)

@@ -167,3 +167,23 @@ def test_signed_sub16_is_not_sign_extended(oracle):
     ip = abi.inv_params(4, 1, 1, 12, True, num_levels=0, reversible=True)
     back = oracle.inverse(ip, np.array([-1, -2048, 2047, -5000], np.int32)).view("<u2")
     assert back.tolist() == [0x0FFF, 0x0800, 0x07FF, 0x0800]
+
+
+def test_inverse_max_shift_rule(oracle):
+    """applyInverseMaxShift (t2/tile_decoder.go:1113-1138): threshold rule, shift <= 0 is the identity, shift >= 31 zeroes,
+    INT_MIN keeps Go's wrapped magnitude (negative, below every threshold: untouched)."""
+    v = np.array([0, 1, -1, 7, 8, -8, 9, -9, 1023, 1024, -1024, 1 << 20, -(1 << 20), (1 << 31) - 1, -(1 << 31)], np.int64).astype(np.int32)
+    assert np.array_equal(oracle.inverse_max_shift(v, 0), v)
+    assert np.array_equal(oracle.inverse_max_shift(v, -3), v)
+    assert not oracle.inverse_max_shift(v, 31).any() and not oracle.inverse_max_shift(v, 200).any()
+    want3 = np.array([0, 1, -1, 7, 1, -1, 1, -1, 127, 128, -128, 1 << 17, -(1 << 17), (1 << 28) - 1, -(1 << 31)], np.int64).astype(np.int32)
+    assert np.array_equal(oracle.inverse_max_shift(v, 3), want3)
+    # an encoder-side MaxShift (ROI magnitudes << s, background below 2^s) is undone exactly
+    rng = np.random.default_rng(5)
+    for s_ in (1, 5, 12, 20):
+        bg = rng.integers(-(1 << s_) + 1, 1 << s_, 1000).astype(np.int32)
+        roi = rng.integers(-(1 << (30 - s_)) + 1, 1 << (30 - s_), 1000).astype(np.int32)
+        roi[roi == 0] = 1
+        sent = np.concatenate([bg, (roi.astype(np.int64) << s_).astype(np.int32)])
+        back = oracle.inverse_max_shift(sent, s_)
+        assert np.array_equal(back[:1000], bg) and np.array_equal(back[1000:], roi)
