@@ -20,6 +20,10 @@ PC.check_pipeline(ctx, orc, 100, 70, 1, 8, False, 3, False, tile=(48, 32))
 PC.check_pipeline(ctx, orc, 70, 50, 3, 8, False, 2, False, tile=(32, 32))
 PC.check_blocks(ctx, orc, 70, 50, 1, 12, 3, False, cb=(16, 8))
 PC.check_blocks(ctx, orc, 48, 40, 3, 8, 2, True, tile=(32, 32), cb=(8, 8))
+PC.check_blocks_roi(ctx, orc, 48, 40, 3, 8, 2, True, [4, 0, 7], tile=(32, 32), cb=(8, 8))
+PC.check_blocks_roi(ctx, orc, 70, 50, 1, 12, 3, False, [9], cb=(16, 8))
+PC.check_pipelined_order(ctx, orc, 64, 32, 1, 12, 3, False, 9, 4, 3)
+PC.check_pipelined_order(ctx, orc, 48, 32, 3, 8, 2, True, 6, 4, 2)
 PC.check_custom_mct(ctx, orc, 40, 24, 8, 2, True, "bindings")
 PC.check_wavelet_api(ctx, orc, 130, 70, 5, 0, 0)
 PC.check_wavelet_api(ctx, orc, 33, 17, 2, 1, 0)
