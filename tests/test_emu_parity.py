@@ -149,3 +149,15 @@ def test_group_pipelined_job_order(ectx, oracle, w, h, c, bits, L, rev, nframes,
 ])
 def test_code_block_interface_roi(ectx, oracle, w, h, c, bits, L, rev, shifts, tile, cb):
     PC.check_blocks_roi(ectx, oracle, w, h, c, bits, L, rev, shifts, tile=tile, cb=cb)
+
+
+def test_roi_argument_errors(ectx):
+    """j2k_inverse_blocks_roi validates the shifts like the encoder validates ROI.Shift (encoder.go:332-334: at most 255)."""
+    import j2kb200
+    ip = abi.inv_params(32, 32, 1, 8, False, num_levels=2, reversible=True)
+    blocks = np.zeros((1, 32 * 32), np.int32)
+    for bad in ([-1], [256]):
+        with pytest.raises(j2kb200.J2KError) as e:
+            ectx.inverse_blocks(ip, blocks, 16, 16, roi_maxshift=bad)
+        assert e.value.code == abi.J2K_ERR_INVALID_ARG and "invalid ROI shift" in str(e.value)
+    ectx.inverse_blocks(ip, blocks, 16, 16, roi_maxshift=[255])  # shift >= 31 zeroes the blocks: a valid call
