@@ -31,6 +31,25 @@ int main(void) {
     j2k_cblk tab[64];
     int nb = j2k_codeblock_layout(W, H, L, 16, 16, tab, 64);
     if (nb <= 0 || tab[0].band != 0 || tab[0].offset != 0) { fprintf(stderr, "layout\n"); return 7; }
+    /* code-block interface with a decode-side MaxShift ROI: blocks out, every magnitude pushed up by 5 bits as an encoder
+     * with an all-covering region would leave them (and halved as the classic T1 hands them back), shift undone on the way in */
+    {
+        static int32_t blk[W * H], nbps[64];
+        int32_t shift[1] = {5};
+        rc = j2k_forward_blocks(ctx, &fp, 16, 16, 1, px, sizeof px, blk, nbps);
+        if (rc != 0 || j2k_fwd_block_count(&fp, 16, 16) != (size_t)nb) { fprintf(stderr, "forward_blocks: %d %s\n", rc, j2k_last_error(ctx)); return 9; }
+        for (int i = 0; i < W * H; i++) {
+            int32_t v = (blk[i] >> 6) * 2, m = v < 0 ? -v : v;  /* T1 output of the classic lossless path: one half bit */
+            m <<= 5;
+            blk[i] = v < 0 ? -m : m;
+        }
+        ip.fuse_t1_halve = 1;
+        rc = j2k_inverse_blocks_roi(ctx, &ip, 16, 16, 1, blk, shift, back, sizeof back, NULL);
+        ip.fuse_t1_halve = 0;
+        if (rc != 0) { fprintf(stderr, "inverse_blocks_roi: %d %s\n", rc, j2k_last_error(ctx)); return 10; }
+        /* magnitudes below 2^5 after the shift are only the zeros, so the MaxShift rule restores every sample */
+        if (memcmp(px, back, sizeof px) != 0) { fprintf(stderr, "ROI block round trip differs\n"); return 11; }
+    }
     rc = j2k_forward(ctx, &fp, px, 10, co, W * H);  /* short buffer: the reference's error, not a crash */
     if (rc != J2K_ERR_SIZE || strstr(j2k_last_error(ctx), "insufficient pixel data") == NULL) { fprintf(stderr, "error path\n"); return 8; }
     j2k_shutdown(ctx);
