@@ -404,3 +404,22 @@ def check_blocks_roi(ctx, oracle, w, h, c, bits, L, reversible, shifts, tile=(0,
     # no shifts at all == the plain call
     assert np.array_equal(ctx.inverse_blocks(ip, np.ascontiguousarray(back), cb[0], cb[1], roi_maxshift=[0] * c),
                           ctx.inverse_blocks(ip, np.ascontiguousarray(back), cb[0], cb[1]))
+
+
+def check_tall_chunks(ctx, oracle, w, h, c, bits, L, reversible, chunk, seed=41):
+    """Job partitioning of the persistent launch with the chunk heights only big batches reach (ring_chunks in j2k_b200.cu
+    sizes chunks for a job target, so a single test frame gets 8-row-pair chunks): J2K_RING_TARGET_JOBS=1 asks for one
+    chunk per strip, J2K_RING_CHUNK caps it, so the frame is cut into ceil(rows / 2 / chunk) chunks of `chunk` row pairs.
+    The knobs are read when the plan is built: the geometry must be new to the context."""
+    import os
+    old = {k: os.environ.get(k) for k in ("J2K_RING_TARGET_JOBS", "J2K_RING_CHUNK", "J2K_RING_CHUNK_DEEP")}
+    os.environ.update(J2K_RING_TARGET_JOBS="1", J2K_RING_CHUNK=str(chunk))
+    os.environ.pop("J2K_RING_CHUNK_DEEP", None)
+    try:
+        check_pipeline(ctx, oracle, w, h, c, bits, False, L, reversible, kind="noise", seed=seed)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v

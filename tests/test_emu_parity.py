@@ -161,3 +161,8 @@ def test_roi_argument_errors(ectx):
             ectx.inverse_blocks(ip, blocks, 16, 16, roi_maxshift=bad)
         assert e.value.code == abi.J2K_ERR_INVALID_ARG and "invalid ROI shift" in str(e.value)
     ectx.inverse_blocks(ip, blocks, 16, 16, roi_maxshift=[255])  # shift >= 31 zeroes the blocks: a valid call
+
+
+@pytest.mark.parametrize("w,h,c,bits,L,rev,chunk", [(64, 88, 1, 12, 2, False, 16), (64, 72, 1, 16, 2, True, 12), (48, 56, 3, 8, 2, False, 16)])
+def test_tall_chunks(ectx, oracle, w, h, c, bits, L, rev, chunk):
+    PC.check_tall_chunks(ectx, oracle, w, h, c, bits, L, rev, chunk)

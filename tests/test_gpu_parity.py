@@ -331,3 +331,13 @@ def test_group_pipelined_job_order(ctx, oracle, w, h, c, bits, L, rev, nframes, 
 def test_code_block_interface_roi(ctx, oracle, w, h, c, bits, L, rev, shifts, tile, cb):
     """Decode-side MaxShift ROI fused into the block scatter."""
     PC.check_blocks_roi(ctx, oracle, w, h, c, bits, L, rev, shifts, tile=tile, cb=cb, nframes=3)
+
+
+@pytest.mark.parametrize("w,h,c,bits,L,rev,chunk", [
+    (512, 616, 1, 12, 5, False, 64), (512, 1000, 1, 16, 5, True, 64), (264, 600, 3, 8, 3, False, 64), (264, 520, 3, 8, 3, True, 64),
+    (520, 1032, 1, 12, 4, False, 128), (528, 1040, 1, 16, 4, True, 256), (272, 776, 3, 8, 3, False, 128),
+])
+def test_tall_chunks(ctx, oracle, w, h, c, bits, L, rev, chunk):
+    """Chunk heights of 64 row pairs (what the big batches of bench.py and the BASELINE configs run with) and above,
+    forced on single frames and compared with the oracle: chunk seams, warm-up rows, partial last chunks."""
+    PC.check_tall_chunks(ctx, oracle, w, h, c, bits, L, rev, chunk)
