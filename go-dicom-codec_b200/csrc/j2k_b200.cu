@@ -509,7 +509,9 @@ void ring_chunks(RingSeg& g, int NP, int n_cols_total_hint, int level) {
     g.strip_pairs = (sp + align - 1) / align * align;
     if (g.strip_pairs > VP) g.strip_pairs = VP;
     g.nstrips = (g.Kx + g.strip_pairs - 1) / g.strip_pairs;
-    const int max_chunk = level <= 1 ? env_int("J2K_RING_CHUNK", 64) : env_int("J2K_RING_CHUNK_DEEP", env_int("J2K_RING_CHUNK", 64));
+    // chunks as tall as the job target allows, up to 128 row pairs: the 2 (5/3) or 4 (9/7) warm-up pairs a chunk recomputes are
+    // then 1.5-3 % of its rows (6 % at 64); the difference only shows once the board is power-capped
+    const int max_chunk = level <= 1 ? env_int("J2K_RING_CHUNK", 128) : env_int("J2K_RING_CHUNK_DEEP", env_int("J2K_RING_CHUNK", 128));
     const long long target = env_int("J2K_RING_TARGET_JOBS", 148 * 16 * 2);
     long long cols = (long long)n_cols_total_hint * g.nstrips;
     long long want = (target + cols - 1) / cols;
