@@ -167,6 +167,9 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+_SYNTH = {}
+
+
 def cpu_leg(threads, frames, steps, warmup):
     """Oracle port of the reference loops on the host cores; returns (Mpixel/s, ms/step)."""
     import oracle_lib
@@ -174,7 +177,9 @@ def cpu_leg(threads, frames, steps, warmup):
     orc = oracle_lib.Oracle()
     enc, _ = orc.openjpeg_quant_params(LEVELS, BITS)
     fp = abi.fwd_params(W, H, 1, BITS, False, num_levels=LEVELS, reversible=False, steps=orc.runtime_quant_steps(enc, LEVELS, BITS))
-    data = synth_frames(frames, 4242)
+    if "two" not in _SYNTH:
+        _SYNTH["two"] = synth_frames(2, 4242)  # two distinct seeded frames tiled over the sample (as the CUDA arm does)
+    data = np.ascontiguousarray(_SYNTH["two"][np.arange(frames) % 2])
     out = np.empty((frames, PIX), np.int32)
     for _ in range(warmup):
         orc.forward_batch(fp, frames, data, data.strides[0], out, threads)
@@ -183,6 +188,92 @@ def cpu_leg(threads, frames, steps, warmup):
         orc.forward_batch(fp, frames, data, data.strides[0], out, threads)
     dt = (time.perf_counter() - t0) / max(steps, 1)
     return frames * PIX / dt / 1e6, dt * 1e3
+
+
+# ---- the other BASELINE.json configs (C1, C3, C4, C5): resident forward / inverse legs reported inside the same JSON line
+
+OTHER_CONFIGS = [
+    # key, description, w, h, components, bits, signed, levels, reversible, frames per launch, tile
+    ("C1", "C1 x256: 512x512 16-bit signed mono, 5/3 L5 (256 frames per launch)", 512, 512, 1, 16, True, 5, True, 256, (0, 0)),
+    ("C3i", "C3(i) x8: 2048x2048 RGB 8-bit, ICT + 9/7 L5 (8 frames per launch)", 2048, 2048, 3, 8, False, 5, False, 8, (0, 0)),
+    ("C3ii", "C3(ii) x8: 2048x2048 RGB 8-bit, RCT + 5/3 L5 (8 frames per launch)", 2048, 2048, 3, 8, False, 5, True, 8, (0, 0)),
+    ("C4", "C4 block: 250 of the 2000 frames 512x512 16-bit, 5/3 L5 (one GPU's share at N = 8)", 512, 512, 1, 16, False, 5, True, 250, (0, 0)),
+    ("C5", "C5 block: 128 of the 1024 tiles 1024x1024 RGB 8-bit (8192x16384 image), ICT + 9/7 L7 (one GPU's share at N = 8)",
+     8192, 16384, 3, 8, False, 7, False, 1, (1024, 1024)),
+]
+
+
+def config_alg_bytes(samples, s_io, levels):
+    """S*(s_io+4) + 8*S*sum_{k=1}^{L-1} 4^-k (the same figure for both directions)."""
+    return samples * (s_io + 4) + 8 * samples * sum(4.0 ** -k for k in range(1, levels))
+
+
+def t1_roundtrip(torch, q):
+    """Forward output -> what the classic block decoder hands to the inverse when every coding pass is kept (not timed):
+    magnitude m = |q| >> 6 (the 6 fractional bits of jpeg2000/t1/encoder.go:203), reconstructed with one half bit,
+    v = sign * (2 m + 1) (jpeg2000/t1/decoder.go:630-647); zero stays zero.  Without it the inverse legs would see
+    coefficients 32 x too large (every sample clamps, and the float32 inverse-ICT fast path's range guard never passes)."""
+    m = q.abs() >> 6
+    return torch.where(m > 0, torch.sign(q) * (2 * m + 1), torch.zeros_like(q)).to(torch.int32)
+
+
+def run_config(ctx, torch, cfg, steps, peak, traffic=None):
+    """Forward and inverse of one BASELINE config, device-resident, CUDA events, two streams alternating (as `value`)."""
+    import j2kb200
+    from j2kb200 import abi
+    key, name, w, h, c, bits, signed, L, rev, frames, tile = cfg
+    mct = (abi.MCT_RCT if rev else abi.MCT_ICT) if c == 3 else abi.MCT_NONE
+    es = ds = None
+    if not rev:
+        enc, _ = j2kb200.openjpeg_quant_params(L, bits)
+        es, ds = j2kb200.runtime_quant_steps(enc, L, bits), j2kb200.decode_quant_steps(enc, L, bits, False)
+    fp = abi.fwd_params(w, h, c, bits, signed, tile[0], tile[1], L, rev, False, mct, es)
+    ip = abi.inv_params(w, h, c, bits, signed, tile[0], tile[1], L, rev, False, mct, ds)
+    bps = 1 if bits <= 8 else 2
+    fb = w * h * c * bps
+    g = torch.Generator(device="cuda").manual_seed(7)
+    d_in = torch.randint(0, 256, (frames, fb), dtype=torch.uint8, device="cuda", generator=g)
+    if 8 < bits < 16:  # keep the high byte inside the bit depth
+        d_in.view(frames, -1, 2)[:, :, 1] &= (1 << (bits - 8)) - 1
+    d_co = [torch.empty((frames, w * h * c), dtype=torch.int32, device="cuda") for _ in range(2)]
+    d_px = [torch.empty((frames, fb), dtype=torch.uint8, device="cuda") for _ in range(2)]
+    st = [torch.cuda.Stream() for _ in range(2)]
+    torch.cuda.synchronize()
+
+    def timed(fn):
+        for i in range(6):
+            fn(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st[0]); st[1].wait_event(e0)
+        for i in range(steps):
+            fn(i)
+        ev = torch.cuda.Event(); ev.record(st[1]); st[0].wait_event(ev)
+        e1.record(st[0])
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    l0 = ctx.launch_count
+    fms = timed(lambda i: ctx.forward_device(fp, frames, d_in.data_ptr(), fb, d_co[i % 2].data_ptr(), stream=st[i % 2].cuda_stream))
+    launches_per_call = (ctx.launch_count - l0) / (6 + steps)
+    torch.cuda.synchronize()
+    d_dec = d_co[0] if rev else t1_roundtrip(torch, d_co[0])  # 5/3: raw integers both ways (lossless identity below)
+    if not rev:
+        d_co[1] = None
+    torch.cuda.synchronize()
+    ims = timed(lambda i: ctx.inverse_device(ip, frames, d_dec.data_ptr(), d_px[i % 2].data_ptr(), fb, stream=st[i % 2].cuda_stream))
+    lossless_ok = bool(torch.equal(d_px[0], d_in)) if rev else None
+    max_err = None if rev or bits > 8 else int((d_px[0].to(torch.int16) - d_in.to(torch.int16)).abs().max().item())
+    S = frames * w * h * c
+    ab = config_alg_bytes(S, bps, L)
+    pix = frames * w * h
+    tr = (traffic or {}).get(key, {})
+    return {"key": key, "config": name, "frames": frames, "steps": steps,
+            "fwd_ms": fms, "inv_ms": ims, "fwd_Mpixel_s": pix / fms / 1e3, "inv_Mpixel_s": pix / ims / 1e3,
+            "algorithmic_bytes": ab, "fwd_frac": ab / (fms * 1e-3) / 1e9 / peak, "inv_frac": ab / (ims * 1e-3) / 1e9 / peak,
+            "fwd_traffic": tr.get("fwd"), "inv_traffic": tr.get("inv"),
+            "launches_per_forward_call": launches_per_call, "lossless_roundtrip_identical": lossless_ok,
+            "lossy_roundtrip_max_abs_error": max_err}
 
 
 _JSON_FD = None
@@ -206,22 +297,41 @@ def emit(line):
         os.write(_JSON_FD, data)
 
 
+def workload_config(frames, world, streams):
+    """The `config` object of BOTH arms (the driver compares them key by key)."""
+    frame_bytes = PIX * 2
+    return {"workload": WORKLOAD, "frames_per_gpu_per_step": frames, "direction": "forward", "levels": LEVELS,
+            "cache": "inputs larger than L2 (%.0f MB in + %.0f MB out per step per GPU)" % (frames * frame_bytes / 1e6, frames * PIX * 4 / 1e6),
+            "parallelism": "frame-sharded, %d rank(s), no collective" % world,
+            "streams": streams}
+
+
 def run_reference(args):
+    """CPU arm: the oracle C port of the reference's Go loops (the Go binary cannot be built in this image) on every host
+    core, one frame per thread, on the same workload / config / steps / warm-up as the CUDA arm.  Each step is a BOUNDED
+    SAMPLE of the step's batch (as many frames as there are host threads, at most the batch): Mpixel/s does not depend on
+    the sample size because frames are independent, and K + W steps then end within a few minutes."""
     rank, _, world = dist_env()
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    frames = max(1, min(cores, 32))  # one frame per host thread ("goroutine-per-frame" upper bound), bounded sample
-    steps = min(args.steps, 5)
-    warm = min(args.warmup, 1)
-    val, ms = cpu_leg(cores, frames, steps, warm)
+    frames = max(1, min(cores, args.frames))  # one frame per host thread ("goroutine-per-frame" upper bound)
+    steps, warm = args.steps, max(args.warmup, 3)
+    # keep the whole run near two minutes whatever the host: shrink the per-step sample, never the step count
+    probe, _ = cpu_leg(cores, frames, 1, 0)
+    est = (steps + warm) * frames * PIX / (probe * 1e6)
+    while est > 150 and frames > 1:
+        frames = max(1, frames // 2)
+        est /= 2
+    val, ms = cpu_leg(min(cores, frames), frames, steps, warm)
     line = {
-        "impl": "reference", "metric": "J2K DWT+MCT+quant Mpixel/s", "value": val, "unit": "Mpixel/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": "J2K DWT+MCT+quant Mpixel/s", "value": val, "unit": "Mpixel/s", "n_gpus": world,
         "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "frames_per_step": frames, "direction": "forward"},
+        "dtype": "f32", "data": "synthetic", "config": workload_config(args.frames, world, max(1, args.streams)),
         "cpu_baseline": {"value": val, "unit": "Mpixel/s", "cores": min(cores, frames), "kind": "port",
-                         "sample": f"{frames} C2 frames per step, one frame per thread, oracle C port of the Go loops "
-                                   f"(gcc -O2 -ffp-contract=off); the Go reference itself cannot run here (no Go toolchain)"},
+                         "sample": f"{frames} of the step's {args.frames} C2 frames per step ({steps} steps, {warm} warm-up), one frame "
+                                   f"per thread on {cores} host cores; oracle C port of the Go loops (gcc -O2 -ffp-contract=off); "
+                                   f"the Go reference itself cannot run here (no Go toolchain)"},
         "e2e": {"value": val, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -240,6 +350,8 @@ def main():
     ap.add_argument("--no-inverse", action="store_true", help="skip the supplementary inverse-direction leg")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
     ap.add_argument("--sustained-seconds", type=float, default=3.0, help="length of the sustained-load leg (0 = skip)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the legs of the other BASELINE configs (C1, C3, C4, C5)")
+    ap.add_argument("--config-steps", type=int, default=20, help="timed launches per direction of each of the other configs")
     args = ap.parse_args()
     protect_stdout()
     if args.impl == "reference":
@@ -385,9 +497,13 @@ def main():
         ip = abi.inv_params(W, H, 1, BITS, False, num_levels=LEVELS, reversible=False, steps=dec)
         d_pix = [torch.empty((B, frame_bytes), dtype=torch.uint8, device="cuda") for _ in range(NS)]
 
+        torch.cuda.synchronize()
+        d_dec = t1_roundtrip(torch, d_outs[0])  # what the block decoder would hand back (not timed)
+        torch.cuda.synchronize()
+
         def istep(i=0):
             k = i % NS
-            ctx.inverse_device(ip, B, d_outs[0].data_ptr(), d_pix[k].data_ptr(), frame_bytes, stream=streams[k].cuda_stream)
+            ctx.inverse_device(ip, B, d_dec.data_ptr(), d_pix[k].data_ptr(), frame_bytes, stream=streams[k].cuda_stream)
 
         for i in range(warm * NS):
             istep(i)
@@ -520,6 +636,21 @@ def main():
         # the e2e results must be the same coefficients as the resident run
         same = all(bool(torch.equal(torch.from_numpy(np.asarray(h[B - 1])).cuda(), d_out[B - 1])) for h in h_outs)
 
+    # ---- the other BASELINE configs, resident, both directions (every rank runs them; rank 0's numbers are reported)
+    configs = None
+    if not args.no_configs:
+        traffic_cfg = None
+        if os.path.exists(tpath):
+            try:
+                traffic_cfg = json.load(open(tpath)).get("configs")
+            except Exception:
+                traffic_cfg = None
+        configs = []
+        for cfg in OTHER_CONFIGS:
+            barrier()
+            configs.append(run_config(ctx, torch, cfg, max(3, args.config_steps), peak, traffic_cfg))
+        barrier()
+
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         v, ms = cpu_leg(1, 2, 5, 1)  # 2 frames x (1 warm-up + 5 steps) ~ 11 s of single-thread CPU work
@@ -532,11 +663,9 @@ def main():
             "metric": "J2K DWT+MCT+quant Mpixel/s", "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
             "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": B, "direction": "forward", "levels": LEVELS,
-                       "cache": "inputs larger than L2 (%.0f MB in + %.0f MB out per step per GPU)" % (B * frame_bytes / 1e6, B * PIX * 4 / 1e6),
-                       "parallelism": "frame-sharded, %d rank(s), no collective" % world,
-                       "streams": NS},
-            "roofline": roofline, "sustained": sustained, "inverse": inverse, "code_blocks": blocks_leg, "cpu_baseline": cpu,
+            "config": workload_config(B, world, NS),
+            "roofline": roofline, "sustained": sustained, "inverse": inverse, "configs": configs, "code_blocks": blocks_leg,
+            "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": "Mpixel/s", "h2d_bytes_per_step": B * frame_bytes, "d2h_bytes_per_step": B * PIX * 4,
                     "steps": e2e_steps, "matches_resident": same, "sync_value": e2e_sync,
                     "api": "j2k_submit_forward / j2k_wait, two steps in flight (sync_value: blocking j2k_forward_batch)"},

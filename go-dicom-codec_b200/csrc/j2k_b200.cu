@@ -18,10 +18,15 @@
 #include <string.h>
 
 #include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/j2k_b200.h"
@@ -38,7 +43,12 @@ using namespace j2k;
 
 namespace {
 
+// Error text lives in two places: the calling thread (context-free calls: j2k_init, the size / table helpers) and the
+// context the failing call ran on.  A cgo caller's goroutine may be moved to another OS thread between the failing call
+// and j2k_last_error(); the per-context copy (and j2k_last_error_copy) is what makes the message survive that.
 thread_local std::string t_err = "";
+thread_local j2k_ctx* t_cur_ctx = nullptr;   // context of the API call running on this thread (CtxGuard)
+void publish_error(j2k_ctx* ctx, const char* msg);
 
 int fail(int code, const char* fmt, ...) {
     char buf[512];
@@ -47,8 +57,15 @@ int fail(int code, const char* fmt, ...) {
     vsnprintf(buf, sizeof buf, fmt, ap);
     va_end(ap);
     t_err = buf;
+    if (t_cur_ctx) publish_error(t_cur_ctx, buf);
     return code;
 }
+
+struct CtxGuard {  // first statement of every entry point that takes a context
+    j2k_ctx* prev;
+    explicit CtxGuard(j2k_ctx* c) : prev(t_cur_ctx) { if (c) t_cur_ctx = c; }
+    ~CtxGuard() { t_cur_ctx = prev; }
+};
 
 #define CK(call)                                                                                         \
     do {                                                                                                 \
@@ -190,8 +207,26 @@ struct PwLaunch {
 
 struct Plan;
 
+// Pinned staging of one device for caller-owned PAGEABLE buffers (SURVEY 8b "Ownership": a Go []byte from
+// PixelData.GetFrame is pageable; the synchronous calls move it through C-owned pinned memory).  A ring of chunks per
+// direction: host threads memcpy a chunk while the copy engine moves the previous ones, so the upload of sub-batch b+1,
+// the kernels of b and the download of b-1 overlap exactly as they do for pinned callers.
+struct Stager {
+    size_t CHUNK = 4u << 20;   // bytes per staging chunk (env J2K_STAGE_CHUNK_KB: tests use small chunks)
+    static constexpr int NSLOT = 8;
+    unsigned char* up[NSLOT] = {};
+    unsigned char* down[NSLOT] = {};
+    cudaEvent_t up_ev[NSLOT] = {}, down_ev[NSLOT] = {};
+    bool up_busy[NSLOT] = {};
+    int up_next = 0;
+    bool ready = false;
+    struct Pending { unsigned char* dst; const unsigned char* src; size_t bytes; };  // device -> pageable host, not yet issued
+    std::vector<Pending> pending;
+};
+
 struct DeviceCtx {
     int dev = 0;
+    Stager stg;
     cudaStream_t s_main = nullptr, s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_t[4] = {nullptr, nullptr, nullptr, nullptr};      // timing
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
@@ -199,6 +234,7 @@ struct DeviceCtx {
     DevBuf in[2], out[2], planes[2], api[8];
     DevBuf blk[2], nbp[2];  // code-block interface: block-major planes and per-block numbps of a sub-batch
     std::map<std::string, std::unique_ptr<Plan>> plans;
+    long long use_clock = 0;   // LRU stamps of `plans`
     std::map<std::string, std::unique_ptr<struct BlockTable>> block_tables;
 };
 
@@ -221,6 +257,7 @@ struct Plan {
     std::vector<LevelLaunch> levels;   // in execution order
     std::vector<PwLaunch> pre, post;   // pointwise launches before / after the level launches
     int launches_per_run = 0;
+    long long last_use = 0;
     ~Plan() { tables.release(); temp.release(); sa.release(); sb.release(); ctemp.release(); ctl.release(); }
 };
 
@@ -229,6 +266,16 @@ struct Plan {
 struct j2k_ctx {
     std::vector<DeviceCtx> devs;
     std::mutex mu;
+    std::mutex err_mu;
+    std::string last_err;       // message of the most recent failing call on this context (any thread)
+    long long err_seq = 0;      // number of failures so far
+    // host threads that fill / drain the pinned staging chunks of pageable callers (started on first use)
+    std::vector<std::thread> workers;
+    std::mutex wq_mu;
+    std::condition_variable wq_cv, wq_done;
+    std::deque<std::function<void()>> wq;
+    int wq_inflight = 0;
+    bool wq_stop = false;
     std::atomic<long long> launches{0};
     j2k_timing last{};
     std::vector<void*> pinned;
@@ -244,6 +291,12 @@ struct j2k_ctx {
 };
 
 namespace {
+
+void publish_error(j2k_ctx* ctx, const char* msg) {
+    std::lock_guard<std::mutex> lk(ctx->err_mu);
+    ctx->last_err = msg;
+    ctx->err_seq++;
+}
 
 // ------------------------------------------------------------------ level kernel dispatch
 
@@ -448,6 +501,18 @@ void set_geom(LevelArgs& a, const LevelGeom& g) {
     a.hskip = g.w <= 1; a.vskip = g.h <= 1;
 }
 
+// The quantizer computes the IEEE quotient c / step' from the correctly rounded reciprocal (Markstein: q0 = c * r,
+// e = fma(-q0, step', c), q = fma(e, r, q0); tests/test_div_markstein.py).  That is exact when step' is a normal float32
+// whose significand is not all ones (the divisor class the published theorem excludes) and whose exponent leaves room
+// for q0 and e next to |c| in {0} U [2^-40, 2^30] (coefficients of <= 16-bit samples).  Runtime steps have 11 fraction bits
+// (quantization.go:130-154), so every step the reference produces qualifies; any other step takes the IEEE division.
+bool markstein_safe(float step_eff) {
+    uint32_t u;
+    memcpy(&u, &step_eff, 4);
+    const int ex = (int)((u >> 23) & 0xFF) - 127;
+    return (u >> 31) == 0 && ex >= -40 && ex <= 40 && (u & 0x7FFFFFu) != 0x7FFFFFu;
+}
+
 // Quantizer / dequantizer mode of band `idx` (QCD order).
 void band_mode_fwd(const Spec& s, int idx, BandIO& b) {
     b.shift = 0; b.step = 1.f; b.rcp = 1.f; b.scale = 1.f;
@@ -461,8 +526,8 @@ void band_mode_fwd(const Spec& s, int idx, BandIO& b) {
     if (s.steps[idx] <= 0) { b.mode = Q_ROUND; return; }  // encoder.go:2320-2321
     b.mode = Q_QUANT;
     b.step = (float)s.steps[idx];                          // float32(stepSize), encoder.go:2323
-    b.rcp = 1.0f / b.step;                                 // correctly rounded reciprocal for div_by_step
     b.scale = s.htj2k ? 1.f : 64.f;                        // encoder.go:2312-2315
+    b.rcp = markstein_safe(b.step) && markstein_safe(b.step / b.scale) ? 1.0f / b.step : 0.f;  // 0: div_by_step divides
 }
 void band_mode_inv(const Spec& s, int idx, BandIO& b) {
     b.shift = 0; b.step = 1.f; b.rcp = 1.f; b.scale = 1.f;
@@ -493,8 +558,8 @@ int env_int(const char* name, int dflt) {
 }
 
 // Job decomposition of one ring segment: even column strips, row chunks sized for ~2 jobs per resident warp.
-void ring_chunks(RingSeg& g, int NP, int n_cols_total_hint, int level) {
-    int VP = 30 * NP;  // 32 lanes minus one halo lane per side (9/7 needs 2 pairs, 5/3 one: both fit NP >= 2)
+void ring_chunks(RingSeg& g, int NP, int n_cols_total_hint, int level, int halo_lanes = 2) {
+    int VP = (32 - halo_lanes) * NP;  // 32 lanes minus one halo lane per side (9/7 needs 2 pairs, 5/3 one: both fit NP >= 2); halo-free: 32
     // strips are a multiple of 8 pairs wide: every band-row piece a warp stores (and every pixel-row piece of the inverse)
     // then covers whole 32-byte sectors, no partial-sector writes at the strip seams (+3 % on C2)
     int align = 8 > NP ? 8 : NP;
@@ -695,7 +760,10 @@ int build_ring_fwd_impl(const Spec& s, Plan& P, const std::vector<long long>& ta
             FastQ& q = g.q[bi];
             q.mode = b.mode; q.shift = 0; q.step = 1.f; q.rcp = 1.f;
             if (WT == 53) { if (b.mode == Q_SHIFT) q.shift = b.shift; else if (b.mode != Q_RAW) return 0; }
-            else if (b.mode == Q_QUANT) { q.step = b.step / b.scale; q.rcp = 1.0f / q.step; }  // scale is a power of two: exact
+            else if (b.mode == Q_QUANT) {
+                if (b.rcp == 0.f) return 0;  // not a Markstein-safe step: the per-level kernels divide (div_by_step)
+                q.step = b.step / b.scale; q.rcp = 1.0f / q.step;  // scale is a power of two: exact
+            }
             else if (b.mode != Q_RAW) return 0;
         }
         g.rcpE = make_float2(g.q[0].rcp, g.q[2].rcp); g.nstE = make_float2(-g.q[0].step, -g.q[2].step);
@@ -783,7 +851,7 @@ int ring_dispatch_fwd(const RingPlan& R, const RingArgs& A, unsigned grid, cudaS
 
 
 bool ring_inv_variant_supported(int WT, int NP, int NC, int OUT, int MCT) {
-    if (NC == 3) return NP == 2 && (OUT == IN_U8 || OUT == IN_U16) && MCT == (WT == 53 ? MCTK_RCT : MCTK_ICT);
+    if (NC == 3) return NP == (WT == 97 ? J2K_INV_RGB_NP : 2) && (OUT == IN_U8 || OUT == IN_U16) && MCT == (WT == 53 ? MCTK_RCT : MCTK_ICT);
     if (NP != 4 || MCT != MCTK_NONE) return false;
     if (OUT == IN_U8 || OUT == IN_U16) return true;
     return OUT == (WT == 53 ? IN_I32 : IN_F32);
@@ -828,7 +896,7 @@ int build_ring_inv_impl(const Spec& s, Plan& P, const std::vector<long long>& ta
         RingSeg& g = R.args.seg[si];
         const bool first = l.level == 1;
         const bool raw_out = l.KIND == IN_U8 || l.KIND == IN_U16;
-        const int NP = l.NC == 3 ? 2 : 4;
+        const int NP = l.NC == 3 ? (WT == 97 ? J2K_INV_RGB_NP : 2) : 4;
         const int ES = l.KIND == IN_U8 ? 1 : (l.KIND == IN_U16 ? 2 : 4);
         const int PB = ES * (raw_out ? l.NC : 1);
         if (a.px != 0 || a.hskip || a.vskip) return 0;
@@ -878,7 +946,7 @@ int build_ring_inv_impl(const Spec& s, Plan& P, const std::vector<long long>& ta
             for (int i = 0; i < a.n_items; i++)
                 if (a.planes_off && (tab[(size_t)(a.planes_off - (const long long*)P.tables.p) + i] % 4)) return 0;
         }
-        ring_chunks(g, NP, g.n_items, l.level);
+        ring_chunks(g, NP, g.n_items, l.level, (J2K_INV_HALO_FREE && WT == 53) ? 0 : 2);
         g.dep_seg = -1; g.dep_div = 1; g.dep_target = 0; g.dep_mul = 1;
         {
             // producer: same class, next coarser level (absent for the coarsest level of the class)
@@ -918,14 +986,14 @@ int build_ring_inv_impl(const Spec& s, Plan& P, const std::vector<long long>& ta
 
 #define RING_INV_CASE(wt, np, nc, out, mct)                                                                                  \
     if (R.WT == wt && R.NP1 == np && R.NC1 == nc && R.IN1 == out && R.MCT1 == mct) {                                         \
-        if (query) return ring_blocks_per_sm((const void*)inv_ring_kernel<wt, np, nc, out, mct>, J2K_INV_CTA_SMEM);         \
-        J2K_LAUNCH_SMEM((inv_ring_kernel<wt, np, nc, out, mct>), grid, J2K_RING_WARPS * 32, J2K_INV_CTA_SMEM, st, A);       \
+        if (query) return ring_blocks_per_sm((const void*)inv_ring_kernel<wt, np, nc, out, mct>, (inv_cta_smem<wt, nc>()));   \
+        J2K_LAUNCH_SMEM((inv_ring_kernel<wt, np, nc, out, mct>), grid, J2K_RING_WARPS * 32, (inv_cta_smem<wt, nc>()), st, A); \
         return 0;                                                                                                           \
     }
 
 int ring_dispatch_inv(const RingPlan& R, const RingArgs& A, unsigned grid, cudaStream_t st, bool query) {
     RING_INV_CASE(97, 4, 1, IN_U8, MCTK_NONE) RING_INV_CASE(97, 4, 1, IN_U16, MCTK_NONE)
-    RING_INV_CASE(97, 2, 3, IN_U8, MCTK_ICT) RING_INV_CASE(97, 2, 3, IN_U16, MCTK_ICT)
+    RING_INV_CASE(97, J2K_INV_RGB_NP, 3, IN_U8, MCTK_ICT) RING_INV_CASE(97, J2K_INV_RGB_NP, 3, IN_U16, MCTK_ICT)
     RING_INV_CASE(97, 4, 1, IN_F32, MCTK_NONE)
     RING_INV_CASE(53, 4, 1, IN_U8, MCTK_NONE) RING_INV_CASE(53, 4, 1, IN_U16, MCTK_NONE)
     RING_INV_CASE(53, 2, 3, IN_U8, MCTK_RCT) RING_INV_CASE(53, 2, 3, IN_U16, MCTK_RCT)
@@ -1190,7 +1258,10 @@ int build_plan(const Spec& s, int nframes, long long frame_samples, Plan& P) {
                     FastQ& q = l.fq.q[bi];
                     q.mode = b.mode; q.shift = 0; q.step = 1.f; q.rcp = 1.f;
                     if (WT == 53) { if (b.mode == Q_SHIFT) q.shift = b.shift; else if (b.mode != Q_RAW) ok = false; }
-                    else if (b.mode == Q_QUANT) { q.step = b.step / b.scale; q.rcp = 1.0f / q.step; }  // scale is a power of two: exact
+                    else if (b.mode == Q_QUANT) {
+                        if (b.rcp == 0.f) ok = false;  // not a Markstein-safe step: the generic kernel divides
+                        q.step = b.step / b.scale; q.rcp = 1.0f / q.step;  // scale is a power of two: exact
+                    }
                     else if (b.mode != Q_RAW) ok = false;
                 }
                 l.fast = ok;
@@ -1615,6 +1686,7 @@ int get_block_table(DeviceCtx& d, const Spec& s, int cbw, int cbh, long long coe
     int rc = T->tab.ensure(host.size() * sizeof(BlockEntry) + 16);
     if (rc) return rc;
     if (!host.empty()) CK(cudaMemcpy(T->tab.p, host.data(), host.size() * sizeof(BlockEntry), cudaMemcpyHostToDevice));
+    CK(cudaDeviceSynchronize());  // the table is read from non-blocking streams (see get_plan)
     *out = T.get();
     d.block_tables[key] = std::move(T);
     return 0;
@@ -1625,8 +1697,10 @@ int launch_gather(j2k_ctx* ctx, BlockTable& T, int nframes, const int32_t* d_coe
     const long long total = (long long)T.nblocks * nframes;
     if (total <= 0) return 0;
     const unsigned grid = (unsigned)((total + 3) / 4);
+    // the 128-bit row copies need 16-byte aligned planes (a sliced device tensor may not be): scalar copies otherwise
+    const int vec_ok = ((((uintptr_t)d_coeffs) | ((uintptr_t)d_blocks)) & 15u) == 0;
     J2K_LAUNCH(gather_blocks_kernel, grid, 128, st, (const int*)d_coeffs, T.coeffs_per_frame, (const BlockEntry*)T.tab.p, T.nblocks, total,
-               (int*)d_blocks, (int*)d_numbps, sub6 ? 1 : 0);
+               (int*)d_blocks, (int*)d_numbps, sub6 ? 1 : 0, vec_ok);
     CK(cudaGetLastError());
     ctx->launches++;
     return 0;
@@ -1650,8 +1724,9 @@ int launch_scatter(j2k_ctx* ctx, BlockTable& T, int nframes, const int32_t* d_bl
     const long long total = (long long)T.nblocks * nframes;
     if (total <= 0) return 0;
     const unsigned grid = (unsigned)((total + 3) / 4);
+    const int vec_ok = ((((uintptr_t)d_coeffs) | ((uintptr_t)d_blocks)) & 15u) == 0;
     J2K_LAUNCH(scatter_blocks_kernel, grid, 128, st, (const int*)d_blocks, T.coeffs_per_frame, (const BlockEntry*)T.tab.p, T.nblocks, total,
-               (int*)d_coeffs, roi);
+               (int*)d_coeffs, roi, vec_ok);
     CK(cudaGetLastError());
     ctx->launches++;
     return 0;
@@ -1659,19 +1734,74 @@ int launch_scatter(j2k_ctx* ctx, BlockTable& T, int nframes, const int32_t* d_bl
 
 // A plan owns its scratch (LL ping-pong planes, job-control block): plans are cached per stream so that launches the
 // caller enqueues on different streams may overlap (the tail of one batch under the head of the next).
+// Cache key of a parameter block: only what the plan depends on.  Callers (C, Go) hand over structs whose padding, reserved
+// words and unused tail entries (steps beyond n_steps, bindings beyond n_bindings, the matrix of an unused MCT mode) hold
+// whatever was on their stack; keyed on the raw bytes every such call would build a new plan.
+template <typename P>
+std::string canonical_params(const P& p, bool is_fwd) {
+    P k;
+    memset(&k, 0, sizeof k);
+    if constexpr (std::is_same<P, j2k_fwd_params>::value) {
+        k.width = p.width; k.height = p.height; k.tile_width = p.tile_width; k.tile_height = p.tile_height;
+        k.fuse_t1_shift = p.reversible && !p.htj2k ? (p.fuse_t1_shift != 0) : 0;
+    } else {
+        k.xsiz = p.xsiz; k.ysiz = p.ysiz; k.xosiz = p.xosiz; k.yosiz = p.yosiz;
+        k.xtsiz = p.xtsiz; k.ytsiz = p.ytsiz; k.xtosiz = p.xtosiz; k.ytosiz = p.ytosiz;
+        k.fuse_t1_halve = p.reversible && !p.htj2k ? (p.fuse_t1_halve != 0) : 0;
+    }
+    (void)is_fwd;
+    k.components = p.components; k.bit_depth = p.bit_depth; k.is_signed = p.is_signed != 0; k.num_levels = p.num_levels;
+    k.reversible = p.reversible != 0; k.htj2k = p.htj2k != 0; k.mct_mode = p.mct_mode;
+    const int C = p.components < 0 ? 0 : (p.components > J2K_MAX_COMPONENTS ? J2K_MAX_COMPONENTS : p.components);
+    if (p.mct_mode == J2K_MCT_CUSTOM_INT || p.mct_mode == J2K_MCT_CUSTOM_Q13 || p.mct_mode == J2K_MCT_CUSTOM_FLOAT) {
+        for (int i = 0; i < C * C; i++) k.mct_matrix[i] = p.mct_matrix[i];
+        k.mct_has_offsets = p.mct_has_offsets != 0;
+        if (k.mct_has_offsets) for (int i = 0; i < C; i++) k.mct_offsets[i] = p.mct_offsets[i];
+    }
+    if (p.mct_mode == J2K_MCT_BINDINGS) {
+        k.n_bindings = p.n_bindings;
+        for (int b = 0; b < p.n_bindings && b < J2K_MAX_BINDINGS; b++) {
+            const j2k_mct_binding& q = p.bindings[b];
+            j2k_mct_binding& o = k.bindings[b];
+            o.n_components = q.n_components; o.element_type = q.element_type; o.has_matrix = q.has_matrix != 0; o.has_offsets = q.has_offsets != 0;
+            const int n = q.n_components > 0 && q.n_components <= J2K_MAX_COMPONENTS ? q.n_components : C;
+            for (int i = 0; i < q.n_components && i < J2K_MAX_COMPONENTS; i++) o.component_ids[i] = q.component_ids[i];
+            if (o.has_matrix) for (int i = 0; i < n * n; i++) o.matrix[i] = q.matrix[i];
+            if (o.has_offsets) for (int i = 0; i < n; i++) o.offsets[i] = q.offsets[i];
+        }
+    }
+    if (!p.reversible) {
+        k.n_steps = p.n_steps;
+        for (int i = 0; i < p.n_steps && i < J2K_MAX_BANDS; i++) k.steps[i] = p.steps[i];
+    }
+    return std::string((const char*)&k, sizeof k);
+}
+
 int get_plan(DeviceCtx& d, const Spec& s, const void* pblob, size_t pbytes, int nframes, long long frame_samples, Plan** out,
              const void* stream_tag = nullptr) {
-    std::string key((const char*)pblob, pbytes);
+    std::string key;
+    if (pbytes == sizeof(j2k_fwd_params) && s.fwd && !s.direct) key = canonical_params(*(const j2k_fwd_params*)pblob, true);
+    else if (pbytes == sizeof(j2k_inv_params) && !s.fwd && !s.direct) key = canonical_params(*(const j2k_inv_params*)pblob, false);
+    else key.assign((const char*)pblob, pbytes);
     char tail[128];
     snprintf(tail, sizeof tail, "|%d|%d|%lld|%d|%d|%d|%p", s.fwd ? 1 : 0, nframes, frame_samples, s.planar_in ? 1 : 0, s.want_planes ? 1 : 0,
              s.direct ? 1 : 0, stream_tag);
     key += tail;
     auto it = d.plans.find(key);
-    if (it != d.plans.end()) { *out = it->second.get(); return 0; }
-    if (d.plans.size() >= 24) d.plans.clear();
+    if (it != d.plans.end()) { it->second->last_use = ++d.use_clock; *out = it->second.get(); return 0; }
+    if (d.plans.size() >= 24) {  // evict the least recently used plan (its buffers are freed: cudaFree waits for the device)
+        auto old = d.plans.begin();
+        for (auto jt = d.plans.begin(); jt != d.plans.end(); ++jt)
+            if (jt->second->last_use < old->second->last_use) old = jt;
+        d.plans.erase(old);
+    }
     std::unique_ptr<Plan> P(new Plan());
     int rc = build_plan(s, nframes, frame_samples, *P);
     if (rc) return rc;
+    // build_plan uploads its tables and zeroes the job-control block with plain cudaMemcpy / cudaMemset (legacy stream, pageable
+    // sources); the plan runs on non-blocking streams that are not ordered against those: finish them before the first launch
+    CK(cudaDeviceSynchronize());
+    P->last_use = ++d.use_clock;
     *out = P.get();
     d.plans[key] = std::move(P);
     return 0;
@@ -1681,6 +1811,152 @@ int set_dev(j2k_ctx* ctx, int di) {
     if (!ctx) return fail(J2K_ERR_INVALID_ARG, "context is NULL");
     if (di < 0 || di >= (int)ctx->devs.size()) return fail(J2K_ERR_INVALID_ARG, "device index %d out of range", di);
     CK(cudaSetDevice(ctx->devs[di].dev));
+    return 0;
+}
+
+// ------------------------------------------------------------------ pageable callers: pinned staging
+
+// Is `p` page-locked host memory (j2k_acquire_buffer, cudaHostAlloc, cudaHostRegister)?  Anything else - a Go slice, a
+// numpy array, malloc - is pageable and goes through the staging ring.
+bool host_pinned(const void* p) {
+#ifdef J2K_EMU
+    (void)p;
+    return getenv("J2K_EMU_PAGEABLE") == nullptr;
+#else
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+#endif
+}
+
+void pool_start(j2k_ctx* ctx) {
+    if (!ctx->workers.empty()) return;
+    unsigned hw = std::thread::hardware_concurrency();
+    int n = env_int("J2K_STAGE_THREADS", hw >= 32 ? 8 : (hw >= 8 ? 4 : 2));
+    if (n < 1) n = 1;
+    for (int i = 0; i < n; i++)
+        ctx->workers.emplace_back([ctx] {
+            for (;;) {
+                std::function<void()> f;
+                {
+                    std::unique_lock<std::mutex> lk(ctx->wq_mu);
+                    ctx->wq_cv.wait(lk, [&] { return ctx->wq_stop || !ctx->wq.empty(); });
+                    if (ctx->wq.empty()) return;  // stop requested and nothing left
+                    f = std::move(ctx->wq.front());
+                    ctx->wq.pop_front();
+                }
+                f();
+                {
+                    std::lock_guard<std::mutex> lk(ctx->wq_mu);
+                    ctx->wq_inflight--;
+                }
+                ctx->wq_done.notify_all();
+            }
+        });
+}
+
+void pool_stop(j2k_ctx* ctx) {
+    {
+        std::lock_guard<std::mutex> lk(ctx->wq_mu);
+        ctx->wq_stop = true;
+    }
+    ctx->wq_cv.notify_all();
+    for (auto& t : ctx->workers) t.join();
+    ctx->workers.clear();
+}
+
+// memcpy split over the staging threads (the caller waits: the chunk is about to be handed to the copy engine / the user)
+void pool_copy(j2k_ctx* ctx, void* dst, const void* src, size_t n) {
+    const size_t nw = ctx->workers.size();
+    if (nw <= 1 || n < (1u << 20)) { memcpy(dst, src, n); return; }
+    size_t piece = ((n + nw - 1) / nw + 4095) & ~(size_t)4095;
+    {
+        std::lock_guard<std::mutex> lk(ctx->wq_mu);
+        for (size_t off = 0; off < n; off += piece) {
+            const size_t m = off + piece <= n ? piece : n - off;
+            unsigned char* d = (unsigned char*)dst + off;
+            const unsigned char* sp = (const unsigned char*)src + off;
+            ctx->wq.push_back([d, sp, m] { memcpy(d, sp, m); });
+            ctx->wq_inflight++;
+        }
+    }
+    ctx->wq_cv.notify_all();
+    std::unique_lock<std::mutex> lk(ctx->wq_mu);
+    ctx->wq_done.wait(lk, [&] { return ctx->wq_inflight == 0; });
+}
+
+int stager_init(j2k_ctx* ctx, DeviceCtx& d) {
+    Stager& S = d.stg;
+    if (S.ready) return 0;
+    pool_start(ctx);
+    S.CHUNK = (size_t)env_int("J2K_STAGE_CHUNK_KB", 4096) << 10;
+    if (S.CHUNK < 1024) S.CHUNK = 1024;
+    for (int k = 0; k < Stager::NSLOT; k++) {
+        CK(cudaHostAlloc((void**)&S.up[k], S.CHUNK, cudaHostAllocPortable));
+        CK(cudaHostAlloc((void**)&S.down[k], S.CHUNK, cudaHostAllocPortable));
+        CK(cudaEventCreateWithFlags(&S.up_ev[k], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&S.down_ev[k], cudaEventDisableTiming));
+    }
+    S.ready = true;
+    return 0;
+}
+
+void stager_release(DeviceCtx& d) {
+    Stager& S = d.stg;
+    for (int k = 0; k < Stager::NSLOT; k++) {
+        if (S.up[k]) cudaFreeHost(S.up[k]);
+        if (S.down[k]) cudaFreeHost(S.down[k]);
+        if (S.up_ev[k]) cudaEventDestroy(S.up_ev[k]);
+        if (S.down_ev[k]) cudaEventDestroy(S.down_ev[k]);
+        S.up[k] = S.down[k] = nullptr; S.up_ev[k] = S.down_ev[k] = nullptr;
+    }
+    S.ready = false;
+}
+
+// pageable host -> device on the upload stream, chunk by chunk through the pinned ring
+int stage_up(j2k_ctx* ctx, DeviceCtx& d, void* dst, const unsigned char* src, size_t bytes) {
+    int rc = stager_init(ctx, d);
+    if (rc) return rc;
+    Stager& S = d.stg;
+    for (size_t off = 0; off < bytes; off += S.CHUNK) {
+        const size_t n = off + S.CHUNK <= bytes ? S.CHUNK : bytes - off;
+        const int k = S.up_next;
+        S.up_next = (k + 1) % Stager::NSLOT;
+        if (S.up_busy[k]) CK(cudaEventSynchronize(S.up_ev[k]));  // the copy engine has drained this chunk
+        pool_copy(ctx, S.up[k], src + off, n);
+        CK(cudaMemcpyAsync((unsigned char*)dst + off, S.up[k], n, cudaMemcpyHostToDevice, d.s_h2d));
+        CK(cudaEventRecord(S.up_ev[k], d.s_h2d));
+        S.up_busy[k] = true;
+    }
+    return 0;
+}
+
+// device -> pageable host for everything queued in S.pending: a sliding window of NSLOT chunks in flight on the download
+// stream, each copied out to the caller's buffer as soon as its event has fired
+int stage_drain(j2k_ctx* ctx, DeviceCtx& d) {
+    Stager& S = d.stg;
+    if (S.pending.empty()) return 0;
+    int rc = stager_init(ctx, d);
+    if (rc) return rc;
+    struct Chunk { unsigned char* dst; const unsigned char* src; size_t n; };
+    std::vector<Chunk> ch;
+    for (const Stager::Pending& p : S.pending)
+        for (size_t off = 0; off < p.bytes; off += S.CHUNK)
+            ch.push_back({p.dst + off, p.src + off, off + S.CHUNK <= p.bytes ? S.CHUNK : p.bytes - off});
+    S.pending.clear();
+    size_t issued = 0, done = 0;
+    while (done < ch.size()) {
+        while (issued < ch.size() && issued - done < (size_t)Stager::NSLOT) {
+            const int k = (int)(issued % Stager::NSLOT);
+            CK(cudaMemcpyAsync(S.down[k], ch[issued].src, ch[issued].n, cudaMemcpyDeviceToHost, d.s_d2h));
+            CK(cudaEventRecord(S.down_ev[k], d.s_d2h));
+            issued++;
+        }
+        const int k = (int)(done % Stager::NSLOT);
+        CK(cudaEventSynchronize(S.down_ev[k]));
+        pool_copy(ctx, ch[done].dst, S.down[k], ch[done].n);
+        done++;
+    }
     return 0;
 }
 
@@ -1694,6 +1970,7 @@ struct HostJob {
     size_t pix_bytes_per_frame; long long coeffs_per_frame;
     int cb_w = 0, cb_h = 0;      // > 0: coefficients cross the boundary block-major (code-block interface)
     int32_t* h_numbps = nullptr; // forward, block mode: cblkNumbps per block
+    bool may_stage = true;       // synchronous call: pageable buffers go through the pinned staging ring (async: rejected)
     RoiShifts roi{};             // inverse, block mode: per-component MaxShift applied while scattering
 };
 
@@ -1708,11 +1985,29 @@ int enqueue_host_job(j2k_ctx* ctx, int di, const HostJob& J, int f0, int f1, boo
     // sub-batches: enough frames per launch to fill the GPU, at least two to overlap copies with kernels
     long long frame_samples_total = HW * s.C;
     // ~16 Msamples per sub-batch: the first upload (the only copy nothing hides) stays short, a launch still fills the GPU
-    static const long long sub_samples = (long long)env_int("J2K_SUBBATCH_MSAMPLES", 16) << 20;
+    static const long long sub_samples = env_int("J2K_SUBBATCH_SAMPLES", 0) > 0 ? (long long)env_int("J2K_SUBBATCH_SAMPLES", 0)
+                                                                                   : (long long)env_int("J2K_SUBBATCH_MSAMPLES", 16) << 20;
     int sub = (int)(sub_samples / (frame_samples_total > 0 ? frame_samples_total : 1));
     if (sub < 1) sub = 1;
     if (sub > n) sub = n;
     if (timing) CK(cudaEventRecord(d.ev_t[0], d.s_h2d));
+    // caller-owned pageable memory (a Go slice, a numpy array) moves through the pinned staging ring; pinned buffers
+    // (j2k_acquire_buffer) are handed to the copy engine as they are
+    const bool page_in = !host_pinned(J.fwd ? (const void*)J.h_pix_in : (const void*)J.h_coef_in);
+    const bool page_out = !host_pinned(J.fwd ? (const void*)J.h_coef_out : (const void*)J.h_pix_out) ||
+                          (J.h_planes && !host_pinned(J.h_planes)) || (J.h_numbps && !host_pinned(J.h_numbps));
+    if ((page_in || page_out) && !J.may_stage)
+        return fail(J2K_ERR_INVALID_ARG, "asynchronous calls need buffers from j2k_acquire_buffer (pinned); this one is pageable");
+    auto up = [&](void* dst, const unsigned char* src, size_t bytes) -> int {
+        if (page_in) return stage_up(ctx, d, dst, src, bytes);
+        CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, d.s_h2d));
+        return 0;
+    };
+    auto down = [&](void* dst, const void* src, size_t bytes) -> int {
+        if (page_out) { d.stg.pending.push_back({(unsigned char*)dst, (const unsigned char*)src, bytes}); return 0; }
+        CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, d.s_d2h));
+        return 0;
+    };
     int it = 0;
     for (int b = f0; b < f1; b += sub, it++) {
         const int nb = (b + sub <= f1) ? sub : f1 - b;
@@ -1733,13 +2028,17 @@ int enqueue_host_job(j2k_ctx* ctx, int di, const HostJob& J, int f0, int f1, boo
         if (J.fwd) {
             if (J.planar || J.frame_stride_bytes == J.pix_bytes_per_frame) {
                 const unsigned char* src = J.planar ? J.h_pix_in : J.h_pix_in + (size_t)b * J.frame_stride_bytes;
-                CK(cudaMemcpyAsync(d.in[slot].p, src, in_bytes, cudaMemcpyHostToDevice, d.s_h2d));
+                if ((rc = up(d.in[slot].p, src, in_bytes))) return rc;
+            } else if (page_in) {
+                for (int f = 0; f < nb; f++)
+                    if ((rc = up((unsigned char*)d.in[slot].p + (size_t)f * J.pix_bytes_per_frame,
+                                 J.h_pix_in + (size_t)(b + f) * J.frame_stride_bytes, J.pix_bytes_per_frame))) return rc;
             } else {
                 CK(cudaMemcpy2DAsync(d.in[slot].p, J.pix_bytes_per_frame, J.h_pix_in + (size_t)b * J.frame_stride_bytes, J.frame_stride_bytes,
                                      J.pix_bytes_per_frame, nb, cudaMemcpyHostToDevice, d.s_h2d));
             }
         } else {
-            CK(cudaMemcpyAsync(BT ? d.blk[slot].p : d.in[slot].p, J.h_coef_in + (size_t)b * J.coeffs_per_frame, in_bytes, cudaMemcpyHostToDevice, d.s_h2d));
+            if ((rc = up(BT ? d.blk[slot].p : d.in[slot].p, (const unsigned char*)(J.h_coef_in + (size_t)b * J.coeffs_per_frame), in_bytes))) return rc;
         }
         CK(cudaEventRecord(d.ev_in[slot], d.s_h2d));
         CK(cudaStreamWaitEvent(d.s_main, d.ev_in[slot], 0));
@@ -1756,23 +2055,32 @@ int enqueue_host_job(j2k_ctx* ctx, int di, const HostJob& J, int f0, int f1, boo
                                                !s.htj2k, d.s_main))) return rc;
         CK(cudaEventRecord(d.ev_k[slot], d.s_main));
         d.ev_k_used[slot] = true;
+        // pageable output: the previous sub-batch's results leave now, while this sub-batch computes (its own slot is free
+        // again before the sub-batch after this one is enqueued)
+        if (page_out && (rc = stage_drain(ctx, d))) return rc;
         CK(cudaStreamWaitEvent(d.s_d2h, d.ev_k[slot], 0));
         if (J.fwd) {
-            CK(cudaMemcpyAsync(J.h_coef_out + (size_t)b * J.coeffs_per_frame, BT ? d.blk[slot].p : d.out[slot].p, out_bytes, cudaMemcpyDeviceToHost, d.s_d2h));
-            if (BT && J.h_numbps)
-                CK(cudaMemcpyAsync(J.h_numbps + (size_t)b * BT->nblocks, d.nbp[slot].p, (size_t)nb * BT->nblocks * 4, cudaMemcpyDeviceToHost, d.s_d2h));
+            if ((rc = down(J.h_coef_out + (size_t)b * J.coeffs_per_frame, BT ? d.blk[slot].p : d.out[slot].p, out_bytes))) return rc;
+            if (BT && J.h_numbps && (rc = down(J.h_numbps + (size_t)b * BT->nblocks, d.nbp[slot].p, (size_t)nb * BT->nblocks * 4))) return rc;
         } else {
-            if (J.frame_stride_bytes == J.pix_bytes_per_frame)
-                CK(cudaMemcpyAsync(J.h_pix_out + (size_t)b * J.frame_stride_bytes, d.out[slot].p, out_bytes, cudaMemcpyDeviceToHost, d.s_d2h));
-            else
+            if (J.frame_stride_bytes == J.pix_bytes_per_frame) {
+                if ((rc = down(J.h_pix_out + (size_t)b * J.frame_stride_bytes, d.out[slot].p, out_bytes))) return rc;
+            } else if (page_out) {
+                for (int f = 0; f < nb; f++)
+                    if ((rc = down(J.h_pix_out + (size_t)(b + f) * J.frame_stride_bytes, (unsigned char*)d.out[slot].p + (size_t)f * J.pix_bytes_per_frame,
+                                   J.pix_bytes_per_frame))) return rc;
+            } else {
                 CK(cudaMemcpy2DAsync(J.h_pix_out + (size_t)b * J.frame_stride_bytes, J.frame_stride_bytes, d.out[slot].p, J.pix_bytes_per_frame,
                                      J.pix_bytes_per_frame, nb, cudaMemcpyDeviceToHost, d.s_d2h));
-            if (J.h_planes)
-                CK(cudaMemcpyAsync(J.h_planes + (size_t)b * s.C * HW, d.planes[slot].p, (size_t)nb * s.C * HW * 4, cudaMemcpyDeviceToHost, d.s_d2h));
+            }
+            if (J.h_planes && (rc = down(J.h_planes + (size_t)b * s.C * HW, d.planes[slot].p, (size_t)nb * s.C * HW * 4))) return rc;
         }
-        CK(cudaEventRecord(d.ev_out[slot], d.s_d2h));
-        d.ev_out_used[slot] = true;
+        if (!page_out) {
+            CK(cudaEventRecord(d.ev_out[slot], d.s_d2h));
+            d.ev_out_used[slot] = true;
+        }
     }
+    if (page_out && (rc = stage_drain(ctx, d))) return rc;
     if (timing) {
         CK(cudaEventRecord(d.ev_t[2], d.s_main));
         CK(cudaEventRecord(d.ev_t[3], d.s_d2h));
@@ -1791,7 +2099,9 @@ int sync_dev(j2k_ctx* ctx, int di) {
 }
 
 // Shards nframes over the devices in contiguous blocks (no collective), optionally waits.
-int run_host_batch(j2k_ctx* ctx, const HostJob& J, int nframes, bool wait, std::vector<int>* used) {
+int run_host_batch(j2k_ctx* ctx, const HostJob& J0, int nframes, bool wait, std::vector<int>* used) {
+    HostJob J = J0;
+    J.may_stage = wait;
     const int nd = (int)ctx->devs.size();
     const int per = (nframes + nd - 1) / nd;
     std::lock_guard<std::mutex> lk(ctx->mu);
@@ -1837,7 +2147,27 @@ extern "C" {
 
 int j2k_abi_version(void) { return J2K_B200_ABI_VERSION; }
 
-const char* j2k_last_error(j2k_ctx*) { return t_err.c_str(); }
+// With a context: the message of the most recent failing call ON THAT CONTEXT, whichever thread made it (copied into a
+// per-thread buffer so that the pointer stays valid); without: the calling thread's last message (j2k_init, size helpers).
+const char* j2k_last_error(j2k_ctx* ctx) {
+    if (!ctx) return t_err.c_str();
+    thread_local std::string ret;
+    std::lock_guard<std::mutex> lk(ctx->err_mu);
+    ret = ctx->last_err;
+    return ret.c_str();
+}
+
+// Copy form for bindings that must not hold a C pointer (cgo): writes at most cap - 1 bytes + NUL, returns the full length.
+size_t j2k_last_error_copy(j2k_ctx* ctx, char* buf, size_t cap) {
+    std::string msg;
+    if (ctx) { std::lock_guard<std::mutex> lk(ctx->err_mu); msg = ctx->last_err; } else msg = t_err;
+    if (buf && cap) {
+        size_t n = msg.size() < cap - 1 ? msg.size() : cap - 1;
+        memcpy(buf, msg.data(), n);
+        buf[n] = 0;
+    }
+    return msg.size();
+}
 
 int j2k_init(j2k_ctx** out, const int* devices, int n_devices) {
     if (!out) return fail(J2K_ERR_INVALID_ARG, "ctx out pointer is NULL");
@@ -1891,6 +2221,8 @@ void j2k_shutdown(j2k_ctx* ctx) {
         for (int k = 0; k < 2; k++) { cudaEventDestroy(d.ev_in[k]); cudaEventDestroy(d.ev_k[k]); cudaEventDestroy(d.ev_out[k]); }
         cudaStreamDestroy(d.s_main); cudaStreamDestroy(d.s_h2d); cudaStreamDestroy(d.s_d2h);
     }
+    pool_stop(ctx);
+    for (auto& d : ctx->devs) { cudaSetDevice(d.dev); stager_release(d); }
     for (auto& kv : ctx->tickets) for (auto& t : kv.second) cudaEventDestroy(t.ev);
     for (void* p : ctx->pinned) cudaFreeHost(p);
     for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
@@ -1901,6 +2233,7 @@ int j2k_device_count(const j2k_ctx* ctx) { return ctx ? (int)ctx->devs.size() : 
 int64_t j2k_launch_count(const j2k_ctx* ctx) { return ctx ? (int64_t)ctx->launches.load() : 0; }
 
 int j2k_last_timing(j2k_ctx* ctx, j2k_timing* out) {
+    CtxGuard cg_(ctx);
     if (!ctx || !out) return fail(J2K_ERR_INVALID_ARG, "NULL argument");
     std::lock_guard<std::mutex> lk(ctx->mu);
     *out = ctx->last;
@@ -1908,6 +2241,7 @@ int j2k_last_timing(j2k_ctx* ctx, j2k_timing* out) {
 }
 
 int j2k_set_profiling(j2k_ctx* ctx, int enabled) {
+    CtxGuard cg_(ctx);
     if (!ctx) return fail(J2K_ERR_INVALID_ARG, "context is NULL");
     std::lock_guard<std::mutex> lk(ctx->mu);
     ctx->profiling = enabled != 0;
@@ -1915,6 +2249,7 @@ int j2k_set_profiling(j2k_ctx* ctx, int enabled) {
 }
 
 int j2k_get_profile(j2k_ctx* ctx, float* ms, int32_t* levels, int max) {
+    CtxGuard cg_(ctx);
     if (!ctx || !ms || max < 0) return fail(J2K_ERR_INVALID_ARG, "bad argument");
     std::lock_guard<std::mutex> lk(ctx->mu);
     int n = (int)ctx->prof_level.size();
@@ -1928,6 +2263,7 @@ int j2k_get_profile(j2k_ctx* ctx, float* ms, int32_t* levels, int max) {
 }
 
 void* j2k_acquire_buffer(j2k_ctx* ctx, size_t nbytes) {
+    CtxGuard cg_(ctx);
     if (!ctx || nbytes == 0) { fail(J2K_ERR_INVALID_ARG, "NULL context or zero size"); return nullptr; }
     void* p = nullptr;
     cudaSetDevice(ctx->devs[0].dev);
@@ -1972,6 +2308,7 @@ int j2k_inv_tile_bounds(const j2k_inv_params* p, int idx, int32_t b[4]) {
 
 static int forward_host(j2k_ctx* ctx, const j2k_fwd_params* p, int nframes, const void* pixels, size_t stride, int32_t* coeffs_out,
                         bool planar, bool wait, std::vector<int>* used) {
+    CtxGuard cg_(ctx);
     if (!ctx) return fail(J2K_ERR_INVALID_ARG, "context is NULL");
     Spec s;
     int rc = spec_from_fwd(p, planar, s);
@@ -1988,6 +2325,7 @@ static int forward_host(j2k_ctx* ctx, const j2k_fwd_params* p, int nframes, cons
 }
 
 int j2k_forward(j2k_ctx* ctx, const j2k_fwd_params* p, const void* pixels, size_t nbytes, int32_t* coeffs_out, size_t ncoeffs) {
+    CtxGuard cg_(ctx);
     if (!p) return fail(J2K_ERR_INVALID_ARG, "params is NULL");
     size_t need = j2k_fwd_pixel_bytes(p);
     if (nbytes < need) return fail(J2K_ERR_SIZE, "insufficient pixel data: got %zu bytes, need %zu", nbytes, need);  // encoder.go:346-348
@@ -1996,6 +2334,7 @@ int j2k_forward(j2k_ctx* ctx, const j2k_fwd_params* p, const void* pixels, size_
 }
 
 int j2k_forward_planar(j2k_ctx* ctx, const j2k_fwd_params* p, const int32_t* const* planes, int32_t* coeffs_out, size_t ncoeffs) {
+    CtxGuard cg_(ctx);
     if (!p || !planes) return fail(J2K_ERR_INVALID_ARG, "NULL argument");
     int rc = validate_common(p->width, p->height, p->components, p->bit_depth, p->num_levels);
     if (rc) return rc;
@@ -2010,11 +2349,13 @@ int j2k_forward_planar(j2k_ctx* ctx, const j2k_fwd_params* p, const int32_t* con
 }
 
 int j2k_forward_batch(j2k_ctx* ctx, const j2k_fwd_params* p, int nframes, const void* pixels, size_t frame_stride_bytes, int32_t* coeffs_out) {
+    CtxGuard cg_(ctx);
     return forward_host(ctx, p, nframes, pixels, frame_stride_bytes, coeffs_out, false, true, nullptr);
 }
 
 int j2k_forward_device(j2k_ctx* ctx, int dev, const j2k_fwd_params* p, int nframes, const void* d_pixels, size_t frame_stride_bytes,
                        int32_t* d_coeffs, void* cuda_stream) {
+    CtxGuard cg_(ctx);
     int rc = set_dev(ctx, dev);
     if (rc) return rc;
     Spec s;
@@ -2034,6 +2375,7 @@ int j2k_forward_device(j2k_ctx* ctx, int dev, const j2k_fwd_params* p, int nfram
 
 static int inverse_host(j2k_ctx* ctx, const j2k_inv_params* p, int nframes, const int32_t* coeffs_in, void* pixels_out, size_t stride,
                         int32_t* planes_out, bool wait, std::vector<int>* used) {
+    CtxGuard cg_(ctx);
     if (!ctx) return fail(J2K_ERR_INVALID_ARG, "context is NULL");
     Spec s;
     int rc = spec_from_inv(p, planes_out != nullptr, s);
@@ -2051,6 +2393,7 @@ static int inverse_host(j2k_ctx* ctx, const j2k_inv_params* p, int nframes, cons
 
 int j2k_inverse(j2k_ctx* ctx, const j2k_inv_params* p, const int32_t* coeffs_in, size_t ncoeffs, void* pixels_out, size_t nbytes,
                 int32_t* planes_out) {
+    CtxGuard cg_(ctx);
     if (!p) return fail(J2K_ERR_INVALID_ARG, "params is NULL");
     if (ncoeffs < j2k_inv_coeff_count(p)) return fail(J2K_ERR_SIZE, "coefficient buffer too small: got %zu, need %zu", ncoeffs, j2k_inv_coeff_count(p));
     size_t need = j2k_inv_pixel_bytes(p);
@@ -2060,11 +2403,13 @@ int j2k_inverse(j2k_ctx* ctx, const j2k_inv_params* p, const int32_t* coeffs_in,
 
 int j2k_inverse_batch(j2k_ctx* ctx, const j2k_inv_params* p, int nframes, const int32_t* coeffs_in, void* pixels_out,
                       size_t frame_stride_bytes, int32_t* planes_out) {
+    CtxGuard cg_(ctx);
     return inverse_host(ctx, p, nframes, coeffs_in, pixels_out, frame_stride_bytes, planes_out, true, nullptr);
 }
 
 int j2k_inverse_device(j2k_ctx* ctx, int dev, const j2k_inv_params* p, int nframes, const int32_t* d_coeffs, void* d_pixels,
                        size_t frame_stride_bytes, int32_t* d_planes, void* cuda_stream) {
+    CtxGuard cg_(ctx);
     int rc = set_dev(ctx, dev);
     if (rc) return rc;
     Spec s;
@@ -2117,6 +2462,7 @@ static j2k_fwd_params block_mode_params(const j2k_fwd_params* p) {
 
 int j2k_forward_blocks(j2k_ctx* ctx, const j2k_fwd_params* p, int cb_width, int cb_height, int nframes, const void* pixels,
                        size_t frame_stride_bytes, int32_t* blocks_out, int32_t* numbps_out) {
+    CtxGuard cg_(ctx);
     if (!ctx) return fail(J2K_ERR_INVALID_ARG, "context is NULL");
     if (!p) return fail(J2K_ERR_INVALID_ARG, "params is NULL");
     int rc = validate_cb(cb_width, cb_height);
@@ -2137,11 +2483,13 @@ int j2k_forward_blocks(j2k_ctx* ctx, const j2k_fwd_params* p, int cb_width, int 
 
 int j2k_inverse_blocks(j2k_ctx* ctx, const j2k_inv_params* p, int cb_width, int cb_height, int nframes, const int32_t* blocks_in,
                        void* pixels_out, size_t frame_stride_bytes, int32_t* planes_out) {
+    CtxGuard cg_(ctx);
     return j2k_inverse_blocks_roi(ctx, p, cb_width, cb_height, nframes, blocks_in, nullptr, pixels_out, frame_stride_bytes, planes_out);
 }
 
 int j2k_inverse_blocks_roi(j2k_ctx* ctx, const j2k_inv_params* p, int cb_width, int cb_height, int nframes, const int32_t* blocks_in,
                            const int32_t* roi_maxshift, void* pixels_out, size_t frame_stride_bytes, int32_t* planes_out) {
+    CtxGuard cg_(ctx);
     if (!ctx) return fail(J2K_ERR_INVALID_ARG, "context is NULL");
     if (!p) return fail(J2K_ERR_INVALID_ARG, "params is NULL");
     int rc = validate_cb(cb_width, cb_height);
@@ -2162,6 +2510,7 @@ int j2k_inverse_blocks_roi(j2k_ctx* ctx, const j2k_inv_params* p, int cb_width, 
 
 int j2k_gather_blocks_device(j2k_ctx* ctx, int dev, const j2k_fwd_params* p, int cb_width, int cb_height, int nframes,
                              const int32_t* d_coeffs, int32_t* d_blocks, int32_t* d_numbps, void* cuda_stream) {
+    CtxGuard cg_(ctx);
     int rc = set_dev(ctx, dev);
     if (rc) return rc;
     if (!p) return fail(J2K_ERR_INVALID_ARG, "params is NULL");
@@ -2173,16 +2522,23 @@ int j2k_gather_blocks_device(j2k_ctx* ctx, int dev, const j2k_fwd_params* p, int
     DeviceCtx& d = ctx->devs[dev];
     BlockTable* BT = nullptr;
     if ((rc = get_block_table(d, s, cb_width, cb_height, (long long)j2k_fwd_coeff_count(p), &BT))) return rc;
-    return launch_gather(ctx, *BT, nframes, d_coeffs, d_blocks, d_numbps, !s.htj2k, cuda_stream ? (cudaStream_t)cuda_stream : d.s_main);
+    // cblkNumbps counts bit planes above the 6 fractional bits of the T1 fixed point (encoder.go:3349-3362).  The coefficients
+    // carry those bits when they come from the 9/7 quantizer (scale 64) or from a 5/3 forward with fuse_t1_shift; a classic 5/3
+    // plane WITHOUT the fused shift holds plain integers (the caller shifts the block copies, encoder.go:3294-3300), whose bit
+    // length already is the count.  HTJ2K has no fixed point.
+    const bool sub6 = !s.htj2k && !(s.reversible && !s.fuse_shift);
+    return launch_gather(ctx, *BT, nframes, d_coeffs, d_blocks, d_numbps, sub6, cuda_stream ? (cudaStream_t)cuda_stream : d.s_main);
 }
 
 int j2k_scatter_blocks_device(j2k_ctx* ctx, int dev, const j2k_inv_params* p, int cb_width, int cb_height, int nframes,
                               const int32_t* d_blocks, int32_t* d_coeffs, void* cuda_stream) {
+    CtxGuard cg_(ctx);
     return j2k_scatter_blocks_roi_device(ctx, dev, p, cb_width, cb_height, nframes, d_blocks, nullptr, d_coeffs, cuda_stream);
 }
 
 int j2k_scatter_blocks_roi_device(j2k_ctx* ctx, int dev, const j2k_inv_params* p, int cb_width, int cb_height, int nframes,
                                   const int32_t* d_blocks, const int32_t* roi_maxshift, int32_t* d_coeffs, void* cuda_stream) {
+    CtxGuard cg_(ctx);
     int rc = set_dev(ctx, dev);
     if (rc) return rc;
     if (!p) return fail(J2K_ERR_INVALID_ARG, "params is NULL");
@@ -2225,6 +2581,7 @@ static int64_t make_ticket(j2k_ctx* ctx, const std::vector<int>& used) {
 
 int64_t j2k_submit_forward(j2k_ctx* ctx, const j2k_fwd_params* p, int nframes, const void* pixels, size_t frame_stride_bytes,
                            int32_t* coeffs_out) {
+    CtxGuard cg_(ctx);
     std::vector<int> used;
     int rc = forward_host(ctx, p, nframes, pixels, frame_stride_bytes, coeffs_out, false, false, &used);
     if (rc) return rc;
@@ -2233,6 +2590,7 @@ int64_t j2k_submit_forward(j2k_ctx* ctx, const j2k_fwd_params* p, int nframes, c
 
 int64_t j2k_submit_inverse(j2k_ctx* ctx, const j2k_inv_params* p, int nframes, const int32_t* coeffs_in, void* pixels_out,
                            size_t frame_stride_bytes, int32_t* planes_out) {
+    CtxGuard cg_(ctx);
     std::vector<int> used;
     int rc = inverse_host(ctx, p, nframes, coeffs_in, pixels_out, frame_stride_bytes, planes_out, false, &used);
     if (rc) return rc;
@@ -2240,6 +2598,7 @@ int64_t j2k_submit_inverse(j2k_ctx* ctx, const j2k_inv_params* p, int nframes, c
 }
 
 int j2k_wait(j2k_ctx* ctx, int64_t ticket) {
+    CtxGuard cg_(ctx);
     if (!ctx) return fail(J2K_ERR_INVALID_ARG, "context is NULL");
     std::vector<j2k_ctx::TicketEv> evs;
     {
@@ -2262,6 +2621,7 @@ int j2k_wait(j2k_ctx* ctx, int64_t ticket) {
 // ---- wavelet package API: in place on a host plane, origin (x0, y0), stride = width
 
 static int dwt_api(j2k_ctx* ctx, void* data, int width, int height, int levels, int x0, int y0, bool reversible, bool fwd, bool f64 = false) {
+    CtxGuard cg_(ctx);
     if (!ctx || !data) return fail(J2K_ERR_INVALID_ARG, "NULL argument");
     if (width <= 0 || height <= 0) return fail(J2K_ERR_INVALID_ARG, "invalid dimensions: %dx%d", width, height);
     if (levels < 0) levels = 0;
@@ -2276,7 +2636,7 @@ static int dwt_api(j2k_ctx* ctx, void* data, int width, int height, int levels, 
     s.mct_mode = J2K_MCT_NONE; s.direct = true;
     TileGeom g{0, 0, width, height, x0, y0, 0};
     s.tiles.push_back(g);
-    struct { int w, h, l, x, y, r, f; } blob = {width, height, levels, x0 & 0xfffff, y0 & 0xfffff, reversible, fwd};
+    struct { int w, h, l, x, y, r, f; } blob = {width, height, levels, x0, y0, reversible, fwd};
     Plan* P = nullptr;
     if ((rc = get_plan(d, s, &blob, sizeof blob, 1, (long long)width * height, &P))) return rc;
     size_t bytes = (size_t)width * height * 4;
@@ -2324,6 +2684,7 @@ int j2k_ll_dimensions(int width, int height, int levels, int x0, int y0, int* ll
 }
 
 int j2k_convert_f64_to_i32(j2k_ctx* ctx, const double* in, int32_t* out, size_t n) {
+    CtxGuard cg_(ctx);
     if (!ctx) return fail(J2K_ERR_INVALID_ARG, "context is NULL");
     if (n == 0) return J2K_OK;
     if (!in || !out) return fail(J2K_ERR_INVALID_ARG, "NULL buffer");
@@ -2344,6 +2705,7 @@ int j2k_convert_f64_to_i32(j2k_ctx* ctx, const double* in, int32_t* out, size_t 
 // colorspace.InterleaveComponents / DeinterleaveComponents (rgb.go:54-98)
 static int interleave_api(j2k_ctx* ctx, const int32_t* const* planes_in, int32_t* const* planes_out, int32_t* inter_out, const int32_t* inter_in,
                           size_t n, int C) {
+    CtxGuard cg_(ctx);
     if (!ctx) return fail(J2K_ERR_INVALID_ARG, "context is NULL");
     if (C <= 0 || C > 16) return fail(J2K_ERR_INVALID_ARG, "invalid number of components: %d", C);
     if (n == 0) return J2K_OK;
@@ -2373,11 +2735,13 @@ static int interleave_api(j2k_ctx* ctx, const int32_t* const* planes_in, int32_t
 }
 
 int j2k_interleave_components(j2k_ctx* ctx, const int32_t* const* components, int n_components, size_t n_pixels, int32_t* out) {
+    CtxGuard cg_(ctx);
     if (!components || !out) return fail(J2K_ERR_INVALID_ARG, "NULL buffer");
     return interleave_api(ctx, components, nullptr, out, nullptr, n_pixels, n_components);
 }
 
 int j2k_deinterleave_components(j2k_ctx* ctx, const int32_t* data, size_t n_pixels, int n_components, int32_t* const* components_out) {
+    CtxGuard cg_(ctx);
     if (!data || !components_out) return fail(J2K_ERR_INVALID_ARG, "NULL buffer");
     for (int c = 0; c < n_components; c++)
         if (!components_out[c]) return fail(J2K_ERR_INVALID_ARG, "component %d is NULL", c);
@@ -2392,6 +2756,7 @@ int j2k_dwt97_inverse(j2k_ctx* ctx, float* data, int w, int h, int levels, int x
 // ---- pointwise package APIs
 
 static int api3(j2k_ctx* ctx, int op, size_t n, const int32_t* a, const int32_t* b, const int32_t* c, int32_t* x, int32_t* y, int32_t* z) {
+    CtxGuard cg_(ctx);
     if (!ctx) return fail(J2K_ERR_INVALID_ARG, "context is NULL");
     if (n == 0) return J2K_OK;
     if (!a || !b || !c || !x || !y || !z) return fail(J2K_ERR_INVALID_ARG, "NULL buffer");
@@ -2419,6 +2784,7 @@ int j2k_ict_inverse(j2k_ctx* ctx, size_t n, const int32_t* y, const int32_t* cb,
 
 // colorspace.ConvertRGBToYCbCr / ConvertYCbCrToRGB (rgb.go:17-52): the ICT on an interleaved RGB image
 int j2k_rgb_to_ycbcr(j2k_ctx* ctx, const int32_t* rgb, int width, int height, int32_t* y, int32_t* cb, int32_t* cr) {
+    CtxGuard cg_(ctx);
     if (!ctx) return fail(J2K_ERR_INVALID_ARG, "context is NULL");
     if (width <= 0 || height <= 0) return J2K_OK;
     if (!rgb || !y || !cb || !cr) return fail(J2K_ERR_INVALID_ARG, "NULL buffer");
@@ -2442,6 +2808,7 @@ int j2k_rgb_to_ycbcr(j2k_ctx* ctx, const int32_t* rgb, int width, int height, in
 }
 
 int j2k_ycbcr_to_rgb(j2k_ctx* ctx, const int32_t* y, const int32_t* cb, const int32_t* cr, int width, int height, int32_t* rgb) {
+    CtxGuard cg_(ctx);
     if (!ctx) return fail(J2K_ERR_INVALID_ARG, "context is NULL");
     if (width <= 0 || height <= 0) return J2K_OK;
     if (!rgb || !y || !cb || !cr) return fail(J2K_ERR_INVALID_ARG, "NULL buffer");
@@ -2466,6 +2833,7 @@ int j2k_ycbcr_to_rgb(j2k_ctx* ctx, const int32_t* y, const int32_t* cb, const in
 }
 
 static int api1(j2k_ctx* ctx, int op, const void* in, void* out, size_t n, double step) {
+    CtxGuard cg_(ctx);
     if (!ctx) return fail(J2K_ERR_INVALID_ARG, "context is NULL");
     if (n == 0) return J2K_OK;
     if (!in || !out) return fail(J2K_ERR_INVALID_ARG, "NULL buffer");

@@ -115,10 +115,11 @@ __device__ __forceinline__ float lift97(float x, float l, float r, float c) {
 }
 
 // IEEE-correct c / step from a correctly rounded reciprocal (Markstein): q0 = c*r, e = c - q0*step
-// exactly (fma), q = q0 + e*r.  Outside the safe exponent range fall back to the true division.
+// exactly (fma), q = q0 + e*r.  Outside the safe exponent range, and for steps the host marks with rcp == 0
+// (markstein_safe in j2k_b200.cu: all-ones significand, extreme exponents), it is the true division.
 __device__ __forceinline__ float div_by_step(float c, float step, float rcp) {
     float a = fabsf(c);
-    if (a > 1e-30f && a < 1e30f) {
+    if (rcp != 0.f && a > 1e-30f && a < 1e30f) {
         float q0 = __fmul_rn(c, rcp);
         float e = __fmaf_rn(-q0, step, c);
         return __fmaf_rn(e, rcp, q0);

@@ -329,7 +329,7 @@ __device__ __forceinline__ int go_abs_max(int m, int v) {  // calculateMaxBitpla
 
 __global__ void __launch_bounds__(128) gather_blocks_kernel(const int* __restrict__ coeffs, long long coeffs_per_frame,
                                                             const BlockEntry* __restrict__ tab, int nblocks, long long total,
-                                                            int* __restrict__ blocks, int* __restrict__ numbps, int sub6) {
+                                                            int* __restrict__ blocks, int* __restrict__ numbps, int sub6, int vec_ok) {
     const int lane = threadIdx.x & 31;
     const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (wid >= total) return;
@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(128) gather_blocks_kernel(const int* __restric
     const int* src = coeffs + frame * coeffs_per_frame + e.plane_off;
     int* dst = blocks + frame * coeffs_per_frame + e.block_off;
     int m = 0;
-    if (e.vec) {
+    if (e.vec && vec_ok) {
         const int w4 = e.w >> 2, n4 = w4 * e.h;
 #pragma unroll 4
         for (int i = lane; i < n4; i += 32) {
@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(128) gather_blocks_kernel(const int* __restric
 
 __global__ void __launch_bounds__(128) scatter_blocks_kernel(const int* __restrict__ blocks, long long coeffs_per_frame,
                                                              const BlockEntry* __restrict__ tab, int nblocks, long long total,
-                                                             int* __restrict__ coeffs, const RoiShifts roi) {
+                                                             int* __restrict__ coeffs, const RoiShifts roi, int vec_ok) {
     const int lane = threadIdx.x & 31;
     const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (wid >= total) return;
@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(128) scatter_blocks_kernel(const int* __restri
     const int* src = blocks + frame * coeffs_per_frame + e.block_off;
     int* dst = coeffs + frame * coeffs_per_frame + e.plane_off;
     const int sh = roi.any ? roi.shift[e.comp] : 0;  // warp-uniform
-    if (e.vec) {
+    if (e.vec && vec_ok) {
         const int w4 = e.w >> 2, n4 = w4 * e.h;
 #pragma unroll 4
         for (int i = lane; i < n4; i += 32) {

@@ -51,10 +51,14 @@ namespace j2k {
 #define J2K_RING_WARP_SMEM (J2K_RING_BYTES + J2K_RING_MAXD * 8)
 #define J2K_RING_CTA_SMEM (J2K_RING_WARPS * J2K_RING_WARP_SMEM)
 #ifndef J2K_INV_RING_BYTES
-#define J2K_INV_RING_BYTES 17408  // inverse: a stage holds four band rows per component (8 stages of four 512 B + 32 B rows)
+#define J2K_INV_RING_BYTES 18432  // inverse: a stage holds four band rows per component (4 stages of 2 x four 576 B rows for halo-free strips)
 #endif
-#define J2K_INV_WARP_SMEM (J2K_INV_RING_BYTES + J2K_RING_MAXD * 8)
-#define J2K_INV_CTA_SMEM (J2K_RING_WARPS * J2K_INV_WARP_SMEM)
+#ifndef J2K_INV_HALO_FREE
+#define J2K_INV_HALO_FREE 1       // 5/3 inverse: strips of 32 storing lanes (InvRing::HF)
+#endif
+#ifndef J2K_INV_RING_BYTES_53
+#define J2K_INV_RING_BYTES_53 13824  // single-component 5/3 inverse: 3 stages, so that 4 CTAs (16 warps) fit one SM
+#endif
 
 struct RingSeg {
     // level window (px == 0 always on this path)
@@ -299,6 +303,24 @@ __device__ __forceinline__ unsigned pack_clamp2(int a, int b, const RawPack& p) 
     w = __vadd2(w, p.dc2);
     return w & p.mask2;
 }
+#endif
+
+// The same on two values that arrive as the bit patterns of (n + 1.5 * 2^23) in float32, |n| < 2^15: the low 16 bits of
+// each pattern are n modulo 2^16, so one PRMT replaces the two F2I and the saturating pack.
+__device__ __forceinline__ unsigned pack_clamp2_magic(unsigned ua, unsigned ub, const RawPack& p) {  // ua -> low half, ub -> high half
+#ifdef J2K_EMU
+    return pack_clamp2((int)(short)(ua & 0xFFFFu), (int)(short)(ub & 0xFFFFu), p);
+#else
+    unsigned w = __byte_perm(ua, ub, 0x5410);
+    w = __vmaxs2(w, p.lo2);
+    w = __vmins2(w, p.hi2);
+    w = __vadd2(w, p.dc2);
+    return w & p.mask2;
+#endif
+}
+
+#ifndef J2K_ICT_FAST
+#define J2K_ICT_FAST 1       // float32 form of the float64 inverse ICT behind a distance-to-tie guard (InvRing::ict_fast_row)
 #endif
 
 // ------------------------------------------------------------------ forward job
@@ -822,10 +844,41 @@ struct RingJob { int seg, item, chunk, strip; };
     __syncthreads();                                                                              \
     const int* name = name##_s
 #endif
+struct ClaimQ { unsigned cnt; int base[16]; unsigned tag[16]; };  // J2K_RING_CTA_CLAIM == 2: ticket counter, posted group bases
+#ifndef J2K_EMU
+__device__ __forceinline__ void claimq_init(ClaimQ& q) {
+    if (threadIdx.x < 16) { q.base[threadIdx.x] = 0; q.tag[threadIdx.x] = 0; }
+    if (threadIdx.x == 0) q.cnt = 0;
+    __syncthreads();
+}
+#endif
 template <bool CTA>
-__device__ __forceinline__ bool ring_claim(const RingArgs& A, const int* sb, int lane, RingJob& J) {
+__device__ __forceinline__ bool ring_claim(const RingArgs& A, const int* sb, int lane, RingJob& J, ClaimQ* cq = nullptr) {
     int job = 0;
-#if J2K_RING_CTA_CLAIM && !defined(J2K_EMU)
+#if J2K_RING_CTA_CLAIM == 2 && !defined(J2K_EMU)
+    if constexpr (CTA) {
+        // Group claiming without a CTA barrier: the warps of a CTA take tickets from a shared counter; the warp that draws the
+        // first ticket of a group of NW claims NW consecutive jobs with ONE global atomic and posts the base, the others of the
+        // group pick it up (they are at most one atomic round trip behind).  The CTA still walks adjacent strips of the same
+        // rows, but a warp that finishes early no longer waits for the slowest one (stall_barrier 4-7 % of the forward kernels).
+        if (lane == 0) {
+            const unsigned nw = blockDim.x >> 5;
+            const unsigned idx = atomicAdd(&cq->cnt, 1u), grp = idx / nw, slot = idx - grp * nw;
+            volatile int* rb = cq->base + (grp & 15u);
+            volatile unsigned* rt = cq->tag + (grp & 15u);
+            if (slot == 0) {
+                *rb = (int)atomicAdd(A.ctl, nw);
+                __threadfence_block();
+                *rt = grp + 1u;
+            } else {
+                while (*rt != grp + 1u) {}
+                __threadfence_block();
+            }
+            job = *rb + (int)slot;
+        }
+        job = __shfl_sync(0xffffffffu, job, 0);
+    } else
+#elif J2K_RING_CTA_CLAIM && !defined(J2K_EMU)
     if constexpr (CTA) {
     __shared__ int s_job;
     __syncthreads();  // every warp has read the previous group's base
@@ -933,7 +986,14 @@ __global__ void J2K_RING_BOUNDS fwd_ring_kernel(const __grid_constant__ RingArgs
     rw.one = A.one;
     RingJob J;
     J2K_RING_SCHED_DECL(A, sched);
-    while (ring_claim<true>(A, sched, lane, J)) {
+#if J2K_RING_CTA_CLAIM == 2 && !defined(J2K_EMU)
+    __shared__ ClaimQ cq;
+    claimq_init(cq);
+    ClaimQ* const cqp = &cq;
+#else
+    ClaimQ* const cqp = nullptr;
+#endif
+    while (ring_claim<true>(A, sched, lane, J, cqp)) {
         const RingSeg& S = A.seg[J.seg];
         ring_wait_dep(A, S, J.item, lane);
         if (S.first) {
@@ -959,20 +1019,31 @@ namespace j2k {
 // type for an intermediate level, or rounded / inverse-MCT / DC-shifted / clamped / packed pixels for level 1.
 // Reference order per level: rows, then columns (dwt53.go:318-354, dwt97.go:360-384).
 
-template <int WT, int NP, int NC, int OUT, int MCT>
+// staging bytes per warp of the inverse kernel whose level-1 variant is (WT, NC1)
+template <int WT, int NC1> __host__ __device__ constexpr int inv_ring_bytes() { return (WT == 53 && NC1 == 1) ? J2K_INV_RING_BYTES_53 : J2K_INV_RING_BYTES; }
+template <int WT, int NC1> __host__ __device__ constexpr int inv_cta_smem() { return J2K_RING_WARPS * (inv_ring_bytes<WT, NC1>() + J2K_RING_MAXD * 8); }
+
+template <int WT, int NP, int NC, int OUT, int MCT, int RB = J2K_INV_RING_BYTES>
 struct InvRing {
     typedef typename Wt<WT>::T T;
     static constexpr int LAG = Wt<WT>::LAG;
-    static constexpr int HLN = (Wt<WT>::HALO + NP - 1) / NP;
+    // Halo-free strips (5/3): the inverse runs the horizontal synthesis FIRST, on staged band rows, so the one band sample
+    // a lane needs from each neighbour is read straight from the staged row (for the strip's outer lanes it belongs to the
+    // next strip, or is the mirrored sample fix_halo wrote) instead of coming from a halo lane through a shuffle: all 32
+    // lanes store, a 512-wide frame is two full strips instead of three of 22 lanes, and strips are 128 pairs = whole
+    // 512-byte band-row pieces.  The staged slot still carries one lane width of extra samples per side (SHL).
+    static constexpr bool HF = J2K_INV_HALO_FREE && WT == 53;
+    static constexpr int HLN = HF ? 0 : (Wt<WT>::HALO + NP - 1) / NP;  // halo lanes per side
+    static constexpr int SHL = HF ? 1 : 0;                               // staged-only lane widths per side
     static constexpr int NS = 2 * NP;
     static constexpr bool FINAL = (OUT == IN_U8 || OUT == IN_U16);
     static constexpr int LB = NP * 4;          // bytes per lane per band row
-    static constexpr int ROWB = 32 * LB + 32;  // staged band row slot
+    static constexpr int ROWB = (32 + 2 * SHL) * LB + 32;  // staged band row slot
     static constexpr int NROWS = 4 * NC;       // LL, HL, LH, HH per component
     static constexpr int RPS = (NC == 1) ? 2 : 1;  // row pairs (= loop iterations) per stage
     static constexpr int PAIRB = NROWS * ROWB;     // staged bytes of one row pair
     static constexpr int STAGEB = RPS * PAIRB;
-    static constexpr int D = (J2K_INV_RING_BYTES / STAGEB) > J2K_RING_MAXD ? J2K_RING_MAXD : (J2K_INV_RING_BYTES / STAGEB);
+    static constexpr int D = (RB / STAGEB) > J2K_RING_MAXD ? J2K_RING_MAXD : (RB / STAGEB);
     static_assert(D >= 2, "ring too small for this stage size");
     static_assert(NC == 1 || FINAL, "3-component jobs write interleaved pixels");
 
@@ -1052,6 +1123,68 @@ struct InvRing {
         }
     }
 
+    // Fast form of "round half-even, then the float64 inverse ICT with math.Round" (t2/tile_decoder.go:913, ict.go:16-21) for one
+    // row of 8-bit pixels, valid while M = max(|y|, |cb|, |cr|) < 512 (y, cb, cr: the rounded samples, small integers).
+    //   R = Round(y + 1.402 cr), B = Round(y + 1.772 cb).  The real values have fractions that are multiples of 1/500 and 1/250:
+    //     either an exact tie (cr = 250 mod 500, cb = 125 mod 250) or at least 0.002 / 0.004 away from one.  The constants are
+    //     split so that the float32 result is exact AT the ties: 1.402 = 1.375 + 0.027, 1.772 = 1.75 + 0.022;
+    //     a = fma(1.375, cr, y) is exact (three fraction bits), t = fma(0.027f, cr, a) has one rounding and an error of
+    //     |cr| 2^-30 before it, far below half a float32 grid step at |t| < 2^11, so a real tie k + 1/2 comes out as exactly
+    //     k + 1/2.  Go's float64 product lands on the tie too (|cr| 2^-53 relative error of the constant against a 2^-44
+    //     grid; tests/test_ict_fast.py checks every value), so math.Round rounds it half AWAY from zero; here t' = t (1 + 2^-20)
+    //     pushes a tie eight grid steps away from zero before rint, and moves a non-tie by < |t| 2^-20 + 2^-14 < 0.0015:
+    //     never across the tie that is >= 0.002 away.  No guard is needed for R and B.
+    //   G = Round(y - 0.34413 cb - 0.71414 cr): fractions are multiples of 1e-5, float32 cannot separate them, so G keeps a
+    //     distance-to-tie guard: t = fma(-0.71414f, cr, fma(-0.34413f, cb, y)) differs from Go's float64 value by less than
+    //     4.2 M 2^-24 (constant errors M 2^-26 + M 2^-25, two roundings of <= 1.35 M 2^-24 and 2.06 M 2^-24); a lane whose t comes
+    //     closer than E = M 2^-21 to a half-integer in any sample of the row returns false and takes the float64 path
+    //     (2 E of the samples: 0.02 % at M = 200).
+    // rint(t) is t + 1.5 * 2^23 - 1.5 * 2^23 (exact for |t| < 2^22, round half-even); the biased sum's low mantissa bits are the
+    // integer itself, which pack_clamp2_magic picks up without an F2I.
+    static __device__ __forceinline__ bool ict_fast_row(const RawPack& rp, unsigned char* xrow, const float2 (&x)[NC][NP]) {
+        static_assert(NC == 3 && OUT == IN_U8, "8-bit interleaved RGB");
+        const float2 MG = splat2(12582912.0f), NMG = splat2(-12582912.0f), NEG1 = splat2(-1.0f), BIAS = splat2(9.5367431640625e-7f);
+        const float2 cRh = splat2(1.375f), cRl = splat2(0.027f), cBh = splat2(1.75f), cBl = splat2(0.022f);
+        const float2 cG1 = splat2(-0.34413f), cG2 = splat2(-0.71414f);
+        unsigned u[3][NS];  // biased bit patterns of R, G, B per sample
+        float mag = 0.f, dist = 0.f;
+#pragma unroll
+        for (int j = 0; j < NP; j++) {
+            const float2 y = add2(add2(x[0][j], MG), NMG), cb = add2(add2(x[1][j], MG), NMG), cr = add2(add2(x[2][j], MG), NMG);
+            mag = fmaxf(mag, fmaxf(fabsf(y.x), fabsf(y.y)));
+            mag = fmaxf(mag, fmaxf(fabsf(cb.x), fabsf(cb.y)));
+            mag = fmaxf(mag, fmaxf(fabsf(cr.x), fabsf(cr.y)));
+            const float2 tr = fma2(cRl, cr, fma2(cRh, cr, y)), tb = fma2(cBl, cb, fma2(cBh, cb, y));
+            const float2 tg = fma2(cG2, cr, fma2(cG1, cb, y));
+            const float2 br = add2(fma2(tr, BIAS, tr), MG), bb = add2(fma2(tb, BIAS, tb), MG), bg = add2(tg, MG);
+            const float2 d = fma2(add2(bg, NMG), NEG1, tg);  // tg - rint(tg), exact
+            dist = fmaxf(dist, fmaxf(fabsf(d.x), fabsf(d.y)));
+            u[0][2 * j] = __float_as_uint(br.x); u[0][2 * j + 1] = __float_as_uint(br.y);
+            u[1][2 * j] = __float_as_uint(bg.x); u[1][2 * j + 1] = __float_as_uint(bg.y);
+            u[2][2 * j] = __float_as_uint(bb.x); u[2][2 * j + 1] = __float_as_uint(bb.y);
+        }
+        if (!(mag < 512.0f) || !(dist < 0.5f - mag * 4.76837158203125e-7f)) return false;
+        constexpr int NWO = NS * 3 / 4;
+        unsigned wv[NWO];
+#pragma unroll
+        for (int k = 0; k < NWO; k++) {
+            const unsigned t0 = pack_clamp2_magic(u[(4 * k) % 3][(4 * k) / 3], u[(4 * k + 1) % 3][(4 * k + 1) / 3], rp);
+            const unsigned t1 = pack_clamp2_magic(u[(4 * k + 2) % 3][(4 * k + 2) / 3], u[(4 * k + 3) % 3][(4 * k + 3) / 3], rp);
+            wv[k] = __byte_perm(t0, t1, 0x6420);
+        }
+        if constexpr (NWO % 4 == 0) {
+#pragma unroll
+            for (int k = 0; k < NWO / 4; k++) *((uint4*)xrow + k) = make_uint4(wv[4 * k], wv[4 * k + 1], wv[(4 * k + 2) % NWO], wv[(4 * k + 3) % NWO]);
+        } else if constexpr (NWO % 2 == 0) {
+#pragma unroll
+            for (int k = 0; k < NWO / 2; k++) *((uint2*)xrow + k) = make_uint2(wv[2 * k], wv[(2 * k + 1) % NWO]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < NWO; k++) *((unsigned*)xrow + k) = wv[k];
+        }
+        return true;
+    }
+
     // planar destination (intermediate LL, wavelet-package API, generic path): working-type bits, or rounded samples
     static __device__ __forceinline__ void store_planar(int* p, const int (&q)[NS]) {
         if constexpr (NS == 8) {
@@ -1072,14 +1205,14 @@ struct InvRing {
         const int kxe = min(kxs + S.strip_pairs, S.Kx);
         const int nl = (kxe - kxs + NP - 1) / NP + 2 * HLN;
         const int kx0 = kxs - HLN * NP + lane * NP;
-        const int k0w = kxs - HLN * NP;           // band index of lane 0's first element
+        const int k0w = kxs - (HLN + SHL) * NP;   // band index of the first staged element
         const int m = (k0w * 4) & 15;
         const int vb = k0w * 4 - m;               // virtual (16 B aligned) byte position of the slot start inside a band row
         const int c0 = max(vb, 0);
-        const int c1 = min(vb + ((m + nl * LB + 15) & ~15), bw * 4);
+        const int c1 = min(vb + ((m + (nl + 2 * SHL) * LB + 15) & ~15), bw * 4);
         const unsigned copy_bytes = (unsigned)(c1 - c0);
         const int dst_off = c0 - vb;
-        const int lane_off = m + lane * LB;
+        const int lane_off = m + (lane + SHL) * LB;
         const bool fix_l = kxs == 0, fix_r = kxe == S.Kx;
         const bool fix = fix_l || fix_r;
         const bool st = lane >= HLN && kx0 < kxe && kx0 + NP <= bw;
@@ -1277,20 +1410,29 @@ struct InvRing {
                 if (planes) planes += 2 * planes_rs;
                 if (!st) return;
                 if constexpr (FINAL) {
+                    constexpr bool ICTF = J2K_ICT_FAST && NC == 3 && MCT == MCTK_ICT && OUT == IN_U8;
                     int iv[NC][NS];
                     if (re >= 0 && re < h) {
+                        bool done = false;
+                        if constexpr (ICTF) { if (!prow) done = ict_fast_row(rp, xrow, xe); }
+                        if (!done) {
 #pragma unroll
-                        for (int c = 0; c < NC; c++)
+                            for (int c = 0; c < NC; c++)
 #pragma unroll
-                            for (int j = 0; j < NP; j++) { iv[c][2 * j] = __float2int_rn(xe[c][j].x); iv[c][2 * j + 1] = __float2int_rn(xe[c][j].y); }
-                        store_final(S, raw, rp, xrow, prow, iv);
+                                for (int j = 0; j < NP; j++) { iv[c][2 * j] = __float2int_rn(xe[c][j].x); iv[c][2 * j + 1] = __float2int_rn(xe[c][j].y); }
+                            store_final(S, raw, rp, xrow, prow, iv);
+                        }
                     }
                     if (ro < h) {
+                        bool done = false;
+                        if constexpr (ICTF) { if (!prow) done = ict_fast_row(rp, xrow + xpitch, xo); }
+                        if (!done) {
 #pragma unroll
-                        for (int c = 0; c < NC; c++)
+                            for (int c = 0; c < NC; c++)
 #pragma unroll
-                            for (int j = 0; j < NP; j++) { iv[c][2 * j] = __float2int_rn(xo[c][j].x); iv[c][2 * j + 1] = __float2int_rn(xo[c][j].y); }
-                        store_final(S, raw, rp, xrow + xpitch, prow ? prow + planes_rs : nullptr, iv);
+                                for (int j = 0; j < NP; j++) { iv[c][2 * j] = __float2int_rn(xo[c][j].x); iv[c][2 * j + 1] = __float2int_rn(xo[c][j].y); }
+                            store_final(S, raw, rp, xrow + xpitch, prow ? prow + planes_rs : nullptr, iv);
+                        }
                     }
                 } else {
                     int q[NS];
@@ -1363,32 +1505,35 @@ struct InvRing {
                     }
                     // horizontal synthesis of the low-type row (q0 | q1) and the high-type row (q2 | q3) (dwt53.go:123-234)
                     int e[NS], o[NS];
-                    {
+                    // neighbours: the high sample left of the lane's span, the low and high samples right of it.  Halo-free
+                    // strips read them from the staged rows (every lane: no shuffle, no lane predicate); otherwise they come
+                    // from the adjacent lanes.
+                    auto hsyn = [&](const int (&ql)[NP], const int (&qh)[NP], int row_l, bool halve_l, bool halve_h, int (&out)[NS]) {
                         int s[NP + 1], d[NP + 1];
 #pragma unroll
-                        for (int j = 0; j < NP; j++) { s[j] = q0[j]; d[j + 1] = q1[j]; }
-                        d[0] = __shfl_up_sync(0xffffffffu, d[NP], 1);
+                        for (int j = 0; j < NP; j++) { s[j] = ql[j]; d[j + 1] = qh[j]; }
+                        if constexpr (HF) {
+                            const smem_t pl = stage + row_l * ROWB + lane_off, ph = pl + ROWB;
+                            int dl = (int)lds32(ph - 4), sr = (int)lds32(pl + LB), dr = (int)lds32(ph + LB);
+                            if (halve_h) { dl /= 2; dr /= 2; }
+                            if (halve_l) sr /= 2;
+                            d[0] = dl;
 #pragma unroll
-                        for (int j = 0; j < NP; j++) s[j] = s[j] - ((d[j] + d[j + 1] + 2) >> 2);
-                        s[NP] = __shfl_down_sync(0xffffffffu, s[0], 1);
+                            for (int j = 0; j < NP; j++) s[j] = s[j] - ((d[j] + d[j + 1] + 2) >> 2);
+                            s[NP] = sr - ((d[NP] + dr + 2) >> 2);
+                        } else {
+                            d[0] = __shfl_up_sync(0xffffffffu, d[NP], 1);
+#pragma unroll
+                            for (int j = 0; j < NP; j++) s[j] = s[j] - ((d[j] + d[j + 1] + 2) >> 2);
+                            s[NP] = __shfl_down_sync(0xffffffffu, s[0], 1);
+                        }
 #pragma unroll
                         for (int j = 0; j < NP; j++) d[j + 1] = d[j + 1] + ((s[j] + s[j + 1]) >> 1);
 #pragma unroll
-                        for (int j = 0; j < NP; j++) { e[2 * j] = s[j]; e[2 * j + 1] = d[j + 1]; }
-                    }
-                    {
-                        int s[NP + 1], d[NP + 1];
-#pragma unroll
-                        for (int j = 0; j < NP; j++) { s[j] = q2[j]; d[j + 1] = q3[j]; }
-                        d[0] = __shfl_up_sync(0xffffffffu, d[NP], 1);
-#pragma unroll
-                        for (int j = 0; j < NP; j++) s[j] = s[j] - ((d[j] + d[j + 1] + 2) >> 2);
-                        s[NP] = __shfl_down_sync(0xffffffffu, s[0], 1);
-#pragma unroll
-                        for (int j = 0; j < NP; j++) d[j + 1] = d[j + 1] + ((s[j] + s[j + 1]) >> 1);
-#pragma unroll
-                        for (int j = 0; j < NP; j++) { o[2 * j] = s[j]; o[2 * j + 1] = d[j + 1]; }
-                    }
+                        for (int j = 0; j < NP; j++) { out[2 * j] = s[j]; out[2 * j + 1] = d[j + 1]; }
+                    };
+                    hsyn(q0, q1, 4 * c + 0, halve_ll, halve_hl, e);
+                    hsyn(q2, q3, 4 * c + 2, halve_lh, halve_hh, o);
                     // vertical synthesis (dwt53.go:318-354 columns after rows)
 #pragma unroll
                     for (int s = 0; s < NS; s++) {
@@ -1436,12 +1581,19 @@ struct InvRing {
 
 // WT: 53 / 97.  OUT1 / NC1 / MCT1: the variant of segments with first == 1 (level 1: packed pixels, or planar for the
 // wavelet-package API / generic path); coarser levels always write planar working-type LL planes.
+#ifndef J2K_INV_MINB_53
+#define J2K_INV_MINB_53 4    // resident CTAs per SM targeted by the single-component 5/3 inverse (128 registers, 16 warps: +2 % on C1 / C4)
+#endif
+#ifndef J2K_INV_RGB_NP
+#define J2K_INV_RGB_NP 2     // sample pairs per lane of the 3-component level-1 inverse (4: 2 CTAs/SM, the window state of three components in 255 registers)
+#endif
 template <int WT, int NP1, int NC1, int OUT1, int MCT1>
-__global__ void __launch_bounds__(J2K_RING_WARPS * 32, J2K_RING_MINB) inv_ring_kernel(const __grid_constant__ RingArgs A) {
+__global__ void __launch_bounds__(J2K_RING_WARPS * 32, (NC1 == 3 && NP1 == 4) ? 2 : ((WT == 53 && NC1 == 1) ? J2K_INV_MINB_53 : J2K_RING_MINB)) inv_ring_kernel(const __grid_constant__ RingArgs A) {
     J2K_SMEM_DECL(smem);
     const int lane = threadIdx.x & 31;
     RingWarp rw;
-    ring_warp_init(smem, rw, lane, J2K_INV_RING_BYTES);
+    constexpr int RB = inv_ring_bytes<WT, NC1>();
+    ring_warp_init(smem, rw, lane, RB);
     rw.one = A.one;
     RingJob J;
     #ifndef J2K_INV_CTA_CLAIM
@@ -1451,8 +1603,8 @@ __global__ void __launch_bounds__(J2K_RING_WARPS * 32, J2K_RING_MINB) inv_ring_k
     while (ring_claim<(J2K_INV_CTA_CLAIM != 0)>(A, sched, lane, J)) {
         const RingSeg& S = A.seg[J.seg];
         ring_wait_dep(A, S, J.item, lane);
-        if (S.first) InvRing<WT, NP1, NC1, OUT1, MCT1>::run(S, A.raw, J.item, J.chunk, J.strip, rw, lane);
-        else InvRing<WT, 4, 1, (WT == 53 ? IN_I32 : IN_F32), MCTK_NONE>::run(S, A.raw, J.item, J.chunk, J.strip, rw, lane);
+        if (S.first) InvRing<WT, NP1, NC1, OUT1, MCT1, RB>::run(S, A.raw, J.item, J.chunk, J.strip, rw, lane);
+        else InvRing<WT, 4, 1, (WT == 53 ? IN_I32 : IN_F32), MCTK_NONE, RB>::run(S, A.raw, J.item, J.chunk, J.strip, rw, lane);
         ring_signal(A, S, J.item, lane);
     }
     ring_retire(A, lane);

@@ -175,7 +175,7 @@ LIB_PATH = os.path.join(os.path.dirname(_PKG_DIR), "csrc", "build", "libj2kb200.
 
 # every symbol include/j2k_b200.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = [
-    "j2k_init", "j2k_shutdown", "j2k_last_error", "j2k_abi_version", "j2k_device_count", "j2k_launch_count",
+    "j2k_init", "j2k_shutdown", "j2k_last_error", "j2k_last_error_copy", "j2k_abi_version", "j2k_device_count", "j2k_launch_count",
     "j2k_last_timing", "j2k_set_profiling", "j2k_get_profile", "j2k_acquire_buffer", "j2k_release_buffer",
     "j2k_fwd_pixel_bytes", "j2k_fwd_coeff_count", "j2k_inv_pixel_bytes", "j2k_inv_coeff_count",
     "j2k_fwd_tile_bounds", "j2k_inv_tile_bounds",
@@ -216,6 +216,7 @@ def load(path: str | None = None) -> C.CDLL:
         "j2k_init": (ci, [C.POINTER(vp), C.POINTER(ci), ci]),
         "j2k_shutdown": (None, [vp]),
         "j2k_last_error": (C.c_char_p, [vp]),
+        "j2k_last_error_copy": (C.c_size_t, [vp, C.c_char_p, C.c_size_t]),
         "j2k_abi_version": (ci, []),
         "j2k_device_count": (ci, [vp]),
         "j2k_launch_count": (C.c_int64, [vp]),

@@ -13,7 +13,7 @@
  *
  * Conventions
  *   - return 0 on success, a negative j2k_status on failure; the message is
- *     available through j2k_last_error() (per calling thread).  Nothing ever
+ *     available through j2k_last_error(ctx) (kept per context, not per thread).  Nothing ever
  *     falls back to a CPU implementation: without a usable CUDA device every
  *     compute entry point fails with J2K_ERR_CUDA.
  *   - all host buffers are caller-owned; no pointer is retained after return
@@ -153,8 +153,13 @@ typedef struct j2k_ctx j2k_ctx;
  * shim's init(), next to RegisterJPEG2000LosslessCodec (jpeg2000/lossless/codec.go:306-322). */
 int j2k_init(j2k_ctx** ctx, const int* devices, int n_devices);
 void j2k_shutdown(j2k_ctx* ctx);
-/* Message of the last failure on the calling thread (never NULL). */
+/* Message of the most recent failing call on `ctx`, whichever thread made it (never NULL; the pointer stays valid on the
+ * calling thread until its next j2k_last_error call).  ctx == NULL: the calling thread's last message (j2k_init and the
+ * context-free helpers).  A goroutine may change OS threads between a failing cgo call and this one - the message is
+ * kept per context for exactly that reason; wrap call + fetch in one Go function (integration/go/j2kb200.go). */
 const char* j2k_last_error(j2k_ctx* ctx);
+/* The same, copied into a caller buffer (at most cap - 1 bytes + NUL); returns the full message length. */
+size_t j2k_last_error_copy(j2k_ctx* ctx, char* buf, size_t cap);
 int j2k_abi_version(void);
 int j2k_device_count(const j2k_ctx* ctx);
 /* Total number of CUDA kernels this context has launched (bench.py's gpu_launches). */
@@ -290,7 +295,12 @@ int j2k_inverse_blocks_roi(j2k_ctx* ctx, const j2k_inv_params* p, int cb_width, 
                            int32_t* planes_out);
 
 /* Device-resident halves of the two calls above (plane <-> block-major), for pipelines that
- * keep coefficients on the device; enqueued on `cuda_stream`, not synchronised. */
+ * keep coefficients on the device; enqueued on `cuda_stream`, not synchronised.
+ * The gather copies the coefficients AS THEY ARE (no shift) and counts cblkNumbps for them: with `p` exactly as it was
+ * given to j2k_forward_device, numbps is right for 9/7 (6 fractional bits from the quantizer), HTJ2K (none) and 5/3 with
+ * or without fuse_t1_shift (without it the plane holds plain integers and the caller applies the `<<6` of
+ * encoder.go:3294-3300 to the block copies; the bit count of the integers is then the count T1 needs).
+ * Planes that are not 16-byte aligned (a sliced device tensor) take scalar copies. */
 int j2k_gather_blocks_device(j2k_ctx* ctx, int dev, const j2k_fwd_params* p, int cb_width, int cb_height, int nframes,
                              const int32_t* d_coeffs, int32_t* d_blocks, int32_t* d_numbps, void* cuda_stream);
 int j2k_scatter_blocks_device(j2k_ctx* ctx, int dev, const j2k_inv_params* p, int cb_width, int cb_height, int nframes,

@@ -67,3 +67,17 @@ def test_header_compiles_as_c_and_a_c_program_round_trips(tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
     assert "c abi ok" in out.stdout
+
+
+def test_error_text_is_kept_per_context_across_threads(tmp_path):
+    """tests/c/err_threads.c: thread A fails, thread B reads the message through the context (cgo goroutine migration)."""
+    import subprocess
+    import emu_lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = emu_lib.build()
+    exe = str(tmp_path / "err_threads")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pthread", "-I", os.path.join(root, "include"), "-o", exe,
+                           os.path.join(root, "tests", "c", "err_threads.c"), lib, "-Wl,-rpath," + os.path.dirname(lib)])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert "crosses threads" in out.stdout
