@@ -603,6 +603,7 @@ def main():
     # before step i is waited for, so its upload runs under step i's download; every step still moves its own input
     # H2D and its own result D2H inside the timed region.  `sync_value` is the same through the blocking call.
     e2e_val, e2e_sync, same, e2e_steps = None, None, None, 0
+    e2e_page = same_page = pcie_ceiling = pcie_gbs = None
     if not args.no_e2e:
         h_in = ctx.pinned(B * frame_bytes).reshape(B, frame_bytes)
         h_outs = [ctx.pinned(B * PIX * 4, np.int32).reshape(B, PIX) for _ in range(2)]
@@ -635,6 +636,45 @@ def main():
         e2e_val = world * B * PIX / (float(t.item()) / e2e_steps) / 1e6
         # the e2e results must be the same coefficients as the resident run
         same = all(bool(torch.equal(torch.from_numpy(np.asarray(h[B - 1])).cuda(), d_out[B - 1])) for h in h_outs)
+        # the same blocking call with PAGEABLE caller memory (plain numpy arrays: what a Go []byte from PixelData.GetFrame is):
+        # the library moves it through its pinned staging ring, host threads copying chunks while the copy engines run
+        n_in = np.array(h_in)            # pageable copies
+        n_out = np.empty((B, PIX), np.int32)
+        ctx.forward_batch(fp, n_in, n_out)
+        barrier()
+        pg_steps = max(2, min(e2e_steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(pg_steps):
+            ctx.forward_batch(fp, n_in, n_out)
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], device="cuda")
+        if use_dist:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_page = world * B * PIX / (float(t.item()) / pg_steps) / 1e6
+        same_page = bool(np.array_equal(n_out[B - 1], np.asarray(h_outs[0][B - 1])))
+        # ceiling of any end-to-end number on this box: the step's bytes, up and down at once, with plain pinned cudaMemcpyAsync
+        d_scr_in = torch.empty(B * frame_bytes, dtype=torch.uint8, device="cuda")
+        d_scr_out = torch.empty(B * PIX, dtype=torch.int32, device="cuda")
+        t_in = torch.from_numpy(h_in.reshape(-1))
+        t_out = torch.from_numpy(h_outs[0].reshape(-1))
+        s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+        def pcie_step():
+            with torch.cuda.stream(s_up):
+                d_scr_in.copy_(t_in, non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                t_out.copy_(d_scr_out, non_blocking=True)
+        pcie_step(); torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            pcie_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], device="cuda")
+        if use_dist:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        pcie_ceiling = world * B * PIX / (float(t.item()) / 3) / 1e6
+        pcie_gbs = (B * frame_bytes + B * PIX * 4) / (dt / 3) / 1e9
 
     # ---- the other BASELINE configs, resident, both directions (every rank runs them; rank 0's numbers are reported)
     configs = None
@@ -668,7 +708,12 @@ def main():
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": "Mpixel/s", "h2d_bytes_per_step": B * frame_bytes, "d2h_bytes_per_step": B * PIX * 4,
                     "steps": e2e_steps, "matches_resident": same, "sync_value": e2e_sync,
-                    "api": "j2k_submit_forward / j2k_wait, two steps in flight (sync_value: blocking j2k_forward_batch)"},
+                    "pageable_value": e2e_page, "pageable_matches": same_page,
+                    "pcie_ceiling": pcie_ceiling, "pcie_GBps_this_rank": pcie_gbs,
+                    "api": "j2k_submit_forward / j2k_wait, two steps in flight, pinned buffers (sync_value: blocking j2k_forward_batch, "
+                           "pinned; pageable_value: the same call on plain numpy arrays through the library's pinned staging ring; "
+                           "pcie_ceiling: the step's bytes up and down at once with bare pinned copies, max over ranks - no "
+                           "end-to-end figure on this box can exceed it)"},
             "gpu_launches": int(launches), "clocks": clocks,
         }
         emit(line)

@@ -190,6 +190,7 @@ struct RingPlan {
     bool ok = false;
     RingArgs args;
     int WT = 0, NP1 = 0, NC1 = 0, IN1 = 0, MCT1 = 0, SG1 = 0;
+    int UA = 0;  // general-alignment kernel variant (rows / bands that are not 16-byte aligned, partial vectors at the right edge)
     int x_buf[J2K_RING_MAXSEG], ll_buf[J2K_RING_MAXSEG], band_buf[J2K_RING_MAXSEG], planes_buf[J2K_RING_MAXSEG];
     int level[J2K_RING_MAXSEG];
     int cut = 0;  // levels 1..cut run in the persistent launch, deeper ones (geometry it does not take) on the per-level kernels
@@ -233,6 +234,7 @@ struct DeviceCtx {
     bool ev_k_used[2] = {false, false}, ev_out_used[2] = {false, false};
     DevBuf in[2], out[2], planes[2], api[8];
     DevBuf blk[2], nbp[2];  // code-block interface: block-major planes and per-block numbps of a sub-batch
+    DevBuf gsh[2], gmk[2];  // general-scaling ROI of a sub-batch: per-block shifts, per-sample mask
     std::map<std::string, std::unique_ptr<Plan>> plans;
     long long use_clock = 0;   // LRU stamps of `plans`
     std::map<std::string, std::unique_ptr<struct BlockTable>> block_tables;
@@ -720,6 +722,7 @@ int build_ring_fwd_impl(const Spec& s, Plan& P, const std::vector<long long>& ta
     if (order.empty() || order.size() > J2K_RING_MAXSEG) return 0;
     std::vector<int> seg_of(P.levels.size(), -1);
     bool have_first = false;
+    bool ua = false;
     int n_ctl = 2, jobs = 0;
     for (size_t si = 0; si < order.size(); si++) {
         const LevelLaunch& l = P.levels[order[si]];
@@ -733,7 +736,8 @@ int build_ring_fwd_impl(const Spec& s, Plan& P, const std::vector<long long>& ta
         const int ES = l.KIND == IN_U8 ? 1 : (l.KIND == IN_U16 ? 2 : 4);
         const int PB = ES * (raw_in ? l.NC : 1);
         if (a.px != 0 || a.hskip || a.vskip) return 0;
-        if (a.w % (2 * NP)) return 0;  // whole-vector stores only: low and high band widths are multiples of NP
+        bool seg_ua = false;           // this level needs the general-alignment variant
+        if (a.w % (2 * NP)) seg_ua = true;  // aligned variant: whole-vector stores only (low and high band widths multiples of NP)
         if (first) {
             if (!ring_variant_supported(WT, NP, l.NC, l.KIND, l.MCT, SG)) return 0;
             if (l.NC == 1 && raw_in && s.C != 1) return 0;  // strided components
@@ -745,15 +749,35 @@ int build_ring_fwd_impl(const Spec& s, Plan& P, const std::vector<long long>& ta
         // alignment of the staged side: row pitch, row length and every item origin are multiples of 16 bytes
         const long long pitch = (long long)a.x_row_stride * ES;
         const long long row_bytes = (long long)a.w * PB;
-        if (pitch % 16 || row_bytes % 16 || row_bytes > 0x7fffffffLL) return 0;
-        for (int i = 0; i < a.n_items; i++)
-            if ((tab[l.o_x + i] * ES) % 16) return 0;
+        if (row_bytes > 0x7fffffffLL) return 0;
+        if (pitch % 16 || row_bytes % 16) seg_ua = true;
+        int lalign = 16 | (int)(pitch & 15) | (PB == 1 ? 8 : 0);
+        for (int i = 0; i < a.n_items; i++) {
+            if ((tab[l.o_x + i] * ES) % 16) seg_ua = true;
+            lalign |= (int)((tab[l.o_x + i] * ES) & 15);
+        }
         // alignment of the band side for NP-wide vector stores
         if ((a.hl.row_stride % NP) || (a.lw % NP) || (a.hl.comp_stride % NP) || (a.ll.row_stride % NP) || (a.ll.comp_stride % NP) ||
             (a.hl.x_off % NP) || (a.hh.x_off % NP) || (a.ll.x_off % NP) || (a.lh_.x_off % NP))
-            return 0;
+            seg_ua = true;
         for (int i = 0; i < a.n_items; i++)
-            if ((tab[l.o_plane + i] % NP) || (tab[l.o_ll + i] % NP)) return 0;
+            if ((tab[l.o_plane + i] % NP) || (tab[l.o_ll + i] % NP)) seg_ua = true;
+        if (seg_ua) {
+            // the general-alignment variant exists for single-component jobs on raw words (level 1) and on LL planes (deeper
+            // levels); windows narrower than one vector per lane pair stay on the per-level kernels
+            if (!env_int("J2K_RING_UA", 1) || l.NC != 1 || NP != 4 || a.w < 16 || a.h < 2 || (first && !raw_in)) return 0;
+            ua = true;
+        }
+        {   // widest access every lane address / band row is guaranteed to allow (powers of two; used by the UA variant only)
+            g.load_align = lalign & -lalign;
+            auto cls = [&](const BandIO& b, size_t o_tab) {
+                long long m = 4 | b.row_stride | b.x_off;
+                for (int i = 0; i < a.n_items; i++) m |= tab[o_tab + i];
+                return (int)(m & -m);
+            };
+            g.st_cls[0] = cls(a.ll, l.o_ll); g.st_cls[1] = cls(a.hl, l.o_plane); g.st_cls[2] = cls(a.lh_, l.o_plane); g.st_cls[3] = cls(a.hh, l.o_plane);
+            g.x_align = 16;
+        }
         const BandIO* bands[4] = {&a.ll, &a.hl, &a.lh_, &a.hh};
         for (int bi = 0; bi < 4; bi++) {
             const BandIO& b = *bands[bi];
@@ -801,6 +825,8 @@ int build_ring_fwd_impl(const Spec& s, Plan& P, const std::vector<long long>& ta
         seg_of[order[si]] = (int)si;
     }
     if (!have_first) return 0;
+    if (ua && (R.NC1 != 1 || R.NP1 != 4 || (R.IN1 != IN_U8 && R.IN1 != IN_U16))) return 0;  // a deep level needs the general variant but level 1 has none
+    R.UA = ua ? 1 : 0;
     R.args.nseg = (int)order.size();
     for (int k = 0; k < R.args.nseg; k++) R.args.seg[k].has_waiters = 0;
     for (int k = 0; k < R.args.nseg; k++)
@@ -828,9 +854,15 @@ int ring_blocks_per_sm(const void* fn, int smem_bytes) {
 }
 
 #define RING_CASE(wt, np, nc, in, mct, sg)                                                                                   \
-    if (R.WT == wt && R.NP1 == np && R.NC1 == nc && R.IN1 == in && R.MCT1 == mct && R.SG1 == sg) {                           \
-        if (query) return ring_blocks_per_sm((const void*)fwd_ring_kernel<wt, np, nc, in, mct, sg>, J2K_RING_CTA_SMEM);                      \
-        J2K_LAUNCH_SMEM((fwd_ring_kernel<wt, np, nc, in, mct, sg>), grid, J2K_RING_WARPS * 32, J2K_RING_CTA_SMEM, st, A);   \
+    if (R.WT == wt && R.NP1 == np && R.NC1 == nc && R.IN1 == in && R.MCT1 == mct && R.SG1 == sg && !R.UA) {                  \
+        if (query) return ring_blocks_per_sm((const void*)fwd_ring_kernel<wt, np, nc, in, mct, sg>, fwd_cta_smem<0>());      \
+        J2K_LAUNCH_SMEM((fwd_ring_kernel<wt, np, nc, in, mct, sg>), grid, J2K_RING_WARPS * 32, fwd_cta_smem<0>(), st, A);    \
+        return 0;                                                                                                           \
+    }
+#define RING_CASE_UA(wt, in, sg)                                                                                             \
+    if (R.WT == wt && R.NP1 == 4 && R.NC1 == 1 && R.IN1 == in && R.MCT1 == MCTK_NONE && R.SG1 == sg && R.UA) {               \
+        if (query) return ring_blocks_per_sm((const void*)fwd_ring_kernel<wt, 4, 1, in, MCTK_NONE, sg, 1>, fwd_cta_smem<1>()); \
+        J2K_LAUNCH_SMEM((fwd_ring_kernel<wt, 4, 1, in, MCTK_NONE, sg, 1>), grid, J2K_RING_WARPS * 32, fwd_cta_smem<1>(), st, A); \
         return 0;                                                                                                           \
     }
 
@@ -846,6 +878,8 @@ int ring_dispatch_fwd(const RingPlan& R, const RingArgs& A, unsigned grid, cudaS
     RING_CASE(53, 4, 1, IN_U8, MCTK_NONE, 1) RING_CASE(53, 4, 1, IN_U16, MCTK_NONE, 1)
     RING_CASE(53, 2, 3, IN_U8, MCTK_RCT, 0) RING_CASE(53, 2, 3, IN_U16, MCTK_RCT, 0)
     RING_CASE(53, 4, 1, IN_I32, MCTK_NONE, 0)
+    RING_CASE_UA(97, IN_U8, 0) RING_CASE_UA(97, IN_U16, 0) RING_CASE_UA(97, IN_U8, 1) RING_CASE_UA(97, IN_U16, 1)
+    RING_CASE_UA(53, IN_U8, 0) RING_CASE_UA(53, IN_U16, 0) RING_CASE_UA(53, IN_U8, 1) RING_CASE_UA(53, IN_U16, 1)
     return -1;
 }
 
@@ -889,6 +923,7 @@ int build_ring_inv_impl(const Spec& s, Plan& P, const std::vector<long long>& ta
             if (P.levels[i].level == k) order.push_back((int)i);
     if (order.empty() || order.size() > J2K_RING_MAXSEG) return 0;
     bool have_first = false;
+    bool ua = false;
     int n_ctl = 2, jobs = 0;
     for (size_t si = 0; si < order.size(); si++) {
         const LevelLaunch& l = P.levels[order[si]];
@@ -900,7 +935,8 @@ int build_ring_inv_impl(const Spec& s, Plan& P, const std::vector<long long>& ta
         const int ES = l.KIND == IN_U8 ? 1 : (l.KIND == IN_U16 ? 2 : 4);
         const int PB = ES * (raw_out ? l.NC : 1);
         if (a.px != 0 || a.hskip || a.vskip) return 0;
-        if (a.w % 8) return 0;  // band rows are staged in 16-byte units: low and high band widths are multiples of 4
+        bool seg_ua = false;          // this level needs the general-alignment variant
+        if (a.w % 8) seg_ua = true;   // aligned variant: band rows are staged in 16-byte units (low and high band widths multiples of 4)
         if (first) {
             if (!ring_inv_variant_supported(WT, NP, l.NC, l.KIND, l.MCT)) return 0;
             if (l.NC == 1 && raw_out && s.C != 1) return 0;  // strided components
@@ -911,15 +947,28 @@ int build_ring_inv_impl(const Spec& s, Plan& P, const std::vector<long long>& ta
         }
         // destination rows: vector stores
         const long long pitch = (long long)a.x_row_stride * ES;
-        if (pitch % 16 || ((long long)a.w * PB) % 16) return 0;
-        for (int i = 0; i < a.n_items; i++)
-            if ((tab[l.o_x + i] * ES) % 16) return 0;
+        if (pitch % 16 || ((long long)a.w * PB) % 16) seg_ua = true;
+        int xalign = 16 | (int)(pitch & 15);
+        for (int i = 0; i < a.n_items; i++) {
+            if ((tab[l.o_x + i] * ES) % 16) seg_ua = true;
+            xalign |= (int)((tab[l.o_x + i] * ES) & 15);
+        }
         // band rows: 16-byte aligned TMA segments
         if ((a.hl.row_stride % 4) || (a.lw % 4) || (a.hl.comp_stride % 4) || (a.ll.row_stride % 4) || (a.ll.comp_stride % 4) ||
             (a.hl.x_off % 4) || (a.hh.x_off % 4) || (a.ll.x_off % 4) || (a.lh_.x_off % 4))
-            return 0;
-        for (int i = 0; i < a.n_items; i++)
-            if ((tab[l.o_plane + i] % 4) || (tab[l.o_ll + i] % 4)) return 0;
+            seg_ua = true;
+        long long lal = 4 | a.hl.row_stride | a.ll.row_stride | a.hl.x_off | a.hh.x_off | a.ll.x_off | a.lh_.x_off;
+        for (int i = 0; i < a.n_items; i++) {
+            if ((tab[l.o_plane + i] % 4) || (tab[l.o_ll + i] % 4)) seg_ua = true;
+            lal |= tab[l.o_plane + i] | tab[l.o_ll + i];
+        }
+        if (seg_ua) {
+            if (!env_int("J2K_RING_UA", 1) || l.NC != 1 || NP != 4 || a.w < 16 || a.h < 2 || (first && !raw_out)) return 0;
+            ua = true;
+        }
+        g.load_align = (int)(lal & -lal) * 4;   // bytes every staged lane address is aligned to (band samples are ints)
+        g.x_align = xalign & -xalign;           // bytes the destination rows are aligned to
+        g.st_cls[0] = g.st_cls[1] = g.st_cls[2] = g.st_cls[3] = 4;
         const BandIO* bands[4] = {&a.ll, &a.hl, &a.lh_, &a.hh};
         float scl[4];
         for (int bi = 0; bi < 4; bi++) {
@@ -942,9 +991,14 @@ int build_ring_inv_impl(const Spec& s, Plan& P, const std::vector<long long>& ta
         g.ll = a.ll; g.hl = a.hl; g.lh_ = a.lh_; g.hh = a.hh;
         g.planes_out = nullptr; g.planes_off = a.planes_off; g.planes_comp_stride = a.planes_comp_stride; g.planes_row_stride = a.planes_row_stride;
         if (l.planes_buf) {
-            if ((a.planes_row_stride % 4) || (a.planes_comp_stride % 4)) return 0;
+            long long pal = 4 | a.planes_row_stride | a.planes_comp_stride;
             for (int i = 0; i < a.n_items; i++)
-                if (a.planes_off && (tab[(size_t)(a.planes_off - (const long long*)P.tables.p) + i] % 4)) return 0;
+                if (a.planes_off) pal |= tab[(size_t)(a.planes_off - (const long long*)P.tables.p) + i];
+            if (pal & 3) {
+                if (!env_int("J2K_RING_UA", 1) || l.NC != 1 || NP != 4 || a.w < 16 || a.h < 2) return 0;
+                ua = true;
+            }
+            g.st_cls[0] = (int)(pal & -pal);  // GetImageData plane rows (UA)
         }
         ring_chunks(g, NP, g.n_items, l.level, (J2K_INV_HALO_FREE && WT == 53) ? 0 : 2);
         g.dep_seg = -1; g.dep_div = 1; g.dep_target = 0; g.dep_mul = 1;
@@ -970,6 +1024,8 @@ int build_ring_inv_impl(const Spec& s, Plan& P, const std::vector<long long>& ta
         R.planes_buf[si] = l.planes_buf;
     }
     if (!have_first) return 0;
+    if (ua && (R.NC1 != 1 || R.NP1 != 4 || (R.IN1 != IN_U8 && R.IN1 != IN_U16))) return 0;  // a coarse level needs the general variant but level 1 has none
+    R.UA = ua ? 1 : 0;
     R.args.nseg = (int)order.size();
     for (int k = 0; k < R.args.nseg; k++) R.args.seg[k].has_waiters = 0;
     for (int k = 0; k < R.args.nseg; k++)
@@ -984,8 +1040,14 @@ int build_ring_inv_impl(const Spec& s, Plan& P, const std::vector<long long>& ta
     return 0;
 }
 
+#define RING_INV_CASE_UA(wt, out)                                                                                            \
+    if (R.WT == wt && R.NP1 == 4 && R.NC1 == 1 && R.IN1 == out && R.MCT1 == MCTK_NONE && R.UA) {                             \
+        if (query) return ring_blocks_per_sm((const void*)inv_ring_kernel<wt, 4, 1, out, MCTK_NONE, 1>, (inv_cta_smem<wt, 1, 1>())); \
+        J2K_LAUNCH_SMEM((inv_ring_kernel<wt, 4, 1, out, MCTK_NONE, 1>), grid, J2K_RING_WARPS * 32, (inv_cta_smem<wt, 1, 1>()), st, A); \
+        return 0;                                                                                                           \
+    }
 #define RING_INV_CASE(wt, np, nc, out, mct)                                                                                  \
-    if (R.WT == wt && R.NP1 == np && R.NC1 == nc && R.IN1 == out && R.MCT1 == mct) {                                         \
+    if (R.WT == wt && R.NP1 == np && R.NC1 == nc && R.IN1 == out && R.MCT1 == mct && !R.UA) {                                \
         if (query) return ring_blocks_per_sm((const void*)inv_ring_kernel<wt, np, nc, out, mct>, (inv_cta_smem<wt, nc>()));   \
         J2K_LAUNCH_SMEM((inv_ring_kernel<wt, np, nc, out, mct>), grid, J2K_RING_WARPS * 32, (inv_cta_smem<wt, nc>()), st, A); \
         return 0;                                                                                                           \
@@ -998,6 +1060,7 @@ int ring_dispatch_inv(const RingPlan& R, const RingArgs& A, unsigned grid, cudaS
     RING_INV_CASE(53, 4, 1, IN_U8, MCTK_NONE) RING_INV_CASE(53, 4, 1, IN_U16, MCTK_NONE)
     RING_INV_CASE(53, 2, 3, IN_U8, MCTK_RCT) RING_INV_CASE(53, 2, 3, IN_U16, MCTK_RCT)
     RING_INV_CASE(53, 4, 1, IN_I32, MCTK_NONE)
+    RING_INV_CASE_UA(97, IN_U8) RING_INV_CASE_UA(97, IN_U16) RING_INV_CASE_UA(53, IN_U8) RING_INV_CASE_UA(53, IN_U16)
     return -1;
 }
 
@@ -1972,6 +2035,8 @@ struct HostJob {
     int32_t* h_numbps = nullptr; // forward, block mode: cblkNumbps per block
     bool may_stage = true;       // synchronous call: pageable buffers go through the pinned staging ring (async: rejected)
     RoiShifts roi{};             // inverse, block mode: per-component MaxShift applied while scattering
+    const int32_t* h_block_shift = nullptr;      // inverse, block mode: general-scaling shift per (frame, block), or NULL
+    const unsigned char* h_sample_mask = nullptr; // and its optional per-sample mask (block-major, one byte per coefficient)
 };
 
 int enqueue_host_job(j2k_ctx* ctx, int di, const HostJob& J, int f0, int f1, bool timing) {
@@ -2047,7 +2112,24 @@ int enqueue_host_job(j2k_ctx* ctx, int di, const HostJob& J, int f0, int f1, boo
         long long fs = J.fwd ? (J.planar ? 0 : (long long)(J.pix_bytes_per_frame / (s.bit_depth <= 8 ? 1 : 2))) : (long long)(J.pix_bytes_per_frame / (s.bit_depth <= 8 ? 1 : 2));
         if ((rc = get_plan(d, s, J.pblob, J.pbytes, nb, fs, &P))) return rc;
         if (timing && it == 0) CK(cudaEventRecord(d.ev_t[1], d.s_main));
-        if (!J.fwd && BT && (rc = launch_scatter(ctx, *BT, nb, (const int32_t*)d.blk[slot].p, (int32_t*)d.in[slot].p, d.s_main, J.roi))) return rc;
+        if (!J.fwd && BT) {
+            RoiShifts roi = J.roi;
+            if (J.h_block_shift) {  // general scaling: this sub-batch's per-block shifts (and mask) go up behind the blocks
+                const size_t nsh = (size_t)nb * BT->nblocks * 4;
+                if ((rc = d.gsh[slot].ensure(nsh + 16))) return rc;
+                if ((rc = up(d.gsh[slot].p, (const unsigned char*)(J.h_block_shift + (size_t)b * BT->nblocks), nsh))) return rc;
+                roi.block_shift = (const int*)d.gsh[slot].p;
+                if (J.h_sample_mask) {
+                    const size_t nmk = (size_t)nb * J.coeffs_per_frame;
+                    if ((rc = d.gmk[slot].ensure(nmk + 16))) return rc;
+                    if ((rc = up(d.gmk[slot].p, J.h_sample_mask + (size_t)b * J.coeffs_per_frame, nmk))) return rc;
+                    roi.sample_mask = (const unsigned char*)d.gmk[slot].p;
+                }
+                CK(cudaEventRecord(d.ev_in[slot], d.s_h2d));
+                CK(cudaStreamWaitEvent(d.s_main, d.ev_in[slot], 0));
+            }
+            if ((rc = launch_scatter(ctx, *BT, nb, (const int32_t*)d.blk[slot].p, (int32_t*)d.in[slot].p, d.s_main, roi))) return rc;
+        }
         if (J.fwd) rc = run_plan(ctx, *P, d.in[slot].p, d.out[slot].p, nullptr, J.planar, d.s_main);
         else rc = run_plan(ctx, *P, d.out[slot].p, d.in[slot].p, J.h_planes ? d.planes[slot].p : nullptr, false, d.s_main);
         if (rc < 0) return rc;
@@ -2215,6 +2297,8 @@ void j2k_shutdown(j2k_ctx* ctx) {
         for (auto& b : d.planes) b.release();
         for (auto& b : d.blk) b.release();
         for (auto& b : d.nbp) b.release();
+        for (auto& b : d.gsh) b.release();
+        for (auto& b : d.gmk) b.release();
         d.block_tables.clear();
         for (auto& b : d.api) b.release();
         for (auto& ev : d.ev_t) if (ev) cudaEventDestroy(ev);
@@ -2230,6 +2314,13 @@ void j2k_shutdown(j2k_ctx* ctx) {
 }
 
 int j2k_device_count(const j2k_ctx* ctx) { return ctx ? (int)ctx->devs.size() : 0; }
+// CUDA devices visible to this process (0 when there is none or the runtime fails): what a binding passes to j2k_init to
+// build a context over every GPU.
+int j2k_visible_devices(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n < 0 ? 0 : n;
+}
 int64_t j2k_launch_count(const j2k_ctx* ctx) { return ctx ? (int64_t)ctx->launches.load() : 0; }
 
 int j2k_last_timing(j2k_ctx* ctx, j2k_timing* out) {
@@ -2345,6 +2436,23 @@ int j2k_forward_planar(j2k_ctx* ctx, const j2k_fwd_params* p, const int32_t* con
         if (!planes[c]) return fail(J2K_ERR_INVALID_ARG, "component %d is NULL", c);
         memcpy(packed.data() + c * hw, planes[c], hw * 4);
     }
+    return forward_host(ctx, p, 1, packed.data(), 0, coeffs_out, true, true, nullptr);
+}
+
+// The same with the component planes in ONE buffer (component c at planes + c * plane_stride): the form a cgo caller can
+// use, because a [][]int32 (Go pointers to Go pointers) cannot cross the boundary.
+int j2k_forward_planar_flat(j2k_ctx* ctx, const j2k_fwd_params* p, const int32_t* planes, size_t plane_stride, int32_t* coeffs_out,
+                            size_t ncoeffs) {
+    CtxGuard cg_(ctx);
+    if (!p || !planes) return fail(J2K_ERR_INVALID_ARG, "NULL argument");
+    int rc = validate_common(p->width, p->height, p->components, p->bit_depth, p->num_levels);
+    if (rc) return rc;
+    const size_t hw = (size_t)p->width * p->height;
+    if (plane_stride < hw) return fail(J2K_ERR_SIZE, "plane stride %zu smaller than a plane (%zu samples)", plane_stride, hw);
+    if (ncoeffs < j2k_fwd_coeff_count(p)) return fail(J2K_ERR_SIZE, "coefficient buffer too small");
+    if (plane_stride == hw) return forward_host(ctx, p, 1, planes, 0, coeffs_out, true, true, nullptr);
+    std::vector<int32_t> packed(hw * p->components);
+    for (int c = 0; c < p->components; c++) memcpy(packed.data() + c * hw, planes + c * plane_stride, hw * 4);
     return forward_host(ctx, p, 1, packed.data(), 0, coeffs_out, true, true, nullptr);
 }
 
@@ -2490,6 +2598,14 @@ int j2k_inverse_blocks(j2k_ctx* ctx, const j2k_inv_params* p, int cb_width, int 
 int j2k_inverse_blocks_roi(j2k_ctx* ctx, const j2k_inv_params* p, int cb_width, int cb_height, int nframes, const int32_t* blocks_in,
                            const int32_t* roi_maxshift, void* pixels_out, size_t frame_stride_bytes, int32_t* planes_out) {
     CtxGuard cg_(ctx);
+    return j2k_inverse_blocks_roi_general(ctx, p, cb_width, cb_height, nframes, blocks_in, roi_maxshift, nullptr, nullptr, pixels_out,
+                                          frame_stride_bytes, planes_out);
+}
+
+int j2k_inverse_blocks_roi_general(j2k_ctx* ctx, const j2k_inv_params* p, int cb_width, int cb_height, int nframes, const int32_t* blocks_in,
+                                   const int32_t* roi_maxshift, const int32_t* block_scale_shift, const uint8_t* sample_mask, void* pixels_out,
+                                   size_t frame_stride_bytes, int32_t* planes_out) {
+    CtxGuard cg_(ctx);
     if (!ctx) return fail(J2K_ERR_INVALID_ARG, "context is NULL");
     if (!p) return fail(J2K_ERR_INVALID_ARG, "params is NULL");
     int rc = validate_cb(cb_width, cb_height);
@@ -2505,6 +2621,15 @@ int j2k_inverse_blocks_roi(j2k_ctx* ctx, const j2k_inv_params* p, int cb_width, 
     J.frame_stride_bytes = frame_stride_bytes; J.cb_w = cb_width; J.cb_h = cb_height;
     if ((rc = make_roi(roi_maxshift, p->components, J.roi))) return rc;
     if (frame_stride_bytes < J.pix_bytes_per_frame) return fail(J2K_ERR_SIZE, "frame stride smaller than a frame");
+    if (sample_mask && !block_scale_shift) return fail(J2K_ERR_INVALID_ARG, "a sample mask needs the per-block general-scaling shifts");
+    if (block_scale_shift) {
+        const size_t nblk = j2k_inv_block_count(p, cb_width, cb_height);
+        for (size_t i = 0; i < nblk * (size_t)nframes; i++)
+            if (block_scale_shift[i] < 0 || block_scale_shift[i] > 30)
+                return fail(J2K_ERR_INVALID_ARG, "invalid general-scaling shift %d for block %zu (0..30)", block_scale_shift[i], i);
+        J.h_block_shift = block_scale_shift;
+        J.h_sample_mask = sample_mask;
+    }
     return run_host_batch(ctx, J, nframes, true, nullptr);
 }
 
@@ -2539,6 +2664,14 @@ int j2k_scatter_blocks_device(j2k_ctx* ctx, int dev, const j2k_inv_params* p, in
 int j2k_scatter_blocks_roi_device(j2k_ctx* ctx, int dev, const j2k_inv_params* p, int cb_width, int cb_height, int nframes,
                                   const int32_t* d_blocks, const int32_t* roi_maxshift, int32_t* d_coeffs, void* cuda_stream) {
     CtxGuard cg_(ctx);
+    return j2k_scatter_blocks_roi_general_device(ctx, dev, p, cb_width, cb_height, nframes, d_blocks, roi_maxshift, nullptr, nullptr, d_coeffs,
+                                                 cuda_stream);
+}
+
+int j2k_scatter_blocks_roi_general_device(j2k_ctx* ctx, int dev, const j2k_inv_params* p, int cb_width, int cb_height, int nframes,
+                                          const int32_t* d_blocks, const int32_t* roi_maxshift, const int32_t* d_block_scale_shift,
+                                          const uint8_t* d_sample_mask, int32_t* d_coeffs, void* cuda_stream) {
+    CtxGuard cg_(ctx);
     int rc = set_dev(ctx, dev);
     if (rc) return rc;
     if (!p) return fail(J2K_ERR_INVALID_ARG, "params is NULL");
@@ -2552,6 +2685,9 @@ int j2k_scatter_blocks_roi_device(j2k_ctx* ctx, int dev, const j2k_inv_params* p
     if ((rc = get_block_table(d, s, cb_width, cb_height, (long long)j2k_inv_coeff_count(p), &BT))) return rc;
     RoiShifts roi;
     if ((rc = make_roi(roi_maxshift, p->components, roi))) return rc;
+    if (d_sample_mask && !d_block_scale_shift) return fail(J2K_ERR_INVALID_ARG, "a sample mask needs the per-block general-scaling shifts");
+    roi.block_shift = (const int*)d_block_scale_shift;   // values must lie in 0..30 (not checked: device memory)
+    roi.sample_mask = d_sample_mask;
     return launch_scatter(ctx, *BT, nframes, d_blocks, d_coeffs, cuda_stream ? (cudaStream_t)cuda_stream : d.s_main, roi);
 }
 

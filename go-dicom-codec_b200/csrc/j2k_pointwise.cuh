@@ -307,7 +307,17 @@ struct BlockEntry {
 
 // Srgn = 0 (MaxShift) ROI shifts per component, 0 = none (t2/tile_decoder.go:726-730)
 #define J2K_ROI_MAXC 16
-struct RoiShifts { int any; int shift[J2K_ROI_MAXC]; };
+struct RoiShifts {
+    int any; int shift[J2K_ROI_MAXC];
+    // general scaling (RGN Srgn = 1, t2/tile_decoder.go:735-742): per (frame, block) shift, 0 = block outside the region;
+    // optional per-sample mask in block-major order (non-zero = the sample is divided), NULL = the whole block
+    const int* block_shift;
+    const unsigned char* sample_mask;
+};
+
+// applyInverseGeneralScaling (t2/tile_decoder.go:1082-1090): data /= 2^shift, Go's truncating division.  It follows the
+// classic 5/3 "/2" in decodeCodeBlock; truncating divisions by positive powers of two commute, so it may run before it.
+__device__ __forceinline__ int inverse_general_scaling(int v, int shift) { return shift > 0 ? v / (1 << shift) : v; }
 
 // applyInverseMaxShift (t2/tile_decoder.go:1113-1138): magnitudes at or above 2^shift belong to the ROI and come down by
 // `shift`; shift >= 31 zeroes the block.  -mag wraps for INT_MIN as in Go (then mag < thresh: untouched).
@@ -384,6 +394,18 @@ __global__ void __launch_bounds__(128) scatter_blocks_kernel(const int* __restri
     const int* src = blocks + frame * coeffs_per_frame + e.block_off;
     int* dst = coeffs + frame * coeffs_per_frame + e.plane_off;
     const int sh = roi.any ? roi.shift[e.comp] : 0;  // warp-uniform
+    const int gs = roi.block_shift ? roi.block_shift[frame * nblocks + b] : 0;  // warp-uniform: general scaling of this block
+    if (gs > 0) {  // the rare path: one sample at a time, masked or whole block
+        const unsigned char* mk = roi.sample_mask ? roi.sample_mask + frame * coeffs_per_frame + e.block_off : nullptr;
+        const int n = e.w * e.h;
+        for (int i = lane; i < n; i += 32) {
+            const int y = i / e.w, x = i - y * e.w;
+            int v = inverse_max_shift(src[i], sh);
+            if (!mk || mk[i]) v = inverse_general_scaling(v, gs);
+            dst[(long long)y * e.stride + x] = v;
+        }
+        return;
+    }
     if (e.vec && vec_ok) {
         const int w4 = e.w >> 2, n4 = w4 * e.h;
 #pragma unroll 4

@@ -48,10 +48,14 @@ namespace j2k {
 #ifndef J2K_RING_MINB
 #define J2K_RING_MINB 3      // resident CTAs per SM the register allocation targets (168 registers: no spills in the 9/7 loop)
 #endif
-#define J2K_RING_WARP_SMEM (J2K_RING_BYTES + J2K_RING_MAXD * 8)
-#define J2K_RING_CTA_SMEM (J2K_RING_WARPS * J2K_RING_WARP_SMEM)
+#ifndef J2K_RING_BYTES_UA
+#define J2K_RING_BYTES_UA 13056  // general-alignment variant: 3 stages of four 1088 B rows (float32), 5 of four 576 B rows (u16)
+#endif
 #ifndef J2K_INV_RING_BYTES
 #define J2K_INV_RING_BYTES 18432  // inverse: a stage holds four band rows per component (4 stages of 2 x four 576 B rows for halo-free strips)
+#endif
+#ifndef J2K_INV_RING_BYTES_UA
+#define J2K_INV_RING_BYTES_UA 18432  // general-alignment variant: 4 stages of 2 x four 576 B rows (9/7), 3 stages of 2 x four 608 B rows (5/3)
 #endif
 #ifndef J2K_INV_HALO_FREE
 #define J2K_INV_HALO_FREE 1       // 5/3 inverse: strips of 32 storing lanes (InvRing::HF)
@@ -78,6 +82,10 @@ struct RingSeg {
     FastQ q[4];
     float2 rcpE, nstE, rcpO, nstO;     // forward: quantizer pairs (LL, LH) and (HL, HH): reciprocal and negated step' (9/7)
                                        // inverse: rcpE / rcpO hold the dequantizer scale pairs (LL, LH) / (HL, HH)
+    // general-alignment variant (UA): bytes every staged lane address is aligned to; store vector width (ints) of the
+    // LL / HL / LH / HH rows (forward) or bytes the pixel / plane rows are aligned to (inverse: x_align)
+    int load_align, x_align;
+    int st_cls[4];
     int dep_mul;                       // inverse: the job waits on dep_mul consecutive counters starting at item * dep_mul
     int x_mode;                        // inverse, planar destination: 1 = store the 9/7 samples rounded half-even to int32
     int32_t* planes_out;               // inverse final: optional GetImageData planes (decoder.go:738-740)
@@ -136,6 +144,9 @@ __device__ __forceinline__ bool elect_one() { return emu::lane_id() == 0; }
 __device__ __forceinline__ uint4 lds128(smem_t a) { uint4 v; memcpy(&v, a, 16); return v; }
 __device__ __forceinline__ uint2 lds64(smem_t a) { uint2 v; memcpy(&v, a, 8); return v; }
 __device__ __forceinline__ unsigned lds32(smem_t a) { unsigned v; memcpy(&v, a, 4); return v; }
+__device__ __forceinline__ unsigned lds16(smem_t a) { unsigned short v; memcpy(&v, a, 2); return v; }
+__device__ __forceinline__ unsigned lds8(smem_t a) { return *a; }
+__device__ __forceinline__ void sts32(smem_t a, unsigned v) { memcpy(a, &v, 4); }
 #else
 #define J2K_SMEM_DECL(name) extern __shared__ __align__(128) unsigned char name[]
 typedef unsigned smem_t;  // 32-bit shared-window address
@@ -220,6 +231,17 @@ __device__ __forceinline__ unsigned lds32(smem_t a) {
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
 }
+__device__ __forceinline__ unsigned lds16(smem_t a) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ unsigned lds8(smem_t a) {
+    unsigned v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts32(smem_t a, unsigned v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 #endif
 
 struct RingWarp {
@@ -329,7 +351,15 @@ __device__ __forceinline__ unsigned pack_clamp2_magic(unsigned ua, unsigned ub, 
 // produces ONE component (item = 3 * pixel item + component): it converts all three samples of a pixel and evaluates
 // only its own row of the ICT, so the warp runs the single-component pipeline (NP = 4, full occupancy) at the price of
 // converting the raw bytes three times (they arrive through L2 / shared memory, not HBM).
-template <int WT, int NP, int NC, int IN, int MCT, int SG, int XC = 1>
+// UA = 1: the general-alignment variant.  Nothing about the window has to be a multiple of anything: rows may start at any
+// byte (the TMA copy then starts at the 16-byte boundary below the wanted segment and the row keeps its own phase, stored
+// in the slot's tail), lanes read their spans with the widest load every row's phase allows, band rows are stored with the
+// widest vector their alignment allows and masked at the window's right edge, so widths like 2140 or 2022 (CR / DX
+// detectors) and odd LL windows stay on the persistent kernel instead of falling to the per-level kernels.
+template <int UA> __host__ __device__ constexpr int fwd_ring_bytes() { return UA ? J2K_RING_BYTES_UA : J2K_RING_BYTES; }
+template <int UA> __host__ __device__ constexpr int fwd_cta_smem() { return J2K_RING_WARPS * (fwd_ring_bytes<UA>() + J2K_RING_MAXD * 8); }
+
+template <int WT, int NP, int NC, int IN, int MCT, int SG, int XC = 1, int UA = 0>
 struct FwdRing {
     typedef FwdLevel<WT, NP, NC, IN, MCT> Slow;
     typedef typename Wt<WT>::T T;
@@ -340,10 +370,12 @@ struct FwdRing {
     static constexpr int PB = ES * (RAWIN ? NC * XC : 1);  // bytes per pixel position of one staged row
     static constexpr int LB = NS * PB;                // bytes per lane per row
     static constexpr int NW = LB / 4;                 // 32-bit words per lane per row
-    static constexpr int ROWB = 32 * LB + 32;         // staged row slot (16 B slack for the alignment phase, 16 B rounding)
+    static constexpr int ROWB = 32 * LB + 32 + (UA ? 32 : 0);  // staged row slot (16 B slack for the alignment phase, 16 B rounding; UA: + the row's own phase, and its value in the last word)
     static constexpr int RPS = 2;                     // row pairs (= loop iterations) per stage: one barrier, one issue per two
+    static_assert(!UA || (NC == 1 && XC == 1 && NP == 4), "general alignment: single-component jobs");
     static constexpr int STAGEB = 2 * RPS * ROWB;
-    static constexpr int D = (J2K_RING_BYTES / STAGEB) > J2K_RING_MAXD ? J2K_RING_MAXD : (J2K_RING_BYTES / STAGEB);
+    static constexpr int RBYTES = fwd_ring_bytes<UA>();
+    static constexpr int D = (RBYTES / STAGEB) > J2K_RING_MAXD ? J2K_RING_MAXD : (RBYTES / STAGEB);
     static constexpr int LDALIGN = (LB % 16 == 0) ? 16 : (LB % 8 == 0 ? 8 : 4);
     static constexpr bool MAGIC = (WT == 97 && RAWIN && SG == 0);  // u8/u16 -> float32 without I2F
     static_assert(D >= 2, "ring too small for this row size");
@@ -367,6 +399,27 @@ struct FwdRing {
         } else {
 #pragma unroll
             for (int k = 0; k < NW; k++) w[k] = lds32(p + 4 * k);
+        }
+    }
+
+    // the same from an address that is only `la` bytes aligned (UA; warp-uniform la)
+    static __device__ __forceinline__ void fetch_ua(smem_t p, unsigned (&w)[NW], int la) {
+        if (la >= LDALIGN) { fetch(p, w); return; }
+        if (LB % 8 == 0 && la >= 8) {
+#pragma unroll
+            for (int k = 0; k < NW / 2; k++) {
+                uint2 q = lds64(p + 8 * k);
+                w[2 * k] = q.x; w[(2 * k + 1) % NW] = q.y;
+            }
+        } else if (la >= 4) {
+#pragma unroll
+            for (int k = 0; k < NW; k++) w[k] = lds32(p + 4 * k);
+        } else if (la >= 2) {
+#pragma unroll
+            for (int k = 0; k < NW; k++) w[k] = lds16(p + 4 * k) | (lds16(p + 4 * k + 2) << 16);
+        } else {
+#pragma unroll
+            for (int k = 0; k < NW; k++) w[k] = lds8(p + 4 * k) | (lds8(p + 4 * k + 1) << 8) | (lds8(p + 4 * k + 2) << 16) | (lds8(p + 4 * k + 3) << 24);
         }
     }
 
@@ -425,6 +478,7 @@ struct FwdRing {
 #pragma unroll
                 for (int r = 0; r < 2 * RPS; r++) {  // every row of the stage: one pass, one warp barrier per four rows
                     unsigned char* row = st + r * ROWB;
+                    if constexpr (UA) row += *(const int*)(row + ROWB - 4);  // this row's phase
 #pragma unroll
                     for (int c = 0; c < PB / ES; c++) {
                         if constexpr (ES == 1) row[d_o + c] = row[so + c];
@@ -440,8 +494,9 @@ struct FwdRing {
     // one staged row of this lane as working values in scalar form (5/3, signed raw words, border lanes)
     // (every lane reads its span, also the lanes past the strip's right halo: the slot is theirs, the junk they compute is
     // never stored and never reaches a storing lane -- no branch in front of the loads, so they hoist freely)
-    static __device__ __forceinline__ void load_scalar(smem_t row, int lane_off, const RawFmt& raw, int dc, T (&out)[NC][NS]) {
+    static __device__ __forceinline__ void load_scalar(smem_t row, int lane_off, const RawFmt& raw, int dc, T (&out)[NC][NS], int la = 16) {
         unsigned wv[NW];
+        if constexpr (UA) fetch_ua(row + lane_off + (int)lds32(row + ROWB - 4), wv, la); else
         fetch(row + lane_off, wv);
         int v[NC][NS];
         words_to_ints(wv, v);
@@ -450,9 +505,10 @@ struct FwdRing {
 
     // the same row as column pairs of float32 (9/7): pair j = samples 2j, 2j+1
     static __device__ __forceinline__ void load_pairs(smem_t row, int lane_off, const RawFmt& raw, int dc, float fmagic,
-                                                      float one, float2 (&out)[NC][NP], float k0 = 0.f, float k1 = 0.f, float k2 = 0.f) {
+                                                      float one, float2 (&out)[NC][NP], float k0 = 0.f, float k1 = 0.f, float k2 = 0.f, int la = 16) {
         {
             unsigned wv[NW];
+            if constexpr (UA) fetch_ua(row + lane_off + (int)lds32(row + ROWB - 4), wv, la); else
             fetch(row + lane_off, wv);
             if constexpr (XC == 3) {
                 // one row of the float32 ICT (encoder.go:277-288): (r * k0 + g * k1) + b * k2 on exact float32(int) inputs
@@ -528,6 +584,22 @@ struct FwdRing {
         else *p = o[0];
     }
 
+    // UA: nv of the lane's NP values lie inside the band (<= 0: none), the row allows `cls`-int vectors
+    static __device__ __forceinline__ void store_ua(int* p, const int (&o)[NP], int nv, int cls) {
+        if (nv >= NP && cls >= 4) { *(int4*)p = make_int4(o[0], o[1], o[2 % NP], o[3 % NP]); return; }
+        if (cls >= 2) {
+#pragma unroll
+            for (int j = 0; j + 1 < NP; j += 2) {
+                if (j + 1 < nv) *(int2*)(p + j) = make_int2(o[j], o[j + 1]);
+                else if (j < nv) p[j] = o[j];
+            }
+            return;
+        }
+#pragma unroll
+        for (int j = 0; j < NP; j++)
+            if (j < nv) p[j] = o[j];
+    }
+
     static __device__ __forceinline__ void run(const RingSeg& S, const RawFmt& raw, int item, int chunk, int strip, RingWarp& rw,
                                                int lane) {
         const int w = S.w, h = S.h, py = S.py;
@@ -544,10 +616,16 @@ struct FwdRing {
         const unsigned copy_bytes = (unsigned)(c1 - c0);
         const int dst_off = c0 - vb;
         const int lane_off = m + lane * LB;
-        const bool fix_l = kxs == 0, fix_r = kxe == S.Kx;           // warp-uniform: this strip touches a window border
+        // warp-uniform: this strip touches a window border (UA: its right halo lane may reach past the window although another,
+        // narrower strip follows)
+        const bool fix_l = kxs == 0, fix_r = UA ? (2 * kxe + NS > w) : (kxe == S.Kx);
         const bool fix = fix_l || fix_r;
-        // the window width is a multiple of 2 NP on this path: a lane stores whole vectors or nothing
-        const bool st = lane >= HLN && kx0 < kxe && kx0 + NP <= hw;
+        // the window width is a multiple of 2 NP on the aligned path: a lane stores whole vectors or nothing; UA masks per band
+        const bool st = lane >= HLN && kx0 < kxe && (UA || kx0 + NP <= hw);
+        const int nv_l = S.lw - kx0, nv_h = hw - kx0;   // UA: values of this lane inside the low- / high-pass bands
+        const int la = UA ? S.load_align : 16;
+        const int cls_ll = S.st_cls[0], cls_hl = S.st_cls[1], cls_lh = S.st_cls[2], cls_hh = S.st_cls[3];
+        (void)nv_l; (void)nv_h; (void)la; (void)cls_ll; (void)cls_hl; (void)cls_lh; (void)cls_hh;
 
         const unsigned long long pol_load = S.pol_load, pol_ll = S.pol_ll, pol_band = S.pol_band;
         (void)pol_load; (void)pol_ll; (void)pol_band;
@@ -592,6 +670,24 @@ struct FwdRing {
             if (elect_one()) {
                 const smem_t bar = rw.bars + 8 * pslot;
                 const smem_t dst = dst_s + pslot * STAGEB;
+                if constexpr (UA) {
+                    // every row starts at its own byte: copy from the 16-byte boundary below it, remember the phase in the slot
+                    const unsigned char* rp[2 * RPS];
+                    unsigned ph[2 * RPS], nb[2 * RPS], total = 0;
+                    const bool inr = pj >= s_lo && pj < s_hi;
+                    const int r0 = r_begin + 2 * RPS * pj;
+#pragma unroll
+                    for (int k = 0; k < 2 * RPS; k++) {
+                        rp[k] = inr ? psrc + k * pitch : src + (long long)mirror_fast(r0 + k, h) * pitch;
+                        ph[k] = (unsigned)((size_t)rp[k] & 15u);
+                        nb[k] = (ph[k] + copy_bytes + 15u) & ~15u;
+                        total += nb[k];
+                        sts32(rw.ring + pslot * STAGEB + k * ROWB + ROWB - 4, ph[k]);
+                    }
+                    mbar_expect_tx(bar, total);
+#pragma unroll
+                    for (int k = 0; k < 2 * RPS; k++) bulk_g2s(dst + k * ROWB, rp[k] - ph[k], nb[k], bar J2K_POL_ARG(pol_load));
+                } else {
                 mbar_expect_tx(bar, 2 * RPS * copy_bytes);
                 if (pj >= s_lo && pj < s_hi) {
 #pragma unroll
@@ -600,6 +696,7 @@ struct FwdRing {
                     const int r0 = r_begin + 2 * RPS * pj;
 #pragma unroll
                     for (int k = 0; k < 2 * RPS; k++) bulk_g2s(dst + k * ROWB, src + (long long)mirror_fast(r0 + k, h) * pitch, copy_bytes, bar J2K_POL_ARG(pol_load));
+                }
                 }
             }
             pj++;
@@ -643,8 +740,8 @@ struct FwdRing {
                 const smem_t row_e = stage + half * 2 * ROWB;
                 const smem_t row_o = row_e + ROWB;
 
-                load_pairs(row_e, lane_off, raw, dc, fmagic, one, out.pe, k0, k1, k2);
-                load_pairs(row_o, lane_off, raw, dc, fmagic, one, out.po, k0, k1, k2);
+                load_pairs(row_e, lane_off, raw, dc, fmagic, one, out.pe, k0, k1, k2, la);
+                load_pairs(row_o, lane_off, raw, dc, fmagic, one, out.po, k0, k1, k2, la);
                 // vertical lifting on column pairs; the finished (low, high) row values of column s land in Q[c][s]
                 float2 Q[NC][NS];
 #pragma unroll
@@ -725,6 +822,10 @@ struct FwdRing {
                             q_hh[j] = raw_hh ? __float_as_int(vo.y) : __float2int_rn(ro.y);
                         }
                     }
+                    if constexpr (UA) {
+                        if (row_l) { store_ua(p_ll, q_ll, nv_l, cls_ll); store_ua(p_hl, q_hl, nv_h, cls_hl); }
+                        if (row_h) { store_ua(p_lh, q_lh, nv_l, cls_lh); store_ua(p_hh, q_hh, nv_h, cls_hh); }
+                    } else {
                     if (row_l) {
                         store_vec(p_ll + c * cs_ll, q_ll, pol_ll);
                         store_vec(p_hl + c * cs_b, q_hl, pol_band);
@@ -732,6 +833,7 @@ struct FwdRing {
                     if (row_h) {
                         store_vec(p_lh + c * cs_b, q_lh, pol_band);
                         store_vec(p_hh + c * cs_b, q_hh, pol_band);
+                    }
                     }
                 }
                 p_ll += rs_ll; p_hl += rs_b; p_lh += rs_b; p_hh += rs_b;
@@ -767,8 +869,8 @@ struct FwdRing {
                 const smem_t row_o = row_e + ROWB;
 
                 int lo[NC][NS], hi[NC][NS];
-                load_scalar(row_e, lane_off, raw, dc, out.pe);
-                load_scalar(row_o, lane_off, raw, dc, out.po);
+                load_scalar(row_e, lane_off, raw, dc, out.pe, la);
+                load_scalar(row_o, lane_off, raw, dc, out.po, la);
 #pragma unroll
                 for (int c = 0; c < NC; c++)
 #pragma unroll
@@ -790,14 +892,18 @@ struct FwdRing {
                     if (row_l) {
 #pragma unroll
                         for (int j = 0; j < NP; j++) { q_a[j] = (int)((unsigned)lo[c][2 * j] << sh_ll); q_b[j] = (int)((unsigned)lo[c][2 * j + 1] << sh_hl); }
+                        if constexpr (UA) { store_ua(p_ll, q_a, nv_l, cls_ll); store_ua(p_hl, q_b, nv_h, cls_hl); } else {
                         store_vec(p_ll + c * cs_ll, q_a, pol_ll);
                         store_vec(p_hl + c * cs_b, q_b, pol_band);
+                        }
                     }
                     if (row_h) {
 #pragma unroll
                         for (int j = 0; j < NP; j++) { q_a[j] = (int)((unsigned)hi[c][2 * j] << sh_lh); q_b[j] = (int)((unsigned)hi[c][2 * j + 1] << sh_hh); }
+                        if constexpr (UA) { store_ua(p_lh, q_a, nv_l, cls_lh); store_ua(p_hh, q_b, nv_h, cls_hh); } else {
                         store_vec(p_lh + c * cs_b, q_a, pol_band);
                         store_vec(p_hh + c * cs_b, q_b, pol_band);
+                        }
                     }
                 }
                 p_ll += rs_ll; p_hl += rs_b; p_lh += rs_b; p_hh += rs_b;
@@ -977,12 +1083,12 @@ __device__ __forceinline__ void ring_warp_init(unsigned char* smem, RingWarp& rw
 #endif
 #define J2K_RING_BOUNDS __launch_bounds__(J2K_RING_WARPS * 32, (WT == 97 && NC1 == 3 && NP1 == 2) ? J2K_RING_MINB_RGB97 : J2K_RING_MINB)
 #endif
-template <int WT, int NP1, int NC1, int IN1, int MCT1, int SG1>
+template <int WT, int NP1, int NC1, int IN1, int MCT1, int SG1, int UA = 0>
 __global__ void J2K_RING_BOUNDS fwd_ring_kernel(const __grid_constant__ RingArgs A) {
     J2K_SMEM_DECL(smem);
     const int lane = threadIdx.x & 31;
     RingWarp rw;
-    ring_warp_init(smem, rw, lane, J2K_RING_BYTES);
+    ring_warp_init(smem, rw, lane, fwd_ring_bytes<UA>());
     rw.one = A.one;
     RingJob J;
     J2K_RING_SCHED_DECL(A, sched);
@@ -999,8 +1105,8 @@ __global__ void J2K_RING_BOUNDS fwd_ring_kernel(const __grid_constant__ RingArgs
         if (S.first) {
             // NC1 == 3 with NP1 == 4 names the component-split variant (one component per job)
             if constexpr (NC1 == 3 && NP1 == 4) FwdRing<WT, 4, 1, IN1, MCT1, SG1, 3>::run(S, A.raw, J.item, J.chunk, J.strip, rw, lane);
-            else FwdRing<WT, NP1, NC1, IN1, MCT1, SG1>::run(S, A.raw, J.item, J.chunk, J.strip, rw, lane);
-        } else FwdRing<WT, 4, 1, (WT == 53 ? IN_I32 : IN_F32), MCTK_NONE, 0>::run(S, A.raw, J.item, J.chunk, J.strip, rw, lane);
+            else FwdRing<WT, NP1, NC1, IN1, MCT1, SG1, 1, UA>::run(S, A.raw, J.item, J.chunk, J.strip, rw, lane);
+        } else FwdRing<WT, 4, 1, (WT == 53 ? IN_I32 : IN_F32), MCTK_NONE, 0, 1, UA>::run(S, A.raw, J.item, J.chunk, J.strip, rw, lane);
         ring_signal(A, S, J.item, lane);
     }
     ring_retire(A, lane);
@@ -1020,10 +1126,15 @@ namespace j2k {
 // Reference order per level: rows, then columns (dwt53.go:318-354, dwt97.go:360-384).
 
 // staging bytes per warp of the inverse kernel whose level-1 variant is (WT, NC1)
-template <int WT, int NC1> __host__ __device__ constexpr int inv_ring_bytes() { return (WT == 53 && NC1 == 1) ? J2K_INV_RING_BYTES_53 : J2K_INV_RING_BYTES; }
-template <int WT, int NC1> __host__ __device__ constexpr int inv_cta_smem() { return J2K_RING_WARPS * (inv_ring_bytes<WT, NC1>() + J2K_RING_MAXD * 8); }
+template <int WT, int NC1, int UA = 0> __host__ __device__ constexpr int inv_ring_bytes() {
+    return UA ? J2K_INV_RING_BYTES_UA : ((WT == 53 && NC1 == 1) ? J2K_INV_RING_BYTES_53 : J2K_INV_RING_BYTES);
+}
+template <int WT, int NC1, int UA = 0> __host__ __device__ constexpr int inv_cta_smem() { return J2K_RING_WARPS * (inv_ring_bytes<WT, NC1, UA>() + J2K_RING_MAXD * 8); }
 
-template <int WT, int NP, int NC, int OUT, int MCT, int RB = J2K_INV_RING_BYTES>
+// UA = 1: general-alignment variant of the inverse (see FwdRing): band rows staged from any byte position with their own
+// phase, lanes fetch with the widest load the phases allow, pixel / LL rows stored with the widest access their alignment
+// allows and masked at the window's right edge; odd window widths (low band one sample wider than the high band) included.
+template <int WT, int NP, int NC, int OUT, int MCT, int RB = J2K_INV_RING_BYTES, int UA = 0>
 struct InvRing {
     typedef typename Wt<WT>::T T;
     static constexpr int LAG = Wt<WT>::LAG;
@@ -1038,8 +1149,9 @@ struct InvRing {
     static constexpr int NS = 2 * NP;
     static constexpr bool FINAL = (OUT == IN_U8 || OUT == IN_U16);
     static constexpr int LB = NP * 4;          // bytes per lane per band row
-    static constexpr int ROWB = (32 + 2 * SHL) * LB + 32;  // staged band row slot
+    static constexpr int ROWB = (32 + 2 * SHL) * LB + 32 + (UA ? 32 : 0);  // staged band row slot (UA: + the row's phase, its value in the last word)
     static constexpr int NROWS = 4 * NC;       // LL, HL, LH, HH per component
+    static_assert(!UA || (NC == 1 && NP == 4), "general alignment: single-component jobs");
     static constexpr int RPS = (NC == 1) ? 2 : 1;  // row pairs (= loop iterations) per stage
     static constexpr int PAIRB = NROWS * ROWB;     // staged bytes of one row pair
     static constexpr int STAGEB = RPS * PAIRB;
@@ -1053,30 +1165,85 @@ struct InvRing {
         else q[0] = (int)lds32(p);
     }
 
+    // the lane's NP band samples from an address that is only `la` bytes aligned (UA; warp-uniform la >= 4)
+    static __device__ __forceinline__ void fetch_ua(smem_t p, int (&q)[NP], int la) {
+        if (la >= 16) { fetch(p, q); return; }
+        if (la >= 8) {
+#pragma unroll
+            for (int k = 0; k < NP / 2; k++) { uint2 v = lds64(p + 8 * k); q[2 * k] = (int)v.x; q[(2 * k + 1) % NP] = (int)v.y; }
+        } else {
+#pragma unroll
+            for (int k = 0; k < NP; k++) q[k] = (int)lds32(p + 4 * k);
+        }
+    }
+    static __device__ __forceinline__ int row_phase(smem_t row) { return UA ? (int)lds32(row + ROWB - 4) : 0; }
+
     // Border strips: band samples just outside the window, mirrored in the interleaved domain (low stays low, high
     // stays high): lanes 0..NP-1 write the left span, lanes NP..2NP-1 the right one, in every staged band row.
+    // An odd window has one high-pass sample less than low-pass samples: the high rows' outside starts one index earlier.
     static __device__ __forceinline__ void fix_halo(smem_t stage, int lane, bool fix_l, bool fix_r, int w, int bw, int vb) {
         if (lane < 2 * NP) {
             const bool left = lane < NP;
             const int k = left ? lane : lane - NP;
             if (left ? fix_l : fix_r) {
                 const int kx = left ? -(k + 1) : bw + k;  // band index outside [0, bw)
-                const int src_lo = mirror_fast(2 * kx, w) >> 1, src_hi = (mirror_fast(2 * kx + 1, w) - 1) >> 1;
+                const int kxh = (UA && !left) ? kx - (2 * bw - w) : kx;  // the same for the high-pass rows (w - bw samples)
+                const int src_lo = mirror_fast(2 * kx, w) >> 1, src_hi = (mirror_fast(2 * kxh + 1, w) - 1) >> 1;
                 unsigned char* st = smem_ptr(stage);
 #pragma unroll
                 for (int r = 0; r < RPS * NROWS; r++) {  // every band row of the stage (PAIRB == NROWS * ROWB)
                     const int src = (r & 1) ? src_hi : src_lo;  // rows 1, 3 (HL, HH) are horizontally high-pass
+                    const int dst = (r & 1) ? kxh : kx;
                     unsigned char* row = st + r * ROWB;
-                    *(unsigned*)(row + kx * 4 - vb) = *(const unsigned*)(row + src * 4 - vb);
+                    if constexpr (UA) row += *(const int*)(row + ROWB - 4);  // this row's phase
+                    *(unsigned*)(row + dst * 4 - vb) = *(const unsigned*)(row + src * 4 - vb);
                 }
             }
         }
         __syncwarp();
     }
 
+    // UA stores.  n valid ints of q at p, rows allowing `cls`-int vectors (planar destinations: LL planes, wavelet API)
+    static __device__ __forceinline__ void store_ints_ua(int* p, const int (&q)[NS], int n, int cls) {
+#pragma unroll
+        for (int g = 0; g < NS; g += 4) {
+            if (g + 4 <= n && cls >= 4) { *(int4*)(p + g) = make_int4(q[g], q[g + 1], q[(g + 2) % NS], q[(g + 3) % NS]); continue; }
+#pragma unroll
+            for (int j = g; j < g + 4 && j < NS; j += 2) {
+                if (j + 1 < n && cls >= 2) *(int2*)(p + j) = make_int2(q[j], q[(j + 1) % NS]);
+                else { if (j < n) p[j] = q[j]; if (j + 1 < n) p[j + 1] = q[(j + 1) % NS]; }
+            }
+        }
+    }
+    // nb valid bytes of the packed words wv at xrow, which is `al` bytes aligned (packed pixel rows)
+    template <int NWO>
+    static __device__ __forceinline__ void store_bytes_ua(unsigned char* xrow, const unsigned (&wv)[NWO], int nb, int al) {
+        if (nb >= NWO * 4 && al >= NWO * 4) {
+            if constexpr (NWO == 4) *(uint4*)xrow = make_uint4(wv[0], wv[1], wv[2 % NWO], wv[3 % NWO]);
+            else if constexpr (NWO == 2) *(uint2*)xrow = make_uint2(wv[0], wv[1 % NWO]);
+            else *(unsigned*)xrow = wv[0];
+            return;
+        }
+#pragma unroll
+        for (int k = 0; k < NWO; k++) {
+            const int left = nb - 4 * k;  // valid bytes of this word
+            if (left >= 4 && al >= 4) { *(unsigned*)(xrow + 4 * k) = wv[k]; continue; }
+            if (al >= 2) {
+                if (left >= 2) *(unsigned short*)(xrow + 4 * k) = (unsigned short)(wv[k] & 0xFFFFu);
+                else if (left >= 1) xrow[4 * k] = (unsigned char)(wv[k] & 0xFFu);
+                if (left >= 4) *(unsigned short*)(xrow + 4 * k + 2) = (unsigned short)(wv[k] >> 16);
+                else if (left >= 3) xrow[4 * k + 2] = (unsigned char)((wv[k] >> 16) & 0xFFu);
+            } else {
+#pragma unroll
+                for (int b = 0; b < 4; b++)
+                    if (b < left) xrow[4 * k + b] = (unsigned char)((wv[k] >> (8 * b)) & 0xFFu);
+            }
+        }
+    }
+
     // final stage of level 1: inverse MCT -> (+DC, optional planes) -> clamp -> pack -> one vector store per row
     static __device__ __forceinline__ void store_final(const RingSeg& S, const RawFmt& raw, const RawPack& rp, unsigned char* xrow, int* prow,
-                                                       int (&iv)[NC][NS]) {
+                                                       int (&iv)[NC][NS], int nvs = NS, int xal = 16, int pcls = 4) {
         if constexpr (NC == 3 && MCT != MCTK_NONE) {
 #pragma unroll
             for (int s = 0; s < NS; s++) {
@@ -1085,6 +1252,14 @@ struct InvRing {
                 iv[0][s] = r; iv[1][s] = g; iv[2][s] = b;
             }
         }
+        if constexpr (UA) {
+            if (prow) {
+                int t[NS];
+#pragma unroll
+                for (int s = 0; s < NS; s++) t[s] = iv[0][s] + raw.dc;
+                store_ints_ua(prow, t, nvs, pcls);
+            }
+        } else
         if (prow) {
 #pragma unroll
             for (int c = 0; c < NC; c++) {
@@ -1111,6 +1286,7 @@ struct InvRing {
                 wv[k] = pack_clamp2(iv[(2 * k) % NC][(2 * k) / NC], iv[(2 * k + 1) % NC][(2 * k + 1) / NC], rp);
             }
         }
+        if constexpr (UA) { store_bytes_ua<NWO>(xrow, wv, nvs * ES, xal); return; }
         if constexpr (NWO % 4 == 0) {
 #pragma unroll
             for (int k = 0; k < NWO / 4; k++) *((uint4*)xrow + k) = make_uint4(wv[4 * k], wv[4 * k + 1], wv[(4 * k + 2) % NWO], wv[(4 * k + 3) % NWO]);
@@ -1213,9 +1389,13 @@ struct InvRing {
         const unsigned copy_bytes = (unsigned)(c1 - c0);
         const int dst_off = c0 - vb;
         const int lane_off = m + (lane + SHL) * LB;
-        const bool fix_l = kxs == 0, fix_r = kxe == S.Kx;
+        // (UA: the lanes right of a strip may reach past the high-pass band although another, narrower strip follows)
+        const bool fix_l = kxs == 0, fix_r = UA ? (kxe + NP > w - bw) : (kxe == S.Kx);
         const bool fix = fix_l || fix_r;
-        const bool st = lane >= HLN && kx0 < kxe && kx0 + NP <= bw;
+        const bool st = lane >= HLN && kx0 < kxe && (UA || kx0 + NP <= bw);
+        const int nvs = w - 2 * kx0;                 // UA: samples of this lane inside the window (<= 0: none, >= NS: all)
+        const int la = UA ? S.load_align : 16, xal = UA ? S.x_align : 16, pcls = UA ? S.st_cls[0] : 4;
+        (void)nvs; (void)la; (void)xal; (void)pcls;
         const float one = rw.one;
 
         const int ky0 = chunk * S.chunk_pairs;
@@ -1248,6 +1428,33 @@ struct InvRing {
             if (elect_one()) {
                 const smem_t bar = rw.bars + 8 * pslot;
                 const smem_t dst = dst_s + pslot * STAGEB;
+                if constexpr (UA) {
+                    // every band row starts at its own byte: copy from the 16-byte boundary below, remember the phase in the slot
+                    const unsigned char* rp[RPS * 4];
+                    unsigned ph[RPS * 4], nb[RPS * 4], total = 0;
+                    const bool inr = pj >= s_lo && pj < s_hi;
+#pragma unroll
+                    for (int k = 0; k < RPS; k++) {
+                        if (inr) {
+                            rp[4 * k + 0] = q_ll + k * rp_ll; rp[4 * k + 1] = q_hl + k * rp_b; rp[4 * k + 2] = q_lh + k * rp_b; rp[4 * k + 3] = q_hh + k * rp_b;
+                        } else {
+                            const int t = t_begin + RPS * pj + k;
+                            const int pl = mirror_fast(2 * t - py, h), phh = mirror_fast(2 * t + 1 - py, h);
+                            const int yl = (pl - py) >> 1, yh = (phh - (1 - py)) >> 1;
+                            rp[4 * k + 0] = b_ll + yl * rp_ll; rp[4 * k + 1] = b_hl + yl * rp_b; rp[4 * k + 2] = b_lh + yh * rp_b; rp[4 * k + 3] = b_hh + yh * rp_b;
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < RPS * 4; r++) {
+                        ph[r] = (unsigned)((size_t)rp[r] & 15u);
+                        nb[r] = (ph[r] + copy_bytes + 15u) & ~15u;
+                        total += nb[r];
+                        sts32(rw.ring + pslot * STAGEB + r * ROWB + ROWB - 4, ph[r]);
+                    }
+                    mbar_expect_tx(bar, total);
+#pragma unroll
+                    for (int r = 0; r < RPS * 4; r++) bulk_g2s(dst + r * ROWB, rp[r] - ph[r], nb[r], bar);
+                } else {
                 mbar_expect_tx(bar, RPS * NROWS * copy_bytes);
                 if (pj >= s_lo && pj < s_hi) {
 #pragma unroll
@@ -1274,6 +1481,7 @@ struct InvRing {
                             bulk_g2s(dst + k * PAIRB + (4 * c + 3) * ROWB, b_hh + c * cp_b + yh * rp_b, copy_bytes, bar);
                         }
                     }
+                }
                 }
             }
             pj++;
@@ -1329,10 +1537,18 @@ struct InvRing {
                     // dequantize: S[j] = (LL, LH)[j], Dd[j] = (HL, HH)[j] as (low-type row, high-type row) pairs
                     float2 Sx[NP + 1], Dx[NP + 1];  // Dx[0] = previous lane's last high, Sx[NP] = next lane's first low
                     int q0[NP], q1[NP], q2[NP], q3[NP];
+                    if constexpr (UA) {
+                        const smem_t r0 = stage + (4 * c) * ROWB;
+                        fetch_ua(r0 + lane_off + row_phase(r0), q0, la);
+                        fetch_ua(r0 + ROWB + lane_off + row_phase(r0 + ROWB), q1, la);
+                        fetch_ua(r0 + 2 * ROWB + lane_off + row_phase(r0 + 2 * ROWB), q2, la);
+                        fetch_ua(r0 + 3 * ROWB + lane_off + row_phase(r0 + 3 * ROWB), q3, la);
+                    } else {
                     fetch(stage + (4 * c + 0) * ROWB + lane_off, q0);  // every lane, also past the strip (see FwdRing::load_scalar)
                     fetch(stage + (4 * c + 1) * ROWB + lane_off, q1);
                     fetch(stage + (4 * c + 2) * ROWB + lane_off, q2);
                     fetch(stage + (4 * c + 3) * ROWB + lane_off, q3);
+                    }
                     // float32(q) * float32(scale) (t2/tile_decoder.go:970-987); DQ_CVT is scale == 1 (exact); then the
                     // horizontal synthesis scaling: low * K, high * two_invK (dwt97.go:207-212)
                     if (std_modes) {  // every level but the coarsest: LL is the float32 plane of the level below
@@ -1420,7 +1636,7 @@ struct InvRing {
                             for (int c = 0; c < NC; c++)
 #pragma unroll
                                 for (int j = 0; j < NP; j++) { iv[c][2 * j] = __float2int_rn(xe[c][j].x); iv[c][2 * j + 1] = __float2int_rn(xe[c][j].y); }
-                            store_final(S, raw, rp, xrow, prow, iv);
+                            store_final(S, raw, rp, xrow, prow, iv, nvs, xal, pcls);
                         }
                     }
                     if (ro < h) {
@@ -1431,7 +1647,7 @@ struct InvRing {
                             for (int c = 0; c < NC; c++)
 #pragma unroll
                                 for (int j = 0; j < NP; j++) { iv[c][2 * j] = __float2int_rn(xo[c][j].x); iv[c][2 * j + 1] = __float2int_rn(xo[c][j].y); }
-                            store_final(S, raw, rp, xrow + xpitch, prow ? prow + planes_rs : nullptr, iv);
+                            store_final(S, raw, rp, xrow + xpitch, prow ? prow + planes_rs : nullptr, iv, nvs, xal, pcls);
                         }
                     }
                 } else {
@@ -1442,6 +1658,7 @@ struct InvRing {
                             q[2 * j] = x_mode == 1 ? __float2int_rn(xe[0][j].x) : __float_as_int(xe[0][j].x);
                             q[2 * j + 1] = x_mode == 1 ? __float2int_rn(xe[0][j].y) : __float_as_int(xe[0][j].y);
                         }
+                        if constexpr (UA) store_ints_ua((int*)xrow, q, nvs, xal >> 2); else
                         store_planar((int*)xrow, q);
                     }
                     if (ro < h) {
@@ -1450,6 +1667,7 @@ struct InvRing {
                             q[2 * j] = x_mode == 1 ? __float2int_rn(xo[0][j].x) : __float_as_int(xo[0][j].x);
                             q[2 * j + 1] = x_mode == 1 ? __float2int_rn(xo[0][j].y) : __float_as_int(xo[0][j].y);
                         }
+                        if constexpr (UA) store_ints_ua((int*)(xrow + xpitch), q, nvs, xal >> 2); else
                         store_planar((int*)(xrow + xpitch), q);
                     }
                 }
@@ -1489,10 +1707,18 @@ struct InvRing {
 #pragma unroll
                 for (int c = 0; c < NC; c++) {
                     int q0[NP], q1[NP], q2[NP], q3[NP];
+                    if constexpr (UA) {
+                        const smem_t r0 = stage + (4 * c) * ROWB;
+                        fetch_ua(r0 + lane_off + row_phase(r0), q0, la);
+                        fetch_ua(r0 + ROWB + lane_off + row_phase(r0 + ROWB), q1, la);
+                        fetch_ua(r0 + 2 * ROWB + lane_off + row_phase(r0 + 2 * ROWB), q2, la);
+                        fetch_ua(r0 + 3 * ROWB + lane_off + row_phase(r0 + 3 * ROWB), q3, la);
+                    } else {
                     fetch(stage + (4 * c + 0) * ROWB + lane_off, q0);  // every lane, also past the strip (see FwdRing::load_scalar)
                     fetch(stage + (4 * c + 1) * ROWB + lane_off, q1);
                     fetch(stage + (4 * c + 2) * ROWB + lane_off, q2);
                     fetch(stage + (4 * c + 3) * ROWB + lane_off, q3);
+                    }
                     // t2/tile_decoder.go:989-993: truncating /2 of the classic T1 output (fuse_t1_halve only: warp-uniform)
                     if (any_halve) {
 #pragma unroll
@@ -1513,7 +1739,8 @@ struct InvRing {
 #pragma unroll
                         for (int j = 0; j < NP; j++) { s[j] = ql[j]; d[j + 1] = qh[j]; }
                         if constexpr (HF) {
-                            const smem_t pl = stage + row_l * ROWB + lane_off, ph = pl + ROWB;
+                            const smem_t rl = stage + row_l * ROWB;
+                            const smem_t pl = rl + lane_off + row_phase(rl), ph = rl + ROWB + lane_off + row_phase(rl + ROWB);
                             int dl = (int)lds32(ph - 4), sr = (int)lds32(pl + LB), dr = (int)lds32(ph + LB);
                             if (halve_h) { dl /= 2; dr /= 2; }
                             if (halve_l) sr /= 2;
@@ -1553,8 +1780,11 @@ struct InvRing {
                 if (planes) planes += 2 * planes_rs;
                 if (!st) return;
                 if constexpr (FINAL) {
-                    if (re >= 0 && re < h) store_final(S, raw, rp, xrow, prow, xe);
-                    if (ro < h) store_final(S, raw, rp, xrow + xpitch, prow ? prow + planes_rs : nullptr, xo);
+                    if (re >= 0 && re < h) store_final(S, raw, rp, xrow, prow, xe, nvs, xal, pcls);
+                    if (ro < h) store_final(S, raw, rp, xrow + xpitch, prow ? prow + planes_rs : nullptr, xo, nvs, xal, pcls);
+                } else if constexpr (UA) {
+                    if (re >= 0 && re < h) store_ints_ua((int*)xrow, xe[0], nvs, xal >> 2);
+                    if (ro < h) store_ints_ua((int*)(xrow + xpitch), xo[0], nvs, xal >> 2);
                 } else {
                     if (re >= 0 && re < h) store_planar((int*)xrow, xe[0]);
                     if (ro < h) store_planar((int*)(xrow + xpitch), xo[0]);
@@ -1587,12 +1817,12 @@ struct InvRing {
 #ifndef J2K_INV_RGB_NP
 #define J2K_INV_RGB_NP 2     // sample pairs per lane of the 3-component level-1 inverse (4: 2 CTAs/SM, the window state of three components in 255 registers)
 #endif
-template <int WT, int NP1, int NC1, int OUT1, int MCT1>
-__global__ void __launch_bounds__(J2K_RING_WARPS * 32, (NC1 == 3 && NP1 == 4) ? 2 : ((WT == 53 && NC1 == 1) ? J2K_INV_MINB_53 : J2K_RING_MINB)) inv_ring_kernel(const __grid_constant__ RingArgs A) {
+template <int WT, int NP1, int NC1, int OUT1, int MCT1, int UA = 0>
+__global__ void __launch_bounds__(J2K_RING_WARPS * 32, (NC1 == 3 && NP1 == 4) ? 2 : ((WT == 53 && NC1 == 1 && !UA) ? J2K_INV_MINB_53 : J2K_RING_MINB)) inv_ring_kernel(const __grid_constant__ RingArgs A) {
     J2K_SMEM_DECL(smem);
     const int lane = threadIdx.x & 31;
     RingWarp rw;
-    constexpr int RB = inv_ring_bytes<WT, NC1>();
+    constexpr int RB = inv_ring_bytes<WT, NC1, UA>();
     ring_warp_init(smem, rw, lane, RB);
     rw.one = A.one;
     RingJob J;
@@ -1603,8 +1833,8 @@ __global__ void __launch_bounds__(J2K_RING_WARPS * 32, (NC1 == 3 && NP1 == 4) ? 
     while (ring_claim<(J2K_INV_CTA_CLAIM != 0)>(A, sched, lane, J)) {
         const RingSeg& S = A.seg[J.seg];
         ring_wait_dep(A, S, J.item, lane);
-        if (S.first) InvRing<WT, NP1, NC1, OUT1, MCT1, RB>::run(S, A.raw, J.item, J.chunk, J.strip, rw, lane);
-        else InvRing<WT, 4, 1, (WT == 53 ? IN_I32 : IN_F32), MCTK_NONE, RB>::run(S, A.raw, J.item, J.chunk, J.strip, rw, lane);
+        if (S.first) InvRing<WT, NP1, NC1, OUT1, MCT1, RB, UA>::run(S, A.raw, J.item, J.chunk, J.strip, rw, lane);
+        else InvRing<WT, 4, 1, (WT == 53 ? IN_I32 : IN_F32), MCTK_NONE, RB, UA>::run(S, A.raw, J.item, J.chunk, J.strip, rw, lane);
         ring_signal(A, S, J.item, lane);
     }
     ring_retire(A, lane);

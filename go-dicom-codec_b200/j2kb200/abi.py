@@ -175,15 +175,16 @@ LIB_PATH = os.path.join(os.path.dirname(_PKG_DIR), "csrc", "build", "libj2kb200.
 
 # every symbol include/j2k_b200.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = [
-    "j2k_init", "j2k_shutdown", "j2k_last_error", "j2k_last_error_copy", "j2k_abi_version", "j2k_device_count", "j2k_launch_count",
+    "j2k_init", "j2k_shutdown", "j2k_last_error", "j2k_last_error_copy", "j2k_abi_version", "j2k_device_count", "j2k_visible_devices", "j2k_launch_count",
     "j2k_last_timing", "j2k_set_profiling", "j2k_get_profile", "j2k_acquire_buffer", "j2k_release_buffer",
     "j2k_fwd_pixel_bytes", "j2k_fwd_coeff_count", "j2k_inv_pixel_bytes", "j2k_inv_coeff_count",
     "j2k_fwd_tile_bounds", "j2k_inv_tile_bounds",
-    "j2k_forward", "j2k_forward_planar", "j2k_forward_batch", "j2k_forward_device",
+    "j2k_forward", "j2k_forward_planar", "j2k_forward_planar_flat", "j2k_forward_batch", "j2k_forward_device",
     "j2k_inverse", "j2k_inverse_batch", "j2k_inverse_device",
     "j2k_submit_forward", "j2k_submit_inverse", "j2k_wait",
     "j2k_codeblock_layout", "j2k_fwd_block_count", "j2k_inv_block_count", "j2k_forward_blocks", "j2k_inverse_blocks",
     "j2k_gather_blocks_device", "j2k_scatter_blocks_device", "j2k_inverse_blocks_roi", "j2k_scatter_blocks_roi_device",
+    "j2k_inverse_blocks_roi_general", "j2k_scatter_blocks_roi_general_device",
     "j2k_dwt53_forward", "j2k_dwt53_inverse", "j2k_dwt97_forward", "j2k_dwt97_inverse", "j2k_convert_f32_to_i32",
     "j2k_rct_forward", "j2k_rct_inverse", "j2k_ict_forward", "j2k_ict_inverse",
     "j2k_dwt97_forward_f64", "j2k_dwt97_inverse_f64", "j2k_convert_f64_to_i32", "j2k_ll_dimensions",
@@ -219,6 +220,7 @@ def load(path: str | None = None) -> C.CDLL:
         "j2k_last_error_copy": (C.c_size_t, [vp, C.c_char_p, C.c_size_t]),
         "j2k_abi_version": (ci, []),
         "j2k_device_count": (ci, [vp]),
+        "j2k_visible_devices": (ci, []),
         "j2k_launch_count": (C.c_int64, [vp]),
         "j2k_last_timing": (ci, [vp, C.POINTER(Timing)]),
         "j2k_set_profiling": (ci, [vp, ci]),
@@ -233,6 +235,7 @@ def load(path: str | None = None) -> C.CDLL:
         "j2k_inv_tile_bounds": (ci, [IP, ci, i32p]),
         "j2k_forward": (ci, [vp, FP, vp, sz, vp, sz]),
         "j2k_forward_planar": (ci, [vp, FP, C.POINTER(vp), vp, sz]),
+        "j2k_forward_planar_flat": (ci, [vp, FP, vp, sz, vp, sz]),
         "j2k_forward_batch": (ci, [vp, FP, ci, vp, sz, vp]),
         "j2k_forward_device": (ci, [vp, ci, FP, ci, vp, sz, vp, vp]),
         "j2k_inverse": (ci, [vp, IP, vp, sz, vp, sz, vp]),
@@ -249,6 +252,8 @@ def load(path: str | None = None) -> C.CDLL:
         "j2k_gather_blocks_device": (ci, [vp, ci, FP, ci, ci, ci, vp, vp, vp, vp]),
         "j2k_scatter_blocks_device": (ci, [vp, ci, IP, ci, ci, ci, vp, vp, vp]),
         "j2k_inverse_blocks_roi": (ci, [vp, IP, ci, ci, ci, vp, vp, vp, sz, vp]),
+        "j2k_inverse_blocks_roi_general": (ci, [vp, IP, ci, ci, ci, vp, vp, vp, vp, vp, sz, vp]),
+        "j2k_scatter_blocks_roi_general_device": (ci, [vp, ci, IP, ci, ci, ci, vp, vp, vp, vp, vp, vp]),
         "j2k_scatter_blocks_roi_device": (ci, [vp, ci, IP, ci, ci, ci, vp, vp, vp, vp]),
         "j2k_dwt53_forward": (ci, [vp, vp, ci, ci, ci, ci, ci]),
         "j2k_dwt53_inverse": (ci, [vp, vp, ci, ci, ci, ci, ci]),

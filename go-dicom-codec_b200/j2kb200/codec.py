@@ -99,6 +99,14 @@ class Context:
         self._ck(self.lib.j2k_forward_planar(self.h, C.byref(p), arr, _vp(out), out.size))
         return out
 
+    def forward_planar_flat(self, p: abi.FwdParams, planes: np.ndarray) -> np.ndarray:
+        """planes: int32 [components, >= H*W] (row stride = plane stride): the cgo-callable twin of forward_planar."""
+        pl = np.asarray(planes, dtype=np.int32)
+        assert pl.ndim == 2 and pl.strides[1] == 4
+        out = np.empty(self.lib.j2k_fwd_coeff_count(C.byref(p)), np.int32)
+        self._ck(self.lib.j2k_forward_planar_flat(self.h, C.byref(p), _vp(pl), pl.strides[0] // 4, _vp(out), out.size))
+        return out
+
     def forward_batch(self, p: abi.FwdParams, frames: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
         """frames: [nframes, frame_bytes] uint8 (row stride = frame stride)."""
         assert frames.ndim == 2 and frames.dtype == np.uint8 and frames.strides[1] == 1
@@ -167,16 +175,26 @@ class Context:
         return out, nb
 
     def inverse_blocks(self, p: abi.InvParams, blocks: np.ndarray, cb_width=64, cb_height=64, want_planes: bool = False,
-                       roi_maxshift=None):
+                       roi_maxshift=None, block_scale_shift=None, sample_mask=None):
         """roi_maxshift: per-component MaxShift (RGN Srgn = 0) undone on the device while the blocks are scattered
-        (decodeCodeBlock, t2/tile_decoder.go:726-730); None = the blocks carry no ROI scaling."""
+        (decodeCodeBlock, t2/tile_decoder.go:726-730); None = the blocks carry no ROI scaling.
+        block_scale_shift [nframes, nblocks] (+ optional sample_mask [nframes, coeff_count] bytes, block-major): general
+        scaling (Srgn = 1, :735-742) of the blocks the region touches."""
         assert blocks.ndim == 2 and blocks.dtype == np.int32 and blocks.flags.c_contiguous
         n = blocks.shape[0]
         nbytes = self.lib.j2k_inv_pixel_bytes(C.byref(p))
         out = np.empty((n, nbytes), np.uint8)
         w, h = p.xsiz - p.xosiz, p.ysiz - p.yosiz
         planes = np.empty((n, p.components, h, w), np.int32) if want_planes else None
-        if roi_maxshift is None:
+        if block_scale_shift is not None:
+            bs = np.ascontiguousarray(block_scale_shift, dtype=np.int32)
+            mk = None if sample_mask is None else np.ascontiguousarray(sample_mask, dtype=np.uint8)
+            roi = None if roi_maxshift is None else np.ascontiguousarray(roi_maxshift, dtype=np.int32)
+            self._ck(self.lib.j2k_inverse_blocks_roi_general(self.h, C.byref(p), cb_width, cb_height, n, _vp(blocks),
+                                                             _vp(roi) if roi is not None else None, _vp(bs),
+                                                             _vp(mk) if mk is not None else None, _vp(out), nbytes,
+                                                             _vp(planes) if want_planes else None))
+        elif roi_maxshift is None:
             self._ck(self.lib.j2k_inverse_blocks(self.h, C.byref(p), cb_width, cb_height, n, _vp(blocks), _vp(out), nbytes,
                                                  _vp(planes) if want_planes else None))
         else:

@@ -162,6 +162,8 @@ const char* j2k_last_error(j2k_ctx* ctx);
 size_t j2k_last_error_copy(j2k_ctx* ctx, char* buf, size_t cap);
 int j2k_abi_version(void);
 int j2k_device_count(const j2k_ctx* ctx);
+/* CUDA devices visible to the process: `j2k_init(&ctx, NULL, j2k_visible_devices())` builds a context over all of them. */
+int j2k_visible_devices(void);
 /* Total number of CUDA kernels this context has launched (bench.py's gpu_launches). */
 int64_t j2k_launch_count(const j2k_ctx* ctx);
 int j2k_last_timing(j2k_ctx* ctx, j2k_timing* out);
@@ -202,6 +204,11 @@ int j2k_forward(j2k_ctx* ctx, const j2k_fwd_params* p, const void* pixels, size_
 /* Planar twin for Encoder.EncodeComponents([][]int32) (jpeg2000/encoder.go:221-273): skips convertPixelData. */
 int j2k_forward_planar(j2k_ctx* ctx, const j2k_fwd_params* p, const int32_t* const* planes,
                        int32_t* coeffs_out, size_t ncoeffs);
+
+/* The same with the planes in one buffer, component c at planes + c * plane_stride (samples): the cgo-callable form -
+ * a Go [][]int32 holds Go pointers and cannot cross the boundary; the shim flattens it (integration/go/j2kb200.go). */
+int j2k_forward_planar_flat(j2k_ctx* ctx, const j2k_fwd_params* p, const int32_t* planes, size_t plane_stride,
+                            int32_t* coeffs_out, size_t ncoeffs);
 
 /* Batched frames sharing one parameter set: the frame loops of the codec adapters
  * (jpeg2000/lossless/codec.go:246-261, jpeg2000/lossy/codec.go:149-176).  Frames are
@@ -294,6 +301,20 @@ int j2k_inverse_blocks_roi(j2k_ctx* ctx, const j2k_inv_params* p, int cb_width, 
                            const int32_t* blocks_in, const int32_t* roi_maxshift, void* pixels_out, size_t frame_stride_bytes,
                            int32_t* planes_out);
 
+/* The whole ROI tail of decodeCodeBlock (t2/tile_decoder.go:723-742) on the device, general scaling (RGN Srgn = 1) included:
+ * after the MaxShift rule and the classic 5/3 "/2", a block that intersects the region has its samples - all of them, or
+ * those its mask names - divided by 2^shift with Go's truncating division (applyInverseGeneralScaling /
+ * applyInverseGeneralScalingMasked, :1082-1111).  The geometry stays in Go (ROIInfo.context / blockMask, :201-252); what
+ * crosses the boundary is its result:
+ *   block_scale_shift : nframes x j2k_inv_block_count() values, block order of j2k_codeblock_layout per tile-component:
+ *                       the shift of a block with style == 1 && shiftVal > 0 && inside, else 0.  NULL = no general scaling.
+ *   sample_mask       : optional, one byte per coefficient in block-major order (the layout of blocks_in): non-zero = the
+ *                       sample lies in the region (blockMask).  NULL = whole blocks (the rectangle form).
+ * Truncating divisions by powers of two commute, so the kernel applies the scaling while scattering, before the "/2". */
+int j2k_inverse_blocks_roi_general(j2k_ctx* ctx, const j2k_inv_params* p, int cb_width, int cb_height, int nframes,
+                                   const int32_t* blocks_in, const int32_t* roi_maxshift, const int32_t* block_scale_shift,
+                                   const uint8_t* sample_mask, void* pixels_out, size_t frame_stride_bytes, int32_t* planes_out);
+
 /* Device-resident halves of the two calls above (plane <-> block-major), for pipelines that
  * keep coefficients on the device; enqueued on `cuda_stream`, not synchronised.
  * The gather copies the coefficients AS THEY ARE (no shift) and counts cblkNumbps for them: with `p` exactly as it was
@@ -308,6 +329,11 @@ int j2k_scatter_blocks_device(j2k_ctx* ctx, int dev, const j2k_inv_params* p, in
 /* `roi_maxshift` is a HOST array (one shift per component, NULL = none), as in j2k_inverse_blocks_roi. */
 int j2k_scatter_blocks_roi_device(j2k_ctx* ctx, int dev, const j2k_inv_params* p, int cb_width, int cb_height, int nframes,
                                   const int32_t* d_blocks, const int32_t* roi_maxshift, int32_t* d_coeffs, void* cuda_stream);
+/* With general scaling: `d_block_scale_shift` (nframes x blocks, values 0..30) and `d_sample_mask` (optional, block-major bytes)
+ * are DEVICE arrays, as j2k_inverse_blocks_roi_general describes them. */
+int j2k_scatter_blocks_roi_general_device(j2k_ctx* ctx, int dev, const j2k_inv_params* p, int cb_width, int cb_height, int nframes,
+                                          const int32_t* d_blocks, const int32_t* roi_maxshift, const int32_t* d_block_scale_shift,
+                                          const uint8_t* d_sample_mask, int32_t* d_coeffs, void* cuda_stream);
 
 /* -------------------------------------------- wavelet package API (in place) */
 

@@ -16,6 +16,7 @@ import "C"
 
 import (
 	"fmt"
+	"runtime"
 	"sync"
 	"unsafe"
 )
@@ -26,16 +27,47 @@ var (
 	ierr error
 )
 
-// Init creates the process-wide context over every visible device (frames and tiles are sharded over the GPUs in
-// contiguous blocks; there is no collective).  Safe to call from any goroutine, any number of times.
+// Init creates the process-wide context over EVERY visible device (frames and tiles of a batch are sharded over the
+// GPUs in contiguous blocks; there is no collective).  devices == nil -> devices 0 .. j2k_visible_devices()-1.  Safe to
+// call from any goroutine, any number of times.
 func Init() error {
 	once.Do(func() {
-		if rc := C.j2k_init(&ctx, nil, 0); rc != 0 {
+		runtime.LockOSThread() // j2k_init's message (no context yet) is per thread: fetch it on the thread that failed
+		defer runtime.UnlockOSThread()
+		n := C.j2k_visible_devices()
+		if n <= 0 {
+			ierr = fmt.Errorf("j2k_b200: no CUDA device visible; the GPU path has no CPU fallback")
+			return
+		}
+		if rc := C.j2k_init(&ctx, nil, n); rc != 0 {
 			ierr = fmt.Errorf("j2k_b200: init failed (%d): %s", int(rc), C.GoString(C.j2k_last_error(nil)))
 		}
 	})
 	return ierr
 }
+
+// InitDevices is Init over an explicit device list (one context per process; the first call wins).
+func InitDevices(devices []int) error {
+	once.Do(func() {
+		runtime.LockOSThread()
+		defer runtime.UnlockOSThread()
+		ids := make([]C.int, len(devices))
+		for i, d := range devices {
+			ids[i] = C.int(d)
+		}
+		var p *C.int
+		if len(ids) > 0 {
+			p = &ids[0]
+		}
+		if rc := C.j2k_init(&ctx, p, C.int(len(ids))); rc != 0 {
+			ierr = fmt.Errorf("j2k_b200: init failed (%d): %s", int(rc), C.GoString(C.j2k_last_error(nil)))
+		}
+	})
+	return ierr
+}
+
+// DeviceCount reports how many GPUs the context shards batches over.
+func DeviceCount() int { return int(C.j2k_device_count(ctx)) }
 
 // Shutdown releases the context (streams, device scratch, pinned staging).
 func Shutdown() {
@@ -45,8 +77,13 @@ func Shutdown() {
 	}
 }
 
+// lastErr turns a negative status into an error.  The library keeps the text of a failure per CONTEXT (not per OS
+// thread), so it is still there when the goroutine has been moved to another thread between the failing cgo call and
+// this one; j2k_last_error_copy writes into a Go-owned buffer, so no C pointer outlives the call.
 func lastErr(rc C.int) error {
-	return fmt.Errorf("j2k_b200 error %d: %s", int(rc), C.GoString(C.j2k_last_error(ctx)))
+	var buf [512]C.char
+	C.j2k_last_error_copy(ctx, &buf[0], C.size_t(len(buf)))
+	return fmt.Errorf("j2k_b200 error %d: %s", int(rc), C.GoString(&buf[0]))
 }
 
 // MCT modes (j2k_mct_mode).
@@ -150,7 +187,7 @@ type InvParams struct {
 	IsSigned                                              bool
 	NumLevels                                             int
 	Reversible, HTJ2K                                     bool      // COD transformation == 1; code-block style bit 0x40
-	Steps                                                 []float64 // decodeQuantizationSteps(...) incl. the 0.5 / 1.0 factor
+	Steps                                                 []float64 // raw decodeQuantizationSteps(...) values, WITHOUT the 0.5 factor (the library applies 0.5*step for classic, step for HTJ2K)
 	MCTMode                                               int
 	MCTMatrix                                             []float64
 	MCTOffsets                                            []int32
@@ -203,11 +240,48 @@ func (p *InvParams) CoeffCount() int { cp := p.c(); return int(C.j2k_inv_coeff_c
 func (p *InvParams) PixelBytes() int { cp := p.c(); return int(C.j2k_inv_pixel_bytes(&cp)) }
 
 // Forward: one frame, interleaved pixel bytes in, all tiles' coefficient planes out (tile-major, component-major,
-// row-major, stride = tile width) - what transformTile returns for every tile.  The C side copies out of / into the Go
-// slices before it returns: no Go pointer is retained (cgo rule).
+// row-major, stride = tile width) - what transformTile returns for every tile.  A Go slice is pageable memory: the C
+// side moves it through its pinned staging ring (host threads fill 4 MB chunks while the copy engines drain them) and
+// has copied everything out of / into the slices when it returns: no Go pointer is retained (cgo rule).
 func Forward(p *FwdParams, pixels []byte, coeffs []int32) error {
 	cp := p.c()
 	rc := C.j2k_forward(ctx, &cp, unsafe.Pointer(&pixels[0]), C.size_t(len(pixels)),
+		(*C.int32_t)(unsafe.Pointer(&coeffs[0])), C.size_t(len(coeffs)))
+	if rc != 0 {
+		return lastErr(rc)
+	}
+	return nil
+}
+
+// ForwardPlanar is the binding of Encoder.EncodeComponents([][]int32) (encoder.go:221-273): component planes in, no byte
+// conversion.  A [][]int32 holds Go pointers to Go memory and must not be passed to C, so the planes are flattened into
+// one slice (component c at c*Width*Height) - when the caller's planes already are consecutive windows of one backing
+// array (as convertPixelData's successor can allocate them) the copy is skipped.
+func ForwardPlanar(p *FwdParams, planes [][]int32, coeffs []int32) error {
+	hw := p.Width * p.Height
+	if len(planes) != p.Components {
+		return fmt.Errorf("expected %d components, got %d", p.Components, len(planes)) // encoder.go:229-231
+	}
+	for i, pl := range planes {
+		if len(pl) != hw {
+			return fmt.Errorf("component %d: expected %d pixels, got %d", i, hw, len(pl)) // encoder.go:234-238
+		}
+	}
+	flat := planes[0][:hw:hw]
+	contiguous := true
+	for c := 1; c < len(planes) && contiguous; c++ {
+		contiguous = uintptr(unsafe.Pointer(&planes[c][0])) == uintptr(unsafe.Pointer(&planes[0][0]))+uintptr(4*c*hw)
+	}
+	if contiguous && len(planes) > 1 {
+		flat = unsafe.Slice(&planes[0][0], hw*len(planes))
+	} else if len(planes) > 1 {
+		flat = make([]int32, hw*len(planes))
+		for c, pl := range planes {
+			copy(flat[c*hw:], pl)
+		}
+	}
+	cp := p.c()
+	rc := C.j2k_forward_planar_flat(ctx, &cp, (*C.int32_t)(unsafe.Pointer(&flat[0])), C.size_t(hw),
 		(*C.int32_t)(unsafe.Pointer(&coeffs[0])), C.size_t(len(coeffs)))
 	if rc != 0 {
 		return lastErr(rc)

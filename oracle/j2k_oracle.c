@@ -1400,6 +1400,15 @@ ORC_API int orc_scatter_blocks(const int32_t* blocks, int width, int height, int
     return n;
 }
 
+/* applyInverseGeneralScaling / applyInverseGeneralScalingMasked (jpeg2000/t2/tile_decoder.go:1082-1111): data /= 2^shift with
+ * Go's truncating division, for the whole block or for the samples its mask names (mask == NULL: whole block). */
+ORC_API void orc_inverse_general_scaling(int32_t* data, const uint8_t* mask, size_t n, int shift) {
+    if (shift <= 0) return;
+    const int32_t factor = (int32_t)((int64_t)1 << shift);
+    for (size_t i = 0; i < n; i++)
+        if (!mask || mask[i]) data[i] /= factor;
+}
+
 /* applyInverseMaxShift (jpeg2000/t2/tile_decoder.go:1113-1138), the Srgn = 0 branch of decodeCodeBlock (:726-730):
  * shift <= 0 leaves the block alone, shift >= 31 zeroes it, otherwise magnitudes >= 2^shift come down by shift
  * (Go's -val wraps for INT_MIN: the magnitude stays negative, fails the threshold test and the value is kept). */

@@ -228,6 +228,12 @@ class Oracle:
         self.lib.orc_scatter_blocks(_p(b), C.c_int(width), C.c_int(height), C.c_int(num_levels), C.c_int(cbw), C.c_int(cbh), _p(plane))
         return plane
 
+    def inverse_general_scaling(self, data, shift, mask=None):
+        a = np.ascontiguousarray(data, dtype=np.int32).copy()
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        self.lib.orc_inverse_general_scaling(_p(a), _p(m) if m is not None else None, C.c_size_t(a.size), C.c_int(int(shift)))
+        return a
+
     def inverse_max_shift(self, data, shift):
         a = np.array(data, dtype=np.int32, copy=True).reshape(-1)
         self.lib.orc_inverse_max_shift(_p(a), C.c_size_t(a.size), C.c_int(shift))

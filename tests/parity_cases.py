@@ -86,6 +86,8 @@ def check_pipeline(ctx, oracle, w, h, c, bits, signed, L, reversible, tile=(0, 0
         px, planes = ctx.inverse(ip, back_in, want_planes=True)
         opx, oplanes = oracle.inverse(ip, back_in, want_planes=True)
         assert np.array_equal(planes, oplanes), "inverse planes (GetImageData)"
+        if c == 3 and not reversible:  # without the planes the level-1 inverse may take the float32 inverse-ICT fast path
+            assert np.array_equal(ctx.inverse(ip, back_in), opx), "inverse pixels (no planes requested)"
     else:
         px = ctx.inverse(ip, back_in)
         opx = oracle.inverse(ip, back_in)
@@ -153,7 +155,14 @@ def check_planar(ctx, oracle, w, h, c, bits, signed, L, reversible, seed=4):
     lo, hi = (-(2 ** (bits - 1)), 2 ** (bits - 1)) if signed else (0, 2 ** bits)
     planes = [rng.integers(lo, hi, (h, w)).astype(np.int32) for _ in range(c)]
     fp, _ = fwd_inv_params(w, h, c, bits, signed, L, reversible, oracle)
-    assert np.array_equal(ctx.forward_planar(fp, planes), oracle.forward_planar(fp, planes)), "planar forward"
+    want = oracle.forward_planar(fp, planes)
+    assert np.array_equal(ctx.forward_planar(fp, planes), want), "planar forward"
+    # the cgo-callable twin: one buffer, component c at c * plane_stride (tight, and with a padded stride)
+    flat = np.stack([p.reshape(-1) for p in planes])
+    assert np.array_equal(ctx.forward_planar_flat(fp, flat), want), "flat planar forward"
+    padded = np.zeros((c, w * h + 24), np.int32)
+    padded[:, :w * h] = flat
+    assert np.array_equal(ctx.forward_planar_flat(fp, padded), want), "flat planar forward, padded stride"
 
 
 def check_package_api(ctx, oracle, n=100_003, seed=6):
@@ -423,3 +432,60 @@ def check_tall_chunks(ctx, oracle, w, h, c, bits, L, reversible, chunk, seed=41)
                 os.environ.pop(k, None)
             else:
                 os.environ[k] = v
+
+
+def check_blocks_roi_general(ctx, oracle, w, h, c, bits, L, reversible, tile=(0, 0), cb=(32, 32), seed=37, nframes=2, masked=True, maxshift=None):
+    """The whole ROI tail of decodeCodeBlock on the device (t2/tile_decoder.go:723-742): MaxShift (Srgn = 0), the classic 5/3
+    "/2", then general scaling (Srgn = 1): blocks the region touches are divided by 2^shift - every sample (rectangle form,
+    applyInverseGeneralScaling :1082-1090) or the samples of their mask (applyInverseGeneralScalingMasked :1093-1111), with
+    Go's truncating division.  Checked against the oracle's restatements applied per block in the reference's order, followed
+    by its scatter and inverse."""
+    rng = np.random.default_rng(seed)
+    fp, ip = fwd_inv_params(w, h, c, bits, False, L, reversible, oracle, tile)
+    frames = np.stack([raw_bytes(synth(rng, h, w, c, bits, False, "smooth" if f else "noise")) for f in range(nframes)])
+    blocks, _ = ctx.forward_blocks(fp, frames, cb[0], cb[1])
+    if reversible:
+        sent = ((blocks >> 6) * 2).astype(np.int32)      # T1 output of the classic lossless path: one half bit
+        ip.fuse_t1_halve = 1
+    else:
+        sent = np.stack([M.t1_emulate(blocks[f], False) for f in range(nframes)]).astype(np.int32)
+    # per tile-component block tables, in the order the library numbers the blocks
+    tiles = tile_list(oracle, fp)
+    tabs, nblk = [], 0
+    for (x0, y0, x1, y1) in tiles:
+        t = oracle.codeblock_layout(x1 - x0, y1 - y0, L, cb[0], cb[1])
+        tabs.append(t)
+        nblk += len(t) * c
+    shifts = np.zeros((nframes, nblk), np.int32)
+    mask = np.zeros(sent.shape, np.uint8) if masked else None
+    want_planes = []
+    for f in range(nframes):
+        planes, off, bi = [], 0, 0
+        for (x0, y0, x1, y1), t in zip(tiles, tabs):
+            tw, th = x1 - x0, y1 - y0
+            for comp in range(c):
+                seg = sent[f][off:off + tw * th].copy()
+                if maxshift is not None:
+                    seg = oracle.inverse_max_shift(seg, int(maxshift[comp]))
+                if reversible:
+                    seg = np.where(seg < 0, -((-seg.astype(np.int64)) // 2), seg // 2).astype(np.int32)  # Go "/ 2" (t2/tile_decoder.go:989-993)
+                for b in t:
+                    n = int(b.width) * int(b.height)
+                    o = int(b.offset)
+                    sh = int(rng.integers(0, 9)) if rng.random() < 0.6 else 0
+                    shifts[f, bi] = sh
+                    mk = None
+                    if masked:
+                        mk = (rng.random(n) < 0.5).astype(np.uint8)
+                        mask[f, off + o:off + o + n] = mk
+                    if sh > 0:
+                        seg[o:o + n] = oracle.inverse_general_scaling(seg[o:o + n], sh, mk)
+                    bi += 1
+                planes.append(oracle.scatter_blocks(seg, tw, th, L, cb[0], cb[1]).reshape(-1))
+                off += tw * th
+        want_planes.append(np.concatenate(planes))
+    px = ctx.inverse_blocks(ip, np.ascontiguousarray(sent), cb[0], cb[1], roi_maxshift=maxshift, block_scale_shift=shifts, sample_mask=mask)
+    ip2 = fwd_inv_params(w, h, c, bits, False, L, reversible, oracle, tile)[1]   # the oracle side already halved: no fused "/2"
+    for f in range(nframes):
+        want_px = oracle.inverse(ip2, want_planes[f])
+        assert np.array_equal(px[f], want_px), f"inverse from general-scaling ROI blocks, frame {f}"

@@ -166,3 +166,27 @@ def test_roi_argument_errors(ectx):
 @pytest.mark.parametrize("w,h,c,bits,L,rev,chunk", [(64, 88, 1, 12, 2, False, 16), (64, 72, 1, 16, 2, True, 12), (48, 56, 3, 8, 2, False, 16)])
 def test_tall_chunks(ectx, oracle, w, h, c, bits, L, rev, chunk):
     PC.check_tall_chunks(ectx, oracle, w, h, c, bits, L, rev, chunk)
+
+
+@pytest.mark.parametrize("w,h,c,bits,signed,L,rev", [
+    (140, 20, 1, 16, False, 2, False), (150, 22, 1, 12, False, 3, False), (134, 18, 1, 8, False, 2, False), (131, 17, 1, 8, False, 3, False),
+    (140, 20, 1, 16, True, 2, True), (150, 23, 1, 12, False, 3, True), (134, 18, 1, 8, True, 2, True), (133, 9, 1, 8, False, 2, True),
+    (270, 12, 1, 16, False, 4, False), (271, 13, 1, 16, False, 4, True), (535, 10, 1, 16, False, 3, False), (300, 11, 1, 8, False, 5, True),
+])
+def test_general_alignment_ring_variant(ectx, oracle, w, h, c, bits, signed, L, rev, capfd):
+    """Widths that are not a multiple of 8 (row pitch not a multiple of 16 bytes, band rows at odd offsets, odd LL windows):
+    the persistent kernels' general-alignment variant (FwdRing / InvRing with UA = 1) takes them, level 1 included, in both
+    directions - per-row staging phases, masked partial vectors at the right edge, the extra high-pass mirror of odd windows."""
+    import os
+    os.environ["J2K_B200_TRACE"] = "1"
+    PC.check_pipeline(ectx, oracle, w, h, c, bits, signed, L, rev, kind="noise", seed=w)
+    err = capfd.readouterr().err
+    if "[j2k]" in err:
+        assert "fwd ring" in err and "inv ring" in err
+
+
+@pytest.mark.parametrize("w,h,c,bits,L,rev,tile,cb,masked", [(64, 48, 1, 12, 2, True, (0, 0), (16, 16), True), (70, 50, 1, 8, 3, False, (0, 0), (16, 8), False), (48, 40, 3, 8, 2, True, (32, 32), (8, 8), True)])
+def test_code_block_interface_roi_general_scaling(ectx, oracle, w, h, c, bits, L, rev, tile, cb, masked):
+    """SURVEY 8f rank 3, second half: inverse general scaling (RGN Srgn = 1) fused into the block scatter, whole-block and masked."""
+    PC.check_blocks_roi_general(ectx, oracle, w, h, c, bits, L, rev, tile=tile, cb=cb, masked=masked)
+    PC.check_blocks_roi_general(ectx, oracle, w, h, c, bits, L, rev, tile=tile, cb=cb, masked=masked, maxshift=[3] * c, seed=5)

@@ -341,3 +341,42 @@ def test_tall_chunks(ctx, oracle, w, h, c, bits, L, rev, chunk):
     """Chunk heights of 64 row pairs (what the big batches of bench.py and the BASELINE configs run with) and above,
     forced on single frames and compared with the oracle: chunk seams, warm-up rows, partial last chunks."""
     PC.check_tall_chunks(ctx, oracle, w, h, c, bits, L, rev, chunk)
+
+
+@pytest.mark.parametrize("w,h,c,bits,signed,L,rev", [
+    (2140, 1760, 1, 16, False, 6, False), (2140, 1760, 1, 12, False, 5, True), (2022, 2022, 1, 12, False, 6, False), (2022, 2022, 1, 16, True, 5, True),
+    (2023, 1001, 1, 8, False, 5, False), (2023, 1001, 1, 8, False, 5, True), (1766, 2140, 1, 10, False, 6, False), (4097, 333, 1, 16, False, 4, True),
+    (1000, 600, 1, 16, False, 5, False), (250, 250, 1, 8, True, 3, True),
+])
+def test_general_alignment_ring_variant(ctx, oracle, w, h, c, bits, signed, L, rev):
+    """CR / DX detector sizes (2140 x 1760, 2022 x 2022) and other widths that are not a multiple of 8: the general-alignment
+    variant of the persistent kernels (TMA copies from the 16-byte boundary below each row, per-row phases, masked stores)."""
+    PC.check_pipeline(ctx, oracle, w, h, c, bits, signed, L, rev, kind="noise", seed=w + h)
+    PC.check_pipeline(ctx, oracle, w, h, c, bits, signed, L, rev, kind="smooth", seed=w)
+
+
+def test_general_alignment_batch_and_device_buffers(ctx, oracle):
+    """A batch of odd-sized frames (every frame starts at its own alignment) through the host path and the device path."""
+    import torch
+    rng = np.random.default_rng(91)
+    w, h, n = 2022, 333, 5   # frame bytes = 2022 * 333 * 2: not a multiple of 16, so frames 1.. start unaligned
+    fp, ip = PC.fwd_inv_params(w, h, 1, 12, False, 5, True, oracle)
+    frames = np.stack([PC.raw_bytes(PC.synth(rng, h, w, 1, 12, False, "noise")) for _ in range(n)])
+    co = ctx.forward_batch(fp, frames)
+    for f in range(n):
+        assert np.array_equal(co[f], oracle.forward(fp, frames[f])), f
+    assert np.array_equal(ctx.inverse_batch(ip, co), frames)
+    d_in = torch.from_numpy(frames).cuda()
+    d_co = torch.empty((n, w * h), dtype=torch.int32, device="cuda")
+    d_px = torch.empty_like(d_in)
+    ctx.forward_device(fp, n, d_in.data_ptr(), frames.shape[1], d_co.data_ptr())
+    ctx.inverse_device(ip, n, d_co.data_ptr(), d_px.data_ptr(), frames.shape[1])
+    torch.cuda.synchronize()
+    assert np.array_equal(d_co.cpu().numpy(), co) and np.array_equal(d_px.cpu().numpy(), frames)
+
+
+@pytest.mark.parametrize("w,h,c,bits,L,rev,tile,cb,masked", [(512, 384, 1, 12, 4, True, (0, 0), (32, 32), True), (640, 480, 1, 16, 5, False, (0, 0), (64, 64), False), (300, 200, 3, 8, 3, True, (128, 128), (16, 16), True), (333, 211, 3, 8, 3, False, (0, 0), (32, 32), True)])
+def test_code_block_interface_roi_general_scaling(ctx, oracle, w, h, c, bits, L, rev, tile, cb, masked):
+    """SURVEY 8f rank 3, second half: inverse general scaling (RGN Srgn = 1) fused into the block scatter, whole-block and masked."""
+    PC.check_blocks_roi_general(ctx, oracle, w, h, c, bits, L, rev, tile=tile, cb=cb, masked=masked)
+    PC.check_blocks_roi_general(ctx, oracle, w, h, c, bits, L, rev, tile=tile, cb=cb, masked=masked, maxshift=[3] * c, seed=5)
