@@ -445,19 +445,25 @@ def main():
     ctx.set_profiling(False)
     # the same launch back to back on ONE stream (no overlap between launches, no idle gap between them): the kernel's
     # average launch duration over a timed region, CUDA events on the launching stream
-    serial_ms = None
+    serial_ms, serial_windows = None, []
     if 100 in per_level:
-        barrier()
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # three windows with a pause in between (the board's power state right after the 100-step burst moves a single window by
+        # +-2.5 % from run to run); the median window is reported, all three are kept in the line
         nser = max(10, min(args.steps, 50))
+        serial_windows = []
         for _ in range(3):
-            ctx.forward_device(fp, B, d_in.data_ptr(), frame_bytes, d_outs[0].data_ptr(), stream=streams[0].cuda_stream)
-        k0.record(streams[0])
-        for _ in range(nser):
-            ctx.forward_device(fp, B, d_in.data_ptr(), frame_bytes, d_outs[0].data_ptr(), stream=streams[0].cuda_stream)
-        k1.record(streams[0])
-        barrier()
-        serial_ms = k0.elapsed_time(k1) / nser
+            barrier()
+            time.sleep(0.05)
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for _ in range(3):
+                ctx.forward_device(fp, B, d_in.data_ptr(), frame_bytes, d_outs[0].data_ptr(), stream=streams[0].cuda_stream)
+            k0.record(streams[0])
+            for _ in range(nser):
+                ctx.forward_device(fp, B, d_in.data_ptr(), frame_bytes, d_outs[0].data_ptr(), stream=streams[0].cuda_stream)
+            k1.record(streams[0])
+            barrier()
+            serial_windows.append(k0.elapsed_time(k1) / nser)
+        serial_ms = statistics.median(serial_windows)
     peak, peak_src = measured_peak()
     step_alg = B * alg_bytes_per_frame()
     fused = 100 in per_level  # the persistent ring kernel: ONE launch runs all levels of all frames
@@ -487,7 +493,9 @@ def main():
         "step_algorithmic_GBps": step_alg / (ms_step * 1e-3) / 1e9, "step_frac": step_alg / (ms_step * 1e-3) / 1e9 / peak,
         "per_level_ms": {str(k): statistics.median(v) for k, v in sorted(per_level.items())},
         "kernel_ms_single_launches": [round(x, 4) for x in per_level.get(100, lvl1)],
-        "kernel_ms_how": "average of back-to-back launches on one stream, CUDA events on that stream (single_launches: one launch at a time with a host sync in between)",
+        "kernel_ms_windows": [round(x, 4) for x in serial_windows],
+        "kernel_ms_how": "average of back-to-back launches on one stream, CUDA events on that stream: median of three windows of %d launches "
+                         "(kernel_ms_windows); single_launches: one launch at a time with a host sync in between" % (max(10, min(args.steps, 50))),
     }
 
     # ---- inverse direction, device-resident (supplementary: the headline metric is the forward step above)
@@ -664,17 +672,22 @@ def main():
             with torch.cuda.stream(s_dn):
                 t_out.copy_(d_scr_out, non_blocking=True)
         pcie_step(); torch.cuda.synchronize()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(3):
-            pcie_step()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        t = torch.tensor([dt], device="cuda")
-        if use_dist:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        pcie_ceiling = world * B * PIX / (float(t.item()) / 3) / 1e6
-        pcie_gbs = (B * frame_bytes + B * PIX * 4) / (dt / 3) / 1e9
+        best = None
+        for _ in range(3):   # best of three windows of three steps: this is a ceiling, not a mean
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                pcie_step()
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / 3
+            t = torch.tensor([dt], device="cuda")
+            if use_dist:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt_all = float(t.item())
+            if best is None or dt_all < best[0]:
+                best = (dt_all, dt)
+        pcie_ceiling = world * B * PIX / best[0] / 1e6
+        pcie_gbs = (B * frame_bytes + B * PIX * 4) / best[1] / 1e9
 
     # ---- the other BASELINE configs, resident, both directions (every rank runs them; rank 0's numbers are reported)
     configs = None

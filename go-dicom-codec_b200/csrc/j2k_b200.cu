@@ -191,6 +191,7 @@ struct RingPlan {
     RingArgs args;
     int WT = 0, NP1 = 0, NC1 = 0, IN1 = 0, MCT1 = 0, SG1 = 0;
     int UA = 0;  // general-alignment kernel variant (rows / bands that are not 16-byte aligned, partial vectors at the right edge)
+    int X3 = 0;  // inverse, ICT + 9/7 8-bit RGB: the three-producer level-1 kernel (inv3w_kernel), jobs claimed three at a time
     int x_buf[J2K_RING_MAXSEG], ll_buf[J2K_RING_MAXSEG], band_buf[J2K_RING_MAXSEG], planes_buf[J2K_RING_MAXSEG];
     int level[J2K_RING_MAXSEG];
     int cut = 0;  // levels 1..cut run in the persistent launch, deeper ones (geometry it does not take) on the per-level kernels
@@ -560,7 +561,7 @@ int env_int(const char* name, int dflt) {
 }
 
 // Job decomposition of one ring segment: even column strips, row chunks sized for ~2 jobs per resident warp.
-void ring_chunks(RingSeg& g, int NP, int n_cols_total_hint, int level, int halo_lanes = 2) {
+void ring_chunks(RingSeg& g, int NP, int n_cols_total_hint, int level, int halo_lanes = 2, int target_div = 1) {
     int VP = (32 - halo_lanes) * NP;  // 32 lanes minus one halo lane per side (9/7 needs 2 pairs, 5/3 one: both fit NP >= 2); halo-free: 32
     // strips are a multiple of 8 pairs wide: every band-row piece a warp stores (and every pixel-row piece of the inverse)
     // then covers whole 32-byte sectors, no partial-sector writes at the strip seams (+3 % on C2)
@@ -579,7 +580,9 @@ void ring_chunks(RingSeg& g, int NP, int n_cols_total_hint, int level, int halo_
     // chunks as tall as the job target allows, up to 128 row pairs: the 2 (5/3) or 4 (9/7) warm-up pairs a chunk recomputes are
     // then 1.5-3 % of its rows (6 % at 64); the difference only shows once the board is power-capped
     const int max_chunk = level <= 1 ? env_int("J2K_RING_CHUNK", 128) : env_int("J2K_RING_CHUNK_DEEP", env_int("J2K_RING_CHUNK", 128));
-    const long long target = env_int("J2K_RING_TARGET_JOBS", 148 * 16 * 2);
+    // (target_div: a job of the three-producer inverse occupies a whole CTA, and every job boundary drains its exchange
+    // pipeline: four times fewer, taller jobs: +11 % on C3, +2.5 % on C5)
+    const long long target = env_int("J2K_RING_TARGET_JOBS", 148 * 16 * 2) / target_div;
     long long cols = (long long)n_cols_total_hint * g.nstrips;
     long long want = (target + cols - 1) / cols;
     if (want < 1) want = 1;
@@ -614,7 +617,7 @@ int ring_schedule(RingPlan& R, Plan& P, int n_ctl) {
     RingArgs& A = R.args;
     std::vector<int> begin, info;
     const int lag = env_int("J2K_RING_LAG", J2K_RING_DEFAULT_LAG);
-    bool chain = A.nseg >= 2 && lag > 0;
+    bool chain = A.nseg >= 2 && lag > 0 && !R.X3;  // (the three-producer inverse numbers its jobs in triples: level-major order only)
     int base = 0x7fffffff;
     for (int k = 0; k < A.nseg; k++) base = A.seg[k].n_items < base ? A.seg[k].n_items : base;
     for (int k = 0; k < A.nseg && chain; k++)
@@ -923,24 +926,27 @@ int build_ring_inv_impl(const Spec& s, Plan& P, const std::vector<long long>& ta
             if (P.levels[i].level == k) order.push_back((int)i);
     if (order.empty() || order.size() > J2K_RING_MAXSEG) return 0;
     bool have_first = false;
-    bool ua = false;
+    bool ua = false, x3_any = false;
     int n_ctl = 2, jobs = 0;
+    R.X3 = 0;
     for (size_t si = 0; si < order.size(); si++) {
         const LevelLaunch& l = P.levels[order[si]];
         const LevelArgs& a = l.a;
         RingSeg& g = R.args.seg[si];
         const bool first = l.level == 1;
         const bool raw_out = l.KIND == IN_U8 || l.KIND == IN_U16;
-        const int NP = l.NC == 3 ? (WT == 97 ? J2K_INV_RGB_NP : 2) : 4;
+        // ICT + 9/7 on 8-bit RGB: level 1 as three single-component producers + one pixel consumer per CTA (inv3w_kernel)
+        const bool x3 = first && WT == 97 && l.NC == 3 && l.KIND == IN_U8 && l.MCT == MCTK_ICT && env_int("J2K_INV3W", J2K_INV3W_DEFAULT) != 0;
+        const int NP = l.NC == 3 ? (x3 ? 4 : (WT == 97 ? J2K_INV_RGB_NP : 2)) : 4;
         const int ES = l.KIND == IN_U8 ? 1 : (l.KIND == IN_U16 ? 2 : 4);
         const int PB = ES * (raw_out ? l.NC : 1);
         if (a.px != 0 || a.hskip || a.vskip) return 0;
         bool seg_ua = false;          // this level needs the general-alignment variant
         if (a.w % 8) seg_ua = true;   // aligned variant: band rows are staged in 16-byte units (low and high band widths multiples of 4)
         if (first) {
-            if (!ring_inv_variant_supported(WT, NP, l.NC, l.KIND, l.MCT)) return 0;
+            if (!x3 && !ring_inv_variant_supported(WT, NP, l.NC, l.KIND, l.MCT)) return 0;
             if (l.NC == 1 && raw_out && s.C != 1) return 0;  // strided components
-            if (!have_first) { R.WT = WT; R.NP1 = NP; R.NC1 = l.NC; R.IN1 = l.KIND; R.MCT1 = l.MCT; R.SG1 = 0; have_first = true; }
+            if (!have_first) { R.WT = WT; R.NP1 = NP; R.NC1 = l.NC; R.IN1 = l.KIND; R.MCT1 = l.MCT; R.SG1 = 0; R.X3 = x3 ? 1 : 0; have_first = true; }
             else if (R.NP1 != NP || R.NC1 != l.NC || R.IN1 != l.KIND || R.MCT1 != l.MCT) return 0;
         } else {
             if (l.NC != 1 || l.KIND != (WT == 53 ? IN_I32 : IN_F32)) return 0;
@@ -1000,7 +1006,7 @@ int build_ring_inv_impl(const Spec& s, Plan& P, const std::vector<long long>& ta
             }
             g.st_cls[0] = (int)(pal & -pal);  // GetImageData plane rows (UA)
         }
-        ring_chunks(g, NP, g.n_items, l.level, (J2K_INV_HALO_FREE && WT == 53) ? 0 : 2);
+        ring_chunks(g, NP, g.n_items, l.level, (J2K_INV_HALO_FREE && WT == 53) ? 0 : 2, x3 ? 4 : 1);
         g.dep_seg = -1; g.dep_div = 1; g.dep_target = 0; g.dep_mul = 1;
         {
             // producer: same class, next coarser level (absent for the coarsest level of the class)
@@ -1015,9 +1021,11 @@ int build_ring_inv_impl(const Spec& s, Plan& P, const std::vector<long long>& ta
         }
         g.job_begin = jobs;
         long long nj = (long long)g.n_items * g.nchunks * g.nstrips;
+        if (x3) nj *= 3;  // a pixel job holds three job numbers, one per component (producer warp)
         if (nj + jobs > 0x3fffffffLL) return 0;
         jobs += (int)nj;
         g.job_end = jobs;
+        x3_any = x3_any || x3;
         g.done_base = n_ctl;
         n_ctl += g.n_items;
         R.x_buf[si] = l.x_buf; R.ll_buf[si] = l.ll_buf; R.band_buf[si] = l.band_buf; R.level[si] = l.level;
@@ -1026,6 +1034,20 @@ int build_ring_inv_impl(const Spec& s, Plan& P, const std::vector<long long>& ta
     if (!have_first) return 0;
     if (ua && (R.NC1 != 1 || R.NP1 != 4 || (R.IN1 != IN_U8 && R.IN1 != IN_U16))) return 0;  // a coarse level needs the general variant but level 1 has none
     R.UA = ua ? 1 : 0;
+    if (R.X3) {
+        // jobs are claimed three at a time per CTA: every segment's range starts at a multiple of three (the padding numbers
+        // decode to items past the end and are skipped); no pipelined slices for this variant
+        if (order.size() > 1 && R.args.seg[0].first) return 0;
+        int shift = 0;
+        for (int k = 0; k < (int)order.size(); k++) {
+            RingSeg& g = R.args.seg[k];
+            g.job_begin += shift; g.job_end += shift;
+            const int pad = (3 - g.job_end % 3) % 3;
+            g.job_end += pad;   // padding numbers belong to the segment; they decode to an item past its end
+            shift += pad;
+        }
+        jobs += shift;
+    }
     R.args.nseg = (int)order.size();
     for (int k = 0; k < R.args.nseg; k++) R.args.seg[k].has_waiters = 0;
     for (int k = 0; k < R.args.nseg; k++)
@@ -1054,6 +1076,21 @@ int build_ring_inv_impl(const Spec& s, Plan& P, const std::vector<long long>& ta
     }
 
 int ring_dispatch_inv(const RingPlan& R, const RingArgs& A, unsigned grid, cudaStream_t st, bool query) {
+    if (R.X3) {
+        if (query) {
+#ifdef J2K_EMU
+            return 1;
+#else
+            int n = 0;
+            const void* fn = (const void*)inv3w_kernel<IN_U8>;
+            if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, J2K_X3_CTA_SMEM) != cudaSuccess) return -1;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, 128, J2K_X3_CTA_SMEM) != cudaSuccess) return -1;
+            return n;
+#endif
+        }
+        J2K_LAUNCH_SMEM((inv3w_kernel<IN_U8>), grid, 128, J2K_X3_CTA_SMEM, st, A);
+        return 0;
+    }
     RING_INV_CASE(97, 4, 1, IN_U8, MCTK_NONE) RING_INV_CASE(97, 4, 1, IN_U16, MCTK_NONE)
     RING_INV_CASE(97, J2K_INV_RGB_NP, 3, IN_U8, MCTK_ICT) RING_INV_CASE(97, J2K_INV_RGB_NP, 3, IN_U16, MCTK_ICT)
     RING_INV_CASE(97, 4, 1, IN_F32, MCTK_NONE)
@@ -1509,7 +1546,7 @@ int run_plan(j2k_ctx* ctx, Plan& P, void* pixels, void* coeffs, void* planes, bo
                     R.IN1, R.MCT1, R.SG1, A.nseg, A.total_jobs, A.nslice, R.grid);
         if (!per_level) {
             unsigned grid = R.grid;
-            unsigned need = (unsigned)((A.total_jobs + J2K_RING_WARPS - 1) / J2K_RING_WARPS);
+            unsigned need = R.X3 ? (unsigned)((A.total_jobs + 2) / 3) : (unsigned)((A.total_jobs + J2K_RING_WARPS - 1) / J2K_RING_WARPS);
             if (need < grid) grid = need;
             if (grid < 1) grid = 1;
             prof.begin(100);

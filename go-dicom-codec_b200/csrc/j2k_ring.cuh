@@ -147,6 +147,8 @@ __device__ __forceinline__ unsigned lds32(smem_t a) { unsigned v; memcpy(&v, a, 
 __device__ __forceinline__ unsigned lds16(smem_t a) { unsigned short v; memcpy(&v, a, 2); return v; }
 __device__ __forceinline__ unsigned lds8(smem_t a) { return *a; }
 __device__ __forceinline__ void sts32(smem_t a, unsigned v) { memcpy(a, &v, 4); }
+__device__ __forceinline__ void sts128f(smem_t a, float2 u, float2 v) { float t[4] = {u.x, u.y, v.x, v.y}; memcpy(a, t, 16); }
+__device__ __forceinline__ void mbar_arrive(smem_t) {}
 #else
 #define J2K_SMEM_DECL(name) extern __shared__ __align__(128) unsigned char name[]
 typedef unsigned smem_t;  // 32-bit shared-window address
@@ -242,6 +244,10 @@ __device__ __forceinline__ unsigned lds8(smem_t a) {
     return v;
 }
 __device__ __forceinline__ void sts32(smem_t a, unsigned v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts128f(smem_t a, float2 u, float2 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(u.x), "f"(u.y), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(smem_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 #endif
 
 struct RingWarp {
@@ -297,13 +303,17 @@ __device__ __forceinline__ float2 shfl_up2(float2 v) {
 // +DC, clamp, two's-complement wrap and packing of GetPixelData (decoder.go:777-944) on two samples per instruction:
 // saturate both to int16 (the clamp range lies inside it), clamp to [lo - dc, hi - dc], add dc modulo 2^16, keep the
 // low B bits (the un-sign-extended word of a negative signed sample).  SASS: I2IP.S16.S32.SAT, VIMNMX.S16x2, VIADD.16x2.
-struct RawPack { unsigned lo2, hi2, dc2, mask2; };
+struct RawPack { unsigned lo2, hi2, dc2, mask2, lo2d, hi2d; float magic_dc; };
 __device__ __forceinline__ RawPack make_raw_pack(const RawFmt& r) {
     RawPack p;
     p.lo2 = ((unsigned)(r.clamp_lo - r.dc) & 0xFFFFu) * 0x10001u;
     p.hi2 = ((unsigned)(r.clamp_hi - r.dc) & 0xFFFFu) * 0x10001u;
     p.dc2 = ((unsigned)r.dc & 0xFFFFu) * 0x10001u;
     p.mask2 = ((unsigned)(r.clamp_hi - r.clamp_lo) & 0xFFFFu) * 0x10001u;  // 2^B - 1 in both halves
+    // the same clamp on values that carry the DC shift already (pack_clamp2_magic_dc: the shift rides in the rounding constant)
+    p.lo2d = ((unsigned)r.clamp_lo & 0xFFFFu) * 0x10001u;
+    p.hi2d = ((unsigned)r.clamp_hi & 0xFFFFu) * 0x10001u;
+    p.magic_dc = 12582912.0f + (float)r.dc;   // 1.5 * 2^23 + dc, exact
     return p;
 }
 #ifdef J2K_EMU
@@ -337,6 +347,25 @@ __device__ __forceinline__ unsigned pack_clamp2_magic(unsigned ua, unsigned ub, 
     w = __vmaxs2(w, p.lo2);
     w = __vmins2(w, p.hi2);
     w = __vadd2(w, p.dc2);
+    return w & p.mask2;
+#endif
+}
+
+// ... and with the DC shift folded into the bias (patterns of n + dc + 1.5 * 2^23): clamp to [clamp_lo, clamp_hi] directly,
+// no packed add; the mask only matters for signed samples (wrap of the negative words), where dc is 0.
+__device__ __forceinline__ unsigned pack_clamp2_magic_dc(unsigned ua, unsigned ub, const RawPack& p) {
+#ifdef J2K_EMU
+    auto one = [&](unsigned u, int sh) {
+        int v = (int)(short)(u & 0xFFFFu);
+        const int lo = (short)(p.lo2d >> sh), hi = (short)(p.hi2d >> sh);
+        v = v < lo ? lo : (v > hi ? hi : v);
+        return ((unsigned)v & (p.mask2 >> sh)) & 0xFFFFu;
+    };
+    return one(ua, 0) | (one(ub, 16) << 16);
+#else
+    unsigned w = __byte_perm(ua, ub, 0x5410);
+    w = __vmaxs2(w, p.lo2d);
+    w = __vmins2(w, p.hi2d);
     return w & p.mask2;
 #endif
 }
@@ -402,25 +431,29 @@ struct FwdRing {
         }
     }
 
-    // the same from an address that is only `la` bytes aligned (UA; warp-uniform la)
-    static __device__ __forceinline__ void fetch_ua(smem_t p, unsigned (&w)[NW], int la) {
-        if (la >= LDALIGN) { fetch(p, w); return; }
-        if (LB % 8 == 0 && la >= 8) {
+    // the same from a lane address at ANY byte phase (UA): lane_off + phase = an aligned part (multiple of the lane vector
+    // LDALIGN) plus a warp-uniform byte offset p < LDALIGN.  The lane loads its aligned vectors plus one more with the
+    // conflict-free 128- / 64-bit loads of the aligned kernels and extracts its words with funnel shifts (narrow loads at a
+    // 16-byte lane stride would be 4-way bank-conflicted: measured 2.6 x the short-scoreboard stalls).
+    static __device__ __forceinline__ void fetch_ua(smem_t row, int off, unsigned (&w)[NW]) {
+        constexpr int AW = LDALIGN / 4;          // words per aligned vector
+        constexpr int NV = LB / LDALIGN + 1;     // aligned vectors that cover the lane's span at any phase
+        const int p = off & (LDALIGN - 1);
+        const smem_t a = row + (off - p);
+        unsigned W[NV * AW];
 #pragma unroll
-            for (int k = 0; k < NW / 2; k++) {
-                uint2 q = lds64(p + 8 * k);
-                w[2 * k] = q.x; w[(2 * k + 1) % NW] = q.y;
-            }
-        } else if (la >= 4) {
-#pragma unroll
-            for (int k = 0; k < NW; k++) w[k] = lds32(p + 4 * k);
-        } else if (la >= 2) {
-#pragma unroll
-            for (int k = 0; k < NW; k++) w[k] = lds16(p + 4 * k) | (lds16(p + 4 * k + 2) << 16);
-        } else {
-#pragma unroll
-            for (int k = 0; k < NW; k++) w[k] = lds8(p + 4 * k) | (lds8(p + 4 * k + 1) << 8) | (lds8(p + 4 * k + 2) << 16) | (lds8(p + 4 * k + 3) << 24);
+        for (int v = 0; v < NV; v++) {
+            if constexpr (LDALIGN == 16) { const uint4 q = lds128(a + 16 * v); W[4 * v] = q.x; W[4 * v + 1] = q.y; W[4 * v + 2] = q.z; W[4 * v + 3] = q.w; }
+            else if constexpr (LDALIGN == 8) { const uint2 q = lds64(a + 8 * v); W[2 * v] = q.x; W[2 * v + 1] = q.y; }
+            else W[v] = lds32(a + 4 * v);
         }
+        const int q = p >> 2, sh = 8 * (p & 3);  // warp-uniform: word offset, bit shift
+#pragma unroll
+        for (int qq = 0; qq < AW; qq++)
+            if (q == qq) {
+#pragma unroll
+                for (int k = 0; k < NW; k++) w[k] = __funnelshift_r(W[qq + k], W[qq + k + 1], sh);
+            }
     }
 
     // raw words of one lane -> integers (no sign fix, no DC shift yet)
@@ -494,9 +527,10 @@ struct FwdRing {
     // one staged row of this lane as working values in scalar form (5/3, signed raw words, border lanes)
     // (every lane reads its span, also the lanes past the strip's right halo: the slot is theirs, the junk they compute is
     // never stored and never reaches a storing lane -- no branch in front of the loads, so they hoist freely)
-    static __device__ __forceinline__ void load_scalar(smem_t row, int lane_off, const RawFmt& raw, int dc, T (&out)[NC][NS], int la = 16) {
+    template <int LA = 16>
+    static __device__ __forceinline__ void load_scalar(smem_t row, int lane_off, const RawFmt& raw, int dc, T (&out)[NC][NS]) {
         unsigned wv[NW];
-        if constexpr (UA) fetch_ua(row + lane_off + (int)lds32(row + ROWB - 4), wv, la); else
+        if constexpr (UA) fetch_ua(row, lane_off + (int)lds32(row + ROWB - 4), wv); else
         fetch(row + lane_off, wv);
         int v[NC][NS];
         words_to_ints(wv, v);
@@ -504,11 +538,12 @@ struct FwdRing {
     }
 
     // the same row as column pairs of float32 (9/7): pair j = samples 2j, 2j+1
+    template <int LA = 16>
     static __device__ __forceinline__ void load_pairs(smem_t row, int lane_off, const RawFmt& raw, int dc, float fmagic,
-                                                      float one, float2 (&out)[NC][NP], float k0 = 0.f, float k1 = 0.f, float k2 = 0.f, int la = 16) {
+                                                      float one, float2 (&out)[NC][NP], float k0 = 0.f, float k1 = 0.f, float k2 = 0.f) {
         {
             unsigned wv[NW];
-            if constexpr (UA) fetch_ua(row + lane_off + (int)lds32(row + ROWB - 4), wv, la); else
+            if constexpr (UA) fetch_ua(row, lane_off + (int)lds32(row + ROWB - 4), wv); else
             fetch(row + lane_off, wv);
             if constexpr (XC == 3) {
                 // one row of the float32 ICT (encoder.go:277-288): (r * k0 + g * k1) + b * k2 on exact float32(int) inputs
@@ -584,23 +619,34 @@ struct FwdRing {
         else *p = o[0];
     }
 
-    // UA: nv of the lane's NP values lie inside the band (<= 0: none), the row allows `cls`-int vectors
-    static __device__ __forceinline__ void store_ua(int* p, const int (&o)[NP], int nv, int cls) {
-        if (nv >= NP && cls >= 4) { *(int4*)p = make_int4(o[0], o[1], o[2 % NP], o[3 % NP]); return; }
-        if (cls >= 2) {
+    // UA: nv of the lane's NP values lie inside the band (<= 0: none); SC = ints per store every band row of the job allows
+    template <int SC>
+    static __device__ __forceinline__ void store_ua(int* p, const int (&o)[NP], int nv) {
+        if constexpr (SC >= 2) {
 #pragma unroll
             for (int j = 0; j + 1 < NP; j += 2) {
                 if (j + 1 < nv) *(int2*)(p + j) = make_int2(o[j], o[j + 1]);
                 else if (j < nv) p[j] = o[j];
             }
-            return;
-        }
+        } else {
 #pragma unroll
-        for (int j = 0; j < NP; j++)
-            if (j < nv) p[j] = o[j];
+            for (int j = 0; j < NP; j++)
+                if (j < nv) p[j] = o[j];
+        }
     }
 
+    // The job loop is instantiated per (load alignment, store class) of the general-alignment variant and chosen once per job.
     static __device__ __forceinline__ void run(const RingSeg& S, const RawFmt& raw, int item, int chunk, int strip, RingWarp& rw,
+                                               int lane) {
+        if constexpr (!UA) run_t<16, 4>(S, raw, item, chunk, strip, rw, lane);
+        else {
+            const int sc = min(min(S.st_cls[0], S.st_cls[1]), min(S.st_cls[2], S.st_cls[3]));
+            if (sc >= 2) run_t<4, 2>(S, raw, item, chunk, strip, rw, lane); else run_t<4, 1>(S, raw, item, chunk, strip, rw, lane);
+        }
+    }
+
+    template <int LA, int SC>
+    static __device__ __forceinline__ void run_t(const RingSeg& S, const RawFmt& raw, int item, int chunk, int strip, RingWarp& rw,
                                                int lane) {
         const int w = S.w, h = S.h, py = S.py;
         const int hw = w - S.lw, hh = h - S.lh, lh = S.lh;
@@ -623,9 +669,7 @@ struct FwdRing {
         // the window width is a multiple of 2 NP on the aligned path: a lane stores whole vectors or nothing; UA masks per band
         const bool st = lane >= HLN && kx0 < kxe && (UA || kx0 + NP <= hw);
         const int nv_l = S.lw - kx0, nv_h = hw - kx0;   // UA: values of this lane inside the low- / high-pass bands
-        const int la = UA ? S.load_align : 16;
-        const int cls_ll = S.st_cls[0], cls_hl = S.st_cls[1], cls_lh = S.st_cls[2], cls_hh = S.st_cls[3];
-        (void)nv_l; (void)nv_h; (void)la; (void)cls_ll; (void)cls_hl; (void)cls_lh; (void)cls_hh;
+        (void)nv_l; (void)nv_h;
 
         const unsigned long long pol_load = S.pol_load, pol_ll = S.pol_ll, pol_band = S.pol_band;
         (void)pol_load; (void)pol_ll; (void)pol_band;
@@ -740,8 +784,8 @@ struct FwdRing {
                 const smem_t row_e = stage + half * 2 * ROWB;
                 const smem_t row_o = row_e + ROWB;
 
-                load_pairs(row_e, lane_off, raw, dc, fmagic, one, out.pe, k0, k1, k2, la);
-                load_pairs(row_o, lane_off, raw, dc, fmagic, one, out.po, k0, k1, k2, la);
+                load_pairs<LA>(row_e, lane_off, raw, dc, fmagic, one, out.pe, k0, k1, k2);
+                load_pairs<LA>(row_o, lane_off, raw, dc, fmagic, one, out.po, k0, k1, k2);
                 // vertical lifting on column pairs; the finished (low, high) row values of column s land in Q[c][s]
                 float2 Q[NC][NS];
 #pragma unroll
@@ -823,8 +867,8 @@ struct FwdRing {
                         }
                     }
                     if constexpr (UA) {
-                        if (row_l) { store_ua(p_ll, q_ll, nv_l, cls_ll); store_ua(p_hl, q_hl, nv_h, cls_hl); }
-                        if (row_h) { store_ua(p_lh, q_lh, nv_l, cls_lh); store_ua(p_hh, q_hh, nv_h, cls_hh); }
+                        if (row_l) { store_ua<SC>(p_ll, q_ll, nv_l); store_ua<SC>(p_hl, q_hl, nv_h); }
+                        if (row_h) { store_ua<SC>(p_lh, q_lh, nv_l); store_ua<SC>(p_hh, q_hh, nv_h); }
                     } else {
                     if (row_l) {
                         store_vec(p_ll + c * cs_ll, q_ll, pol_ll);
@@ -869,8 +913,8 @@ struct FwdRing {
                 const smem_t row_o = row_e + ROWB;
 
                 int lo[NC][NS], hi[NC][NS];
-                load_scalar(row_e, lane_off, raw, dc, out.pe, la);
-                load_scalar(row_o, lane_off, raw, dc, out.po, la);
+                load_scalar<LA>(row_e, lane_off, raw, dc, out.pe);
+                load_scalar<LA>(row_o, lane_off, raw, dc, out.po);
 #pragma unroll
                 for (int c = 0; c < NC; c++)
 #pragma unroll
@@ -892,7 +936,7 @@ struct FwdRing {
                     if (row_l) {
 #pragma unroll
                         for (int j = 0; j < NP; j++) { q_a[j] = (int)((unsigned)lo[c][2 * j] << sh_ll); q_b[j] = (int)((unsigned)lo[c][2 * j + 1] << sh_hl); }
-                        if constexpr (UA) { store_ua(p_ll, q_a, nv_l, cls_ll); store_ua(p_hl, q_b, nv_h, cls_hl); } else {
+                        if constexpr (UA) { store_ua<SC>(p_ll, q_a, nv_l); store_ua<SC>(p_hl, q_b, nv_h); } else {
                         store_vec(p_ll + c * cs_ll, q_a, pol_ll);
                         store_vec(p_hl + c * cs_b, q_b, pol_band);
                         }
@@ -900,7 +944,7 @@ struct FwdRing {
                     if (row_h) {
 #pragma unroll
                         for (int j = 0; j < NP; j++) { q_a[j] = (int)((unsigned)hi[c][2 * j] << sh_lh); q_b[j] = (int)((unsigned)hi[c][2 * j + 1] << sh_hh); }
-                        if constexpr (UA) { store_ua(p_lh, q_a, nv_l, cls_lh); store_ua(p_hh, q_b, nv_h, cls_hh); } else {
+                        if constexpr (UA) { store_ua<SC>(p_lh, q_a, nv_l); store_ua<SC>(p_hh, q_b, nv_h); } else {
                         store_vec(p_lh + c * cs_b, q_a, pol_band);
                         store_vec(p_hh + c * cs_b, q_b, pol_band);
                         }
@@ -1131,10 +1175,39 @@ template <int WT, int NC1, int UA = 0> __host__ __device__ constexpr int inv_rin
 }
 template <int WT, int NC1, int UA = 0> __host__ __device__ constexpr int inv_cta_smem() { return J2K_RING_WARPS * (inv_ring_bytes<WT, NC1, UA>() + J2K_RING_MAXD * 8); }
 
+// Exchange ring of the three-producer level-1 inverse (inv3w_kernel): DX stages, a stage = one row pair of all three
+// components as half-even-rounded float32 samples, [component][row e / o][half][lane] x 16 bytes (conflict-free 128-bit
+// accesses).  Producers (one warp per component) fill a stage and arrive on full[stage]; the consumer warp drains it and
+// arrives on empty[stage].
+#ifndef J2K_X3_DX
+#define J2K_X3_DX 4
+#endif
+#define J2K_X3_STAGEB (3 * 2 * 2 * 32 * 16)
+struct XchPort {
+    smem_t data, full, empty;
+    unsigned cnt;   // stages produced / consumed so far by this warp (all warps of the CTA count the same stages)
+    int dx;         // stages in the ring
+    __device__ __forceinline__ void put(int comp, int lane, const float2 (&xe)[4], const float2 (&xo)[4]) {
+        const int slot = (int)(cnt % (unsigned)dx);
+        mbar_wait(empty + 8 * slot, ((cnt / (unsigned)dx) & 1u) ^ 1u);
+        const float2 MG = splat2(12582912.0f), NMG = splat2(-12582912.0f);
+        const smem_t b = data + slot * J2K_X3_STAGEB + comp * 2048 + lane * 16;
+        sts128f(b, add2(add2(xe[0], MG), NMG), add2(add2(xe[1], MG), NMG));
+        sts128f(b + 512, add2(add2(xe[2], MG), NMG), add2(add2(xe[3], MG), NMG));
+        sts128f(b + 1024, add2(add2(xo[0], MG), NMG), add2(add2(xo[1], MG), NMG));
+        sts128f(b + 1536, add2(add2(xo[2], MG), NMG), add2(add2(xo[3], MG), NMG));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full + 8 * slot);
+        cnt++;
+    }
+};
+
 // UA = 1: general-alignment variant of the inverse (see FwdRing): band rows staged from any byte position with their own
 // phase, lanes fetch with the widest load the phases allow, pixel / LL rows stored with the widest access their alignment
 // allows and masked at the window's right edge; odd window widths (low band one sample wider than the high band) included.
-template <int WT, int NP, int NC, int OUT, int MCT, int RB = J2K_INV_RING_BYTES, int UA = 0>
+// XCH = 1: the job is one COMPONENT of a three-component level 1 (inv3w_kernel): the finished rows go to the CTA's exchange
+// ring instead of memory.
+template <int WT, int NP, int NC, int OUT, int MCT, int RB = J2K_INV_RING_BYTES, int UA = 0, int XCH = 0>
 struct InvRing {
     typedef typename Wt<WT>::T T;
     static constexpr int LAG = Wt<WT>::LAG;
@@ -1165,16 +1238,11 @@ struct InvRing {
         else q[0] = (int)lds32(p);
     }
 
-    // the lane's NP band samples from an address that is only `la` bytes aligned (UA; warp-uniform la >= 4)
-    static __device__ __forceinline__ void fetch_ua(smem_t p, int (&q)[NP], int la) {
-        if (la >= 16) { fetch(p, q); return; }
-        if (la >= 8) {
+    // the lane's NP band samples at any 4-byte phase (UA: band samples are ints).  Four 32-bit loads: two aligned 128-bit
+    // loads plus a warp-uniform word select (the forward kernel's form) were measured 10 - 16 % slower here.
+    static __device__ __forceinline__ void fetch_ua(smem_t row, int off, int (&q)[NP]) {
 #pragma unroll
-            for (int k = 0; k < NP / 2; k++) { uint2 v = lds64(p + 8 * k); q[2 * k] = (int)v.x; q[(2 * k + 1) % NP] = (int)v.y; }
-        } else {
-#pragma unroll
-            for (int k = 0; k < NP; k++) q[k] = (int)lds32(p + 4 * k);
-        }
+        for (int k = 0; k < NP; k++) q[k] = (int)lds32(row + off + 4 * k);
     }
     static __device__ __forceinline__ int row_phase(smem_t row) { return UA ? (int)lds32(row + ROWB - 4) : 0; }
 
@@ -1203,36 +1271,26 @@ struct InvRing {
         __syncwarp();
     }
 
-    // UA stores.  n valid ints of q at p, rows allowing `cls`-int vectors (planar destinations: LL planes, wavelet API)
-    static __device__ __forceinline__ void store_ints_ua(int* p, const int (&q)[NS], int n, int cls) {
+    // UA stores: the variant (XA = bytes every destination row is aligned to: 8, 4 or 1 = element-wise) is a template
+    // parameter of the job loop, chosen once per job.  n valid ints of q at p (planar destinations: LL planes, GetImageData)
+    template <int XA>
+    static __device__ __forceinline__ void store_ints_ua(int* p, const int (&q)[NS], int n) {
 #pragma unroll
-        for (int g = 0; g < NS; g += 4) {
-            if (g + 4 <= n && cls >= 4) { *(int4*)(p + g) = make_int4(q[g], q[g + 1], q[(g + 2) % NS], q[(g + 3) % NS]); continue; }
-#pragma unroll
-            for (int j = g; j < g + 4 && j < NS; j += 2) {
-                if (j + 1 < n && cls >= 2) *(int2*)(p + j) = make_int2(q[j], q[(j + 1) % NS]);
-                else { if (j < n) p[j] = q[j]; if (j + 1 < n) p[j + 1] = q[(j + 1) % NS]; }
-            }
+        for (int j = 0; j < NS; j += 2) {
+            if (XA >= 8 && j + 1 < n) *(int2*)(p + j) = make_int2(q[j], q[(j + 1) % NS]);
+            else { if (j < n) p[j] = q[j]; if (j + 1 < n) p[j + 1] = q[(j + 1) % NS]; }
         }
     }
-    // nb valid bytes of the packed words wv at xrow, which is `al` bytes aligned (packed pixel rows)
-    template <int NWO>
-    static __device__ __forceinline__ void store_bytes_ua(unsigned char* xrow, const unsigned (&wv)[NWO], int nb, int al) {
-        if (nb >= NWO * 4 && al >= NWO * 4) {
-            if constexpr (NWO == 4) *(uint4*)xrow = make_uint4(wv[0], wv[1], wv[2 % NWO], wv[3 % NWO]);
-            else if constexpr (NWO == 2) *(uint2*)xrow = make_uint2(wv[0], wv[1 % NWO]);
-            else *(unsigned*)xrow = wv[0];
-            return;
-        }
+    // nb valid bytes of the packed words wv at xrow (packed pixel rows; ES = bytes per sample)
+    template <int XA, int NWO, int ES>
+    static __device__ __forceinline__ void store_bytes_ua(unsigned char* xrow, const unsigned (&wv)[NWO], int nb) {
 #pragma unroll
         for (int k = 0; k < NWO; k++) {
             const int left = nb - 4 * k;  // valid bytes of this word
-            if (left >= 4 && al >= 4) { *(unsigned*)(xrow + 4 * k) = wv[k]; continue; }
-            if (al >= 2) {
+            if (XA >= 4 && left >= 4) { *(unsigned*)(xrow + 4 * k) = wv[k]; continue; }
+            if constexpr (ES == 2) {
                 if (left >= 2) *(unsigned short*)(xrow + 4 * k) = (unsigned short)(wv[k] & 0xFFFFu);
-                else if (left >= 1) xrow[4 * k] = (unsigned char)(wv[k] & 0xFFu);
                 if (left >= 4) *(unsigned short*)(xrow + 4 * k + 2) = (unsigned short)(wv[k] >> 16);
-                else if (left >= 3) xrow[4 * k + 2] = (unsigned char)((wv[k] >> 16) & 0xFFu);
             } else {
 #pragma unroll
                 for (int b = 0; b < 4; b++)
@@ -1242,8 +1300,9 @@ struct InvRing {
     }
 
     // final stage of level 1: inverse MCT -> (+DC, optional planes) -> clamp -> pack -> one vector store per row
+    template <int XA = 16, int PA = 16>
     static __device__ __forceinline__ void store_final(const RingSeg& S, const RawFmt& raw, const RawPack& rp, unsigned char* xrow, int* prow,
-                                                       int (&iv)[NC][NS], int nvs = NS, int xal = 16, int pcls = 4) {
+                                                       int (&iv)[NC][NS], int nvs = NS) {
         if constexpr (NC == 3 && MCT != MCTK_NONE) {
 #pragma unroll
             for (int s = 0; s < NS; s++) {
@@ -1257,7 +1316,7 @@ struct InvRing {
                 int t[NS];
 #pragma unroll
                 for (int s = 0; s < NS; s++) t[s] = iv[0][s] + raw.dc;
-                store_ints_ua(prow, t, nvs, pcls);
+                store_ints_ua<PA>(prow, t, nvs);
             }
         } else
         if (prow) {
@@ -1286,7 +1345,7 @@ struct InvRing {
                 wv[k] = pack_clamp2(iv[(2 * k) % NC][(2 * k) / NC], iv[(2 * k + 1) % NC][(2 * k + 1) / NC], rp);
             }
         }
-        if constexpr (UA) { store_bytes_ua<NWO>(xrow, wv, nvs * ES, xal); return; }
+        if constexpr (UA) { store_bytes_ua<XA, NWO, ES>(xrow, wv, nvs * ES); return; }
         if constexpr (NWO % 4 == 0) {
 #pragma unroll
             for (int k = 0; k < NWO / 4; k++) *((uint4*)xrow + k) = make_uint4(wv[4 * k], wv[4 * k + 1], wv[(4 * k + 2) % NWO], wv[(4 * k + 3) % NWO]);
@@ -1317,23 +1376,26 @@ struct InvRing {
     //     (2 E of the samples: 0.02 % at M = 200).
     // rint(t) is t + 1.5 * 2^23 - 1.5 * 2^23 (exact for |t| < 2^22, round half-even); the biased sum's low mantissa bits are the
     // integer itself, which pack_clamp2_magic picks up without an F2I.
+    template <bool PRE = false>  // PRE: the samples arrive rounded already (inv3w_kernel's exchange ring)
     static __device__ __forceinline__ bool ict_fast_row(const RawPack& rp, unsigned char* xrow, const float2 (&x)[NC][NP]) {
         static_assert(NC == 3 && OUT == IN_U8, "8-bit interleaved RGB");
         const float2 MG = splat2(12582912.0f), NMG = splat2(-12582912.0f), NEG1 = splat2(-1.0f), BIAS = splat2(9.5367431640625e-7f);
+        const float2 MGD = splat2(rp.magic_dc), NMGD = splat2(-rp.magic_dc);  // output bias with the DC shift folded in (exact)
         const float2 cRh = splat2(1.375f), cRl = splat2(0.027f), cBh = splat2(1.75f), cBl = splat2(0.022f);
         const float2 cG1 = splat2(-0.34413f), cG2 = splat2(-0.71414f);
         unsigned u[3][NS];  // biased bit patterns of R, G, B per sample
         float mag = 0.f, dist = 0.f;
 #pragma unroll
         for (int j = 0; j < NP; j++) {
-            const float2 y = add2(add2(x[0][j], MG), NMG), cb = add2(add2(x[1][j], MG), NMG), cr = add2(add2(x[2][j], MG), NMG);
+            const float2 y = PRE ? x[0][j] : add2(add2(x[0][j], MG), NMG), cb = PRE ? x[1][j] : add2(add2(x[1][j], MG), NMG),
+                         cr = PRE ? x[2][j] : add2(add2(x[2][j], MG), NMG);
             mag = fmaxf(mag, fmaxf(fabsf(y.x), fabsf(y.y)));
             mag = fmaxf(mag, fmaxf(fabsf(cb.x), fabsf(cb.y)));
             mag = fmaxf(mag, fmaxf(fabsf(cr.x), fabsf(cr.y)));
             const float2 tr = fma2(cRl, cr, fma2(cRh, cr, y)), tb = fma2(cBl, cb, fma2(cBh, cb, y));
             const float2 tg = fma2(cG2, cr, fma2(cG1, cb, y));
-            const float2 br = add2(fma2(tr, BIAS, tr), MG), bb = add2(fma2(tb, BIAS, tb), MG), bg = add2(tg, MG);
-            const float2 d = fma2(add2(bg, NMG), NEG1, tg);  // tg - rint(tg), exact
+            const float2 br = add2(fma2(tr, BIAS, tr), MGD), bb = add2(fma2(tb, BIAS, tb), MGD), bg = add2(tg, MGD);
+            const float2 d = fma2(add2(bg, NMGD), NEG1, tg);  // tg - rint(tg), exact (the integer dc moves no fraction)
             dist = fmaxf(dist, fmaxf(fabsf(d.x), fabsf(d.y)));
             u[0][2 * j] = __float_as_uint(br.x); u[0][2 * j + 1] = __float_as_uint(br.y);
             u[1][2 * j] = __float_as_uint(bg.x); u[1][2 * j + 1] = __float_as_uint(bg.y);
@@ -1344,8 +1406,8 @@ struct InvRing {
         unsigned wv[NWO];
 #pragma unroll
         for (int k = 0; k < NWO; k++) {
-            const unsigned t0 = pack_clamp2_magic(u[(4 * k) % 3][(4 * k) / 3], u[(4 * k + 1) % 3][(4 * k + 1) / 3], rp);
-            const unsigned t1 = pack_clamp2_magic(u[(4 * k + 2) % 3][(4 * k + 2) / 3], u[(4 * k + 3) % 3][(4 * k + 3) / 3], rp);
+            const unsigned t0 = pack_clamp2_magic_dc(u[(4 * k) % 3][(4 * k) / 3], u[(4 * k + 1) % 3][(4 * k + 1) / 3], rp);
+            const unsigned t1 = pack_clamp2_magic_dc(u[(4 * k + 2) % 3][(4 * k + 2) / 3], u[(4 * k + 3) % 3][(4 * k + 3) / 3], rp);
             wv[k] = __byte_perm(t0, t1, 0x6420);
         }
         if constexpr (NWO % 4 == 0) {
@@ -1373,8 +1435,23 @@ struct InvRing {
         }
     }
 
+    // The job loop is instantiated per destination alignment of the general-alignment variant and chosen once per job
+    // (XA: pixel / LL rows, PA: GetImageData plane rows; in bytes, 1 = element-wise stores).
     static __device__ __forceinline__ void run(const RingSeg& S, const RawFmt& raw, int item, int chunk, int strip, RingWarp& rw,
-                                               int lane) {
+                                               int lane, XchPort* xp = nullptr, int comp = 0) {
+        if constexpr (!UA) run_t<16, 16>(S, raw, item, chunk, strip, rw, lane, xp, comp);
+        else {
+            const bool pa = S.st_cls[0] >= 2;  // plane rows allow 64-bit stores
+            if (S.x_align >= 8) { if (pa) run_t<8, 8>(S, raw, item, chunk, strip, rw, lane); else run_t<8, 4>(S, raw, item, chunk, strip, rw, lane); }
+            else if (S.x_align >= 4) { if (pa) run_t<4, 8>(S, raw, item, chunk, strip, rw, lane); else run_t<4, 4>(S, raw, item, chunk, strip, rw, lane); }
+            else { if (pa) run_t<1, 8>(S, raw, item, chunk, strip, rw, lane); else run_t<1, 4>(S, raw, item, chunk, strip, rw, lane); }
+        }
+    }
+
+    template <int XA, int PA>
+    static __device__ __forceinline__ void run_t(const RingSeg& S, const RawFmt& raw, int item, int chunk, int strip, RingWarp& rw,
+                                               int lane, XchPort* xp = nullptr, int comp = 0) {
+        static_assert(!XCH || (WT == 97 && NC == 1 && NP == 4 && !FINAL && !UA), "exchange mode: one 9/7 component per job");
         const int w = S.w, h = S.h, py = S.py;
         const int bw = S.lw;  // == w - lw on this path (w is a multiple of 2 NP)
         const int kxs = strip * S.strip_pairs;
@@ -1394,8 +1471,7 @@ struct InvRing {
         const bool fix = fix_l || fix_r;
         const bool st = lane >= HLN && kx0 < kxe && (UA || kx0 + NP <= bw);
         const int nvs = w - 2 * kx0;                 // UA: samples of this lane inside the window (<= 0: none, >= NS: all)
-        const int la = UA ? S.load_align : 16, xal = UA ? S.x_align : 16, pcls = UA ? S.st_cls[0] : 4;
-        (void)nvs; (void)la; (void)xal; (void)pcls;
+        (void)nvs;
         const float one = rw.one;
 
         const int ky0 = chunk * S.chunk_pairs;
@@ -1410,6 +1486,7 @@ struct InvRing {
         const unsigned char* b_hh = (const unsigned char*)((const int*)S.hh.base + S.hh.off[item] + (long long)S.hh.y_off * S.hh.row_stride + S.hh.x_off) + c0;
         const long long rp_ll = (long long)S.ll.row_stride * 4, rp_b = (long long)S.hl.row_stride * 4;
         const long long cp_ll = S.ll.comp_stride * 4, cp_b = S.hl.comp_stride * 4;
+        if constexpr (XCH) { b_ll += comp * cp_ll; b_hl += comp * cp_b; b_lh += comp * cp_b; b_hh += comp * cp_b; }
 
         const int n_st = (n_it + RPS - 1) / RPS;
         int pj = 0, pslot = 0;
@@ -1539,10 +1616,10 @@ struct InvRing {
                     int q0[NP], q1[NP], q2[NP], q3[NP];
                     if constexpr (UA) {
                         const smem_t r0 = stage + (4 * c) * ROWB;
-                        fetch_ua(r0 + lane_off + row_phase(r0), q0, la);
-                        fetch_ua(r0 + ROWB + lane_off + row_phase(r0 + ROWB), q1, la);
-                        fetch_ua(r0 + 2 * ROWB + lane_off + row_phase(r0 + 2 * ROWB), q2, la);
-                        fetch_ua(r0 + 3 * ROWB + lane_off + row_phase(r0 + 3 * ROWB), q3, la);
+                        fetch_ua(r0, lane_off + row_phase(r0), q0);
+                        fetch_ua(r0 + ROWB, lane_off + row_phase(r0 + ROWB), q1);
+                        fetch_ua(r0 + 2 * ROWB, lane_off + row_phase(r0 + 2 * ROWB), q2);
+                        fetch_ua(r0 + 3 * ROWB, lane_off + row_phase(r0 + 3 * ROWB), q3);
                     } else {
                     fetch(stage + (4 * c + 0) * ROWB + lane_off, q0);  // every lane, also past the strip (see FwdRing::load_scalar)
                     fetch(stage + (4 * c + 1) * ROWB + lane_off, q1);
@@ -1618,6 +1695,7 @@ struct InvRing {
                     }
                 }
                 if (it < 2 * LAG) return;
+                if constexpr (XCH) { xp->put(comp, lane, xe[0], xo[0]); return; }  // every lane, every emitting iteration: the consumer masks
                 const int ky = ky0 + it - 2 * LAG;
                 const int re = 2 * ky - py, ro = re + 1;
                 unsigned char* const xrow = xlane;
@@ -1636,7 +1714,7 @@ struct InvRing {
                             for (int c = 0; c < NC; c++)
 #pragma unroll
                                 for (int j = 0; j < NP; j++) { iv[c][2 * j] = __float2int_rn(xe[c][j].x); iv[c][2 * j + 1] = __float2int_rn(xe[c][j].y); }
-                            store_final(S, raw, rp, xrow, prow, iv, nvs, xal, pcls);
+                            store_final<XA, PA>(S, raw, rp, xrow, prow, iv, nvs);
                         }
                     }
                     if (ro < h) {
@@ -1647,7 +1725,7 @@ struct InvRing {
                             for (int c = 0; c < NC; c++)
 #pragma unroll
                                 for (int j = 0; j < NP; j++) { iv[c][2 * j] = __float2int_rn(xo[c][j].x); iv[c][2 * j + 1] = __float2int_rn(xo[c][j].y); }
-                            store_final(S, raw, rp, xrow + xpitch, prow ? prow + planes_rs : nullptr, iv, nvs, xal, pcls);
+                            store_final<XA, PA>(S, raw, rp, xrow + xpitch, prow ? prow + planes_rs : nullptr, iv, nvs);
                         }
                     }
                 } else {
@@ -1658,7 +1736,7 @@ struct InvRing {
                             q[2 * j] = x_mode == 1 ? __float2int_rn(xe[0][j].x) : __float_as_int(xe[0][j].x);
                             q[2 * j + 1] = x_mode == 1 ? __float2int_rn(xe[0][j].y) : __float_as_int(xe[0][j].y);
                         }
-                        if constexpr (UA) store_ints_ua((int*)xrow, q, nvs, xal >> 2); else
+                        if constexpr (UA) store_ints_ua<XA>((int*)xrow, q, nvs); else
                         store_planar((int*)xrow, q);
                     }
                     if (ro < h) {
@@ -1667,7 +1745,7 @@ struct InvRing {
                             q[2 * j] = x_mode == 1 ? __float2int_rn(xo[0][j].x) : __float_as_int(xo[0][j].x);
                             q[2 * j + 1] = x_mode == 1 ? __float2int_rn(xo[0][j].y) : __float_as_int(xo[0][j].y);
                         }
-                        if constexpr (UA) store_ints_ua((int*)(xrow + xpitch), q, nvs, xal >> 2); else
+                        if constexpr (UA) store_ints_ua<XA>((int*)(xrow + xpitch), q, nvs); else
                         store_planar((int*)(xrow + xpitch), q);
                     }
                 }
@@ -1709,10 +1787,10 @@ struct InvRing {
                     int q0[NP], q1[NP], q2[NP], q3[NP];
                     if constexpr (UA) {
                         const smem_t r0 = stage + (4 * c) * ROWB;
-                        fetch_ua(r0 + lane_off + row_phase(r0), q0, la);
-                        fetch_ua(r0 + ROWB + lane_off + row_phase(r0 + ROWB), q1, la);
-                        fetch_ua(r0 + 2 * ROWB + lane_off + row_phase(r0 + 2 * ROWB), q2, la);
-                        fetch_ua(r0 + 3 * ROWB + lane_off + row_phase(r0 + 3 * ROWB), q3, la);
+                        fetch_ua(r0, lane_off + row_phase(r0), q0);
+                        fetch_ua(r0 + ROWB, lane_off + row_phase(r0 + ROWB), q1);
+                        fetch_ua(r0 + 2 * ROWB, lane_off + row_phase(r0 + 2 * ROWB), q2);
+                        fetch_ua(r0 + 3 * ROWB, lane_off + row_phase(r0 + 3 * ROWB), q3);
                     } else {
                     fetch(stage + (4 * c + 0) * ROWB + lane_off, q0);  // every lane, also past the strip (see FwdRing::load_scalar)
                     fetch(stage + (4 * c + 1) * ROWB + lane_off, q1);
@@ -1739,6 +1817,8 @@ struct InvRing {
 #pragma unroll
                         for (int j = 0; j < NP; j++) { s[j] = ql[j]; d[j + 1] = qh[j]; }
                         if constexpr (HF) {
+                            // (every lane reads its neighbours' samples from the staged row; shuffles for the inner lanes plus
+                            // predicated loads for the strip's outer lanes were measured 9 % slower on C1 / C4)
                             const smem_t rl = stage + row_l * ROWB;
                             const smem_t pl = rl + lane_off + row_phase(rl), ph = rl + ROWB + lane_off + row_phase(rl + ROWB);
                             int dl = (int)lds32(ph - 4), sr = (int)lds32(pl + LB), dr = (int)lds32(ph + LB);
@@ -1780,11 +1860,11 @@ struct InvRing {
                 if (planes) planes += 2 * planes_rs;
                 if (!st) return;
                 if constexpr (FINAL) {
-                    if (re >= 0 && re < h) store_final(S, raw, rp, xrow, prow, xe, nvs, xal, pcls);
-                    if (ro < h) store_final(S, raw, rp, xrow + xpitch, prow ? prow + planes_rs : nullptr, xo, nvs, xal, pcls);
+                    if (re >= 0 && re < h) store_final<XA, PA>(S, raw, rp, xrow, prow, xe, nvs);
+                    if (ro < h) store_final<XA, PA>(S, raw, rp, xrow + xpitch, prow ? prow + planes_rs : nullptr, xo, nvs);
                 } else if constexpr (UA) {
-                    if (re >= 0 && re < h) store_ints_ua((int*)xrow, xe[0], nvs, xal >> 2);
-                    if (ro < h) store_ints_ua((int*)(xrow + xpitch), xo[0], nvs, xal >> 2);
+                    if (re >= 0 && re < h) store_ints_ua<XA>((int*)xrow, xe[0], nvs);
+                    if (ro < h) store_ints_ua<XA>((int*)(xrow + xpitch), xo[0], nvs);
                 } else {
                     if (re >= 0 && re < h) store_planar((int*)xrow, xe[0]);
                     if (ro < h) store_planar((int*)(xrow + xpitch), xo[0]);
@@ -1814,6 +1894,9 @@ struct InvRing {
 #ifndef J2K_INV_MINB_53
 #define J2K_INV_MINB_53 4    // resident CTAs per SM targeted by the single-component 5/3 inverse (128 registers, 16 warps: +2 % on C1 / C4)
 #endif
+#ifndef J2K_INV3W_DEFAULT
+#define J2K_INV3W_DEFAULT 1  // ICT + 9/7 8-bit RGB inverse: three-producer level 1 (inv3w_kernel) instead of one warp per pixel strip
+#endif
 #ifndef J2K_INV_RGB_NP
 #define J2K_INV_RGB_NP 2     // sample pairs per lane of the 3-component level-1 inverse (4: 2 CTAs/SM, the window state of three components in 255 registers)
 #endif
@@ -1838,6 +1921,210 @@ __global__ void __launch_bounds__(J2K_RING_WARPS * 32, (NC1 == 3 && NP1 == 4) ? 
         ring_signal(A, S, J.item, lane);
     }
     ring_retire(A, lane);
+}
+
+
+// ------------------------------------------------------------------ three-producer level-1 inverse (ICT + 9/7, 8-bit RGB)
+//
+// The level-1 inverse of a three-component 9/7 frame needs all three components of a pixel at its very end (the inverse
+// ICT), which forced the one-warp-per-pixel-strip job to carry three vertical window states (NP = 2: half the columns per
+// lane, twice the per-lane overhead, 1.0 warp instruction per sample against 0.66 for a single component).  Here a CTA of
+// four warps shares the job instead: warps 0..2 each run the SINGLE-component pipeline (InvRing<97, NP = 4> in exchange
+// mode, own TMA ring) for Y, Cb, Cr of the same pixel strip and hand their finished, rounded rows to warp 3 through a
+// DX-stage shared-memory ring (mbarrier full / empty per stage: the warps are decoupled by DX row pairs, no CTA barrier in
+// the loop); warp 3 runs the inverse ICT (float32 fast path, float64 fallback per lane), +DC, clamp, pack and the pixel
+// stores.  Coarser levels: warps 0..2 take ordinary single-component jobs, warp 3 idles.  Jobs are taken three at a time
+// per CTA; a level-1 pixel job occupies three consecutive job numbers (one per component), every segment's job range is
+// padded to a multiple of three.
+#ifndef J2K_X3_RING_BYTES
+#define J2K_X3_RING_BYTES 13056   // producer staging per warp: 3 stages of 2 x four 544 B band rows
+#endif
+#define J2K_X3_WARP_SMEM (J2K_X3_RING_BYTES + J2K_RING_MAXD * 8)
+#define J2K_X3_CTA_SMEM (3 * J2K_X3_WARP_SMEM + J2K_X3_DX * J2K_X3_STAGEB + 2 * J2K_X3_DX * 8)
+
+template <int OUT>
+struct Inv3WConsumer {
+    typedef InvRing<97, 4, 3, OUT, MCTK_ICT> C3;   // its pixel tail: ict_fast_row / store_final (inverse ICT, pack, stores)
+    static constexpr int NP = 4, NS = 8;
+    static __device__ __forceinline__ void run(const RingSeg& S, const RawFmt& raw, int item, int chunk, int strip, XchPort& xp, int lane) {
+        const int h = S.h, py = S.py, bw = S.lw;
+        const int kxs = strip * S.strip_pairs;
+        const int kxe = min(kxs + S.strip_pairs, S.Kx);
+        const int kx0 = kxs - NP + lane * NP;     // the producers' lane mapping (one halo lane per side)
+        const bool st = lane >= 1 && kx0 < kxe && kx0 + NP <= bw;
+        const int ky0 = chunk * S.chunk_pairs;
+        const int ky1 = min(ky0 + S.chunk_pairs, S.Ky);
+        constexpr int XES = (OUT == IN_U8) ? 1 : 2;
+        unsigned char* xlane = (unsigned char*)S.x_base + S.x_off[item] * XES + (long long)(2 * kx0) * (3 * XES);
+        const long long xpitch = S.x_row_bytes;
+        int* planes = S.planes_out ? S.planes_out + S.planes_off[item] + 2 * kx0 : nullptr;
+        const int planes_rs = S.planes_row_stride;
+        const RawPack rp = make_raw_pack(raw);
+        xlane += (long long)(2 * ky0 - py) * xpitch;
+        if (planes) planes += (long long)(2 * ky0 - py) * planes_rs;
+        auto emit = [&](const float2 (&x)[3][NP], unsigned char* xrow, int* prow) {
+            bool done = false;
+            if constexpr (J2K_ICT_FAST && OUT == IN_U8) { if (!prow) done = C3::template ict_fast_row<true>(rp, xrow, x); }
+            if (!done) {
+                int iv[3][NS];
+#pragma unroll
+                for (int c = 0; c < 3; c++)
+#pragma unroll
+                    for (int j = 0; j < NP; j++) { iv[c][2 * j] = __float2int_rn(x[c][j].x); iv[c][2 * j + 1] = __float2int_rn(x[c][j].y); }
+                C3::store_final(S, raw, rp, xrow, prow, iv);
+            }
+        };
+#pragma unroll 1
+        for (int ky = ky0; ky < ky1; ky++) {
+            const int slot = (int)(xp.cnt % (unsigned)xp.dx);
+            mbar_wait(xp.full + 8 * slot, (xp.cnt / (unsigned)xp.dx) & 1u);
+            const smem_t b = xp.data + slot * J2K_X3_STAGEB + lane * 16;
+            float2 xe[3][NP], xo[3][NP];
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const uint4 e0 = lds128(b + c * 2048), e1 = lds128(b + c * 2048 + 512), o0 = lds128(b + c * 2048 + 1024), o1 = lds128(b + c * 2048 + 1536);
+                xe[c][0] = make_float2(__uint_as_float(e0.x), __uint_as_float(e0.y)); xe[c][1] = make_float2(__uint_as_float(e0.z), __uint_as_float(e0.w));
+                xe[c][2] = make_float2(__uint_as_float(e1.x), __uint_as_float(e1.y)); xe[c][3] = make_float2(__uint_as_float(e1.z), __uint_as_float(e1.w));
+                xo[c][0] = make_float2(__uint_as_float(o0.x), __uint_as_float(o0.y)); xo[c][1] = make_float2(__uint_as_float(o0.z), __uint_as_float(o0.w));
+                xo[c][2] = make_float2(__uint_as_float(o1.x), __uint_as_float(o1.y)); xo[c][3] = make_float2(__uint_as_float(o1.z), __uint_as_float(o1.w));
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(xp.empty + 8 * slot);  // the values are in registers: the stage may be refilled
+            xp.cnt++;
+            const int re = 2 * ky - py, ro = re + 1;
+            if (st) {
+                if (re >= 0 && re < h) emit(xe, xlane, planes);
+                if (ro < h) emit(xo, xlane + xpitch, planes ? planes + planes_rs : nullptr);
+            }
+            xlane += 2 * xpitch;
+            if (planes) planes += 2 * planes_rs;
+        }
+    }
+};
+
+// job number -> (segment, item, chunk, strip, component); level-1 pixel jobs hold three numbers, ranges are padded to
+// multiples of three (J.item < 0: a padding number, nothing to do)
+__device__ __forceinline__ void x3_decode(const RingArgs& A, int job, RingJob& J, int& comp) {
+    int k = 0;
+    while (k + 1 < A.nseg && job >= A.seg[k].job_end) k++;
+    const RingSeg& S = A.seg[k];
+    int local = job - S.job_begin;
+    comp = 0;
+    if (S.first) { comp = local % 3; local /= 3; }
+    const int ns = S.nstrips, nc = S.nchunks;
+    J.seg = k;
+    J.strip = local % ns;
+    J.chunk = (local / ns) % nc;
+    J.item = local / (ns * nc);
+    if (J.item >= S.n_items) J.item = -1;
+}
+
+template <int OUT>
+__global__ void __launch_bounds__(128, J2K_RING_MINB) inv3w_kernel(const __grid_constant__ RingArgs A) {
+    J2K_SMEM_DECL(smem);
+    const int lane = threadIdx.x & 31;
+#ifdef J2K_EMU
+    // the emulator runs warps one after the other: ONE warp plays all four roles of a pixel job in turn, with an exchange
+    // ring deep enough for a whole chunk (the arithmetic and the index logic are the same; the barriers are no-ops)
+    static thread_local unsigned char* xbig = nullptr;
+    if (!xbig) xbig = (unsigned char*)malloc((size_t)J2K_X3_STAGEB * 4096);
+    RingWarp rw;
+    rw.ring = smem_handle(smem);
+    rw.bars = rw.ring + J2K_X3_RING_BYTES;
+    rw.phase = 0;
+    rw.one = A.one;
+    for (;;) {
+        int job = 0;
+        if (lane == 0) job = (int)atomicAdd(A.ctl, 3u);
+        job = __shfl_sync(0xffffffffu, job, 0);
+        if (job >= A.total_jobs) break;
+        RingJob J; int comp;
+        x3_decode(A, job, J, comp);
+        const RingSeg& S = A.seg[J.seg];
+        if (S.first) {
+            if (J.item < 0) continue;
+            XchPort xp{smem_handle(xbig), smem_handle(xbig), smem_handle(xbig), 0u, 4096};
+            for (int c = 0; c < 3; c++) {
+                xp.cnt = 0;
+                InvRing<97, 4, 1, IN_F32, MCTK_NONE, J2K_X3_RING_BYTES, 0, 1>::run(S, A.raw, J.item, J.chunk, J.strip, rw, lane, &xp, c);
+            }
+            xp.cnt = 0;
+            Inv3WConsumer<OUT>::run(S, A.raw, J.item, J.chunk, J.strip, xp, lane);
+        } else {
+            for (int q = 0; q < 3; q++) {
+                x3_decode(A, job + q, J, comp);
+                if (J.item < 0 || job + q >= A.seg[J.seg].job_end) continue;
+                const RingSeg& T = A.seg[J.seg];
+                InvRing<97, 4, 1, IN_F32, MCTK_NONE, J2K_X3_RING_BYTES>::run(T, A.raw, J.item, J.chunk, J.strip, rw, lane);
+                if (T.has_waiters && lane == 0) red_release_add(A.ctl + T.done_base + J.item, 1u);
+            }
+        }
+    }
+    ring_retire(A, lane);
+#else
+    const int wib = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    __shared__ int s_job;
+    RingWarp rw;
+    rw.phase = 0;
+    rw.one = A.one;
+    if (wib < 3) {
+        rw.ring = smem_handle(smem + wib * J2K_X3_WARP_SMEM);
+        rw.bars = rw.ring + J2K_X3_RING_BYTES;
+        if (lane == 0) {
+            for (int q = 0; q < J2K_RING_MAXD; q++) mbar_init(rw.bars + 8 * q, 1);
+        }
+    } else {
+        rw.ring = rw.bars = 0;
+    }
+    XchPort xp;
+    xp.data = smem_handle(smem + 3 * J2K_X3_WARP_SMEM);
+    xp.full = xp.data + J2K_X3_DX * J2K_X3_STAGEB;
+    xp.empty = xp.full + 8 * J2K_X3_DX;
+    xp.cnt = 0;
+    xp.dx = J2K_X3_DX;
+    if (threadIdx.x == 96) {
+        for (int q = 0; q < J2K_X3_DX; q++) { mbar_init(xp.full + 8 * q, 3); mbar_init(xp.empty + 8 * q, 1); }
+    }
+    if (lane == 0) mbar_fence_init();
+    __syncthreads();
+    // Job triples are claimed per CTA through a barrier (one atomic per triple).  Measured alternative, rejected: dealing the
+    // triples round-robin to the CTAs, so that the producers start the next pixel job while the consumer drains the last one
+    // (no barrier, no pipeline drain at job boundaries) - C3 0.48 and C5 0.46 of the roofline against 0.54 / 0.53 with the
+    // barrier and four-times-taller jobs: the dynamic claim keeps the CTAs on adjacent strips and balances the tail.
+    for (;;) {
+        __syncthreads();  // every warp has read the previous base
+        if (threadIdx.x == 0) s_job = (int)atomicAdd(A.ctl, 3u);
+        __syncthreads();
+        const int base = s_job;
+        if (base >= A.total_jobs) break;
+        RingJob J; int comp;
+        x3_decode(A, base + (wib < 3 ? wib : 0), J, comp);
+        const RingSeg& S = A.seg[J.seg];
+        if (S.first) {
+            // the three numbers of a pixel job never straddle a segment: ranges are padded to multiples of three
+            if (J.item < 0) continue;
+            if (wib < 3) {
+                if (S.dep_seg >= 0) {  // this component's LL plane of the level below is complete
+                    if (lane == 0) {
+                        const unsigned* d = A.ctl + A.seg[S.dep_seg].done_base + 3 * J.item + comp;
+                        while (ld_relaxed(d) < (unsigned)S.dep_target) backoff();
+                        (void)ld_acquire(d);
+                        fence_proxy_async_global();
+                    }
+                    __syncwarp();
+                }
+                InvRing<97, 4, 1, IN_F32, MCTK_NONE, J2K_X3_RING_BYTES, 0, 1>::run(S, A.raw, J.item, J.chunk, J.strip, rw, lane, &xp, comp);
+            } else {
+                Inv3WConsumer<OUT>::run(S, A.raw, J.item, J.chunk, J.strip, xp, lane);
+            }
+        } else if (wib < 3 && J.item >= 0 && base + wib < S.job_end) {
+            ring_wait_dep(A, S, J.item, lane);
+            InvRing<97, 4, 1, IN_F32, MCTK_NONE, J2K_X3_RING_BYTES>::run(S, A.raw, J.item, J.chunk, J.strip, rw, lane);
+            ring_signal(A, S, J.item, lane);
+        }
+    }
+    ring_retire(A, lane);
+#endif
 }
 
 }  // namespace j2k

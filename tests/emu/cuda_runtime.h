@@ -84,6 +84,10 @@ template <typename T> static inline T __shfl_sync(unsigned, T v, int src) {
 }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
 static inline void __threadfence() {}
+static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) {
+    sh &= 31;
+    return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
+}
 static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
     unsigned long long src = ((unsigned long long)y << 32) | x;
     unsigned r = 0;

@@ -57,7 +57,8 @@ def test_htj2k_and_fused_t1_shift(ectx, oracle):
 @pytest.mark.parametrize("w,h,c,bits,signed,L,rev", [
     (512, 12, 1, 16, False, 2, False), (512, 12, 1, 12, True, 2, True), (384, 10, 1, 8, False, 2, False),
     (384, 10, 1, 8, True, 2, True), (136, 12, 3, 8, False, 2, False), (136, 12, 3, 16, False, 2, True),
-    (520, 9, 1, 16, False, 3, False), (128, 16, 3, 8, False, 2, False), (128, 16, 3, 8, False, 2, True),
+    (520, 9, 1, 16, False, 3, False), (128, 16, 3, 8, False, 2, False), (128, 16, 3, 8, False, 2, True), (128, 16, 3, 8, True, 2, False),
+    (256, 20, 3, 7, False, 3, False),
     (128, 16, 3, 16, False, 2, False), (128, 16, 3, 12, False, 2, True), (256, 24, 1, 8, False, 2, False),
 ])
 def test_fast_path_shapes(ectx, oracle, w, h, c, bits, signed, L, rev, capfd):

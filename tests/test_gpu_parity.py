@@ -36,6 +36,7 @@ def test_wavelet_api(ctx, oracle, w, h, levels, x0, y0):
     (300, 200, 2, 8, False, 3, True, "noise"), (300, 200, 4, 12, True, 3, False, "noise"),
     (64, 64, 1, 8, False, 0, True, "noise"), (64, 64, 1, 8, False, 0, False, "noise"), (1, 1, 1, 8, False, 2, False, "noise"),
     (2048, 64, 1, 16, False, 3, True, "smooth"), (64, 2048, 1, 12, False, 3, False, "smooth"),
+    (512, 384, 3, 8, True, 4, False, "noise"), (768, 256, 3, 8, False, 5, False, "noise"), (512, 256, 3, 7, False, 3, False, "noise"),  # ICT + 9/7: signed, noise, 7-bit
 ])
 def test_pipeline(ctx, oracle, w, h, c, bits, signed, L, rev, kind):
     PC.check_pipeline(ctx, oracle, w, h, c, bits, signed, L, rev, kind=kind, seed=w + h)
