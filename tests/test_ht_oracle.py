@@ -1,0 +1,70 @@
+"""The HTJ2K cleanup-pass block-decoder oracle (oracle/ht_oracle.c) against the reference's own interop contract:
+the 14 OpenJPH codestreams of test-data/htj2k/interop decode to input.raw (jpeg2000/htj2k/interop_manifest_test.go:43-74).
+CPU only."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.join(os.path.dirname(HERE), "go-dicom-codec_b200"))
+
+import ht_cases  # noqa: E402
+import ht_oracle_lib  # noqa: E402
+import oracle_lib  # noqa: E402
+from j2kb200 import abi  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def ht():
+    return ht_oracle_lib.HtOracle()
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    return oracle_lib.Oracle()
+
+
+def decode_fixture(ht, oracle, name, kind):
+    fx = ht_cases.load(name, kind, oracle.codeblock_layout)
+    h = fx["header"]
+    blocks, status = ht.decode_blocks(fx["stream"], fx["offsets"], fx["lengths"], fx["kmax"], fx["mmsb"], fx["widths"], fx["heights"],
+                                      fx["out_offsets"], h.components * fx["plane_samples"])
+    assert not status.any(), status
+    co = np.concatenate([oracle.scatter_blocks(blocks[c * fx["plane_samples"]:(c + 1) * fx["plane_samples"]], h.width, h.height,
+                                               h.num_levels, h.cbw, h.cbh).reshape(-1) for c in range(h.components)])
+    ip = abi.inv_params(h.width, h.height, h.components, h.depth[0], h.signed[0], num_levels=h.num_levels, reversible=True, htj2k=True,
+                        mct_mode=abi.MCT_RCT if h.mct else abi.MCT_NONE)
+    return fx, oracle.inverse(ip, co)
+
+
+@pytest.mark.parametrize("name,kind", ht_cases.fixtures())
+def test_openjph_fixtures_decode_to_input_raw(ht, oracle, name, kind):
+    fx, px = decode_fixture(ht, oracle, name, kind)
+    h = fx["header"]
+    assert h.cb_style & 0x40, "HT code-blocks"
+    assert all(b.passes in (0, 1) for comp in fx["blocks"] for b in comp), "OpenJPH lossless emits the cleanup pass only"
+    assert np.array_equal(px, fx["raw"])
+
+
+def test_tables_match_the_generated_product_tables(ht):
+    # tools/gen_ht_tables.py builds the packed tables the CUDA decoder indexes; the oracle builds its own at run time
+    inc = open(os.path.join(os.path.dirname(HERE), "go-dicom-codec_b200", "csrc", "j2k_ht_tables.inc")).read()
+    import re
+    for which, cname in enumerate(("HT_VLC_TBL0", "HT_VLC_TBL1", "HT_UVLC_TBL0", "HT_UVLC_TBL1")):
+        body = inc.split(cname + "[", 1)[1].split("{", 1)[1].split("}", 1)[0]
+        vals = np.array([int(x, 16) for x in re.findall(r"0x[0-9A-Fa-f]+", body)], np.uint16)
+        assert np.array_equal(vals, ht.table(which)), cname
+
+
+def test_empty_and_invalid_blocks(ht):
+    rc, out = ht.decode_block(b"", 8, 8, 10, 3)
+    assert rc == 0 and not out.any()  # decoder.go:44-46
+    rc, out = ht.decode_block(b"\x00\x00\x00\x00", 8, 8, 0, 3)
+    assert rc == -1 and not out.any()  # decoder.go:48-50
+    rc, out = ht.decode_block(b"\x00\x00\x00\x00", 8, 8, 10, 30)
+    assert rc == -2  # openjph_cleanup_decoder.go:125-127
+    rc, out = ht.decode_block(b"\x00\x00\x00\x00", 8, 8, 10, 3)
+    assert rc == -2  # Scup = 0 < 2: decoder.go:63-65
