@@ -33,6 +33,7 @@
 #include "j2k_kernels.cuh"
 #include "j2k_pointwise.cuh"
 #include "j2k_ring.cuh"
+#include "j2k_ht.cuh"
 
 #ifndef J2K_LAUNCH
 #define J2K_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
@@ -236,6 +237,7 @@ struct DeviceCtx {
     DevBuf in[2], out[2], planes[2], api[8];
     DevBuf blk[2], nbp[2];  // code-block interface: block-major planes and per-block numbps of a sub-batch
     DevBuf gsh[2], gmk[2];  // general-scaling ROI of a sub-batch: per-block shifts, per-sample mask
+    DevBuf ht_bytes, ht_desc, ht_status;  // HTJ2K block decoding: cleanup segments, descriptors, per-block result codes
     std::map<std::string, std::unique_ptr<Plan>> plans;
     long long use_clock = 0;   // LRU stamps of `plans`
     std::map<std::string, std::unique_ptr<struct BlockTable>> block_tables;
@@ -1806,6 +1808,33 @@ int launch_gather(j2k_ctx* ctx, BlockTable& T, int nframes, const int32_t* d_coe
     return 0;
 }
 
+// HT code-blocks hold at most 4096 samples (ISO/IEC 15444-15 restricts xcb + ycb <= 12 as Part 1 does)
+int validate_ht_cb(int cbw, int cbh) {
+    int rc = validate_cb(cbw, cbh);
+    if (rc) return rc;
+    if ((long long)cbw * cbh > 4096) return fail(J2K_ERR_UNSUPPORTED, "HT code-blocks hold at most 4096 samples (%d x %d)", cbw, cbh);
+    return 0;
+}
+
+// One warp per code-block (j2k_ht.cuh); to_planes: decoded samples go straight into the Mallat planes (assembleSubbands).
+int launch_ht_decode(j2k_ctx* ctx, BlockTable& T, int cbw, int cbh, int nframes, const unsigned char* d_bytes, const HtBlock* d_descs,
+                     int32_t* d_out, int to_planes, int32_t* d_status, cudaStream_t st) {
+    const long long total = (long long)T.nblocks * nframes;
+    if (total <= 0) return 0;
+    const int warps = 4;
+    const int wsm = ht_warp_smem(cbw, cbh);
+    const int smem = warps * wsm;
+#ifndef J2K_EMU
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(ht_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+#endif
+    const unsigned grid = (unsigned)((total + warps - 1) / warps);
+    J2K_LAUNCH_SMEM(ht_decode_kernel, grid, warps * 32, smem, st, d_bytes, d_descs, (const BlockEntry*)T.tab.p, T.nblocks, total,
+                    T.coeffs_per_frame, (int*)d_out, to_planes, (int*)d_status, wsm);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+}
+
 // Per-component MaxShift values of the caller (NULL: no ROI) -> kernel argument.
 int make_roi(const int32_t* roi_maxshift, int C, RoiShifts& r) {
     memset(&r, 0, sizeof r);
@@ -2726,6 +2755,143 @@ int j2k_scatter_blocks_roi_general_device(j2k_ctx* ctx, int dev, const j2k_inv_p
     roi.block_shift = (const int*)d_block_scale_shift;   // values must lie in 0..30 (not checked: device memory)
     roi.sample_mask = d_sample_mask;
     return launch_scatter(ctx, *BT, nframes, d_blocks, d_coeffs, cuda_stream ? (cudaStream_t)cuda_stream : d.s_main, roi);
+}
+
+// ---- HTJ2K block decoding on the device (decode side)
+
+static_assert(sizeof(j2k_ht_cblk) == 16 && sizeof(HtBlock) == 16, "j2k_ht_cblk and the kernel's record must agree");
+
+namespace ht_host {
+#define J2K_HT_TABLE static const
+#include "j2k_ht_tables.inc"
+#undef J2K_HT_TABLE
+}  // namespace ht_host
+
+int j2k_ht_table(int which, uint16_t* out) {
+    const unsigned short* t = which == 0 ? ht_host::HT_VLC_TBL0 : which == 1 ? ht_host::HT_VLC_TBL1 : which == 2 ? ht_host::HT_UVLC_TBL0
+                              : which == 3 ? ht_host::HT_UVLC_TBL1 : nullptr;
+    if (!t) return fail(J2K_ERR_INVALID_ARG, "no such table: %d", which);
+    const int n = which < 2 ? 1024 : which == 2 ? 320 : 256;
+    if (out) memcpy(out, t, (size_t)n * 2);
+    return n;
+}
+
+// Host form of both HT entry points: cleanup segments + records up, HT decode (-> block-major planes, or -> coefficient planes
+// followed by the inverse plan), results down.  Frames are sharded over the context's devices in contiguous blocks.
+static int ht_host_run(j2k_ctx* ctx, const j2k_inv_params* p, int cbw, int cbh, int nframes, const uint8_t* bytes, size_t nbytes,
+                       const j2k_ht_cblk* cblks, int32_t* blocks_out, void* pixels_out, size_t frame_stride_bytes, int32_t* planes_out,
+                       int32_t* status_out) {
+    if (!ctx) return fail(J2K_ERR_INVALID_ARG, "context is NULL");
+    if (!p) return fail(J2K_ERR_INVALID_ARG, "params is NULL");
+    int rc = validate_ht_cb(cbw, cbh);
+    if (rc) return rc;
+    Spec s;
+    if ((rc = spec_from_inv(p, planes_out != nullptr, s))) return rc;
+    if (!cblks || (!bytes && nbytes) || (!blocks_out && !pixels_out)) return fail(J2K_ERR_INVALID_ARG, "NULL buffer");
+    if (nframes <= 0) return fail(J2K_ERR_INVALID_ARG, "nframes must be positive");
+    const long long cpf = (long long)j2k_inv_coeff_count(p);
+    const size_t nblk = j2k_inv_block_count(p, cbw, cbh);
+    const size_t pixb = j2k_inv_pixel_bytes(p);
+    const int bps = s.bit_depth <= 8 ? 1 : 2;
+    if (pixels_out && (frame_stride_bytes < pixb || frame_stride_bytes % bps)) return fail(J2K_ERR_SIZE, "bad frame stride");
+    for (size_t i = 0; i < nblk * (size_t)nframes; i++)
+        if (cblks[i].length && (cblks[i].offset > nbytes || cblks[i].length > nbytes - cblks[i].offset))
+            return fail(J2K_ERR_SIZE, "code-block %zu: segment [%llu, +%u) lies outside the %zu-byte stream", i,
+                        (unsigned long long)cblks[i].offset, cblks[i].length, nbytes);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const int nd = (int)ctx->devs.size();
+    const int per = (nframes + nd - 1) / nd;
+    std::vector<std::vector<HtBlock>> recs(nd);   // re-based records: alive until the devices are synchronised below
+    int used = 0;
+    for (int di = 0; di < nd && rc == 0; di++) {
+        const int f0 = di * per, f1 = f0 + per > nframes ? nframes : f0 + per;
+        if (f0 >= f1) break;
+        used = di + 1;
+        if ((rc = sync_dev(ctx, di))) break;   // the slot buffers may still serve an asynchronous job
+        DeviceCtx& d = ctx->devs[di];
+        const int n = f1 - f0;
+        const size_t count = (size_t)n * nblk;
+        const j2k_ht_cblk* src = cblks + (size_t)f0 * nblk;
+        unsigned long long lo = ~0ull, hi = 0;
+        for (size_t i = 0; i < count; i++)
+            if (src[i].length) {
+                if (src[i].offset < lo) lo = src[i].offset;
+                if (src[i].offset + src[i].length > hi) hi = src[i].offset + src[i].length;
+            }
+        if (hi == 0) lo = 0;
+        std::vector<HtBlock>& r = recs[di];
+        r.resize(count);
+        for (size_t i = 0; i < count; i++) {
+            r[i].offset = src[i].length ? src[i].offset - lo : 0;
+            r[i].length = src[i].length; r[i].kmax = src[i].kmax; r[i].mmsb = src[i].missing_msbs; r[i].reserved = 0;
+        }
+        BlockTable* BT = nullptr;
+        if ((rc = get_block_table(d, s, cbw, cbh, cpf, &BT))) break;
+        if ((rc = d.ht_bytes.ensure((size_t)(hi - lo) + 16))) break;
+        if ((rc = d.ht_desc.ensure(count * sizeof(HtBlock) + 16))) break;
+        if (status_out && (rc = d.ht_status.ensure(count * 4 + 16))) break;
+        DevBuf& coef = pixels_out ? d.in[0] : d.blk[0];
+        if ((rc = coef.ensure((size_t)n * cpf * 4))) break;
+        cudaStream_t st = d.s_main;
+        if (hi > lo) CK(cudaMemcpyAsync(d.ht_bytes.p, bytes + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d.ht_desc.p, r.data(), count * sizeof(HtBlock), cudaMemcpyHostToDevice, st));
+        if ((rc = launch_ht_decode(ctx, *BT, cbw, cbh, n, (const unsigned char*)d.ht_bytes.p, (const HtBlock*)d.ht_desc.p, (int32_t*)coef.p,
+                                   pixels_out ? 1 : 0, status_out ? (int32_t*)d.ht_status.p : nullptr, st))) break;
+        if (status_out) CK(cudaMemcpyAsync(status_out + (size_t)f0 * nblk, d.ht_status.p, count * 4, cudaMemcpyDeviceToHost, st));
+        if (!pixels_out) {
+            CK(cudaMemcpyAsync(blocks_out + (size_t)f0 * cpf, coef.p, (size_t)n * cpf * 4, cudaMemcpyDeviceToHost, st));
+            continue;
+        }
+        if ((rc = d.out[0].ensure((size_t)n * pixb))) break;
+        if (planes_out && (rc = d.planes[0].ensure((size_t)n * cpf * 4))) break;
+        Plan* P = nullptr;
+        if ((rc = get_plan(d, s, p, sizeof *p, n, (long long)(pixb / bps), &P))) break;
+        rc = run_plan(ctx, *P, d.out[0].p, d.in[0].p, planes_out ? d.planes[0].p : nullptr, false, st);
+        if (rc < 0) break;
+        rc = 0;
+        unsigned char* hp = (unsigned char*)pixels_out + (size_t)f0 * frame_stride_bytes;
+        if (frame_stride_bytes == pixb) CK(cudaMemcpyAsync(hp, d.out[0].p, (size_t)n * pixb, cudaMemcpyDeviceToHost, st));
+        else CK(cudaMemcpy2DAsync(hp, frame_stride_bytes, d.out[0].p, pixb, pixb, n, cudaMemcpyDeviceToHost, st));
+        if (planes_out) CK(cudaMemcpyAsync(planes_out + (size_t)f0 * cpf, d.planes[0].p, (size_t)n * cpf * 4, cudaMemcpyDeviceToHost, st));
+    }
+    for (int di = 0; di < used; di++) {
+        int r2 = sync_dev(ctx, di);
+        if (rc == 0) rc = r2;
+    }
+    return rc;
+}
+
+int j2k_ht_decode_blocks(j2k_ctx* ctx, const j2k_inv_params* p, int cb_width, int cb_height, int nframes, const uint8_t* bytes,
+                         size_t nbytes, const j2k_ht_cblk* cblks, int32_t* blocks_out, int32_t* status_out) {
+    CtxGuard cg_(ctx);
+    if (!blocks_out) return fail(J2K_ERR_INVALID_ARG, "NULL buffer");
+    return ht_host_run(ctx, p, cb_width, cb_height, nframes, bytes, nbytes, cblks, blocks_out, nullptr, 0, nullptr, status_out);
+}
+
+int j2k_inverse_ht(j2k_ctx* ctx, const j2k_inv_params* p, int cb_width, int cb_height, int nframes, const uint8_t* bytes, size_t nbytes,
+                   const j2k_ht_cblk* cblks, void* pixels_out, size_t frame_stride_bytes, int32_t* planes_out, int32_t* status_out) {
+    CtxGuard cg_(ctx);
+    if (!pixels_out) return fail(J2K_ERR_INVALID_ARG, "NULL buffer");
+    return ht_host_run(ctx, p, cb_width, cb_height, nframes, bytes, nbytes, cblks, nullptr, pixels_out, frame_stride_bytes, planes_out,
+                       status_out);
+}
+
+int j2k_ht_decode_device(j2k_ctx* ctx, int dev, const j2k_inv_params* p, int cb_width, int cb_height, int nframes, const uint8_t* d_bytes,
+                         const j2k_ht_cblk* d_cblks, int32_t* d_out, int to_planes, int32_t* d_status, void* cuda_stream) {
+    CtxGuard cg_(ctx);
+    int rc = set_dev(ctx, dev);
+    if (rc) return rc;
+    if (!p) return fail(J2K_ERR_INVALID_ARG, "params is NULL");
+    if ((rc = validate_ht_cb(cb_width, cb_height))) return rc;
+    Spec s;
+    if ((rc = spec_from_inv(p, false, s))) return rc;
+    if (!d_bytes || !d_cblks || !d_out || nframes <= 0) return fail(J2K_ERR_INVALID_ARG, "bad device buffers / nframes");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceCtx& d = ctx->devs[dev];
+    BlockTable* BT = nullptr;
+    if ((rc = get_block_table(d, s, cb_width, cb_height, (long long)j2k_inv_coeff_count(p), &BT))) return rc;
+    return launch_ht_decode(ctx, *BT, cb_width, cb_height, nframes, d_bytes, (const HtBlock*)d_cblks, d_out, to_planes ? 1 : 0, d_status,
+                            cuda_stream ? (cudaStream_t)cuda_stream : d.s_main);
 }
 
 // ---- asynchronous

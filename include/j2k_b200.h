@@ -335,6 +335,54 @@ int j2k_scatter_blocks_roi_general_device(j2k_ctx* ctx, int dev, const j2k_inv_p
                                           const int32_t* d_blocks, const int32_t* roi_maxshift, const int32_t* d_block_scale_shift,
                                           const uint8_t* d_sample_mask, int32_t* d_coeffs, void* cuda_stream);
 
+/* ------------------------------- HTJ2K block decoding on the device (decode side) */
+
+/* One HT code-block as T2 leaves it (cbInfo, jpeg2000/t2/tile_decoder.go:453-526): where its cleanup segment lies in the
+ * caller's byte stream and the two facts HTDecoder.SetCodingContext receives (jpeg2000/htj2k/decoder.go:92-96, set at
+ * t2/tile_decoder.go:601-609).  One record per (frame, block) in the order of the code-block interface: frame-major, then
+ * tiles (raster), components, j2k_codeblock_layout order. */
+typedef struct j2k_ht_cblk {
+    uint64_t offset;        /* first byte of the segment in `bytes`                                                   */
+    uint32_t length;        /* Lcup, bytes of the cleanup segment; 0 = block not included / no data: zero coefficients
+                             * (HTDecoder.Decode, decoder.go:44-46; shouldDecode, t2/tile_decoder.go:672-689)          */
+    uint8_t kmax;           /* bandNumbps of the block's sub-band (bandNumbpsFromQCD, t2/bitplane.go:22-61)           */
+    uint8_t missing_msbs;   /* zero bit-planes from the packet header (htj2kMissingMSBs, t2/tile_decoder.go:691-699)  */
+    uint16_t reserved;
+} j2k_ht_cblk;
+
+/* Per-block result codes in `status_out` (optional, one int32 per record).  A failing block decodes to zeros, which is what
+ * TileDecoder.decodeCodeBlock substitutes when the block decoder returns an error (t2/tile_decoder.go:718-721); the call
+ * itself still returns J2K_OK. */
+#define J2K_HT_OK 0
+#define J2K_HT_ERR_KMAX (-1)     /* "HTJ2K OpenJPH cleanup decoding requires band precision context" (decoder.go:48-50)        */
+#define J2K_HT_ERR_SEGMENT (-2)  /* missing MSBs >= 30 or an invalid Scup locator (openjph_cleanup_decoder.go:122-127, decoder.go:63-65) */
+#define J2K_HT_ERR_UQ (-3)       /* "U_q exceeds missing_msbs+2" (openjph_cleanup_decoder.go:292-294,333-335)                   */
+
+/* HTDecoder.Decode (jpeg2000/htj2k/decoder.go:43-58 -> decodeOpenJPHCleanup, openjph_cleanup_decoder.go:115-161) for every
+ * code-block of nframes frames: `blocks_out` receives the block-major planes j2k_inverse_blocks consumes.  HT code-blocks
+ * hold at most 4096 samples (cb_width * cb_height <= 4096, ISO/IEC 15444-15); larger sizes return J2K_ERR_UNSUPPORTED.
+ * Only the cleanup pass is decoded, as in the reference (SigProp / MagRef segments are ignored there too). */
+int j2k_ht_decode_blocks(j2k_ctx* ctx, const j2k_inv_params* p, int cb_width, int cb_height, int nframes, const uint8_t* bytes,
+                         size_t nbytes, const j2k_ht_cblk* cblks, int32_t* blocks_out, int32_t* status_out);
+
+/* The whole decode tail on the device: HT block decoding written straight into the coefficient planes (assembleSubbands,
+ * t2/tile_decoder.go:840-883, fused into the decoder's stores), then everything j2k_inverse_batch does.  Compressed bytes go
+ * up, pixels come down.  p->htj2k should be set (HT blocks carry no T1 fixed point; no "/2", tile_decoder.go:732-734). */
+int j2k_inverse_ht(j2k_ctx* ctx, const j2k_inv_params* p, int cb_width, int cb_height, int nframes, const uint8_t* bytes,
+                   size_t nbytes, const j2k_ht_cblk* cblks, void* pixels_out, size_t frame_stride_bytes, int32_t* planes_out,
+                   int32_t* status_out);
+
+/* Device-resident form: `d_bytes`, `d_cblks` (nframes x blocks records), `d_out` and `d_status` (optional) are device
+ * pointers; to_planes = 1 writes Mallat coefficient planes (input of j2k_inverse_device), 0 block-major planes.  Offsets and
+ * lengths in device memory cannot be checked against the stream size: the caller guarantees offset + length <= nbytes. */
+int j2k_ht_decode_device(j2k_ctx* ctx, int dev, const j2k_inv_params* p, int cb_width, int cb_height, int nframes,
+                         const uint8_t* d_bytes, const j2k_ht_cblk* d_cblks, int32_t* d_out, int to_planes, int32_t* d_status,
+                         void* cuda_stream);
+
+/* The packed decode tables the device decoder indexes (which: 0 VLC initial row, 1 VLC other rows, 2 UVLC initial, 3 UVLC
+ * other rows; vlc_tables.go:862-925, uvlc_tables.go:30-143); returns the entry count, copies them when out != NULL. */
+int j2k_ht_table(int which, uint16_t* out);
+
 /* -------------------------------------------- wavelet package API (in place) */
 
 /* wavelet.ForwardMultilevelWithParity / InverseMultilevelWithParity

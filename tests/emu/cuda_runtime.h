@@ -83,6 +83,8 @@ template <typename T> static inline T __shfl_sync(unsigned, T v, int src) {
     T r; memcpy(&r, &b, 4); return r;
 }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
+static inline unsigned atomicOr(unsigned* p, unsigned v) { unsigned o = *p; *p = o | v; return o; }
+static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 static inline void __threadfence() {}
 static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) {
     sh &= 31;
