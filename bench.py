@@ -351,6 +351,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
     ap.add_argument("--sustained-seconds", type=float, default=3.0, help="length of the sustained-load leg (0 = skip)")
     ap.add_argument("--no-configs", action="store_true", help="skip the legs of the other BASELINE configs (C1, C3, C4, C5)")
+    ap.add_argument("--no-ht", action="store_true", help="skip the HTJ2K block-decoding leg")
     ap.add_argument("--config-steps", type=int, default=20, help="timed launches per direction of each of the other configs")
     args = ap.parse_args()
     protect_stdout()
@@ -572,6 +573,106 @@ def main():
                       "what": "gather: sub-band extraction + code-block partition + numbps (encoder.go:3059-3285,3349-3362); "
                               "scatter: assembleSubbands (t2/tile_decoder.go:840-883); 8 B/sample each, resident"}
 
+    # ---- HTJ2K block decoding on the device (decode side): C2-shaped frames assembled from the committed
+    # fixture of HT-coded 64 x 64 blocks (tests/golden/ht_blocks_64.npz, made by tools/make_ht_fixture.py); resident = the two
+    # HT kernels (+ the inverse plan behind them); end to end = cleanup segments up, pixels down, against the same frames
+    # crossing PCIe as int32 coefficient planes (j2k_submit_inverse).
+    ht_leg = None
+    fixture = os.path.join(ROOT, "tests", "golden", "ht_blocks_64.npz")
+    if not args.no_ht and not args.no_inverse and os.path.exists(fixture):
+        fx = np.load(fixture)
+        nfx = len(fx["offsets"])
+        nblk = int(ctx.lib.j2k_fwd_block_count(C.byref(fp), 64, 64))
+        Bh = max(1, min(B, 8))   # frames per step of this leg
+        iph = abi.inv_params(W, H, 1, BITS, False, num_levels=LEVELS, reversible=False, htj2k=True,
+                             steps=j2kb200.decode_quant_steps(enc, LEVELS, BITS, False))
+        lay = ctx.codeblock_layout(W, H, LEVELS, 64, 64)
+        assert all(b.width == 64 and b.height == 64 for b in lay) and len(lay) == nblk
+        sel = (np.arange(Bh * nblk, dtype=np.int64) * 7 + np.arange(Bh * nblk) // nblk) % nfx   # fixture block of (frame, block)
+        lens = fx["lengths"][sel].astype(np.uint32)
+        offs = np.concatenate([[0], np.cumsum(lens, dtype=np.uint64)[:-1]]).astype(np.uint64)
+        segs = [fx["stream"][int(o):int(o) + int(n)] for o, n in zip(fx["offsets"], fx["lengths"])]
+        h_stream = ctx.pinned(int(lens.sum()) + 16)
+        h_stream[:int(lens.sum())] = np.concatenate([segs[i] for i in sel])
+        rec = j2kb200.Context.ht_records(offs, lens, fx["kmax"][sel], fx["mmsb"][sel])
+        # expected coefficient planes of frame 0 from the fixture's stored coefficients
+        want0 = np.empty((H, W), np.int32)
+        for b, i in zip(lay, sel[:nblk]):
+            want0[b.y0:b.y0 + 64, b.x0:b.x0 + 64] = fx["coeffs"][i]
+        d_bytes = torch.from_numpy(np.asarray(h_stream)).cuda()
+        d_rec = torch.from_numpy(rec.view(np.uint8)).cuda()
+        d_co = torch.empty((Bh, PIX), dtype=torch.int32, device="cuda")
+        d_px = torch.empty((Bh, frame_bytes), dtype=torch.uint8, device="cuda")
+        s0 = streams[0].cuda_stream
+
+        def ht_only():
+            ctx.ht_decode_device(iph, Bh, C.c_void_p(d_bytes.data_ptr()), C.c_void_p(d_rec.data_ptr()), C.c_void_p(d_co.data_ptr()), True,
+                                 stream=C.c_void_p(s0))
+
+        def ht_full():
+            ht_only()
+            ctx.inverse_device(iph, Bh, d_co.data_ptr(), d_px.data_ptr(), frame_bytes, stream=s0)
+
+        def timed_ht(fn, n):
+            for _ in range(warm):
+                fn()
+            barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(streams[0])
+            for _ in range(n):
+                fn()
+            a1.record(streams[0])
+            barrier()
+            t = torch.tensor([a0.elapsed_time(a1)], device="cuda")
+            if use_dist:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item()) / n
+
+        nst = max(5, min(args.steps, 20))
+        ht_ms = timed_ht(ht_only, nst)
+        full_ms = timed_ht(ht_full, nst)
+        decoded_ok = bool(np.array_equal(d_co[0].cpu().numpy().reshape(H, W), want0))
+        # end to end, pinned buffers, two tickets in flight: HT segments up vs int32 planes up, pixels down in both
+        h_px = [ctx.pinned(Bh * frame_bytes).reshape(Bh, frame_bytes) for _ in range(2)]
+        h_co = ctx.pinned(Bh * PIX * 4, np.int32).reshape(Bh, PIX)
+        h_co[:] = d_co.cpu().numpy()
+
+        def e2e_loop(submit, n):
+            ctx.wait(submit(0)); ctx.wait(submit(1))
+            barrier()
+            t0 = time.perf_counter()
+            prev = submit(0)
+            for i in range(1, n):
+                cur = submit(i & 1)
+                ctx.wait(prev)
+                prev = cur
+            ctx.wait(prev)
+            t = torch.tensor([time.perf_counter() - t0], device="cuda")
+            if use_dist:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item()) / n
+
+        ne = max(3, min(args.steps, 10))
+        dt_ht = e2e_loop(lambda k: ctx.submit_inverse_ht(iph, Bh, h_stream, rec, h_px[k]), ne)
+        px_ht = np.array(h_px[0][Bh - 1])
+        dt_pl = e2e_loop(lambda k: ctx.submit_inverse(iph, h_co, h_px[k]), ne)
+        same_px = bool(np.array_equal(px_ht, np.asarray(h_px[0][Bh - 1])) and np.array_equal(px_ht, d_px[Bh - 1].cpu().numpy()))
+        ht_leg = {"frames_per_step": Bh, "blocks_per_frame": nblk, "code_block": [64, 64],
+                  "compressed_bytes_per_frame": int(lens.sum()) // Bh, "bits_per_sample": float(lens.sum()) * 8 / (Bh * PIX),
+                  "ht_decode_ms": ht_ms, "ht_decode_Mpixel_s": world * Bh * PIX / (ht_ms * 1e-3) / 1e6,
+                  "ht_decode_plus_inverse_ms": full_ms, "ht_decode_plus_inverse_Mpixel_s": world * Bh * PIX / (full_ms * 1e-3) / 1e6,
+                  "decoded_matches_fixture": decoded_ok,
+                  "e2e": {"value": world * Bh * PIX / dt_ht / 1e6, "unit": "Mpixel/s", "h2d_bytes_per_step": int(lens.sum()) + int(rec.nbytes),
+                          "d2h_bytes_per_step": Bh * frame_bytes, "api": "j2k_submit_inverse_ht / j2k_wait, two steps in flight, pinned buffers"},
+                  "e2e_planes": {"value": world * Bh * PIX / dt_pl / 1e6, "unit": "Mpixel/s", "h2d_bytes_per_step": Bh * PIX * 4,
+                                 "d2h_bytes_per_step": Bh * frame_bytes, "api": "j2k_submit_inverse (int32 coefficient planes up), same frames"},
+                  "pixels_identical": same_px,
+                  "what": "HTDecoder.Decode (htj2k/decoder.go:43-58) for every code-block + assembleSubbands + inverse 9/7 path on the device; "
+                          "frames assembled from tests/golden/ht_blocks_64.npz (256 HT-coded blocks of a C2 frame, cyclic)"}
+        for a in [h_stream, h_co] + h_px:
+            ctx.release(a)
+        del d_bytes, d_rec, d_co, d_px
+
     # ---- sustained load: the same resident step for a few seconds.  The K-step region above is a burst (tens of ms at
     # boost clocks); held for seconds the board reaches its power limit and the SM clock settles lower, which this
     # co-limited kernel feels.  Reported next to `value`, never instead of it.
@@ -717,7 +818,7 @@ def main():
             "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": workload_config(B, world, NS),
-            "roofline": roofline, "sustained": sustained, "inverse": inverse, "configs": configs, "code_blocks": blocks_leg,
+            "roofline": roofline, "sustained": sustained, "inverse": inverse, "configs": configs, "code_blocks": blocks_leg, "ht_decode": ht_leg,
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": "Mpixel/s", "h2d_bytes_per_step": B * frame_bytes, "d2h_bytes_per_step": B * PIX * 4,
                     "steps": e2e_steps, "matches_resident": same, "sync_value": e2e_sync,

@@ -237,7 +237,9 @@ struct DeviceCtx {
     DevBuf in[2], out[2], planes[2], api[8];
     DevBuf blk[2], nbp[2];  // code-block interface: block-major planes and per-block numbps of a sub-batch
     DevBuf gsh[2], gmk[2];  // general-scaling ROI of a sub-batch: per-block shifts, per-sample mask
-    DevBuf ht_bytes, ht_desc, ht_status;  // HTJ2K block decoding: cleanup segments, descriptors, per-block result codes
+    DevBuf ht_bytes[2], ht_desc[2], ht_status[2];  // HTJ2K block decoding of a sub-batch: cleanup segments, records, result codes
+    DevBuf ht_scratch;                             // (inf, u_q) per quad between the two HT kernels
+    cudaEvent_t ev_ht = nullptr; bool ev_ht_used = false;
     std::map<std::string, std::unique_ptr<Plan>> plans;
     long long use_clock = 0;   // LRU stamps of `plans`
     std::map<std::string, std::unique_ptr<struct BlockTable>> block_tables;
@@ -1816,22 +1818,30 @@ int validate_ht_cb(int cbw, int cbh) {
     return 0;
 }
 
-// One warp per code-block (j2k_ht.cuh); to_planes: decoded samples go straight into the Mallat planes (assembleSubbands).
-int launch_ht_decode(j2k_ctx* ctx, BlockTable& T, int cbw, int cbh, int nframes, const unsigned char* d_bytes, const HtBlock* d_descs,
-                     int32_t* d_out, int to_planes, int32_t* d_status, cudaStream_t st) {
+// Two launches (j2k_ht.cuh): VLC / MEL / UVLC with one thread per code-block into the device's scratch (4 B per quad), then
+// MagSgn with one warp per code-block; to_planes: decoded samples go straight into the Mallat planes (assembleSubbands).
+// The scratch is one buffer per device: a launch on another stream waits for the previous one's MagSgn kernel.
+int launch_ht_decode(j2k_ctx* ctx, DeviceCtx& d, BlockTable& T, int cbw, int cbh, int nframes, const unsigned char* d_bytes,
+                     const HtBlock* d_descs, int32_t* d_out, int to_planes, int32_t* d_status, cudaStream_t st) {
     const long long total = (long long)T.nblocks * nframes;
     if (total <= 0) return 0;
-    const int warps = 4;
-    const int wsm = ht_warp_smem(cbw, cbh);
-    const int smem = warps * wsm;
-#ifndef J2K_EMU
-    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(ht_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-#endif
-    const unsigned grid = (unsigned)((total + warps - 1) / warps);
-    J2K_LAUNCH_SMEM(ht_decode_kernel, grid, warps * 32, smem, st, d_bytes, d_descs, (const BlockEntry*)T.tab.p, T.nblocks, total,
-                    T.coeffs_per_frame, (int*)d_out, to_planes, (int*)d_status, wsm);
+    const int scw = ht_scratch_words(cbw, cbh), qs = (cbw + 1) / 2;
+    int rc = d.ht_scratch.ensure((size_t)total * scw * 4 + 16);
+    if (rc) return rc;
+    if (!d.ev_ht) CK(cudaEventCreateWithFlags(&d.ev_ht, cudaEventDisableTiming));
+    if (d.ev_ht_used) CK(cudaStreamWaitEvent(st, d.ev_ht, 0));
+    J2K_LAUNCH(ht_vlc_kernel, (unsigned)((total + 31) / 32), 32, st, d_bytes, d_descs, (const BlockEntry*)T.tab.p, T.nblocks, total,
+               (unsigned*)d.ht_scratch.p, scw, qs);
     CK(cudaGetLastError());
-    ctx->launches++;
+    const int warps = 4;
+    const int wsm = ht_warp_smem(cbw);
+    J2K_LAUNCH_SMEM(ht_magsgn_kernel, (unsigned)((total + warps - 1) / warps), warps * 32, warps * wsm, st, d_bytes, d_descs,
+                    (const BlockEntry*)T.tab.p, T.nblocks, total, T.coeffs_per_frame, (const unsigned*)d.ht_scratch.p, scw, qs, (int*)d_out,
+                    to_planes, (int*)d_status, wsm);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(d.ev_ht, st));
+    d.ev_ht_used = true;
+    ctx->launches += 2;
     return 0;
 }
 
@@ -2103,6 +2113,8 @@ struct HostJob {
     RoiShifts roi{};             // inverse, block mode: per-component MaxShift applied while scattering
     const int32_t* h_block_shift = nullptr;      // inverse, block mode: general-scaling shift per (frame, block), or NULL
     const unsigned char* h_sample_mask = nullptr; // and its optional per-sample mask (block-major, one byte per coefficient)
+    // inverse, block mode, HTJ2K: the blocks arrive as HT cleanup segments and are decoded on the device (j2k_inverse_ht)
+    const unsigned char* h_ht_bytes = nullptr; const j2k_ht_cblk* h_ht_recs = nullptr; int32_t* h_ht_status = nullptr;
 };
 
 int enqueue_host_job(j2k_ctx* ctx, int di, const HostJob& J, int f0, int f1, bool timing) {
@@ -2124,9 +2136,10 @@ int enqueue_host_job(j2k_ctx* ctx, int di, const HostJob& J, int f0, int f1, boo
     if (timing) CK(cudaEventRecord(d.ev_t[0], d.s_h2d));
     // caller-owned pageable memory (a Go slice, a numpy array) moves through the pinned staging ring; pinned buffers
     // (j2k_acquire_buffer) are handed to the copy engine as they are
-    const bool page_in = !host_pinned(J.fwd ? (const void*)J.h_pix_in : (const void*)J.h_coef_in);
+    const bool page_in = !host_pinned(J.fwd ? (const void*)J.h_pix_in : J.h_ht_recs ? (const void*)J.h_ht_bytes : (const void*)J.h_coef_in);
     const bool page_out = !host_pinned(J.fwd ? (const void*)J.h_coef_out : (const void*)J.h_pix_out) ||
-                          (J.h_planes && !host_pinned(J.h_planes)) || (J.h_numbps && !host_pinned(J.h_numbps));
+                          (J.h_planes && !host_pinned(J.h_planes)) || (J.h_numbps && !host_pinned(J.h_numbps)) ||
+                          (J.h_ht_status && !host_pinned(J.h_ht_status));
     if ((page_in || page_out) && !J.may_stage)
         return fail(J2K_ERR_INVALID_ARG, "asynchronous calls need buffers from j2k_acquire_buffer (pinned); this one is pageable");
     auto up = [&](void* dst, const unsigned char* src, size_t bytes) -> int {
@@ -2151,7 +2164,7 @@ int enqueue_host_job(j2k_ctx* ctx, int di, const HostJob& J, int f0, int f1, boo
         BlockTable* BT = nullptr;
         if (J.cb_w > 0) {
             if ((rc = get_block_table(d, s, J.cb_w, J.cb_h, J.coeffs_per_frame, &BT))) return rc;
-            if ((rc = d.blk[slot].ensure((size_t)nb * J.coeffs_per_frame * 4))) return rc;
+            if (!J.h_ht_recs && (rc = d.blk[slot].ensure((size_t)nb * J.coeffs_per_frame * 4))) return rc;
             if (J.fwd && (rc = d.nbp[slot].ensure((size_t)nb * BT->nblocks * 4 + 16))) return rc;
         }
         // the slot's previous kernel must have consumed `in`, its previous D2H must have drained `out`
@@ -2168,6 +2181,28 @@ int enqueue_host_job(j2k_ctx* ctx, int di, const HostJob& J, int f0, int f1, boo
                 CK(cudaMemcpy2DAsync(d.in[slot].p, J.pix_bytes_per_frame, J.h_pix_in + (size_t)b * J.frame_stride_bytes, J.frame_stride_bytes,
                                      J.pix_bytes_per_frame, nb, cudaMemcpyHostToDevice, d.s_h2d));
             }
+        } else if (J.h_ht_recs) {
+            // this sub-batch's cleanup segments (the byte range its records span) and the records, re-based to that range
+            const size_t count = (size_t)nb * BT->nblocks;
+            const j2k_ht_cblk* src = J.h_ht_recs + (size_t)b * BT->nblocks;
+            unsigned long long lo = ~0ull, hi = 0;
+            for (size_t i = 0; i < count; i++)
+                if (src[i].length) {
+                    if (src[i].offset < lo) lo = src[i].offset;
+                    if (src[i].offset + src[i].length > hi) hi = src[i].offset + src[i].length;
+                }
+            if (hi == 0) lo = 0;
+            std::vector<HtBlock> r(count);
+            for (size_t i = 0; i < count; i++) {
+                r[i].offset = src[i].length ? src[i].offset - lo : 0;
+                r[i].length = src[i].length; r[i].kmax = src[i].kmax; r[i].mmsb = src[i].missing_msbs; r[i].reserved = 0;
+            }
+            if ((rc = d.ht_bytes[slot].ensure((size_t)(hi - lo) + 16))) return rc;
+            if ((rc = d.ht_desc[slot].ensure(count * sizeof(HtBlock) + 16))) return rc;
+            if (J.h_ht_status && (rc = d.ht_status[slot].ensure(count * 4 + 16))) return rc;
+            if (hi > lo && (rc = up(d.ht_bytes[slot].p, J.h_ht_bytes + lo, (size_t)(hi - lo)))) return rc;
+            // the re-based records live in `r`: always through the pinned staging ring, which copies them before it returns
+            if ((rc = stage_up(ctx, d, d.ht_desc[slot].p, (const unsigned char*)r.data(), count * sizeof(HtBlock)))) return rc;
         } else {
             if ((rc = up(BT ? d.blk[slot].p : d.in[slot].p, (const unsigned char*)(J.h_coef_in + (size_t)b * J.coeffs_per_frame), in_bytes))) return rc;
         }
@@ -2178,7 +2213,11 @@ int enqueue_host_job(j2k_ctx* ctx, int di, const HostJob& J, int f0, int f1, boo
         long long fs = J.fwd ? (J.planar ? 0 : (long long)(J.pix_bytes_per_frame / (s.bit_depth <= 8 ? 1 : 2))) : (long long)(J.pix_bytes_per_frame / (s.bit_depth <= 8 ? 1 : 2));
         if ((rc = get_plan(d, s, J.pblob, J.pbytes, nb, fs, &P))) return rc;
         if (timing && it == 0) CK(cudaEventRecord(d.ev_t[1], d.s_main));
-        if (!J.fwd && BT) {
+        if (!J.fwd && BT && J.h_ht_recs) {
+            // HT block decoding straight into the coefficient planes (assembleSubbands fused into the decoder's stores)
+            if ((rc = launch_ht_decode(ctx, d, *BT, J.cb_w, J.cb_h, nb, (const unsigned char*)d.ht_bytes[slot].p, (const HtBlock*)d.ht_desc[slot].p,
+                                       (int32_t*)d.in[slot].p, 1, J.h_ht_status ? (int32_t*)d.ht_status[slot].p : nullptr, d.s_main))) return rc;
+        } else if (!J.fwd && BT) {
             RoiShifts roi = J.roi;
             if (J.h_block_shift) {  // general scaling: this sub-batch's per-block shifts (and mask) go up behind the blocks
                 const size_t nsh = (size_t)nb * BT->nblocks * 4;
@@ -2222,6 +2261,7 @@ int enqueue_host_job(j2k_ctx* ctx, int di, const HostJob& J, int f0, int f1, boo
                                      J.pix_bytes_per_frame, nb, cudaMemcpyDeviceToHost, d.s_d2h));
             }
             if (J.h_planes && (rc = down(J.h_planes + (size_t)b * s.C * HW, d.planes[slot].p, (size_t)nb * s.C * HW * 4))) return rc;
+            if (J.h_ht_status && (rc = down(J.h_ht_status + (size_t)b * BT->nblocks, d.ht_status[slot].p, (size_t)nb * BT->nblocks * 4))) return rc;
         }
         if (!page_out) {
             CK(cudaEventRecord(d.ev_out[slot], d.s_d2h));
@@ -2369,6 +2409,7 @@ void j2k_shutdown(j2k_ctx* ctx) {
         for (auto& b : d.api) b.release();
         for (auto& ev : d.ev_t) if (ev) cudaEventDestroy(ev);
         for (int k = 0; k < 2; k++) { cudaEventDestroy(d.ev_in[k]); cudaEventDestroy(d.ev_k[k]); cudaEventDestroy(d.ev_out[k]); }
+        if (d.ev_ht) cudaEventDestroy(d.ev_ht);
         cudaStreamDestroy(d.s_main); cudaStreamDestroy(d.s_h2d); cudaStreamDestroy(d.s_d2h);
     }
     pool_stop(ctx);
@@ -2776,28 +2817,37 @@ int j2k_ht_table(int which, uint16_t* out) {
     return n;
 }
 
-// Host form of both HT entry points: cleanup segments + records up, HT decode (-> block-major planes, or -> coefficient planes
-// followed by the inverse plan), results down.  Frames are sharded over the context's devices in contiguous blocks.
-static int ht_host_run(j2k_ctx* ctx, const j2k_inv_params* p, int cbw, int cbh, int nframes, const uint8_t* bytes, size_t nbytes,
-                       const j2k_ht_cblk* cblks, int32_t* blocks_out, void* pixels_out, size_t frame_stride_bytes, int32_t* planes_out,
-                       int32_t* status_out) {
+static int64_t make_ticket(j2k_ctx* ctx, const std::vector<int>& used);
+
+// Argument checks shared by the HT entry points; fills the geometry they need.
+static int ht_check(j2k_ctx* ctx, const j2k_inv_params* p, int cbw, int cbh, int nframes, const uint8_t* bytes, size_t nbytes,
+                    const j2k_ht_cblk* cblks, bool want_planes, Spec& s, size_t& nblk) {
     if (!ctx) return fail(J2K_ERR_INVALID_ARG, "context is NULL");
     if (!p) return fail(J2K_ERR_INVALID_ARG, "params is NULL");
     int rc = validate_ht_cb(cbw, cbh);
     if (rc) return rc;
-    Spec s;
-    if ((rc = spec_from_inv(p, planes_out != nullptr, s))) return rc;
-    if (!cblks || (!bytes && nbytes) || (!blocks_out && !pixels_out)) return fail(J2K_ERR_INVALID_ARG, "NULL buffer");
+    if ((rc = spec_from_inv(p, want_planes, s))) return rc;
+    if (!cblks || (!bytes && nbytes)) return fail(J2K_ERR_INVALID_ARG, "NULL buffer");
     if (nframes <= 0) return fail(J2K_ERR_INVALID_ARG, "nframes must be positive");
-    const long long cpf = (long long)j2k_inv_coeff_count(p);
-    const size_t nblk = j2k_inv_block_count(p, cbw, cbh);
-    const size_t pixb = j2k_inv_pixel_bytes(p);
-    const int bps = s.bit_depth <= 8 ? 1 : 2;
-    if (pixels_out && (frame_stride_bytes < pixb || frame_stride_bytes % bps)) return fail(J2K_ERR_SIZE, "bad frame stride");
+    nblk = j2k_inv_block_count(p, cbw, cbh);
     for (size_t i = 0; i < nblk * (size_t)nframes; i++)
         if (cblks[i].length && (cblks[i].offset > nbytes || cblks[i].length > nbytes - cblks[i].offset))
             return fail(J2K_ERR_SIZE, "code-block %zu: segment [%llu, +%u) lies outside the %zu-byte stream", i,
                         (unsigned long long)cblks[i].offset, cblks[i].length, nbytes);
+    return 0;
+}
+
+// HTDecoder.Decode for every block, block-major planes back to the host (the code-block interface's layout): cleanup segments
+// and records up, one launch, planes down.  Frames are sharded over the context's devices in contiguous blocks.
+int j2k_ht_decode_blocks(j2k_ctx* ctx, const j2k_inv_params* p, int cb_width, int cb_height, int nframes, const uint8_t* bytes,
+                         size_t nbytes, const j2k_ht_cblk* cblks, int32_t* blocks_out, int32_t* status_out) {
+    CtxGuard cg_(ctx);
+    Spec s;
+    size_t nblk = 0;
+    int rc = ht_check(ctx, p, cb_width, cb_height, nframes, bytes, nbytes, cblks, false, s, nblk);
+    if (rc) return rc;
+    if (!blocks_out) return fail(J2K_ERR_INVALID_ARG, "NULL buffer");
+    const long long cpf = (long long)j2k_inv_coeff_count(p);
     std::lock_guard<std::mutex> lk(ctx->mu);
     const int nd = (int)ctx->devs.size();
     const int per = (nframes + nd - 1) / nd;
@@ -2826,33 +2876,18 @@ static int ht_host_run(j2k_ctx* ctx, const j2k_inv_params* p, int cbw, int cbh, 
             r[i].length = src[i].length; r[i].kmax = src[i].kmax; r[i].mmsb = src[i].missing_msbs; r[i].reserved = 0;
         }
         BlockTable* BT = nullptr;
-        if ((rc = get_block_table(d, s, cbw, cbh, cpf, &BT))) break;
-        if ((rc = d.ht_bytes.ensure((size_t)(hi - lo) + 16))) break;
-        if ((rc = d.ht_desc.ensure(count * sizeof(HtBlock) + 16))) break;
-        if (status_out && (rc = d.ht_status.ensure(count * 4 + 16))) break;
-        DevBuf& coef = pixels_out ? d.in[0] : d.blk[0];
-        if ((rc = coef.ensure((size_t)n * cpf * 4))) break;
+        if ((rc = get_block_table(d, s, cb_width, cb_height, cpf, &BT))) break;
+        if ((rc = d.ht_bytes[0].ensure((size_t)(hi - lo) + 16))) break;
+        if ((rc = d.ht_desc[0].ensure(count * sizeof(HtBlock) + 16))) break;
+        if (status_out && (rc = d.ht_status[0].ensure(count * 4 + 16))) break;
+        if ((rc = d.blk[0].ensure((size_t)n * cpf * 4))) break;
         cudaStream_t st = d.s_main;
-        if (hi > lo) CK(cudaMemcpyAsync(d.ht_bytes.p, bytes + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(d.ht_desc.p, r.data(), count * sizeof(HtBlock), cudaMemcpyHostToDevice, st));
-        if ((rc = launch_ht_decode(ctx, *BT, cbw, cbh, n, (const unsigned char*)d.ht_bytes.p, (const HtBlock*)d.ht_desc.p, (int32_t*)coef.p,
-                                   pixels_out ? 1 : 0, status_out ? (int32_t*)d.ht_status.p : nullptr, st))) break;
-        if (status_out) CK(cudaMemcpyAsync(status_out + (size_t)f0 * nblk, d.ht_status.p, count * 4, cudaMemcpyDeviceToHost, st));
-        if (!pixels_out) {
-            CK(cudaMemcpyAsync(blocks_out + (size_t)f0 * cpf, coef.p, (size_t)n * cpf * 4, cudaMemcpyDeviceToHost, st));
-            continue;
-        }
-        if ((rc = d.out[0].ensure((size_t)n * pixb))) break;
-        if (planes_out && (rc = d.planes[0].ensure((size_t)n * cpf * 4))) break;
-        Plan* P = nullptr;
-        if ((rc = get_plan(d, s, p, sizeof *p, n, (long long)(pixb / bps), &P))) break;
-        rc = run_plan(ctx, *P, d.out[0].p, d.in[0].p, planes_out ? d.planes[0].p : nullptr, false, st);
-        if (rc < 0) break;
-        rc = 0;
-        unsigned char* hp = (unsigned char*)pixels_out + (size_t)f0 * frame_stride_bytes;
-        if (frame_stride_bytes == pixb) CK(cudaMemcpyAsync(hp, d.out[0].p, (size_t)n * pixb, cudaMemcpyDeviceToHost, st));
-        else CK(cudaMemcpy2DAsync(hp, frame_stride_bytes, d.out[0].p, pixb, pixb, n, cudaMemcpyDeviceToHost, st));
-        if (planes_out) CK(cudaMemcpyAsync(planes_out + (size_t)f0 * cpf, d.planes[0].p, (size_t)n * cpf * 4, cudaMemcpyDeviceToHost, st));
+        if (hi > lo) CK(cudaMemcpyAsync(d.ht_bytes[0].p, bytes + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d.ht_desc[0].p, r.data(), count * sizeof(HtBlock), cudaMemcpyHostToDevice, st));
+        if ((rc = launch_ht_decode(ctx, d, *BT, cb_width, cb_height, n, (const unsigned char*)d.ht_bytes[0].p, (const HtBlock*)d.ht_desc[0].p,
+                                   (int32_t*)d.blk[0].p, 0, status_out ? (int32_t*)d.ht_status[0].p : nullptr, st))) break;
+        if (status_out) CK(cudaMemcpyAsync(status_out + (size_t)f0 * nblk, d.ht_status[0].p, count * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(blocks_out + (size_t)f0 * cpf, d.blk[0].p, (size_t)n * cpf * 4, cudaMemcpyDeviceToHost, st));
     }
     for (int di = 0; di < used; di++) {
         int r2 = sync_dev(ctx, di);
@@ -2861,19 +2896,42 @@ static int ht_host_run(j2k_ctx* ctx, const j2k_inv_params* p, int cbw, int cbh, 
     return rc;
 }
 
-int j2k_ht_decode_blocks(j2k_ctx* ctx, const j2k_inv_params* p, int cb_width, int cb_height, int nframes, const uint8_t* bytes,
-                         size_t nbytes, const j2k_ht_cblk* cblks, int32_t* blocks_out, int32_t* status_out) {
-    CtxGuard cg_(ctx);
-    if (!blocks_out) return fail(J2K_ERR_INVALID_ARG, "NULL buffer");
-    return ht_host_run(ctx, p, cb_width, cb_height, nframes, bytes, nbytes, cblks, blocks_out, nullptr, 0, nullptr, status_out);
+// The decode tail on the device, on the pipelined host-batch path (sub-batches on three streams, pinned staging for pageable
+// callers): cleanup segments + records up, HT decode into the coefficient planes, the inverse plan, pixels down.
+static int inverse_ht_host(j2k_ctx* ctx, const j2k_inv_params* p, int cbw, int cbh, int nframes, const uint8_t* bytes, size_t nbytes,
+                           const j2k_ht_cblk* cblks, void* pixels_out, size_t frame_stride_bytes, int32_t* planes_out, int32_t* status_out,
+                           bool wait, std::vector<int>* used) {
+    Spec s;
+    size_t nblk = 0;
+    int rc = ht_check(ctx, p, cbw, cbh, nframes, bytes, nbytes, cblks, planes_out != nullptr, s, nblk);
+    if (rc) return rc;
+    if (!pixels_out) return fail(J2K_ERR_INVALID_ARG, "NULL buffer");
+    HostJob J{};
+    J.fwd = false; J.planar = false; J.spec = &s; J.pblob = p; J.pbytes = sizeof *p;
+    J.h_pix_out = (unsigned char*)pixels_out; J.h_planes = planes_out;
+    J.pix_bytes_per_frame = j2k_inv_pixel_bytes(p); J.coeffs_per_frame = (long long)j2k_inv_coeff_count(p);
+    J.frame_stride_bytes = frame_stride_bytes; J.cb_w = cbw; J.cb_h = cbh;
+    J.h_ht_bytes = bytes; J.h_ht_recs = cblks; J.h_ht_status = status_out;
+    if (frame_stride_bytes < J.pix_bytes_per_frame) return fail(J2K_ERR_SIZE, "frame stride smaller than a frame");
+    return run_host_batch(ctx, J, nframes, wait, used);
 }
 
 int j2k_inverse_ht(j2k_ctx* ctx, const j2k_inv_params* p, int cb_width, int cb_height, int nframes, const uint8_t* bytes, size_t nbytes,
                    const j2k_ht_cblk* cblks, void* pixels_out, size_t frame_stride_bytes, int32_t* planes_out, int32_t* status_out) {
     CtxGuard cg_(ctx);
-    if (!pixels_out) return fail(J2K_ERR_INVALID_ARG, "NULL buffer");
-    return ht_host_run(ctx, p, cb_width, cb_height, nframes, bytes, nbytes, cblks, nullptr, pixels_out, frame_stride_bytes, planes_out,
-                       status_out);
+    return inverse_ht_host(ctx, p, cb_width, cb_height, nframes, bytes, nbytes, cblks, pixels_out, frame_stride_bytes, planes_out, status_out,
+                           true, nullptr);
+}
+
+int64_t j2k_submit_inverse_ht(j2k_ctx* ctx, const j2k_inv_params* p, int cb_width, int cb_height, int nframes, const uint8_t* bytes,
+                              size_t nbytes, const j2k_ht_cblk* cblks, void* pixels_out, size_t frame_stride_bytes, int32_t* planes_out,
+                              int32_t* status_out) {
+    CtxGuard cg_(ctx);
+    std::vector<int> used;
+    int rc = inverse_ht_host(ctx, p, cb_width, cb_height, nframes, bytes, nbytes, cblks, pixels_out, frame_stride_bytes, planes_out, status_out,
+                             false, &used);
+    if (rc) return rc;
+    return make_ticket(ctx, used);
 }
 
 int j2k_ht_decode_device(j2k_ctx* ctx, int dev, const j2k_inv_params* p, int cb_width, int cb_height, int nframes, const uint8_t* d_bytes,
@@ -2890,7 +2948,7 @@ int j2k_ht_decode_device(j2k_ctx* ctx, int dev, const j2k_inv_params* p, int cb_
     DeviceCtx& d = ctx->devs[dev];
     BlockTable* BT = nullptr;
     if ((rc = get_block_table(d, s, cb_width, cb_height, (long long)j2k_inv_coeff_count(p), &BT))) return rc;
-    return launch_ht_decode(ctx, *BT, cb_width, cb_height, nframes, d_bytes, (const HtBlock*)d_cblks, d_out, to_planes ? 1 : 0, d_status,
+    return launch_ht_decode(ctx, d, *BT, cb_width, cb_height, nframes, d_bytes, (const HtBlock*)d_cblks, d_out, to_planes ? 1 : 0, d_status,
                             cuda_stream ? (cudaStream_t)cuda_stream : d.s_main);
 }
 

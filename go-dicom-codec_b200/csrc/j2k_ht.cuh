@@ -6,18 +6,22 @@
 // coefficient plane the inverse ring kernel reads (or into the block-major plane of the code-block interface).  What crosses
 // PCIe on the decode side is then the compressed cleanup segments + 16 bytes per block instead of 4 bytes per sample.
 //
-// ONE WARP per code-block, two phases:
-//   1. VLC / MEL / UVLC (openjph_cleanup_decoder.go:180-276): inherently serial (every codeword length depends on the
-//      context of the quads before it), so lane 0 walks the quad pairs and leaves (inf, u_q) per quad in shared memory --
-//      the `scratch` array of the reference, same layout.  The reverse VLC reader and the MEL reader follow
-//      vlc_reverse_decoder.go:18-100 and openjph_cleanup_decoder.go:25-101 (byte-wise instead of 4-byte chunks; the bit
-//      values are the same, see the notes at the readers).
-//   2. MagSgn (openjph_cleanup_decoder.go:278-372, :432-447): the number of bits of every sample is known once U_q is, and
-//      U_q of a quad row depends only on the row above (the exponent predictor), so a quad row is decoded by 32 lanes at once:
-//      one lane per quad, bit offsets by a warp prefix sum.  Random access into the MagSgn stream needs the byte-stuffing
-//      removed first: the warp un-stuffs 512 source bytes at a time (a byte after 0xFF carries 7 bits, magsgn.go:160-204;
-//      beyond the end the stream reads as 0xFF) into a 16 Kbit ring in shared memory, each lane depositing its 16 bytes at
-//      the bit position a prefix sum over the lanes' bit counts gives it.
+// Two kernels per batch of code-blocks:
+//   1. ht_vlc_kernel -- VLC / MEL / UVLC (openjph_cleanup_decoder.go:180-276).  Inherently serial inside a block (every codeword
+//      length depends on the context of the quads before it), so the parallelism is ACROSS blocks: one THREAD per code-block,
+//      32 blocks per warp walking their quad pairs in lock-step (same loop structure, data-dependent lengths).  A first version
+//      ran this phase on lane 0 of a warp-per-block kernel; ncu showed it issue-bound at 123 k warp instructions per 64 x 64
+//      block with 4.7 of 32 lanes active -- a warp instruction costs the same issue slot for 1 lane as for 32.  Each thread
+//      leaves (inf, u_q) per quad -- the `scratch` array of the reference -- in a global buffer (4 B per quad, ~1 B per
+//      sample); the previous quad row's significance pattern, which the context needs, lives in a per-thread local array.
+//      The reverse VLC reader and the MEL reader follow vlc_reverse_decoder.go:18-100 and openjph_cleanup_decoder.go:25-101
+//      (byte-wise instead of 4-byte chunks; the bit values are the same, see the notes at the readers).
+//   2. ht_magsgn_kernel -- MagSgn (openjph_cleanup_decoder.go:278-372, :432-447), one WARP per code-block: the number of bits
+//      of every sample is known once U_q is, and U_q of a quad row depends only on the row above (the exponent predictor), so
+//      a quad row is decoded by 32 lanes at once: one lane per quad, bit offsets by a warp prefix sum.  Random access into
+//      the MagSgn stream needs the byte-stuffing removed first: the warp un-stuffs 512 source bytes at a time (a byte after
+//      0xFF carries 7 bits, magsgn.go:160-204; beyond the end the stream reads as 0xFF) into a 16 Kbit ring in shared memory,
+//      each lane depositing its 16 bytes at the bit position a prefix sum over the lanes' bit counts gives it.
 // Errors (U_q beyond missing_msbs + 2, bad Scup, Kmax = 0 ...) zero the block, as TileDecoder.decodeCodeBlock does
 // (t2/tile_decoder.go:718-721), and are reported per block in `status`.
 #pragma once
@@ -38,19 +42,13 @@ struct HtBlock {                 // == j2k_ht_cblk (include/j2k_b200.h)
 #define HT_RING_WORDS 512        // un-stuffed MagSgn bits: 16 Kbit ring per warp
 #define HT_RING_MASK (HT_RING_WORDS - 1)
 
-// shared memory per warp (bytes) for code-blocks up to cbw x cbh
-__host__ __device__ inline int ht_sstr(int w) { return ((w + 2) + 7) & ~7; }
-__host__ __device__ inline int ht_warp_smem(int cbw, int cbh) {
-    const int scratch = ht_sstr(cbw) * ((cbh + 1) / 2 + 1) + 8;   // uint16, openjph_cleanup_decoder.go:135-136
-    const int vn = 2 * ((cbw + 1) / 2 + 2);                       // uint32, two rows of the exponent-predictor state
-    return ((scratch * 2 + 15) & ~15) + vn * 4 + HT_RING_WORDS * 4;
-}
+#define HT_MAX_QW 512            // quads per row of the widest code-block (1024 samples)
 
-__device__ __forceinline__ unsigned ht_warp_or(unsigned v) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, d);
-    return v;
-}
+// global scratch per code-block: one 32-bit word (inf | u_q << 16) per quad, rows of cbw / 2 quads
+__host__ __device__ inline int ht_scratch_words(int cbw, int cbh) { return ((cbw + 1) / 2) * ((cbh + 1) / 2); }
+// shared memory per warp of the MagSgn kernel (bytes): two rows of exponent-predictor state + the bit ring
+__host__ __device__ inline int ht_warp_smem(int cbw) { return 2 * ((cbw + 1) / 2 + 2) * 4 + HT_RING_WORDS * 4; }
+
 __device__ __forceinline__ int ht_warp_incl_scan(int v, int lane) {
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -76,6 +74,8 @@ struct HtRev {
         num = 4 - (((tmp & 7) == 7) ? 1 : 0);
         unstuff = (b | 0x0F) > 0x8F;
     }
+    // (measured: four bytes per step, loaded together as the reference's readChunk does, is slower here -- 0.78 -> 1.02 ms for
+    // 65536 blocks: the extra predicated work costs more than the exposed load latency it saves)
     __device__ __forceinline__ void fill() {
         while (num < 32 && pos >= 0) {
             const unsigned b = data[pos--];
@@ -158,17 +158,48 @@ struct HtCleanup {
     }
 };
 
-// Phase 1: openjph_cleanup_decoder.go:180-256 (decodeOpenJPHInitialRow, decodeOpenJPHRemainingRows)
-__device__ __noinline__ void ht_phase1(const unsigned char* cleanup, int scup, int width, int height, int sstr, unsigned short* scratch) {
+// decoder.go:44-50, openjph_cleanup_decoder.go:116-133 + parseStandardSegments (decoder.go:60-70): 0 and the suffix length, or
+// the error code of the block.  Both kernels evaluate it.
+__device__ __forceinline__ int ht_validate(const unsigned char* __restrict__ bytes, const HtBlock& d, int& scup) {
+    scup = 0;
+    const int lcup = (int)d.length;
+    if (lcup == 0) return 0;
+    if (d.kmax == 0) return -1;
+    if (d.mmsb >= 30 || lcup < 2) return -2;
+    const unsigned char* cb = bytes + d.offset;
+    scup = ((int)cb[lcup - 1] << 4) | (cb[lcup - 2] & 0x0F);
+    if (scup < 2 || scup > lcup || scup > 4079) return -2;
+    return 0;
+}
+
+// Kernel 1: openjph_cleanup_decoder.go:180-256 (decodeOpenJPHInitialRow, decodeOpenJPHRemainingRows), one thread per block.
+// `sc`: ht_scratch_words(cbw, cbh) words per block, row stride qs = cbw / 2 quads.  The reference keeps (inf, u_q) of the
+// row above in its scratch array and reads three entries of it per quad pair (sp - sstr, + 2, + 4); here those are
+// prow[q0], prow[q0 + 1], prow[q0 + 2], overwritten with the current row's patterns once the pair is done (entries past the
+// last quad stay zero: the reference's sentinels).
+__global__ void __launch_bounds__(32) ht_vlc_kernel(const unsigned char* __restrict__ bytes, const HtBlock* __restrict__ descs,
+                                                    const BlockEntry* __restrict__ tab, int nblocks, long long total,
+                                                    unsigned* __restrict__ sc_all, int sc_words, int qs) {
+    const long long wid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (wid >= total) return;
+    const int bi = (int)(wid % nblocks);
+    const int width = tab[bi].w, height = tab[bi].h;
+    const HtBlock d = descs[wid];
+    int scup;
+    if (d.length == 0 || ht_validate(bytes, d, scup) != 0) return;
+    unsigned* sc = sc_all + wid * sc_words;
+    const unsigned char* cleanup = bytes + d.offset + (d.length - scup);
+    const int qw = (width + 1) >> 1;
+    unsigned char prow[HT_MAX_QW + 4];
+    for (int i = 0; i < qw + 3; i++) prow[i] = 0;
     HtCleanup st;
     st.mel.init(cleanup, scup);
     st.vlc.init(cleanup, scup);
     st.run = st.mel.run();
     int cq = 0;
-    for (int x = 0, sp = 0; x < width; sp += 4) {
+    for (int x = 0, q0 = 0; x < width; q0 += 2) {
         unsigned t0 = HT_VLC_TBL0[cq + (int)(st.vlc.peek() & 0x7F)];
         if (cq == 0) t0 = st.zero_run(t0);
-        scratch[sp] = (unsigned short)t0;
         x += 2;
         cq = (int)(((t0 & 0x10) << 3) | ((t0 & 0xE0) << 2));
         st.vlc.advance((int)(t0 & 7));
@@ -176,7 +207,6 @@ __device__ __noinline__ void ht_phase1(const unsigned char* cleanup, int scup, i
         unsigned t1 = HT_VLC_TBL0[cq + (int)(st.vlc.peek() & 0x7F)];
         if (cq == 0 && x < width) t1 = st.zero_run(t1);
         if (x >= width) t1 = 0;
-        scratch[sp + 2] = (unsigned short)t1;
         x += 2;
         cq = (int)(((t1 & 0x10) << 3) | ((t1 & 0xE0) << 2));
         st.vlc.advance((int)(t1 & 7));
@@ -189,42 +219,40 @@ __device__ __noinline__ void ht_phase1(const unsigned char* cleanup, int scup, i
         }
         int u0, u1;
         st.uvlc(HT_UVLC_TBL0, mode, u0, u1);
-        scratch[sp + 1] = (unsigned short)(1 + u0);
-        scratch[sp + 3] = (unsigned short)(1 + u1);
+        sc[q0] = (t0 & 0xFFFF) | ((unsigned)(1 + u0) << 16);
+        if (q0 + 1 < qw) sc[q0 + 1] = (t1 & 0xFFFF) | ((unsigned)(1 + u1) << 16);
+        prow[q0] = (unsigned char)(t0 & 0xF0);
+        prow[q0 + 1] = (unsigned char)(t1 & 0xF0);
     }
-    const int sentinel = ((width + 3) / 4) * 4;
-    scratch[sentinel] = 0;
-    scratch[sentinel + 1] = 0;
     for (int y = 2; y < height; y += 2) {
         cq = 0;
-        int sp = (y >> 1) * sstr;
-        for (int x = 0; x < width; sp += 4) {
-            cq |= (int)(((scratch[sp - sstr] & 0xA0) << 2) | ((scratch[sp - sstr + 2] & 0x20) << 4));
+        unsigned* row = sc + (y >> 1) * qs;
+        for (int x = 0, q0 = 0; x < width; q0 += 2) {
+            const unsigned p0 = prow[q0], p1 = prow[q0 + 1], p2 = prow[q0 + 2];
+            cq |= (int)(((p0 & 0xA0) << 2) | ((p1 & 0x20) << 4));
             unsigned t0 = HT_VLC_TBL1[cq + (int)(st.vlc.peek() & 0x7F)];
             if (cq == 0) t0 = st.zero_run(t0);
-            scratch[sp] = (unsigned short)t0;
             x += 2;
             cq = (int)(((t0 & 0x40) << 2) | ((t0 & 0x80) << 1));
-            cq |= (int)(scratch[sp - sstr] & 0x80);
-            cq |= (int)(((scratch[sp - sstr + 2] & 0xA0) << 2) | ((scratch[sp - sstr + 4] & 0x20) << 4));
+            cq |= (int)(p0 & 0x80);
+            cq |= (int)(((p1 & 0xA0) << 2) | ((p2 & 0x20) << 4));
             st.vlc.advance((int)(t0 & 7));
 
             unsigned t1 = HT_VLC_TBL1[cq + (int)(st.vlc.peek() & 0x7F)];
             if (cq == 0 && x < width) t1 = st.zero_run(t1);
             if (x >= width) t1 = 0;
-            scratch[sp + 2] = (unsigned short)t1;
             x += 2;
             cq = (int)(((t1 & 0x40) << 2) | ((t1 & 0x80) << 1));
-            cq |= (int)(scratch[sp - sstr + 2] & 0x80);
+            cq |= (int)(p1 & 0x80);
             st.vlc.advance((int)(t1 & 7));
 
             int u0, u1;
             st.uvlc(HT_UVLC_TBL1, (int)(((t0 & 0x8) << 3) | ((t1 & 0x8) << 4)), u0, u1);
-            scratch[sp + 1] = (unsigned short)u0;
-            scratch[sp + 3] = (unsigned short)u1;
+            row[q0] = (t0 & 0xFFFF) | ((unsigned)u0 << 16);
+            if (q0 + 1 < qw) row[q0 + 1] = (t1 & 0xFFFF) | ((unsigned)u1 << 16);
+            prow[q0] = (unsigned char)(t0 & 0xF0);
+            prow[q0 + 1] = (unsigned char)(t1 & 0xF0);
         }
-        scratch[sp] = 0;
-        scratch[sp + 1] = 0;
     }
 }
 
@@ -309,12 +337,13 @@ __device__ __forceinline__ int ht_final(unsigned v, unsigned shift) {   // openj
     return (v & 0x80000000u) ? -mag : mag;
 }
 
-// One warp per code-block.  `tab`: the block table of the code-block interface (plane / block-major offsets, sizes).
+// Kernel 2: one warp per code-block.  `tab`: the block table of the code-block interface (plane / block-major offsets, sizes).
 // to_planes: 1 = write the Mallat coefficient planes (assembleSubbands fused), 0 = block-major planes.
-__global__ void __launch_bounds__(128) ht_decode_kernel(const unsigned char* __restrict__ bytes, const HtBlock* __restrict__ descs,
+__global__ void __launch_bounds__(128) ht_magsgn_kernel(const unsigned char* __restrict__ bytes, const HtBlock* __restrict__ descs,
                                                         const BlockEntry* __restrict__ tab, int nblocks, long long total,
-                                                        long long coeffs_per_frame, int* __restrict__ out, int to_planes,
-                                                        int* __restrict__ status, int warp_smem) {
+                                                        long long coeffs_per_frame, const unsigned* __restrict__ sc_all, int sc_words,
+                                                        int qs, int* __restrict__ out, int to_planes, int* __restrict__ status,
+                                                        int warp_smem) {
     J2K_SMEM_DECL(smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
@@ -326,44 +355,25 @@ __global__ void __launch_bounds__(128) ht_decode_kernel(const unsigned char* __r
     const int width = e.w, height = e.h;
     int* dst = out + frame * coeffs_per_frame + (to_planes ? e.plane_off : e.block_off);
     const long long dstride = to_planes ? e.stride : e.w;
-
-    // decoder.go:44-50, openjph_cleanup_decoder.go:116-133
-    int rc = 0;
     const int lcup = (int)d.length;
-    int scup = 0;
-    if (lcup > 0) {
-        if (d.kmax == 0) rc = -1;
-        else if (d.mmsb >= 30 || lcup < 2) rc = -2;
-        else {
-            const unsigned char* cb = bytes + d.offset;
-            scup = ((int)cb[lcup - 1] << 4) | (cb[lcup - 2] & 0x0F);
-            if (scup < 2 || scup > lcup || scup > 4079) rc = -2;
-        }
-    }
+    int scup;
+    int rc = ht_validate(bytes, d, scup);
     if (lcup > 0 && rc == 0) {
         unsigned char* my = smem + (size_t)warp * warp_smem;
-        const int sstr = ht_sstr(width);
-        const int nscratch = sstr * ((height + 1) / 2 + 1) + 8;
-        unsigned short* scratch = (unsigned short*)my;
         const int qw = (width + 1) >> 1, qh = (height + 1) >> 1;
-        unsigned* vnbuf = (unsigned*)(my + ((nscratch * 2 + 15) & ~15));
+        unsigned* vnbuf = (unsigned*)my;
         const int vnlen = qw + 2;
-        // ht_warp_smem sized the region for the nominal block (>= this one): scratch and the vn rows from the front, the ring
-        // at the end
         HtRing ring;
         ring.w = (unsigned*)(my + warp_smem - HT_RING_WORDS * 4);
-        for (int i = lane; i < (nscratch + 1) / 2; i += 32) ((unsigned*)scratch)[i] = 0;
         for (int i = lane; i < 2 * vnlen; i += 32) vnbuf[i] = 0;
         for (int i = lane; i < HT_RING_WORDS; i += 32) ring.w[i] = 0;
         __syncwarp();
-        const unsigned char* cb = bytes + d.offset;
-        if (lane == 0) ht_phase1(cb + (lcup - scup), scup, width, height, sstr, scratch);
-        __syncwarp();
-
-        ring.src = cb; ring.len = lcup - scup; ring.pos = 0; ring.wbits = 0; ring.rbits = 0; ring.last = 0;
+        const unsigned* sc = sc_all + wid * sc_words;
+        ring.src = bytes + d.offset; ring.len = lcup - scup; ring.pos = 0; ring.wbits = 0; ring.rbits = 0; ring.last = 0;
         const int mmsbp2 = d.mmsb + 2, pm1 = 30 - d.mmsb - 1;
         const unsigned shift = (unsigned)(31 - (int)d.kmax);
         unsigned err = 0;
+        unsigned ent_pf = lane < qw ? sc[lane] : 0;
         for (int qy = 0; qy < qh && !err; qy++) {
             const int y = 2 * qy;
             const unsigned* vold = vnbuf + (qy & 1) * vnlen;
@@ -372,8 +382,13 @@ __global__ void __launch_bounds__(128) ht_decode_kernel(const unsigned char* __r
             for (int g0 = 0; g0 < qw; g0 += 32) {
                 const int q = g0 + lane;
                 const bool act = q < qw;
-                const unsigned inf = act ? scratch[qy * sstr + 2 * q] : 0;
-                int uq = act ? (int)scratch[qy * sstr + 2 * q + 1] : 0;
+                unsigned ent;
+                if (g0 == 0) {   // the first group's entries were loaded a row ahead
+                    ent = ent_pf;
+                    ent_pf = (qy + 1 < qh && lane < qw) ? sc[(qy + 1) * qs + lane] : 0;
+                } else ent = act ? sc[qy * qs + q] : 0;
+                const unsigned inf = ent & 0xFFFF;
+                int uq = (int)(ent >> 16);
                 if (qy > 0) {
                     unsigned gamma = inf & 0xF0;
                     gamma &= gamma - 0x10;
@@ -381,15 +396,14 @@ __global__ void __launch_bounds__(128) ht_decode_kernel(const unsigned char* __r
                     const int emax = 31 - __clz((int)(ev | 2));
                     uq += gamma ? emax : 1;
                 }
-                const bool bad = act && uq > mmsbp2;
-                if (ht_warp_or(bad ? 1u : 0u)) { err = 1; break; }
                 const bool right = act && (2 * q + 1 < width);   // samples 2 and 3 exist
-                int nbits = 0;
+                int nbits = (act && uq > mmsbp2) ? (1 << 16) : 0;   // bits 16..: quads whose U_q is out of range
 #pragma unroll
                 for (int i = 0; i < 4; i++)
                     if (act && (i < 2 || right) && (inf & (1u << (4 + i)))) nbits += uq - (int)((inf >> (12 + i)) & 1);
                 const int incl = ht_warp_incl_scan(nbits, lane);
                 const int need = __shfl_sync(0xffffffffu, incl, 31);
+                if (need >> 16) { err = 1; break; }
                 while ((int)(ring.wbits - ring.rbits) < need) ring.refill(lane);
                 unsigned off = ring.rbits + (unsigned)(incl - nbits);
                 unsigned v0, v1, v2, v3, n0, n1, n2, n3;

@@ -84,6 +84,15 @@ class Cblk(C.Structure):
     ]
 
 
+class HtCblk(C.Structure):
+    """j2k_ht_cblk: one HT code-block as T2 leaves it (cbInfo, jpeg2000/t2/tile_decoder.go:453-526) plus the coding context
+    of HTDecoder.SetCodingContext (jpeg2000/htj2k/decoder.go:92-96)."""
+    _fields_ = [("offset", C.c_uint64), ("length", C.c_uint32), ("kmax", C.c_uint8), ("missing_msbs", C.c_uint8), ("reserved", C.c_uint16)]
+
+
+HT_OK, HT_ERR_KMAX, HT_ERR_SEGMENT, HT_ERR_UQ = 0, -1, -2, -3
+
+
 class Timing(C.Structure):
     _fields_ = [
         ("h2d_ms", C.c_float), ("kernel_ms", C.c_float), ("d2h_ms", C.c_float), ("total_ms", C.c_float),
@@ -255,6 +264,11 @@ def load(path: str | None = None) -> C.CDLL:
         "j2k_inverse_blocks_roi_general": (ci, [vp, IP, ci, ci, ci, vp, vp, vp, vp, vp, sz, vp]),
         "j2k_scatter_blocks_roi_general_device": (ci, [vp, ci, IP, ci, ci, ci, vp, vp, vp, vp, vp, vp]),
         "j2k_scatter_blocks_roi_device": (ci, [vp, ci, IP, ci, ci, ci, vp, vp, vp, vp]),
+        "j2k_ht_decode_blocks": (ci, [vp, IP, ci, ci, ci, vp, sz, vp, vp, vp]),
+        "j2k_inverse_ht": (ci, [vp, IP, ci, ci, ci, vp, sz, vp, vp, sz, vp, vp]),
+        "j2k_submit_inverse_ht": (C.c_int64, [vp, IP, ci, ci, ci, vp, sz, vp, vp, sz, vp, vp]),
+        "j2k_ht_decode_device": (ci, [vp, ci, IP, ci, ci, ci, vp, vp, vp, ci, vp, vp]),
+        "j2k_ht_table": (ci, [ci, vp]),
         "j2k_dwt53_forward": (ci, [vp, vp, ci, ci, ci, ci, ci]),
         "j2k_dwt53_inverse": (ci, [vp, vp, ci, ci, ci, ci, ci]),
         "j2k_dwt97_forward": (ci, [vp, vp, ci, ci, ci, ci, ci]),

@@ -204,6 +204,56 @@ class Context:
                                                      _vp(planes) if want_planes else None))
         return (out, planes) if want_planes else out
 
+    # ---- HTJ2K block decoding on the device (decode side)
+    @staticmethod
+    def ht_records(offsets, lengths, kmax, missing_msbs) -> np.ndarray:
+        """j2k_ht_cblk records (one per frame and block, code-block interface order) from four parallel arrays."""
+        rec = np.zeros(len(offsets), dtype=np.dtype([("offset", "<u8"), ("length", "<u4"), ("kmax", "u1"), ("missing_msbs", "u1"),
+                                                      ("reserved", "<u2")]))
+        rec["offset"], rec["length"], rec["kmax"], rec["missing_msbs"] = offsets, lengths, kmax, missing_msbs
+        assert rec.dtype.itemsize == C.sizeof(abi.HtCblk)
+        return rec
+
+    def ht_decode_blocks(self, p: abi.InvParams, nframes: int, stream: np.ndarray, records: np.ndarray, cb_width=64, cb_height=64):
+        """HTDecoder.Decode (jpeg2000/htj2k/decoder.go:43-58) for every code-block: -> (block-major planes [nframes, coeffs],
+        status [nframes, blocks]); a failing block reads as zeros (t2/tile_decoder.go:718-721)."""
+        stream = np.ascontiguousarray(stream, dtype=np.uint8)
+        nblk = self.lib.j2k_inv_block_count(C.byref(p), cb_width, cb_height)
+        assert records.size == nframes * nblk, (records.size, nframes, nblk)
+        out = np.empty((nframes, self.lib.j2k_inv_coeff_count(C.byref(p))), np.int32)
+        status = np.empty((nframes, nblk), np.int32)
+        self._ck(self.lib.j2k_ht_decode_blocks(self.h, C.byref(p), cb_width, cb_height, nframes, _vp(stream), stream.size, _vp(records),
+                                               _vp(out), _vp(status)))
+        return out, status
+
+    def inverse_ht(self, p: abi.InvParams, nframes: int, stream: np.ndarray, records: np.ndarray, cb_width=64, cb_height=64,
+                   want_planes: bool = False):
+        """HT block decoding + assembleSubbands + the whole inverse path on the device: cleanup segments in, pixels out.
+        -> (pixels [nframes, bytes], status [nframes, blocks]) (+ planes)."""
+        stream = np.ascontiguousarray(stream, dtype=np.uint8)
+        nblk = self.lib.j2k_inv_block_count(C.byref(p), cb_width, cb_height)
+        assert records.size == nframes * nblk, (records.size, nframes, nblk)
+        nbytes = self.lib.j2k_inv_pixel_bytes(C.byref(p))
+        out = np.empty((nframes, nbytes), np.uint8)
+        status = np.empty((nframes, nblk), np.int32)
+        w, h = p.xsiz - p.xosiz, p.ysiz - p.yosiz
+        planes = np.empty((nframes, p.components, h, w), np.int32) if want_planes else None
+        self._ck(self.lib.j2k_inverse_ht(self.h, C.byref(p), cb_width, cb_height, nframes, _vp(stream), stream.size, _vp(records), _vp(out),
+                                         nbytes, _vp(planes) if want_planes else None, _vp(status)))
+        return (out, status, planes) if want_planes else (out, status)
+
+    def submit_inverse_ht(self, p: abi.InvParams, nframes: int, stream: np.ndarray, records: np.ndarray, out: np.ndarray,
+                          status: np.ndarray | None = None, cb_width=64, cb_height=64) -> int:
+        """Ticketed inverse_ht: `stream`, `out` (and `status`) come from acquire(); `records` may be any array (it is copied)."""
+        return self._ck(self.lib.j2k_submit_inverse_ht(self.h, C.byref(p), cb_width, cb_height, nframes, _vp(stream), stream.size,
+                                                       _vp(records), _vp(out), out.strides[0], None,
+                                                       _vp(status) if status is not None else None))
+
+    def ht_decode_device(self, p: abi.InvParams, nframes, d_bytes: int, d_records: int, d_out: int, to_planes: bool, d_status: int = 0,
+                         cb_width=64, cb_height=64, dev=0, stream=0):
+        self._ck(self.lib.j2k_ht_decode_device(self.h, dev, C.byref(p), cb_width, cb_height, nframes, d_bytes, d_records, d_out,
+                                               int(to_planes), d_status or None, stream or None))
+
     def gather_blocks_device(self, p: abi.FwdParams, nframes, d_coeffs: int, d_blocks: int, d_numbps: int, cb_width=64, cb_height=64,
                              stream: int = 0, dev: int = 0):
         self._ck(self.lib.j2k_gather_blocks_device(self.h, dev, C.byref(p), cb_width, cb_height, nframes, C.c_void_p(d_coeffs),

@@ -372,6 +372,11 @@ int j2k_inverse_ht(j2k_ctx* ctx, const j2k_inv_params* p, int cb_width, int cb_h
                    size_t nbytes, const j2k_ht_cblk* cblks, void* pixels_out, size_t frame_stride_bytes, int32_t* planes_out,
                    int32_t* status_out);
 
+/* Ticketed form (j2k_wait); buffers from j2k_acquire_buffer, as for j2k_submit_inverse. */
+int64_t j2k_submit_inverse_ht(j2k_ctx* ctx, const j2k_inv_params* p, int cb_width, int cb_height, int nframes, const uint8_t* bytes,
+                              size_t nbytes, const j2k_ht_cblk* cblks, void* pixels_out, size_t frame_stride_bytes,
+                              int32_t* planes_out, int32_t* status_out);
+
 /* Device-resident form: `d_bytes`, `d_cblks` (nframes x blocks records), `d_out` and `d_status` (optional) are device
  * pointers; to_planes = 1 writes Mallat coefficient planes (input of j2k_inverse_device), 0 block-major planes.  Offsets and
  * lengths in device memory cannot be checked against the stream size: the caller guarantees offset + length <= nbytes. */

@@ -481,3 +481,219 @@ EXPORT void orc_ht_decode_blocks(const uint8_t* bytes, const uint64_t* offsets, 
         if (status) status[i] = rc;
     }
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Stream GENERATOR for the tests and the bench: an HT cleanup-pass block encoder written from ISO/IEC 15444-15 clause 7
+ * against the decoder above (NOT a restatement of the reference's openjph_cleanup_encoder.go, and not byte-identical to
+ * OpenJPH: where several VLC entries fit, it takes the one with the most known bits; MEL and VLC are not fused).  Its only
+ * contract is the round trip: orc_ht_decode_block(orc_ht_encode_block(x)) == x, which tests/test_ht_oracle.py checks on
+ * every generated block before the stream is used to exercise the CUDA decoder.
+ * Input: width*height signed values, |x| <= 2^(missing_msbs + 1); the block decodes to x with kmax = missing_msbs + 1. */
+
+typedef struct { uint8_t* buf; int cap, pos; uint32_t cur; int n, max; } fw_t;   /* MagSgn: forward, LSB first */
+static int fw_put(fw_t* w, uint32_t v, int nbits) {
+    for (int i = 0; i < nbits; i++) {
+        w->cur |= ((v >> i) & 1u) << w->n;
+        if (++w->n == w->max) {
+            if (w->pos >= w->cap) return -1;
+            w->buf[w->pos++] = (uint8_t)w->cur;
+            w->max = w->cur == 0xFF ? 7 : 8;
+            w->cur = 0; w->n = 0;
+        }
+    }
+    return 0;
+}
+static int fw_flush(fw_t* w) {
+    while (w->n != 0) if (fw_put(w, 1, 1)) return -1;   /* pad with ones (the decoder reads 0xFF beyond the end) */
+    return 0;
+}
+
+typedef struct { uint8_t* buf; int cap, pos; uint32_t cur; int n, max; int k, run; } melw_t;   /* MEL: forward, MSB first */
+static int melw_bit(melw_t* w, int b) {
+    w->cur = (w->cur << 1) | (uint32_t)b;
+    if (++w->n == w->max) {
+        if (w->pos >= w->cap) return -1;
+        w->buf[w->pos++] = (uint8_t)w->cur;
+        w->max = w->cur == 0xFF ? 7 : 8;
+        w->cur = 0; w->n = 0;
+    }
+    return 0;
+}
+static int melw_event(melw_t* w, int bit) {
+    int e = MEL_E[w->k];
+    if (!bit) {
+        if (++w->run >= (1 << e)) {
+            if (melw_bit(w, 1)) return -1;
+            w->run = 0;
+            if (w->k < 12) w->k++;
+        }
+        return 0;
+    }
+    if (melw_bit(w, 0)) return -1;
+    for (int i = e - 1; i >= 0; i--) if (melw_bit(w, (w->run >> i) & 1)) return -1;
+    w->run = 0;
+    if (w->k > 0) w->k--;
+    return 0;
+}
+static int melw_flush(melw_t* w) {
+    if (w->run > 0 && melw_bit(w, 1)) return -1;
+    while (w->n != 0) if (melw_bit(w, 0)) return -1;
+    return 0;
+}
+
+/* VLC: written LSB first into bytes that end up in reverse order; a byte that follows one > 0x8F stops at 7 bits when those
+ * are all ones (the reverse reader's un-stuffing rule, vlc_reverse_decoder.go:42-87) */
+typedef struct { uint8_t* buf; int cap, pos; uint32_t cur; int n; int prev_big; } vlcw_t;
+static int vlcw_emit(vlcw_t* w) {
+    if (w->pos >= w->cap) return -1;
+    w->buf[w->pos++] = (uint8_t)w->cur;
+    w->prev_big = w->cur > 0x8F;
+    w->cur = 0; w->n = 0;
+    return 0;
+}
+static int vlcw_put(vlcw_t* w, uint32_t v, int nbits) {
+    for (int i = 0; i < nbits; i++) {
+        w->cur |= ((v >> i) & 1u) << w->n;
+        w->n++;
+        if (w->n == 7 && w->prev_big && (w->cur & 0x7F) == 0x7F) { if (vlcw_emit(w)) return -1; }
+        else if (w->n == 8) { if (vlcw_emit(w)) return -1; }
+    }
+    return 0;
+}
+
+static int enc_lookup(const unsigned char (*src)[7], int n, int cq, int rho, int uoff, int emb, int* cwd, int* len, int* ek) {
+    int best = -1, bestpop = -1;
+    for (int j = 0; j < n; j++) {
+        const unsigned char* e = src[j];
+        if (e[0] != cq || e[1] != rho || e[2] != uoff) continue;
+        if (uoff) { if ((emb & e[3]) != e[4]) continue; }
+        else if (e[3] || e[4]) continue;
+        int pop = __builtin_popcount(e[3]);
+        if (pop > bestpop) { bestpop = pop; best = j; }
+    }
+    if (best < 0) return -1;
+    *cwd = src[best][5]; *len = src[best][6]; *ek = src[best][3];
+    return 0;
+}
+
+/* u >= 1: prefix (value, bits) and suffix (value, bits) of the U-VLC code, bits LSB first (uvlc_tables.go:41-51) */
+static void uvlc_code(int u, int* pv, int* pl, int* sv, int* sl) {
+    if (u == 1) { *pv = 1; *pl = 1; *sv = 0; *sl = 0; }
+    else if (u == 2) { *pv = 2; *pl = 2; *sv = 0; *sl = 0; }
+    else if (u <= 4) { *pv = 4; *pl = 3; *sv = u - 3; *sl = 1; }
+    else { *pv = 0; *pl = 3; *sv = u - 5; *sl = 5; }
+}
+
+EXPORT int orc_ht_encode_block(const int32_t* x, int width, int height, int missing_msbs, uint8_t* out, int cap) {
+    init_tables();
+    const int qw = (width + 1) / 2, qh = (height + 1) / 2;
+    int any = 0;
+    for (int i = 0; i < width * height; i++) any |= x[i] != 0;
+    if (!any) return 0;   /* not included: no bytes */
+    uint8_t* msb = (uint8_t*)malloc((size_t)cap);
+    uint8_t* melb = (uint8_t*)malloc((size_t)cap);
+    uint8_t* vlcb = (uint8_t*)malloc((size_t)cap);
+    uint8_t* rho_prev = (uint8_t*)calloc((size_t)qw + 2, 1);
+    uint8_t* rho_cur = (uint8_t*)calloc((size_t)qw + 2, 1);
+    uint32_t* vn1 = (uint32_t*)calloc((size_t)qw + 2, 4), *vn3 = (uint32_t*)calloc((size_t)qw + 2, 4);   /* row above, index q + 1 */
+    uint32_t* cn1 = (uint32_t*)calloc((size_t)qw + 2, 4), *cn3 = (uint32_t*)calloc((size_t)qw + 2, 4);
+    fw_t ms = {msb, cap, 0, 0, 0, 8};
+    melw_t mel = {melb, cap, 0, 0, 0, 8, 0, 0};
+    vlcw_t vlc = {vlcb, cap, 0, 0xF, 4, 1};   /* the first byte's low nibble belongs to Scup and counts as 0xF */
+    int rc = 0;
+    for (int qy = 0; qy < qh && !rc; qy++) {
+        memset(rho_cur, 0, (size_t)qw + 2);
+        memset(cn1, 0, ((size_t)qw + 2) * 4); memset(cn3, 0, ((size_t)qw + 2) * 4);
+        for (int q0 = 0; q0 < qw && !rc; q0 += 2) {
+            int uoff[2] = {0, 0}, u[2] = {0, 0};
+            for (int k = 0; k < 2; k++) {
+                int q = q0 + k;
+                if (q >= qw) break;
+                uint32_t vn[4] = {0, 0, 0, 0}; int sgn[4] = {0, 0, 0, 0}, rho = 0, maxe = 0;
+                for (int i = 0; i < 4; i++) {
+                    int xx = 2 * q + (i >> 1), yy = 2 * qy + (i & 1);
+                    if (xx >= width || yy >= height) continue;
+                    int32_t v = x[yy * width + xx];
+                    if (!v) continue;
+                    uint32_t m = v < 0 ? (uint32_t)(-(int64_t)v) : (uint32_t)v;
+                    rho |= 1 << i; sgn[i] = v < 0; vn[i] = 2 * m - 1;
+                    int e = bitlen32(vn[i]);
+                    if (e > maxe) maxe = e;
+                }
+                rho_cur[q + 1] = (uint8_t)rho;
+                cn1[q + 1] = vn[1]; cn3[q + 1] = vn[3];
+                int cq, kappa = 1;
+                uint8_t L = rho_cur[q];   /* left quad (index q - 1 + 1) */
+                if (qy == 0) cq = (((L & 1) | ((L >> 1) & 1))) | (((L >> 2) & 1) << 1) | (((L >> 3) & 1) << 2);
+                else {
+                    uint8_t Aw = rho_prev[q], A = rho_prev[q + 1], Ae = rho_prev[q + 2];
+                    cq = (((Aw >> 3) & 1) | ((A >> 1) & 1)) | ((((L >> 2) & 1) | ((L >> 3) & 1)) << 1) | ((((A >> 3) & 1) | ((Ae >> 1) & 1)) << 2);
+                    if (__builtin_popcount(rho) > 1) {
+                        uint32_t o = vn3[q] | vn1[q + 1] | vn3[q + 1] | vn1[q + 2];
+                        kappa = bitlen32(o | 2) - 1;
+                    }
+                }
+                if (cq == 0 && melw_event(&mel, rho != 0)) { rc = -1; break; }
+                if (rho == 0 && cq == 0) continue;
+                int Uq = maxe > kappa ? maxe : kappa;
+                if (rho == 0) Uq = kappa;
+                if (Uq > missing_msbs + 2) { rc = -2; break; }
+                u[k] = Uq - kappa; uoff[k] = u[k] > 0;
+                int emb = 0;
+                if (uoff[k]) for (int i = 0; i < 4; i++) if ((rho >> i & 1) && bitlen32(vn[i]) == Uq) emb |= 1 << i;
+                int cwd, len, ek;
+                if (qy == 0 ? enc_lookup(HT_VLC_SRC0, (int)(sizeof(HT_VLC_SRC0) / 7), cq, rho, uoff[k], emb, &cwd, &len, &ek)
+                            : enc_lookup(HT_VLC_SRC1, (int)(sizeof(HT_VLC_SRC1) / 7), cq, rho, uoff[k], emb, &cwd, &len, &ek)) { rc = -3; break; }
+                if (vlcw_put(&vlc, (uint32_t)cwd, len)) { rc = -1; break; }
+                for (int i = 0; i < 4; i++) {
+                    if (!(rho >> i & 1)) continue;
+                    int mn = Uq - ((ek >> i) & 1);
+                    uint32_t val = (vn[i] & ~1u) | (uint32_t)sgn[i];
+                    if (fw_put(&ms, mn >= 32 ? val : (val & ((1u << mn) - 1)), mn)) { rc = -1; break; }
+                }
+            }
+            if (rc) break;
+            int m0 = uoff[0], m1 = uoff[1], a = u[0], b = u[1];
+            int pv, pl, sv, sl, pv2, pl2, sv2, sl2;
+            if (m0 && m1) {
+                if (qy == 0) {
+                    int big = (a < b ? a : b) > 2;
+                    if (melw_event(&mel, big)) { rc = -1; break; }
+                    if (big) { a -= 2; b -= 2; }
+                    else if (a > 2) {   /* u1 is 1 or 2: one bit behind the first prefix */
+                        uvlc_code(a, &pv, &pl, &sv, &sl);
+                        if (vlcw_put(&vlc, (uint32_t)pv, pl) || vlcw_put(&vlc, (uint32_t)(b - 1), 1) || vlcw_put(&vlc, (uint32_t)sv, sl)) rc = -1;
+                        continue;
+                    }
+                }
+                uvlc_code(a, &pv, &pl, &sv, &sl);
+                uvlc_code(b, &pv2, &pl2, &sv2, &sl2);
+                if (vlcw_put(&vlc, (uint32_t)pv, pl) || vlcw_put(&vlc, (uint32_t)pv2, pl2) || vlcw_put(&vlc, (uint32_t)sv, sl) || vlcw_put(&vlc, (uint32_t)sv2, sl2)) rc = -1;
+            } else if (m0 || m1) {
+                uvlc_code(m0 ? a : b, &pv, &pl, &sv, &sl);
+                if (vlcw_put(&vlc, (uint32_t)pv, pl) || vlcw_put(&vlc, (uint32_t)sv, sl)) rc = -1;
+            }
+        }
+        uint8_t* t = rho_prev; rho_prev = rho_cur; rho_cur = t;
+        uint32_t* tn = vn1; vn1 = cn1; cn1 = tn;
+        tn = vn3; vn3 = cn3; cn3 = tn;
+    }
+    int lcup = rc;
+    if (!rc) {
+        if (fw_flush(&ms) || melw_flush(&mel)) rc = -1;
+        if (!rc && vlc.n > 0 && vlcw_emit(&vlc)) rc = -1;
+        if (!rc && vlc.pos == 0 && vlcw_emit(&vlc)) rc = -1;   /* the nibble byte always exists */
+        int scup = mel.pos + vlc.pos + 1;
+        lcup = ms.pos + scup;
+        if (!rc && (scup > 4079 || lcup > cap)) rc = -4;
+        if (!rc) {
+            memcpy(out, msb, (size_t)ms.pos);
+            memcpy(out + ms.pos, melb, (size_t)mel.pos);
+            for (int i = 0; i < vlc.pos; i++) out[ms.pos + mel.pos + i] = vlcb[vlc.pos - 1 - i];
+            out[lcup - 1] = (uint8_t)(scup >> 4);
+            out[lcup - 2] = (uint8_t)((out[lcup - 2] & 0xF0) | (scup & 0xF));
+        } else lcup = rc;
+    }
+    free(msb); free(melb); free(vlcb); free(rho_prev); free(rho_cur); free(vn1); free(vn3); free(cn1); free(cn3);
+    return lcup;
+}

@@ -44,6 +44,16 @@ class HtOracle:
                                           C.c_int(missing_msbs), _p(out))
         return rc, out
 
+    def encode_block(self, x, missing_msbs):
+        """the test-stream GENERATOR (see ht_oracle.c): bytes of a cleanup segment that decodes to x with kmax = missing_msbs + 1;
+        b"" for an all-zero block"""
+        a = np.ascontiguousarray(x, np.int32)
+        h, w = a.shape
+        out = np.zeros(w * h * 5 + 64, np.uint8)
+        n = self.lib.orc_ht_encode_block(_p(a), C.c_int(w), C.c_int(h), C.c_int(missing_msbs), _p(out), C.c_int(out.size))
+        assert n >= 0, n
+        return out[:n].tobytes()
+
     def decode_blocks(self, stream, offsets, lengths, kmax, mmsb, widths, heights, out_offsets, total_samples):
         """every array one entry per block; returns (block-major int32 buffer, status per block)"""
         n = len(offsets)

@@ -46,7 +46,7 @@ def test_no_device_is_an_error_not_a_fallback():
 def test_product_sources_never_load_the_oracle():
     """The product path must not import, link or execute anything under oracle/ (it is the checker)."""
     pk = os.path.join(ROOT, "go-dicom-codec_b200")
-    banned = ("oracle_lib", "j2k_oracle", "libj2k_oracle", "np_mirror", "import oracle", "oracle/")
+    banned = ("oracle_lib", "j2k_oracle", "ht_oracle", "libj2k_oracle", "libht_oracle", "np_mirror", "import oracle", "oracle/")
     for d, _, files in os.walk(pk):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):

@@ -1,0 +1,94 @@
+"""HTJ2K block decoder on the B200 (sm_100a build, through the C ABI) against the oracle: every OpenJPH interop codestream,
+corrupted segments, generated streams at every block shape, and C1/C3-sized frames.  Bit-exact, status codes included."""
+import numpy as np
+import pytest
+
+import ht_cases
+import ht_parity as HP
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ht():
+    import ht_oracle_lib
+    return ht_oracle_lib.HtOracle()
+
+
+@pytest.mark.parametrize("name,kind", ht_cases.fixtures())
+def test_openjph_fixtures(ctx, ht, oracle, name, kind):
+    HP.check_fixture(ctx, ht, oracle, name, kind, nframes=3 if "128x128" in name else 1)
+
+
+@pytest.mark.parametrize("name,kind", ht_cases.fixtures()[::2])
+def test_mutated_segments(ctx, ht, oracle, name, kind):
+    HP.check_mutations(ctx, ht, oracle, name, kind, rounds=6, seed=11)
+
+
+@pytest.mark.parametrize("w,h,levels,cbw,cbh", [(64, 64, 0, 64, 64), (70, 37, 1, 32, 32), (33, 65, 1, 64, 64), (40, 24, 0, 4, 4),
+                                                (130, 9, 0, 128, 32), (9, 130, 0, 16, 256), (260, 4, 0, 1024, 4), (5, 300, 0, 4, 1024),
+                                                (1, 7, 0, 8, 8), (7, 1, 0, 8, 8), (2, 2, 0, 4, 4), (512, 512, 3, 64, 64), (300, 200, 2, 32, 64)])
+def test_random_streams(ctx, ht, oracle, w, h, levels, cbw, cbh):
+    HP.check_random_streams(ctx, ht, oracle, w, h, levels, cbw, cbh, seed=w * 131 + h)
+
+
+@pytest.mark.parametrize("w,h,levels,cbw,cbh,bits,density,comps,rev", [
+    (64, 64, 0, 64, 64, 12, 0.7, 1, True), (96, 80, 2, 32, 32, 8, 0.3, 1, True), (75, 61, 2, 64, 64, 16, 0.9, 1, True),
+    (128, 32, 1, 128, 32, 10, 0.5, 1, False), (40, 40, 1, 16, 16, 8, 0.6, 3, True), (33, 130, 1, 8, 512, 12, 1.0, 1, True),
+    (150, 10, 0, 1024, 4, 9, 0.8, 1, True), (48, 48, 2, 64, 64, 8, 0.05, 3, False),
+    (512, 512, 5, 64, 64, 16, 0.8, 1, True),       # C1-shaped
+    (512, 384, 5, 64, 64, 8, 0.5, 3, False),       # C3-shaped, ICT + 9/7 behind the block decoder
+    (2140, 300, 4, 64, 64, 16, 1.0, 1, False),     # odd DX width: edge blocks of every size
+    (257, 255, 3, 32, 128, 14, 0.95, 1, True),
+])
+def test_generated_streams(ctx, ht, oracle, w, h, levels, cbw, cbh, bits, density, comps, rev):
+    HP.check_generated(ctx, ht, oracle, w, h, levels, cbw, cbh, bits, density, seed=w + 7 * h, components=comps, reversible=rev)
+
+
+def test_generated_batch(ctx, ht, oracle):
+    HP.check_generated(ctx, ht, oracle, 256, 256, 4, 64, 64, 12, 0.7, seed=5, nframes=4)
+
+
+def test_error_codes(ctx, ht, oracle):
+    HP.check_error_codes(ctx, ht, oracle)
+
+
+def test_unsupported_block_size_and_bad_offsets(ctx):
+    import j2kb200
+    from j2kb200 import abi
+    ip = abi.inv_params(64, 64, 1, 8, False, num_levels=0, reversible=True, htj2k=True)
+    rec = j2kb200.Context.ht_records([0], [4], [8], [7])
+    with pytest.raises(Exception, match="4096"):
+        ctx.ht_decode_blocks(ip, 1, np.zeros(16, np.uint8), rec, 128, 64)
+    rec = j2kb200.Context.ht_records([10], [40], [8], [7])
+    with pytest.raises(Exception, match="outside"):
+        ctx.ht_decode_blocks(ip, 1, np.zeros(16, np.uint8), rec, 64, 64)
+
+
+def test_async_ticket_and_pinned_buffers(ctx, ht, oracle):
+    """j2k_submit_inverse_ht with library-owned pinned buffers, two tickets in flight, every frame compared"""
+    from j2kb200 import abi
+    from j2kb200.codec import Context
+    fx = ht_cases.load("mono_u16_888x459", "fo_htj2k_lossless", oracle.codeblock_layout)
+    h = fx["header"]
+    ip = abi.inv_params(h.width, h.height, 1, h.depth[0], h.signed[0], num_levels=h.num_levels, reversible=True, htj2k=True)
+    F = 5
+    nb = len(fx["offsets"])
+    rec = Context.ht_records(np.tile(fx["offsets"], F), np.tile(fx["lengths"], F), np.tile(fx["kmax"], F), np.tile(fx["mmsb"], F))
+    stream = ctx.pinned(fx["stream"].size)
+    stream[:] = fx["stream"]
+    outs = [ctx.pinned(F * fx["raw"].size).reshape(F, -1) for _ in range(2)]
+    sts = [ctx.pinned(F * nb * 4, np.int32).reshape(F, nb) for _ in range(2)]
+    for o, s_ in zip(outs, sts):
+        o[:] = 0
+        s_[:] = -9
+    t0 = ctx.submit_inverse_ht(ip, F, stream, rec, outs[0], sts[0], h.cbw, h.cbh)
+    t1 = ctx.submit_inverse_ht(ip, F, stream, rec, outs[1], sts[1], h.cbw, h.cbh)
+    ctx.wait(t1)
+    ctx.wait(t0)
+    for o, s_ in zip(outs, sts):
+        assert not s_.any()
+        for f in range(F):
+            assert np.array_equal(o[f], fx["raw"]), f
+    for a in [stream] + outs + sts:
+        ctx.release(a)

@@ -16,7 +16,7 @@ summ() { # name note
   { echo "# executed warp instructions per code region (tools/ncu_groups.py) and per opcode (tools/ncu_mix.py): $1"; python tools/ncu_groups.py $f 10; python tools/ncu_mix.py $f 24; } > $out/ncu_${tag}_${1}_instructions.txt 2>&1
   case " $keep " in *" $1 "*) ;; *) rm -f $f;; esac
 }
-common="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --streams 1 --no-configs"
+common="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --streams 1 --no-configs --no-ht"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:fwd_ring_kernel --launch-skip 4 --launch-count 1 \
   -f -o gpurun_out/prof_fwd_ring_$tag $common --no-inverse > gpurun_out/ncu_fwd_$tag.log 2>&1; echo fwd rc=$?
 summ fwd_ring "tools/final_r02.sh $tag: $common --no-inverse, fwd_ring_kernel, 32 C2 frames, launch 5"

@@ -5,7 +5,7 @@
 """
 import csv, subprocess, sys
 rep = sys.argv[1]
-reason = sys.argv[2] if len(sys.argv) > 2 else None
+reason = (sys.argv[2] or None) if len(sys.argv) > 2 else None
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 25
 text = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(text.splitlines()))
