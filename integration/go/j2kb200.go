@@ -446,3 +446,36 @@ func InverseBlocks(p *InvParams, cbWidth, cbHeight, nframes int, blocks []int32,
 	}
 	return nil
 }
+
+// HTBlock mirrors j2k_ht_cblk: one HT code-block as T2 leaves it (cbInfo, t2/tile_decoder.go:453-526) plus the coding
+// context HTDecoder.SetCodingContext receives (htj2k/decoder.go:92-96; set at t2/tile_decoder.go:601-609).
+type HTBlock struct {
+	Offset      uint64 // first byte of the cleanup segment in the stream handed to InverseHT
+	Length      uint32 // Lcup; 0 = block not included (shouldDecode, t2/tile_decoder.go:672-689): zero coefficients
+	Kmax        uint8  // bandNumbpsFromQCD (t2/bitplane.go:22-61)
+	MissingMSBs uint8  // htj2kMissingMSBs (t2/tile_decoder.go:691-699)
+	_           uint16
+}
+
+// InverseHT: the whole HTJ2K decode tail on the device.  stream holds the cleanup segments of every code-block of nframes
+// frames (T2 already parsed the packets), blocks one record per (frame, block) in CodeBlockLayout order; the device runs
+// HTDecoder.Decode (htj2k/decoder.go:43-58) for every block, assembleSubbands (t2/tile_decoder.go:840-883) and everything
+// InverseBatch does.  status (optional, one entry per record) receives 0 or the block decoder's error code; a failing
+// block reads as zeros, as decodeCodeBlock substitutes (t2/tile_decoder.go:718-721).
+func InverseHT(p *InvParams, cbWidth, cbHeight, nframes int, stream []byte, blocks []HTBlock, pixels []byte, frameStride int, status []int32) error {
+	cp := p.c()
+	var st *C.int32_t
+	if len(status) > 0 {
+		st = (*C.int32_t)(unsafe.Pointer(&status[0]))
+	}
+	var sp *C.uint8_t
+	if len(stream) > 0 {
+		sp = (*C.uint8_t)(unsafe.Pointer(&stream[0]))
+	}
+	rc := C.j2k_inverse_ht(ctx, &cp, C.int(cbWidth), C.int(cbHeight), C.int(nframes), sp, C.size_t(len(stream)),
+		(*C.j2k_ht_cblk)(unsafe.Pointer(&blocks[0])), unsafe.Pointer(&pixels[0]), C.size_t(frameStride), nil, st)
+	if rc != 0 {
+		return lastErr(rc)
+	}
+	return nil
+}

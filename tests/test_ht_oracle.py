@@ -68,3 +68,22 @@ def test_empty_and_invalid_blocks(ht):
     assert rc == -2  # openjph_cleanup_decoder.go:125-127
     rc, out = ht.decode_block(b"\x00\x00\x00\x00", 8, 8, 10, 3)
     assert rc == -2  # Scup = 0 < 2: decoder.go:63-65
+
+
+def test_generator_round_trips_through_the_pinned_decoder(ht):
+    """oracle/ht_oracle.c's stream generator (an HT cleanup encoder written against the decoder, not a restatement of the
+    reference's encoder) is only trusted through this property: decode(encode(x)) == x for every block shape and magnitude."""
+    rng = np.random.default_rng(0)
+    for t in range(300):
+        w, h = int(rng.integers(1, 65)), int(rng.integers(1, 65))
+        if t % 10 == 0:
+            w, h = [(1024, 4), (4, 1024), (128, 32), (512, 8), (1, 1), (2, 1), (1, 2), (64, 64), (63, 64), (64, 63)][(t // 10) % 10]
+        bits = int(rng.integers(1, 30 if t % 7 == 0 else 17))
+        x = (rng.integers(-(1 << bits) + 1, 1 << bits, (h, w)) * (rng.random((h, w)) < rng.random())).astype(np.int32)
+        mmsb = min(29, bits - 1 + int(rng.integers(0, 3)))
+        data = ht.encode_block(x, mmsb)
+        if not x.any():
+            assert data == b""
+            continue
+        rc, y = ht.decode_block(data, w, h, mmsb + 1, mmsb)
+        assert rc == 0 and np.array_equal(x, y), (t, w, h, bits)
