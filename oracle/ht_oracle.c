@@ -697,3 +697,361 @@ EXPORT int orc_ht_encode_block(const int32_t* x, int width, int height, int miss
     free(msb); free(melb); free(vlcb); free(rho_prev); free(rho_cur); free(vn1); free(vn3); free(cn1); free(cn3);
     return lcup;
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * ORACLE of the HTJ2K cleanup-pass block ENCODER: a loop-for-loop restatement of HTEncoder.Encode ->
+ * encodeOpenJPHCleanup, /root/reference/jpeg2000/htj2k/encoder.go:54-68 and openjph_cleanup_encoder.go (line numbers below).
+ * PINNED: tests/test_ht_oracle.py re-encodes every code-block of the 14 OpenJPH interop codestreams from its decoded
+ * coefficients and compares with the bytes in the codestream -- the block-level form of the reference's own byte-parity
+ * test (htj2k/go_byte_parity_test.go:11-44). */
+
+typedef struct { uint8_t* buf; int n; int tmp, remaining, run, k, threshold; } omel_t;       /* :8-62 */
+static void omel_emit(omel_t* m, int v) {
+    m->tmp = (m->tmp << 1) | (v & 1);
+    if (--m->remaining == 0) {
+        m->buf[m->n++] = (uint8_t)m->tmp;
+        m->remaining = m->tmp == 0xFF ? 7 : 8;
+        m->tmp = 0;
+    }
+}
+static void omel_encode(omel_t* m, int bit) {
+    if (!bit) {
+        if (++m->run >= m->threshold) {
+            omel_emit(m, 1);
+            m->run = 0;
+            if (m->k < 12) m->k++;
+            m->threshold = 1 << MEL_E[m->k];
+        }
+        return;
+    }
+    omel_emit(m, 0);
+    for (int t = MEL_E[m->k]; t > 0;) { t--; omel_emit(m, (m->run >> t) & 1); }
+    m->run = 0;
+    if (m->k > 0) m->k--;
+    m->threshold = 1 << MEL_E[m->k];
+}
+
+typedef struct { uint8_t* buf; int n; int used, tmp, last_gt_8f; } ovlc_t;                   /* :64-112 */
+static void ovlc_encode(ovlc_t* v, int cwd, int len) {
+    while (len > 0) {
+        int avail = 8;
+        if (v->last_gt_8f) avail--;
+        avail -= v->used;
+        int t = avail < len ? avail : len;
+        v->tmp |= (cwd & ((1 << t) - 1)) << v->used;
+        v->used += t;
+        avail -= t;
+        len -= t;
+        cwd >>= t;
+        if (avail == 0) {
+            if (v->last_gt_8f && v->tmp != 0x7F) { v->last_gt_8f = 0; continue; }
+            v->buf[v->n++] = (uint8_t)v->tmp;
+            v->last_gt_8f = v->tmp > 0x8F;
+            v->tmp = 0;
+            v->used = 0;
+        }
+    }
+}
+
+typedef struct { uint8_t* buf; int n; int max_bits, used; uint32_t tmp; } oms_t;            /* :114-166 */
+static void oms_encode(oms_t* m, uint32_t cwd, int len) {
+    while (len > 0) {
+        int t = m->max_bits - m->used < len ? m->max_bits - m->used : len;
+        m->tmp |= (cwd & (uint32_t)(((uint64_t)1 << t) - 1)) << m->used;
+        m->used += t;
+        cwd = t >= 32 ? 0 : cwd >> t;
+        len -= t;
+        if (m->used >= m->max_bits) {
+            uint8_t b = (uint8_t)m->tmp;
+            m->buf[m->n++] = b;
+            m->max_bits = b == 0xFF ? 7 : 8;
+            m->tmp = 0;
+            m->used = 0;
+        }
+    }
+}
+static void oms_terminate(oms_t* m) {
+    if (m->used != 0) {
+        int t = m->max_bits - m->used;
+        m->tmp |= (uint32_t)((0xFF & ((1 << t) - 1)) << m->used);
+        m->used += t;
+        if ((uint8_t)m->tmp != 0xFF) m->buf[m->n++] = (uint8_t)m->tmp;
+    } else if (m->max_bits == 7 && m->n > 0) m->n--;
+}
+
+typedef struct { int pre, pre_len, suf, suf_len, ext, ext_len; } ouvlc_t;                    /* :168-198 */
+static ouvlc_t ouvlc(int code) {
+    ouvlc_t e = {0, 0, 0, 0, 0, 0};
+    if (code <= 0) return e;
+    if (code == 1) { e.pre = 1; e.pre_len = 1; return e; }
+    if (code == 2) { e.pre = 2; e.pre_len = 2; return e; }
+    if (code <= 4) { e.pre = 4; e.pre_len = 3; e.suf = code - 3; e.suf_len = 1; return e; }
+    if (code <= 32) { e.pre = 0; e.pre_len = 3; e.suf = code - 5; e.suf_len = 5; return e; }
+    e.pre = 0; e.pre_len = 3; e.suf = 28 + ((code - 33) % 4); e.suf_len = 5; e.ext = (code - 33) / 4; e.ext_len = 4;
+    return e;
+}
+
+static uint16_t ENC0[2048], ENC1[2048];
+static int enc_ready;
+static void init_enc_table(const unsigned char (*src)[7], int n, uint16_t* dst) {            /* :432-470 */
+    for (int i = 0; i < 2048; i++) {
+        int cq = i >> 8, rho = (i >> 4) & 0xF, eps = i & 0xF;
+        dst[i] = 0;
+        if ((eps & rho) != eps || (rho == 0 && cq == 0)) continue;
+        const unsigned char* best = NULL;
+        if (eps != 0) {
+            int best_ek = -1;
+            for (int j = 0; j < n; j++) {
+                const unsigned char* e = src[j];
+                if (e[0] == cq && e[1] == rho && e[2] == 1 && (eps & e[3]) == e[4]) {
+                    int ones = __builtin_popcount(e[3]);
+                    if (ones >= best_ek) { best = e; best_ek = ones; }
+                }
+            }
+        } else {
+            for (int j = 0; j < n; j++) {
+                const unsigned char* e = src[j];
+                if (e[0] == cq && e[1] == rho && e[2] == 0) { best = e; break; }
+            }
+        }
+        if (best) dst[i] = (uint16_t)((best[5] << 8) | (best[6] << 4) | best[3]);
+    }
+}
+static void init_enc(void) {
+    if (enc_ready) return;
+    init_enc_table(HT_VLC_SRC0, (int)(sizeof(HT_VLC_SRC0) / 7), ENC0);
+    init_enc_table(HT_VLC_SRC1, (int)(sizeof(HT_VLC_SRC1) / 7), ENC1);
+    enc_ready = 1;
+}
+/* which: 0 ojphEncoderVLCTable0, 1 ojphEncoderVLCTable1 (2048 entries each) */
+EXPORT int orc_ht_enc_table(int which, uint16_t* out) {
+    init_enc();
+    memcpy(out, which ? ENC1 : ENC0, 2048 * 2);
+    return 2048;
+}
+
+typedef struct { const uint32_t* cb; int width, height; unsigned p; } oenc_t;
+
+static void prep_sample(const oenc_t* h, int x, int y, int idx, int* rho, int* eqmax, int* eq, uint32_t* s) {   /* :396-413 */
+    if (x >= h->width || y >= h->height) return;
+    uint32_t t = h->cb[y * h->width + x];
+    uint32_t val = (t + t) >> h->p;
+    val &= ~(uint32_t)1;
+    if (val == 0) return;
+    *rho += 1 << (idx % 4);
+    val--;
+    eq[idx] = bitlen32(val);
+    if (eq[idx] > *eqmax) *eqmax = eq[idx];
+    val--;
+    s[idx] = val + (t >> 31);
+}
+static void prep_quad(const oenc_t* h, int x, int y, int off, int* rho, int* eqmax, int* eq, uint32_t* s) {      /* :382-394 */
+    prep_sample(h, x, y, off, rho, eqmax, eq, s);
+    prep_sample(h, x, y + 1, off + 1, rho, eqmax, eq, s);
+    prep_sample(h, x + 1, y, off + 2, rho, eqmax, eq, s);
+    prep_sample(h, x + 1, y + 1, off + 3, rho, eqmax, eq, s);
+}
+static int oeps(const int* eq, int eqmax, int u) {                                          /* :415-426 */
+    if (u <= 0) return 0;
+    int eps = 0;
+    for (int i = 0; i < 4; i++) if (eq[i] == eqmax) eps |= 1 << i;
+    return eps;
+}
+static int otuple(int initial, int cq, int rho, int eps) {                                  /* :428-438 */
+    if (rho == 0 && cq == 0) return 0;
+    return initial ? ENC0[(cq << 8) | (rho << 4) | eps] : ENC1[(cq << 8) | (rho << 4) | eps];
+}
+static void oms_quad(oms_t* ms, int rho, int uq, int tuple, const uint32_t* s) {            /* :472-483 */
+    for (int i = 0; i < 4; i++) {
+        if (!(rho & (1 << i))) continue;
+        int m = uq - ((tuple >> i) & 1);
+        if (m < 0) m = 0;
+        oms_encode(ms, s[i] & (uint32_t)(((uint64_t)1 << m) - 1), m);
+    }
+}
+static void ouvlc_initial(ovlc_t* v, int u0, int u1) {                                      /* :485-511 */
+    ouvlc_t c0, c1;
+    if (u0 > 2 && u1 > 2) {
+        c0 = ouvlc(u0 - 2); c1 = ouvlc(u1 - 2);
+        ovlc_encode(v, c0.pre, c0.pre_len); ovlc_encode(v, c1.pre, c1.pre_len);
+        ovlc_encode(v, c0.suf, c0.suf_len); ovlc_encode(v, c1.suf, c1.suf_len);
+        return;
+    }
+    if (u0 > 2 && u1 > 0) {
+        c0 = ouvlc(u0);
+        ovlc_encode(v, c0.pre, c0.pre_len); ovlc_encode(v, u1 - 1, 1); ovlc_encode(v, c0.suf, c0.suf_len);
+        return;
+    }
+    c0 = ouvlc(u0); c1 = ouvlc(u1);
+    ovlc_encode(v, c0.pre, c0.pre_len); ovlc_encode(v, c1.pre, c1.pre_len);
+    ovlc_encode(v, c0.suf, c0.suf_len); ovlc_encode(v, c1.suf, c1.suf_len);
+}
+static void ouvlc_noninitial(ovlc_t* v, int u0, int u1) {                                   /* :513-520 */
+    ouvlc_t c0 = ouvlc(u0), c1 = ouvlc(u1);
+    ovlc_encode(v, c0.pre, c0.pre_len); ovlc_encode(v, c1.pre, c1.pre_len);
+    ovlc_encode(v, c0.suf, c0.suf_len); ovlc_encode(v, c1.suf, c1.suf_len);
+}
+static int imax(int a, int b) { return a > b ? a : b; }
+static int imin(int a, int b) { return a < b ? a : b; }
+
+/* HTEncoder.Encode (encoder.go:54-68) -> encodeOpenJPHCleanup (openjph_cleanup_encoder.go:200-252).
+ * Returns the number of bytes written to out (0: the block is empty, "return nil, nil"), or
+ * -1 invalid Kmax (:201-203 / encoder.go:64-66), -5 "HTJ2K cleanup suffix is empty" (:246-248), -6 out too small. */
+EXPORT int orc_ht_encode_ref(const int32_t* data, int width, int height, int kmax, uint8_t* out, int cap) {
+    init_tables();
+    init_enc();
+    if (kmax <= 0 || kmax >= 31) return -1;
+    const int n = width * height;
+    uint32_t* cb = (uint32_t*)malloc((size_t)n * 4);
+    unsigned shift = (unsigned)(31 - kmax);
+    uint32_t max_val = 0;
+    for (int i = 0; i < n; i++) {
+        uint32_t sign = 0;
+        int32_t mag = data[i];
+        if (mag < 0) { sign = 0x80000000u; mag = (int32_t)(0u - (uint32_t)mag); }
+        uint32_t val = (uint32_t)mag << shift;
+        cb[i] = sign | val;
+        max_val |= val;
+    }
+    if (max_val < ((uint32_t)1 << shift)) { free(cb); return 0; }
+    int missing_msbs = kmax - 1;
+    oenc_t h = {cb, width, height, (unsigned)(30 - missing_msbs)};
+    size_t room = (size_t)n * 5 + 256;
+    omel_t mel = {(uint8_t*)malloc(room), 0, 0, 8, 0, 0, 1};
+    ovlc_t vlc = {(uint8_t*)malloc(room), 0, 4, 0xF, 1};
+    vlc.buf[vlc.n++] = 0xFF;
+    oms_t ms = {(uint8_t*)malloc(room), 0, 8, 0, 0};
+    int qn = (width + 1) / 2 + 2;
+    uint8_t* e_val = (uint8_t*)calloc((size_t)qn + 2, 1);
+    uint8_t* cx_val = (uint8_t*)calloc((size_t)qn + 2, 1);
+    {   /* encodeOJPHInitialRows, :254-313 */
+        int lep = 0, lcxp = 0, cq0 = 0;
+        e_val[lep] = 0; cx_val[lcxp] = 0;
+        for (int x = 0; x < width; x += 4) {
+            int eqmax[2] = {0, 0}, eq[8] = {0}, rho[2] = {0, 0};
+            uint32_t s[8] = {0};
+            prep_quad(&h, x, 0, 0, &rho[0], &eqmax[0], eq, s);
+            int uq0 = imax(eqmax[0], 1), u0 = uq0 - 1;
+            int eps0 = oeps(eq, eqmax[0], u0);
+            e_val[lep] = (uint8_t)imax(e_val[lep], eq[1]);
+            lep++;
+            e_val[lep] = (uint8_t)eq[3];
+            cx_val[lcxp] |= (uint8_t)((rho[0] & 2) >> 1);
+            lcxp++;
+            cx_val[lcxp] = (uint8_t)((rho[0] & 8) >> 3);
+            int t0 = otuple(1, cq0, rho[0], eps0);
+            ovlc_encode(&vlc, t0 >> 8, (t0 >> 4) & 7);
+            if (cq0 == 0) omel_encode(&mel, rho[0] != 0);
+            oms_quad(&ms, rho[0], uq0, t0, s);
+            int u1 = 0;
+            if (x + 2 < width) {
+                prep_quad(&h, x + 2, 0, 4, &rho[1], &eqmax[1], eq, s);
+                int cq1 = (rho[0] >> 1) | (rho[0] & 1);
+                int uq1 = imax(eqmax[1], 1);
+                u1 = uq1 - 1;
+                int eps1 = oeps(eq + 4, eqmax[1], u1);
+                e_val[lep] = (uint8_t)imax(e_val[lep], eq[5]);
+                lep++;
+                e_val[lep] = (uint8_t)eq[7];
+                cx_val[lcxp] |= (uint8_t)((rho[1] & 2) >> 1);
+                lcxp++;
+                cx_val[lcxp] = (uint8_t)((rho[1] & 8) >> 3);
+                int t1 = otuple(1, cq1, rho[1], eps1);
+                ovlc_encode(&vlc, t1 >> 8, (t1 >> 4) & 7);
+                if (cq1 == 0) omel_encode(&mel, rho[1] != 0);
+                oms_quad(&ms, rho[1], uq1, t1, s + 4);
+            }
+            if (u0 > 0 && u1 > 0) omel_encode(&mel, imin(u0, u1) > 2);
+            ouvlc_initial(&vlc, u0, u1);
+            cq0 = (rho[1] >> 1) | (rho[1] & 1);
+        }
+        e_val[lep + 1] = 0;
+    }
+    for (int y = 2; y < height; y += 2) {   /* encodeOJPHSubsequentRows, :315-380 */
+        int lep = 0;
+        int max_e = imax(e_val[lep], e_val[lep + 1]) - 1;
+        e_val[lep] = 0;
+        int lcxp = 0;
+        int cq0 = cx_val[lcxp] + (cx_val[lcxp + 1] << 2);
+        cx_val[lcxp] = 0;
+        for (int x = 0; x < width; x += 4) {
+            int eqmax[2] = {0, 0}, eq[8] = {0}, rho[2] = {0, 0};
+            uint32_t s[8] = {0};
+            prep_quad(&h, x, y, 0, &rho[0], &eqmax[0], eq, s);
+            int kappa = 1;
+            if (rho[0] & (rho[0] - 1)) kappa = imax(1, max_e);
+            int uq0 = imax(eqmax[0], kappa), u0 = uq0 - kappa;
+            int eps0 = oeps(eq, eqmax[0], u0);
+            e_val[lep] = (uint8_t)imax(e_val[lep], eq[1]);
+            lep++;
+            max_e = imax(e_val[lep], e_val[lep + 1]) - 1;
+            e_val[lep] = (uint8_t)eq[3];
+            cx_val[lcxp] |= (uint8_t)((rho[0] & 2) >> 1);
+            lcxp++;
+            int cq1 = cx_val[lcxp] + (cx_val[lcxp + 1] << 2);
+            cx_val[lcxp] = (uint8_t)((rho[0] & 8) >> 3);
+            int t0 = otuple(0, cq0, rho[0], eps0);
+            ovlc_encode(&vlc, t0 >> 8, (t0 >> 4) & 7);
+            if (cq0 == 0) omel_encode(&mel, rho[0] != 0);
+            oms_quad(&ms, rho[0], uq0, t0, s);
+            int u1 = 0;
+            if (x + 2 < width) {
+                prep_quad(&h, x + 2, y, 4, &rho[1], &eqmax[1], eq, s);
+                kappa = 1;
+                if (rho[1] & (rho[1] - 1)) kappa = imax(1, max_e);
+                cq1 |= ((rho[0] & 4) >> 1) | ((rho[0] & 8) >> 2);
+                int uq1 = imax(eqmax[1], kappa);
+                u1 = uq1 - kappa;
+                int eps1 = oeps(eq + 4, eqmax[1], u1);
+                e_val[lep] = (uint8_t)imax(e_val[lep], eq[5]);
+                lep++;
+                max_e = imax(e_val[lep], e_val[lep + 1]) - 1;
+                e_val[lep] = (uint8_t)eq[7];
+                cx_val[lcxp] |= (uint8_t)((rho[1] & 2) >> 1);
+                lcxp++;
+                cq0 = cx_val[lcxp] + (cx_val[lcxp + 1] << 2);
+                cx_val[lcxp] = (uint8_t)((rho[1] & 8) >> 3);
+                int t1 = otuple(0, cq1, rho[1], eps1);
+                ovlc_encode(&vlc, t1 >> 8, (t1 >> 4) & 7);
+                if (cq1 == 0) omel_encode(&mel, rho[1] != 0);
+                oms_quad(&ms, rho[1], uq1, t1, s + 4);
+            }
+            ouvlc_noninitial(&vlc, u0, u1);
+            cq0 |= ((rho[1] & 4) >> 1) | ((rho[1] & 8) >> 2);
+        }
+    }
+    /* terminateOJPHMELVLC, :522-545 */
+    if (mel.run > 0) omel_emit(&mel, 1);
+    mel.tmp <<= mel.remaining;
+    int mel_mask = (0xFF << mel.remaining) & 0xFF;
+    int vlc_mask = vlc.used > 0 ? 0xFF >> (8 - vlc.used) : 0;
+    if ((mel_mask | vlc_mask) != 0) {
+        int fuse = mel.tmp | vlc.tmp;
+        if ((((fuse ^ mel.tmp) & mel_mask) | ((fuse ^ vlc.tmp) & vlc_mask)) == 0 && fuse != 0xFF && vlc.n > 1) {
+            mel.buf[mel.n++] = (uint8_t)fuse;
+        } else {
+            mel.buf[mel.n++] = (uint8_t)mel.tmp;
+            vlc.buf[vlc.n++] = (uint8_t)vlc.tmp;
+        }
+    }
+    oms_terminate(&ms);
+    int rc;
+    int suffix = mel.n + vlc.n;
+    if (suffix == 0) rc = -5;
+    else if (ms.n + suffix > cap) rc = -6;
+    else {
+        memcpy(out, ms.buf, (size_t)ms.n);
+        memcpy(out + ms.n, mel.buf, (size_t)mel.n);
+        /* ojphVLCWriter.bytes(), :104-112: newest byte first, the Scup placeholder last */
+        int o = ms.n + mel.n;
+        for (int i = vlc.n - 1; i >= 1; i--) out[o++] = vlc.buf[i];
+        out[o++] = vlc.buf[0];
+        rc = o;
+        if (rc >= 2) {   /* writeScupLocator, encoder.go:84-90 */
+            out[rc - 1] = (uint8_t)(suffix >> 4);
+            out[rc - 2] = (uint8_t)((out[rc - 2] & 0xF0) | (suffix & 0x0F));
+        }
+    }
+    free(cb); free(mel.buf); free(vlc.buf); free(ms.buf); free(e_val); free(cx_val);
+    return rc;
+}

@@ -54,6 +54,19 @@ class HtOracle:
         assert n >= 0, n
         return out[:n].tobytes()
 
+    def encode_ref(self, x, kmax):
+        """oracle restatement of HTEncoder.Encode (htj2k/encoder.go:54-68): bytes (b"" for an empty block) or a negative code"""
+        a = np.ascontiguousarray(x, np.int32)
+        h, w = a.shape
+        out = np.zeros(w * h * 6 + 512, np.uint8)
+        n = self.lib.orc_ht_encode_ref(_p(a), C.c_int(w), C.c_int(h), C.c_int(kmax), _p(out), C.c_int(out.size))
+        return out[:n].tobytes() if n >= 0 else n
+
+    def enc_table(self, which):
+        out = np.zeros(2048, np.uint16)
+        self.lib.orc_ht_enc_table(C.c_int(which), _p(out))
+        return out
+
     def decode_blocks(self, stream, offsets, lengths, kmax, mmsb, widths, heights, out_offsets, total_samples):
         """every array one entry per block; returns (block-major int32 buffer, status per block)"""
         n = len(offsets)
