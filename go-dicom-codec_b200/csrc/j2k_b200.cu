@@ -34,6 +34,7 @@
 #include "j2k_pointwise.cuh"
 #include "j2k_ring.cuh"
 #include "j2k_ht.cuh"
+#include "j2k_ht_enc.cuh"
 
 #ifndef J2K_LAUNCH
 #define J2K_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
@@ -240,6 +241,11 @@ struct DeviceCtx {
     DevBuf ht_bytes[2], ht_desc[2], ht_status[2];  // HTJ2K block decoding of a sub-batch: cleanup segments, records, result codes
     DevBuf ht_scratch;                             // (inf, u_q) per quad between the two HT kernels
     cudaEvent_t ev_ht = nullptr; bool ev_ht_used = false;
+    // HTJ2K block encoding: per-block scratch slots, block info, stream offsets, per-block Kmax; per sub-batch slot the compact
+    // stream + records on the device and a pinned landing area for (total, records)
+    DevBuf he_slots, he_info, he_off, he_kmax, he_bytes[2], he_recs[2];
+    std::vector<unsigned char> he_kmax_host;
+    void* he_pin[2] = {nullptr, nullptr}; size_t he_pin_cap[2] = {0, 0};
     std::map<std::string, std::unique_ptr<Plan>> plans;
     long long use_clock = 0;   // LRU stamps of `plans`
     std::map<std::string, std::unique_ptr<struct BlockTable>> block_tables;
@@ -1845,6 +1851,62 @@ int launch_ht_decode(j2k_ctx* ctx, DeviceCtx& d, BlockTable& T, int cbw, int cbh
     return 0;
 }
 
+// Per-block Kmax in block-table order from the caller's [components][3 * levels + 1] table (bandNumbps per sub-band:
+// index 0 = LL, then HL, LH, HH from the coarsest resolution; Encoder.bandNumbps, encoder.go:3303).
+int ht_block_kmax(const Spec& s, int cbw, int cbh, const uint8_t* kmax, std::vector<unsigned char>& out, int& kmax_max) {
+    out.clear();
+    kmax_max = 0;
+    const int nb = 3 * s.L + 1;
+    std::vector<j2k_cblk> t;
+    for (const TileGeom& g : s.tiles) {
+        t.clear();
+        codeblock_layout(g.tw, g.th, s.L, cbw, cbh, t);
+        for (int c = 0; c < s.C; c++)
+            for (const j2k_cblk& b : t) {
+                const int idx = b.res == 0 ? 0 : 1 + 3 * (b.res - 1) + (b.band - 1);
+                const int k = kmax[c * nb + idx];
+                // "invalid HTJ2K Kmax" (openjph_cleanup_encoder.go:201-203) / "requires Kmax coding context" (encoder.go:64-66)
+                if (k <= 0 || k >= 31) return fail(J2K_ERR_INVALID_ARG, "invalid HTJ2K Kmax: %d (component %d, sub-band %d)", k, c, idx);
+                if (k > kmax_max) kmax_max = k;
+                out.push_back((unsigned char)k);
+            }
+    }
+    return 0;
+}
+
+// Four launches (j2k_ht_enc.cuh).  d_kmax: per-block Kmax (block-table order) on the device; d_offsets: total + 1 words, the
+// last one receives the size of the compact stream; nothing is written to d_bytes beyond `cap`.
+int launch_ht_encode(j2k_ctx* ctx, DeviceCtx& d, BlockTable& T, int cbw, int cbh, int kmax_max, int nframes, const int32_t* d_coeffs,
+                     const unsigned char* d_kmax, unsigned char* d_bytes, unsigned long long cap, HtBlock* d_recs,
+                     unsigned long long* d_offsets, cudaStream_t st) {
+    const long long total = (long long)T.nblocks * nframes;
+    if (total <= 0) return 0;
+    const HtEncLayout L = ht_enc_layout(cbw, cbh, kmax_max);
+    int rc = d.he_slots.ensure((size_t)total * L.slot_bytes + 64);
+    if (rc) return rc;
+    if ((rc = d.he_info.ensure((size_t)total * sizeof(HtEncInfo) + 64))) return rc;
+    const int warps = 4, wsm = ht_enc_warp_smem(cbw);
+    J2K_LAUNCH_SMEM(ht_enc_quads_kernel, (unsigned)((total + warps - 1) / warps), warps * 32, warps * wsm, st, (const int*)d_coeffs,
+                    T.coeffs_per_frame, (const BlockEntry*)T.tab.p, d_kmax, T.nblocks, total, (unsigned char*)d.he_slots.p, L,
+                    (HtEncInfo*)d.he_info.p, wsm);
+    CK(cudaGetLastError());
+    J2K_LAUNCH(ht_enc_pack_kernel, (unsigned)((total + 31) / 32), 32, st, total, (unsigned char*)d.he_slots.p, L, (HtEncInfo*)d.he_info.p);
+    CK(cudaGetLastError());
+    J2K_LAUNCH(ht_enc_scan_kernel, 1, 1024, st, (const HtEncInfo*)d.he_info.p, total, d_offsets);
+    CK(cudaGetLastError());
+    J2K_LAUNCH(ht_enc_compact_kernel, (unsigned)((total + warps - 1) / warps), warps * 32, st, total, (const unsigned char*)d.he_slots.p, L,
+               (const HtEncInfo*)d.he_info.p, (const unsigned long long*)d_offsets, d_kmax, T.nblocks, d_bytes, cap, d_recs);
+    CK(cudaGetLastError());
+    ctx->launches += 4;
+    return 0;
+}
+
+// upper bound of the compact stream of `total` blocks (what the per-block output areas can hold)
+size_t ht_enc_bound(int cbw, int cbh, int kmax_max, long long total) {
+    const HtEncLayout L = ht_enc_layout(cbw, cbh, kmax_max);
+    return (size_t)total * (size_t)(L.slot_bytes - L.ms_out_off);
+}
+
 // Per-component MaxShift values of the caller (NULL: no ROI) -> kernel argument.
 int make_roi(const int32_t* roi_maxshift, int C, RoiShifts& r) {
     memset(&r, 0, sizeof r);
@@ -2410,6 +2472,7 @@ void j2k_shutdown(j2k_ctx* ctx) {
         for (auto& ev : d.ev_t) if (ev) cudaEventDestroy(ev);
         for (int k = 0; k < 2; k++) { cudaEventDestroy(d.ev_in[k]); cudaEventDestroy(d.ev_k[k]); cudaEventDestroy(d.ev_out[k]); }
         if (d.ev_ht) cudaEventDestroy(d.ev_ht);
+        for (int k = 0; k < 2; k++) if (d.he_pin[k]) cudaFreeHost(d.he_pin[k]);
         cudaStreamDestroy(d.s_main); cudaStreamDestroy(d.s_h2d); cudaStreamDestroy(d.s_d2h);
     }
     pool_stop(ctx);
@@ -2950,6 +3013,157 @@ int j2k_ht_decode_device(j2k_ctx* ctx, int dev, const j2k_inv_params* p, int cb_
     if ((rc = get_block_table(d, s, cb_width, cb_height, (long long)j2k_inv_coeff_count(p), &BT))) return rc;
     return launch_ht_decode(ctx, d, *BT, cb_width, cb_height, nframes, d_bytes, (const HtBlock*)d_cblks, d_out, to_planes ? 1 : 0, d_status,
                             cuda_stream ? (cudaStream_t)cuda_stream : d.s_main);
+}
+
+// ---- HTJ2K block encoding on the device (encode side)
+
+namespace ht_host_enc {   // host copy of the device table (same generated file)
+#define J2K_HT_TABLE static const
+#include "j2k_ht_enc_tables.inc"
+#undef J2K_HT_TABLE
+}  // namespace ht_host_enc
+
+int j2k_ht_enc_table(int which, uint16_t* out) {
+    if (which != 0 && which != 1) return fail(J2K_ERR_INVALID_ARG, "no such table: %d", which);
+    if (out) memcpy(out, which ? ht_host_enc::HT_ENC_TBL1 : ht_host_enc::HT_ENC_TBL0, 2048 * 2);
+    return 2048;
+}
+
+size_t j2k_ht_encode_bound(const j2k_fwd_params* p, int cb_width, int cb_height, int kmax_max, int nframes) {
+    if (!p || validate_ht_cb(cb_width, cb_height) || kmax_max <= 0 || kmax_max >= 31 || nframes <= 0) return 0;
+    return ht_enc_bound(cb_width, cb_height, kmax_max, (long long)j2k_fwd_block_count(p, cb_width, cb_height) * nframes);
+}
+
+int j2k_ht_encode_device(j2k_ctx* ctx, int dev, const j2k_fwd_params* p, int cb_width, int cb_height, int nframes, const int32_t* d_coeffs,
+                         const uint8_t* kmax, uint8_t* d_bytes, size_t bytes_cap, j2k_ht_cblk* d_cblks, uint64_t* d_offsets,
+                         void* cuda_stream) {
+    CtxGuard cg_(ctx);
+    int rc = set_dev(ctx, dev);
+    if (rc) return rc;
+    if (!p) return fail(J2K_ERR_INVALID_ARG, "params is NULL");
+    if ((rc = validate_ht_cb(cb_width, cb_height))) return rc;
+    Spec s;
+    if ((rc = spec_from_fwd(p, false, s))) return rc;
+    if (!d_coeffs || !kmax || !d_bytes || !d_cblks || !d_offsets || nframes <= 0) return fail(J2K_ERR_INVALID_ARG, "bad buffers / nframes");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceCtx& d = ctx->devs[dev];
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : d.s_main;
+    int kmax_max = 0;
+    // the previous call's upload of the table may still be in flight from this vector
+    CK(cudaStreamSynchronize(st));
+    if ((rc = ht_block_kmax(s, cb_width, cb_height, kmax, d.he_kmax_host, kmax_max))) return rc;
+    BlockTable* BT = nullptr;
+    if ((rc = get_block_table(d, s, cb_width, cb_height, (long long)j2k_fwd_coeff_count(p), &BT))) return rc;
+    if ((rc = d.he_kmax.ensure(d.he_kmax_host.size() + 16))) return rc;
+    CK(cudaMemcpyAsync(d.he_kmax.p, d.he_kmax_host.data(), d.he_kmax_host.size(), cudaMemcpyHostToDevice, st));
+    return launch_ht_encode(ctx, d, *BT, cb_width, cb_height, kmax_max, nframes, d_coeffs, (const unsigned char*)d.he_kmax.p, d_bytes,
+                            (unsigned long long)bytes_cap, (HtBlock*)d_cblks, (unsigned long long*)d_offsets, st);
+}
+
+// Pixels up, compressed cleanup segments + records down.  Sub-batches on three streams with a lag of one: the size of
+// sub-batch i's stream is read (a host wait on its kernels) after sub-batch i + 1 has been enqueued, then its bytes leave on
+// the download stream while i + 1 computes.
+int j2k_forward_ht(j2k_ctx* ctx, const j2k_fwd_params* p, int cb_width, int cb_height, int nframes, const void* pixels,
+                   size_t frame_stride_bytes, const uint8_t* kmax, uint8_t* bytes_out, size_t bytes_cap, size_t* nbytes_out,
+                   j2k_ht_cblk* cblks_out) {
+    CtxGuard cg_(ctx);
+    if (!ctx) return fail(J2K_ERR_INVALID_ARG, "context is NULL");
+    if (!p) return fail(J2K_ERR_INVALID_ARG, "params is NULL");
+    int rc = validate_ht_cb(cb_width, cb_height);
+    if (rc) return rc;
+    Spec s;
+    if ((rc = spec_from_fwd(p, false, s))) return rc;
+    if (!pixels || !kmax || !bytes_out || !cblks_out || !nbytes_out) return fail(J2K_ERR_INVALID_ARG, "NULL buffer");
+    if (nframes <= 0) return fail(J2K_ERR_INVALID_ARG, "nframes must be positive");
+    const size_t pixb = j2k_fwd_pixel_bytes(p);
+    const long long cpf = (long long)j2k_fwd_coeff_count(p);
+    const int bps = s.bit_depth <= 8 ? 1 : 2;
+    if (frame_stride_bytes < pixb || frame_stride_bytes % bps) return fail(J2K_ERR_SIZE, "bad frame stride");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if ((rc = sync_dev(ctx, 0))) return rc;   // the slot buffers may still serve an asynchronous job
+    DeviceCtx& d = ctx->devs[0];
+    if ((rc = set_dev(ctx, 0))) return rc;
+    int kmax_max = 0;
+    if ((rc = ht_block_kmax(s, cb_width, cb_height, kmax, d.he_kmax_host, kmax_max))) return rc;
+    BlockTable* BT = nullptr;
+    if ((rc = get_block_table(d, s, cb_width, cb_height, cpf, &BT))) return rc;
+    const size_t nblk = (size_t)BT->nblocks;
+    if ((rc = d.he_kmax.ensure(d.he_kmax_host.size() + 16))) return rc;
+    CK(cudaMemcpyAsync(d.he_kmax.p, d.he_kmax_host.data(), d.he_kmax_host.size(), cudaMemcpyHostToDevice, d.s_main));
+    static const long long sub_samples = (long long)env_int("J2K_SUBBATCH_MSAMPLES", 16) << 20;
+    int sub = (int)(sub_samples / (cpf > 0 ? cpf : 1));
+    if (sub < 1) sub = 1;
+    if (sub > nframes) sub = nframes;
+    struct Pend { int slot, f0, n; };
+    size_t base = 0;
+    bool have = false, used_out[2] = {false, false}, used_k[2] = {false, false};
+    Pend pend{};
+    auto finish = [&](const Pend& q) -> int {
+        CK(cudaEventSynchronize(d.ev_k[q.slot]));
+        const size_t count = (size_t)q.n * nblk;
+        const unsigned long long tot = *(const unsigned long long*)d.he_pin[q.slot];
+        const HtBlock* r = (const HtBlock*)((const char*)d.he_pin[q.slot] + 16);
+        if (base + tot > bytes_cap) {
+            *nbytes_out = base + (size_t)tot;
+            return fail(J2K_ERR_SIZE, "the compressed stream needs more than the %zu bytes provided (%zu so far)", bytes_cap, base + (size_t)tot);
+        }
+        if (tot) CK(cudaMemcpyAsync(bytes_out + base, d.he_bytes[q.slot].p, (size_t)tot, cudaMemcpyDeviceToHost, d.s_d2h));
+        CK(cudaEventRecord(d.ev_out[q.slot], d.s_d2h));
+        used_out[q.slot] = true;
+        j2k_ht_cblk* dst = cblks_out + (size_t)q.f0 * nblk;
+        for (size_t i = 0; i < count; i++) {
+            dst[i].offset = r[i].offset + base; dst[i].length = r[i].length; dst[i].kmax = r[i].kmax; dst[i].missing_msbs = r[i].mmsb;
+            dst[i].reserved = 0;
+        }
+        base += (size_t)tot;
+        return 0;
+    };
+    int it = 0;
+    for (int b = 0; b < nframes && rc == 0; b += sub, it++) {
+        const int nb = b + sub <= nframes ? sub : nframes - b;
+        const int slot = it & 1;
+        const size_t count = (size_t)nb * nblk;
+        const size_t bound = ht_enc_bound(cb_width, cb_height, kmax_max, (long long)count);
+        if ((rc = d.in[slot].ensure((size_t)nb * pixb))) break;
+        if ((rc = d.out[slot].ensure((size_t)nb * cpf * 4))) break;
+        if ((rc = d.he_bytes[slot].ensure(bound + 64))) break;
+        if ((rc = d.he_recs[slot].ensure(count * sizeof(HtBlock) + 64))) break;
+        if ((rc = d.he_off.ensure((count + 1) * 8 + 64))) break;
+        const size_t pin_need = 16 + count * sizeof(HtBlock);
+        if (d.he_pin_cap[slot] < pin_need) {
+            if (d.he_pin[slot]) cudaFreeHost(d.he_pin[slot]);
+            d.he_pin[slot] = nullptr; d.he_pin_cap[slot] = 0;
+            CK(cudaHostAlloc(&d.he_pin[slot], pin_need + pin_need / 4, cudaHostAllocPortable));
+            d.he_pin_cap[slot] = pin_need + pin_need / 4;
+        }
+        if (used_k[slot]) CK(cudaStreamWaitEvent(d.s_h2d, d.ev_k[slot], 0));   // the slot's previous kernels have consumed `in`
+        const unsigned char* src = (const unsigned char*)pixels + (size_t)b * frame_stride_bytes;
+        if (frame_stride_bytes == pixb) CK(cudaMemcpyAsync(d.in[slot].p, src, (size_t)nb * pixb, cudaMemcpyHostToDevice, d.s_h2d));
+        else CK(cudaMemcpy2DAsync(d.in[slot].p, pixb, src, frame_stride_bytes, pixb, nb, cudaMemcpyHostToDevice, d.s_h2d));
+        CK(cudaEventRecord(d.ev_in[slot], d.s_h2d));
+        CK(cudaStreamWaitEvent(d.s_main, d.ev_in[slot], 0));
+        if (used_out[slot]) CK(cudaStreamWaitEvent(d.s_main, d.ev_out[slot], 0));   // its previous stream has left the device
+        Plan* P = nullptr;
+        if ((rc = get_plan(d, s, p, sizeof *p, nb, (long long)(pixb / bps), &P))) break;
+        rc = run_plan(ctx, *P, d.in[slot].p, d.out[slot].p, nullptr, false, d.s_main);
+        if (rc < 0) break;
+        if ((rc = launch_ht_encode(ctx, d, *BT, cb_width, cb_height, kmax_max, nb, (const int32_t*)d.out[slot].p,
+                                   (const unsigned char*)d.he_kmax.p, (unsigned char*)d.he_bytes[slot].p, (unsigned long long)bound,
+                                   (HtBlock*)d.he_recs[slot].p, (unsigned long long*)d.he_off.p, d.s_main))) break;
+        CK(cudaMemcpyAsync(d.he_pin[slot], (const unsigned long long*)d.he_off.p + count, 8, cudaMemcpyDeviceToHost, d.s_main));
+        CK(cudaMemcpyAsync((char*)d.he_pin[slot] + 16, d.he_recs[slot].p, count * sizeof(HtBlock), cudaMemcpyDeviceToHost, d.s_main));
+        CK(cudaEventRecord(d.ev_k[slot], d.s_main));
+        used_k[slot] = true;
+        if (have && (rc = finish(pend))) break;
+        pend = Pend{slot, b, nb};
+        have = true;
+    }
+    if (rc == 0 && have) rc = finish(pend);
+    int r2 = sync_dev(ctx, 0);
+    if (rc == 0) rc = r2;
+    d.ev_k_used[0] = d.ev_k_used[1] = false; d.ev_out_used[0] = d.ev_out_used[1] = false;
+    if (rc == 0) *nbytes_out = base;
+    return rc < 0 ? rc : J2K_OK;
 }
 
 // ---- asynchronous

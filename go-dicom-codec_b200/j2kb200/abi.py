@@ -269,6 +269,10 @@ def load(path: str | None = None) -> C.CDLL:
         "j2k_submit_inverse_ht": (C.c_int64, [vp, IP, ci, ci, ci, vp, sz, vp, vp, sz, vp, vp]),
         "j2k_ht_decode_device": (ci, [vp, ci, IP, ci, ci, ci, vp, vp, vp, ci, vp, vp]),
         "j2k_ht_table": (ci, [ci, vp]),
+        "j2k_forward_ht": (ci, [vp, FP, ci, ci, ci, vp, sz, vp, vp, sz, C.POINTER(sz), vp]),
+        "j2k_ht_encode_bound": (sz, [FP, ci, ci, ci, ci]),
+        "j2k_ht_encode_device": (ci, [vp, ci, FP, ci, ci, ci, vp, vp, vp, sz, vp, vp, vp]),
+        "j2k_ht_enc_table": (ci, [ci, vp]),
         "j2k_dwt53_forward": (ci, [vp, vp, ci, ci, ci, ci, ci]),
         "j2k_dwt53_inverse": (ci, [vp, vp, ci, ci, ci, ci, ci]),
         "j2k_dwt97_forward": (ci, [vp, vp, ci, ci, ci, ci, ci]),

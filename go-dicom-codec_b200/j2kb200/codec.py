@@ -254,6 +254,26 @@ class Context:
         self._ck(self.lib.j2k_ht_decode_device(self.h, dev, C.byref(p), cb_width, cb_height, nframes, d_bytes, d_records, d_out,
                                                int(to_planes), d_status or None, stream or None))
 
+    # ---- HTJ2K block encoding on the device (encode side)
+    def forward_ht(self, p: abi.FwdParams, frames: np.ndarray, kmax, cb_width=64, cb_height=64, out: np.ndarray | None = None):
+        """j2k_forward_batch + HTEncoder.Encode (jpeg2000/htj2k/encoder.go:54-68) of every code-block on the device.
+        frames [n, frame bytes]; kmax [components, 3 * levels + 1] band precisions (Encoder.bandNumbps).
+        -> (stream bytes, records [n * blocks] as a structured array: offset, length, kmax, missing_msbs)."""
+        assert frames.ndim == 2 and frames.dtype == np.uint8 and frames.flags.c_contiguous
+        n = frames.shape[0]
+        km = np.ascontiguousarray(kmax, dtype=np.uint8).reshape(-1)
+        assert km.size == p.components * (3 * p.num_levels + 1), km.size
+        nblk = self.lib.j2k_fwd_block_count(C.byref(p), cb_width, cb_height)
+        if out is None:
+            cap = self.lib.j2k_ht_encode_bound(C.byref(p), cb_width, cb_height, int(km.max()) if km.size and 0 < km.max() < 31 else 30, n)
+            out = np.empty(max(cap, 16), np.uint8)
+        rec = self.ht_records(np.zeros(n * nblk, np.uint64), np.zeros(n * nblk, np.uint32), np.zeros(n * nblk, np.uint8),
+                              np.zeros(n * nblk, np.uint8))
+        got = C.c_size_t(0)
+        self._ck(self.lib.j2k_forward_ht(self.h, C.byref(p), cb_width, cb_height, n, _vp(frames), frames.strides[0], _vp(km), _vp(out),
+                                         out.size, C.byref(got), _vp(rec)))
+        return out[:got.value], rec
+
     def gather_blocks_device(self, p: abi.FwdParams, nframes, d_coeffs: int, d_blocks: int, d_numbps: int, cb_width=64, cb_height=64,
                              stream: int = 0, dev: int = 0):
         self._ck(self.lib.j2k_gather_blocks_device(self.h, dev, C.byref(p), cb_width, cb_height, nframes, C.c_void_p(d_coeffs),

@@ -388,6 +388,36 @@ int j2k_ht_decode_device(j2k_ctx* ctx, int dev, const j2k_inv_params* p, int cb_
  * other rows; vlc_tables.go:862-925, uvlc_tables.go:30-143); returns the entry count, copies them when out != NULL. */
 int j2k_ht_table(int which, uint16_t* out);
 
+/* ------------------------------- HTJ2K block encoding on the device (encode side) */
+
+/* HTEncoder.Encode (jpeg2000/htj2k/encoder.go:54-68 -> encodeOpenJPHCleanup, openjph_cleanup_encoder.go:200-252) for every
+ * code-block, behind j2k_forward_batch on the device: the coefficient planes never leave it; the blocks are read straight
+ * from them (the sub-band extraction and partitionIntoCodeBlocks copies of buildTilePacketEncoder, encoder.go:2424-2431).
+ * Byte-identical to the reference encoder (and to OpenJPH: htj2k/go_byte_parity_test.go).
+ *   kmax      : components x (3 * num_levels + 1) band precisions, Encoder.bandNumbps per sub-band (index 0 = LL, then HL, LH,
+ *               HH from the coarsest resolution); each 1..30 ("invalid HTJ2K Kmax", openjph_cleanup_encoder.go:201-203)
+ *   bytes_out : the cleanup segments of all blocks, back to back in block order; *nbytes_out receives their total size.
+ *               When bytes_cap is too small the call fails with J2K_ERR_SIZE and *nbytes_out holds a size that was needed
+ *               (j2k_ht_encode_bound gives a capacity that always suffices)
+ *   cblks_out : one record per (frame, block) in the order of the code-block interface: offset / length of the block's
+ *               segment (length 0: the block is empty, "return nil, nil" :218-220 -> not included in the packet), its Kmax and
+ *               missing_msbs = Kmax - 1 (zeroBitPlanes of codeBlockPassLayout, encoder.go:3381-3388) -- what T2 needs.
+ * p->htj2k should be set (no T1 fixed point, encoder.go:3293-3300).  Runs on the context's first device. */
+int j2k_forward_ht(j2k_ctx* ctx, const j2k_fwd_params* p, int cb_width, int cb_height, int nframes, const void* pixels,
+                   size_t frame_stride_bytes, const uint8_t* kmax, uint8_t* bytes_out, size_t bytes_cap, size_t* nbytes_out,
+                   j2k_ht_cblk* cblks_out);
+size_t j2k_ht_encode_bound(const j2k_fwd_params* p, int cb_width, int cb_height, int kmax_max, int nframes);
+
+/* Device-resident form behind j2k_forward_device: `d_coeffs` (Mallat planes), `d_bytes` (capacity bytes_cap), `d_cblks`
+ * (nframes x blocks records) and `d_offsets` (nframes x blocks + 1 values: the offset of every block; the last one is the
+ * size of the stream, which is not written past bytes_cap) are device pointers; `kmax` is a host array as above. */
+int j2k_ht_encode_device(j2k_ctx* ctx, int dev, const j2k_fwd_params* p, int cb_width, int cb_height, int nframes,
+                         const int32_t* d_coeffs, const uint8_t* kmax, uint8_t* d_bytes, size_t bytes_cap, j2k_ht_cblk* d_cblks,
+                         uint64_t* d_offsets, void* cuda_stream);
+
+/* The encoder's VLC lookup (which: 0 initial quad row, 1 other rows; openjph_cleanup_encoder.go:440-470), 2048 entries. */
+int j2k_ht_enc_table(int which, uint16_t* out);
+
 /* -------------------------------------------- wavelet package API (in place) */
 
 /* wavelet.ForwardMultilevelWithParity / InverseMultilevelWithParity

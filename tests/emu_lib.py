@@ -11,7 +11,7 @@ CSRC = os.path.join(ROOT, "go-dicom-codec_b200", "csrc")
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(CSRC, f) for f in ("j2k_b200.cu", "j2k_kernels.cuh", "j2k_pointwise.cuh", "j2k_ring.cuh", "j2k_ht.cuh", "j2k_ht_tables.inc")]
+    srcs = [os.path.join(CSRC, f) for f in ("j2k_b200.cu", "j2k_kernels.cuh", "j2k_pointwise.cuh", "j2k_ring.cuh", "j2k_ht.cuh", "j2k_ht_tables.inc", "j2k_ht_enc.cuh", "j2k_ht_enc_tables.inc")]
     srcs += [os.path.join(EMU, f) for f in ("cuda_runtime.h", "emu_runtime.cpp")]
     srcs.append(os.path.join(ROOT, "include", "j2k_b200.h"))
     stale = (not os.path.exists(LIB)) or any(os.path.getmtime(f) > os.path.getmtime(LIB) for f in srcs)

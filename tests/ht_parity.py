@@ -166,3 +166,99 @@ def check_generated(ctx, ht, oracle, w, h, levels, cbw, cbh, bits, density, seed
     for f in range(nframes):
         co = np.concatenate([p.reshape(-1) for p in frames[f]])
         assert np.array_equal(px[f], oracle.inverse(ip, co)), f
+
+
+def band_kmax_table(components, levels, base):
+    """a plausible bandNumbps table: `base` bits + the usual sub-band gains"""
+    t = np.zeros((components, 3 * levels + 1), np.uint8)
+    for c in range(components):
+        t[c, 0] = base
+        for r in range(1, levels + 1):
+            t[c, 1 + 3 * (r - 1):4 + 3 * (r - 1)] = (base + 1, base + 1, base + 2)
+    return np.minimum(t, 30)
+
+
+def check_encode(ctx, ht, oracle, w, h, comps, bits, levels, cbw, cbh, seed, nframes=1, reversible=True, base=None, tile=None):
+    """forward transform + HT block encoding on the device: every block's bytes == the oracle's restatement of HTEncoder.Encode
+    applied to the oracle's coefficients of the same frame; records consistent; the stream decodes back (device decoder)"""
+    rng = np.random.default_rng(seed)
+    depth = 8 if bits <= 8 else 16
+    bpp = 1 if depth == 8 else 2
+    yy, xx = np.mgrid[0:h, 0:w]
+    frames = []
+    for f in range(nframes):
+        planes = [((np.sin((xx + 31 * f) / (9.0 + c)) * np.cos(yy / (7.0 + c)) * 0.35 + 0.5) * ((1 << bits) - 1) + rng.normal(0, (1 << bits) / 64.0, (h, w))).clip(0, (1 << bits) - 1)
+                  for c in range(comps)]
+        if f % 2 == 1:
+            planes[0][: h // 2, : w // 2] = 0   # flat regions: empty blocks, MEL runs
+        px = np.stack(planes, axis=-1).astype("<u2" if bpp == 2 else np.uint8)
+        frames.append(px.reshape(-1).view(np.uint8))
+    frames = np.ascontiguousarray(np.stack(frames))
+    kw = dict(num_levels=levels, reversible=reversible, htj2k=True)
+    if tile:
+        kw.update(tile_width=tile[0], tile_height=tile[1])
+    if reversible:
+        kw["mct_mode"] = abi.MCT_RCT if comps == 3 else abi.MCT_NONE
+    else:
+        enc, _ = oracle.openjpeg_quant_params(levels, bits)
+        kw["steps"] = oracle.runtime_quant_steps(enc, levels, bits)
+        kw["mct_mode"] = abi.MCT_ICT if comps == 3 else abi.MCT_NONE
+    fp = abi.fwd_params(w, h, comps, bits, False, **kw)
+    kmax = band_kmax_table(comps, levels, base if base is not None else bits + 2)
+    stream, rec = ctx.forward_ht(fp, frames, kmax, cbw, cbh)
+    nblk = rec.size // nframes
+    # the oracle's coefficients and block layout (per tile, per component)
+    pos = 0
+    for f in range(nframes):
+        co = oracle.forward(fp, frames[f])
+        k = f * nblk
+        off = 0
+        ntiles = 1
+        tiles = [(w, h)]
+        if tile:
+            tiles = []
+            for ty in range(0, h, tile[1]):
+                for tx in range(0, w, tile[0]):
+                    tiles.append((min(tile[0], w - tx), min(tile[1], h - ty)))
+        for (tw, th) in tiles:
+            lay = oracle.codeblock_layout(tw, th, levels, cbw, cbh)
+            for c in range(comps):
+                plane = co[off:off + tw * th].reshape(th, tw)
+                off += tw * th
+                for b in lay:
+                    idx = 0 if b.res == 0 else 1 + 3 * (b.res - 1) + (b.band - 1)
+                    km = int(kmax[c, idx])
+                    want = ht.encode_ref(plane[b.y0:b.y0 + b.height, b.x0:b.x0 + b.width], km)
+                    r = rec[k]
+                    assert int(r["kmax"]) == km and int(r["missing_msbs"]) == km - 1, (f, k)
+                    assert int(r["length"]) == len(want), (f, k, b.width, b.height, int(r["length"]), len(want))
+                    if want:
+                        assert int(r["offset"]) == pos, (f, k)
+                        got = stream[pos:pos + len(want)].tobytes()
+                        assert got == want, (f, k, b.width, b.height, [i for i in range(len(want)) if got[i] != want[i]][:6])
+                        pos += len(want)
+                    k += 1
+        assert k == (f + 1) * nblk
+    assert pos == stream.size
+    return stream, rec, fp, frames
+
+
+def check_fixture_encode(ctx, oracle, name, kind):
+    """input.raw -> forward 5/3 (+ RCT) + HT block encoding on the device == the code-block bytes OpenJPH wrote into the
+    fixture codestream (the reference's byte-parity test, htj2k/go_byte_parity_test.go:11-44, below the packet layer)"""
+    import j2c_parse
+    fx = ht_cases.load(name, kind, oracle.codeblock_layout)
+    h = fx["header"]
+    L = h.num_levels
+    fp = abi.fwd_params(h.width, h.height, h.components, h.depth[0], h.signed[0], num_levels=L, reversible=True, htj2k=True,
+                        mct_mode=abi.MCT_RCT if h.mct else abi.MCT_NONE)
+    kmax = np.array([[j2c_parse.band_kmax(h, i) for i in range(3 * L + 1)] for _ in range(h.components)], np.uint8)
+    stream, rec = ctx.forward_ht(fp, fx["raw"].reshape(1, -1), kmax, h.cbw, h.cbh)
+    assert rec.size == len(fx["offsets"])
+    for k in range(rec.size):
+        o, n = int(fx["offsets"][k]), int(fx["lengths"][k])
+        assert int(rec[k]["length"]) == n, (k, int(rec[k]["length"]), n)
+        if n:
+            assert int(rec[k]["kmax"]) == int(fx["kmax"][k]) and int(rec[k]["missing_msbs"]) == int(fx["mmsb"][k])
+            ro = int(rec[k]["offset"])
+            assert stream[ro:ro + n].tobytes() == fx["stream"][o:o + n].tobytes(), k

@@ -58,3 +58,33 @@ def test_generated_streams(ectx, ht, oracle, w, h, levels, cbw, cbh, bits, densi
 
 def test_generated_two_frames(ectx, ht, oracle):
     HP.check_generated(ectx, ht, oracle, 72, 56, 2, 32, 32, 12, 0.6, seed=3, nframes=2)
+
+
+@pytest.mark.parametrize("w,h,comps,bits,levels,cbw,cbh,rev", [
+    (64, 64, 1, 8, 0, 64, 64, True), (96, 80, 1, 12, 2, 32, 32, True), (75, 61, 1, 16, 2, 64, 64, True), (128, 32, 1, 10, 1, 128, 32, False),
+    (40, 40, 3, 8, 1, 16, 16, True), (33, 130, 1, 12, 1, 8, 512, True), (150, 10, 1, 9, 0, 1024, 4, True), (48, 48, 3, 8, 2, 64, 64, False),
+    (1, 1, 1, 8, 0, 4, 4, True), (2, 7, 1, 8, 0, 4, 4, True),
+])
+def test_encode(ectx, ht, oracle, w, h, comps, bits, levels, cbw, cbh, rev):
+    HP.check_encode(ectx, ht, oracle, w, h, comps, bits, levels, cbw, cbh, seed=w * 3 + h, reversible=rev)
+
+
+def test_encode_frames_tiles_and_tight_kmax(ectx, ht, oracle):
+    HP.check_encode(ectx, ht, oracle, 72, 56, 1, 12, 2, 32, 32, seed=4, nframes=3)
+    HP.check_encode(ectx, ht, oracle, 70, 50, 3, 8, 2, 32, 32, seed=5, tile=(32, 32))
+    # Kmax below the data's magnitudes: the reference shifts bits out of the 32-bit word; the same bytes are expected
+    HP.check_encode(ectx, ht, oracle, 64, 48, 1, 12, 1, 64, 64, seed=6, base=6)
+
+
+def test_encoder_table_matches_the_oracle(ectx, ht):
+    import numpy as np
+    for which in (0, 1):
+        t = np.zeros(2048, np.uint16)
+        assert ectx.lib.j2k_ht_enc_table(which, t.ctypes.data) == 2048
+        assert np.array_equal(t, ht.enc_table(which))
+
+
+@pytest.mark.parametrize("name,kind", [("mono_u8_127x129", "fo_htj2k_lossless"), ("mono_s16_128x128", "fo_htj2k_lossless_rpcl"),
+                                       ("mono_u16_128x128", "fo_htj2k_lossless"), ("rgb_u8_127x129", "fo_htj2k_lossless_rpcl")])
+def test_encode_reproduces_the_openjph_fixture_blocks(ectx, oracle, name, kind):
+    HP.check_fixture_encode(ectx, oracle, name, kind)

@@ -92,3 +92,48 @@ def test_async_ticket_and_pinned_buffers(ctx, ht, oracle):
             assert np.array_equal(o[f], fx["raw"]), f
     for a in [stream] + outs + sts:
         ctx.release(a)
+
+
+# ---- encode side
+
+@pytest.mark.parametrize("name,kind", ht_cases.fixtures())
+def test_encode_reproduces_the_openjph_fixture_blocks(ctx, oracle, name, kind):
+    HP.check_fixture_encode(ctx, oracle, name, kind)
+
+
+@pytest.mark.parametrize("w,h,comps,bits,levels,cbw,cbh,rev", [
+    (64, 64, 1, 8, 0, 64, 64, True), (96, 80, 1, 12, 2, 32, 32, True), (75, 61, 1, 16, 2, 64, 64, True), (128, 32, 1, 10, 1, 128, 32, False),
+    (40, 40, 3, 8, 1, 16, 16, True), (33, 130, 1, 12, 1, 8, 512, True), (150, 10, 1, 9, 0, 1024, 4, True), (48, 48, 3, 8, 2, 64, 64, False),
+    (1, 1, 1, 8, 0, 4, 4, True), (2, 7, 1, 8, 0, 4, 4, True),
+    (512, 512, 1, 16, 5, 64, 64, True),        # C1-shaped
+    (512, 384, 3, 8, 5, 64, 64, False),        # C3-shaped: ICT + 9/7 + quantization in front of the block encoder
+    (2140, 300, 1, 16, 4, 64, 64, False),      # odd DX width
+    (257, 255, 1, 14, 3, 32, 128, True),
+])
+def test_encode(ctx, ht, oracle, w, h, comps, bits, levels, cbw, cbh, rev):
+    HP.check_encode(ctx, ht, oracle, w, h, comps, bits, levels, cbw, cbh, seed=w * 3 + h, reversible=rev)
+
+
+def test_encode_batches_tiles_tight_kmax_and_round_trip(ctx, ht, oracle):
+    HP.check_encode(ctx, ht, oracle, 256, 256, 1, 12, 4, 64, 64, seed=4, nframes=5)
+    HP.check_encode(ctx, ht, oracle, 70, 50, 3, 8, 2, 32, 32, seed=5, tile=(32, 32))
+    HP.check_encode(ctx, ht, oracle, 64, 48, 1, 12, 1, 64, 64, seed=6, base=6)
+    # encode -> decode on the device == the frames (lossless 5/3)
+    from j2kb200 import abi
+    stream, rec, fp, frames = HP.check_encode(ctx, ht, oracle, 300, 200, 1, 12, 3, 64, 64, seed=7, nframes=3)
+    ip = abi.inv_params(300, 200, 1, 12, False, num_levels=3, reversible=True, htj2k=True)
+    px, st = ctx.inverse_ht(ip, 3, np.concatenate([stream, np.zeros(16, np.uint8)]), rec)
+    assert not st.any() and np.array_equal(px, frames)
+
+
+def test_encode_sub_batches_and_small_capacity(ctx, ht, oracle, monkeypatch):
+    """more frames than one sub-batch holds (the lagged download path), and a stream buffer that is too small"""
+    import j2kb200
+    from j2kb200 import abi
+    stream, rec, fp, frames = HP.check_encode(ctx, ht, oracle, 1024, 1024, 1, 12, 5, 64, 64, seed=8, nframes=40)
+    small = np.empty(stream.size // 2, np.uint8)
+    with pytest.raises(j2kb200.J2KError) as e:
+        ctx.forward_ht(fp, frames, HP.band_kmax_table(1, 5, 14), out=small)
+    assert e.value.code == abi.J2K_ERR_SIZE
+    with pytest.raises(j2kb200.J2KError, match="Kmax"):
+        ctx.forward_ht(fp, frames[:1], np.full((1, 16), 31, np.uint8))
