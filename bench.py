@@ -673,6 +673,101 @@ def main():
             ctx.release(a)
         del d_bytes, d_rec, d_co, d_px
 
+    # ---- HTJ2K block ENCODING on the device (encode side): the bench workload's frames through the forward
+    # kernel and the HT block encoder; resident = forward + the four encoder launches; end to end = pixels up, cleanup segments +
+    # records down (j2k_forward_ht), against the same frames leaving as int32 coefficient planes (j2k_forward_batch).
+    hte_leg = None
+    if not args.no_ht:
+        Be = max(1, min(B, 8))
+        fph = abi.fwd_params(W, H, 1, BITS, False, num_levels=LEVELS, reversible=False, htj2k=True, steps=steps_enc)
+        guard = 2   # OpenJPEG's guard bits (quantization.go): bandNumbps = exponent + guard - 1 (encoder.go:3303, t2/bitplane.go:22-61)
+        kmax = np.array([[(int(e) >> 11) + guard - 1 for e in enc]], np.uint8)
+        nblk = int(ctx.lib.j2k_fwd_block_count(C.byref(fph), 64, 64))
+        cap = int(ctx.lib.j2k_ht_encode_bound(C.byref(fph), 64, 64, int(kmax.max()), Be))
+        d_cof = torch.empty((Be, PIX), dtype=torch.int32, device="cuda")
+        d_str = torch.empty(cap, dtype=torch.uint8, device="cuda")
+        d_rcs = torch.empty(Be * nblk * 16, dtype=torch.uint8, device="cuda")
+        d_off = torch.empty(Be * nblk + 1, dtype=torch.int64, device="cuda")
+        s0 = streams[0].cuda_stream
+
+        def enc_only():
+            ctx._ck(ctx.lib.j2k_ht_encode_device(ctx.h, 0, C.byref(fph), 64, 64, Be, C.c_void_p(d_cof.data_ptr()), kmax.ctypes.data,
+                                                 C.c_void_p(d_str.data_ptr()), cap, C.c_void_p(d_rcs.data_ptr()),
+                                                 C.c_void_p(d_off.data_ptr()), C.c_void_p(s0)))
+
+        def enc_full():
+            ctx.forward_device(fph, Be, d_in.data_ptr(), frame_bytes, d_cof.data_ptr(), stream=s0)
+            enc_only()
+
+        def timed_e(fn, n):
+            for _ in range(warm):
+                fn()
+            barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(streams[0])
+            for _ in range(n):
+                fn()
+            a1.record(streams[0])
+            barrier()
+            t = torch.tensor([a0.elapsed_time(a1)], device="cuda")
+            if use_dist:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item()) / n
+
+        nst = max(5, min(args.steps, 20))
+        ctx.forward_device(fph, Be, d_in.data_ptr(), frame_bytes, d_cof.data_ptr(), stream=s0)
+        enc_ms = timed_e(enc_only, nst)
+        full_ms = timed_e(enc_full, nst)
+        nbytes = int(d_off[Be * nblk].item())
+        # round trip on the device: the HT decoder gives the coefficient planes back
+        d_back = torch.empty_like(d_cof)
+        iph2 = abi.inv_params(W, H, 1, BITS, False, num_levels=LEVELS, reversible=False, htj2k=True,
+                              steps=j2kb200.decode_quant_steps(enc, LEVELS, BITS, False))
+        ctx.ht_decode_device(iph2, Be, C.c_void_p(d_str.data_ptr()), C.c_void_p(d_rcs.data_ptr()), C.c_void_p(d_back.data_ptr()), True,
+                             stream=C.c_void_p(s0))
+        torch.cuda.synchronize()
+        round_trip = bool(torch.equal(d_back, d_cof))
+        # end to end with pinned buffers
+        h_pix = ctx.pinned(Be * frame_bytes).reshape(Be, frame_bytes)
+        for f in range(Be):
+            h_pix[f] = host[f % host.shape[0]]
+        h_str = ctx.pinned(cap)
+        h_cf = ctx.pinned(Be * PIX * 4, np.int32).reshape(Be, PIX)
+
+        def wall(fn, n):
+            fn(); fn()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(n):
+                fn()
+            t = torch.tensor([time.perf_counter() - t0], device="cuda")
+            if use_dist:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item()) / n
+
+        ne = max(3, min(args.steps, 10))
+        got = {}
+        def e2e_ht():
+            got["s"], got["r"] = ctx.forward_ht(fph, h_pix, kmax, out=h_str)
+        dt_h = wall(e2e_ht, ne)
+        dt_p = wall(lambda: ctx.forward_batch(fph, h_pix, h_cf), ne)
+        same_stream = bool(got["s"].size == nbytes and np.array_equal(np.asarray(got["s"][:4096]), d_str[:4096].cpu().numpy()))
+        hte_leg = {"frames_per_step": Be, "blocks_per_frame": nblk, "code_block": [64, 64], "kmax": [int(k) for k in kmax[0]],
+                   "compressed_bytes_per_frame": nbytes // Be, "bits_per_sample": nbytes * 8 / (Be * PIX),
+                   "ht_encode_ms": enc_ms, "ht_encode_Mpixel_s": world * Be * PIX / (enc_ms * 1e-3) / 1e6,
+                   "forward_plus_ht_encode_ms": full_ms, "forward_plus_ht_encode_Mpixel_s": world * Be * PIX / (full_ms * 1e-3) / 1e6,
+                   "decodes_back_to_the_coefficients": round_trip,
+                   "e2e": {"value": world * Be * PIX / dt_h / 1e6, "unit": "Mpixel/s", "h2d_bytes_per_step": Be * frame_bytes,
+                           "d2h_bytes_per_step": nbytes + Be * nblk * 16, "api": "j2k_forward_ht (blocking), pinned buffers"},
+                   "e2e_planes": {"value": world * Be * PIX / dt_p / 1e6, "unit": "Mpixel/s", "h2d_bytes_per_step": Be * frame_bytes,
+                                  "d2h_bytes_per_step": Be * PIX * 4, "api": "j2k_forward_batch (blocking, int32 coefficient planes down), same frames"},
+                   "stream_identical_to_resident": same_stream,
+                   "what": "HTEncoder.Encode (htj2k/encoder.go:54-68) for every code-block behind the forward kernel, byte-identical to the "
+                           "reference encoder (tests/test_ht_gpu.py); the bench workload's frames"}
+        for a in (h_pix, h_str, h_cf):
+            ctx.release(a)
+        del d_cof, d_str, d_rcs, d_off, d_back
+
     # ---- sustained load: the same resident step for a few seconds.  The K-step region above is a burst (tens of ms at
     # boost clocks); held for seconds the board reaches its power limit and the SM clock settles lower, which this
     # co-limited kernel feels.  Reported next to `value`, never instead of it.
@@ -818,7 +913,7 @@ def main():
             "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": workload_config(B, world, NS),
-            "roofline": roofline, "sustained": sustained, "inverse": inverse, "configs": configs, "code_blocks": blocks_leg, "ht_decode": ht_leg,
+            "roofline": roofline, "sustained": sustained, "inverse": inverse, "configs": configs, "code_blocks": blocks_leg, "ht_decode": ht_leg, "ht_encode": hte_leg,
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": "Mpixel/s", "h2d_bytes_per_step": B * frame_bytes, "d2h_bytes_per_step": B * PIX * 4,
                     "steps": e2e_steps, "matches_resident": same, "sync_value": e2e_sync,

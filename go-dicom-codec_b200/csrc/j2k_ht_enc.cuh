@@ -41,10 +41,10 @@ __host__ inline HtEncLayout ht_enc_layout(int cbw, int cbh, int kmax_max) {
     int o = 0;
     L.ms_bits_off = o; o += ht_align16(ms_bits / 8 + 8);
     L.vlc_bits_off = o; o += ht_align16(vlc_bits / 8 + 8);
-    L.mel_ev_off = o; o += ht_align16(mel_ev / 8 + 8);
-    L.ms_out_off = o; o += ht_align16(ms_bits / 7 + 16);
-    L.mel_out_off = o; o += ht_align16(mel_ev * 6 / 7 + 16);
-    L.vlc_out_off = o; o += ht_align16(vlc_bits / 7 + 16);
+    L.mel_ev_off = o; o += ht_align16(mel_ev / 8 + 48);
+    L.ms_out_off = o; o += ht_align16(ms_bits / 7 + 32);
+    L.mel_out_off = o; o += ht_align16(mel_ev * 6 / 7 + 32);
+    L.vlc_out_off = o; o += ht_align16(vlc_bits / 7 + 32);
     L.slot_bytes = o;
     return L;
 }
@@ -266,15 +266,62 @@ __global__ void __launch_bounds__(128) ht_enc_quads_kernel(const int* __restrict
     }
 }
 
-// sequential reader of an un-stuffed bit stream (words in global memory)
+// Sequential reader of an un-stuffed bit stream (words in global memory).  A thread of the pack kernel runs alone on its block,
+// so its speed is the latency of its own loads: 16 bytes per load, the next 16 requested one step ahead.  (The stream areas are
+// 16-byte aligned and followed by other areas of the slot, so reading a vector or two past the last word stays inside it.)
 struct HtBitIn {
-    const unsigned* w; unsigned long long acc; int nacc; unsigned next, left;
-    __device__ __forceinline__ void init(const unsigned* p, unsigned nbits) { w = p; acc = 0; nacc = 0; next = 0; left = nbits; }
+    const uint4* w; uint4 cur, nxt; int wi, vi; unsigned long long acc; int nacc; unsigned left;
+    __device__ __forceinline__ void init(const void* p, unsigned nbits) {
+        w = (const uint4*)p; acc = 0; nacc = 0; left = nbits; wi = 0; vi = 0;
+        cur = w[0]; nxt = w[1];
+    }
+    __device__ __forceinline__ unsigned word() {
+        const unsigned v = cur.x;
+        cur.x = cur.y; cur.y = cur.z; cur.z = cur.w;
+        if (++wi == 4) { cur = nxt; vi++; nxt = w[vi + 1]; wi = 0; }
+        return v;
+    }
     __device__ __forceinline__ unsigned take(int n) {   // n <= 8, n <= left
-        if (nacc < n) { acc |= (unsigned long long)w[next++] << nacc; nacc += 32; }
+        if (nacc < n) { acc |= (unsigned long long)word() << nacc; nacc += 32; }
         const unsigned v = (unsigned)acc & ((1u << n) - 1);
         acc >>= n; nacc -= n; left -= (unsigned)n;
         return v;
+    }
+    __device__ __forceinline__ unsigned peek32() {      // the next 32 bits (left >= 32)
+        if (nacc < 32) { acc |= (unsigned long long)word() << nacc; nacc += 32; }
+        return (unsigned)acc;
+    }
+    __device__ __forceinline__ void skip32() { acc >>= 32; nacc -= 32; left -= 32; }
+};
+
+// Byte writer: 16 bytes per store (the output areas are 16-byte aligned, with room for a last full vector)
+struct HtByteOut {
+    uint4* p; unsigned n; unsigned long long lo, hi;
+    __device__ __forceinline__ void init(void* q) { p = (uint4*)q; n = 0; lo = 0; hi = 0; }
+    __device__ __forceinline__ void put(unsigned b) {
+        const unsigned k = n & 15;
+        if (k < 8) lo |= (unsigned long long)(b & 0xFF) << (8 * k);
+        else hi |= (unsigned long long)(b & 0xFF) << (8 * (k - 8));
+        if ((++n & 15) == 0) { *p++ = make_uint4((unsigned)lo, (unsigned)(lo >> 32), (unsigned)hi, (unsigned)(hi >> 32)); lo = 0; hi = 0; }
+    }
+    __device__ __forceinline__ void put4(unsigned w4) {   // four bytes, least significant first
+        const unsigned k = n & 15;
+        unsigned long long over = 0;
+        if (k < 8) {
+            lo |= (unsigned long long)w4 << (8 * k);
+            if (k > 4) hi |= (unsigned long long)w4 >> (64 - 8 * k);
+        } else {
+            hi |= (unsigned long long)w4 << (8 * (k - 8));
+            if (k > 12) over = (unsigned long long)w4 >> (8 * (16 - k));
+        }
+        n += 4;
+        if (k >= 12) {
+            *p++ = make_uint4((unsigned)lo, (unsigned)(lo >> 32), (unsigned)hi, (unsigned)(hi >> 32));
+            lo = over; hi = 0;
+        }
+    }
+    __device__ __forceinline__ void finish() {
+        if (n & 15) *p = make_uint4((unsigned)lo, (unsigned)(lo >> 32), (unsigned)hi, (unsigned)(hi >> 32));
     }
 };
 
@@ -289,53 +336,61 @@ __global__ void __launch_bounds__(32) ht_enc_pack_kernel(long long total, unsign
     // ---- MagSgn: ojphMSWriter.encode / terminate (:114-166), fed 8 (or 7) bits at a time
     unsigned ms_n = 0;
     {
-        HtBitIn in; in.init((const unsigned*)(slot + L.ms_bits_off), I.ms_nbits);
-        unsigned char* out = slot + L.ms_out_off;
+        HtBitIn in; in.init(slot + L.ms_bits_off, I.ms_nbits);
+        HtByteOut out; out.init(slot + L.ms_out_off);
         int max_bits = 8;
         while (in.left >= (unsigned)max_bits) {
+            // four bytes at a time while none of them is 0xFF (only a 0xFF byte changes the width of the byte after it):
+            // a lone thread pays ~200 cycles of dependent instructions per byte, and 98 % of the words take this path
+            if (max_bits == 8 && in.left >= 32) {
+                const unsigned w4 = in.peek32(), nw = ~w4;
+                if (((nw - 0x01010101u) & w4 & 0x80808080u) == 0) { out.put4(w4); in.skip32(); continue; }
+            }
             const unsigned b = in.take(max_bits);
-            out[ms_n++] = (unsigned char)b;
+            out.put(b);
             max_bits = b == 0xFF ? 7 : 8;
         }
         const int used = (int)in.left;
+        ms_n = out.n;
         if (used != 0) {
             unsigned tmp = in.take(used);
             const int t = max_bits - used;
             tmp |= (0xFFu & ((1u << t) - 1)) << used;
-            if ((tmp & 0xFF) != 0xFF) out[ms_n++] = (unsigned char)tmp;
+            if ((tmp & 0xFF) != 0xFF) { out.put(tmp); ms_n++; }
         } else if (max_bits == 7 && ms_n > 0) ms_n--;
+        out.finish();
     }
     // ---- VLC: ojphVLCWriter.encode (:74-102) bit-serially (the stuffing decision only looks at the accumulated byte)
-    unsigned vlc_n = 0; int vtmp = 0xF, vused = 4; bool vlast = true;
-    unsigned char* vout = slot + L.vlc_out_off;
-    vout[vlc_n++] = 0xFF;
+    int vtmp = 0xF, vused = 4; bool vlast = true;
+    HtByteOut vout; vout.init(slot + L.vlc_out_off);
+    vout.put(0xFF);
     {
-        HtBitIn in; in.init((const unsigned*)(slot + L.vlc_bits_off), I.vlc_nbits);
+        HtBitIn in; in.init(slot + L.vlc_bits_off, I.vlc_nbits);
         while (in.left > 0) {
             int avail = 8 - (vlast ? 1 : 0) - vused;
             const int t = (int)min((unsigned)avail, in.left);
             if (t > 0) { vtmp |= (int)in.take(t) << vused; vused += t; avail -= t; }
             if (avail == 0) {
                 if (vlast && vtmp != 0x7F) { vlast = false; continue; }
-                vout[vlc_n++] = (unsigned char)vtmp;
+                vout.put((unsigned)vtmp);
                 vlast = vtmp > 0x8F;
                 vtmp = 0; vused = 0;
             }
         }
     }
     // ---- MEL: ojphMELWriter (:8-62)
-    unsigned mel_n = 0; int mtmp = 0, mrem = 8, mrun = 0, mk = 0, mthr = 1;
-    unsigned char* mout = slot + L.mel_out_off;
+    int mtmp = 0, mrem = 8, mrun = 0, mk = 0, mthr = 1;
+    HtByteOut mout; mout.init(slot + L.mel_out_off);
     auto emit = [&](int v) {
         mtmp = (mtmp << 1) | (v & 1);
         if (--mrem == 0) {
-            mout[mel_n++] = (unsigned char)mtmp;
+            mout.put((unsigned)mtmp);
             mrem = mtmp == 0xFF ? 7 : 8;
             mtmp = 0;
         }
     };
     {
-        HtBitIn in; in.init((const unsigned*)(slot + L.mel_ev_off), I.mel_nev);
+        HtBitIn in; in.init(slot + L.mel_ev_off, I.mel_nev);
         while (in.left > 0) {
             const int bit = (int)in.take(1);
             const int ev = (int)((0x5433222111000ULL >> (4 * mk)) & 0xF);
@@ -362,14 +417,15 @@ __global__ void __launch_bounds__(32) ht_enc_pack_kernel(long long total, unsign
     const int vlc_mask = vused > 0 ? 0xFF >> (8 - vused) : 0;
     if ((mel_mask | vlc_mask) != 0) {
         const int fuse = mtmp | vtmp;
-        if ((((fuse ^ mtmp) & mel_mask) | ((fuse ^ vtmp) & vlc_mask)) == 0 && fuse != 0xFF && vlc_n > 1) {
-            mout[mel_n++] = (unsigned char)fuse;
+        if ((((fuse ^ mtmp) & mel_mask) | ((fuse ^ vtmp) & vlc_mask)) == 0 && fuse != 0xFF && vout.n > 1) {
+            mout.put((unsigned)fuse);
         } else {
-            mout[mel_n++] = (unsigned char)mtmp;
-            vout[vlc_n++] = (unsigned char)vtmp;
+            mout.put((unsigned)mtmp);
+            vout.put((unsigned)vtmp);
         }
     }
-    I.ms_n = ms_n; I.mel_n = mel_n; I.vlc_n = vlc_n; I.total = ms_n + mel_n + vlc_n;
+    vout.finish(); mout.finish();
+    I.ms_n = ms_n; I.mel_n = mout.n; I.vlc_n = vout.n; I.total = ms_n + mout.n + vout.n;
     info[wid] = I;
 }
 

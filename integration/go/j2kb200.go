@@ -479,3 +479,22 @@ func InverseHT(p *InvParams, cbWidth, cbHeight, nframes int, stream []byte, bloc
 	}
 	return nil
 }
+
+// ForwardHT: the whole HTJ2K encode front on the device.  pixels holds nframes frames; kmax the band precisions
+// (Encoder.bandNumbps, encoder.go:1687-1694: components x (3*levels+1), index 0 = LL, then HL, LH, HH from the coarsest
+// resolution).  The device runs everything ForwardBatch does and then HTEncoder.Encode (htj2k/encoder.go:54-68) for every
+// code-block, reading the blocks straight from the coefficient planes.  stream receives the cleanup segments back to back
+// (cap(stream) must hold them: C.j2k_ht_encode_bound gives a size that always does); blocks one record per (frame, block) in
+// CodeBlockLayout order: Length == 0 is an empty block (HTEncoder returns nil: not included in the packet), MissingMSBs is
+// the zeroBitPlanes codeBlockPassLayout would compute (encoder.go:3381-3388).  Returns the number of stream bytes.
+func ForwardHT(p *FwdParams, cbWidth, cbHeight, nframes int, pixels []byte, frameStride int, kmax []uint8, stream []byte, blocks []HTBlock) (int, error) {
+	cp := p.c()
+	var n C.size_t
+	rc := C.j2k_forward_ht(ctx, &cp, C.int(cbWidth), C.int(cbHeight), C.int(nframes), unsafe.Pointer(&pixels[0]), C.size_t(frameStride),
+		(*C.uint8_t)(unsafe.Pointer(&kmax[0])), (*C.uint8_t)(unsafe.Pointer(&stream[0])), C.size_t(cap(stream)), &n,
+		(*C.j2k_ht_cblk)(unsafe.Pointer(&blocks[0])))
+	if rc != 0 {
+		return int(n), lastErr(rc)
+	}
+	return int(n), nil
+}
