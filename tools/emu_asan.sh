@@ -27,6 +27,25 @@ PC.check_pipelined_order(ctx, orc, 48, 32, 3, 8, 2, True, 6, 4, 2)
 PC.check_custom_mct(ctx, orc, 40, 24, 8, 2, True, "bindings")
 PC.check_wavelet_api(ctx, orc, 130, 70, 5, 0, 0)
 PC.check_wavelet_api(ctx, orc, 33, 17, 2, 1, 0)
+# HTJ2K block coder (round 2): every block shape, corrupted segments (the decoder must stay inside its buffers whatever the
+# bytes say), the encoder's vector reads past the end of its streams
+import ht_oracle_lib, ht_parity as HP
+ht = ht_oracle_lib.HtOracle()
+HP.check_fixture(ctx, ht, orc, "mono_u8_127x129", "fo_htj2k_lossless")
+HP.check_fixture(ctx, ht, orc, "rgb_u8_127x129", "fo_htj2k_lossless_rpcl")
+HP.check_mutations(ctx, ht, orc, "mono_u16_128x128", "fo_htj2k_lossless", rounds=4, seed=1)
+HP.check_mutations(ctx, ht, orc, "rgb_u8_128x128", "fo_htj2k_lossless", rounds=3, seed=2)
+for g in [(64, 64, 0, 64, 64), (70, 37, 1, 32, 32), (40, 24, 0, 4, 4), (130, 9, 0, 128, 32), (9, 130, 0, 16, 256), (260, 4, 0, 1024, 4),
+          (5, 300, 0, 4, 1024), (1, 7, 0, 8, 8), (2, 2, 0, 4, 4)]:
+    HP.check_random_streams(ctx, ht, orc, *g, seed=g[0] * 131 + g[1])
+for g in [(64, 64, 0, 64, 64, 12, 0.7, 1, True), (75, 61, 2, 64, 64, 16, 0.9, 1, True), (33, 130, 1, 8, 512, 12, 1.0, 1, True),
+          (150, 10, 0, 1024, 4, 9, 0.8, 1, True), (48, 48, 2, 64, 64, 8, 0.05, 3, False)]:
+    HP.check_generated(ctx, ht, orc, *g[:7], seed=3, components=g[7], reversible=g[8])
+for g in [(64, 64, 1, 8, 0, 64, 64, True), (75, 61, 1, 16, 2, 64, 64, True), (40, 40, 3, 8, 1, 16, 16, True), (33, 130, 1, 12, 1, 8, 512, True),
+          (150, 10, 1, 9, 0, 1024, 4, True), (48, 48, 3, 8, 2, 64, 64, False), (1, 1, 1, 8, 0, 4, 4, True), (2, 7, 1, 8, 0, 4, 4, True)]:
+    HP.check_encode(ctx, ht, orc, *g[:7], seed=5, reversible=g[7])
+HP.check_encode(ctx, ht, orc, 72, 56, 1, 12, 2, 32, 32, seed=4, nframes=3)
+HP.check_encode(ctx, ht, orc, 64, 48, 1, 12, 1, 64, 64, seed=6, base=6)
 print("asan run clean")
 PY
 LD_PRELOAD=$(g++ -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0 python $out/run.py
