@@ -3080,57 +3080,79 @@ int j2k_forward_ht(j2k_ctx* ctx, const j2k_fwd_params* p, int cb_width, int cb_h
     const int bps = s.bit_depth <= 8 ? 1 : 2;
     if (frame_stride_bytes < pixb || frame_stride_bytes % bps) return fail(J2K_ERR_SIZE, "bad frame stride");
     std::lock_guard<std::mutex> lk(ctx->mu);
-    if ((rc = sync_dev(ctx, 0))) return rc;   // the slot buffers may still serve an asynchronous job
-    DeviceCtx& d = ctx->devs[0];
-    if ((rc = set_dev(ctx, 0))) return rc;
-    int kmax_max = 0;
-    if ((rc = ht_block_kmax(s, cb_width, cb_height, kmax, d.he_kmax_host, kmax_max))) return rc;
-    BlockTable* BT = nullptr;
-    if ((rc = get_block_table(d, s, cb_width, cb_height, cpf, &BT))) return rc;
-    const size_t nblk = (size_t)BT->nblocks;
-    if ((rc = d.he_kmax.ensure(d.he_kmax_host.size() + 16))) return rc;
-    CK(cudaMemcpyAsync(d.he_kmax.p, d.he_kmax_host.data(), d.he_kmax_host.size(), cudaMemcpyHostToDevice, d.s_main));
+    // Frames are sharded over the context's devices in contiguous blocks like every host-batch call (no collective).  Each
+    // device runs its own lagged pipeline; the host visits the devices round-robin, one sub-batch each per turn, and appends
+    // a finished sub-batch's segments to the output as it collects it -- so with several devices the segments are NOT in
+    // frame order in bytes_out; the records' offsets locate them.
     // bigger sub-batches than the transform-only paths (64 Msamples): the per-block packing kernel needs the blocks of several
     // frames to fill the GPU (measured on 32 C2 frames: 14.6 Gpixel/s at 16 Msamples, 20.9 at 64)
-    static const long long sub_samples = (long long)env_int("J2K_HT_SUBBATCH_MSAMPLES", 64) << 20;
+    const long long sub_samples = (long long)env_int("J2K_HT_SUBBATCH_MSAMPLES", 64) << 20;
     int sub = (int)(sub_samples / (cpf > 0 ? cpf : 1));
     if (sub < 1) sub = 1;
-    if (sub > nframes) sub = nframes;
     struct Pend { int slot, f0, n; };
+    struct DevRun {
+        int di, next, f_end, it;
+        bool have, used_out[2], used_k[2];
+        Pend pend;
+        BlockTable* BT;
+    };
+    const int nd = (int)ctx->devs.size();
+    const int per = (nframes + nd - 1) / nd;
+    std::vector<DevRun> runs;
+    int kmax_max = 0;
+    size_t nblk = 0;
+    for (int di = 0; di < nd; di++) {
+        const int f0 = di * per, f1 = f0 + per > nframes ? nframes : f0 + per;
+        if (f0 >= f1) break;
+        if ((rc = sync_dev(ctx, di))) return rc;   // the slot buffers may still serve an asynchronous job
+        DeviceCtx& d = ctx->devs[di];
+        DevRun r{};
+        r.di = di; r.next = f0; r.f_end = f1;
+        if ((rc = ht_block_kmax(s, cb_width, cb_height, kmax, d.he_kmax_host, kmax_max))) return rc;
+        if ((rc = get_block_table(d, s, cb_width, cb_height, cpf, &r.BT))) return rc;
+        nblk = (size_t)r.BT->nblocks;
+        if ((rc = d.he_kmax.ensure(d.he_kmax_host.size() + 16))) return rc;
+        CK(cudaMemcpyAsync(d.he_kmax.p, d.he_kmax_host.data(), d.he_kmax_host.size(), cudaMemcpyHostToDevice, d.s_main));
+        runs.push_back(r);
+    }
     size_t base = 0;
-    bool have = false, used_out[2] = {false, false}, used_k[2] = {false, false};
-    Pend pend{};
-    auto finish = [&](const Pend& q) -> int {
+    auto finish = [&](DevRun& r, const Pend& q) -> int {
+        int rc2 = set_dev(ctx, r.di);
+        if (rc2) return rc2;
+        DeviceCtx& d = ctx->devs[r.di];
         CK(cudaEventSynchronize(d.ev_k[q.slot]));
         const size_t count = (size_t)q.n * nblk;
         const unsigned long long tot = *(const unsigned long long*)d.he_pin[q.slot];
-        const HtBlock* r = (const HtBlock*)((const char*)d.he_pin[q.slot] + 16);
+        const HtBlock* rec = (const HtBlock*)((const char*)d.he_pin[q.slot] + 16);
         if (base + tot > bytes_cap) {
             *nbytes_out = base + (size_t)tot;
             return fail(J2K_ERR_SIZE, "the compressed stream needs more than the %zu bytes provided (%zu so far)", bytes_cap, base + (size_t)tot);
         }
         if (tot) CK(cudaMemcpyAsync(bytes_out + base, d.he_bytes[q.slot].p, (size_t)tot, cudaMemcpyDeviceToHost, d.s_d2h));
         CK(cudaEventRecord(d.ev_out[q.slot], d.s_d2h));
-        used_out[q.slot] = true;
+        r.used_out[q.slot] = true;
         j2k_ht_cblk* dst = cblks_out + (size_t)q.f0 * nblk;
         for (size_t i = 0; i < count; i++) {
-            dst[i].offset = r[i].offset + base; dst[i].length = r[i].length; dst[i].kmax = r[i].kmax; dst[i].missing_msbs = r[i].mmsb;
+            dst[i].offset = rec[i].offset + base; dst[i].length = rec[i].length; dst[i].kmax = rec[i].kmax; dst[i].missing_msbs = rec[i].mmsb;
             dst[i].reserved = 0;
         }
         base += (size_t)tot;
         return 0;
     };
-    int it = 0;
-    for (int b = 0; b < nframes && rc == 0; b += sub, it++) {
-        const int nb = b + sub <= nframes ? sub : nframes - b;
-        const int slot = it & 1;
+    auto enqueue = [&](DevRun& r) -> int {
+        int rc2 = set_dev(ctx, r.di);
+        if (rc2) return rc2;
+        DeviceCtx& d = ctx->devs[r.di];
+        const int b = r.next;
+        const int nb = b + sub <= r.f_end ? sub : r.f_end - b;
+        const int slot = r.it & 1;
         const size_t count = (size_t)nb * nblk;
         const size_t bound = ht_enc_bound(cb_width, cb_height, kmax_max, (long long)count);
-        if ((rc = d.in[slot].ensure((size_t)nb * pixb))) break;
-        if ((rc = d.out[slot].ensure((size_t)nb * cpf * 4))) break;
-        if ((rc = d.he_bytes[slot].ensure(bound + 64))) break;
-        if ((rc = d.he_recs[slot].ensure(count * sizeof(HtBlock) + 64))) break;
-        if ((rc = d.he_off.ensure((count + 1) * 8 + 64))) break;
+        if ((rc2 = d.in[slot].ensure((size_t)nb * pixb))) return rc2;
+        if ((rc2 = d.out[slot].ensure((size_t)nb * cpf * 4))) return rc2;
+        if ((rc2 = d.he_bytes[slot].ensure(bound + 64))) return rc2;
+        if ((rc2 = d.he_recs[slot].ensure(count * sizeof(HtBlock) + 64))) return rc2;
+        if ((rc2 = d.he_off.ensure((count + 1) * 8 + 64))) return rc2;
         const size_t pin_need = 16 + count * sizeof(HtBlock);
         if (d.he_pin_cap[slot] < pin_need) {
             if (d.he_pin[slot]) cudaFreeHost(d.he_pin[slot]);
@@ -3138,32 +3160,47 @@ int j2k_forward_ht(j2k_ctx* ctx, const j2k_fwd_params* p, int cb_width, int cb_h
             CK(cudaHostAlloc(&d.he_pin[slot], pin_need + pin_need / 4, cudaHostAllocPortable));
             d.he_pin_cap[slot] = pin_need + pin_need / 4;
         }
-        if (used_k[slot]) CK(cudaStreamWaitEvent(d.s_h2d, d.ev_k[slot], 0));   // the slot's previous kernels have consumed `in`
+        if (r.used_k[slot]) CK(cudaStreamWaitEvent(d.s_h2d, d.ev_k[slot], 0));   // the slot's previous kernels have consumed `in`
         const unsigned char* src = (const unsigned char*)pixels + (size_t)b * frame_stride_bytes;
         if (frame_stride_bytes == pixb) CK(cudaMemcpyAsync(d.in[slot].p, src, (size_t)nb * pixb, cudaMemcpyHostToDevice, d.s_h2d));
         else CK(cudaMemcpy2DAsync(d.in[slot].p, pixb, src, frame_stride_bytes, pixb, nb, cudaMemcpyHostToDevice, d.s_h2d));
         CK(cudaEventRecord(d.ev_in[slot], d.s_h2d));
         CK(cudaStreamWaitEvent(d.s_main, d.ev_in[slot], 0));
-        if (used_out[slot]) CK(cudaStreamWaitEvent(d.s_main, d.ev_out[slot], 0));   // its previous stream has left the device
+        if (r.used_out[slot]) CK(cudaStreamWaitEvent(d.s_main, d.ev_out[slot], 0));   // its previous stream has left the device
         Plan* P = nullptr;
-        if ((rc = get_plan(d, s, p, sizeof *p, nb, (long long)(pixb / bps), &P))) break;
-        rc = run_plan(ctx, *P, d.in[slot].p, d.out[slot].p, nullptr, false, d.s_main);
-        if (rc < 0) break;
-        if ((rc = launch_ht_encode(ctx, d, *BT, cb_width, cb_height, kmax_max, nb, (const int32_t*)d.out[slot].p,
-                                   (const unsigned char*)d.he_kmax.p, (unsigned char*)d.he_bytes[slot].p, (unsigned long long)bound,
-                                   (HtBlock*)d.he_recs[slot].p, (unsigned long long*)d.he_off.p, d.s_main))) break;
+        if ((rc2 = get_plan(d, s, p, sizeof *p, nb, (long long)(pixb / bps), &P))) return rc2;
+        rc2 = run_plan(ctx, *P, d.in[slot].p, d.out[slot].p, nullptr, false, d.s_main);
+        if (rc2 < 0) return rc2;
+        if ((rc2 = launch_ht_encode(ctx, d, *r.BT, cb_width, cb_height, kmax_max, nb, (const int32_t*)d.out[slot].p,
+                                    (const unsigned char*)d.he_kmax.p, (unsigned char*)d.he_bytes[slot].p, (unsigned long long)bound,
+                                    (HtBlock*)d.he_recs[slot].p, (unsigned long long*)d.he_off.p, d.s_main))) return rc2;
         CK(cudaMemcpyAsync(d.he_pin[slot], (const unsigned long long*)d.he_off.p + count, 8, cudaMemcpyDeviceToHost, d.s_main));
         CK(cudaMemcpyAsync((char*)d.he_pin[slot] + 16, d.he_recs[slot].p, count * sizeof(HtBlock), cudaMemcpyDeviceToHost, d.s_main));
         CK(cudaEventRecord(d.ev_k[slot], d.s_main));
-        used_k[slot] = true;
-        if (have && (rc = finish(pend))) break;
-        pend = Pend{slot, b, nb};
-        have = true;
+        r.used_k[slot] = true;
+        const Pend now{slot, b, nb};
+        r.next = b + nb; r.it++;
+        // the size of the previous sub-batch's stream is read (a host wait on its kernels) now that this one is enqueued;
+        // its bytes then leave on the download stream while this one computes
+        if (r.have && (rc2 = finish(r, r.pend))) return rc2;
+        r.pend = now; r.have = true;
+        return 0;
+    };
+    for (bool more = true; more && rc == 0;) {
+        more = false;
+        for (DevRun& r : runs) {
+            if (rc) break;
+            if (r.next < r.f_end) rc = enqueue(r);
+            else if (r.have) { rc = finish(r, r.pend); r.have = false; }
+            if (r.next < r.f_end || r.have) more = true;
+        }
     }
-    if (rc == 0 && have) rc = finish(pend);
-    int r2 = sync_dev(ctx, 0);
-    if (rc == 0) rc = r2;
-    d.ev_k_used[0] = d.ev_k_used[1] = false; d.ev_out_used[0] = d.ev_out_used[1] = false;
+    for (DevRun& r : runs) {
+        int r2 = sync_dev(ctx, r.di);
+        if (rc == 0) rc = r2;
+        DeviceCtx& d = ctx->devs[r.di];
+        d.ev_k_used[0] = d.ev_k_used[1] = false; d.ev_out_used[0] = d.ev_out_used[1] = false;
+    }
     if (rc == 0) *nbytes_out = base;
     return rc < 0 ? rc : J2K_OK;
 }

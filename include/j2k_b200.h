@@ -396,13 +396,16 @@ int j2k_ht_table(int which, uint16_t* out);
  * Byte-identical to the reference encoder (and to OpenJPH: htj2k/go_byte_parity_test.go).
  *   kmax      : components x (3 * num_levels + 1) band precisions, Encoder.bandNumbps per sub-band (index 0 = LL, then HL, LH,
  *               HH from the coarsest resolution); each 1..30 ("invalid HTJ2K Kmax", openjph_cleanup_encoder.go:201-203)
- *   bytes_out : the cleanup segments of all blocks, back to back in block order; *nbytes_out receives their total size.
+ *   bytes_out : the cleanup segments of all blocks, back to back (in block order when the context has one device; with several,
+ *               sub-batch by sub-batch as the host collects them from the devices -- the records locate every segment);
+ *               *nbytes_out receives their total size.
  *               When bytes_cap is too small the call fails with J2K_ERR_SIZE and *nbytes_out holds a size that was needed
  *               (j2k_ht_encode_bound gives a capacity that always suffices)
  *   cblks_out : one record per (frame, block) in the order of the code-block interface: offset / length of the block's
  *               segment (length 0: the block is empty, "return nil, nil" :218-220 -> not included in the packet), its Kmax and
  *               missing_msbs = Kmax - 1 (zeroBitPlanes of codeBlockPassLayout, encoder.go:3381-3388) -- what T2 needs.
- * p->htj2k should be set (no T1 fixed point, encoder.go:3293-3300).  Runs on the context's first device. */
+ * p->htj2k should be set (no T1 fixed point, encoder.go:3293-3300).  The frames are sharded over the context's devices in
+ * contiguous blocks like every host-batch call (no collective). */
 int j2k_forward_ht(j2k_ctx* ctx, const j2k_fwd_params* p, int cb_width, int cb_height, int nframes, const void* pixels,
                    size_t frame_stride_bytes, const uint8_t* kmax, uint8_t* bytes_out, size_t bytes_cap, size_t* nbytes_out,
                    j2k_ht_cblk* cblks_out);

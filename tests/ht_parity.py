@@ -178,9 +178,11 @@ def band_kmax_table(components, levels, base):
     return np.minimum(t, 30)
 
 
-def check_encode(ctx, ht, oracle, w, h, comps, bits, levels, cbw, cbh, seed, nframes=1, reversible=True, base=None, tile=None):
+def check_encode(ctx, ht, oracle, w, h, comps, bits, levels, cbw, cbh, seed, nframes=1, reversible=True, base=None, tile=None, ordered=True):
     """forward transform + HT block encoding on the device: every block's bytes == the oracle's restatement of HTEncoder.Encode
-    applied to the oracle's coefficients of the same frame; records consistent; the stream decodes back (device decoder)"""
+    applied to the oracle's coefficients of the same frame; records consistent; the stream decodes back (device decoder).
+    ordered=False: a context with several devices appends the sub-batches as it collects them, so only the records locate the
+    segments; they must still tile the stream exactly (disjoint, no gaps)."""
     rng = np.random.default_rng(seed)
     depth = 8 if bits <= 8 else 16
     bpp = 1 if depth == 8 else 2
@@ -209,6 +211,7 @@ def check_encode(ctx, ht, oracle, w, h, comps, bits, levels, cbw, cbh, seed, nfr
     nblk = rec.size // nframes
     # the oracle's coefficients and block layout (per tile, per component)
     pos = 0
+    spans = []
     for f in range(nframes):
         co = oracle.forward(fp, frames[f])
         k = f * nblk
@@ -233,13 +236,19 @@ def check_encode(ctx, ht, oracle, w, h, comps, bits, levels, cbw, cbh, seed, nfr
                     assert int(r["kmax"]) == km and int(r["missing_msbs"]) == km - 1, (f, k)
                     assert int(r["length"]) == len(want), (f, k, b.width, b.height, int(r["length"]), len(want))
                     if want:
-                        assert int(r["offset"]) == pos, (f, k)
-                        got = stream[pos:pos + len(want)].tobytes()
+                        ro = int(r["offset"])
+                        if ordered:
+                            assert ro == pos, (f, k)
+                        assert ro + len(want) <= stream.size, (f, k)
+                        got = stream[ro:ro + len(want)].tobytes()
                         assert got == want, (f, k, b.width, b.height, [i for i in range(len(want)) if got[i] != want[i]][:6])
                         pos += len(want)
+                        spans.append((ro, len(want)))
                     k += 1
         assert k == (f + 1) * nblk
     assert pos == stream.size
+    spans.sort()
+    assert all(spans[i][0] + spans[i][1] == spans[i + 1][0] for i in range(len(spans) - 1)) and (not spans or spans[0][0] == 0)
     return stream, rec, fp, frames
 
 

@@ -76,6 +76,19 @@ def test_encode_frames_tiles_and_tight_kmax(ectx, ht, oracle):
     HP.check_encode(ectx, ht, oracle, 64, 48, 1, 12, 1, 64, 64, seed=6, base=6)
 
 
+def test_encode_sharded_over_the_devices_of_a_context(ht, oracle, monkeypatch):
+    """j2k_forward_ht cuts the frames into contiguous blocks, one per device of the context (here: the emulated device twice),
+    each with its own lagged sub-batch pipeline; sub-batches of one frame so that every device runs several."""
+    import emu_lib
+    import j2kb200
+    monkeypatch.setenv("J2K_HT_SUBBATCH_MSAMPLES", "0")   # -> one frame per sub-batch
+    with j2kb200.Context(devices=[0, 0], lib_path=emu_lib.build()) as c2:
+        assert c2.device_count == 2
+        HP.check_encode(c2, ht, oracle, 72, 56, 1, 12, 2, 32, 32, seed=4, nframes=7, ordered=False)
+        HP.check_encode(c2, ht, oracle, 40, 40, 3, 8, 1, 16, 16, seed=9, nframes=2, reversible=False, ordered=False)
+        HP.check_encode(c2, ht, oracle, 64, 48, 1, 12, 1, 64, 64, seed=6, nframes=1, ordered=False)   # fewer frames than devices
+
+
 def test_encoder_table_matches_the_oracle(ectx, ht):
     import numpy as np
     for which in (0, 1):

@@ -137,3 +137,23 @@ def test_encode_sub_batches_and_small_capacity(ctx, ht, oracle, monkeypatch):
     assert e.value.code == abi.J2K_ERR_SIZE
     with pytest.raises(j2kb200.J2KError, match="Kmax"):
         ctx.forward_ht(fp, frames[:1], np.full((1, 16), 31, np.uint8))
+
+
+def test_encode_sharded_over_the_devices_of_a_context(ht, oracle, monkeypatch):
+    """j2k_forward_ht shards the frames over the devices of the context in contiguous blocks, each with its own
+    lagged sub-batch pipeline.  Every visible device, plus device 0 once more, so that the path runs on a one-GPU box too; the
+    segments are located by the records (with several devices they are appended as the host collects them)."""
+    import torch
+
+    import j2kb200
+    from j2kb200 import abi
+    devs = list(range(torch.cuda.device_count())) + [0]
+    with j2kb200.Context(devices=devs) as mctx:
+        assert mctx.device_count == len(devs)
+        stream, rec, fp, frames = HP.check_encode(mctx, ht, oracle, 300, 200, 1, 12, 3, 64, 64, seed=7, nframes=2 * len(devs) + 1, ordered=False)
+        ip = abi.inv_params(300, 200, 1, 12, False, num_levels=3, reversible=True, htj2k=True)
+        px, st = mctx.inverse_ht(ip, frames.shape[0], np.concatenate([stream, np.zeros(16, np.uint8)]), rec)
+        assert not st.any() and np.array_equal(px, frames)
+        monkeypatch.setenv("J2K_HT_SUBBATCH_MSAMPLES", "1")   # several sub-batches per device: the lagged collection, interleaved
+        HP.check_encode(mctx, ht, oracle, 1024, 1024, 1, 12, 5, 64, 64, seed=8, nframes=9, ordered=False)
+        HP.check_encode(mctx, ht, oracle, 128, 96, 3, 8, 2, 32, 32, seed=3, nframes=1, reversible=False, ordered=False)   # fewer frames than devices
