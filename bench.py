@@ -195,8 +195,8 @@ def cpu_leg(threads, frames, steps, warmup):
 OTHER_CONFIGS = [
     # key, description, w, h, components, bits, signed, levels, reversible, frames per launch, tile
     ("C1", "C1 x256: 512x512 16-bit signed mono, 5/3 L5 (256 frames per launch)", 512, 512, 1, 16, True, 5, True, 256, (0, 0)),
-    ("C3i", "C3(i) x8: 2048x2048 RGB 8-bit, ICT + 9/7 L5 (8 frames per launch)", 2048, 2048, 3, 8, False, 5, False, 8, (0, 0)),
-    ("C3ii", "C3(ii) x8: 2048x2048 RGB 8-bit, RCT + 5/3 L5 (8 frames per launch)", 2048, 2048, 3, 8, False, 5, True, 8, (0, 0)),
+    ("C3i", "C3(i) x32: 2048x2048 RGB 8-bit, ICT + 9/7 L5 (32 frames per launch)", 2048, 2048, 3, 8, False, 5, False, 32, (0, 0)),
+    ("C3ii", "C3(ii) x32: 2048x2048 RGB 8-bit, RCT + 5/3 L5 (32 frames per launch)", 2048, 2048, 3, 8, False, 5, True, 32, (0, 0)),
     ("C4", "C4 block: 250 of the 2000 frames 512x512 16-bit, 5/3 L5 (one GPU's share at N = 8)", 512, 512, 1, 16, False, 5, True, 250, (0, 0)),
     ("C5", "C5 block: 128 of the 1024 tiles 1024x1024 RGB 8-bit (8192x16384 image), ICT + 9/7 L7 (one GPU's share at N = 8)",
      8192, 16384, 3, 8, False, 7, False, 1, (1024, 1024)),

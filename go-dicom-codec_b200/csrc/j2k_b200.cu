@@ -570,6 +570,17 @@ int env_int(const char* name, int dflt) {
     return v && *v ? atoi(v) : dflt;
 }
 
+// SMs of the current device (the emulator has one)
+int device_sm_count() {
+#ifdef J2K_EMU
+    return 1;
+#else
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) return 148;
+    return sms;
+#endif
+}
+
 // Job decomposition of one ring segment: even column strips, row chunks sized for ~2 jobs per resident warp.
 void ring_chunks(RingSeg& g, int NP, int n_cols_total_hint, int level, int halo_lanes = 2, int target_div = 1) {
     int VP = (32 - halo_lanes) * NP;  // 32 lanes minus one halo lane per side (9/7 needs 2 pairs, 5/3 one: both fit NP >= 2); halo-free: 32
@@ -697,7 +708,7 @@ int ring_schedule(RingPlan& R, Plan& P, int n_ctl) {
 
 // Converts the per-level launch list into ONE persistent launch when every level qualifies; otherwise P.ring.ok stays false
 // and run_plan uses the per-level kernels.
-int build_ring_fwd_impl(const Spec& s, Plan& P, const std::vector<long long>& tab, bool split3, int cut);
+int build_ring_fwd_impl(const Spec& s, Plan& P, const std::vector<long long>& tab, bool split3, int cut, bool allow_x3);
 int ring_schedule(RingPlan& R, Plan& P, int n_ctl);
 
 // The persistent launch takes levels 1..cut, the largest cut whose levels all have the geometry it needs (window widths
@@ -707,9 +718,10 @@ int ring_schedule(RingPlan& R, Plan& P, int n_ctl);
 int build_ring_fwd(const Spec& s, Plan& P, const std::vector<long long>& tab) {
     int maxlevel = 0;
     for (auto& l : P.levels) maxlevel = l.level > maxlevel ? l.level : maxlevel;
-    for (int split = (!s.reversible && env_int("J2K_RING_SPLIT3", 1)) ? 1 : 0; split >= 0; split--)
+    // split 2: component-split level 1 on fwd3w_kernel (big launches only), 1: as component jobs of fwd_ring_kernel, 0: NP = 2
+    for (int split = (!s.reversible && env_int("J2K_RING_SPLIT3", 1)) ? (env_int("J2K_FWD3W", J2K_FWD3W_DEFAULT) ? 2 : 1) : 0; split >= 0; split--)
         for (int cut = maxlevel; cut >= 1; cut--) {
-            int rc = build_ring_fwd_impl(s, P, tab, split != 0, cut);
+            int rc = build_ring_fwd_impl(s, P, tab, split != 0, cut, split == 2);
             if (rc) return rc;
             if (P.ring.ok) {
                 P.ring.cut = cut;
@@ -720,7 +732,7 @@ int build_ring_fwd(const Spec& s, Plan& P, const std::vector<long long>& tab) {
     return 0;
 }
 
-int build_ring_fwd_impl(const Spec& s, Plan& P, const std::vector<long long>& tab, bool split3, int cut) {
+int build_ring_fwd_impl(const Spec& s, Plan& P, const std::vector<long long>& tab, bool split3, int cut, bool allow_x3) {
     RingPlan& R = P.ring;
     R.ok = false;
     if (env_int("J2K_RING_DISABLE", 0)) return 0;
@@ -737,6 +749,9 @@ int build_ring_fwd_impl(const Spec& s, Plan& P, const std::vector<long long>& ta
     bool have_first = false;
     bool ua = false;
     int n_ctl = 2, jobs = 0;
+    R.X3 = 0;
+    // component-split level 1 as one converting producer warp + three single-component consumers per CTA (fwd3w_kernel)
+    const bool use_x3 = split3 && allow_x3;
     for (size_t si = 0; si < order.size(); si++) {
         const LevelLaunch& l = P.levels[order[si]];
         const LevelArgs& a = l.a;
@@ -744,6 +759,7 @@ int build_ring_fwd_impl(const Spec& s, Plan& P, const std::vector<long long>& ta
         const bool first = l.level == 1;
         const bool raw_in = l.KIND == IN_U8 || l.KIND == IN_U16;
         const bool split = split3 && first && l.NC == 3 && raw_in && l.MCT == MCTK_ICT;  // one component per job
+        const bool x3 = split && use_x3;
         const int NP = (l.NC == 3 && !split) ? 2 : 4;
         const int SG = (raw_in && P.raw.sign_sub != 0) ? 1 : 0;
         const int ES = l.KIND == IN_U8 ? 1 : (l.KIND == IN_U16 ? 2 : 4);
@@ -754,7 +770,7 @@ int build_ring_fwd_impl(const Spec& s, Plan& P, const std::vector<long long>& ta
         if (first) {
             if (!ring_variant_supported(WT, NP, l.NC, l.KIND, l.MCT, SG)) return 0;
             if (l.NC == 1 && raw_in && s.C != 1) return 0;  // strided components
-            if (!have_first) { R.WT = WT; R.NP1 = NP; R.NC1 = l.NC; R.IN1 = l.KIND; R.MCT1 = l.MCT; R.SG1 = SG; have_first = true; }
+            if (!have_first) { R.WT = WT; R.NP1 = NP; R.NC1 = l.NC; R.IN1 = l.KIND; R.MCT1 = l.MCT; R.SG1 = SG; R.X3 = x3 ? 1 : 0; have_first = true; }
             else if (R.NP1 != NP || R.NC1 != l.NC || R.IN1 != l.KIND || R.MCT1 != l.MCT || R.SG1 != SG) return 0;
         } else {
             if (l.NC != 1 || l.KIND != (WT == 53 ? IN_I32 : IN_F32)) return 0;
@@ -813,7 +829,32 @@ int build_ring_fwd_impl(const Spec& s, Plan& P, const std::vector<long long>& ta
         g.x_off = a.x_off;
         g.x_row_bytes = pitch;
         g.ll = a.ll; g.hl = a.hl; g.lh_ = a.lh_; g.hh = a.hh;
-        ring_chunks(g, NP, g.n_items, l.level);
+        if (x3) {
+            // A pixel job of fwd3w_kernel occupies a quad (four warps), and a launch has only sms x 4 quads: the chunk height
+            // is chosen so that the job count fills whole rounds of them.  Estimated makespan of n chunks of cp row pairs:
+            // rounds x (cp + the 2 LAG warm-up pairs a chunk recomputes + the start-up bubble of a job, ~16 pairs measured).
+            ring_chunks(g, NP, a.n_items, l.level, 2, env_int("J2K_FWD3W_TDIV", 4));
+            const long long slots = (long long)device_sm_count() * J2K_F3_QUADS;
+            // Small launches stay on the component jobs: with fewer than ~3 full-height jobs per quad the coarser levels no longer
+            // overlap level 1 and the tail decides (8 C3 frames: 0.57 against 0.62 of the HBM peak; 32 frames: 0.71 against 0.70;
+            // 128 C5 tiles: 0.65 against 0.60).  J2K_FWD3W=2 forces the kernel (tests).
+            if (env_int("J2K_FWD3W", J2K_FWD3W_DEFAULT) < 2 &&
+                (long long)a.n_items * g.nstrips * g.Ky < (long long)env_int("J2K_FWD3W_MIN_PAIRS", 400) * slots) return 0;
+            if (!env_int("J2K_FWD3W_TDIV", 0)) {
+                const int max_chunk = env_int("J2K_RING_CHUNK", 128), min_chunk = env_int("J2K_RING_CHUNK_MIN", 8);
+                const int bubble = env_int("J2K_FWD3W_BUBBLE", 16);
+                long long best = -1;
+                for (int n = 1; n <= g.Ky; n++) {
+                    const int cp = (g.Ky + n - 1) / n;
+                    if (cp > max_chunk) continue;
+                    if (cp < min_chunk && best >= 0) break;
+                    const int nch = (g.Ky + cp - 1) / cp;
+                    const long long nj = (long long)a.n_items * g.nstrips * nch;
+                    const long long cost = ((nj + slots - 1) / slots) * (cp + 4 + bubble);
+                    if (best < 0 || cost < best) { best = cost; g.chunk_pairs = cp; g.nchunks = nch; }
+                }
+            }
+        } else ring_chunks(g, NP, g.n_items, l.level);
         g.dep_seg = -1; g.dep_div = 1; g.dep_target = 0;
         if (!first) {
             // producer: same class, previous level
@@ -840,6 +881,19 @@ int build_ring_fwd_impl(const Spec& s, Plan& P, const std::vector<long long>& ta
     if (!have_first) return 0;
     if (ua && (R.NC1 != 1 || R.NP1 != 4 || (R.IN1 != IN_U8 && R.IN1 != IN_U16))) return 0;  // a deep level needs the general variant but level 1 has none
     R.UA = ua ? 1 : 0;
+    if (R.X3) {
+        // jobs are claimed three at a time per CTA: every segment's range starts at a multiple of three (the padding numbers
+        // decode to items past the end and are skipped); no pipelined slices for this variant
+        int shift = 0;
+        for (int k = 0; k < (int)order.size(); k++) {
+            RingSeg& g = R.args.seg[k];
+            g.job_begin += shift; g.job_end += shift;
+            const int pad = (3 - g.job_end % 3) % 3;
+            g.job_end += pad;
+            shift += pad;
+        }
+        jobs += shift;
+    }
     R.args.nseg = (int)order.size();
     for (int k = 0; k < R.args.nseg; k++) R.args.seg[k].has_waiters = 0;
     for (int k = 0; k < R.args.nseg; k++)
@@ -881,7 +935,30 @@ int ring_blocks_per_sm(const void* fn, int smem_bytes) {
 
 
 // query = true: resident CTAs per SM of the variant (or -1); query = false: launch (0 = launched, -1 = no such variant)
+#define RING_CASE_F3(in)                                                                                                     \
+    if (R.IN1 == in) {                                                                                                      \
+        if (query) {                                                                                                        \
+            const void* fn = (const void*)fwd3w_kernel<in>;                                                                 \
+            int n = 1;                                                                                                      \
+            J2K_F3_QUERY(fn, n)                                                                                             \
+            return n;                                                                                                       \
+        }                                                                                                                   \
+        J2K_LAUNCH_SMEM((fwd3w_kernel<in>), grid, J2K_F3_QUADS * 128, J2K_F3_CTA_SMEM, st, A);                                             \
+        return 0;                                                                                                           \
+    }
+#ifdef J2K_EMU
+#define J2K_F3_QUERY(fn, n) (void)fn;
+#else
+#define J2K_F3_QUERY(fn, n)                                                                                                  \
+    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, J2K_F3_CTA_SMEM) != cudaSuccess) return -1;    \
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, J2K_F3_QUADS * 128, J2K_F3_CTA_SMEM) != cudaSuccess) return -1;
+#endif
+
 int ring_dispatch_fwd(const RingPlan& R, const RingArgs& A, unsigned grid, cudaStream_t st, bool query) {
+    if (R.X3) {
+        RING_CASE_F3(IN_U8) RING_CASE_F3(IN_U16)
+        return -1;
+    }
     RING_CASE(97, 4, 1, IN_U8, MCTK_NONE, 0) RING_CASE(97, 4, 1, IN_U16, MCTK_NONE, 0)
     RING_CASE(97, 4, 1, IN_U8, MCTK_NONE, 1) RING_CASE(97, 4, 1, IN_U16, MCTK_NONE, 1)
     RING_CASE(97, 2, 3, IN_U8, MCTK_ICT, 0) RING_CASE(97, 2, 3, IN_U16, MCTK_ICT, 0)
@@ -1552,11 +1629,13 @@ int run_plan(j2k_ctx* ctx, Plan& P, void* pixels, void* coeffs, void* planes, bo
         static const bool dry = env_int("J2K_RING_DRY", 0) != 0;  // diagnostic: launch overhead only (no job is claimed)
         if (dry) A.total_jobs = 0;
         if (trace)
-            fprintf(stderr, "[j2k] %s ring WT=%d NP=%d NC=%d kind=%d mct=%d sg=%d segs=%d jobs=%d slices=%d grid=%u\n", P.fwd ? "fwd" : "inv", R.WT, R.NP1, R.NC1,
-                    R.IN1, R.MCT1, R.SG1, A.nseg, A.total_jobs, A.nslice, R.grid);
+            fprintf(stderr, "[j2k] %s ring WT=%d NP=%d NC=%d kind=%d mct=%d sg=%d segs=%d jobs=%d slices=%d grid=%u x3=%d\n", P.fwd ? "fwd" : "inv", R.WT, R.NP1, R.NC1,
+                    R.IN1, R.MCT1, R.SG1, A.nseg, A.total_jobs, A.nslice, R.grid, R.X3);
         if (!per_level) {
             unsigned grid = R.grid;
+            // (three-producer inverse: a CTA per job triple; one-producer forward: four quads per CTA, a triple each)
             unsigned need = R.X3 ? (unsigned)((A.total_jobs + 2) / 3) : (unsigned)((A.total_jobs + J2K_RING_WARPS - 1) / J2K_RING_WARPS);
+            if (R.X3 && P.fwd) need = (need + J2K_F3_QUADS - 1) / J2K_F3_QUADS;
             if (need < grid) grid = need;
             if (grid < 1) grid = 1;
             prof.begin(100);

@@ -388,7 +388,27 @@ __device__ __forceinline__ unsigned pack_clamp2_magic_dc(unsigned ua, unsigned u
 template <int UA> __host__ __device__ constexpr int fwd_ring_bytes() { return UA ? J2K_RING_BYTES_UA : J2K_RING_BYTES; }
 template <int UA> __host__ __device__ constexpr int fwd_cta_smem() { return J2K_RING_WARPS * (fwd_ring_bytes<UA>() + J2K_RING_MAXD * 8); }
 
-template <int WT, int NP, int NC, int IN, int MCT, int SG, int XC = 1, int UA = 0>
+// Exchange ring of the one-producer level-1 forward (fwd3w_kernel): DX stages, a stage = the four rows (two row pairs) of
+// one raw stage as float32 ICT outputs of all three components, [component][row][half][lane] x 16 bytes (conflict-free
+// 128-bit accesses; a lane's eight samples are half 0 = samples 0..3, half 1 = samples 4..7).  The producer warp fills a
+// stage and arrives on full[stage]; the three consumer warps (one per component) each arrive on empty[stage] when they
+// are done reading it.
+#ifndef J2K_F3_DX
+#define J2K_F3_DX 3
+#endif
+#define J2K_F3_ROWB 1024
+#define J2K_F3_COMPB (4 * J2K_F3_ROWB)
+#define J2K_F3_STAGEB (3 * J2K_F3_COMPB)
+struct FxPort {
+    smem_t data, full, empty;
+    unsigned cnt;   // stages produced / consumed so far by this warp (all four warps of the CTA count the same stages)
+    int dx;         // stages in the ring
+};
+
+// XCH = 1: the job is one COMPONENT of a three-component level 1 whose rows arrive converted (float32 ICT outputs) through
+// the CTA's exchange ring instead of the TMA ring; XCH = 2: the producer of that ring (stages the raw pixel rows once,
+// converts all three components, no wavelet).
+template <int WT, int NP, int NC, int IN, int MCT, int SG, int XC = 1, int UA = 0, int XCH = 0>
 struct FwdRing {
     typedef FwdLevel<WT, NP, NC, IN, MCT> Slow;
     typedef typename Wt<WT>::T T;
@@ -411,6 +431,10 @@ struct FwdRing {
     static_assert(LB % 4 == 0, "lane span must be whole words");
     static_assert(NC == 1 || RAWIN, "3-component jobs read interleaved raw words");
     static_assert(XC == 1 || (XC == 3 && NC == 1 && MAGIC && MCT == MCTK_ICT), "component split: unsigned raw RGB, float32 ICT");
+    static_assert(XCH == 0 || (WT == 97 && NP == 4 && NC == 1 && !UA), "exchange mode: single-component 9/7 jobs");
+    static_assert(XCH != 1 || (IN == IN_F32 && XC == 1), "exchange consumer reads float32 rows");
+    static_assert(XCH != 2 || XC == 3, "exchange producer stages interleaved raw RGB");
+    static constexpr int SROWB = XCH == 1 ? J2K_F3_ROWB : ROWB;   // distance of the rows the job loop reads
 
     static __device__ __forceinline__ void fetch(smem_t p, unsigned (&w)[NW]) {
         if constexpr (LDALIGN == 16) {
@@ -609,6 +633,17 @@ struct FwdRing {
         }
     }
 
+    // exchange consumer: the lane's eight float32 samples of one row (two conflict-free 128-bit loads)
+    static __device__ __forceinline__ void load_xch(smem_t p, float2 (&out)[NC][NP]) {
+        const uint4 a = lds128(p), b = lds128(p + 512);
+        out[0][0] = make_float2(__uint_as_float(a.x), __uint_as_float(a.y));
+        out[0][1] = make_float2(__uint_as_float(a.z), __uint_as_float(a.w));
+        if constexpr (NP == 4) {
+            out[0][2] = make_float2(__uint_as_float(b.x), __uint_as_float(b.y));
+            out[0][3] = make_float2(__uint_as_float(b.z), __uint_as_float(b.w));
+        }
+    }
+
     static __device__ __forceinline__ void store_vec(int* p, const int (&o)[NP], unsigned long long pol) {
 #if J2K_RING_L2_HINTS
         if constexpr (NP == 4) { stg128_hint(p, o[0], o[1], o[2], o[3], pol); return; }
@@ -637,8 +672,8 @@ struct FwdRing {
 
     // The job loop is instantiated per (load alignment, store class) of the general-alignment variant and chosen once per job.
     static __device__ __forceinline__ void run(const RingSeg& S, const RawFmt& raw, int item, int chunk, int strip, RingWarp& rw,
-                                               int lane) {
-        if constexpr (!UA) run_t<16, 4>(S, raw, item, chunk, strip, rw, lane);
+                                               int lane, FxPort* xp = nullptr, int xcomp = 0) {
+        if constexpr (!UA) run_t<16, 4>(S, raw, item, chunk, strip, rw, lane, xp, xcomp);
         else {
             const int sc = min(min(S.st_cls[0], S.st_cls[1]), min(S.st_cls[2], S.st_cls[3]));
             if (sc >= 2) run_t<4, 2>(S, raw, item, chunk, strip, rw, lane); else run_t<4, 1>(S, raw, item, chunk, strip, rw, lane);
@@ -647,7 +682,8 @@ struct FwdRing {
 
     template <int LA, int SC>
     static __device__ __forceinline__ void run_t(const RingSeg& S, const RawFmt& raw, int item, int chunk, int strip, RingWarp& rw,
-                                               int lane) {
+                                               int lane, FxPort* xp = nullptr, int xcomp = 0) {
+        (void)xp; (void)xcomp;
         const int w = S.w, h = S.h, py = S.py;
         const int hw = w - S.lw, hh = h - S.lh, lh = S.lh;
         const int kxs = strip * S.strip_pairs;
@@ -676,8 +712,9 @@ struct FwdRing {
         const int dc = S.dc;
         const float fmagic = 8388608.0f + (float)dc;
         const float one = rw.one;
-        const int comp = XC == 3 ? item % 3 : 0;   // component-split first level: item = 3 * pixel item + component
-        if constexpr (XC == 3) item /= 3;
+        // component-split first level: item = 3 * pixel item + component; exchange mode: pixel item, the consumer's component given
+        const int comp = XCH == 1 ? xcomp : ((XC == 3 && XCH == 0) ? item % 3 : 0);
+        if constexpr (XC == 3 && XCH == 0) item /= 3;
         // this component's row of the ICT matrix (encoder.go:277-288); warp-uniform
         const float k0 = comp == 0 ? 0.299f : (comp == 1 ? -0.16875f : 0.5f);
         const float k1 = comp == 0 ? 0.587f : (comp == 1 ? -0.331260f : -0.41869f);
@@ -700,7 +737,7 @@ struct FwdRing {
         int* p_hh = (int*)S.hh.base + S.hh.off[item] + (long long)S.hh.y_off * S.hh.row_stride + S.hh.x_off + kx0;
         const int rs_ll = S.ll.row_stride, rs_b = S.hl.row_stride;
         const long long cs_ll = S.ll.comp_stride, cs_b = S.hl.comp_stride;
-        if constexpr (XC == 3) { p_ll += comp * cs_ll; p_hl += comp * cs_b; p_lh += comp * cs_b; p_hh += comp * cs_b; }
+        if constexpr (XC == 3 || XCH == 1) { p_ll += comp * cs_ll; p_hl += comp * cs_b; p_lh += comp * cs_b; p_hh += comp * cs_b; }
         // rows of the first storing iteration (low-type row ky0 - py, high-type row ky0); they advance one row per iteration
         p_ll += (long long)(ky0 - py) * rs_ll; p_hl += (long long)(ky0 - py) * rs_b;
         p_lh += (long long)ky0 * rs_b; p_hh += (long long)ky0 * rs_b;
@@ -748,14 +785,28 @@ struct FwdRing {
             pslot = (pslot + 1 == D) ? 0 : pslot + 1;
         };
         __syncwarp();
+        if constexpr (XCH != 1) {
 #pragma unroll 1
         for (int j = 0; j < D - 1 && j < n_st; j++) issue();
+        }
 
         int cslot = 0;
+        int xheld = -1;  // exchange consumer: the stage slot this warp is reading
+        (void)xheld;
         smem_t stage = rw.ring;
         // start of a stage: the previous stage's slot is free once every lane is past its arithmetic -> refill, then wait
         auto next_stage = [&]() {
             __syncwarp();
+            if constexpr (XCH == 1) {
+                // hand the stage just read back to the producer, wait for the next one
+                if (xheld >= 0 && lane == 0) mbar_arrive(xp->empty + 8 * xheld);
+                const int slot = (int)(xp->cnt % (unsigned)xp->dx);
+                mbar_wait(xp->full + 8 * slot, (xp->cnt / (unsigned)xp->dx) & 1u);
+                stage = xp->data + slot * J2K_F3_STAGEB + comp * J2K_F3_COMPB;
+                xheld = slot;
+                xp->cnt++;
+                return;
+            }
             if (pj < n_st) issue();
             mbar_wait(rw.bars + 8 * cslot, (rw.phase >> cslot) & 1u);
             rw.phase ^= 1u << cslot;
@@ -764,7 +815,50 @@ struct FwdRing {
             if (fix) fix_halo(stage, lane, fix_l, fix_r, w, vb);
         };
         const smem_t lane_s = rw.ring + lane_off;
-        if constexpr (WT == 97) {
+        if constexpr (XCH == 2) {
+            // Producer of the exchange ring: every raw stage is converted ONCE for all three components (unpack, - DC, the three
+            // rows of the float32 ICT, encoder.go:277-288, same operation order as the component-split jobs) and handed to the
+            // three single-component consumers of the CTA.
+            const float2 nm = splat2(-fmagic);
+#pragma unroll 1
+            for (int sj = 0; sj < n_st; sj++) {
+                next_stage();
+                const int slot = (int)(xp->cnt % (unsigned)xp->dx);
+                mbar_wait(xp->empty + 8 * slot, ((xp->cnt / (unsigned)xp->dx) & 1u) ^ 1u);
+                const smem_t xb = xp->data + slot * J2K_F3_STAGEB + lane * 16;
+#pragma unroll
+                for (int r = 0; r < 2 * RPS; r++) {
+                    unsigned wv[NW];
+                    fetch(stage + r * ROWB + lane_off, wv);
+                    float2 y[NP], cb[NP], cr[NP];
+#pragma unroll
+                    for (int j = 0; j < NP; j++) {
+                        float2 f[3];
+#pragma unroll
+                        for (int c = 0; c < 3; c++) {
+                            unsigned p[2];
+#pragma unroll
+                            for (int k = 0; k < 2; k++) {
+                                const int e = 3 * (2 * j + k) + c;
+                                if constexpr (IN == IN_U8) p[k] = __byte_perm(wv[e >> 2], 0x4B000000u, 0x7440u | (e & 3));
+                                else p[k] = __byte_perm(wv[e >> 1], 0x4B000000u, (e & 1) ? 0x7432u : 0x7410u);
+                            }
+                            f[c] = add2(make_float2(__uint_as_float(p[0]), __uint_as_float(p[1])), nm);
+                        }
+                        y[j] = addp2(mul2(f[2], splat2(0.114f)), addp2(mul2(f[0], splat2(0.299f)), mul2(f[1], splat2(0.587f)), one), one);
+                        cb[j] = addp2(mul2(f[2], splat2(0.5f)), addp2(mul2(f[0], splat2(-0.16875f)), mul2(f[1], splat2(-0.331260f)), one), one);
+                        cr[j] = addp2(mul2(f[2], splat2(-0.08131f)), addp2(mul2(f[0], splat2(0.5f)), mul2(f[1], splat2(-0.41869f)), one), one);
+                    }
+                    const smem_t xr = xb + r * J2K_F3_ROWB;
+                    sts128f(xr, y[0], y[1]); sts128f(xr + 512, y[2], y[3]);
+                    sts128f(xr + J2K_F3_COMPB, cb[0], cb[1]); sts128f(xr + J2K_F3_COMPB + 512, cb[2], cb[3]);
+                    sts128f(xr + 2 * J2K_F3_COMPB, cr[0], cr[1]); sts128f(xr + 2 * J2K_F3_COMPB + 512, cr[2], cr[3]);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(xp->full + 8 * slot);
+                xp->cnt++;
+            }
+        } else if constexpr (WT == 97) {
             const float2 A2 = splat2(J2K_ALPHA), B2 = splat2(J2K_BETA), G2 = splat2(J2K_GAMMA), D2 = splat2(J2K_DELTA);
             // quantizer constants per row pair: E positions hold (LL, LH), O positions hold (HL, HH)
             const float2 rcpE = S.rcpE, nstE = S.nstE, rcpO = S.rcpO, nstO = S.nstO;
@@ -781,11 +875,16 @@ struct FwdRing {
             // one iteration: consumes the vertical window state `in`, leaves the advanced state in `out`
             auto body = [&](int it, const int half, const VState& in, VState& out) {
                 if (half == 0) next_stage();
-                const smem_t row_e = stage + half * 2 * ROWB;
-                const smem_t row_o = row_e + ROWB;
+                const smem_t row_e = stage + half * 2 * SROWB;
+                const smem_t row_o = row_e + SROWB;
 
+                if constexpr (XCH == 1) {
+                    load_xch(row_e + lane * 16, out.pe);
+                    load_xch(row_o + lane * 16, out.po);
+                } else {
                 load_pairs<LA>(row_e, lane_off, raw, dc, fmagic, one, out.pe, k0, k1, k2);
                 load_pairs<LA>(row_o, lane_off, raw, dc, fmagic, one, out.po, k0, k1, k2);
+                }
                 // vertical lifting on column pairs; the finished (low, high) row values of column s land in Q[c][s]
                 float2 Q[NC][NS];
 #pragma unroll
@@ -897,6 +996,10 @@ struct FwdRing {
                 body(it, 0, sa, sb);
                 if (it + 1 >= n_it) break;
                 body(it + 1, 1, sb, sa);
+            }
+            if constexpr (XCH == 1) {  // the last stage goes back to the producer
+                __syncwarp();
+                if (xheld >= 0 && lane == 0) mbar_arrive(xp->empty + 8 * xheld);
             }
         } else {
             const int sh_ll = S.q[0].shift, sh_hl = S.q[1].shift, sh_lh = S.q[2].shift, sh_hh = S.q[3].shift;
@@ -2004,19 +2107,21 @@ struct Inv3WConsumer {
 
 // job number -> (segment, item, chunk, strip, component); level-1 pixel jobs hold three numbers, ranges are padded to
 // multiples of three (J.item < 0: a padding number, nothing to do)
-__device__ __forceinline__ void x3_decode(const RingArgs& A, int job, RingJob& J, int& comp) {
+// (fdiv = 3: the forward's first segment counts its items per component, S.n_items = 3 x pixel items)
+__device__ __forceinline__ void x3_decode(const RingArgs& A, int job, RingJob& J, int& comp, int fdiv = 1) {
     int k = 0;
     while (k + 1 < A.nseg && job >= A.seg[k].job_end) k++;
     const RingSeg& S = A.seg[k];
     int local = job - S.job_begin;
     comp = 0;
-    if (S.first) { comp = local % 3; local /= 3; }
+    int n_items = S.n_items;
+    if (S.first) { comp = local % 3; local /= 3; n_items /= fdiv; }
     const int ns = S.nstrips, nc = S.nchunks;
     J.seg = k;
     J.strip = local % ns;
     J.chunk = (local / ns) % nc;
     J.item = local / (ns * nc);
-    if (J.item >= S.n_items) J.item = -1;
+    if (J.item >= n_items) J.item = -1;
 }
 
 template <int OUT>
@@ -2121,6 +2226,169 @@ __global__ void __launch_bounds__(128, J2K_RING_MINB) inv3w_kernel(const __grid_
             ring_wait_dep(A, S, J.item, lane);
             InvRing<97, 4, 1, IN_F32, MCTK_NONE, J2K_X3_RING_BYTES>::run(S, A.raw, J.item, J.chunk, J.strip, rw, lane);
             ring_signal(A, S, J.item, lane);
+        }
+    }
+    ring_retire(A, lane);
+#endif
+}
+
+// ------------------------------------------------------------------ one-producer level-1 forward (ICT + 9/7, raw RGB)
+//
+// Mirror image of inv3w_kernel.  The component-split level 1 (FwdRing XC = 3) lets every component job unpack all three
+// samples of a pixel and keep one ICT row: the raw bytes are converted three times (35.9 thread instructions per sample
+// against 25.9 for a single-component frame).  Here a CTA of four warps shares a pixel job: warp 3 stages the raw rows
+// (own TMA ring), converts them ONCE and writes the float32 Y / Cb / Cr rows into an exchange ring in shared memory;
+// warps 0..2 each run the single-component pipeline (FwdRing<97, NP = 4, IN_F32> in exchange mode) for one component,
+// reading their rows from that ring (mbarrier full / empty per stage, no CTA barrier in the loop).  Coarser levels: warps
+// 0..2 take ordinary single-component jobs with private TMA rings that alias the (then idle) exchange ring, warp 3 idles.
+// Jobs are taken three at a time per CTA; a level-1 pixel job occupies three consecutive job numbers, every segment's
+// job range is padded to a multiple of three.
+#ifndef J2K_FWD3W_DEFAULT
+#define J2K_FWD3W_DEFAULT 1   // ICT + 9/7 raw RGB forward: one-producer level 1 (fwd3w_kernel) instead of three converting component jobs
+#endif
+// A CTA holds FOUR such quads (16 warps, one CTA per SM): warps 0..3 (warpgroup 0) are the producers of quads 0..3, warps
+// 4 + 3q .. 6 + 3q the consumers of quad q.  The producers give registers back (setmaxnreg.dec) and the consumer
+// warpgroups take them (setmaxnreg.inc), so the SM runs 12 wavelet warps with the full window state in registers PLUS the
+// four converting warps - with uniform registers a fourth CTA of four warps does not fit (168 x 16 warps).  There is no
+// CTA barrier in the job loop: a quad's producer claims the job triples (one atomic each), announces them to its
+// consumers through a two-slot queue in shared memory and runs ahead into the next job while they finish the last one.
+#define J2K_F3_QUADS 4
+#define J2K_F3_REGS_PRODUCER 56
+#define J2K_F3_REGS_CONSUMER 152   // 12 x 32 x 152 + 4 x 32 x 56 = 65536 = 512 threads x 128 registers at launch
+#define J2K_F3_XBYTES (3 * J2K_RING_BYTES)       // exchange ring / the three private rings of the coarser levels
+// per quad: exchange / private rings, the producer's raw ring, 4 x MAXD staging barriers, full / empty of the exchange ring,
+// full / empty of the job queue, the queue's two job numbers
+#define J2K_F3_QUAD_SMEM (J2K_F3_XBYTES + J2K_RING_BYTES + 4 * J2K_RING_MAXD * 8 + 2 * J2K_F3_DX * 8 + 4 * 8 + 16 + 160)
+#define J2K_F3_CTA_SMEM (J2K_F3_QUADS * J2K_F3_QUAD_SMEM)
+static_assert(J2K_F3_DX * J2K_F3_STAGEB <= J2K_F3_XBYTES, "exchange ring must fit the aliased staging");
+static_assert(J2K_F3_QUAD_SMEM % 128 == 0, "quads keep the 128-byte alignment of the staging");
+
+template <int IN>
+__global__ void __launch_bounds__(J2K_F3_QUADS * 128, 1) fwd3w_kernel(const __grid_constant__ RingArgs A) {
+    J2K_SMEM_DECL(smem);
+    const int lane = threadIdx.x & 31;
+    typedef FwdRing<97, 4, 1, IN, MCTK_ICT, 0, 3, 0, 2> Producer;
+    typedef FwdRing<97, 4, 1, IN_F32, MCTK_NONE, 0, 1, 0, 1> Consumer;
+    typedef FwdRing<97, 4, 1, IN_F32, MCTK_NONE, 0, 1, 0> Deep;
+#ifdef J2K_EMU
+    // the emulator runs warps one after the other: ONE warp plays all four roles of a pixel job in turn, with an exchange
+    // ring deep enough for a whole chunk (the arithmetic and the index logic are the same; the barriers are no-ops)
+    static thread_local unsigned char* xbig = nullptr;
+    if (!xbig) xbig = (unsigned char*)malloc((size_t)J2K_F3_STAGEB * 256);
+    RingWarp rw;
+    rw.ring = smem_handle(smem);
+    rw.bars = rw.ring + J2K_RING_BYTES;
+    rw.phase = 0;
+    rw.one = A.one;
+    for (;;) {
+        int job = 0;
+        if (lane == 0) job = (int)atomicAdd(A.ctl, 3u);
+        job = __shfl_sync(0xffffffffu, job, 0);
+        if (job >= A.total_jobs) break;
+        RingJob J; int comp;
+        x3_decode(A, job, J, comp, 3);
+        const RingSeg& S = A.seg[J.seg];
+        if (S.first) {
+            if (J.item < 0) continue;
+            FxPort xp{smem_handle(xbig), smem_handle(xbig), smem_handle(xbig), 0u, 256};
+            Producer::run(S, A.raw, J.item, J.chunk, J.strip, rw, lane, &xp, 0);
+            for (int c = 0; c < 3; c++) {
+                xp.cnt = 0;
+                Consumer::run(S, A.raw, J.item, J.chunk, J.strip, rw, lane, &xp, c);
+                if (S.has_waiters && lane == 0) red_release_add(A.ctl + S.done_base + 3 * J.item + c, 1u);
+            }
+        } else {
+            for (int q = 0; q < 3; q++) {
+                x3_decode(A, job + q, J, comp, 3);
+                if (J.item < 0 || job + q >= A.seg[J.seg].job_end) continue;
+                const RingSeg& T = A.seg[J.seg];
+                Deep::run(T, A.raw, J.item, J.chunk, J.strip, rw, lane);
+                if (T.has_waiters && lane == 0) red_release_add(A.ctl + T.done_base + J.item, 1u);
+            }
+        }
+    }
+    ring_retire(A, lane);
+#else
+    const int wib = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const bool producer = wib < J2K_F3_QUADS;
+    const int quad = producer ? wib : (wib - J2K_F3_QUADS) / 3;
+    const int role = producer ? 3 : (wib - J2K_F3_QUADS) % 3;   // consumers: their component
+    unsigned char* qs = smem + quad * J2K_F3_QUAD_SMEM;
+    RingWarp rw;
+    rw.phase = 0;
+    rw.one = A.one;
+    // consumers: private staging inside the exchange region (coarser levels only); producer: the raw-row staging behind it
+    rw.ring = smem_handle(qs + role * J2K_RING_BYTES);
+    rw.bars = smem_handle(qs + 4 * J2K_RING_BYTES + role * J2K_RING_MAXD * 8);
+    if (lane == 0) {
+        for (int q = 0; q < J2K_RING_MAXD; q++) mbar_init(rw.bars + 8 * q, 1);
+    }
+    FxPort xp;
+    xp.data = smem_handle(qs);
+    xp.full = smem_handle(qs + 4 * J2K_RING_BYTES + 4 * J2K_RING_MAXD * 8);
+    xp.empty = xp.full + 8 * J2K_F3_DX;
+    xp.cnt = 0;
+    xp.dx = J2K_F3_DX;
+    const smem_t jq_full = xp.empty + 8 * J2K_F3_DX, jq_empty = jq_full + 16, jq_job = jq_empty + 16;
+    if (producer && lane == 0) {
+        for (int q = 0; q < J2K_F3_DX; q++) { mbar_init(xp.full + 8 * q, 1); mbar_init(xp.empty + 8 * q, 3); }
+        for (int q = 0; q < 2; q++) { mbar_init(jq_full + 8 * q, 1); mbar_init(jq_empty + 8 * q, 3); }
+    }
+    if (lane == 0) mbar_fence_init();
+    __syncthreads();
+    unsigned jcnt = 0;  // job triples announced / taken so far
+    if (producer) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(J2K_F3_REGS_PRODUCER));
+        for (;;) {
+            int base = 0;
+            if (lane == 0) base = (int)atomicAdd(A.ctl, 3u);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const int slot = (int)(jcnt & 1u);
+            mbar_wait(jq_empty + 8 * slot, ((jcnt >> 1) & 1u) ^ 1u);
+            if (lane == 0) { sts32(jq_job + 4 * slot, (unsigned)base); mbar_arrive(jq_full + 8 * slot); }
+            jcnt++;
+            if (base >= A.total_jobs) break;
+            RingJob J; int comp;
+            x3_decode(A, base, J, comp, 3);
+            const RingSeg& S = A.seg[J.seg];
+            if (S.first && J.item >= 0) Producer::run(S, A.raw, J.item, J.chunk, J.strip, rw, lane, &xp, 0);
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(J2K_F3_REGS_CONSUMER));
+        bool deep_seen = false;
+        for (;;) {
+            const int slot = (int)(jcnt & 1u);
+            mbar_wait(jq_full + 8 * slot, (jcnt >> 1) & 1u);
+            const int base = __shfl_sync(0xffffffffu, (int)lds32(jq_job + 4 * slot), 0);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(jq_empty + 8 * slot);
+            jcnt++;
+            if (base >= A.total_jobs) break;
+            RingJob J; int comp;
+            x3_decode(A, base + role, J, comp, 3);
+            const RingSeg& S = A.seg[J.seg];
+            if (S.first) {
+                // the three numbers of a pixel job never straddle a segment: ranges are padded to multiples of three
+                if (J.item < 0) continue;
+                Consumer::run(S, A.raw, J.item, J.chunk, J.strip, rw, lane, &xp, comp);
+                if (S.has_waiters) {
+                    __syncwarp();
+                    if (lane == 0) red_release_add(A.ctl + S.done_base + 3 * J.item + comp, 1u);
+                }
+            } else {
+                if (!deep_seen) {
+                    // level 1 is over for this quad (the list is level-major): the exchange region becomes the three private
+                    // staging rings once all three consumers have read its last stage (generic-proxy accesses before, bulk copies after)
+                    fence_proxy_async();
+                    asm volatile("bar.sync %0, 96;" ::"r"(1 + quad) : "memory");
+                    deep_seen = true;
+                }
+                if (J.item >= 0 && base + role < S.job_end) {
+                    ring_wait_dep(A, S, J.item, lane);
+                    Deep::run(S, A.raw, J.item, J.chunk, J.strip, rw, lane);
+                    ring_signal(A, S, J.item, lane);
+                }
+            }
         }
     }
     ring_retire(A, lane);

@@ -330,8 +330,9 @@ def check_pipelined_order(ctx, oracle, w, h, c, bits, L, reversible, nframes, gr
     J2K_RING_GROUP_KS / J2K_RING_LAG are read when the plan is built, so the geometry must be new to the context)."""
     import os
     import re
-    old = {k: os.environ.get(k) for k in ("J2K_RING_GROUP_KS", "J2K_RING_LAG", "J2K_B200_TRACE")}
-    os.environ.update(J2K_RING_GROUP_KS=str(group_ks), J2K_RING_LAG=str(lag), J2K_B200_TRACE="1")
+    old = {k: os.environ.get(k) for k in ("J2K_RING_GROUP_KS", "J2K_RING_LAG", "J2K_B200_TRACE", "J2K_FWD3W")}
+    # (the one-producer RGB forward numbers its jobs in triples and keeps the level-major list: component-split jobs here)
+    os.environ.update(J2K_RING_GROUP_KS=str(group_ks), J2K_RING_LAG=str(lag), J2K_B200_TRACE="1", J2K_FWD3W="0")
     try:
         rng = np.random.default_rng(w + nframes)
         frames = np.stack([raw_bytes(synth(rng, h, w, c, bits, False, "noise")) for _ in range(nframes)])
@@ -489,3 +490,38 @@ def check_blocks_roi_general(ctx, oracle, w, h, c, bits, L, reversible, tile=(0,
     for f in range(nframes):
         want_px = oracle.inverse(ip2, want_planes[f])
         assert np.array_equal(px[f], want_px), f"inverse from general-scaling ROI blocks, frame {f}"
+
+
+def check_one_producer_forward(ctx, oracle, w, h, bits, L, nframes, tile=(0, 0), chunk=0, capfd=None, arm_on="2"):
+    """ICT + 9/7 forward of a batch of raw RGB frames through the one-producer level-1 kernel (fwd3w_kernel, j2k_ring.cuh)
+    and, for the same frames, through the component-split jobs it replaces (J2K_FWD3W=0): both bit-identical to the oracle
+    (encoder.go:277-288 + dwt97.go:47-190 + encoder.go:2311-2329).  Environment knobs are read when a plan is built, so each
+    arm uses a geometry / batch size new to the context (a frame more for the second arm)."""
+    import os
+    import re
+    old = {k: os.environ.get(k) for k in ("J2K_FWD3W", "J2K_RING_CHUNK", "J2K_B200_TRACE")}
+    try:
+        os.environ["J2K_B200_TRACE"] = "1"
+        if chunk:
+            os.environ["J2K_RING_CHUNK"] = str(chunk)
+        rng = np.random.default_rng(w * 7 + h)
+        frames = np.stack([raw_bytes(synth(rng, h, w, 3, bits, False, "noise" if f & 1 else "smooth")) for f in range(nframes + 1)])
+        fp, _ = fwd_inv_params(w, h, 3, bits, False, L, False, oracle, tile)
+        want = [oracle.forward(fp, frames[f]) for f in range(nframes + 1)]
+        for arm, n in ((arm_on, nframes), ("0", nframes + 1)):  # 2: also for launches below the size the plan builder asks for (1)
+            os.environ["J2K_FWD3W"] = arm
+            co = ctx.forward_batch(fp, frames[:n])
+            for f in range(n):
+                nd = int(np.count_nonzero(co[f] != want[f]))
+                assert nd == 0, f"J2K_FWD3W={arm}, frame {f}: {nd} differing coefficients"
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    if capfd is not None:
+        err = capfd.readouterr().err
+        if "[j2k]" in err:  # the trace is latched at first use
+            x3 = [int(m) for m in re.findall(r"fwd ring .* x3=(\d)", err)]
+            assert x3 and x3[0] == 1 and x3[-1] == 0, err

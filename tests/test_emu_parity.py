@@ -191,3 +191,18 @@ def test_code_block_interface_roi_general_scaling(ectx, oracle, w, h, c, bits, L
     """SURVEY 8f rank 3, second half: inverse general scaling (RGN Srgn = 1) fused into the block scatter, whole-block and masked."""
     PC.check_blocks_roi_general(ectx, oracle, w, h, c, bits, L, rev, tile=tile, cb=cb, masked=masked)
     PC.check_blocks_roi_general(ectx, oracle, w, h, c, bits, L, rev, tile=tile, cb=cb, masked=masked, maxshift=[3] * c, seed=5)
+
+
+@pytest.mark.parametrize("w,h,bits,L,nframes,tile,chunk", [
+    (512, 44, 8, 3, 2, (0, 0), 0), (256, 40, 8, 2, 3, (0, 0), 8), (512, 24, 16, 3, 1, (0, 0), 0), (256, 64, 8, 2, 2, (128, 32), 0),
+    (768, 50, 12, 2, 2, (0, 0), 8), (320, 37, 8, 2, 1, (0, 0), 0),
+])
+def test_one_producer_rgb97_forward(ectx, oracle, w, h, bits, L, nframes, tile, chunk, capfd):
+    """fwd3w_kernel: ICT + 9/7 level 1 of raw RGB frames as one converting producer warp + three single-component consumers
+    per CTA (several strips, chunks, frames and tile classes; odd heights; coarser levels as job triples behind it)."""
+    PC.check_one_producer_forward(ectx, oracle, w, h, bits, L, nframes, tile, chunk, capfd)
+
+
+def test_one_producer_rgb97_forward_default_policy(ectx, oracle, capfd):
+    """A launch big enough for the plan builder to pick fwd3w_kernel by itself (the emulated device has one SM = four quads)."""
+    PC.check_one_producer_forward(ectx, oracle, 256, 200, 8, 2, 8, capfd=capfd, arm_on="1")

@@ -381,3 +381,13 @@ def test_code_block_interface_roi_general_scaling(ctx, oracle, w, h, c, bits, L,
     """SURVEY 8f rank 3, second half: inverse general scaling (RGN Srgn = 1) fused into the block scatter, whole-block and masked."""
     PC.check_blocks_roi_general(ctx, oracle, w, h, c, bits, L, rev, tile=tile, cb=cb, masked=masked)
     PC.check_blocks_roi_general(ctx, oracle, w, h, c, bits, L, rev, tile=tile, cb=cb, masked=masked, maxshift=[3] * c, seed=5)
+
+
+@pytest.mark.parametrize("w,h,bits,L,nframes,tile,chunk", [
+    (1024, 600, 8, 4, 3, (0, 0), 0), (512, 520, 8, 3, 9, (0, 0), 64), (1024, 256, 16, 4, 2, (0, 0), 0), (2048, 1024, 8, 3, 2, (512, 512), 0),
+    (768, 330, 12, 3, 2, (0, 0), 16), (256, 37, 8, 2, 5, (0, 0), 0), (2048, 2048, 8, 5, 2, (0, 0), 0),
+])
+def test_one_producer_rgb97_forward(ctx, oracle, w, h, bits, L, nframes, tile, chunk):
+    """fwd3w_kernel (one converting producer warp + three single-component consumers per CTA) with real concurrency: many
+    CTAs, exchange-ring wrap-around, job triples of the coarser levels waiting on the per-component counters."""
+    PC.check_one_producer_forward(ctx, oracle, w, h, bits, L, nframes, tile, chunk)
