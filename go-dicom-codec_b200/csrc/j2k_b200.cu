@@ -230,6 +230,7 @@ struct Stager {
 
 struct DeviceCtx {
     int dev = 0;
+    bool failed = false;   // a CUDA call failed and the device did not come back: left out of the round-robin (run_host_batch)
     Stager stg;
     cudaStream_t s_main = nullptr, s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_t[4] = {nullptr, nullptr, nullptr, nullptr};      // timing
@@ -1093,7 +1094,7 @@ int build_ring_inv_impl(const Spec& s, Plan& P, const std::vector<long long>& ta
             }
             g.st_cls[0] = (int)(pal & -pal);  // GetImageData plane rows (UA)
         }
-        ring_chunks(g, NP, g.n_items, l.level, (J2K_INV_HALO_FREE && WT == 53) ? 0 : 2, x3 ? 4 : 1);
+        ring_chunks(g, NP, g.n_items, l.level, (J2K_INV_HALO_FREE && WT == 53) ? 0 : 2, x3 ? env_int("J2K_INV3W_TDIV", 4) : 1);
         g.dep_seg = -1; g.dep_div = 1; g.dep_target = 0; g.dep_mul = 1;
         {
             // producer: same class, next coarser level (absent for the coarsest level of the class)
@@ -2427,30 +2428,91 @@ int sync_dev(j2k_ctx* ctx, int di) {
     return 0;
 }
 
+// Failure detection: after a failing CUDA call on device slot `di`, is the device itself gone?  A sticky error
+// (illegal address, ECC, a GPU that fell off the bus) makes every later call on it fail, cudaDeviceSynchronize included; a
+// logic error (bad launch configuration, a missing kernel variant) leaves the device usable.  A lost device is marked and
+// stays out of the round-robin for the life of the context.  J2K_FAULT_DEVICE=<slot> injects such a failure (tests).
+int fault_slot() {
+    const char* v = getenv("J2K_FAULT_DEVICE");
+    return v && *v ? atoi(v) : -1;
+}
+bool device_lost(j2k_ctx* ctx, int di) {
+    DeviceCtx& d = ctx->devs[di];
+    if (d.failed) return true;
+    bool lost = fault_slot() == di;
+    if (!lost) {
+        if (cudaSetDevice(d.dev) != cudaSuccess) lost = true;
+        else if (cudaDeviceSynchronize() != cudaSuccess) lost = true;
+        cudaGetLastError();
+    }
+    if (lost) {
+        d.failed = true;
+        char msg[160];
+        snprintf(msg, sizeof msg, "device slot %d (CUDA device %d) failed and was removed from the round-robin", di, d.dev);
+        publish_error(ctx, msg);
+    }
+    return lost;
+}
+std::vector<int> healthy_devs(j2k_ctx* ctx) {
+    std::vector<int> h;
+    for (int di = 0; di < (int)ctx->devs.size(); di++)
+        if (!ctx->devs[di].failed) h.push_back(di);
+    return h;
+}
+
+// Frames [f0, f1) over the healthy devices in contiguous blocks.  Blocking calls re-run the block of a device that was lost on
+// the devices that are left; asynchronous submissions report the error (the device is out for the next call).
+int run_frames(j2k_ctx* ctx, const HostJob& J, int f0, int f1, bool wait, std::vector<int>* used, bool timing, int* timing_dev) {
+    const std::vector<int> H = healthy_devs(ctx);
+    if (H.empty()) return fail(J2K_ERR_CUDA, "no usable device left in this context (every device failed)");
+    const int n = f1 - f0, nh = (int)H.size();
+    const int per = (n + nh - 1) / nh;
+    struct Part { int di, a, b, rc; };
+    std::vector<Part> parts;
+    for (int k = 0; k < nh; k++) {
+        const int a = f0 + k * per, b = a + per > f1 ? f1 : a + per;
+        if (a >= b) break;
+        Part pt{H[k], a, b, 0};
+        if (fault_slot() == pt.di) pt.rc = fail(J2K_ERR_CUDA, "injected fault on device slot %d (J2K_FAULT_DEVICE)", pt.di);
+        else pt.rc = enqueue_host_job(ctx, pt.di, J, a, b, timing && k == 0);
+        if (timing && k == 0 && timing_dev) *timing_dev = pt.di;
+        if (used) used->push_back(pt.di);
+        parts.push_back(pt);
+        if (pt.rc && !wait) break;
+    }
+    if (!wait) {
+        for (auto& pt : parts)
+            if (pt.rc) { device_lost(ctx, pt.di); return pt.rc; }
+        return 0;
+    }
+    for (auto& pt : parts) {
+        if (ctx->devs[pt.di].failed || fault_slot() == pt.di) continue;
+        const int r2 = sync_dev(ctx, pt.di);
+        if (pt.rc == 0) pt.rc = r2;
+    }
+    int rc = 0;
+    for (auto& pt : parts) {
+        if (!pt.rc) continue;
+        if (!device_lost(ctx, pt.di)) { if (!rc) rc = pt.rc; continue; }  // not the device: the caller's error
+        if (timing_dev && *timing_dev == pt.di) *timing_dev = -1;
+        const int r2 = run_frames(ctx, J, pt.a, pt.b, true, nullptr, false, nullptr);   // the lost device's block, on the others
+        if (!rc) rc = r2;
+    }
+    return rc;
+}
+
 // Shards nframes over the devices in contiguous blocks (no collective), optionally waits.
 int run_host_batch(j2k_ctx* ctx, const HostJob& J0, int nframes, bool wait, std::vector<int>* used) {
     HostJob J = J0;
     J.may_stage = wait;
-    const int nd = (int)ctx->devs.size();
-    const int per = (nframes + nd - 1) / nd;
     std::lock_guard<std::mutex> lk(ctx->mu);
     long long l0 = ctx->launches.load();
-    int rc = 0;
-    for (int di = 0; di < nd && rc == 0; di++) {
-        int f0 = di * per, f1 = f0 + per > nframes ? nframes : f0 + per;
-        if (f0 >= f1) break;
-        rc = enqueue_host_job(ctx, di, J, f0, f1, wait && di == 0);
-        if (used) used->push_back(di);
-    }
+    int tdev = -1;
+    int rc = run_frames(ctx, J, 0, nframes, wait, used, wait, &tdev);
     if (!wait) return rc;
-    for (int di = 0; di < nd; di++) {
-        int f0 = di * per;
-        if (f0 >= nframes) break;
-        int r2 = sync_dev(ctx, di);
-        if (rc == 0) rc = r2;
-    }
-    if (rc == 0) {
-        DeviceCtx& d = ctx->devs[0];
+    if (rc == 0 && tdev >= 0) {
+        DeviceCtx& d = ctx->devs[tdev];
+        if (set_dev(ctx, tdev)) return 0;
         j2k_timing t{};
         cudaEventElapsedTime(&t.h2d_ms, d.ev_t[0], d.ev_t[1]);
         cudaEventElapsedTime(&t.kernel_ms, d.ev_t[1], d.ev_t[2]);
@@ -2563,6 +2625,10 @@ void j2k_shutdown(j2k_ctx* ctx) {
 }
 
 int j2k_device_count(const j2k_ctx* ctx) { return ctx ? (int)ctx->devs.size() : 0; }
+int j2k_device_failed(const j2k_ctx* ctx, int slot) {
+    if (!ctx || slot < 0 || slot >= (int)ctx->devs.size()) return -1;
+    return ctx->devs[slot].failed ? 1 : 0;
+}
 // CUDA devices visible to this process (0 when there is none or the runtime fails): what a binding passes to j2k_init to
 // build a context over every GPU.
 int j2k_visible_devices(void) {
@@ -2991,14 +3057,17 @@ int j2k_ht_decode_blocks(j2k_ctx* ctx, const j2k_inv_params* p, int cb_width, in
     if (!blocks_out) return fail(J2K_ERR_INVALID_ARG, "NULL buffer");
     const long long cpf = (long long)j2k_inv_coeff_count(p);
     std::lock_guard<std::mutex> lk(ctx->mu);
-    const int nd = (int)ctx->devs.size();
+    const std::vector<int> H = healthy_devs(ctx);   // devices lost earlier stay out (j2k_device_failed)
+    if (H.empty()) return fail(J2K_ERR_CUDA, "no usable device left in this context (every device failed)");
+    const int nd = (int)H.size();
     const int per = (nframes + nd - 1) / nd;
-    std::vector<std::vector<HtBlock>> recs(nd);   // re-based records: alive until the devices are synchronised below
+    std::vector<std::vector<HtBlock>> recs(ctx->devs.size());   // re-based records: alive until the devices are synchronised below
     int used = 0;
-    for (int di = 0; di < nd && rc == 0; di++) {
-        const int f0 = di * per, f1 = f0 + per > nframes ? nframes : f0 + per;
+    for (int hk = 0; hk < nd && rc == 0; hk++) {
+        const int di = H[hk];
+        const int f0 = hk * per, f1 = f0 + per > nframes ? nframes : f0 + per;
         if (f0 >= f1) break;
-        used = di + 1;
+        used = hk + 1;
         if ((rc = sync_dev(ctx, di))) break;   // the slot buffers may still serve an asynchronous job
         DeviceCtx& d = ctx->devs[di];
         const int n = f1 - f0;
@@ -3031,9 +3100,10 @@ int j2k_ht_decode_blocks(j2k_ctx* ctx, const j2k_inv_params* p, int cb_width, in
         if (status_out) CK(cudaMemcpyAsync(status_out + (size_t)f0 * nblk, d.ht_status[0].p, count * 4, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(blocks_out + (size_t)f0 * cpf, d.blk[0].p, (size_t)n * cpf * 4, cudaMemcpyDeviceToHost, st));
     }
-    for (int di = 0; di < used; di++) {
-        int r2 = sync_dev(ctx, di);
+    for (int hk = 0; hk < used; hk++) {
+        int r2 = sync_dev(ctx, H[hk]);
         if (rc == 0) rc = r2;
+        if (r2) device_lost(ctx, H[hk]);
     }
     return rc;
 }
@@ -3175,13 +3245,16 @@ int j2k_forward_ht(j2k_ctx* ctx, const j2k_fwd_params* p, int cb_width, int cb_h
         Pend pend;
         BlockTable* BT;
     };
-    const int nd = (int)ctx->devs.size();
+    const std::vector<int> H = healthy_devs(ctx);   // devices lost earlier stay out (j2k_device_failed)
+    if (H.empty()) return fail(J2K_ERR_CUDA, "no usable device left in this context (every device failed)");
+    const int nd = (int)H.size();
     const int per = (nframes + nd - 1) / nd;
     std::vector<DevRun> runs;
     int kmax_max = 0;
     size_t nblk = 0;
-    for (int di = 0; di < nd; di++) {
-        const int f0 = di * per, f1 = f0 + per > nframes ? nframes : f0 + per;
+    for (int hk = 0; hk < nd; hk++) {
+        const int di = H[hk];
+        const int f0 = hk * per, f1 = f0 + per > nframes ? nframes : f0 + per;
         if (f0 >= f1) break;
         if ((rc = sync_dev(ctx, di))) return rc;   // the slot buffers may still serve an asynchronous job
         DeviceCtx& d = ctx->devs[di];

@@ -2232,6 +2232,11 @@ __global__ void __launch_bounds__(128, J2K_RING_MINB) inv3w_kernel(const __grid_
 #endif
 }
 
+// Measured and rejected (round 2, profiles/exp_r02_inv3q_rejected.log): this job split with four quads per CTA and setmaxnreg, as
+// fwd3w_kernel below does for the forward direction (12 wavelet warps per SM instead of 9).  The inverse wavelet warp needs
+// 166 registers and the pixel warp about 100; 12 x 144 + 4 x 80 and 12 x 152 + 4 x 56 both spill (232 / 416 bytes of stack)
+// and run at 0.28 / 0.17 of the HBM peak on C5 against 0.51 for this kernel (bit-exact either way).
+
 // ------------------------------------------------------------------ one-producer level-1 forward (ICT + 9/7, raw RGB)
 //
 // Mirror image of inv3w_kernel.  The component-split level 1 (FwdRing XC = 3) lets every component job unpack all three

@@ -184,7 +184,7 @@ LIB_PATH = os.path.join(os.path.dirname(_PKG_DIR), "csrc", "build", "libj2kb200.
 
 # every symbol include/j2k_b200.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = [
-    "j2k_init", "j2k_shutdown", "j2k_last_error", "j2k_last_error_copy", "j2k_abi_version", "j2k_device_count", "j2k_visible_devices", "j2k_launch_count",
+    "j2k_init", "j2k_shutdown", "j2k_last_error", "j2k_last_error_copy", "j2k_abi_version", "j2k_device_count", "j2k_device_failed", "j2k_visible_devices", "j2k_launch_count",
     "j2k_last_timing", "j2k_set_profiling", "j2k_get_profile", "j2k_acquire_buffer", "j2k_release_buffer",
     "j2k_fwd_pixel_bytes", "j2k_fwd_coeff_count", "j2k_inv_pixel_bytes", "j2k_inv_coeff_count",
     "j2k_fwd_tile_bounds", "j2k_inv_tile_bounds",
@@ -230,6 +230,7 @@ def load(path: str | None = None) -> C.CDLL:
         "j2k_abi_version": (ci, []),
         "j2k_device_count": (ci, [vp]),
         "j2k_visible_devices": (ci, []),
+        "j2k_device_failed": (ci, [vp, ci]),
         "j2k_launch_count": (C.c_int64, [vp]),
         "j2k_last_timing": (ci, [vp, C.POINTER(Timing)]),
         "j2k_set_profiling": (ci, [vp, ci]),

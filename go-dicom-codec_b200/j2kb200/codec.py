@@ -58,6 +58,10 @@ class Context:
     def device_count(self) -> int:
         return int(self.lib.j2k_device_count(self.h))
 
+    def device_failed(self, slot: int) -> bool:
+        """True when the device in `slot` was lost and removed from the round-robin (j2k_device_failed)."""
+        return int(self.lib.j2k_device_failed(self.h, slot)) == 1
+
     def last_timing(self) -> abi.Timing:
         t = abi.Timing()
         self._ck(self.lib.j2k_last_timing(self.h, C.byref(t)))

@@ -162,6 +162,12 @@ const char* j2k_last_error(j2k_ctx* ctx);
 size_t j2k_last_error_copy(j2k_ctx* ctx, char* buf, size_t cap);
 int j2k_abi_version(void);
 int j2k_device_count(const j2k_ctx* ctx);
+/* Failure detection (SURVEY 5 "a failed GPU is removed from the round-robin"; the reference has no counterpart, its errors
+ * are plain Go `error`s, encoder.go:183-189).  When a CUDA call of a host-batch entry point fails and the device does not
+ * answer a synchronise any more, its slot is marked failed: the blocking calls re-run that device's frame block on the
+ * remaining devices and return J2K_OK if they succeed (the event is kept in j2k_last_error), asynchronous submissions
+ * return the error, and every later call shards over the devices that are left.  1 = slot failed, 0 = in use, -1 = bad slot. */
+int j2k_device_failed(const j2k_ctx* ctx, int slot);
 /* CUDA devices visible to the process: `j2k_init(&ctx, NULL, j2k_visible_devices())` builds a context over all of them. */
 int j2k_visible_devices(void);
 /* Total number of CUDA kernels this context has launched (bench.py's gpu_launches). */

@@ -69,6 +69,10 @@ func InitDevices(devices []int) error {
 // DeviceCount reports how many GPUs the context shards batches over.
 func DeviceCount() int { return int(C.j2k_device_count(ctx)) }
 
+// DeviceFailed reports whether the GPU in `slot` was lost (a CUDA call failed and the device no longer answers) and has been
+// removed from the round-robin: blocking calls re-run its frame block on the remaining GPUs, later calls skip it.
+func DeviceFailed(slot int) bool { return C.j2k_device_failed(ctx, C.int(slot)) == 1 }
+
 // Shutdown releases the context (streams, device scratch, pinned staging).
 func Shutdown() {
 	if ctx != nil {

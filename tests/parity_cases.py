@@ -525,3 +525,32 @@ def check_one_producer_forward(ctx, oracle, w, h, bits, L, nframes, tile=(0, 0),
         if "[j2k]" in err:  # the trace is latched at first use
             x3 = [int(m) for m in re.findall(r"fwd ring .* x3=(\d)", err)]
             assert x3 and x3[0] == 1 and x3[-1] == 0, err
+
+
+def check_failed_device(oracle, monkeypatch, lib_path=None, devices=(0, 0)):
+    import j2kb200
+    import pytest
+    rng = np.random.default_rng(77)
+    w, h, n = 96, 64, 5
+    frames = np.stack([raw_bytes(synth(rng, h, w, 1, 12, False, "smooth")) for _ in range(n)])
+    fp, ip = fwd_inv_params(w, h, 1, 12, False, 3, True, oracle)
+    want = np.stack([oracle.forward(fp, frames[f]) for f in range(n)])
+    with j2kb200.Context(devices=list(devices), lib_path=lib_path) as c2:
+        assert c2.device_count == 2 and not c2.device_failed(0) and not c2.device_failed(1)
+        assert np.array_equal(c2.forward_batch(fp, frames), want)        # both slots healthy
+        monkeypatch.setenv("J2K_FAULT_DEVICE", "1")
+        got = c2.forward_batch(fp, frames)                                # slot 1 fails: its block is re-run on slot 0
+        monkeypatch.delenv("J2K_FAULT_DEVICE")
+        assert np.array_equal(got, want)
+        assert c2.device_failed(1) and not c2.device_failed(0)
+        assert "removed from the round-robin" in c2.lib.j2k_last_error(c2.h).decode()
+        assert np.array_equal(c2.inverse_batch(ip, want), frames.reshape(n, -1))   # later calls: slot 0 only
+        assert np.array_equal(c2.forward_batch(fp, frames), want)
+        monkeypatch.setenv("J2K_FAULT_DEVICE", "0")
+        with pytest.raises(j2kb200.J2KError) as e:                        # the last device goes: an error, not a hang
+            c2.forward_batch(fp, frames)
+        monkeypatch.delenv("J2K_FAULT_DEVICE")
+        assert e.value.code == abi.J2K_ERR_CUDA and c2.device_failed(0)
+        with pytest.raises(j2kb200.J2KError) as e:
+            c2.forward_batch(fp, frames)
+        assert "no usable device" in str(e.value)

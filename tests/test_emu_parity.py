@@ -206,3 +206,10 @@ def test_one_producer_rgb97_forward(ectx, oracle, w, h, bits, L, nframes, tile, 
 def test_one_producer_rgb97_forward_default_policy(ectx, oracle, capfd):
     """A launch big enough for the plan builder to pick fwd3w_kernel by itself (the emulated device has one SM = four quads)."""
     PC.check_one_producer_forward(ectx, oracle, 256, 200, 8, 2, 8, capfd=capfd, arm_on="1")
+
+
+def test_failed_device_is_removed_from_the_round_robin(oracle, monkeypatch):
+    """SURVEY 5 "a failed GPU is removed from the round-robin": a device slot whose CUDA calls fail (J2K_FAULT_DEVICE injects
+    that) is marked failed, the blocking call re-runs its frame block on the remaining slot and still returns every frame
+    bit-exact, later calls shard over what is left, and a context with no device left reports an error instead of hanging."""
+    PC.check_failed_device(oracle, monkeypatch, __import__("emu_lib").build())

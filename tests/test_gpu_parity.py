@@ -391,3 +391,8 @@ def test_one_producer_rgb97_forward(ctx, oracle, w, h, bits, L, nframes, tile, c
     """fwd3w_kernel (one converting producer warp + three single-component consumers per CTA) with real concurrency: many
     CTAs, exchange-ring wrap-around, job triples of the coarser levels waiting on the per-component counters."""
     PC.check_one_producer_forward(ctx, oracle, w, h, bits, L, nframes, tile, chunk)
+
+
+def test_failed_device_is_removed_from_the_round_robin(oracle, monkeypatch):
+    """The same on the real runtime: a context with two slots on GPU 0, slot 1 failing (fault injection), then slot 0."""
+    PC.check_failed_device(oracle, monkeypatch)
