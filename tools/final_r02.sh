@@ -29,9 +29,9 @@ cap() { # config-substring kernel-regex name
     -f -o gpurun_out/prof_${3}_$tag python tools/config_bench.py --steps 2 --only "$1" > gpurun_out/ncu_${3}_$tag.log 2>&1; echo $3 rc=$?
   summ $3 "tools/final_r02.sh $tag: ncu --set full --clock-control none --import-source on -k regex:$2, tools/config_bench.py --only '$1', launch 4"
 }
-cap "C3(i)" fwd_ring_kernel fwd_rgb97
+cap "C3(i)" fwd3w_kernel fwd_rgb97
 cap "C3(i)" inv3w_kernel inv_rgb97
-cap "C5" fwd_ring_kernel fwd_c5
+cap "C5" fwd3w_kernel fwd_c5
 cap "C5" inv3w_kernel inv_c5
 cap "C1" fwd_ring_kernel fwd_c1
 cap "C1" inv_ring_kernel inv_c1
