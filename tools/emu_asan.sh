@@ -24,6 +24,11 @@ PC.check_blocks_roi(ctx, orc, 48, 40, 3, 8, 2, True, [4, 0, 7], tile=(32, 32), c
 PC.check_blocks_roi(ctx, orc, 70, 50, 1, 12, 3, False, [9], cb=(16, 8))
 PC.check_pipelined_order(ctx, orc, 64, 32, 1, 12, 3, False, 9, 4, 3)
 PC.check_pipelined_order(ctx, orc, 48, 32, 3, 8, 2, True, 6, 4, 2)
+# fwd3w_kernel (one converting producer + three consumers per quad; the emulator's warp plays the four roles in turn)
+PC.check_one_producer_forward(ctx, orc, 512, 44, 8, 3, 2)
+PC.check_one_producer_forward(ctx, orc, 256, 64, 8, 2, 2, tile=(128, 32))
+PC.check_one_producer_forward(ctx, orc, 512, 24, 16, 3, 1)
+PC.check_one_producer_forward(ctx, orc, 320, 37, 8, 2, 1, chunk=8)
 PC.check_custom_mct(ctx, orc, 40, 24, 8, 2, True, "bindings")
 PC.check_wavelet_api(ctx, orc, 130, 70, 5, 0, 0)
 PC.check_wavelet_api(ctx, orc, 33, 17, 2, 1, 0)
