@@ -583,7 +583,9 @@ int device_sm_count() {
 }
 
 // Job decomposition of one ring segment: even column strips, row chunks sized for ~2 jobs per resident warp.
-void ring_chunks(RingSeg& g, int NP, int n_cols_total_hint, int level, int halo_lanes = 2, int target_div = 1) {
+// target_halves: job target in halves of the default (3 = 1.5 x); chunk_cap: upper bound of the chunk height (0 = the default)
+void ring_chunks(RingSeg& g, int NP, int n_cols_total_hint, int level, int halo_lanes = 2, int target_div = 1, int target_halves = 2,
+                 int chunk_cap = 0) {
     int VP = (32 - halo_lanes) * NP;  // 32 lanes minus one halo lane per side (9/7 needs 2 pairs, 5/3 one: both fit NP >= 2); halo-free: 32
     // strips are a multiple of 8 pairs wide: every band-row piece a warp stores (and every pixel-row piece of the inverse)
     // then covers whole 32-byte sectors, no partial-sector writes at the strip seams (+3 % on C2)
@@ -601,10 +603,11 @@ void ring_chunks(RingSeg& g, int NP, int n_cols_total_hint, int level, int halo_
     g.nstrips = (g.Kx + g.strip_pairs - 1) / g.strip_pairs;
     // chunks as tall as the job target allows, up to 128 row pairs: the 2 (5/3) or 4 (9/7) warm-up pairs a chunk recomputes are
     // then 1.5-3 % of its rows (6 % at 64); the difference only shows once the board is power-capped
-    const int max_chunk = level <= 1 ? env_int("J2K_RING_CHUNK", 128) : env_int("J2K_RING_CHUNK_DEEP", env_int("J2K_RING_CHUNK", 128));
+    int max_chunk = level <= 1 ? env_int("J2K_RING_CHUNK", 128) : env_int("J2K_RING_CHUNK_DEEP", env_int("J2K_RING_CHUNK", 128));
+    if (chunk_cap > 0 && chunk_cap < max_chunk) max_chunk = chunk_cap;
     // (target_div: a job of the three-producer inverse occupies a whole CTA, and every job boundary drains its exchange
     // pipeline: four times fewer, taller jobs: +11 % on C3, +2.5 % on C5)
-    const long long target = env_int("J2K_RING_TARGET_JOBS", 148 * 16 * 2) / target_div;
+    const long long target = (long long)env_int("J2K_RING_TARGET_JOBS", 148 * 16 * 2) * target_halves / 2 / target_div;
     long long cols = (long long)n_cols_total_hint * g.nstrips;
     long long want = (target + cols - 1) / cols;
     if (want < 1) want = 1;
@@ -855,7 +858,14 @@ int build_ring_fwd_impl(const Spec& s, Plan& P, const std::vector<long long>& ta
                     if (best < 0 || cost < best) { best = cost; g.chunk_pairs = cp; g.nchunks = nch; }
                 }
             }
-        } else ring_chunks(g, NP, g.n_items, l.level);
+        } else {
+            // Measured (profiles/exp_r02_chunk_policy.log): the three-components-per-lane 5/3 level 1 (RCT) runs best with
+            // chunks of at most 32 row pairs (C3(ii) x 32 frames: 0.80 -> 0.88 of the HBM peak); the coarser levels behind
+            // fwd3w_kernel, which only its twelve consumer warps per SM take, with 1.5 x the usual number of jobs
+            // (C3(i) x 32: 0.71 -> 0.74, C5: 0.64 -> 0.65).
+            const int cap = (first && WT == 53 && l.NC == 3) ? env_int("J2K_RING_CHUNK_RGB53", 32) : 0;
+            ring_chunks(g, NP, g.n_items, l.level, 2, 1, (!first && R.X3) ? env_int("J2K_FWD3W_DEEP_HALVES", 3) : 2, cap);
+        }
         g.dep_seg = -1; g.dep_div = 1; g.dep_target = 0;
         if (!first) {
             // producer: same class, previous level
@@ -1094,7 +1104,8 @@ int build_ring_inv_impl(const Spec& s, Plan& P, const std::vector<long long>& ta
             }
             g.st_cls[0] = (int)(pal & -pal);  // GetImageData plane rows (UA)
         }
-        ring_chunks(g, NP, g.n_items, l.level, (J2K_INV_HALO_FREE && WT == 53) ? 0 : 2, x3 ? env_int("J2K_INV3W_TDIV", 4) : 1);
+        ring_chunks(g, NP, g.n_items, l.level, (J2K_INV_HALO_FREE && WT == 53) ? 0 : 2, x3 ? env_int("J2K_INV3W_TDIV", 4) : 1, 2,
+                    (first && WT == 53 && l.NC == 3) ? env_int("J2K_RING_CHUNK_RGB53", 32) : 0);   // (see build_ring_fwd_impl)
         g.dep_seg = -1; g.dep_div = 1; g.dep_target = 0; g.dep_mul = 1;
         {
             // producer: same class, next coarser level (absent for the coarsest level of the class)
