@@ -621,6 +621,22 @@ void ring_chunks(RingSeg& g, int NP, int n_cols_total_hint, int level, int halo_
     g.nchunks = (g.Ky + cp - 1) / cp;
 }
 
+// Level-1 chunk height by estimated makespan: the job count should fill whole rounds of the `slots` warps that run such jobs
+// at once; cost of n chunks of cp row pairs = rounds x (cp + warm-up pairs + start-up bubble).
+void ring_chunks_makespan(RingSeg& g, long long cols, long long slots, int warm_pairs, int max_chunk) {
+    const int min_chunk = env_int("J2K_RING_CHUNK_MIN", 8), bubble = env_int("J2K_RING_BUBBLE", 8);
+    long long best = -1;
+    for (int n = 1; n <= g.Ky; n++) {
+        const int cp = (g.Ky + n - 1) / n;
+        if (cp > max_chunk) continue;
+        if (cp < min_chunk && best >= 0) break;
+        const int nch = (g.Ky + cp - 1) / cp;
+        const long long nj = cols * nch;
+        const long long cost = ((nj + slots - 1) / slots) * (cp + warm_pairs + bubble);
+        if (best < 0 || cost < best) { best = cost; g.chunk_pairs = cp; g.nchunks = nch; }
+    }
+}
+
 bool ring_variant_supported(int WT, int NP, int NC, int IN, int MCT, int SG) {
     if (NC == 3 && NP == 4) return WT == 97 && SG == 0 && (IN == IN_U8 || IN == IN_U16) && MCT == MCTK_ICT;  // component-split first level
     if (NC == 3) return NP == 2 && SG == 0 && (IN == IN_U8 || IN == IN_U16) && MCT == (WT == 53 ? MCTK_RCT : MCTK_ICT);
@@ -1106,6 +1122,15 @@ int build_ring_inv_impl(const Spec& s, Plan& P, const std::vector<long long>& ta
         }
         ring_chunks(g, NP, g.n_items, l.level, (J2K_INV_HALO_FREE && WT == 53) ? 0 : 2, x3 ? env_int("J2K_INV3W_TDIV", 4) : 1, 2,
                     (first && WT == 53 && l.NC == 3) ? env_int("J2K_RING_CHUNK_RGB53", 32) : 0);   // (see build_ring_fwd_impl)
+        // Single-component level 1 of the inverse, aligned variant: the chunk height that fills whole rounds of the resident
+        // warps (level 1 is the END of an inverse launch, nothing has to overlap behind it; measured: C1 0.818 -> 0.840,
+        // C4 0.816 -> 0.844, C2 x16 0.810 -> 0.818, C2 x32 unchanged; the forward, whose coarser levels must overlap its
+        // level 1, loses with the same rule: C1 0.765 -> 0.670 - profiles/exp_r02_chunk_policy.log)
+        if (first && l.NC == 1 && !seg_ua && env_int("J2K_RING_MAKESPAN", 1)) {
+            const int warps = WT == 53 ? 4 * J2K_INV_MINB_53 : 4 * J2K_RING_MINB;
+            ring_chunks_makespan(g, (long long)g.n_items * g.nstrips, (long long)device_sm_count() * warps, WT == 97 ? 4 : 2,
+                                 env_int("J2K_RING_CHUNK", 128));
+        }
         g.dep_seg = -1; g.dep_div = 1; g.dep_target = 0; g.dep_mul = 1;
         {
             // producer: same class, next coarser level (absent for the coarsest level of the class)
