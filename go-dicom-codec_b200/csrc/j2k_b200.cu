@@ -1043,6 +1043,13 @@ int build_ring_inv_impl(const Spec& s, Plan& P, const std::vector<long long>& ta
     bool ua = false, x3_any = false;
     int n_ctl = 2, jobs = 0;
     R.X3 = 0;
+    // (known before the loop reaches level 1: the coarser levels of such a plan are cut into HALF the usual number of jobs -
+    // measured on the final kernels, C3(i) x 32 inverse 0.602 -> 0.620, C5 0.513 -> 0.521; profiles/exp_r02_chunk_policy.log)
+    bool x3_plan = false;
+    for (int oi : order) {
+        const LevelLaunch& l1 = P.levels[oi];
+        if (l1.level == 1 && WT == 97 && l1.NC == 3 && l1.KIND == IN_U8 && l1.MCT == MCTK_ICT && env_int("J2K_INV3W", J2K_INV3W_DEFAULT) != 0) x3_plan = true;
+    }
     for (size_t si = 0; si < order.size(); si++) {
         const LevelLaunch& l = P.levels[order[si]];
         const LevelArgs& a = l.a;
@@ -1120,7 +1127,8 @@ int build_ring_inv_impl(const Spec& s, Plan& P, const std::vector<long long>& ta
             }
             g.st_cls[0] = (int)(pal & -pal);  // GetImageData plane rows (UA)
         }
-        ring_chunks(g, NP, g.n_items, l.level, (J2K_INV_HALO_FREE && WT == 53) ? 0 : 2, x3 ? env_int("J2K_INV3W_TDIV", 4) : 1, 2,
+        ring_chunks(g, NP, g.n_items, l.level, (J2K_INV_HALO_FREE && WT == 53) ? 0 : 2, x3 ? env_int("J2K_INV3W_TDIV", 4) : 1,
+                    (!first && x3_plan) ? env_int("J2K_INV3W_DEEP_HALVES", 1) : 2,
                     (first && WT == 53 && l.NC == 3) ? env_int("J2K_RING_CHUNK_RGB53", 32) : 0);   // (see build_ring_fwd_impl)
         // Single-component level 1 of the inverse, aligned variant: the chunk height that fills whole rounds of the resident
         // warps (level 1 is the END of an inverse launch, nothing has to overlap behind it; measured: C1 0.818 -> 0.840,
