@@ -855,11 +855,12 @@ int build_ring_fwd_impl(const Spec& s, Plan& P, const std::vector<long long>& ta
             // rounds x (cp + the 2 LAG warm-up pairs a chunk recomputes + the start-up bubble of a job, ~16 pairs measured).
             ring_chunks(g, NP, a.n_items, l.level, 2, env_int("J2K_FWD3W_TDIV", 4));
             const long long slots = (long long)device_sm_count() * J2K_F3_QUADS;
-            // Small launches stay on the component jobs: with fewer than ~3 full-height jobs per quad the coarser levels no longer
-            // overlap level 1 and the tail decides (8 C3 frames: 0.57 against 0.62 of the HBM peak; 32 frames: 0.71 against 0.70;
-            // 128 C5 tiles: 0.65 against 0.60).  J2K_FWD3W=2 forces the kernel (tests).
+            // Small launches stay on the component jobs: with little more than one full-height job per quad the coarser levels no
+            // longer overlap level 1 and the tail decides (C3 frames per launch, fwd3w against component jobs, with the job-size
+            // policies below: 8: 0.586 / 0.622, 12: 0.671 / 0.651, 16: 0.713 / 0.672, 24: 0.732 / 0.689, 32: 0.74 / 0.70;
+            // 128 C5 tiles: 0.655 / 0.60 - profiles/exp_r02_chunk_policy.log).  J2K_FWD3W=2 forces the kernel (tests).
             if (env_int("J2K_FWD3W", J2K_FWD3W_DEFAULT) < 2 &&
-                (long long)a.n_items * g.nstrips * g.Ky < (long long)env_int("J2K_FWD3W_MIN_PAIRS", 400) * slots) return 0;
+                (long long)a.n_items * g.nstrips * g.Ky < (long long)env_int("J2K_FWD3W_MIN_PAIRS", 160) * slots) return 0;
             if (!env_int("J2K_FWD3W_TDIV", 0)) {
                 const int max_chunk = env_int("J2K_RING_CHUNK", 128), min_chunk = env_int("J2K_RING_CHUNK_MIN", 8);
                 const int bubble = env_int("J2K_FWD3W_BUBBLE", 16);
