@@ -670,6 +670,18 @@ struct FwdRing {
         }
     }
 
+    // ... and of a strip that lies inside both bands with every storing lane (warp-uniform: all strips of a row but the last)
+    template <int SC>
+    static __device__ __forceinline__ void store_full(int* p, const int (&o)[NP]) {
+        if constexpr (SC >= 2) {
+#pragma unroll
+            for (int j = 0; j + 1 < NP; j += 2) *(int2*)(p + j) = make_int2(o[j], o[j + 1]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < NP; j++) p[j] = o[j];
+        }
+    }
+
     // The job loop is instantiated per (load alignment, store class) of the general-alignment variant and chosen once per job.
     static __device__ __forceinline__ void run(const RingSeg& S, const RawFmt& raw, int item, int chunk, int strip, RingWarp& rw,
                                                int lane, FxPort* xp = nullptr, int xcomp = 0) {
@@ -705,7 +717,9 @@ struct FwdRing {
         // the window width is a multiple of 2 NP on the aligned path: a lane stores whole vectors or nothing; UA masks per band
         const bool st = lane >= HLN && kx0 < kxe && (UA || kx0 + NP <= hw);
         const int nv_l = S.lw - kx0, nv_h = hw - kx0;   // UA: values of this lane inside the low- / high-pass bands
-        (void)nv_l; (void)nv_h;
+        // UA, warp-uniform: every storing lane of this strip holds NP values of both bands (no masks needed)
+        const bool full_w = kxs + ((kxe - kxs + NP - 1) / NP) * NP <= min(S.lw, hw);
+        (void)nv_l; (void)nv_h; (void)full_w;
 
         const unsigned long long pol_load = S.pol_load, pol_ll = S.pol_ll, pol_band = S.pol_band;
         (void)pol_load; (void)pol_ll; (void)pol_band;
@@ -966,8 +980,13 @@ struct FwdRing {
                         }
                     }
                     if constexpr (UA) {
+                        if (full_w) {
+                            if (row_l) { store_full<SC>(p_ll, q_ll); store_full<SC>(p_hl, q_hl); }
+                            if (row_h) { store_full<SC>(p_lh, q_lh); store_full<SC>(p_hh, q_hh); }
+                        } else {
                         if (row_l) { store_ua<SC>(p_ll, q_ll, nv_l); store_ua<SC>(p_hl, q_hl, nv_h); }
                         if (row_h) { store_ua<SC>(p_lh, q_lh, nv_l); store_ua<SC>(p_hh, q_hh, nv_h); }
+                        }
                     } else {
                     if (row_l) {
                         store_vec(p_ll + c * cs_ll, q_ll, pol_ll);
@@ -1039,7 +1058,7 @@ struct FwdRing {
                     if (row_l) {
 #pragma unroll
                         for (int j = 0; j < NP; j++) { q_a[j] = (int)((unsigned)lo[c][2 * j] << sh_ll); q_b[j] = (int)((unsigned)lo[c][2 * j + 1] << sh_hl); }
-                        if constexpr (UA) { store_ua<SC>(p_ll, q_a, nv_l); store_ua<SC>(p_hl, q_b, nv_h); } else {
+                        if constexpr (UA) { if (full_w) { store_full<SC>(p_ll, q_a); store_full<SC>(p_hl, q_b); } else { store_ua<SC>(p_ll, q_a, nv_l); store_ua<SC>(p_hl, q_b, nv_h); } } else {
                         store_vec(p_ll + c * cs_ll, q_a, pol_ll);
                         store_vec(p_hl + c * cs_b, q_b, pol_band);
                         }
@@ -1047,7 +1066,7 @@ struct FwdRing {
                     if (row_h) {
 #pragma unroll
                         for (int j = 0; j < NP; j++) { q_a[j] = (int)((unsigned)hi[c][2 * j] << sh_lh); q_b[j] = (int)((unsigned)hi[c][2 * j + 1] << sh_hh); }
-                        if constexpr (UA) { store_ua<SC>(p_lh, q_a, nv_l); store_ua<SC>(p_hh, q_b, nv_h); } else {
+                        if constexpr (UA) { if (full_w) { store_full<SC>(p_lh, q_a); store_full<SC>(p_hh, q_b); } else { store_ua<SC>(p_lh, q_a, nv_l); store_ua<SC>(p_hh, q_b, nv_h); } } else {
                         store_vec(p_lh + c * cs_b, q_a, pol_band);
                         store_vec(p_hh + c * cs_b, q_b, pol_band);
                         }

@@ -113,8 +113,8 @@ def test_hybrid_plans(ectx, oracle, w, h, c, bits, signed, L, rev, capfd):
     os.environ["J2K_B200_TRACE"] = "1"
     PC.check_pipeline(ectx, oracle, w, h, c, bits, signed, L, rev, seed=w + L)
     err = capfd.readouterr().err
-    if "[j2k]" in err:  # the trace is latched at first use; when it is on, both kinds of launch must appear
-        assert " ring " in err and " level " in err
+    if "[j2k]" in err:  # the trace is latched at first use; when it is on, the persistent launch must appear (since round 2 the
+        assert " ring " in err  # general-alignment variant may take every level: per-level launches behind it are optional)
 
 
 def test_package_api_x1(ectx, oracle):
