@@ -1397,6 +1397,14 @@ struct InvRing {
     // parameter of the job loop, chosen once per job.  n valid ints of q at p (planar destinations: LL planes, GetImageData)
     template <int XA>
     static __device__ __forceinline__ void store_ints_ua(int* p, const int (&q)[NS], int n) {
+        if (n >= NS) {   // every lane of a strip that does not touch the window's right edge: no masks
+#pragma unroll
+            for (int j = 0; j < NS; j += 2) {
+                if constexpr (XA >= 8) *(int2*)(p + j) = make_int2(q[j], q[(j + 1) % NS]);
+                else { p[j] = q[j]; p[j + 1] = q[(j + 1) % NS]; }
+            }
+            return;
+        }
 #pragma unroll
         for (int j = 0; j < NS; j += 2) {
             if (XA >= 8 && j + 1 < n) *(int2*)(p + j) = make_int2(q[j], q[(j + 1) % NS]);
@@ -1406,6 +1414,20 @@ struct InvRing {
     // nb valid bytes of the packed words wv at xrow (packed pixel rows; ES = bytes per sample)
     template <int XA, int NWO, int ES>
     static __device__ __forceinline__ void store_bytes_ua(unsigned char* xrow, const unsigned (&wv)[NWO], int nb) {
+        if (nb >= 4 * NWO) {   // every lane of a strip that does not touch the window's right edge: no masks
+#pragma unroll
+            for (int k = 0; k < NWO; k++) {
+                if constexpr (XA >= 4) *(unsigned*)(xrow + 4 * k) = wv[k];
+                else if constexpr (ES == 2) {
+                    *(unsigned short*)(xrow + 4 * k) = (unsigned short)(wv[k] & 0xFFFFu);
+                    *(unsigned short*)(xrow + 4 * k + 2) = (unsigned short)(wv[k] >> 16);
+                } else {
+#pragma unroll
+                    for (int b = 0; b < 4; b++) xrow[4 * k + b] = (unsigned char)((wv[k] >> (8 * b)) & 0xFFu);
+                }
+            }
+            return;
+        }
 #pragma unroll
         for (int k = 0; k < NWO; k++) {
             const int left = nb - 4 * k;  // valid bytes of this word
