@@ -12,5 +12,5 @@ summ() { f=gpurun_out/prof_${1}_$tag.ncu-rep; [ -f $f ] || { echo missing $f; re
 cap() { timeout 600 ncu --set full --clock-control none --import-source on -k regex:$2 --launch-skip 3 --launch-count 1 \
     -f -o gpurun_out/prof_${3}_$tag python tools/config_bench.py --steps 2 --only "$1" > gpurun_out/ncu_${3}_$tag.log 2>&1; echo $3 rc=$?
   summ $3 "tools/exp_r2aj.sh: ncu --set full --clock-control none --import-source on -k regex:$2, tools/config_bench.py --only '$1', launch 4"; }
-cap "C3(i)" inv3w_kernel inv_rgb97
-cap "C5" inv3w_kernel inv_c5
+cap "DX" fwd_ring_kernel fwd_dx
+cap "DX" inv_ring_kernel inv_dx
