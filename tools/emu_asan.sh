@@ -16,6 +16,10 @@ for c in [(64, 64, 1, 8, False, 3, True), (61, 47, 1, 16, True, 3, True), (64, 6
           (512, 12, 1, 16, False, 2, False), (384, 10, 1, 8, False, 2, False), (136, 12, 3, 8, False, 2, False), (128, 16, 3, 8, False, 2, False),
           (128, 16, 3, 8, False, 2, True), (128, 16, 3, 16, False, 2, False), (520, 9, 1, 16, False, 3, False), (1, 1, 1, 8, False, 2, False)]:
     PC.check_pipeline(ctx, orc, *c)
+# general-alignment ring variants (masked and unmasked store paths, every row phase)
+for c in [(140, 20, 1, 16, False, 2, False), (150, 23, 1, 12, False, 3, True), (134, 18, 1, 8, True, 2, True), (271, 13, 1, 16, False, 4, True),
+          (535, 10, 1, 16, False, 3, False), (131, 17, 1, 8, False, 3, False)]:
+    PC.check_pipeline(ctx, orc, *c)
 PC.check_pipeline(ctx, orc, 100, 70, 1, 8, False, 3, False, tile=(48, 32))
 PC.check_pipeline(ctx, orc, 70, 50, 3, 8, False, 2, False, tile=(32, 32))
 PC.check_blocks(ctx, orc, 70, 50, 1, 12, 3, False, cb=(16, 8))
