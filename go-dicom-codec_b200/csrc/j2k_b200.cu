@@ -2527,7 +2527,13 @@ int run_frames(j2k_ctx* ctx, const HostJob& J, int f0, int f1, bool wait, std::v
     }
     if (!wait) {
         for (auto& pt : parts)
-            if (pt.rc) { device_lost(ctx, pt.di); return pt.rc; }
+            if (pt.rc) {
+                // no ticket will exist for this submission: nothing of it may stay in flight on the caller's buffers
+                for (auto& q : parts)
+                    if (q.rc == 0 && !ctx->devs[q.di].failed && fault_slot() != q.di) (void)sync_dev(ctx, q.di);
+                device_lost(ctx, pt.di);
+                return pt.rc;
+            }
         return 0;
     }
     for (auto& pt : parts) {
