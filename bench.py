@@ -200,6 +200,9 @@ OTHER_CONFIGS = [
     ("C4", "C4 block: 250 of the 2000 frames 512x512 16-bit, 5/3 L5 (one GPU's share at N = 8)", 512, 512, 1, 16, False, 5, True, 250, (0, 0)),
     ("C5", "C5 block: 128 of the 1024 tiles 1024x1024 RGB 8-bit (8192x16384 image), ICT + 9/7 L7 (one GPU's share at N = 8)",
      8192, 16384, 3, 8, False, 7, False, 1, (1024, 1024)),
+    # not BASELINE configs: detector sizes whose width is not a multiple of 8 (round-1 VERDICT item 5: the general-alignment kernels)
+    ("DX", "DX x32: 2140x1760 16-bit mono, 9/7 L6 (width not a multiple of 8)", 2140, 1760, 1, 16, False, 6, False, 32, (0, 0)),
+    ("CR", "CR x32: 2022x2022 12-bit mono, 5/3 L5 (width = 6 mod 8)", 2022, 2022, 1, 12, False, 5, True, 32, (0, 0)),
 ]
 
 

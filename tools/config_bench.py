@@ -25,9 +25,7 @@ def main():
     a = ap.parse_args()
     peak, _ = bench.measured_peak()
     with j2kb200.Context(devices=[0]) as ctx:
-        extra = [("C2", "C2 x16: 4096x4096 12-bit mono, 9/7 L6", 4096, 4096, 1, 12, False, 6, False, 16, (0, 0)),
-                 ("DX", "DX x32: 2140x1760 16-bit mono, 9/7 L6 (width not a multiple of 8)", 2140, 1760, 1, 16, False, 6, False, 32, (0, 0)),
-                 ("CR", "CR x32: 2022x2022 12-bit mono, 5/3 L5 (width = 6 mod 8)", 2022, 2022, 1, 12, False, 5, True, 32, (0, 0))]
+        extra = [("C2", "C2 x16: 4096x4096 12-bit mono, 9/7 L6", 4096, 4096, 1, 12, False, 6, False, 16, (0, 0))]
         for cfg in bench.OTHER_CONFIGS + extra:
             if a.only not in cfg[0] + " " + cfg[1]:
                 continue

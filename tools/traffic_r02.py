@@ -33,7 +33,7 @@ if f:
 if i:
     out["inv_ring_dram_bytes_per_frame"] = i / 32
 out["c2_algorithmic_bytes_per_frame"] = bench.alg_bytes_per_frame()
-names = {"C1": "c1", "C3i": "rgb97", "C3ii": "rgb53", "C4": "c4", "C5": "c5"}
+names = {"C1": "c1", "C3i": "rgb97", "C3ii": "rgb53", "C4": "c4", "C5": "c5", "DX": "dx", "CR": "cr"}
 cfgs = {}
 for cfg in bench.OTHER_CONFIGS:
     key, _, w, h, c, bits, _, L, _, frames, _ = cfg
